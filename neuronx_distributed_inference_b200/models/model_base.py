@@ -1,0 +1,239 @@
+"""Device-side decoder model: embed -> layer loop (KV cache in place) -> last-token gather ->
+lm_head -> on-device sampling.
+
+Role of reference ``NeuronBaseModel`` (models/model_base.py:70-1596).  Differences by design:
+* no tracing: this is an eager ``nn.Module`` replayed through per-bucket CUDA graphs
+  (runtime/runner.py); masks are never materialised — kernels take positions / lengths;
+* one typed :class:`AttnMeta` per forward instead of 24 positional tensors;
+* KV cache updates are in place inside the attention block (no aliasing, no deferred write).
+Subclasses implement ``setup_attr_for_model`` + ``init_model`` exactly like the reference hooks
+(model_base.py:120-141).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules.attention import AttnMeta
+from ..modules.kvcache import BlockKVCacheManager, DataParallelKVCacheManager, KVCacheManager
+from ..modules.sampling import Sampler, mask_padded_logits
+from ..parallel import mappings
+from ..parallel.state import get_tensor_model_parallel_group, get_tp_group
+
+
+@dataclass
+class ModelOutput:
+    """What one forward returns (device tensors)."""
+    tokens: Optional[torch.Tensor] = None          # [B] or [B,T] sampled ids (on-device sampling)
+    logits: Optional[torch.Tensor] = None          # [B,T_out,V] (full vocab) when requested
+    hidden_states: Optional[torch.Tensor] = None   # [B,T_out,H] last hidden (EAGLE / capture)
+    captured: Optional[Dict[str, torch.Tensor]] = None
+    extras: dict = field(default_factory=dict)
+
+
+class DecoderLayer(nn.Module):
+    """Pre-norm transformer block with both norms fused into the following projection and both
+    residual adds fused into the preceding row-parallel projection."""
+
+    def __init__(self, attn: nn.Module, mlp: nn.Module, input_layernorm: nn.Module,
+                 post_attention_layernorm: nn.Module, layer_idx: int = 0, mlp_is_moe: bool = False):
+        super().__init__()
+        self.self_attn = attn
+        self.mlp = mlp
+        self.input_layernorm = input_layernorm
+        self.post_attention_layernorm = post_attention_layernorm
+        self.layer_idx = layer_idx
+        self.mlp_is_moe = mlp_is_moe
+
+    def forward(self, h: torch.Tensor, meta: AttnMeta, kv_mgr, lora=None) -> torch.Tensor:
+        n1, n2 = self.input_layernorm, self.post_attention_layernorm
+        h = self.self_attn(h, meta, kv_mgr, norm_weight=n1.weight, norm_eps=n1.variance_epsilon,
+                           norm_offset=n1.offset, residual=h, lora=lora)
+        if meta.capture is not None:
+            meta.capture[f"layers.{self.layer_idx}.attn_out"] = h
+        h = self.mlp(h, norm_weight=n2.weight, norm_eps=n2.variance_epsilon, norm_offset=n2.offset, residual=h)
+        if meta.capture is not None:
+            meta.capture[f"layers.{self.layer_idx}.out"] = h
+        return h
+
+
+class NeuronBaseModel(nn.Module):
+    """Generic causal decoder.  Subclass hooks: ``setup_attr_for_model(config)`` (set
+    ``tp_degree, hidden_size, num_attention_heads, num_key_value_heads, max_batch_size,
+    buckets``...) and ``init_model(config)`` (create ``embed_tokens, layers, norm, lm_head``)."""
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        self.config = config
+        self.neuron_config = nc = config.neuron_config
+        self.device_ = device
+        self.tp_group = get_tp_group(config)
+        self.vocab_size = getattr(config, "vocab_size", None)
+        self.padding_side = nc.padding_side
+        self.on_device_sampling = nc.on_device_sampling_config is not None
+        self.setup_attr_for_model(config)
+        self.init_model(config)
+        self.init_inference_optimization(config)
+
+    # hooks ---------------------------------------------------------------------------------
+    def setup_attr_for_model(self, config):
+        raise NotImplementedError
+
+    def init_model(self, config):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------------------------
+    def kv_heads_per_rank(self) -> int:
+        return self.layers[0].self_attn.n_kv
+
+    def kv_head_dim(self) -> int:
+        return self.layers[0].self_attn.head_dim
+
+    def init_inference_optimization(self, config):
+        nc = self.neuron_config
+        if self.on_device_sampling:
+            self.sampler = Sampler(nc, self.tp_group, vocab_shard=self.lm_head_is_sharded())
+        n_layers = len(self.layers)
+        dtype = nc.attention_dtype or nc.torch_dtype
+        if nc.is_block_kv_layout:
+            self.kv_mgr = BlockKVCacheManager(n_layers, self.kv_heads_per_rank(), self.kv_head_dim(),
+                                              nc.pa_num_blocks, nc.pa_block_size, dtype, self.device_)
+        else:
+            lines = nc.kv_cache_batch_size + nc.kv_cache_padding_size
+            kw = dict(num_layers=n_layers, num_kv_heads=self.kv_heads_per_rank(), head_dim=self.kv_head_dim(),
+                      max_len=nc.max_length if not nc.speculation_length else nc.max_length + nc.speculation_length,
+                      num_lines=lines, dtype=dtype, device=self.device_,
+                      quant_config=nc.kv_quant_config if nc.kv_cache_quant else None)
+            if nc.attention_dp_degree > 1:
+                from ..parallel.state import get_data_parallel_attention_group
+                g = get_data_parallel_attention_group()
+                self.kv_mgr = DataParallelKVCacheManager(dp_rank=g.rank, dp_size=g.size, **kw)
+            else:
+                self.kv_mgr = KVCacheManager(**kw)
+
+    def lm_head_is_sharded(self) -> bool:
+        return self.tp_group.size > 1 and not getattr(self.lm_head, "gather_output", True)
+
+    # ------------------------------------------------------------------------------------
+    def embed(self, input_ids, inputs_embeds=None, vision_embeddings=None, vision_mask=None):
+        h = inputs_embeds if inputs_embeds is not None else self.embed_tokens(input_ids)
+        if vision_embeddings is not None and vision_mask is not None:
+            h = self.encode_vision_to_input(h, vision_embeddings, vision_mask)
+        scale = getattr(self, "embed_scale", None)
+        if scale is not None:
+            h = h * torch.tensor(scale, dtype=h.dtype, device=h.device)
+        return h
+
+    def encode_vision_to_input(self, h, vision_embeddings, vision_mask):
+        """Scatter image embeddings into the token embeddings at masked positions
+        (reference model_base.py:1193-1200)."""
+        m = vision_mask.bool()
+        if m.dim() == 3:
+            m = m.squeeze(-1)
+        h = h.clone()
+        h[m] = vision_embeddings.reshape(-1, h.shape[-1])[: int(m.sum())].to(h.dtype)
+        return h
+
+    def build_meta(self, input_ids, attention_mask, position_ids, seq_ids, is_prefill, **kw) -> AttnMeta:
+        B, T = input_ids.shape[:2]
+        dev = input_ids.device
+        if seq_ids is None:
+            seq_ids = torch.arange(B, device=dev, dtype=torch.int32)
+        if position_ids is None:
+            position_ids = torch.arange(T, device=dev).unsqueeze(0).expand(B, T)
+        key_valid = None
+        has_prefix = bool(kw.get("has_prefix", False))
+        if is_prefill:
+            if attention_mask is not None and attention_mask.shape[-1] == T:
+                key_valid = attention_mask.to(torch.bool)
+                if bool(key_valid.all()) if not input_ids.is_cuda else False:
+                    key_valid = None
+            if key_valid is not None:
+                write = torch.where(key_valid, position_ids, torch.full_like(position_ids, -1))
+            else:
+                write = position_ids
+        else:
+            write = position_ids
+        meta = AttnMeta(is_prefill=is_prefill, position_ids=position_ids.to(torch.int32),
+                        write_positions=write.to(torch.int32), seq_ids=seq_ids.to(torch.int32), key_valid=key_valid,
+                        active_mask=kw.get("active_mask"), slot_mapping=kw.get("slot_mapping"),
+                        block_table=kw.get("block_table"), has_prefix=has_prefix,
+                        adapter_ids=kw.get("adapter_ids"), rotary_position_ids=kw.get("rotary_position_ids"),
+                        capture={} if kw.get("capture") else None)
+        if self.padding_side != "right" or kw.get("offset_positions"):
+            meta.offset_positions = True
+        return meta
+
+    def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, seq_ids: Optional[torch.Tensor] = None,
+                sampling_params: Optional[torch.Tensor] = None, *, is_prefill: Optional[bool] = None,
+                prev_hidden: Optional[torch.Tensor] = None, inputs_embeds=None, vision_embeddings=None,
+                vision_mask=None, rand=None, output_logits: Optional[bool] = None, output_hidden: bool = False,
+                all_positions: bool = False, **kw) -> ModelOutput:
+        nc = self.neuron_config
+        B, T = input_ids.shape[:2]
+        if is_prefill is None:
+            is_prefill = T > 1 and T != nc.speculation_length and T != nc.medusa_speculation_length
+        meta = self.build_meta(input_ids, attention_mask, position_ids, seq_ids, is_prefill, **kw)
+        h = self.embed(input_ids, inputs_embeds, vision_embeddings, vision_mask)
+        if prev_hidden is not None and hasattr(self, "fuse_prev_hidden"):
+            h = self.fuse_prev_hidden(h, prev_hidden)
+        lora = getattr(self, "lora", None)
+        for layer in self.layers:
+            h = layer(h, meta, self.kv_mgr, lora=lora) if lora is not None else layer(h, meta, self.kv_mgr)
+        # ---- last-token gather (prefill) ------------------------------------------------------
+        if is_prefill and not all_positions:
+            if meta.key_valid is not None and self.padding_side == "right":
+                last = meta.key_valid.sum(-1).clamp_min(1) - 1
+            elif self.padding_side == "right" and attention_mask is None:
+                last = torch.full((B,), T - 1, device=h.device, dtype=torch.long)
+            else:
+                last = meta.position_ids.long().argmax(-1)  # reference model_base.py:974-976
+            h_out = h[torch.arange(B, device=h.device), last.long()].unsqueeze(1)
+        else:
+            h_out = h
+        out = ModelOutput()
+        if output_hidden:
+            out.hidden_states = self.final_hidden(h_out)
+        logits = self.compute_logits(h_out)
+        want_logits = nc.output_logits if output_logits is None else output_logits
+        if self.on_device_sampling:
+            Bo, To, V = logits.shape
+            toks = self.sampler(logits.reshape(Bo * To, V),
+                                None if sampling_params is None else sampling_params.repeat_interleave(To, 0),
+                                rand)
+            out.tokens = toks.view(Bo, To) if To > 1 else toks.view(Bo)
+        if want_logits or not self.on_device_sampling:
+            out.logits = self.gather_logits(logits)
+        out.captured = meta.capture
+        return out
+
+    def final_hidden(self, h):
+        return self.norm(h)
+
+    def compute_logits(self, h) -> torch.Tensor:
+        """Final norm fused into the lm_head GEMM; returns the *local* vocab shard [B,T,V/tp]."""
+        n = self.norm
+        logits = self.lm_head(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, norm_offset=n.offset)
+        soft = getattr(self, "final_logit_softcap", None)
+        if soft:
+            logits = torch.tanh(logits.float() / soft) * soft
+        pad = getattr(self.lm_head, "pad_size", 0)
+        if pad and self.lm_head_is_sharded():
+            logits = mask_padded_logits(logits, self.tp_group.rank, self.tp_group.size, pad)
+        return logits
+
+    def gather_logits(self, logits):
+        if self.lm_head_is_sharded():
+            logits = mappings.all_gather(logits, -1, self.tp_group)
+            pad = getattr(self.lm_head, "pad_size", 0)
+            if pad:
+                logits = logits[..., : logits.shape[-1] - pad]
+        return logits.float()
+
+    def reset(self):
+        self.kv_mgr.reset()

@@ -1,0 +1,202 @@
+"""Attention layer shared by every decoder model (the role of ``NeuronAttentionBase``,
+reference modules/attention/attention_base.py:134-2488).
+
+Data flow per layer (contiguous cache; the paged cache swaps the two cache ops):
+
+    qkv   = Wqkv( rmsnorm(h) )                       one GEMV/GEMM, norm fused in the prologue
+    q     = rope_kv_append(qkv, cos, sin, cache)     q/k norm + RoPE + cache write, one kernel
+    o     = attention( q, cache[seq_ids], pos )      flash-decode (T<=16) or flash-prefill kernel
+    h    += Wo(o)  [+ all-reduce]                    GEMV -> all-reduce -> +residual, one kernel
+
+The reference computes decode attention as "prior (cache) + active (new tokens)" with a shared
+softmax and writes the cache after the layer loop (attention_base.py:1410-1461); we append first
+and attend over the cache, which is the same function of the same inputs and saves a pass.
+
+Variants carried by flags rather than subclasses: sliding window, chunked attention (Llama-4),
+learned sinks (GPT-OSS), q/k RMSNorm pre-RoPE (Qwen3) or L2 norm post-RoPE (Llama-4), clip_qkv
+(DBRX), NoPE layers, logit soft-cap, attention-DP decode, context-parallel prefill (all-gather KV),
+flash decoding (KV sequence-sharded inside a KV-replication group).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..parallel import mappings
+from ..parallel.state import (Group, get_context_parallel_group, get_context_parallel_tp_group,
+                              get_data_parallel_attention_group, get_kv_shared_group,
+                              get_tensor_model_parallel_group)
+from .gqa import GQA, GroupQueryAttention_O, GroupQueryAttention_QKV
+from .norm import L2Norm, RMSNorm
+
+
+@dataclass
+class AttnMeta:
+    """Per-forward attention metadata shared by all layers (replaces the reference's 24-positional
+    tensor ABI, model_base.py:656-718)."""
+    is_prefill: bool
+    position_ids: torch.Tensor                 # [B,T] rotary positions
+    write_positions: torch.Tensor              # [B,T] cache slots (-1 = do not write: padding)
+    seq_ids: torch.Tensor                      # [B] cache lines
+    key_valid: Optional[torch.Tensor] = None   # [B,T] prefill: 1 for real tokens (padding mask)
+    cos: Optional[torch.Tensor] = None
+    sin: Optional[torch.Tensor] = None
+    rope_cache: dict = field(default_factory=dict)   # per-rotary-module (cos, sin)
+    active_mask: Optional[torch.Tensor] = None  # [B,T,T] token-tree visibility among active tokens
+    slot_mapping: Optional[torch.Tensor] = None  # paged: [B,T]
+    block_table: Optional[torch.Tensor] = None   # paged: [B,max_blocks]
+    prefix_len: Optional[torch.Tensor] = None    # [B] cached prefix tokens (prefix caching)
+    has_prefix: bool = False
+    adapter_ids: Optional[torch.Tensor] = None   # multi-LoRA
+    rotary_position_ids: Optional[torch.Tensor] = None  # M-RoPE [3,B,T]
+    capture: Optional[dict] = None               # tensor-capture sink
+
+
+class AttentionBase(nn.Module):
+    def __init__(self, config, *, hidden_size: int, num_attention_heads: int, num_key_value_heads: int,
+                 head_dim: int, rotary_emb: Optional[nn.Module] = None, qkv_bias: bool = False, o_bias: bool = False,
+                 sliding_window: Optional[int] = None, attention_chunk_size: Optional[int] = None,
+                 qk_norm: Optional[str] = None, qk_norm_eps: float = 1e-6, clip_qkv: Optional[float] = None,
+                 learned_sinks: bool = False, softmax_scale: Optional[float] = None, rope_interleaved: bool = False,
+                 use_rope: bool = True, logit_softcap: Optional[float] = None, layer_idx: int = 0,
+                 tensor_model_parallel_group: Optional[Group] = None, sharding_strategy: Optional[GQA] = None,
+                 rms_norm_eps: float = 1e-6, device=None):
+        super().__init__()
+        nc = config.neuron_config
+        self.config, self.neuron_config = config, nc
+        self.layer_idx = layer_idx
+        self.tp_group = tensor_model_parallel_group or get_tensor_model_parallel_group()
+        dtype = nc.torch_dtype
+        self.hidden_size, self.head_dim = hidden_size, head_dim
+        self.num_attention_heads, self.num_key_value_heads = num_attention_heads, num_key_value_heads
+        sp = nc.sequence_parallel_enabled
+        self.qkv_proj = GroupQueryAttention_QKV(hidden_size, head_dim, num_attention_heads, num_key_value_heads,
+                                                self.tp_group, dtype, qkv_bias, sharding_strategy, device,
+                                                sequence_parallel_enabled=sp)
+        self.o_proj = GroupQueryAttention_O(hidden_size, head_dim, num_attention_heads, num_key_value_heads,
+                                            self.tp_group, dtype, o_bias, sharding_strategy, device,
+                                            sequence_parallel_enabled=sp, reduce_dtype=nc.rpl_reduce_dtype)
+        self.n_q, self.n_kv = self.qkv_proj.n_q, self.qkv_proj.n_kv
+        self.rotary_emb = rotary_emb
+        self.use_rope = use_rope and rotary_emb is not None
+        self.rope_interleaved = rope_interleaved
+        self.sliding_window = sliding_window
+        self.attention_chunk_size = attention_chunk_size
+        self.clip_qkv = clip_qkv
+        self.softcap = logit_softcap
+        self.scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(head_dim)
+        self.qk_norm = qk_norm  # None | "rms_pre_rope" | "l2_post_rope"
+        self.qk_norm_eps = qk_norm_eps
+        if qk_norm == "rms_pre_rope":
+            self.q_layernorm = RMSNorm(head_dim, qk_norm_eps, dtype, device=device)
+            self.k_layernorm = RMSNorm(head_dim, qk_norm_eps, dtype, device=device)
+        elif qk_norm == "l2_post_rope":
+            self.qk_l2 = L2Norm(qk_norm_eps)
+        if learned_sinks:
+            # one logit per local q head; sharded with the q heads
+            self.sinks = nn.Parameter(torch.zeros(self.n_q, dtype=torch.float32, device=device), requires_grad=False)
+            self.sinks.partition_dim = 0
+            self.sinks.tp_group = self.tp_group
+            plan = self.qkv_proj.plan
+            self.sinks.shard_fn = lambda full, rank: torch.stack(
+                [full[i] if i >= 0 else full.new_zeros(()) for i in plan.q_idx[rank]])
+        else:
+            self.sinks = None
+        self.rms_norm_eps = rms_norm_eps
+
+    # ------------------------------------------------------------------------------------
+    def _rope(self, meta: AttnMeta):
+        if not self.use_rope:
+            return None, None
+        key = id(self.rotary_emb)
+        if key not in meta.rope_cache:
+            pos = meta.rotary_position_ids if meta.rotary_position_ids is not None else meta.position_ids
+            meta.rope_cache[key] = self.rotary_emb(pos)
+        return meta.rope_cache[key]
+
+    def _simple(self) -> bool:
+        """Eligible for the fused rope+norm+append kernel."""
+        return (self.use_rope and not self.rope_interleaved and self.clip_qkv is None
+                and self.qk_norm in (None, "rms_pre_rope"))
+
+    def forward(self, hidden: torch.Tensor, meta: AttnMeta, kv_mgr, norm_weight=None, norm_eps=None,
+                norm_offset: float = 0.0, residual: Optional[torch.Tensor] = None, lora=None) -> torch.Tensor:
+        """hidden [B,T,H] -> attention block output [B,T,H] (+ residual when given).
+        ``norm_weight``: the layer's input RMSNorm, fused into the QKV projection."""
+        B, T, _ = hidden.shape
+        D, nq, nkv = self.head_dim, self.n_q, self.n_kv
+        qkv = self.qkv_proj(hidden, norm_weight, norm_eps if norm_eps is not None else self.rms_norm_eps, norm_offset)
+        if lora is not None:
+            qkv = qkv + lora("qkv_proj", ops.rmsnorm(hidden, norm_weight, norm_eps, norm_offset)
+                             if norm_weight is not None else hidden, meta.adapter_ids)
+        if self.clip_qkv is not None:
+            qkv = qkv.clamp(-self.clip_qkv, self.clip_qkv)
+        cos, sin = self._rope(meta)
+        paged = meta.slot_mapping is not None
+        k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
+        lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
+        fused = (self._simple() and not paged and qkv.is_cuda and k_cache.dtype == qkv.dtype
+                 and (not meta.is_prefill or not meta.has_prefix))
+        if fused:
+            qn = self.q_layernorm.weight if self.qk_norm == "rms_pre_rope" else None
+            kn = self.k_layernorm.weight if self.qk_norm == "rms_pre_rope" else None
+            k = v = None
+            if meta.is_prefill:
+                # prefill attention consumes the fresh k/v directly (no cache read): split here
+                q, k, v = self._split_norm_rope(qkv, B, T, cos, sin)
+                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions)
+            else:
+                q = ops.rope_kv_append(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, nq, nkv, D,
+                                       False, qn, kn, self.qk_norm_eps)
+        else:
+            q, k, v = self._split_norm_rope(qkv, B, T, cos, sin)
+            if paged:
+                kv_mgr.update(self.layer_idx, k, v, meta.slot_mapping)
+            else:
+                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions)
+        if meta.capture is not None:
+            meta.capture[f"layers.{self.layer_idx}.self_attn.q"] = q
+
+        if meta.is_prefill and not meta.has_prefix:
+            o = ops.attention_prefill(q, k, v, self.scale, True, self.sliding_window, self.attention_chunk_size,
+                                      meta.key_valid, None if self._arange_pos(meta) else meta.position_ids,
+                                      self.sinks, self.softcap)
+        elif paged:
+            if self.attention_chunk_size is not None or meta.active_mask is not None:
+                raise NotImplementedError("chunked attention / token trees with the paged cache")
+            o = ops.paged_attention_decode(q, k_cache, v_cache, meta.block_table, meta.position_ids,
+                                           self.scale, self.sliding_window, self.sinks)
+        else:
+            ks = getattr(kv_mgr, "k_scale", None)
+            vs = getattr(kv_mgr, "v_scale", None)
+            o = ops.attention_decode(q, k_cache, v_cache, lines, meta.position_ids, self.scale, self.sliding_window,
+                                     self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs)
+        o = o.reshape(B, T, nq * D)
+        out = self.o_proj(o, residual)
+        if lora is not None:
+            out = out + lora("o_proj", o, meta.adapter_ids)
+        return out
+
+    def _arange_pos(self, meta: AttnMeta) -> bool:
+        """Prefill kernels assume q position == token index (right padding).  Left padding / offset
+        starts take the masked path."""
+        return self.neuron_config.padding_side == "right" and not getattr(meta, "offset_positions", False)
+
+    def _split_norm_rope(self, qkv, B, T, cos, sin):
+        D, nq, nkv = self.head_dim, self.n_q, self.n_kv
+        q, k, v = qkv.reshape(B, T, nq + 2 * nkv, D).split([nq, nkv, nkv], dim=2)
+        if self.qk_norm == "rms_pre_rope":
+            q = self.q_layernorm(q)
+            k = self.k_layernorm(k)
+        if cos is not None:
+            q = ops.apply_rope(q, cos, sin, self.rope_interleaved)
+            k = ops.apply_rope(k, cos, sin, self.rope_interleaved)
+        if self.qk_norm == "l2_post_rope":
+            q = self.qk_l2(q)
+            k = self.qk_l2(k)
+        return q, k, v

@@ -1,0 +1,215 @@
+"""GQA head sharding + fused QKV / O projections.
+
+Behaviour of reference modules/attention/gqa.py (sharding strategies :32-100, pad/replicate
+:137-243, GroupQueryAttention_QKV :348-953, GroupQueryAttention_O :955-1129) re-expressed as an
+*index plan*: for every TP rank the plan lists which source Q heads (or -1 = zero pad) and which
+source KV heads it owns.  Sharding a weight, a bias or a per-channel quantisation scale is then
+the same row/column gather — no separate pad/replicate code paths for scales.
+"""
+from __future__ import annotations
+
+import enum
+import logging
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..parallel.layers import BaseParallelLinear, _mark
+from ..parallel.state import Group, get_tensor_model_parallel_group
+from ..parallel import mappings
+
+logger = logging.getLogger("b200infer")
+
+
+class GQA(enum.Enum):
+    CONVERT_TO_MHA = "convert-to-mha"
+    REPLICATE_TO_TP_DEGREE = "replicate-to-tp-degree"
+
+
+def determine_sharding_strategy(tp_degree: int, source_key_value_heads: int,
+                                desired_sharding_strategy: Optional[GQA] = None) -> GQA:
+    s = desired_sharding_strategy or GQA.REPLICATE_TO_TP_DEGREE
+    if s == GQA.REPLICATE_TO_TP_DEGREE and tp_degree % source_key_value_heads != 0:
+        if source_key_value_heads % tp_degree == 0:
+            return GQA.CONVERT_TO_MHA  # kv heads split evenly: the strategy is moot
+        logger.warning("TP degree (%d) and KV heads (%d) are not divisible: using CONVERT_TO_MHA",
+                       tp_degree, source_key_value_heads)
+        s = GQA.CONVERT_TO_MHA
+    return s
+
+
+def get_number_of_extra_heads(num_heads: int, tp_degree: int) -> int:
+    return (-num_heads) % tp_degree
+
+
+def get_shardable_head_counts(tp_degree: int, num_attention_heads: int, num_key_value_heads: int,
+                              sharding_strategy: GQA) -> Tuple[int, int]:
+    """Total (padded/replicated) head counts across all ranks."""
+    q = num_attention_heads + get_number_of_extra_heads(num_attention_heads, tp_degree)
+    kv = num_key_value_heads
+    if num_attention_heads == num_key_value_heads:
+        kv = q
+    elif num_key_value_heads < tp_degree or num_key_value_heads % tp_degree != 0:
+        if sharding_strategy == GQA.REPLICATE_TO_TP_DEGREE:
+            assert tp_degree % num_key_value_heads == 0
+            kv = tp_degree
+        else:
+            kv = q
+    return q, kv
+
+
+@dataclass
+class GQAPlan:
+    tp: int
+    n_q: int
+    n_kv: int
+    q_idx: List[List[int]]    # per rank: source q head ids (-1 = pad)
+    kv_idx: List[List[int]]   # per rank: source kv head ids
+
+    @property
+    def q_per_rank(self):
+        return len(self.q_idx[0])
+
+    @property
+    def kv_per_rank(self):
+        return len(self.kv_idx[0])
+
+
+def make_gqa_plan(tp: int, n_q: int, n_kv: int, strategy: Optional[GQA] = None) -> GQAPlan:
+    strategy = determine_sharding_strategy(tp, n_kv, strategy) if n_q != n_kv else GQA.CONVERT_TO_MHA
+    q_tot, kv_tot = get_shardable_head_counts(tp, n_q, n_kv, strategy)
+    qpr, kpr = q_tot // tp, kv_tot // tp
+    group = n_q // n_kv
+    if n_q == n_kv or (kv_tot == q_tot and n_q != n_kv):
+        # MHA (or converted to MHA): tail-pad q heads; kv head follows its q head
+        flat_q = list(range(n_q)) + [-1] * (q_tot - n_q)
+        q_idx = [flat_q[r * qpr:(r + 1) * qpr] for r in range(tp)]
+        kv_idx = [[(h // group if h >= 0 else 0) for h in qs] for qs in q_idx]
+        return GQAPlan(tp, n_q, n_kv, q_idx, kv_idx)
+    if kv_tot == n_kv:
+        # enough KV heads: contiguous split of KV heads and their q groups
+        assert n_q % tp == 0, "num_attention_heads must divide by tp when kv heads are not replicated"
+        kv_idx = [list(range(r * kpr, (r + 1) * kpr)) for r in range(tp)]
+        q_idx = [[k * group + j for k in ks for j in range(group)] for ks in kv_idx]
+        return GQAPlan(tp, n_q, n_kv, q_idx, kv_idx)
+    # REPLICATE_TO_TP_DEGREE: one kv head per rank, q heads of a group interleave-padded
+    rep = tp // n_kv
+    tgt_group = q_tot // n_kv
+    q_idx, kv_idx = [], []
+    for r in range(tp):
+        g, j = divmod(r, rep)
+        heads = []
+        for t in range(j * qpr, (j + 1) * qpr):
+            heads.append(g * group + t if t < group else -1)
+        q_idx.append(heads)
+        kv_idx.append([g])
+    assert tgt_group == rep * qpr
+    return GQAPlan(tp, n_q, n_kv, q_idx, kv_idx)
+
+
+def _gather_heads(t: torch.Tensor, idx: List[int], head_dim: int, dim: int) -> torch.Tensor:
+    """Pick head blocks ``idx`` (size head_dim each, -1 -> zeros) along ``dim``."""
+    shape = list(t.shape)
+    n_src = shape[dim] // head_dim
+    v = t.reshape(shape[:dim] + [n_src, head_dim] + shape[dim + 1:])
+    sel = torch.tensor([max(i, 0) for i in idx], dtype=torch.long)
+    cast = v.dtype in (torch.float8_e4m3fn, torch.float8_e5m2)
+    out = (v.view(torch.uint8) if cast else v).index_select(dim, sel).clone()
+    pad = [k for k, i in enumerate(idx) if i < 0]
+    if pad:
+        out.index_fill_(dim, torch.tensor(pad, dtype=torch.long), 0)
+    if cast:
+        out = out.view(t.dtype)
+    shape[dim] = len(idx) * head_dim
+    return out.reshape(shape)
+
+
+class GroupQueryAttention_QKV(BaseParallelLinear):
+    """Fused ``Wqkv`` column-parallel projection: local rows = [q heads | k heads | v heads] of this
+    rank.  State-dict key: ``Wqkv.weight`` holding the *unsharded* concat [q; k; v]."""
+
+    def __init__(self, hidden_size: int, head_dim: int, num_attention_heads: int, num_key_value_heads: int,
+                 tp_group: Optional[Group] = None, dtype=torch.float32, bias: bool = False,
+                 desired_sharding_strategy: Optional[GQA] = None, device=None,
+                 sequence_parallel_enabled: bool = False, sequence_dimension: int = 1):
+        super().__init__()
+        self.tensor_parallel_group = tp_group or get_tensor_model_parallel_group()
+        tp = self.tensor_parallel_group.size
+        self.hidden_size, self.head_dim = hidden_size, head_dim
+        self.plan = make_gqa_plan(tp, num_attention_heads, num_key_value_heads, desired_sharding_strategy)
+        self.n_q, self.n_kv = self.plan.q_per_rank, self.plan.kv_per_rank
+        self.sequence_parallel_enabled = sequence_parallel_enabled
+        self.sequence_dimension = sequence_dimension
+        out_local = (self.n_q + 2 * self.n_kv) * head_dim
+        self.weight = _mark(nn.Parameter(torch.empty(out_local, hidden_size, dtype=dtype, device=device),
+                                         requires_grad=False), 0, self.tensor_parallel_group)
+        self.weight.shard_fn = self._shard
+        if bias:
+            self.bias = _mark(nn.Parameter(torch.zeros(out_local, dtype=dtype, device=device), requires_grad=False),
+                              0, self.tensor_parallel_group)
+            self.bias.shard_fn = self._shard
+        else:
+            self.register_parameter("bias", None)
+
+    def _shard(self, full: torch.Tensor, rank: int) -> torch.Tensor:
+        """full: [(n_q + 2 n_kv) * D, ...] unsharded (works for weight, bias, per-channel scale)."""
+        p, D = self.plan, self.head_dim
+        if full.shape[0] == 1:  # per-tensor scale
+            return full.clone()
+        q, k, v = full.split([p.n_q * D, p.n_kv * D, p.n_kv * D], 0)
+        return torch.cat([_gather_heads(q, p.q_idx[rank], D, 0), _gather_heads(k, p.kv_idx[rank], D, 0),
+                          _gather_heads(v, p.kv_idx[rank], D, 0)], 0)
+
+    def forward(self, x, norm_weight=None, norm_eps=1e-6, norm_offset=0.0):
+        if self.sequence_parallel_enabled:
+            x = mappings.all_gather(x, self.sequence_dimension, self.tensor_parallel_group)
+        return ops.linear(x, self.weight, self.bias, norm_weight=norm_weight, norm_eps=norm_eps,
+                          norm_offset=norm_offset)
+
+
+class GroupQueryAttention_O(BaseParallelLinear):
+    """Row-parallel output projection whose input columns follow the q-head plan."""
+
+    def __init__(self, hidden_size: int, head_dim: int, num_attention_heads: int, num_key_value_heads: int,
+                 tp_group: Optional[Group] = None, dtype=torch.float32, bias: bool = False,
+                 desired_sharding_strategy: Optional[GQA] = None, device=None,
+                 sequence_parallel_enabled: bool = False, sequence_dimension: int = 1,
+                 reduce_dtype=None, out_size: Optional[int] = None):
+        super().__init__()
+        self.tensor_parallel_group = tp_group or get_tensor_model_parallel_group()
+        tp = self.tensor_parallel_group.size
+        self.plan = make_gqa_plan(tp, num_attention_heads, num_key_value_heads, desired_sharding_strategy)
+        self.head_dim = head_dim
+        self.sequence_parallel_enabled = sequence_parallel_enabled
+        self.sequence_dimension = sequence_dimension
+        self.reduce_dtype = reduce_dtype
+        out_size = out_size or hidden_size
+        self.weight = _mark(nn.Parameter(torch.empty(out_size, self.plan.q_per_rank * head_dim, dtype=dtype,
+                                                     device=device), requires_grad=False),
+                            1, self.tensor_parallel_group)
+        self.weight.shard_fn = self._shard
+        if bias:
+            self.bias = _mark(nn.Parameter(torch.zeros(out_size, dtype=dtype, device=device), requires_grad=False),
+                              None, self.tensor_parallel_group)
+        else:
+            self.register_parameter("bias", None)
+
+    def _shard(self, full: torch.Tensor, rank: int) -> torch.Tensor:
+        if full.dim() == 1 or full.shape[-1] == 1:  # per-out-channel scale / per-tensor: replicated
+            return full.clone()
+        return _gather_heads(full, self.plan.q_idx[rank], self.head_dim, 1)
+
+    def forward(self, x, residual=None):
+        g = self.tensor_parallel_group
+        if g.size == 1:
+            y = ops.linear(x, self.weight, self.bias)
+            return y if residual is None else y + residual
+        if self.sequence_parallel_enabled:
+            y = mappings.reduce_scatter(ops.linear(x, self.weight, None), self.sequence_dimension, g)
+            if self.bias is not None:
+                y = y + self.bias
+            return y if residual is None else y + residual
+        return ops.linear_allreduce(x, self.weight, self.bias, g, residual=residual, reduce_dtype=self.reduce_dtype)

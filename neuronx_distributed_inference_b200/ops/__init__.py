@@ -1,0 +1,238 @@
+"""Op dispatch: hand-written sm_100a kernels on CUDA tensors, PyTorch reference on CPU.
+
+There is exactly one accelerated backend (the in-tree ``_C`` extension built from ``csrc/``);
+there is no multi-backend layer.  A CUDA tensor with the extension missing is an error (set
+``NXDI_B200_ALLOW_TORCH_FALLBACK=1`` to run the PyTorch definitions on GPU for debugging).
+``stats`` counts kernel launches issued through this module (bench.py reports them).
+"""
+from __future__ import annotations
+
+import os
+from collections import Counter
+from typing import Optional
+
+import torch
+
+from . import reference as ref
+from ._ext import load_extension, extension_available
+
+stats = Counter()
+_ALLOW_FALLBACK = os.environ.get("NXDI_B200_ALLOW_TORCH_FALLBACK", "0") == "1"
+GEMV_MAX_TOKENS = 8      # CUDA-core weight-streaming kernel up to here
+_KERNELS_ENABLED = True
+
+
+def set_kernels_enabled(flag: bool):
+    """Debug switch: run the PyTorch definitions on CUDA tensors (accuracy triage)."""
+    global _KERNELS_ENABLED
+    _KERNELS_ENABLED = flag
+
+
+def _C():
+    return load_extension()
+
+
+def _use_cuda(x: torch.Tensor) -> bool:
+    if not x.is_cuda or not _KERNELS_ENABLED:
+        return False
+    if extension_available():
+        return True
+    if _ALLOW_FALLBACK:
+        return False
+    raise RuntimeError("CUDA tensor but the sm_100a extension is not built: run "
+                       "`python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(or set NXDI_B200_ALLOW_TORCH_FALLBACK=1)")
+
+
+_FAST_DTYPES = (torch.bfloat16,)
+
+
+# --------------------------------------------------------------------------------------------
+def rmsnorm(x, weight, eps: float, offset: float = 0.0, residual=None):
+    if _use_cuda(x) and x.dtype in _FAST_DTYPES and x.shape[-1] % 8 == 0 and weight is not None \
+            and weight.dtype == x.dtype:
+        stats["rmsnorm"] += 1
+        x2 = x.reshape(-1, x.shape[-1])
+        if residual is not None:
+            r2 = residual.reshape(-1, x.shape[-1])
+            y, r = _C().rmsnorm(x2, weight, eps, offset, r2)
+            return y.view(x.shape), r.view(x.shape)
+        y, _ = _C().rmsnorm(x2, weight, eps, offset, None)
+        return y.view(x.shape)
+    return ref.rmsnorm(x, weight, eps, offset, residual)
+
+
+_ACT_CODES = {None: 0, "silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
+
+
+def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offset: float = 0.0,
+           act: Optional[str] = None, scale=None):
+    """y = act(rmsnorm(x) @ w^T + bias).  w: [N,K] bf16, or int8/fp8 with per-channel ``scale``."""
+    if _use_cuda(x) and x.dtype in _FAST_DTYPES:
+        K = x.shape[-1]
+        T = x.numel() // K
+        N = w.shape[0]
+        wq = w.dtype in (torch.int8, torch.float8_e4m3fn)
+        ok_w = (w.dtype == x.dtype and scale is None) or (wq and scale is not None and scale.dim() == 1)
+        if ok_w and act in _ACT_CODES and K % 256 == 0 and w.is_contiguous():
+            x2 = x.reshape(T, K)
+            if T <= GEMV_MAX_TOKENS:
+                stats["gemv"] += 1
+                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale)
+                return y.view(*x.shape[:-1], y.shape[-1])
+            if not wq and N % 128 == 0 and K % 64 == 0:
+                if norm_weight is not None:
+                    x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
+                stats["gemm_tcgen05"] += 1
+                y = _C().gemm(x2.contiguous(), w, bias, _ACT_CODES[act])
+                return y.view(*x.shape[:-1], y.shape[-1])
+    return ref.linear(x, w, bias, norm_weight, norm_eps, norm_offset, act, scale)
+
+
+def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=None):
+    """Row-parallel GEMM -> all-reduce (+bias, +residual).  T <= 8 tokens on CUDA with a
+    symmetric workspace attached to the group: ONE kernel (GEMV, P2P stores of partials into every
+    peer, flag wait, reduce, residual add).  Otherwise GEMM then NCCL/gloo all-reduce."""
+    from ..parallel import mappings
+    K = x.shape[-1]
+    T = x.numel() // K
+    if (_use_cuda(x) and x.dtype in _FAST_DTYPES and group.symm is not None and T <= GEMV_MAX_TOKENS
+            and K % 256 == 0 and w.is_contiguous() and (w.dtype == x.dtype or scale is not None)
+            and reduce_dtype in (None, torch.float32)):
+        stats["gemv_allreduce"] += 1
+        y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None,
+                                      scale)
+        return y.view(*x.shape[:-1], y.shape[-1])
+    y = linear(x, w, None, scale=scale)
+    y = mappings.all_reduce(y, group, reduce_dtype=reduce_dtype)
+    if bias is not None:
+        y = y + bias
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+def apply_rope(x, cos, sin, interleaved: bool = False):
+    return ref.apply_rope(x, cos, sin, interleaved)
+
+
+def rope_kv_append(qkv, cos, sin, k_cache, v_cache, seq_ids, positions, n_q, n_kv, head_dim,
+                   interleaved: bool = False, q_norm=None, k_norm=None, norm_eps: float = 1e-6):
+    """Split fused qkv [B,T,(n_q+2n_kv)*D], optional per-head q/k RMSNorm (Qwen3), RoPE on q,k,
+    write k,v into the contiguous cache at (seq_ids[b], positions[b,t]).  Returns q [B,T,n_q,D].
+    ONE kernel on CUDA (csrc/rope_kv.cu)."""
+    B, T = positions.shape
+    D = head_dim
+    if (_use_cuda(qkv) and qkv.dtype in _FAST_DTYPES and k_cache.dtype == qkv.dtype and D % 8 == 0
+            and cos.shape[-1] * 2 == D and not interleaved):
+        stats["rope_kv_append"] += 1
+        return _C().rope_kv_append(qkv.reshape(B, T, -1), cos.contiguous(), sin.contiguous(), k_cache, v_cache,
+                                   seq_ids.to(torch.int32), positions.to(torch.int32), n_q, n_kv, D,
+                                   q_norm, k_norm, norm_eps)
+    q, k, v = qkv.reshape(B, T, n_q + 2 * n_kv, D).split([n_q, n_kv, n_kv], dim=2)
+    if q_norm is not None:
+        q = ref.rmsnorm(q, q_norm, norm_eps)
+        k = ref.rmsnorm(k, k_norm, norm_eps)
+    q = ref.apply_rope(q, cos, sin, interleaved)
+    k = ref.apply_rope(k, cos, sin, interleaved)
+    ref.kv_append(k_cache, v_cache, k, v, seq_ids, positions)
+    return q
+
+
+def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
+    if _use_cuda(k_new) and k_new.dtype in _FAST_DTYPES and k_cache.dtype == k_new.dtype:
+        stats["kv_append"] += 1
+        _C().kv_append(k_cache, v_cache, k_new.contiguous(), v_new.contiguous(), seq_ids.to(torch.int32),
+                       positions.to(torch.int32))
+        return
+    ref.kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions)
+
+
+def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None, chunk=None, sinks=None,
+                     active_mask=None, softcap=None, k_scale=None, v_scale=None):
+    D = q.shape[-1]
+    if (_use_cuda(q) and q.dtype in _FAST_DTYPES and k_cache.dtype == q.dtype and D in (64, 128)
+            and active_mask is None and chunk is None and softcap is None and q.shape[1] <= 16):
+        stats["attn_decode"] += 1
+        return _C().attention_decode(q.contiguous(), k_cache, v_cache, seq_ids.to(torch.int32),
+                                     positions.to(torch.int32), float(scale), int(window or 0), sinks)
+    return ref.attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window, chunk, sinks,
+                                active_mask, softcap, k_scale, v_scale)
+
+
+def attention_prefill(q, k, v, scale, causal: bool = True, window=None, chunk=None, key_valid=None,
+                      q_pos=None, sinks=None, softcap=None):
+    D = q.shape[-1]
+    if (_use_cuda(q) and q.dtype in _FAST_DTYPES and D in (64, 128) and causal and chunk is None
+            and key_valid is None and q_pos is None and softcap is None and q.shape[1] == k.shape[1]):
+        stats["attn_prefill"] += 1
+        return _C().attention_prefill(q.contiguous(), k.contiguous(), v.contiguous(), float(scale),
+                                      int(window or 0), sinks)
+    return ref.attention_prefill(q, k, v, scale, causal, window, chunk, key_valid, q_pos, sinks, softcap)
+
+
+def paged_kv_append(k_cache, v_cache, k_new, v_new, slot_mapping):
+    if _use_cuda(k_new) and k_new.dtype in _FAST_DTYPES and k_cache.dtype == k_new.dtype:
+        stats["paged_kv_append"] += 1
+        _C().paged_kv_append(k_cache, v_cache, k_new.contiguous(), v_new.contiguous(),
+                             slot_mapping.to(torch.int32).contiguous())
+        return
+    ref.paged_kv_append(k_cache, v_cache, k_new, v_new, slot_mapping)
+
+
+def paged_attention_decode(q, k_cache, v_cache, block_table, positions, scale, window=None, sinks=None):
+    D = q.shape[-1]
+    if (_use_cuda(q) and q.dtype in _FAST_DTYPES and k_cache.dtype == q.dtype and D in (64, 128)
+            and q.shape[1] <= 16):
+        stats["paged_attn_decode"] += 1
+        return _C().paged_attention_decode(q.contiguous(), k_cache, v_cache, block_table.to(torch.int32).contiguous(),
+                                           positions.to(torch.int32), float(scale), int(window or 0), sinks)
+    return ref.paged_attention_decode(q, k_cache, v_cache, block_table, positions, scale, window, sinks)
+
+
+def argmax(logits):
+    if _use_cuda(logits) and logits.dim() == 2 and logits.dtype in (torch.float32, torch.bfloat16):
+        stats["argmax"] += 1
+        return _C().argmax(logits.contiguous())
+    return ref.argmax(logits)
+
+
+def sample(logits, top_k, top_p, temperature, rand=None, global_topk: int = 256):
+    if _use_cuda(logits) and logits.dim() == 2 and logits.dtype in (torch.float32, torch.bfloat16) \
+            and global_topk <= 256:
+        stats["topk_sample"] += 1
+        B = logits.shape[0]
+        if rand is None:
+            rand = torch.full((B,), 0.5, device=logits.device)
+        return _C().topk_sample(logits.contiguous(), top_k.to(torch.int32), top_p.float(), temperature.float(),
+                                rand.float(), int(global_topk))
+    return ref.sample(logits, top_k, top_p, temperature, rand, global_topk)
+
+
+def moe_route(router_logits, top_k, act="softmax", normalize=True, act_over_topk=False):
+    return ref.moe_route(router_logits, top_k, act, normalize, act_over_topk)
+
+
+def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_offset=0,
+                gate_up_bias=None, down_bias=None, act_fn=None):
+    N = x.shape[0]
+    if (_use_cuda(x) and x.dtype in _FAST_DTYPES and w_gate_up.dtype == x.dtype and act == "silu_mul"
+            and act_fn is None and gate_up_bias is None and down_bias is None and N <= GEMV_MAX_TOKENS
+            and x.shape[1] % 256 == 0 and w_down.shape[1] % 256 == 0):
+        stats["moe_decode"] += 1
+        return _C().moe_decode(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(),
+                               topk_i.to(torch.int32).contiguous(), int(expert_offset))
+    return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias,
+                           act_fn)
+
+
+def rmsnorm_quant(x, weight, eps, clamp=float("inf")):
+    return ref.rmsnorm_quant(x, weight, eps, clamp)
+
+
+activation = ref.activation
+build_mask = ref.build_mask
+attention_with_mask = ref.attention_with_mask
+quantize_per_channel = ref.quantize_per_channel
+quantize_per_tensor = ref.quantize_per_tensor
+quantize_blockwise = ref.quantize_blockwise

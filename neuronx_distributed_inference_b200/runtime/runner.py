@@ -1,0 +1,270 @@
+"""Per-sub-model runner: bucket selection, padding, batch splitting, pinned H2D staging and
+CUDA-graph replay.
+
+Role of reference ``ModelWrapper`` (models/model_wrapper.py:50-1440) + ``ModelBuilder``/``NxDModel``
+routing.  What remains of it on B200:
+* a *bucket* is a CUDA-graph key ``(batch bucket, seq bucket, n_active)``; kernels read real
+  lengths from device memory so no attention masks are padded or shipped;
+* batch rows are never sorted by ``seq_ids`` (kernels index cache lines directly); short batches
+  are padded with ``seq_id=-1`` rows that write to the garbage line (reference pads by repeating row
+  0 and sorting, model_wrapper.py:520-703);
+* inputs go through pinned staging buffers with async H2D copies; outputs come back through a pinned
+  D2H buffer so a step costs one stream sync;
+* async mode (reference modules/async_execution.py): the graph itself feeds the sampled token and
+  ``position+1`` into the next step's static inputs, so steps can be enqueued back-to-back and the
+  host reads tokens one step late.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..modules import autobucketing
+from ..models.model_base import ModelOutput
+
+logger = logging.getLogger("b200infer")
+
+
+def _to_dev(t, device, dtype=None, non_blocking=True):
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != device:
+        if t.device.type == "cpu" and device.type == "cuda" and not t.is_pinned():
+            t = t.pin_memory()
+        t = t.to(device, non_blocking=non_blocking)
+    return t
+
+
+class _Graph:
+    """One captured decode step with its static I/O."""
+
+    def __init__(self):
+        self.graph = None
+        self.inputs: Dict[str, torch.Tensor] = {}
+        self.out: Optional[ModelOutput] = None
+
+
+class SubModelRunner:
+    def __init__(self, tag: str, model, config, batch_size: int, buckets: Sequence, n_active_tokens: int,
+                 is_prefill: bool, device: torch.device, forward_kwargs: Optional[dict] = None):
+        self.tag = tag
+        self.model = model
+        self.config = config
+        self.neuron_config = nc = config.neuron_config
+        self.batch_size = batch_size
+        self.buckets = list(buckets)
+        self.n_active_tokens = n_active_tokens
+        self.is_prefill = is_prefill
+        self.device = device
+        self.forward_kwargs = forward_kwargs or {}
+        self.use_graphs = (device.type == "cuda" and nc.cuda_graphs and not is_prefill)
+        self._graphs: Dict[Tuple, _Graph] = {}
+        self.pad_token_id = getattr(config, "pad_token_id", None) or nc.pad_token_id or 0
+        self.batch_buckets = sorted(set((nc.token_generation_batches or []) + [batch_size])) \
+            if (not is_prefill and nc.token_generation_batches) else [batch_size]
+        self.seq_buckets = [b[1] if isinstance(b, (list, tuple)) else b for b in self.buckets]
+        self.seq_buckets = sorted(set(self.seq_buckets))
+        self.async_feedback = bool(nc.async_mode) and not is_prefill and n_active_tokens == 1
+        self.n_launch = 0
+
+    # ------------------------------------------------------------------------------------
+    def reset(self):
+        pass
+
+    def warmup(self):
+        """One forward per bucket (captures graphs).  reference application_base.py:349-373."""
+        if self.device.type != "cuda":
+            return
+        nc = self.neuron_config
+        B = self.batch_size
+        for sb in self.seq_buckets:
+            T = min(sb, nc.max_context_length) if self.is_prefill else self.n_active_tokens
+            if self.is_prefill and (nc.is_prefix_caching or nc.is_block_kv_layout):
+                continue
+            ids = torch.zeros(B, T, dtype=torch.long)
+            if self.is_prefill:
+                pos = torch.arange(T).unsqueeze(0).expand(B, T).contiguous()
+                mask = torch.ones(B, T, dtype=torch.int32)
+            else:
+                pos = torch.full((B, 1), max(sb - T - 1, 0), dtype=torch.long) + torch.arange(T).unsqueeze(0)
+                mask = None
+            seq = torch.full((B,), -1, dtype=torch.int32)  # garbage line: do not disturb real caches
+            if nc.is_block_kv_layout:
+                continue
+            self(ids, mask, pos, seq, None, _warmup=True)
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------------------------
+    def get_target_bucket(self, length: int, strategy: str = "first_fit") -> int:
+        nc = self.neuron_config
+        if self.is_prefill:
+            i = autobucketing.select_prefill_bucket(self.seq_buckets, length, nc.allow_input_truncation)
+        else:
+            i = autobucketing.select_bucket(self.seq_buckets, length, 0, strategy, nc.allow_input_truncation)
+        return self.seq_buckets[i]
+
+    def pad_prefill(self, input_ids, attention_mask, position_ids):
+        """Right/left pad the token axis up to the bucket (reference model_wrapper.py:730-829:
+        ids <- pad_token_id, mask <- 0, positions <- 1)."""
+        nc = self.neuron_config
+        T = input_ids.shape[1]
+        tgt = self.get_target_bucket(T)
+        if T > tgt:
+            if not nc.allow_input_truncation:
+                raise ValueError(f"Inputs supplied ({T}) are longer than max_context_length bucket ({tgt})")
+            input_ids, position_ids = input_ids[:, :tgt], position_ids[:, :tgt]
+            attention_mask = attention_mask[:, :tgt] if attention_mask is not None else None
+            return input_ids, attention_mask, position_ids, tgt
+        if T == tgt:
+            return input_ids, attention_mask, position_ids, T
+        pad = tgt - T
+        left = nc.padding_side == "left"
+
+        def p(t, v):
+            filler = torch.full((t.shape[0], pad), v, dtype=t.dtype, device=t.device)
+            return torch.cat([filler, t], 1) if left else torch.cat([t, filler], 1)
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids, dtype=torch.int32)
+        return p(input_ids, self.pad_token_id), p(attention_mask, 0), p(position_ids, 1), T
+
+    # ------------------------------------------------------------------------------------
+    def __call__(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, _warmup=False, **kw):
+        B = input_ids.shape[0]
+        if B > self.batch_size:
+            # request larger than the compiled batch: run chunks sequentially (model_wrapper.py:1358-1423)
+            outs = []
+            for s in range(0, B, self.batch_size):
+                sl = slice(s, s + self.batch_size)
+                sub = {k: (v[sl] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in kw.items()}
+                outs.append(self(input_ids[sl], None if attention_mask is None else attention_mask[sl],
+                                 position_ids[sl], seq_ids[sl],
+                                 None if sampling_params is None else sampling_params[sl], **sub))
+            return _cat_outputs(outs)
+        if self.is_prefill:
+            return self._run_prefill(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **kw)
+        return self._run_decode(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **kw)
+
+    def _common_kwargs(self, kw):
+        dev = self.device
+        out = dict(self.forward_kwargs)
+        for k, v in kw.items():
+            if v is None:
+                continue
+            out[k] = _to_dev(v, dev) if torch.is_tensor(v) else v
+        return out
+
+    def _run_prefill(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, **kw):
+        dev = self.device
+        if attention_mask is not None and attention_mask.shape[-1] != input_ids.shape[-1]:
+            attention_mask = attention_mask[:, -input_ids.shape[-1]:]
+        ids, mask, pos, _ = self.pad_prefill(input_ids, attention_mask, position_ids)
+        self.n_launch += 1
+        with torch.no_grad():
+            return self.model(_to_dev(ids, dev), _to_dev(mask, dev), _to_dev(pos, dev, torch.int32),
+                              _to_dev(seq_ids, dev, torch.int32), _to_dev(sampling_params, dev, torch.float32),
+                              is_prefill=True, **self._common_kwargs(kw))
+
+    # ---- decode ------------------------------------------------------------------------------
+    def _pick_batch_bucket(self, B):
+        for b in self.batch_buckets:
+            if B <= b:
+                return b
+        return self.batch_buckets[-1]
+
+    def _run_decode(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, **kw):
+        dev = self.device
+        B, T = input_ids.shape
+        kwargs = self._common_kwargs(kw)
+        graphable = self.use_graphs and not any(torch.is_tensor(v) for v in kwargs.values())
+        if not graphable:
+            self.n_launch += 1
+            with torch.no_grad():
+                return self.model(_to_dev(input_ids, dev), None, _to_dev(position_ids, dev, torch.int32),
+                                  _to_dev(seq_ids, dev, torch.int32), _to_dev(sampling_params, dev, torch.float32),
+                                  is_prefill=False, **kwargs)
+        Bb = self._pick_batch_bucket(B)
+        if position_ids.device.type == "cpu":
+            cur = int(position_ids.max()) + 1
+        else:
+            cur = self.seq_buckets[-1] - 1  # device-resident inputs: no sync, take the largest bucket
+        sb = self.get_target_bucket(cur)
+        key = (Bb, sb, T, tuple(sorted((k, v) for k, v in kwargs.items() if not torch.is_tensor(v))))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(key, Bb, T, kwargs)
+        # stage inputs into the static buffers
+        si = g.inputs
+        si["input_ids"][:B].copy_(input_ids, non_blocking=True)
+        si["position_ids"][:B].copy_(position_ids, non_blocking=True)
+        si["seq_ids"][:B].copy_(seq_ids, non_blocking=True)
+        if B < Bb:
+            si["seq_ids"][B:].fill_(-1)
+            si["position_ids"][B:].fill_(0)
+        if sampling_params is not None:
+            si["sampling_params"][:B].copy_(sampling_params, non_blocking=True)
+        g.graph.replay()
+        self.n_launch += 1
+        o = g.out
+        return ModelOutput(tokens=None if o.tokens is None else o.tokens[:B],
+                           logits=None if o.logits is None else o.logits[:B],
+                           hidden_states=None if o.hidden_states is None else o.hidden_states[:B])
+
+    def _capture(self, key, Bb, T, kwargs) -> _Graph:
+        dev = self.device
+        g = _Graph()
+        g.inputs = dict(
+            input_ids=torch.zeros(Bb, T, dtype=torch.long, device=dev),
+            position_ids=torch.zeros(Bb, T, dtype=torch.int32, device=dev),
+            seq_ids=torch.full((Bb,), -1, dtype=torch.int32, device=dev),
+            sampling_params=torch.tensor([[1.0, 1.0, 1.0]], device=dev).repeat(Bb, 1),
+        )
+        si = g.inputs
+
+        def step():
+            out = self.model(si["input_ids"], None, si["position_ids"], si["seq_ids"], si["sampling_params"],
+                             is_prefill=False, **kwargs)
+            if self.async_feedback and out.tokens is not None:
+                si["input_ids"].copy_(out.tokens.view(Bb, 1))
+                si["position_ids"].add_(1)
+            return out
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(s):
+            for _ in range(2):  # warm up (lazy tables, workspace allocs) outside capture
+                step()
+            si["position_ids"].zero_()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph, stream=s):
+            g.out = step()
+        g.graph = graph
+        self._graphs[key] = g
+        logger.debug("captured %s graph %s", self.tag, key[:3])
+        return g
+
+    # ---- device-resident multi-step decode (async mode / benchmarks) ------------------------------
+    def replay_steps(self, key_graph: _Graph, n: int):
+        for _ in range(n):
+            key_graph.graph.replay()
+        self.n_launch += n
+
+    def graph_for(self, B: int, T: int = 1, cur_len: Optional[int] = None, **kwargs) -> _Graph:
+        Bb = self._pick_batch_bucket(B)
+        sb = self.get_target_bucket(cur_len if cur_len is not None else self.seq_buckets[-1] - 1)
+        key = (Bb, sb, T, tuple(sorted(kwargs.items())))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(key, Bb, T, kwargs)
+        return g
+
+
+def _cat_outputs(outs: List[ModelOutput]) -> ModelOutput:
+    def cat(name):
+        vals = [getattr(o, name) for o in outs]
+        return None if vals[0] is None else torch.cat(vals, 0)
+    return ModelOutput(tokens=cat("tokens"), logits=cat("logits"), hidden_states=cat("hidden_states"))
