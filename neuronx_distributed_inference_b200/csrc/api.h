@@ -1,0 +1,81 @@
+// Raw-pointer launcher API between the CUDA translation units (compiled by nvcc, no torch headers) and
+// bindings.cpp (compiled by the host compiler against torch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nxdi {
+
+constexpr int SYMM_MAX_RANKS = 8;
+constexpr int SYMM_MAX_TILES = 1024;
+constexpr int GEMV_MAX_T = 8;
+
+struct SymmArgs {
+  float* recv[SYMM_MAX_RANKS];      // peer-mapped receive buffers  [2][tp][8][n_max] fp32
+  uint32_t* flags[SYMM_MAX_RANKS];  // peer-mapped flags            [2][tp][SYMM_MAX_TILES]
+  int rank, world, parity, n_max;
+};
+
+struct GemvParams {
+  const void* x;         // [T, K] bf16
+  const void* w;         // [N, K] bf16 (or int8 / fp8 with `scale`)
+  const void* bias;      // [N] bf16 or null
+  const void* norm_w;    // [K] bf16 or null (fused RMSNorm of x)
+  const void* residual;  // [T, N] bf16 or null
+  const float* scale;    // [N] fp32 per-output-channel dequant scale or null
+  void* y;               // [T, N_out] bf16
+  int T, N, K, ldx, ldy;
+  float eps, norm_offset;
+  int act;        // 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up
+  int x_in_smem;  // 0: read (already normalised) x through L1 from global
+  int wdtype;     // 0 bf16, 1 int8, 2 fp8 e4m3
+  SymmArgs symm;
+};
+
+size_t gemv_smem_bytes(int T, int K, bool x_in_smem);
+void gemv_launch(const GemvParams& p, int mode, cudaStream_t stream);  // mode 0 plain, 1 fused all-reduce
+void rmsnorm_launch(const void* x, const void* res_in, const void* w, void* y, void* res_out, int rows, int H, float eps,
+                    float offset, cudaStream_t stream);
+
+void rope_kv_append_launch(const void* qkv, const float* cos, const float* sin, void* q_out, void* k_cache, void* v_cache,
+                           const int* lines, const int* positions, const void* q_norm, const void* k_norm, float eps, int B,
+                           int T, int nq, int nkv, int D, int L, int S, cudaStream_t stream);
+void kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* lines,
+                      const int* positions, int B, int T, int H, int row_bytes, int L, int S, cudaStream_t stream);
+void paged_kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* slots, int ntok,
+                            int tok_bytes, int n_slots, cudaStream_t stream);
+
+void argmax_launch(const void* logits, int dtype /*0 f32, 1 bf16*/, int64_t* out, float* ws_val, int* ws_idx,
+                   unsigned* tickets, int B, int V, int ld, int nsplit, cudaStream_t stream);
+void topk_sample_launch(const void* logits, int dtype, const int* top_k, const float* top_p, const float* temperature,
+                        const float* rand, int64_t* out, int B, int V, int ld, int K, cudaStream_t stream);
+
+struct AttnDecodeParams {
+  const void* q;        // [B, T, Hq, D] bf16
+  const void* k_cache;  // contiguous [L, Hkv, S, D] or paged [nblk, bs, Hkv, D]
+  const void* v_cache;
+  void* out;            // [B, T, Hq, D] bf16
+  const int* lines;     // [B] cache line per row (contiguous) or null
+  const int* positions;  // [B, T] absolute position of each active token (attends to keys <= position)
+  const int* block_table;  // paged: [B, max_blocks] or null
+  const float* sinks;      // [Hq] or null
+  float* ws_o;             // split-KV workspace: [B*Hkv, nsplit, R, D] fp32
+  float* ws_ml;            // [B*Hkv, nsplit, R, 2]
+  unsigned* tickets;       // [B*Hkv]
+  int B, T, Hq, Hkv, D, S, L, nsplit, window, block_size, max_blocks;
+  float scale;
+};
+void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream);
+
+struct AttnPrefillParams {
+  const void* q;  // [B, T, Hq, D]
+  const void* k;  // [B, T, Hkv, D]
+  const void* v;
+  void* out;      // [B, T, Hq, D]
+  const float* sinks;
+  int B, T, Hq, Hkv, D, window;
+  float scale;
+};
+void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream);
+
+}  // namespace nxdi

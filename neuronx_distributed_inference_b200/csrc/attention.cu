@@ -1,0 +1,420 @@
+// Flash attention for the KV-cache engine: one warp-MMA kernel template serving
+//   * decode / speculation over the contiguous cache  [L, Hkv, S, D]   (split-KV, in-kernel combine)
+//   * decode over the paged cache                     [nblk, bs, Hkv, D] + block table
+//   * causal prefill over fresh K/V                   [B, T, Hkv, D]
+// reference kernels: K1 attention_cte (prefill; causal / sliding window / sink), K2 attention_block_tkg
+// (decode attention stage), K13 sliding-window flash_fwd (modules/sliding_window/attention.py:235-477).
+//
+// A CTA = 4 warps works on up to 64 "rows" that share one KV head:
+//   decode : rows = (active token t, q head g of the GQA group)   -> K/V read ONCE per group
+//   prefill: rows = 64 consecutive tokens of one q head
+// Row blocks of 16 map to warps (RBp in {1,2,4}); the remaining factor KS = 4/RBp splits the 64 keys of each
+// K/V tile between warps, so a 4-row decode step still uses all four warps.  K/V tiles stream through a
+// 2-stage cp.async pipeline into XOR-swizzled shared memory; QK^T and PV run on mma.sync m16n8k16 (bf16, fp32
+// accumulate) with ldmatrix operand loads; softmax is online in the exp2 domain.  Split-KV partials go to a
+// workspace and the last CTA of a (batch, kv-head) — elected by an atomic ticket — combines them, so decode
+// attention is ONE launch regardless of context length.
+#include <cfloat>
+
+#include "api.h"
+#include "common.cuh"
+
+namespace nxdi {
+
+enum { ATTN_DECODE = 0, ATTN_PAGED = 1, ATTN_PREFILL = 2 };
+constexpr int ATT_TILE = 64;
+constexpr int ATT_THREADS = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnArgs {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* out;
+  const int* lines;
+  const int* positions;
+  const int* block_table;
+  const float* sinks;
+  float* ws_o;
+  float* ws_ml;
+  unsigned* tickets;
+  int B, T, Hq, Hkv, S, L, nsplit, window, block_size, max_blocks;
+  float scale_log2;
+};
+
+template <int D>
+__device__ __forceinline__ int swz(int row, int chunk) {  // element offset of a 16-byte chunk in a [rows][D] bf16 tile
+  return row * D + ((chunk ^ (row & 7)) << 3);
+}
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p) {
+  constexpr int CH = D / 8;  // 16-byte chunks per row
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [64][D]
+  __nv_bfloat16* sK = sQ + 64 * D;                                 // [2][64][D]
+  __nv_bfloat16* sV = sK + 2 * 64 * D;                             // [2][64][D]
+  __shared__ float sM[4][16], sL[4][16];
+  __shared__ int s_pos[64];
+  __shared__ bool s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int G = p.Hq / p.Hkv;
+
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- work decomposition ----------------------------------------------------------------------------
+  int b, kvh, split = 0, R, qh0 = 0, tok0 = 0;
+  if (MODE == ATTN_PREFILL) {
+    const int n_qt = (p.T + 63) / 64;
+    const int qt = n_qt - 1 - (int)(blockIdx.x % n_qt);  // heavy (late) tiles first
+    const int bh = blockIdx.x / n_qt;
+    b = bh / p.Hq;
+    qh0 = bh % p.Hq;
+    kvh = qh0 / G;
+    tok0 = qt * 64;
+    R = min(64, p.T - tok0);
+  } else {
+    b = blockIdx.x / p.Hkv;
+    kvh = blockIdx.x % p.Hkv;
+    split = blockIdx.y;
+    R = p.T * G;
+  }
+  const int RB = (R + 15) >> 4;
+  const int RBp = RB <= 1 ? 1 : (RB <= 2 ? 2 : 4);
+  const int KS = 4 / RBp;
+  const int rb = warp % RBp, ks = warp / RBp;
+  const bool warp_active = rb < RB;
+
+  // per-row absolute positions (key j visible iff j <= pos and j > pos - window)
+  int pos_max = -1, pos_min = 0x7fffffff;
+  for (int r = tid; r < 64; r += ATT_THREADS) {
+    int ps = -1;
+    if (r < R) ps = (MODE == ATTN_PREFILL) ? tok0 + r : p.positions[b * p.T + r / G];
+    s_pos[r] = ps;
+  }
+  __syncthreads();
+  for (int r = 0; r < R; ++r) {
+    pos_max = max(pos_max, s_pos[r]);
+    pos_min = min(pos_min, s_pos[r]);
+  }
+  const int cap = (MODE == ATTN_PREFILL) ? p.T : (MODE == ATTN_PAGED ? p.max_blocks * p.block_size : p.S);
+  const int kv_len = min(pos_max + 1, cap);
+  int line = 0;
+  bool seq_ok = true;
+  if (MODE == ATTN_DECODE) {
+    line = p.lines[b];
+    seq_ok = line >= 0 && line < p.L;
+  }
+  const int nt = seq_ok ? (kv_len + ATT_TILE - 1) / ATT_TILE : 0;
+  int t_lo = 0;
+  if (p.window > 0) t_lo = max(0, pos_min - p.window + 1) / ATT_TILE;
+  const int span = max(nt - t_lo, 0);
+  const int tps = (span + p.nsplit - 1) / p.nsplit;
+  const int t_beg = t_lo + split * tps;
+  const int t_end = min(nt, t_beg + tps);
+
+  // ---- Q tile -> shared (swizzled), then A fragments ----------------------------------------------------
+  for (int i = tid; i < 64 * CH; i += ATT_THREADS) {
+    const int r = i / CH, c = i % CH;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < R) {
+      const __nv_bfloat16* src;
+      if (MODE == ATTN_PREFILL)
+        src = p.q + (((size_t)b * p.T + tok0 + r) * p.Hq + qh0) * D;
+      else
+        src = p.q + (((size_t)b * p.T + r / G) * p.Hq + kvh * G + r % G) * D;
+      val = *reinterpret_cast<const uint4*>(src + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sQ + swz<D>(r, c)) = val;
+  }
+
+  auto load_tile = [&](int tile, int buf) {
+    __nv_bfloat16* dK = sK + buf * 64 * D;
+    __nv_bfloat16* dV = sV + buf * 64 * D;
+    for (int i = tid; i < 64 * CH; i += ATT_THREADS) {
+      const int r = i / CH, c = i % CH;
+      const int key = tile * ATT_TILE + r;
+      const bool ok = key < kv_len;
+      const int kk = ok ? key : 0;
+      size_t off;
+      if (MODE == ATTN_DECODE) {
+        off = (((size_t)line * p.Hkv + kvh) * p.S + kk) * D;
+      } else if (MODE == ATTN_PAGED) {
+        const int blk = p.block_table[(size_t)b * p.max_blocks + kk / p.block_size];
+        off = (((size_t)max(blk, 0) * p.block_size + kk % p.block_size) * p.Hkv + kvh) * D;
+      } else {
+        off = (((size_t)b * p.T + kk) * p.Hkv + kvh) * D;
+      }
+      cp_async16(dK + swz<D>(r, c), p.k + off + c * 8, ok);
+      cp_async16(dV + swz<D>(r, c), p.v + off + c * 8, ok);
+    }
+  };
+
+  if (t_beg < t_end) load_tile(t_beg, 0);
+  cp_async_commit();
+  __syncthreads();  // sQ visible
+
+  uint32_t qf[D / 16][4];
+  if (warp_active) {
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      const int row = rb * 16 + (lane & 15);
+      const int chunk = kk * 2 + (lane >> 4);
+      ldmatrix_x4(qf[kk], sQ + swz<D>(row, chunk));
+    }
+  }
+  const int pos_a = s_pos[min(rb * 16 + g, 63)], pos_b = s_pos[min(rb * 16 + g + 8, 63)];
+  int rb_pos_max = -1;  // newest position any row of my block can see (causal skip of whole sub-tiles)
+  for (int i = 0; i < 16; ++i) rb_pos_max = max(rb_pos_max, s_pos[min(rb * 16 + i, 63)]);
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+
+  for (int tile = t_beg; tile < t_end; ++tile) {
+    const int buf = (tile - t_beg) & 1;
+    if (tile + 1 < t_end) {
+      load_tile(tile + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (warp_active) {
+      const __nv_bfloat16* tK = sK + buf * 64 * D;
+      const __nv_bfloat16* tV = sV + buf * 64 * D;
+      for (int j = 0; j < RBp; ++j) {
+        const int st = ks * RBp + j;  // 16-key sub-tile inside the 64-key tile
+        const int key0 = tile * ATT_TILE + st * 16;
+        if (key0 >= kv_len || key0 > rb_pos_max) break;  // nothing visible to this row block from here on
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t kf[4];
+          const int row = st * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int chunk = kk * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4(kf, tK + swz<D>(row, chunk));
+          const uint32_t b0[2] = {kf[0], kf[1]}, b1[2] = {kf[2], kf[3]};
+          mma_bf16_16816(s0, qf[kk], b0);
+          mma_bf16_16816(s1, qf[kk], b1);
+        }
+        // s0: keys key0 + 2*t4 + {0,1}; s1: keys key0 + 8 + 2*t4 + {0,1}; regs [0,1] row g, [2,3] row g+8
+        float sc[8] = {s0[0], s0[1], s1[0], s1[1], s0[2], s0[3], s1[2], s1[3]};
+        const int kidx[4] = {key0 + 2 * t4, key0 + 2 * t4 + 1, key0 + 8 + 2 * t4, key0 + 9 + 2 * t4};
+        float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kj = kidx[e];
+          const bool va = kj <= pos_a && kj < kv_len && (p.window <= 0 || kj > pos_a - p.window);
+          const bool vb = kj <= pos_b && kj < kv_len && (p.window <= 0 || kj > pos_b - p.window);
+          sc[e] = va ? sc[e] * p.scale_log2 : -INFINITY;
+          sc[4 + e] = vb ? sc[4 + e] * p.scale_log2 : -INFINITY;
+          mx_a = fmaxf(mx_a, sc[e]);
+          mx_b = fmaxf(mx_b, sc[4 + e]);
+        }
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+        const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+        const float ca = (mn_a == -INFINITY) ? 1.f : exp2f(m_a - mn_a);
+        const float cb = (mn_b == -INFINITY) ? 1.f : exp2f(m_b - mn_b);
+        const float ba = (mn_a == -INFINITY) ? 0.f : mn_a, bb = (mn_b == -INFINITY) ? 0.f : mn_b;
+        float pa[4], pb[4], sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pa[e] = exp2f(sc[e] - ba);
+          pb[e] = exp2f(sc[4 + e] - bb);
+          sa += pa[e];
+          sb += pb[e];
+        }
+        l_a = l_a * ca + sa;
+        l_b = l_b * cb + sb;
+        m_a = mn_a;
+        m_b = mn_b;
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+          o[i][0] *= ca;
+          o[i][1] *= ca;
+          o[i][2] *= cb;
+          o[i][3] *= cb;
+        }
+        const uint32_t pf[4] = {pack_bf16(pa[0], pa[1]), pack_bf16(pb[0], pb[1]), pack_bf16(pa[2], pa[3]),
+                                pack_bf16(pb[2], pb[3])};
+#pragma unroll
+        for (int dd = 0; dd < D / 16; ++dd) {
+          uint32_t vf[4];
+          const int row = st * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+          const int chunk = dd * 2 + (lane >> 4);
+          ldmatrix_x4_trans(vf, tV + swz<D>(row, chunk));
+          const uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
+          mma_bf16_16816(o[dd * 2], pf, b0);
+          mma_bf16_16816(o[dd * 2 + 1], pf, b1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- merge the KS key-split warps of each row block (through shared memory, reusing the K buffers) ----
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+  float* sO = reinterpret_cast<float*>(sK);  // [4 warps][16][D] fp32 = 4*16*D*4 bytes <= size of sK+sV
+  if (t4 == 0) {
+    sM[warp][g] = m_a;
+    sM[warp][g + 8] = m_b;
+    sL[warp][g] = l_a;
+    sL[warp][g + 8] = l_b;
+  }
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    float* base = sO + (size_t)warp * 16 * D;
+    *reinterpret_cast<float2*>(base + g * D + i * 8 + 2 * t4) = make_float2(o[i][0], o[i][1]);
+    *reinterpret_cast<float2*>(base + (g + 8) * D + i * 8 + 2 * t4) = make_float2(o[i][2], o[i][3]);
+  }
+  __syncthreads();
+
+  const int bh = (MODE == ATTN_PREFILL) ? 0 : blockIdx.x;
+  const bool direct = (MODE == ATTN_PREFILL) || p.nsplit == 1;
+  for (int e = tid; e < RB * 16 * D; e += ATT_THREADS) {
+    const int r = e / D, d = e % D;
+    if (r >= R) continue;
+    const int rbi = r >> 4, i = r & 15;
+    float M = -INFINITY;
+    for (int k2 = 0; k2 < KS; ++k2) M = fmaxf(M, sM[rbi + RBp * k2][i]);
+    float Lsum = 0.f, acc = 0.f;
+    if (M != -INFINITY) {
+      for (int k2 = 0; k2 < KS; ++k2) {
+        const int w = rbi + RBp * k2;
+        const float f = exp2f(sM[w][i] - M);
+        Lsum += sL[w][i] * f;
+        acc += sO[((size_t)w * 16 + i) * D + d] * f;
+      }
+    }
+    if (direct) {
+      int qh, tok;
+      if (MODE == ATTN_PREFILL) {
+        qh = qh0;
+        tok = tok0 + r;
+      } else {
+        qh = kvh * G + r % G;
+        tok = r / G;
+      }
+      float Lf = Lsum;
+      if (p.sinks != nullptr) {
+        const float sk = p.sinks[qh] * kLog2e;
+        if (M == -INFINITY) {
+          Lf = 1.f;
+        } else {
+          Lf += exp2f(sk - M);
+        }
+      }
+      const float val = (M == -INFINITY || Lf == 0.f) ? 0.f : acc / Lf;
+      p.out[(((size_t)b * p.T + tok) * p.Hq + qh) * D + d] = __float2bfloat16(val);
+    } else {
+      const size_t wrow = ((size_t)bh * p.nsplit + split) * 64 + r;
+      p.ws_o[wrow * D + d] = acc;
+      if (d == 0) {
+        p.ws_ml[wrow * 2] = M;
+        p.ws_ml[wrow * 2 + 1] = Lsum;
+      }
+    }
+  }
+  if (direct) return;
+
+  // ---- split-KV combine by the last-arriving CTA of this (batch, kv head) ------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&p.tickets[bh], 1u) == (unsigned)(p.nsplit - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int e = tid; e < R * D; e += ATT_THREADS) {
+    const int r = e / D, d = e % D;
+    float M = -INFINITY;
+    for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(p.ws_ml + (((size_t)bh * p.nsplit + s) * 64 + r) * 2));
+    float Lsum = 0.f, acc = 0.f;
+    if (M != -INFINITY) {
+      for (int s = 0; s < p.nsplit; ++s) {
+        const size_t wrow = ((size_t)bh * p.nsplit + s) * 64 + r;
+        const float ms = __ldcg(p.ws_ml + wrow * 2);
+        if (ms == -INFINITY) continue;
+        const float f = exp2f(ms - M);
+        Lsum += __ldcg(p.ws_ml + wrow * 2 + 1) * f;
+        acc += __ldcg(p.ws_o + wrow * D + d) * f;
+      }
+    }
+    const int qh = kvh * G + r % G, tok = r / G;
+    if (p.sinks != nullptr) {
+      const float sk = p.sinks[qh] * kLog2e;
+      if (M == -INFINITY) Lsum = 1.f; else Lsum += exp2f(sk - M);
+    }
+    const float val = (M == -INFINITY || Lsum == 0.f) ? 0.f : acc / Lsum;
+    p.out[(((size_t)b * p.T + tok) * p.Hq + qh) * D + d] = __float2bfloat16(val);
+  }
+  if (tid == 0) p.tickets[bh] = 0;  // re-arm for the next launch / graph replay
+}
+
+template <int D, int MODE>
+static void launch_attn(const AttnArgs& a, dim3 grid, cudaStream_t stream) {
+  auto kern = attention_kernel<D, MODE>;
+  const size_t smem = (size_t)(64 * D + 4 * 64 * D) * sizeof(__nv_bfloat16);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  launch_pdl(kern, grid, dim3(ATT_THREADS), smem, stream, a);
+}
+
+void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream) {
+  AttnArgs a{};
+  a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  a.k = reinterpret_cast<const __nv_bfloat16*>(p.k_cache);
+  a.v = reinterpret_cast<const __nv_bfloat16*>(p.v_cache);
+  a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  a.lines = p.lines;
+  a.positions = p.positions;
+  a.block_table = p.block_table;
+  a.sinks = p.sinks;
+  a.ws_o = p.ws_o;
+  a.ws_ml = p.ws_ml;
+  a.tickets = p.tickets;
+  a.B = p.B; a.T = p.T; a.Hq = p.Hq; a.Hkv = p.Hkv; a.S = p.S; a.L = p.L; a.nsplit = p.nsplit; a.window = p.window;
+  a.block_size = p.block_size; a.max_blocks = p.max_blocks;
+  a.scale_log2 = p.scale * kLog2e;
+  if (p.T * (p.Hq / p.Hkv) > 64) throw std::runtime_error("attention_decode: T * group size must be <= 64");
+  dim3 grid(p.B * p.Hkv, p.nsplit);
+  const bool paged = p.block_table != nullptr;
+  if (p.D == 128) {
+    if (paged) launch_attn<128, ATTN_PAGED>(a, grid, stream); else launch_attn<128, ATTN_DECODE>(a, grid, stream);
+  } else if (p.D == 64) {
+    if (paged) launch_attn<64, ATTN_PAGED>(a, grid, stream); else launch_attn<64, ATTN_DECODE>(a, grid, stream);
+  } else {
+    throw std::runtime_error("attention_decode: head_dim must be 64 or 128");
+  }
+}
+
+void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream) {
+  AttnArgs a{};
+  a.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  a.k = reinterpret_cast<const __nv_bfloat16*>(p.k);
+  a.v = reinterpret_cast<const __nv_bfloat16*>(p.v);
+  a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  a.sinks = p.sinks;
+  a.B = p.B; a.T = p.T; a.Hq = p.Hq; a.Hkv = p.Hkv; a.nsplit = 1; a.window = p.window;
+  a.scale_log2 = p.scale * kLog2e;
+  dim3 grid(p.B * p.Hq * ((p.T + 63) / 64));
+  if (p.D == 128) launch_attn<128, ATTN_PREFILL>(a, grid, stream);
+  else if (p.D == 64) launch_attn<64, ATTN_PREFILL>(a, grid, stream);
+  else throw std::runtime_error("attention_prefill: head_dim must be 64 or 128");
+}
+
+}  // namespace nxdi

@@ -1,0 +1,338 @@
+// pybind11 surface of the sm_100a extension (neuronx_distributed_inference_b200._C).  Compiled by the host
+// compiler; the CUDA translation units expose raw-pointer launchers (api.h).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+
+#include <map>
+
+#include "api.h"
+
+namespace nxdi {
+
+#define NXDI_CUDA_OK(call)                                                        \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    TORCH_CHECK(e__ == cudaSuccess, #call, " failed: ", cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
+static inline const void* optr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+static inline bool is_bf16(const at::Tensor& t) { return t.scalar_type() == at::kBFloat16; }
+
+// ---- rmsnorm ------------------------------------------------------------------------------------------
+std::tuple<at::Tensor, at::Tensor> rmsnorm(const at::Tensor& x, const at::Tensor& w, double eps, double offset,
+                                           const c10::optional<at::Tensor>& residual) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && is_bf16(x) && x.is_contiguous() && is_bf16(w));
+  const int rows = x.size(0), H = x.size(1);
+  TORCH_CHECK(H % 8 == 0 && H <= 16384, "rmsnorm: hidden must be a multiple of 8 and <= 16384");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty_like(x);
+  at::Tensor res_out;
+  if (residual.has_value()) {
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == x.sizes() && is_bf16(*residual));
+    res_out = at::empty_like(x);
+  }
+  rmsnorm_launch(x.data_ptr(), optr(residual), w.data_ptr(), y.data_ptr(), res_out.defined() ? res_out.data_ptr() : nullptr,
+                 rows, H, (float)eps, (float)offset, cur_stream());
+  return {y, res_out.defined() ? res_out : y};
+}
+
+// ---- skinny GEMM ----------------------------------------------------------------------------------------
+static void fill_params(GemvParams& p, const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
+                        const c10::optional<at::Tensor>& norm_w, double eps, double offset, int act,
+                        const c10::optional<at::Tensor>& residual, const c10::optional<at::Tensor>& scale, at::Tensor& y,
+                        bool x_in_smem) {
+  p.x = x.data_ptr();
+  p.w = w.data_ptr();
+  p.bias = optr(bias);
+  p.norm_w = x_in_smem ? optr(norm_w) : nullptr;
+  p.residual = optr(residual);
+  p.scale = scale.has_value() ? scale->data_ptr<float>() : nullptr;
+  p.y = y.data_ptr();
+  p.T = x.size(0);
+  p.K = x.size(1);
+  p.N = w.size(0);
+  p.ldx = x.stride(0);
+  p.ldy = y.stride(0);
+  p.eps = (float)eps;
+  p.norm_offset = (float)offset;
+  p.act = act;
+  p.x_in_smem = x_in_smem ? 1 : 0;
+  p.wdtype = w.scalar_type() == at::kBFloat16 ? 0 : (w.scalar_type() == at::kChar ? 1 : 2);
+}
+
+static at::Tensor prenorm_if_needed(const at::Tensor& x, const c10::optional<at::Tensor>& norm_w, double eps, double offset,
+                                    bool& x_in_smem) {
+  x_in_smem = gemv_smem_bytes(x.size(0), x.size(1), true) <= 220 * 1024;
+  if (!x_in_smem && norm_w.has_value()) return std::get<0>(rmsnorm(x.contiguous(), *norm_w, eps, offset, c10::nullopt));
+  return x;
+}
+
+static void check_gemv_inputs(const at::Tensor& x, const at::Tensor& w) {
+  TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1));
+  TORCH_CHECK(is_bf16(x) && is_bf16(w), "gemv: bf16 activations and weights");
+  TORCH_CHECK(x.size(0) >= 1 && x.size(0) <= GEMV_MAX_T, "gemv: 1..8 tokens");
+  TORCH_CHECK(x.size(1) % 256 == 0 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && w.is_contiguous());
+}
+
+at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
+                const c10::optional<at::Tensor>& norm_w, double eps, double offset, int64_t act,
+                const c10::optional<at::Tensor>& scale) {
+  check_gemv_inputs(x, w);
+  TORCH_CHECK(!scale.has_value(), "gemv: quantised weights are not wired yet");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int N = w.size(0);
+  const bool glu = act != 0;
+  if (glu) TORCH_CHECK(N % 2 == 0);
+  bool x_in_smem;
+  at::Tensor xn = prenorm_if_needed(x, norm_w, eps, offset, x_in_smem);
+  auto y = at::empty({x.size(0), glu ? N / 2 : N}, x.options());
+  GemvParams p{};
+  fill_params(p, xn, w, bias, norm_w, eps, offset, (int)act, c10::nullopt, scale, y, x_in_smem);
+  gemv_launch(p, 0, cur_stream());
+  return y;
+}
+
+// Row-parallel GEMV -> one-shot all-reduce over NVLink peer buffers -> +bias +residual.  ONE kernel.
+at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
+                          const c10::optional<at::Tensor>& residual, const std::vector<int64_t>& recv_ptrs,
+                          const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t parity, int64_t n_max) {
+  check_gemv_inputs(x, w);
+  const int world = recv_ptrs.size();
+  TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS && (int)flag_ptrs.size() == world);
+  const int N = w.size(0);
+  TORCH_CHECK(N <= n_max && (N + 15) / 16 <= SYMM_MAX_TILES, "gemv_allreduce: output too wide for the workspace");
+  c10::cuda::CUDAGuard guard(x.device());
+  bool x_in_smem;
+  at::Tensor xn = prenorm_if_needed(x, c10::nullopt, 0, 0, x_in_smem);
+  auto y = at::empty({x.size(0), N}, x.options());
+  if (residual.has_value())
+    TORCH_CHECK(residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
+  GemvParams p{};
+  fill_params(p, xn, w, bias, c10::nullopt, 0, 0, 0, residual, c10::nullopt, y, x_in_smem);
+  for (int i = 0; i < world; ++i) {
+    p.symm.recv[i] = reinterpret_cast<float*>(recv_ptrs[i]);
+    p.symm.flags[i] = reinterpret_cast<uint32_t*>(flag_ptrs[i]);
+  }
+  p.symm.rank = rank;
+  p.symm.world = world;
+  p.symm.parity = parity;
+  p.symm.n_max = n_max;
+  gemv_launch(p, 1, cur_stream());
+  return y;
+}
+
+// ---- symmetric (peer-mapped) workspace ---------------------------------------------------------------------
+std::tuple<int64_t, pybind11::bytes> symm_alloc(int64_t nbytes) {
+  void* p = nullptr;
+  NXDI_CUDA_OK(cudaMalloc(&p, nbytes));
+  NXDI_CUDA_OK(cudaMemset(p, 0, nbytes));
+  cudaIpcMemHandle_t h;
+  NXDI_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+  NXDI_CUDA_OK(cudaDeviceSynchronize());
+  return {reinterpret_cast<int64_t>(p), pybind11::bytes(reinterpret_cast<const char*>(&h), sizeof(h))};
+}
+int64_t symm_open(const std::string& handle) {
+  TORCH_CHECK(handle.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle.data(), sizeof(h));
+  void* p = nullptr;
+  NXDI_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return reinterpret_cast<int64_t>(p);
+}
+void symm_close(int64_t ptr) { cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr)); }
+void symm_free(int64_t ptr) { cudaFree(reinterpret_cast<void*>(ptr)); }
+at::Tensor symm_as_tensor(int64_t ptr, int64_t nbytes, int64_t device) {
+  auto opts = at::TensorOptions().dtype(at::kByte).device(at::kCUDA, device);
+  return at::from_blob(reinterpret_cast<void*>(ptr), {nbytes}, opts);
+}
+
+// ---- rope / cache appends -------------------------------------------------------------------------------------
+at::Tensor rope_kv_append(const at::Tensor& qkv, const at::Tensor& cos, const at::Tensor& sin, at::Tensor& k_cache,
+                          at::Tensor& v_cache, const at::Tensor& lines, const at::Tensor& positions, int64_t nq, int64_t nkv,
+                          int64_t D, const c10::optional<at::Tensor>& q_norm, const c10::optional<at::Tensor>& k_norm,
+                          double eps) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.dim() == 3 && qkv.is_contiguous() && is_bf16(qkv) && is_bf16(k_cache));
+  const int B = qkv.size(0), T = qkv.size(1);
+  TORCH_CHECK(qkv.size(2) == (nq + 2 * nkv) * D);
+  TORCH_CHECK(cos.scalar_type() == at::kFloat && cos.is_contiguous() && sin.is_contiguous() &&
+              cos.numel() == (int64_t)B * T * D / 2 && sin.numel() == cos.numel());
+  TORCH_CHECK(k_cache.dim() == 4 && k_cache.size(1) == nkv && k_cache.size(3) == D && k_cache.is_contiguous() &&
+              v_cache.is_contiguous());
+  TORCH_CHECK(lines.scalar_type() == at::kInt && positions.scalar_type() == at::kInt && positions.is_contiguous() &&
+              lines.numel() == B && positions.numel() == B * T);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  auto q = at::empty({B, T, nq, D}, qkv.options());
+  rope_kv_append_launch(qkv.data_ptr(), cos.data_ptr<float>(), sin.data_ptr<float>(), q.data_ptr(), k_cache.data_ptr(),
+                        v_cache.data_ptr(), lines.data_ptr<int>(), positions.data_ptr<int>(), optr(q_norm), optr(k_norm),
+                        (float)eps, B, T, (int)nq, (int)nkv, (int)D, (int)k_cache.size(0), (int)k_cache.size(2), cur_stream());
+  return q;
+}
+
+void kv_append(at::Tensor& k_cache, at::Tensor& v_cache, const at::Tensor& k_new, const at::Tensor& v_new,
+               const at::Tensor& lines, const at::Tensor& positions) {
+  TORCH_CHECK(k_new.is_cuda() && k_new.dim() == 4 && k_new.is_contiguous() && v_new.is_contiguous());
+  TORCH_CHECK(k_cache.is_contiguous() && v_cache.is_contiguous() && k_cache.scalar_type() == k_new.scalar_type());
+  const int B = k_new.size(0), T = k_new.size(1), H = k_new.size(2), D = k_new.size(3);
+  TORCH_CHECK((D * k_new.element_size()) % 16 == 0 && v_new.size(3) == D && k_cache.size(1) == H && k_cache.size(3) == D);
+  TORCH_CHECK(lines.scalar_type() == at::kInt && positions.scalar_type() == at::kInt && positions.is_contiguous());
+  c10::cuda::CUDAGuard guard(k_new.device());
+  kv_append_launch(k_new.data_ptr(), v_new.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), lines.data_ptr<int>(),
+                   positions.data_ptr<int>(), B, T, H, D * (int)k_new.element_size(), (int)k_cache.size(0),
+                   (int)k_cache.size(2), cur_stream());
+}
+
+void paged_kv_append(at::Tensor& k_cache, at::Tensor& v_cache, const at::Tensor& k_new, const at::Tensor& v_new,
+                     const at::Tensor& slots) {
+  TORCH_CHECK(k_new.is_cuda() && k_new.is_contiguous() && v_new.is_contiguous() && k_cache.is_contiguous() &&
+              v_cache.is_contiguous() && k_cache.dim() == 4);
+  const int H = k_cache.size(2), D = k_cache.size(3);
+  const int ntok = k_new.numel() / (H * D);
+  TORCH_CHECK(slots.numel() == ntok && slots.scalar_type() == at::kInt && slots.is_contiguous());
+  c10::cuda::CUDAGuard guard(k_new.device());
+  paged_kv_append_launch(k_new.data_ptr(), v_new.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), slots.data_ptr<int>(),
+                         ntok, H * D * (int)k_new.element_size(), (int)(k_cache.size(0) * k_cache.size(1)), cur_stream());
+}
+
+// ---- sampling ---------------------------------------------------------------------------------------------------
+struct Scratch {
+  at::Tensor f, i, tickets;
+};
+static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t nt) {
+  static std::map<int, Scratch> all;
+  auto& s = all[dev.index()];
+  auto o = at::TensorOptions().device(dev);
+  if (!s.f.defined() || s.f.numel() < nf) s.f = at::empty({std::max<int64_t>(nf, 1 << 16)}, o.dtype(at::kFloat));
+  if (!s.i.defined() || s.i.numel() < ni) s.i = at::empty({std::max<int64_t>(ni, 1 << 16)}, o.dtype(at::kInt));
+  if (!s.tickets.defined() || s.tickets.numel() < nt) s.tickets = at::zeros({std::max<int64_t>(nt, 1 << 14)}, o.dtype(at::kInt));
+  return s;
+}
+
+at::Tensor argmax(const at::Tensor& logits) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  TORCH_CHECK(logits.scalar_type() == at::kFloat || is_bf16(logits), "argmax: fp32 or bf16 logits");
+  const int B = logits.size(0), V = logits.size(1);
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto out = at::empty({B}, logits.options().dtype(at::kLong));
+  const int nsplit = std::max(1, std::min(64, V / 2048));
+  auto& ws = scratch(logits.device(), (int64_t)B * nsplit, (int64_t)B * nsplit, B);
+  argmax_launch(logits.data_ptr(), is_bf16(logits) ? 1 : 0, out.data_ptr<int64_t>(), ws.f.data_ptr<float>(), ws.i.data_ptr<int>(),
+                reinterpret_cast<unsigned*>(ws.tickets.data_ptr<int>()), B, V, (int)logits.stride(0), nsplit, cur_stream());
+  return out;
+}
+
+at::Tensor topk_sample(const at::Tensor& logits, const at::Tensor& top_k, const at::Tensor& top_p,
+                       const at::Tensor& temperature, const at::Tensor& rand, int64_t global_topk) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  TORCH_CHECK(logits.scalar_type() == at::kFloat || is_bf16(logits), "topk_sample: fp32 or bf16 logits");
+  TORCH_CHECK(global_topk >= 1 && global_topk <= 256);
+  const int B = logits.size(0), V = logits.size(1);
+  TORCH_CHECK(top_k.scalar_type() == at::kInt && top_k.numel() == B && top_p.scalar_type() == at::kFloat &&
+              temperature.scalar_type() == at::kFloat && rand.scalar_type() == at::kFloat && rand.numel() == B);
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto out = at::empty({B}, logits.options().dtype(at::kLong));
+  topk_sample_launch(logits.data_ptr(), is_bf16(logits) ? 1 : 0, top_k.data_ptr<int>(), top_p.data_ptr<float>(),
+                     temperature.data_ptr<float>(), rand.data_ptr<float>(), out.data_ptr<int64_t>(), B, V, (int)logits.stride(0),
+                     (int)global_topk, cur_stream());
+  return out;
+}
+
+// ---- attention -----------------------------------------------------------------------------------------------------
+static int pick_nsplit(int B, int Hkv, int S_hint) {
+  const int ctas = B * Hkv;
+  int want = (S_hint + 511) / 512;                  // ~512 keys per split
+  int cap = std::max(1, (2 * 148) / std::max(ctas, 1));  // fill the chip, not more
+  return std::max(1, std::min({want, cap, 64}));
+}
+
+at::Tensor attention_decode(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& v_cache, const at::Tensor& lines,
+                            const at::Tensor& positions, double scale, int64_t window, const c10::optional<at::Tensor>& sinks,
+                            int64_t s_hint) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && is_bf16(q) && is_bf16(k_cache));
+  TORCH_CHECK(k_cache.dim() == 4 && k_cache.is_contiguous() && v_cache.is_contiguous());
+  const int B = q.size(0), T = q.size(1), Hq = q.size(2), D = q.size(3);
+  const int L = k_cache.size(0), Hkv = k_cache.size(1), S = k_cache.size(2);
+  TORCH_CHECK(k_cache.size(3) == D && Hq % Hkv == 0);
+  TORCH_CHECK(lines.scalar_type() == at::kInt && positions.scalar_type() == at::kInt && positions.is_contiguous() &&
+              lines.numel() == B && positions.numel() == B * T);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty_like(q);
+  AttnDecodeParams p{};
+  p.q = q.data_ptr(); p.k_cache = k_cache.data_ptr(); p.v_cache = v_cache.data_ptr(); p.out = out.data_ptr();
+  p.lines = lines.data_ptr<int>(); p.positions = positions.data_ptr<int>(); p.block_table = nullptr;
+  p.sinks = sinks.has_value() ? sinks->data_ptr<float>() : nullptr;
+  p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.D = D; p.S = S; p.L = L; p.window = window; p.scale = (float)scale;
+  p.nsplit = pick_nsplit(B, Hkv, s_hint > 0 ? (int)std::min<int64_t>(s_hint, S) : S);
+  auto& ws = scratch(q.device(), (int64_t)B * Hkv * p.nsplit * 64 * (D + 2), 0, (int64_t)B * Hkv);
+  p.ws_o = ws.f.data_ptr<float>();
+  p.ws_ml = p.ws_o + (int64_t)B * Hkv * p.nsplit * 64 * D;
+  p.tickets = reinterpret_cast<unsigned*>(ws.tickets.data_ptr<int>());
+  attention_decode_launch(p, cur_stream());
+  return out;
+}
+
+at::Tensor paged_attention_decode(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& v_cache,
+                                  const at::Tensor& block_table, const at::Tensor& positions, double scale, int64_t window,
+                                  const c10::optional<at::Tensor>& sinks) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && is_bf16(q) && is_bf16(k_cache));
+  TORCH_CHECK(k_cache.dim() == 4 && k_cache.is_contiguous() && v_cache.is_contiguous());
+  const int B = q.size(0), T = q.size(1), Hq = q.size(2), D = q.size(3);
+  const int bs = k_cache.size(1), Hkv = k_cache.size(2);
+  TORCH_CHECK(k_cache.size(3) == D && Hq % Hkv == 0 && block_table.dim() == 2 && block_table.size(0) == B &&
+              block_table.scalar_type() == at::kInt && block_table.is_contiguous());
+  TORCH_CHECK(positions.scalar_type() == at::kInt && positions.is_contiguous() && positions.numel() == B * T);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty_like(q);
+  AttnDecodeParams p{};
+  p.q = q.data_ptr(); p.k_cache = k_cache.data_ptr(); p.v_cache = v_cache.data_ptr(); p.out = out.data_ptr();
+  p.lines = nullptr; p.positions = positions.data_ptr<int>(); p.block_table = block_table.data_ptr<int>();
+  p.sinks = sinks.has_value() ? sinks->data_ptr<float>() : nullptr;
+  p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.D = D; p.S = 0; p.L = 0; p.window = window; p.scale = (float)scale;
+  p.block_size = bs; p.max_blocks = block_table.size(1);
+  p.nsplit = pick_nsplit(B, Hkv, p.max_blocks * bs);
+  auto& ws = scratch(q.device(), (int64_t)B * Hkv * p.nsplit * 64 * (D + 2), 0, (int64_t)B * Hkv);
+  p.ws_o = ws.f.data_ptr<float>();
+  p.ws_ml = p.ws_o + (int64_t)B * Hkv * p.nsplit * 64 * D;
+  p.tickets = reinterpret_cast<unsigned*>(ws.tickets.data_ptr<int>());
+  attention_decode_launch(p, cur_stream());
+  return out;
+}
+
+at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, double scale, int64_t window,
+                             const c10::optional<at::Tensor>& sinks) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous() && is_bf16(q) &&
+              is_bf16(k) && is_bf16(v));
+  const int B = q.size(0), T = q.size(1), Hq = q.size(2), D = q.size(3), Hkv = k.size(2);
+  TORCH_CHECK(k.size(0) == B && k.size(1) == T && k.size(3) == D && v.sizes() == k.sizes() && Hq % Hkv == 0);
+  c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty_like(q);
+  AttnPrefillParams p{};
+  p.q = q.data_ptr(); p.k = k.data_ptr(); p.v = v.data_ptr(); p.out = out.data_ptr();
+  p.sinks = sinks.has_value() ? sinks->data_ptr<float>() : nullptr;
+  p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.D = D; p.window = window; p.scale = (float)scale;
+  attention_prefill_launch(p, cur_stream());
+  return out;
+}
+
+}  // namespace nxdi
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rmsnorm", &nxdi::rmsnorm);
+  m.def("gemv", &nxdi::gemv);
+  m.def("gemv_allreduce", &nxdi::gemv_allreduce);
+  m.def("symm_alloc", &nxdi::symm_alloc);
+  m.def("symm_open", &nxdi::symm_open);
+  m.def("symm_close", &nxdi::symm_close);
+  m.def("symm_free", &nxdi::symm_free);
+  m.def("symm_as_tensor", &nxdi::symm_as_tensor);
+  m.def("rope_kv_append", &nxdi::rope_kv_append);
+  m.def("kv_append", &nxdi::kv_append);
+  m.def("paged_kv_append", &nxdi::paged_kv_append);
+  m.def("argmax", &nxdi::argmax);
+  m.def("topk_sample", &nxdi::topk_sample);
+  m.def("attention_decode", &nxdi::attention_decode);
+  m.def("paged_attention_decode", &nxdi::paged_attention_decode);
+  m.def("attention_prefill", &nxdi::attention_prefill);
+}

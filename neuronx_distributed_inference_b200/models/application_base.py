@@ -164,8 +164,10 @@ class NeuronApplicationBase(nn.Module):
         return model.eval()
 
     def load(self, compiled_model_path: Optional[str] = None, start_rank_id=None, local_ranks_size=None,
-             skip_warmup: bool = False, state_dict: Optional[dict] = None):
-        """Build the model on this rank's device and load weights."""
+             skip_warmup: bool = False, state_dict: Optional[dict] = None, random_weights: bool = False,
+             seed: int = 0):
+        """Build the model on this rank's device and load weights (``random_weights``: N(0, 0.02) init
+        directly on the device — benchmarks / smoke tests without a checkpoint)."""
         nc = self.neuron_config
         self._init_runtime()
         t0 = time.time()
@@ -180,7 +182,9 @@ class NeuronApplicationBase(nn.Module):
             p = os.path.join(compiled_model_path, "weights", f"tp{g.rank}_sharded_checkpoint")
             if os.path.isdir(p) and nc.save_sharded_checkpoint:
                 pre = load_state_dict(p)
-        if pre is not None:
+        if random_weights:
+            self.init_random_weights(seed)
+        elif pre is not None:
             self.model.load_state_dict(pre, strict=False)
         else:
             sd = state_dict if state_dict is not None else self.checkpoint_loader_fn()
@@ -193,6 +197,24 @@ class NeuronApplicationBase(nn.Module):
         if not (skip_warmup or nc.skip_warmup):
             self.warmup()
         return self
+
+    def init_random_weights(self, seed: int = 0):
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed + 1000 * pstate.get_tensor_model_parallel_group().rank)
+        with torch.no_grad():
+            for name, p in self.model.named_parameters():
+                if p.dim() == 1 and ("norm" in name or "layernorm" in name):
+                    p.fill_(1.0)
+                elif p.dtype in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+                    p.copy_((torch.randn(p.shape, device=self.device, generator=gen) * 20).clamp(-100, 100).to(p.dtype))
+                elif name.endswith(".scale"):
+                    p.fill_(0.001)
+                elif p.is_floating_point():
+                    tmp = torch.empty(p.shape, device=self.device, dtype=torch.float32 if p.numel() < (1 << 28)
+                                      else p.dtype)
+                    tmp.normal_(0.0, 0.02, generator=gen)
+                    p.copy_(tmp)
+                    del tmp
 
     def to_cpu(self):
         """CPU execution path (reference application_base.py:556-628)."""

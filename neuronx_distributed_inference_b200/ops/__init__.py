@@ -80,7 +80,7 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
                 stats["gemv"] += 1
                 y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale)
                 return y.view(*x.shape[:-1], y.shape[-1])
-            if not wq and N % 128 == 0 and K % 64 == 0:
+            if not wq and N % 128 == 0 and K % 64 == 0 and hasattr(_C(), "gemm"):
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
                 stats["gemm_tcgen05"] += 1
@@ -149,13 +149,16 @@ def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
 
 
 def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None, chunk=None, sinks=None,
-                     active_mask=None, softcap=None, k_scale=None, v_scale=None):
+                     active_mask=None, softcap=None, k_scale=None, v_scale=None, seq_hint: int = 0):
+    """``seq_hint``: upper bound on the live context (the TKG bucket) used only to size the split-KV grid."""
     D = q.shape[-1]
     if (_use_cuda(q) and q.dtype in _FAST_DTYPES and k_cache.dtype == q.dtype and D in (64, 128)
-            and active_mask is None and chunk is None and softcap is None and q.shape[1] <= 16):
+            and active_mask is None and chunk is None and softcap is None
+            and q.shape[1] * (q.shape[2] // k_cache.shape[1]) <= 64):
         stats["attn_decode"] += 1
         return _C().attention_decode(q.contiguous(), k_cache, v_cache, seq_ids.to(torch.int32),
-                                     positions.to(torch.int32), float(scale), int(window or 0), sinks)
+                                     positions.to(torch.int32).contiguous(), float(scale), int(window or 0), sinks,
+                                     int(seq_hint))
     return ref.attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window, chunk, sinks,
                                 active_mask, softcap, k_scale, v_scale)
 
@@ -183,7 +186,7 @@ def paged_kv_append(k_cache, v_cache, k_new, v_new, slot_mapping):
 def paged_attention_decode(q, k_cache, v_cache, block_table, positions, scale, window=None, sinks=None):
     D = q.shape[-1]
     if (_use_cuda(q) and q.dtype in _FAST_DTYPES and k_cache.dtype == q.dtype and D in (64, 128)
-            and q.shape[1] <= 16):
+            and q.shape[1] * (q.shape[2] // k_cache.shape[2]) <= 64):
         stats["paged_attn_decode"] += 1
         return _C().paged_attention_decode(q.contiguous(), k_cache, v_cache, block_table.to(torch.int32).contiguous(),
                                            positions.to(torch.int32), float(scale), int(window or 0), sinks)

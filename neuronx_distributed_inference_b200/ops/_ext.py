@@ -53,9 +53,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
     common = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
-              f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-DTORCH_EXTENSION_NAME=_C",
-              "-DTORCH_API_INCLUDE_EXTENSION_H", "--expt-relaxed-constexpr", "--expt-extended-lambda",
-              "-Xcudafe", "--diag_suppress=177,550", "-DNDEBUG"] + GENCODE + _include_flags()
+              "--expt-relaxed-constexpr", "--expt-extended-lambda",
+              "-diag-suppress", "177", "-diag-suppress", "550", "-DNDEBUG", f"-I{_CSRC}"] + GENCODE
     if verbose:
         common += ["-Xptxas", "-v"]
     objs, jobs = [], []
@@ -66,7 +65,13 @@ def build(verbose: bool = False, force: bool = False) -> str:
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dg:
             continue
-        cmd = [nvcc] + common + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", src, "-o", obj]
+        if src.endswith(".cpp"):
+            cxx = os.environ.get("CXX", "g++")
+            cmd = [cxx, "-O2", "-std=c++17", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-DTORCH_EXTENSION_NAME=_C",
+                   "-DTORCH_API_INCLUDE_EXTENSION_H", "-DNDEBUG", "-Wno-deprecated-declarations",
+                   "-I/usr/local/cuda/include"] + _include_flags() + ["-c", src, "-o", obj]
+        else:
+            cmd = [nvcc] + common + ["-c", src, "-o", obj]
         jobs.append((cmd, stamp, dg, src))
 
     def run(job):
@@ -87,7 +92,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if need_link:
         tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
         cmd = [nvcc, "-shared", "-o", _SO] + objs + [f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu",
-                                                    "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcuda",
+                                                    "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart",
                                                     f"-Xlinker=-rpath,{tlib}"] + GENCODE
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -206,6 +206,7 @@ class SubModelRunner:
             si["position_ids"][B:].fill_(0)
         if sampling_params is not None:
             si["sampling_params"][:B].copy_(sampling_params, non_blocking=True)
+        self._symm_even()
         g.graph.replay()
         self.n_launch += 1
         o = g.out
@@ -239,13 +240,21 @@ class SubModelRunner:
             si["position_ids"].zero_()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
+        self._symm_even()
         graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(graph, stream=s):
             g.out = step()
+            self._symm_even()   # captured: keeps the number of fused collectives per replay even
         g.graph = graph
         self._graphs[key] = g
         logger.debug("captured %s graph %s", self.tag, key[:3])
         return g
+
+    def _symm_even(self):
+        from ..parallel.state import get_tensor_model_parallel_group
+        symm = get_tensor_model_parallel_group().symm
+        if symm is not None:
+            symm.ensure_even()
 
     # ---- device-resident multi-step decode (async mode / benchmarks) ------------------------------
     def replay_steps(self, key_graph: _Graph, n: int):

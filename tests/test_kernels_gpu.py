@@ -1,0 +1,192 @@
+"""Numerics of every sm_100a kernel against the plain-PyTorch fp32 definition of the same op."""
+import math
+
+import pytest
+import torch
+
+from neuronx_distributed_inference_b200 import ops
+from neuronx_distributed_inference_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-9)).item()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _ext():
+    from neuronx_distributed_inference_b200.ops._ext import load_extension
+    load_extension()
+
+
+@pytest.mark.parametrize("rows,H", [(1, 4096), (7, 4096), (33, 8192), (4, 1024)])
+def test_rmsnorm(rows, H):
+    x = torch.randn(rows, H, device=DEV, dtype=torch.bfloat16)
+    w = (torch.randn(H, device=DEV) * 0.1 + 1).to(torch.bfloat16)
+    y = ops.rmsnorm(x, w, 1e-5)
+    yr = ref.rmsnorm(x.float(), w.float(), 1e-5)
+    assert _rel(y, yr) < 5e-3
+    r = torch.randn_like(x)
+    y2, r2 = ops.rmsnorm(x, w, 1e-5, 0.0, r)
+    yr2, rr2 = ref.rmsnorm(x, w, 1e-5, 0.0, r)
+    assert _rel(r2, rr2) < 1e-6 and _rel(y2, yr2) < 8e-3
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 8])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (1000 * 16, 2048), (4096, 14336), (512, 512), (40, 256)])
+def test_gemv(T, N, K):
+    x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    y = ops.linear(x, w, b)
+    yr = ref.linear(x.float(), w.float(), b.float())
+    assert y.shape == yr.shape and _rel(y, yr) < 6e-3
+
+
+@pytest.mark.parametrize("T", [1, 2, 5])
+@pytest.mark.parametrize("N,K", [(2 * 14336, 4096), (2 * 1792, 4096), (2 * 11008, 4096)])
+def test_gemv_norm_swiglu(T, N, K):
+    x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16) * 3
+    g = (torch.randn(K, device=DEV) * 0.2 + 1).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    y = ops.linear(x, w, None, norm_weight=g, norm_eps=1e-5, act="silu_mul")
+    xn = ref.rmsnorm(x.float(), g.float(), 1e-5).to(torch.bfloat16).float()
+    yr = ref.linear(xn, w.float(), None, act="silu_mul")
+    assert y.shape == (T, N // 2) and _rel(y, yr) < 8e-3
+
+
+def test_gemv_x_global_path():
+    # T*K too large for shared memory -> pre-normalised x read through L1
+    T, N, K = 8, 1024, 14336
+    x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16)
+    g = torch.ones(K, device=DEV, dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    y = ops.linear(x, w, None, norm_weight=g, norm_eps=1e-5)
+    yr = ref.linear(ref.rmsnorm(x.float(), g.float(), 1e-5).to(torch.bfloat16).float(), w.float())
+    assert _rel(y, yr) < 8e-3
+
+
+@pytest.mark.parametrize("D,nq,nkv", [(128, 32, 8), (64, 8, 8), (128, 4, 1)])
+@pytest.mark.parametrize("T", [1, 3])
+def test_rope_kv_append(D, nq, nkv, T):
+    B, S, L = 3, 64, 4
+    qkv = torch.randn(B, T, (nq + 2 * nkv) * D, device=DEV, dtype=torch.bfloat16)
+    pos = torch.randint(0, S - T, (B, 1), device=DEV) + torch.arange(T, device=DEV)
+    pos[1, -1] = -1  # skipped write
+    ang = torch.rand(B, T, D // 2, device=DEV) * 6
+    cos, sin = ang.cos(), ang.sin()
+    lines = torch.tensor([2, 0, 7], device=DEV, dtype=torch.int32)  # 7 is out of range -> skipped
+    kc = torch.zeros(L, nkv, S, D, device=DEV, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    qn = (torch.randn(D, device=DEV) * 0.1 + 1).to(torch.bfloat16)
+    kn = (torch.randn(D, device=DEV) * 0.1 + 1).to(torch.bfloat16)
+    for norms in (False, True):
+        kc.zero_(); vc.zero_()
+        q = ops.rope_kv_append(qkv, cos, sin, kc, vc, lines, pos.int(), nq, nkv, D, False,
+                               qn if norms else None, kn if norms else None, 1e-6)
+        kr, vr = torch.zeros_like(kc), torch.zeros_like(vc)
+        ops.set_kernels_enabled(False)
+        qr = ops.rope_kv_append(qkv, cos, sin, kr, vr, lines, pos.int(), nq, nkv, D, False,
+                                qn if norms else None, kn if norms else None, 1e-6)
+        ops.set_kernels_enabled(True)
+        assert _rel(q, qr) < 1e-2 and _rel(kc, kr) < 1e-2 and torch.equal(vc, vr)
+
+
+def test_kv_append_and_paged():
+    B, T, H, D, S, L = 2, 5, 4, 128, 32, 3
+    k = torch.randn(B, T, H, D, device=DEV, dtype=torch.bfloat16)
+    v = torch.randn_like(k)
+    pos = torch.tensor([[3, 4, 5, 6, -1], [0, 1, 2, 31, 40]], device=DEV, dtype=torch.int32)
+    lines = torch.tensor([1, 2], device=DEV, dtype=torch.int32)
+    kc = torch.zeros(L, H, S, D, device=DEV, dtype=torch.bfloat16); vc = torch.zeros_like(kc)
+    kr = torch.zeros_like(kc); vr = torch.zeros_like(kc)
+    ops.kv_append(kc, vc, k, v, lines, pos)
+    ref.kv_append(kr, vr, k, v, lines, pos)
+    assert torch.equal(kc, kr) and torch.equal(vc, vr)
+    nb, bs = 6, 8
+    pk = torch.zeros(nb, bs, H, D, device=DEV, dtype=torch.bfloat16); pv = torch.zeros_like(pk)
+    rk = torch.zeros_like(pk); rv = torch.zeros_like(pk)
+    slots = torch.tensor([[0, 1, 9, 17, -1], [47, 5, 6, 7, 8]], device=DEV, dtype=torch.int32)
+    ops.paged_kv_append(pk, pv, k, v, slots)
+    ref.paged_kv_append(rk, rv, k, v, slots)
+    assert torch.equal(pk, rk) and torch.equal(pv, rv)
+
+
+@pytest.mark.parametrize("D", [128, 64])
+@pytest.mark.parametrize("Hq,Hkv,T", [(32, 8, 1), (4, 1, 1), (8, 8, 2), (16, 2, 5), (32, 8, 8)])
+@pytest.mark.parametrize("window", [0, 37])
+def test_attention_decode(D, Hq, Hkv, T, window):
+    if T * (Hq // Hkv) > 64:
+        pytest.skip("rows > 64")
+    B, S, L = 3, 700, 4
+    kc = torch.randn(L, Hkv, S, D, device=DEV, dtype=torch.bfloat16)
+    vc = torch.randn_like(kc)
+    q = torch.randn(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    base = torch.tensor([[5], [300], [S - T - 1]], device=DEV)
+    pos = (base + torch.arange(T, device=DEV)).int()
+    lines = torch.tensor([3, 1, 0], device=DEV, dtype=torch.int32)
+    scale = 1 / math.sqrt(D)
+    o = ops.attention_decode(q, kc, vc, lines, pos, scale, window or None)
+    orf = ref.attention_decode(q.float(), kc.float(), vc.float(), lines, pos, scale, window or None)
+    assert _rel(o, orf) < 1.5e-2
+
+
+def test_attention_decode_sinks_and_masked_line():
+    B, T, Hq, Hkv, D, S, L = 2, 1, 8, 2, 64, 256, 2
+    kc = torch.randn(L, Hkv, S, D, device=DEV, dtype=torch.bfloat16); vc = torch.randn_like(kc)
+    q = torch.randn(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    pos = torch.tensor([[100], [7]], device=DEV, dtype=torch.int32)
+    lines = torch.tensor([1, 0], device=DEV, dtype=torch.int32)
+    sinks = torch.randn(Hq, device=DEV)
+    o = ops.attention_decode(q, kc, vc, lines, pos, 0.125, None, None, sinks)
+    orf = ref.attention_decode(q.float(), kc.float(), vc.float(), lines, pos, 0.125, None, None, sinks)
+    assert _rel(o, orf) < 1.5e-2
+
+
+@pytest.mark.parametrize("D", [128, 64])
+@pytest.mark.parametrize("B,T,Hq,Hkv", [(2, 128, 8, 2), (1, 200, 4, 4), (2, 33, 8, 1), (1, 1024, 4, 1)])
+@pytest.mark.parametrize("window", [0, 50])
+def test_attention_prefill(D, B, T, Hq, Hkv, window):
+    q = torch.randn(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    k = torch.randn(B, T, Hkv, D, device=DEV, dtype=torch.bfloat16)
+    v = torch.randn_like(k)
+    scale = 1 / math.sqrt(D)
+    o = ops.attention_prefill(q, k, v, scale, True, window or None)
+    orf = ref.attention_prefill(q.float(), k.float(), v.float(), scale, True, window or None)
+    assert _rel(o, orf) < 1.5e-2
+
+
+def test_paged_attention_decode():
+    B, T, Hq, Hkv, D, bs, nb = 2, 2, 8, 2, 128, 16, 40
+    kc = torch.randn(nb, bs, Hkv, D, device=DEV, dtype=torch.bfloat16); vc = torch.randn_like(kc)
+    q = torch.randn(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    bt = torch.randperm(nb, device=DEV)[:B * 10].view(B, 10).int()
+    pos = torch.tensor([[100, 101], [17, 18]], device=DEV, dtype=torch.int32)
+    o = ops.paged_attention_decode(q, kc, vc, bt, pos, 0.09)
+    orf = ref.paged_attention_decode(q.float(), kc.float(), vc.float(), bt, pos, 0.09)
+    assert _rel(o, orf) < 1.5e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_argmax(dtype):
+    x = torch.randn(5, 128256, device=DEV).to(dtype)
+    assert torch.equal(ops.argmax(x), x.float().argmax(-1))
+    x = torch.randn(3, 1000, device=DEV).to(dtype)
+    assert torch.equal(ops.argmax(x), x.float().argmax(-1))
+
+
+def test_topk_sample_matches_reference():
+    B, V = 6, 32000
+    logits = torch.randn(B, V, device=DEV) * 3
+    top_k = torch.tensor([1, 5, 50, 0, 256, 10], device=DEV, dtype=torch.int32)
+    top_p = torch.tensor([1.0, 0.9, 0.5, 1.0, 0.95, 1.0], device=DEV)
+    temp = torch.tensor([1.0, 0.7, 1.3, 1.0, 0.0, 2.0], device=DEV)
+    for seed in range(4):
+        torch.manual_seed(seed)
+        rand = torch.rand(B, device=DEV)
+        got = ops.sample(logits, top_k, top_p, temp, rand, 256)
+        exp = ref.sample(logits, top_k, top_p, temp, rand, 256)
+        assert torch.equal(got, exp), (got, exp)
