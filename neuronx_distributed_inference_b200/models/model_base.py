@@ -150,8 +150,6 @@ class NeuronBaseModel(nn.Module):
         if is_prefill:
             if attention_mask is not None and attention_mask.shape[-1] == T:
                 key_valid = attention_mask.to(torch.bool)
-                if bool(key_valid.all()) if not input_ids.is_cuda else False:
-                    key_valid = None
             if key_valid is not None:
                 write = torch.where(key_valid, position_ids, torch.full_like(position_ids, -1))
             else:

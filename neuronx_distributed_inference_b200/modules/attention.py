@@ -163,8 +163,10 @@ class AttentionBase(nn.Module):
             meta.capture[f"layers.{self.layer_idx}.self_attn.q"] = q
 
         if meta.is_prefill and not meta.has_prefix:
+            right = self._arange_pos(meta)
+            # right padding: pad keys sit after every real token, causality alone hides them
             o = ops.attention_prefill(q, k, v, self.scale, True, self.sliding_window, self.attention_chunk_size,
-                                      meta.key_valid, None if self._arange_pos(meta) else meta.position_ids,
+                                      None if right else meta.key_valid, None if right else meta.position_ids,
                                       self.sinks, self.softcap)
         elif paged:
             if self.attention_chunk_size is not None or meta.active_mask is not None:

@@ -123,7 +123,7 @@ def rope_kv_append(qkv, cos, sin, k_cache, v_cache, seq_ids, positions, n_q, n_k
     ONE kernel on CUDA (csrc/rope_kv.cu)."""
     B, T = positions.shape
     D = head_dim
-    if (_use_cuda(qkv) and qkv.dtype in _FAST_DTYPES and k_cache.dtype == qkv.dtype and D % 8 == 0
+    if (_use_cuda(qkv) and qkv.dtype in _FAST_DTYPES and k_cache.dtype == qkv.dtype and D in (64, 128, 256)
             and cos.shape[-1] * 2 == D and not interleaved):
         stats["rope_kv_append"] += 1
         return _C().rope_kv_append(qkv.reshape(B, T, -1), cos.contiguous(), sin.contiguous(), k_cache, v_cache,

@@ -162,6 +162,8 @@ class SubModelRunner:
         if attention_mask is not None and attention_mask.shape[-1] != input_ids.shape[-1]:
             attention_mask = attention_mask[:, -input_ids.shape[-1]:]
         ids, mask, pos, _ = self.pad_prefill(input_ids, attention_mask, position_ids)
+        if mask is not None and mask.device.type == "cpu" and bool(mask.all()):
+            mask = None   # no padding anywhere: skip the mask plumbing (decided on the host, no device sync)
         self.n_launch += 1
         with torch.no_grad():
             return self.model(_to_dev(ids, dev), _to_dev(mask, dev), _to_dev(pos, dev, torch.int32),
