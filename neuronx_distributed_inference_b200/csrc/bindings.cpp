@@ -79,7 +79,7 @@ static void check_gemv_inputs(const at::Tensor& x, const at::Tensor& w) {
 
 at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                 const c10::optional<at::Tensor>& norm_w, double eps, double offset, int64_t act,
-                const c10::optional<at::Tensor>& scale) {
+                const c10::optional<at::Tensor>& scale, const c10::optional<at::Tensor>& residual) {
   check_gemv_inputs(x, w);
   TORCH_CHECK(!scale.has_value(), "gemv: quantised weights are not wired yet");
   c10::cuda::CUDAGuard guard(x.device());
@@ -89,8 +89,10 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
   bool x_in_smem;
   at::Tensor xn = prenorm_if_needed(x, norm_w, eps, offset, x_in_smem);
   auto y = at::empty({x.size(0), glu ? N / 2 : N}, x.options());
+  if (residual.has_value())
+    TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
   GemvParams p{};
-  fill_params(p, xn, w, bias, norm_w, eps, offset, (int)act, c10::nullopt, scale, y, x_in_smem);
+  fill_params(p, xn, w, bias, norm_w, eps, offset, (int)act, residual, scale, y, x_in_smem);
   gemv_launch(p, 0, cur_stream());
   return y;
 }

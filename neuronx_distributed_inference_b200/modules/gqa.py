@@ -205,8 +205,7 @@ class GroupQueryAttention_O(BaseParallelLinear):
     def forward(self, x, residual=None):
         g = self.tensor_parallel_group
         if g.size == 1:
-            y = ops.linear(x, self.weight, self.bias)
-            return y if residual is None else y + residual
+            return ops.linear(x, self.weight, self.bias, residual=residual)
         if self.sequence_parallel_enabled:
             y = mappings.reduce_scatter(ops.linear(x, self.weight, None), self.sequence_dimension, g)
             if self.bias is not None:

@@ -66,8 +66,8 @@ _ACT_CODES = {None: 0, "silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
 
 
 def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offset: float = 0.0,
-           act: Optional[str] = None, scale=None):
-    """y = act(rmsnorm(x) @ w^T + bias).  w: [N,K] bf16, or int8/fp8 with per-channel ``scale``."""
+           act: Optional[str] = None, scale=None, residual=None):
+    """y = act(rmsnorm(x) @ w^T + bias) (+ residual).  w: [N,K] bf16, or int8/fp8 with per-channel ``scale``."""
     if _use_cuda(x) and x.dtype in _FAST_DTYPES:
         K = x.shape[-1]
         T = x.numel() // K
@@ -78,15 +78,19 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
             x2 = x.reshape(T, K)
             if T <= GEMV_MAX_TOKENS:
                 stats["gemv"] += 1
-                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale)
-                return y.view(*x.shape[:-1], y.shape[-1])
+                r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
+                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2)
+                y = y.view(*x.shape[:-1], y.shape[-1])
+                return y if (residual is None or r2 is not None) else y + residual
             if not wq and N % 128 == 0 and K % 64 == 0 and hasattr(_C(), "gemm"):
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
                 stats["gemm_tcgen05"] += 1
                 y = _C().gemm(x2.contiguous(), w, bias, _ACT_CODES[act])
-                return y.view(*x.shape[:-1], y.shape[-1])
-    return ref.linear(x, w, bias, norm_weight, norm_eps, norm_offset, act, scale)
+                y = y.view(*x.shape[:-1], y.shape[-1])
+                return y if residual is None else y + residual
+    y = ref.linear(x, w, bias, norm_weight, norm_eps, norm_offset, act, scale)
+    return y if residual is None else y + residual
 
 
 def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=None):

@@ -126,10 +126,7 @@ class RowParallelLinear(BaseParallelLinear):
         if not self.input_is_parallel:
             x = mappings.scatter_to_region(x, -1, g)
         if g.size == 1 or not self.reduce_output:
-            y = ops.linear(x, self.weight, self.bias if g.size == 1 or g.rank == 0 else None)
-            if residual is not None:
-                y = y + residual
-            return y
+            return ops.linear(x, self.weight, self.bias if g.size == 1 or g.rank == 0 else None, residual=residual)
         if self.sequence_parallel_enabled:
             y = ops.linear(x, self.weight, None)
             y = mappings.reduce_scatter(y, self.sequence_dimension, g)

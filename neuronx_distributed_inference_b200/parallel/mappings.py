@@ -39,8 +39,11 @@ def all_gather(x: torch.Tensor, dim: int, group: Optional[Group] = None) -> torc
         return x
     dim = dim % x.dim()
     x = x.contiguous()
-    out = torch.empty((g.size,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x, group=g.pg)
+    if x.dim() == 0:
+        x = x.reshape(1)
+    flat = torch.empty((g.size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, x, group=g.pg)
+    out = flat.view((g.size,) + tuple(x.shape))
     if dim == 0:
         return out.reshape((-1,) + tuple(x.shape[1:]))
     return out.movedim(0, dim).reshape(x.shape[:dim] + (g.size * x.shape[dim],) + x.shape[dim + 1:])

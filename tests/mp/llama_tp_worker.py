@@ -1,0 +1,69 @@
+"""Worker run under torchrun (gloo on CPU, nccl on GPU): tensor-parallel Llama vs the HF fp32 reference.
+usage: torchrun --nproc-per-node N tests/mp/llama_tp_worker.py <ckpt_dir> <cpu|cuda> [dtype]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+
+def main():
+    ckpt, dev = sys.argv[1], sys.argv[2]
+    dtype = sys.argv[3] if len(sys.argv) > 3 else ("float32" if dev == "cpu" else "bfloat16")
+    from neuronx_distributed_inference_b200.config import NeuronConfig, OnDeviceSamplingConfig, load_pretrained_config
+    from neuronx_distributed_inference_b200.models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaForCausalLM
+    from neuronx_distributed_inference_b200.parallel import state as pstate
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if dev == "cuda":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    nc = NeuronConfig(batch_size=2, seq_len=64, max_context_length=32, torch_dtype=dtype, tp_degree=world,
+                      on_cpu=(dev == "cpu"), output_logits=True, on_device_sampling_config=OnDeviceSamplingConfig(top_k=1))
+    cfg = LlamaInferenceConfig(nc, load_config=load_pretrained_config(ckpt))
+    app = NeuronLlamaForCausalLM(ckpt, cfg)
+    app.load(None, skip_warmup=True)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, cfg.vocab_size, (2, 12), generator=g)
+    mask = torch.ones(2, 12, dtype=torch.int32)
+    mask[1, 9:] = 0
+    out = app(ids, attention_mask=mask)
+    logits = [out.logits[:, 0].float().cpu()]
+    toks = [out.tokens.cpu()]
+    pos = mask.sum(-1).view(2, 1).int()
+    tok = out.tokens.cpu()
+    for _ in range(6):
+        out = app(tok.view(2, 1), position_ids=pos)
+        tok = out.tokens.cpu()
+        logits.append(out.logits[:, 0].float().cpu())
+        toks.append(tok)
+        pos = pos + 1
+    if rank == 0:
+        from transformers import AutoModelForCausalLM
+        hf = AutoModelForCausalLM.from_pretrained(ckpt, torch_dtype=torch.float32).eval()
+        ok = True
+        worst = 0.0
+        with torch.no_grad():
+            for b in range(2):
+                n = int(mask[b].sum())
+                seq = ids[b:b + 1, :n]
+                for step in range(len(logits)):
+                    ref = hf(seq).logits[0, -1]
+                    got = logits[step][b]
+                    err = ((got - ref).norm() / ref.norm()).item()
+                    worst = max(worst, err)
+                    # teacher-force OUR token so later steps stay comparable
+                    seq = torch.cat([seq, toks[step][b].view(1, 1)], 1)
+        tol = 2e-4 if dtype == "float32" else 4e-2
+        ok = worst < tol
+        print(json.dumps({"world": world, "device": dev, "dtype": dtype, "worst_rel_err": worst, "ok": ok}))
+        if not ok:
+            sys.exit(1)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

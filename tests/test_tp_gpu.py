@@ -1,0 +1,31 @@
+"""Tensor parallel on real GPUs: NCCL bootstrap + the fused GEMV->all-reduce kernel over NVLink peer memory."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _ckpt(tmp):
+    from transformers import LlamaConfig
+    from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+    cfg = LlamaConfig(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8,
+                      num_key_value_heads=2, head_dim=128, vocab_size=2048, max_position_embeddings=256,
+                      tie_word_embeddings=False)
+    return save_random_hf_checkpoint(cfg, tmp)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_llama_tp_fused_allreduce_matches_hf(n, tmp_path):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    ckpt = _ckpt(str(tmp_path / "ckpt"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + n), os.path.join(ROOT, "tests", "mp", "llama_tp_worker.py"), ckpt, "cuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"ok": true' in r.stdout
