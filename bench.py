@@ -211,6 +211,16 @@ def ci_harness(app, batch, ctx, seq_len, n_runs=5):
                 output_logits=False)
 
 
+def _hard_exit(code=0):
+    """Tearing down NCCL communicators that were captured into CUDA graphs can block forever in
+    destroy_process_group(); results are already printed, so flush and leave."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,7 +294,7 @@ def main():
         print(json.dumps(out))
     if dist.is_initialized():
         dist.barrier()
-        dist.destroy_process_group()
+        _hard_exit()
     return 0
 
 

@@ -1,5 +1,6 @@
 """Worker run under torchrun (gloo on CPU, nccl on GPU): tensor-parallel Llama vs the HF fp32 reference.
 usage: torchrun --nproc-per-node N tests/mp/llama_tp_worker.py <ckpt_dir> <cpu|cuda> [dtype]"""
+import faulthandler
 import json
 import os
 import sys
@@ -9,7 +10,18 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
+def _hard_exit(code=0):
+    """Tearing down NCCL communicators that were captured into CUDA graphs can block forever in
+    destroy_process_group(); results are already printed, so flush and leave."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
+
+
 def main():
+    faulthandler.dump_traceback_later(int(os.environ.get('DUMP_AFTER', '240')), exit=True)
     ckpt, dev = sys.argv[1], sys.argv[2]
     dtype = sys.argv[3] if len(sys.argv) > 3 else ("float32" if dev == "cpu" else "bfloat16")
     from neuronx_distributed_inference_b200.config import NeuronConfig, OnDeviceSamplingConfig, load_pretrained_config
@@ -62,7 +74,7 @@ def main():
             sys.exit(1)
     if world > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        _hard_exit()
 
 
 if __name__ == "__main__":
