@@ -11,7 +11,7 @@ constexpr int SYMM_MAX_TILES = 1024;
 constexpr int GEMV_MAX_T = 8;
 
 struct SymmArgs {
-  float* recv[SYMM_MAX_RANKS];      // peer-mapped receive buffers  [2][tp][8][n_max] fp32
+  float* recv[SYMM_MAX_RANKS];      // peer-mapped receive buffers  [2][tp][8][n_max] x {fp32 value, u32 flag} (v1: fp32 only)
   uint32_t* flags[SYMM_MAX_RANKS];  // peer-mapped flags            [2][tp][SYMM_MAX_TILES]
   int rank, world, parity, n_max;
 };
@@ -34,6 +34,11 @@ struct GemvParams {
 
 size_t gemv_smem_bytes(int T, int K, bool x_in_smem);
 void gemv_launch(const GemvParams& p, int mode, cudaStream_t stream);  // mode 0 plain, 1 fused all-reduce
+// v2: bulk-async pipelined, stream-K balanced (gemv2.cu)
+bool gemv2_supported(int T, int K);
+int gemv2_grid(int N, int K, bool glu);
+int gemv2_pmax(int N, int K, bool glu);
+void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* tickets, cudaStream_t stream);
 void rmsnorm_launch(const void* x, const void* res_in, const void* w, void* y, void* res_out, int rows, int H, float eps,
                     float offset, cudaStream_t stream);
 

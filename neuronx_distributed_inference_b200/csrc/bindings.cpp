@@ -39,6 +39,37 @@ std::tuple<at::Tensor, at::Tensor> rmsnorm(const at::Tensor& x, const at::Tensor
   return {y, res_out.defined() ? res_out : y};
 }
 
+struct Scratch {
+  at::Tensor f, i, tickets, gemv_ws, gemv_tickets;
+};
+static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t nt);
+
+static bool use_gemv2(int T, int K) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NXDI_B200_GEMV");
+    v = (e == nullptr) ? 2 : atoi(e);
+  }
+  return v == 2 && gemv2_supported(T, K);
+}
+
+static void run_gemv(GemvParams& p, int mode, const at::Device& dev) {
+  if (use_gemv2(p.T, p.K) && p.x_in_smem) {
+    auto& s = scratch(dev, 0, 0, 0);
+    const bool glu = p.act != 0;
+    const int n_tiles = glu ? ((p.N / 2) + 7) / 8 : (p.N + 15) / 16;
+    const int64_t need = (int64_t)n_tiles * gemv2_pmax(p.N, p.K, glu) * 128;
+    auto o = at::TensorOptions().device(dev);
+    if (!s.gemv_ws.defined() || s.gemv_ws.numel() < need) s.gemv_ws = at::empty({std::max<int64_t>(need, 4 << 20)}, o.dtype(at::kFloat));
+    if (!s.gemv_tickets.defined() || s.gemv_tickets.numel() < n_tiles)
+      s.gemv_tickets = at::zeros({std::max<int64_t>(n_tiles, 1 << 15)}, o.dtype(at::kInt));
+    gemv2_launch(p, mode, s.gemv_ws.data_ptr<float>(), reinterpret_cast<unsigned*>(s.gemv_tickets.data_ptr<int>()), cur_stream());
+  } else {
+    TORCH_CHECK(mode == 0 || !use_gemv2(1, 256), "fused all-reduce: v1/v2 kernels use different slot layouts; T*K too large for v2");
+    gemv_launch(p, mode, cur_stream());
+  }
+}
+
 // ---- skinny GEMM ----------------------------------------------------------------------------------------
 static void fill_params(GemvParams& p, const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                         const c10::optional<at::Tensor>& norm_w, double eps, double offset, int act,
@@ -93,7 +124,7 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
     TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
   GemvParams p{};
   fill_params(p, xn, w, bias, norm_w, eps, offset, (int)act, residual, scale, y, x_in_smem);
-  gemv_launch(p, 0, cur_stream());
+  run_gemv(p, 0, x.device());
   return y;
 }
 
@@ -122,7 +153,7 @@ at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::o
   p.symm.world = world;
   p.symm.parity = parity;
   p.symm.n_max = n_max;
-  gemv_launch(p, 1, cur_stream());
+  run_gemv(p, 1, x.device());
   return y;
 }
 
@@ -199,9 +230,6 @@ void paged_kv_append(at::Tensor& k_cache, at::Tensor& v_cache, const at::Tensor&
 }
 
 // ---- sampling ---------------------------------------------------------------------------------------------------
-struct Scratch {
-  at::Tensor f, i, tickets;
-};
 static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t nt) {
   static std::map<int, Scratch> all;
   auto& s = all[dev.index()];

@@ -38,7 +38,7 @@ class SymmetricWorkspace:
         self.parity = 0
         self.calls = 0
         self._C = load_extension()
-        recv_bytes = 2 * self.world * MAX_TOKENS * self.n_max * 4
+        recv_bytes = 2 * self.world * MAX_TOKENS * self.n_max * 8   # {fp32 value, u32 flag} per element (LL)
         flag_bytes = 2 * self.world * SYMM_MAX_TILES * 4
         self._local_recv, h_recv = self._C.symm_alloc(recv_bytes)
         self._local_flags, h_flags = self._C.symm_alloc(flag_bytes)
