@@ -272,7 +272,9 @@ at::Tensor topk_sample(const at::Tensor& logits, const at::Tensor& top_k, const 
 // ---- attention -----------------------------------------------------------------------------------------------------
 static int pick_nsplit(int B, int Hkv, int S_hint) {
   const int ctas = B * Hkv;
-  int want = (S_hint + 511) / 512;                  // ~512 keys per split
+  // short contexts: one 64-key tile per CTA (latency bound: tiles in parallel, not in sequence);
+  // long contexts: ~4 tiles per CTA once the chip is full
+  int want = S_hint <= 2048 ? (S_hint + 63) / 64 : (S_hint + 255) / 256;
   int cap = std::max(1, (2 * 148) / std::max(ctas, 1));  // fill the chip, not more
   return std::max(1, std::min({want, cap, 64}));
 }

@@ -1,13 +1,16 @@
-// GEMV v2: bulk-async (TMA 1-D, UBLKCP) mbarrier-pipelined, stream-K balanced weight-streaming skinny GEMM
+// GEMV v2: TMA (3-D tensor map, UTMALDG) mbarrier-pipelined, stream-K balanced weight-streaming skinny GEMM
 //          Y[T<=8, N] = f( rmsnorm(X)[T,K] · W[N,K]^T )      (+ fused one-shot all-reduce over NVLink)
 //
 // Why a second design (v1 = gemv.cuh, register-staged LDG): ncu on v1 showed warps >90 % stalled on
 // long-scoreboard with DRAM at 51-64 % — in-flight bytes were bounded by registers (2 stages x 8 LDG.128 per
 // warp) and a 16-row tile granularity left 15-35 % of the chip idle in the last wave.  v2 fixes both:
-//   * ONE producer warp streams W with cp.async.bulk (global -> shared, completion on an mbarrier): a stage is
-//     16 weight rows x 256 k (8 KB); up to 20 stages (160 KB) are in flight per SM, independent of registers;
+//   * ONE elected producer thread streams W with TMA tensor loads (cp.async.bulk.tensor.3d, completion on an
+//     mbarrier): W[N,K] is described as a 3-D tensor {64 k, K/64 groups, N rows}; one instruction fetches the box
+//     {64, 4, 16} = 16 weight rows x 256 k = 8 KB into a 128B-swizzled stage; up to 24 stages (192 KB) are in
+//     flight per SM, independent of registers.  (A first version issued sixteen 512-byte 1-D bulk copies per
+//     stage and was TMA-issue bound at 1.4 TB/s — see profiles/.)
 //   * 8 consumer warps wait on the stage's full-barrier, take their 32-k slice as mma.sync A fragments straight
-//     from shared memory (row pitch 512+64 B keeps the 8-lane LDS.128 phases bank-conflict free), multiply with
+//     from shared memory (the 128B swizzle keeps the 8-lane LDS.128 phases bank-conflict free), multiply with
 //     the token fragments of X (RMS-normalised in the prologue, bf16 in shared memory) and release the stage;
 //   * stream-K: the flattened (tile, k-chunk) space is cut into gridDim equal contiguous ranges, so every SM
 //     streams the same number of bytes; a tile that straddles CTAs is finished by the last arriver (atomic
@@ -18,6 +21,7 @@
 //     flag, no fence.sys round trip and no CTA barrier on the critical path.  Slots are self-resetting and
 //     double-buffered by call parity (see parallel/symm.py).
 #include <algorithm>
+#include <string>
 
 #include "api.h"
 #include "common.cuh"
@@ -27,9 +31,9 @@ namespace nxdi {
 constexpr int G2_CONSUMER_WARPS = 8;
 constexpr int G2_THREADS = (G2_CONSUMER_WARPS + 1) * 32;  // + producer warp
 constexpr int G2_KC = 256;                                 // k elements per stage
-constexpr int G2_ROW_PITCH = G2_KC * 2 + 64;               // bytes
-constexpr int G2_STAGE_BYTES = 16 * G2_ROW_PITCH;          // 9216
-constexpr int G2_MAX_STAGES = 20;
+constexpr int G2_STAGE_BYTES = 16 * G2_KC * 2;             // 8192, 128B-swizzled [16 rows][4 groups][64 k]
+constexpr int G2_MAX_STAGES = 24;
+constexpr int G2_SMEM_BUDGET = 224 * 1024;  // dynamic; leaves room for the few static __shared__ words
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -56,12 +60,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
 }
+// element offset (bf16) of 16-byte chunk `chunk` (0..7) of 128-byte line `line` inside a 128B-swizzled stage
+__device__ __forceinline__ int swz128(int line, int chunk) { return line * 64 + ((chunk ^ (line & 7)) << 3); }
 __device__ __forceinline__ void st_ll(float* p, float v, uint32_t flag) {  // 8-byte {value, flag}: single-copy atomic
   asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(flag) : "memory");
 }
@@ -73,6 +80,7 @@ __device__ __forceinline__ void ld_ll(const float* p, float& v, uint32_t& flag) 
 }
 
 struct Gemv2Params {
+  CUtensorMap tmap;   // W as {64, K/64, N}, box {64, 4, 16 (8 for GLU)}, SWIZZLE_128B
   GemvParams g;
   float* ws_part;     // [n_tiles * p_max][128] fp32 stream-K partials
   unsigned* tickets;  // [n_tiles]
@@ -81,7 +89,7 @@ struct Gemv2Params {
 };
 
 template <bool GLU, int MODE>
-__global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const Gemv2Params pp) {
+__global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const __grid_constant__ Gemv2Params pp) {
   const GemvParams& p = pp.g;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,8 +101,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const Gemv2Params 
   const __nv_bfloat16* RES = reinterpret_cast<const __nv_bfloat16*>(p.residual);
   __nv_bfloat16* Y = reinterpret_cast<__nv_bfloat16*>(p.y);
 
-  // shared memory carve-up: [stages][16][pitch] | xs[T][2K+64] | red[8][128] f32 | rstd[64] f32 | barriers
-  uint8_t* stage_base = smem_raw;
+  // shared memory carve-up (stage_base 1024-aligned for the 128B swizzle):
+  //   [stages][8 KB] | xs[T][2K+64] | red[8][128] f32 | rstd[64] f32 | barriers
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int xs_stride = K * 2 + 64;
   uint8_t* xs = stage_base + (size_t)NS * G2_STAGE_BYTES;
   float* red = reinterpret_cast<float*>(xs + (size_t)T * xs_stride);
@@ -112,33 +121,32 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const Gemv2Params 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], G2_CONSUMER_WARPS);
+      mbar_init(&empty_bar[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (warp == G2_CONSUMER_WARPS) {
-    // =========================== producer warp: stream W with bulk async copies ===========================
+    // =========================== producer: one elected thread drives the TMA ===========================
     pdl_launch_dependents();
-    const int r = lane & 15;
-    long long i = 0;
-    for (long long u = u_beg; u < u_end; ++u, ++i) {
-      const int tile = (int)(u / n_chunks), chunk = (int)(u % n_chunks);
-      const int stage = (int)(i % NS);
-      const uint32_t ph = (uint32_t)((i / NS) & 1);
-      mbar_wait(&empty_bar[stage], ph ^ 1u);
-      if (lane == 0) mbar_expect_tx(&full_bar[stage], 16 * G2_KC * 2);
-      __syncwarp();
-      if (lane < 16) {
-        int row;
-        if (GLU) {
-          row = r < 8 ? min(tile * 8 + r, (N >> 1) - 1) : min((N >> 1) + tile * 8 + (r - 8), N - 1);
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&pp.tmap) : "memory");
+      int tile = (int)(u_beg / n_chunks), chunk = (int)(u_beg % n_chunks), stage = 0;
+      uint32_t ph = 0;
+      const int count = (int)(u_end - u_beg);
+      for (int i = 0; i < count; ++i) {
+        mbar_wait(&empty_bar[stage], ph ^ 1u);
+        mbar_expect_tx(&full_bar[stage], G2_STAGE_BYTES);
+        uint8_t* dst = stage_base + (size_t)stage * G2_STAGE_BYTES;
+        if (GLU) {  // 8 gate rows then 8 up rows (rows past the end are zero-filled by the TMA unit)
+          tma_load_3d(dst, &pp.tmap, 0, chunk * 4, tile * 8, &full_bar[stage]);
+          tma_load_3d(dst + G2_STAGE_BYTES / 2, &pp.tmap, 0, chunk * 4, (N >> 1) + tile * 8, &full_bar[stage]);
         } else {
-          row = min(tile * 16 + r, N - 1);
+          tma_load_3d(dst, &pp.tmap, 0, chunk * 4, tile * 16, &full_bar[stage]);
         }
-        bulk_g2s(stage_base + (size_t)stage * G2_STAGE_BYTES + r * G2_ROW_PITCH, W + (size_t)row * K + chunk * G2_KC,
-                 G2_KC * 2, &full_bar[stage]);
+        if (++chunk == n_chunks) { chunk = 0; ++tile; }
+        if (++stage == NS) { stage = 0; ph ^= 1u; }
       }
     }
     return;
@@ -238,34 +246,47 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const Gemv2Params 
     }
   };
 
-  long long i = 0;
+  // Each consumer warp owns whole stages (local unit i -> warp i % 8): 8 k-iterations of 32 per stage, one
+  // barrier wait and one release per 8 KB.  A tile's units are spread over the warps; the flush joins them.
+  const int count = (int)(u_end - u_beg);
   int cur_tile = (int)(u_beg / n_chunks);
-  long long tile_u0 = u_beg;  // first unit of the current tile handled by this CTA
-  for (long long u = u_beg; u < u_end; ++u, ++i) {
-    const int chunk = (int)(u % n_chunks);
-    const int stage = (int)(i % NS);
-    const uint32_t ph = (uint32_t)((i / NS) & 1);
-    mbar_wait(&full_bar[stage], ph);
-    const uint8_t* sA = stage_base + (size_t)stage * G2_STAGE_BYTES + warp * 64 + t4 * 16;
-    const uint4 a0 = *reinterpret_cast<const uint4*>(sA + g * G2_ROW_PITCH);
-    const uint4 a1 = *reinterpret_cast<const uint4*>(sA + (g + 8) * G2_ROW_PITCH);
-    uint4 xv = make_uint4(0u, 0u, 0u, 0u);
-    if (tok_ok) xv = *reinterpret_cast<const uint4*>(xrow + (size_t)(chunk * G2_KC + warp * 32 + t4 * 8) * 2);
-    {
-      const uint32_t a[4] = {a0.x, a1.x, a0.y, a1.y};
-      const uint32_t b[2] = {xv.x, xv.y};
-      mma_bf16_16816(c0, a, b);
+  int chunk_first = (int)(u_beg % n_chunks);  // chunk index of local unit `seg_beg`
+  int seg_beg = 0;                             // local index of the first unit of the current tile segment
+  long long tile_u0 = u_beg;
+  while (seg_beg < count) {
+    const int seg_len = min(n_chunks - chunk_first, count - seg_beg);
+    const long long u = u_beg + seg_beg + seg_len - 1;  // last unit of this segment (global)
+    for (int i = seg_beg + ((warp - seg_beg) & 7); i < seg_beg + seg_len; i += G2_CONSUMER_WARPS) {
+      const int chunk = chunk_first + (i - seg_beg);
+      const int stage = i % NS;
+      const uint32_t ph = (uint32_t)((i / NS) & 1);
+      mbar_wait(&full_bar[stage], ph);
+      const __nv_bfloat16* sA = reinterpret_cast<const __nv_bfloat16*>(stage_base + (size_t)stage * G2_STAGE_BYTES);
+      const uint8_t* xk = xrow + (size_t)(chunk * G2_KC + t4 * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kg = j >> 1, ch = ((j & 1) << 2) + t4;
+        const uint4 a0 = *reinterpret_cast<const uint4*>(sA + swz128(g * 4 + kg, ch));
+        const uint4 a1 = *reinterpret_cast<const uint4*>(sA + swz128((g + 8) * 4 + kg, ch));
+        uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+        if (tok_ok) xv = *reinterpret_cast<const uint4*>(xk + j * 64);
+        {
+          const uint32_t a[4] = {a0.x, a1.x, a0.y, a1.y};
+          const uint32_t b[2] = {xv.x, xv.y};
+          mma_bf16_16816(c0, a, b);
+        }
+        {
+          const uint32_t a[4] = {a0.z, a1.z, a0.w, a1.w};
+          const uint32_t b[2] = {xv.z, xv.w};
+          mma_bf16_16816(c1, a, b);
+        }
+      }
+      // the warp-collective MMAs have consumed every lane's fragments: the stage can be refilled
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
     }
     {
-      const uint32_t a[4] = {a0.z, a1.z, a0.w, a1.w};
-      const uint32_t b[2] = {xv.z, xv.w};
-      mma_bf16_16816(c1, a, b);
-    }
-    // the warp-collective MMA has consumed every lane's fragments: the stage can be refilled
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
-    const bool tile_done = (chunk == n_chunks - 1) || (u + 1 == u_end);
-    if (!tile_done) continue;
-
+      const int chunk = chunk_first + seg_len - 1;
     // ---- flush: cross-warp reduce of the 16x8 tile ----
     float* r = red + warp * 128;
     r[g * 8 + 2 * t4] = c0[0] + c1[0];
@@ -322,8 +343,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const Gemv2Params 
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");  // red / s_flag reusable
+    }
     cur_tile += 1;
     tile_u0 = u + 1;
+    seg_beg += seg_len;
+    chunk_first = 0;
   }
 
   if (MODE == 1) {
@@ -371,11 +395,12 @@ static int g2_num_sms() {
 }
 
 static size_t g2_fixed_smem(int T, int K) {
-  return (size_t)T * (K * 2 + 64) + (G2_CONSUMER_WARPS * 128 + 64) * sizeof(float) + 2 * G2_MAX_STAGES * sizeof(uint64_t) + 128;
+  return (size_t)T * (K * 2 + 64) + (G2_CONSUMER_WARPS * 128 + 64) * sizeof(float) + 2 * G2_MAX_STAGES * sizeof(uint64_t) +
+         128 + 1024;  // + worst-case 1 KB alignment slack
 }
 
 bool gemv2_supported(int T, int K) {
-  return K % G2_KC == 0 && g2_fixed_smem(T, K) + 4 * G2_STAGE_BYTES <= 227 * 1024;
+  return K % G2_KC == 0 && g2_fixed_smem(T, K) + 4 * G2_STAGE_BYTES <= G2_SMEM_BUDGET;
 }
 
 int gemv2_grid(int N, int K, bool glu) {
@@ -394,7 +419,7 @@ static void launch_gemv2(const Gemv2Params& pp, cudaStream_t stream) {
   auto kern = gemv2_kernel<GLU, MODE>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BUDGET);
     configured = true;
   }
   const size_t smem = g2_fixed_smem(pp.g.T, pp.g.K) + (size_t)pp.n_stages * G2_STAGE_BYTES;
@@ -402,15 +427,53 @@ static void launch_gemv2(const Gemv2Params& pp, cudaStream_t stream) {
   launch_pdl(kern, dim3(grid), dim3(G2_THREADS), smem, stream, pp);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || p == nullptr) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// W [N, K] bf16 row-major as a 3-D tensor {64, K/64, N}; box {64, 4, rows}
+void make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K, int box_rows) {
+  cuuint64_t gdim[3] = {64, (cuuint64_t)(K / 64), (cuuint64_t)N};
+  cuuint64_t gstride[2] = {128, (cuuint64_t)K * 2};
+  cuuint32_t box[3] = {64, 4, (cuuint32_t)box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+}
+
 void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* tickets, cudaStream_t stream) {
   Gemv2Params pp;
   pp.g = p;
+  make_weight_tmap(&pp.tmap, p.w, p.N, p.K, p.act != 0 ? 8 : 16);
   pp.ws_part = ws_part;
   pp.tickets = tickets;
   const bool glu = p.act != 0;
   pp.p_max = gemv2_pmax(p.N, p.K, glu);
   const size_t fixed = g2_fixed_smem(p.T, p.K);
-  pp.n_stages = (int)std::min<size_t>(G2_MAX_STAGES, (227 * 1024 - fixed) / G2_STAGE_BYTES);
+  // Shared-memory budget per CTA.  Default ~half an SM so that two CONSECUTIVE kernels of the decode graph are
+  // co-resident: with PDL the next kernel's TMA producer fills its ring while this kernel drains (ncu/bench:
+  // a full-SM ring left a ~8 us bubble at every kernel boundary).
+  static int budget_kb = -1;
+  if (budget_kb < 0) {
+    const char* e = getenv("NXDI_B200_GEMV_SMEM_KB");
+    budget_kb = e ? atoi(e) : 110;
+  }
+  size_t budget = std::min<size_t>((size_t)budget_kb * 1024, G2_SMEM_BUDGET);
+  if (fixed + 4 * G2_STAGE_BYTES > budget) budget = std::min<size_t>(fixed + 6 * G2_STAGE_BYTES, G2_SMEM_BUDGET);
+  pp.n_stages = (int)std::min<size_t>(G2_MAX_STAGES, (budget - fixed) / G2_STAGE_BYTES);
   if (mode == 1) launch_gemv2<false, 1>(pp, stream);
   else if (glu) launch_gemv2<true, 0>(pp, stream);
   else launch_gemv2<false, 0>(pp, stream);

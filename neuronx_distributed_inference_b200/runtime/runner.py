@@ -70,6 +70,7 @@ class SubModelRunner:
         self.seq_buckets = sorted(set(self.seq_buckets))
         self.async_feedback = bool(nc.async_mode) and not is_prefill and n_active_tokens == 1
         self.n_launch = 0
+        self.collector = None   # utils.benchmark.LatencyCollector while benchmarking
 
     # ------------------------------------------------------------------------------------
     def reset(self):
@@ -132,7 +133,16 @@ class SubModelRunner:
         return p(input_ids, self.pad_token_id), p(attention_mask, 0), p(position_ids, 1), T
 
     # ------------------------------------------------------------------------------------
-    def __call__(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, _warmup=False, **kw):
+    def __call__(self, *a, **kw):
+        col = self.collector
+        if col is None:
+            return self._call(*a, **kw)
+        col.pre_hook()
+        out = self._call(*a, **kw)
+        col.hook()
+        return out
+
+    def _call(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, _warmup=False, **kw):
         B = input_ids.shape[0]
         if B > self.batch_size:
             # request larger than the compiled batch: run chunks sequentially (model_wrapper.py:1358-1423)
@@ -140,7 +150,7 @@ class SubModelRunner:
             for s in range(0, B, self.batch_size):
                 sl = slice(s, s + self.batch_size)
                 sub = {k: (v[sl] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in kw.items()}
-                outs.append(self(input_ids[sl], None if attention_mask is None else attention_mask[sl],
+                outs.append(self._call(input_ids[sl], None if attention_mask is None else attention_mask[sl],
                                  position_ids[sl], seq_ids[sl],
                                  None if sampling_params is None else sampling_params[sl], **sub))
             return _cat_outputs(outs)
