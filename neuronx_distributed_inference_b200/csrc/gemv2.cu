@@ -400,7 +400,7 @@ static size_t g2_fixed_smem(int T, int K) {
 }
 
 bool gemv2_supported(int T, int K) {
-  return K % G2_KC == 0 && g2_fixed_smem(T, K) + 4 * G2_STAGE_BYTES <= G2_SMEM_BUDGET;
+  return K % G2_KC == 0 && g2_fixed_smem(T, K) + 8 * G2_STAGE_BYTES <= G2_SMEM_BUDGET;
 }
 
 int gemv2_grid(int N, int K, bool glu) {
@@ -463,17 +463,18 @@ void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* ticke
   const bool glu = p.act != 0;
   pp.p_max = gemv2_pmax(p.N, p.K, glu);
   const size_t fixed = g2_fixed_smem(p.T, p.K);
-  // Shared-memory budget per CTA.  Default ~half an SM so that two CONSECUTIVE kernels of the decode graph are
-  // co-resident: with PDL the next kernel's TMA producer fills its ring while this kernel drains (ncu/bench:
-  // a full-SM ring left a ~8 us bubble at every kernel boundary).
+  // Ring depth: a MULTIPLE OF 8 stages.  Consumer warp w owns the units i == w (mod 8); with NS % 8 == 0 it always
+  // meets the same stages, lap after lap, so its mbarrier phase parity is unambiguous (with NS = 10 a warp could
+  // wait for lap 1 of a stage whose lap 0 had not completed yet and fall through: found on the TP=2 decode shapes).
   static int budget_kb = -1;
   if (budget_kb < 0) {
     const char* e = getenv("NXDI_B200_GEMV_SMEM_KB");
-    budget_kb = e ? atoi(e) : 110;
+    budget_kb = e ? atoi(e) : 224;
   }
-  size_t budget = std::min<size_t>((size_t)budget_kb * 1024, G2_SMEM_BUDGET);
-  if (fixed + 4 * G2_STAGE_BYTES > budget) budget = std::min<size_t>(fixed + 6 * G2_STAGE_BYTES, G2_SMEM_BUDGET);
-  pp.n_stages = (int)std::min<size_t>(G2_MAX_STAGES, (budget - fixed) / G2_STAGE_BYTES);
+  const size_t budget = std::min<size_t>((size_t)budget_kb * 1024, G2_SMEM_BUDGET);
+  int ns = budget > fixed ? (int)((budget - fixed) / G2_STAGE_BYTES) : 0;
+  ns = std::min(ns, G2_MAX_STAGES) / 8 * 8;
+  pp.n_stages = std::max(ns, 8);
   if (mode == 1) launch_gemv2<false, 1>(pp, stream);
   else if (glu) launch_gemv2<true, 0>(pp, stream);
   else launch_gemv2<false, 0>(pp, stream);

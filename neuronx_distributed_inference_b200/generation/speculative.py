@@ -1,0 +1,160 @@
+"""Speculative decoding: vanilla (separate draft application), fused (draft + target in one device step with
+on-device acceptance) and the host loops that drive them.
+
+reference: ``NeuronFusedSpecModel`` (models/model_base.py:1598-3021: ``_token_gen_forward`` :1812-1929,
+``_tkg_postprocessor`` :2799-2855) and the HF-adapter loops ``_standard_assisted_decoding`` /
+``_fused_assisted_decoding`` (utils/hf_adapter.py:495-797).
+
+Conventions (kept from the reference): ``speculation_length = k``; per step the draft proposes ``k-1`` tokens from
+the last accepted token, the target scores the ``k`` tokens ``[last, d1..d_{k-1}]`` in ONE forward with
+``n_active_tokens = k``, the longest matching prefix is accepted plus one bonus token from the target, and the
+step returns ``accepted_tokens`` padded with ``-1`` together with the next inputs — all computed on the device.
+KV caches are never rolled back: rejected positions are simply overwritten by the next step, because every
+kernel addresses the cache by absolute position.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+
+@torch.no_grad()
+def greedy_accept(draft_tokens: torch.Tensor, target_tokens: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """draft_tokens [B,k-1], target_tokens [B,k] (target's arg-max after each of the k inputs).
+    -> (accepted [B,k] padded with -1, n_accepted [B] in 1..k).  Pure tensor ops (graph capturable)."""
+    B, k = target_tokens.shape
+    if k == 1:
+        return target_tokens.clone(), torch.ones(B, dtype=torch.long, device=target_tokens.device)
+    match = (draft_tokens == target_tokens[:, : k - 1]).long()
+    n_match = match.cumprod(-1).sum(-1)                      # leading matches, 0..k-1
+    n_acc = n_match + 1                                       # + bonus token
+    ar = torch.arange(k, device=target_tokens.device).view(1, k)
+    accepted = torch.where(ar < n_acc.view(B, 1), target_tokens, torch.full_like(target_tokens, -1))
+    return accepted, n_acc
+
+
+class FusedSpeculativeModel(nn.Module):
+    """Draft + target in one step (role of ``NeuronFusedSpecModel``).  ``forward`` runs k-1 greedy draft steps, one
+    target verify over k tokens, the acceptance rule and the next-input derivation without any host
+    synchronisation, so the whole step is a single CUDA-graph replay."""
+
+    def __init__(self, target: nn.Module, draft: nn.Module, speculation_length: int):
+        super().__init__()
+        self.target_model = target
+        self.draft_model = draft
+        self.k = speculation_length
+
+    def reset(self):
+        self.target_model.reset()
+        self.draft_model.reset()
+
+    @torch.no_grad()
+    def prefill(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params=None, **kw):
+        """Context encoding of both models on the same prompt (reference :1750-1810); returns the target's token."""
+        out_t = self.target_model(input_ids, attention_mask, position_ids, seq_ids, sampling_params, is_prefill=True, **kw)
+        self.draft_model(input_ids, attention_mask, position_ids, seq_ids, None, is_prefill=True)
+        return out_t
+
+    @torch.no_grad()
+    def forward(self, last_token: torch.Tensor, position: torch.Tensor, seq_ids: torch.Tensor,
+                prev_token: torch.Tensor):
+        """last_token [B,1] at absolute ``position`` [B,1]; ``prev_token`` [B,1] is the token at ``position-1``.
+        The first draft step always feeds ``[prev_token, last_token]``: when the previous step accepted every
+        draft token the draft has not seen ``prev_token`` yet; otherwise it rewrites an identical KV entry, so no
+        host-side branching is needed and the step is shape-static."""
+        k = self.k
+        B = last_token.shape[0]
+        dev = last_token.device
+        cand = [last_token]
+        ids = torch.cat([prev_token, last_token], 1)
+        p2 = torch.cat([position - 1, position], 1)
+        out = self.draft_model(ids, None, p2, seq_ids, None, is_prefill=False, all_positions=True)
+        tok = _last_tokens(out)[:, -1:]
+        pos = position + 1
+        for i in range(k - 1):
+            cand.append(tok)
+            if i == k - 2:
+                break
+            out = self.draft_model(tok, None, pos, seq_ids, None, is_prefill=False)
+            tok = _last_tokens(out)[:, -1:]
+            pos = pos + 1
+        cand_ids = torch.cat(cand, 1)                                          # [B,k]
+        cand_pos = position + torch.arange(k, device=dev, dtype=position.dtype).view(1, k)
+        # ---- one target verify over the k tokens ----
+        out_t = self.target_model(cand_ids, None, cand_pos, seq_ids, None, is_prefill=False, all_positions=True)
+        tgt = _last_tokens(out_t)                                              # [B,k]
+        accepted, n_acc = greedy_accept(cand_ids[:, 1:], tgt)
+        # ---- next inputs on device (reference _tkg_postprocessor :2799-2855) ----
+        next_token = tgt.gather(1, (n_acc - 1).view(B, 1))
+        next_pos = position + n_acc.view(B, 1).to(position.dtype)
+        prev_in_step = tgt.gather(1, (n_acc - 2).clamp_min(0).view(B, 1))
+        next_prev = torch.where(n_acc.view(B, 1) >= 2, prev_in_step, last_token)
+        return accepted, n_acc, next_token, next_pos, next_prev, out_t
+
+
+def _last_tokens(out) -> torch.Tensor:
+    if out.tokens is not None:
+        t = out.tokens
+        return t.view(t.shape[0], -1)
+    return out.logits.argmax(-1)
+
+
+# ---- host loops ----------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def assisted_generate(adapter, input_ids, attention_mask, max_length, eos: List[int], pad_id: int, assistant_model=None,
+                      sampling_params=None, gc=None, return_dict_in_generate: bool = False):
+    """Greedy speculative generation.  ``assistant_model``: a separate draft application (vanilla speculation);
+    when the target was built with ``enable_fused_speculation`` its own fused model is used instead."""
+    model = adapter.neuron_model
+    nc = model.neuron_config
+    k = max(nc.speculation_length, 2)
+    B, P = input_ids.shape
+    fused = getattr(model, "fused_spec_model", None)
+    if fused is None:
+        if assistant_model is None:
+            raise ValueError("speculation needs a draft: pass assistant_model or enable_fused_speculation")
+        fused = FusedSpeculativeModel(model.model, assistant_model.model, k)
+    dev = model.device
+    model.reset()
+    if assistant_model is not None:
+        assistant_model.reset()
+    seq_ids = torch.arange(B, dtype=torch.int32, device=dev)
+    pos0 = (attention_mask.long().cumsum(-1) - 1).clamp_min(0).to(torch.int32)
+    out = fused.prefill(input_ids.to(dev), attention_mask.to(dev), pos0.to(dev), seq_ids)
+    tok = _last_tokens(out)[:, -1:].to(dev)
+    n_valid = attention_mask.sum(-1).view(B, 1).to(dev)
+    position = n_valid.to(torch.int32)           # position of `tok`
+    prev = input_ids.to(dev).gather(1, (n_valid.long() - 1).clamp_min(0))
+    rows = [input_ids[b, : int(n_valid[b])].tolist() + [int(tok[b])] for b in range(B)]
+    done = [int(tok[b]) in eos for b in range(B)]
+    stats = {"steps": 0, "accepted": 0}
+    while not all(done) and min(len(r) for r, d in zip(rows, done) if not d) < max_length:
+        accepted, n_acc, tok, position, prev, _ = fused(tok, position, seq_ids, prev)
+        acc = accepted.cpu()
+        stats["steps"] += 1
+        stats["accepted"] += int(n_acc.sum())
+        for b in range(B):
+            if done[b]:
+                continue
+            for t in acc[b].tolist():
+                if t < 0:
+                    break
+                if len(rows[b]) >= max_length:
+                    done[b] = True
+                    break
+                rows[b].append(t)
+                if t in eos:
+                    done[b] = True
+                    break
+            if len(rows[b]) >= max_length:
+                done[b] = True
+    width = max(len(r) for r in rows)
+    seqs = torch.full((B, width), pad_id, dtype=torch.long)
+    for b, r in enumerate(rows):
+        seqs[b, : len(r)] = torch.tensor(r)
+    if return_dict_in_generate:
+        from ..utils.hf_adapter import GenerateOutput
+        return GenerateOutput(sequences=seqs, speculation_stats=stats)
+    return seqs

@@ -1,0 +1,39 @@
+"""Model registry + task types (reference utils/constants.py:32-68, inference_demo.py:54-63)."""
+import importlib
+
+BENCHMARK_REPORT_FILENAME = "benchmark_report.json"
+TEST_PROMPT = "I believe the meaning of life is"
+
+_P = "neuronx_distributed_inference_b200.models"
+# model-type -> task -> "module:Class" (imported lazily)
+MODEL_TYPES = {
+    "llama": {"causal-lm": f"{_P}.llama.modeling_llama:NeuronLlamaForCausalLM"},
+    "mistral": {"causal-lm": f"{_P}.mistral.modeling_mistral:NeuronMistralForCausalLM"},
+    "qwen2": {"causal-lm": f"{_P}.qwen2.modeling_qwen2:NeuronQwen2ForCausalLM"},
+    "qwen3": {"causal-lm": f"{_P}.qwen3.modeling_qwen3:NeuronQwen3ForCausalLM"},
+    "gemma3": {"causal-lm": f"{_P}.gemma3.modeling_gemma3:NeuronGemma3ForCausalLM"},
+    "mixtral": {"causal-lm": f"{_P}.mixtral.modeling_mixtral:NeuronMixtralForCausalLM"},
+    "dbrx": {"causal-lm": f"{_P}.dbrx.modeling_dbrx:NeuronDbrxForCausalLM"},
+    "qwen3_moe": {"causal-lm": f"{_P}.qwen3_moe.modeling_qwen3_moe:NeuronQwen3MoeForCausalLM"},
+    "llama4": {"causal-lm": f"{_P}.llama4.modeling_llama4_text:NeuronLlama4TextForCausalLM",
+               "image-text-to-text": f"{_P}.llama4.modeling_llama4:NeuronLlama4ForCausalLM"},
+    "gpt_oss": {"causal-lm": f"{_P}.gpt_oss.modeling_gpt_oss:NeuronGptOssForCausalLM"},
+    "deepseek": {"causal-lm": f"{_P}.deepseek.modeling_deepseek:NeuronDeepseekForCausalLM"},
+    "mllama": {"image-text-to-text": f"{_P}.mllama.modeling_mllama:NeuronMllamaForCausalLM"},
+    "pixtral": {"image-text-to-text": f"{_P}.pixtral.modeling_pixtral:NeuronPixtralForCausalLM"},
+    "qwen2_vl": {"image-text-to-text": f"{_P}.qwen2_vl.modeling_qwen2_vl:NeuronQwen2VLForCausalLM"},
+    "qwen3_vl": {"image-text-to-text": f"{_P}.qwen3_vl.modeling_qwen3_vl:NeuronQwen3VLForCausalLM"},
+    "whisper": {"speech-to-text": f"{_P}.whisper.modeling_whisper:NeuronApplicationWhisper"},
+    "flux": {"text-to-image": f"{_P}.diffusers.flux.application:NeuronFluxApplication"},
+}
+TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
+
+
+def get_model_cls(model_type: str, task_type: str = "causal-lm"):
+    try:
+        ref = MODEL_TYPES[model_type][task_type]
+    except KeyError:
+        raise ValueError(f"unsupported model-type/task-type: {model_type}/{task_type}; "
+                         f"known: {sorted(MODEL_TYPES)}") from None
+    mod, cls = ref.split(":")
+    return getattr(importlib.import_module(mod), cls)

@@ -93,8 +93,9 @@ class HuggingFaceGenerationAdapter:
         """positions from the mask; after prefill only the last token is fed (reference :259-334)."""
         position_ids = (attention_mask.long().cumsum(-1) - 1).clamp_min(0)
         if not is_prefill:
-            input_ids = input_ids[:, -1:]
             position_ids = position_ids.amax(-1, keepdim=True)  # == valid length - 1
+            # right padding: the newest token of a row sits at its last VALID index, not in the last column
+            input_ids = input_ids.gather(1, position_ids.long())
         else:
             position_ids = position_ids.masked_fill(attention_mask == 0, 1)
         return input_ids, position_ids

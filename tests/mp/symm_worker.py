@@ -40,7 +40,8 @@ def main():
     log("workspace ok", [hex(p) for p in g.symm.recv_ptrs])
     torch.manual_seed(rank)
     worst = 0.0
-    for (T, N, K) in [(2, 4096, 512), (2, 4096, 1792), (1, 1024, 256), (8, 4096, 2048), (3, 40, 512)]:
+    for (T, N, K) in [(2, 4096, 512), (2, 4096, 1792), (1, 1024, 256), (8, 4096, 2048), (3, 40, 512), (2, 4096, 7168),
+                      (2, 4096, 2048), (2, 8192, 14336)]:
         x = torch.randn(T, K, device=dev, dtype=torch.bfloat16)
         w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
         res = torch.randn(T, N, device=dev, dtype=torch.bfloat16)

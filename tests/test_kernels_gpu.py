@@ -36,7 +36,8 @@ def test_rmsnorm(rows, H):
 
 
 @pytest.mark.parametrize("T", [1, 2, 3, 8])
-@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (1000 * 16, 2048), (4096, 14336), (512, 512), (40, 256)])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (1000 * 16, 2048), (4096, 14336), (512, 512), (40, 256),
+                                 (3072, 4096), (64128, 4096), (4096, 7168), (4096, 2048)])
 def test_gemv(T, N, K):
     x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16)
     w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
@@ -47,7 +48,7 @@ def test_gemv(T, N, K):
 
 
 @pytest.mark.parametrize("T", [1, 2, 5])
-@pytest.mark.parametrize("N,K", [(2 * 14336, 4096), (2 * 1792, 4096), (2 * 11008, 4096)])
+@pytest.mark.parametrize("N,K", [(2 * 14336, 4096), (2 * 1792, 4096), (2 * 11008, 4096), (14336, 4096)])
 def test_gemv_norm_swiglu(T, N, K):
     x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16) * 3
     g = (torch.randn(K, device=DEV) * 0.2 + 1).to(torch.bfloat16)
