@@ -10,7 +10,7 @@
 //   prefill: rows = 64 consecutive tokens of one q head
 // Row blocks of 16 map to warps (RBp in {1,2,4}); the remaining factor KS = 4/RBp splits the 64 keys of each
 // K/V tile between warps, so a 4-row decode step still uses all four warps.  K/V tiles stream through a
-// 2-stage cp.async pipeline into XOR-swizzled shared memory; QK^T and PV run on mma.sync m16n8k16 (bf16, fp32
+// 4-stage cp.async pipeline into XOR-swizzled shared memory; QK^T and PV run on mma.sync m16n8k16 (bf16, fp32
 // accumulate) with ldmatrix operand loads; softmax is online in the exp2 domain.  Split-KV partials go to a
 // workspace and the last CTA of a (batch, kv-head) — elected by an atomic ticket — combines them, so decode
 // attention is ONE launch regardless of context length.
@@ -24,6 +24,7 @@ namespace nxdi {
 enum { ATTN_DECODE = 0, ATTN_PAGED = 1, ATTN_PREFILL = 2 };
 constexpr int ATT_TILE = 64;
 constexpr int ATT_THREADS = 128;
+constexpr int ATT_STAGES = 4;  // cp.async ring depth: a <=256-key decode context is fetched in one go
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnArgs {
@@ -52,8 +53,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   constexpr int CH = D / 8;  // 16-byte chunks per row
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [64][D]
-  __nv_bfloat16* sK = sQ + 64 * D;                                 // [2][64][D]
-  __nv_bfloat16* sV = sK + 2 * 64 * D;                             // [2][64][D]
+  __nv_bfloat16* sK = sQ + 64 * D;                                 // [STAGES][64][D]
+  __nv_bfloat16* sV = sK + ATT_STAGES * 64 * D;                    // [STAGES][64][D]
   __shared__ float sM[4][16], sL[4][16];
   __shared__ int s_pos[64];
   __shared__ bool s_last;
@@ -153,8 +154,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
     }
   };
 
-  if (t_beg < t_end) load_tile(t_beg, 0);
-  cp_async_commit();
+#pragma unroll
+  for (int s = 0; s < ATT_STAGES - 1; ++s) {
+    if (t_beg + s < t_end) load_tile(t_beg + s, s);
+    cp_async_commit();  // one group per tile slot (possibly empty) keeps the wait arithmetic uniform
+  }
   __syncthreads();  // sQ visible
 
   uint32_t qf[D / 16][4];
@@ -176,14 +180,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
 
   for (int tile = t_beg; tile < t_end; ++tile) {
-    const int buf = (tile - t_beg) & 1;
-    if (tile + 1 < t_end) {
-      load_tile(tile + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    const int buf = (tile - t_beg) % ATT_STAGES;
+    if (tile + ATT_STAGES - 1 < t_end) load_tile(tile + ATT_STAGES - 1, (tile - t_beg + ATT_STAGES - 1) % ATT_STAGES);
+    cp_async_commit();
+    cp_async_wait<ATT_STAGES - 1>();
     __syncthreads();
     if (warp_active) {
       const __nv_bfloat16* tK = sK + buf * 64 * D;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
 template <int D, int MODE>
 static void launch_attn(const AttnArgs& a, dim3 grid, cudaStream_t stream) {
   auto kern = attention_kernel<D, MODE>;
-  const size_t smem = (size_t)(64 * D + 4 * 64 * D) * sizeof(__nv_bfloat16);
+  const size_t smem = (size_t)(64 * D + 2 * ATT_STAGES * 64 * D) * sizeof(__nv_bfloat16);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -274,7 +274,8 @@ static int pick_nsplit(int B, int Hkv, int S_hint) {
   const int ctas = B * Hkv;
   // short contexts: one 64-key tile per CTA (latency bound: tiles in parallel, not in sequence);
   // long contexts: ~4 tiles per CTA once the chip is full
-  int want = S_hint <= 2048 ? (S_hint + 63) / 64 : (S_hint + 255) / 256;
+  // (measured: splitting a <=512-key context costs more in the combine than the 4-deep tile prefetch hides)
+  int want = S_hint <= 512 ? 1 : (S_hint + 255) / 256;
   int cap = std::max(1, (2 * 148) / std::max(ctas, 1));  // fill the chip, not more
   return std::max(1, std::min({want, cap, 64}));
 }

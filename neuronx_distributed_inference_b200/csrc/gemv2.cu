@@ -89,7 +89,7 @@ struct Gemv2Params {
 };
 
 template <bool GLU, int MODE>
-__global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const __grid_constant__ Gemv2Params pp) {
+__global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_constant__ Gemv2Params pp) {
   const GemvParams& p = pp.g;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

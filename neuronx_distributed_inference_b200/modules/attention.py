@@ -55,6 +55,8 @@ class AttnMeta:
     adapter_ids: Optional[torch.Tensor] = None   # multi-LoRA
     rotary_position_ids: Optional[torch.Tensor] = None  # M-RoPE [3,B,T]
     capture: Optional[dict] = None               # tensor-capture sink
+    lines: Optional[torch.Tensor] = None         # cache lines of seq_ids (computed once per forward)
+    seq_hint: int = 0                            # upper bound on the live context (TKG bucket)
 
 
 class AttentionBase(nn.Module):
@@ -139,7 +141,9 @@ class AttentionBase(nn.Module):
         cos, sin = self._rope(meta)
         paged = meta.slot_mapping is not None
         k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
-        lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
+        if meta.lines is None:
+            meta.lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
+        lines = meta.lines
         fused = (self._simple() and not paged and qkv.is_cuda and k_cache.dtype == qkv.dtype
                  and (not meta.is_prefill or not meta.has_prefix))
         if fused:
@@ -149,7 +153,7 @@ class AttentionBase(nn.Module):
             if meta.is_prefill:
                 # prefill attention consumes the fresh k/v directly (no cache read): split here
                 q, k, v = self._split_norm_rope(qkv, B, T, cos, sin)
-                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions)
+                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)
             else:
                 q = ops.rope_kv_append(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, nq, nkv, D,
                                        False, qn, kn, self.qk_norm_eps)
@@ -158,7 +162,7 @@ class AttentionBase(nn.Module):
             if paged:
                 kv_mgr.update(self.layer_idx, k, v, meta.slot_mapping)
             else:
-                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions)
+                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)
         if meta.capture is not None:
             meta.capture[f"layers.{self.layer_idx}.self_attn.q"] = q
 
@@ -177,7 +181,8 @@ class AttentionBase(nn.Module):
             ks = getattr(kv_mgr, "k_scale", None)
             vs = getattr(kv_mgr, "v_scale", None)
             o = ops.attention_decode(q, k_cache, v_cache, lines, meta.position_ids, self.scale, self.sliding_window,
-                                     self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs)
+                                     self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs,
+                                     seq_hint=meta.seq_hint)
         o = o.reshape(B, T, nq * D)
         out = self.o_proj(o, residual)
         if lora is not None:

@@ -81,7 +81,7 @@ class KVCacheManager(nn.Module):
             return torch.where(bad, torch.full_like(seq_ids, self.num_lines), seq_ids)
         return seq_ids
 
-    def update(self, layer: int, k_new, v_new, seq_ids, positions):
+    def update(self, layer: int, k_new, v_new, seq_ids, positions, lines=None):
         """k_new/v_new [B,T,H,D]; positions [B,T] (negative => skip)."""
         k, v = self._k[layer], self._v[layer]
         if self.store_dtype != k_new.dtype:
@@ -90,9 +90,9 @@ class KVCacheManager(nn.Module):
             fi = torch.finfo(self.store_dtype)
             k_new = k_new.float().clamp(fi.min, fi.max).to(self.store_dtype)
             v_new = v_new.float().clamp(fi.min, fi.max).to(self.store_dtype)
-            ops.ref.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids), positions)
+            ops.ref.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
         else:
-            ops.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids), positions)
+            ops.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
 
     def bytes(self) -> int:
         return sum(b.numel() * b.element_size() for b in self.buffers())

@@ -81,8 +81,8 @@ class Sampler(nn.Module):
         g = self.tp_group
         if not self.vocab_shard:
             return ops.argmax(logits)
-        lf = logits.float()
-        val, idx = lf.max(-1)
+        idx = ops.argmax(logits)                                  # local arg-max kernel
+        val = logits.gather(1, idx.view(-1, 1)).view(-1).float()
         idx = idx + g.rank * logits.shape[-1]
         packed = torch.stack([val, idx.float()], -1)            # [B,2]
         allp = mappings.all_gather(packed.unsqueeze(0), 0, g)    # [tp,B,2]

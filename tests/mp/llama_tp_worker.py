@@ -14,7 +14,8 @@ def _hard_exit(code=0):
     """Tearing down NCCL communicators that were captured into CUDA graphs can block forever in
     destroy_process_group(); results are already printed, so flush and leave."""
     import torch
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(code)
