@@ -39,6 +39,9 @@ bool gemv2_supported(int T, int K);
 int gemv2_grid(int N, int K, bool glu);
 int gemv2_pmax(int N, int K, bool glu);
 void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* tickets, cudaStream_t stream);
+// tcgen05 / TMEM / TMA GEMM (gemm_tcgen05.cu): C[M,N_out] = epi(A[M,K] · B[N,K]^T)
+void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
+                         int N, int K, int act, cudaStream_t stream);
 void rmsnorm_launch(const void* x, const void* res_in, const void* w, void* y, void* res_out, int rows, int H, float eps,
                     float offset, cudaStream_t stream);
 

@@ -128,6 +128,25 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
   return y;
 }
 
+// tcgen05 GEMM for T > 8 tokens (prefill, long speculation windows)
+at::Tensor gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias, int64_t act,
+                const c10::optional<at::Tensor>& residual) {
+  TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1));
+  TORCH_CHECK(is_bf16(x) && is_bf16(w) && x.stride(1) == 1 && w.is_contiguous());
+  const int M = x.size(0), K = x.size(1), N = w.size(0);
+  TORCH_CHECK(K % 64 == 0 && x.stride(0) % 8 == 0, "gemm: K must be a multiple of 64");
+  const bool glu = act != 0;
+  const int n_out = glu ? N / 2 : N;
+  TORCH_CHECK(n_out % 8 == 0 && (!glu || N % 2 == 0));
+  c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty({M, n_out}, x.options());
+  if (residual.has_value())
+    TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(0) == M && residual->size(1) == n_out && is_bf16(*residual));
+  gemm_tcgen05_launch(x.data_ptr(), (int)x.stride(0), w.data_ptr(), optr(bias), optr(residual), y.data_ptr(), n_out, M, N, K,
+                      (int)act, cur_stream());
+  return y;
+}
+
 // Row-parallel GEMV -> one-shot all-reduce over NVLink peer buffers -> +bias +residual.  ONE kernel.
 at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                           const c10::optional<at::Tensor>& residual, const std::vector<int64_t>& recv_ptrs,
@@ -355,6 +374,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm", &nxdi::rmsnorm);
   m.def("gemv", &nxdi::gemv);
   m.def("gemv_allreduce", &nxdi::gemv_allreduce);
+  m.def("gemm", &nxdi::gemm);
   m.def("symm_alloc", &nxdi::symm_alloc);
   m.def("symm_open", &nxdi::symm_open);
   m.def("symm_close", &nxdi::symm_close);

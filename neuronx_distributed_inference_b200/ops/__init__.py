@@ -20,6 +20,7 @@ stats = Counter()
 _ALLOW_FALLBACK = os.environ.get("NXDI_B200_ALLOW_TORCH_FALLBACK", "0") == "1"
 GEMV_MAX_TOKENS = 8      # CUDA-core weight-streaming kernel up to here
 _KERNELS_ENABLED = True
+_TCGEN05_GEMM = os.environ.get("NXDI_B200_TCGEN05_GEMM", "1") == "1"   # 0: cuBLAS for T > 8 (A/B baseline)
 
 
 def set_kernels_enabled(flag: bool):
@@ -82,13 +83,15 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
                 y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2)
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
-            if not wq and N % 128 == 0 and K % 64 == 0 and hasattr(_C(), "gemm"):
+            n_out = N // 2 if act is not None else N
+            if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM:
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
                 stats["gemm_tcgen05"] += 1
-                y = _C().gemm(x2.contiguous(), w, bias, _ACT_CODES[act])
+                r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
+                y = _C().gemm(x2.contiguous(), w, bias, _ACT_CODES[act], r2)
                 y = y.view(*x.shape[:-1], y.shape[-1])
-                return y if residual is None else y + residual
+                return y if (residual is None or r2 is not None) else y + residual
     y = ref.linear(x, w, bias, norm_weight, norm_eps, norm_offset, act, scale)
     return y if residual is None else y + residual
 

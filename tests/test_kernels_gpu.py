@@ -191,3 +191,27 @@ def test_topk_sample_matches_reference():
         got = ops.sample(logits, top_k, top_p, temp, rand, 256)
         exp = ref.sample(logits, top_k, top_p, temp, rand, 256)
         assert torch.equal(got, exp), (got, exp)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 6144, 4096), (256, 4096, 14336), (77, 1000 * 8, 512), (1024, 4096, 4096),
+                                   (9, 256, 256)])
+def test_gemm_tcgen05(M, N, K):
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    r = torch.randn(M, N, device=DEV, dtype=torch.bfloat16)
+    y = ops.linear(x, w, b, residual=r)
+    yr = ref.linear(x.float(), w.float(), b.float()) + r.float()
+    assert ops.stats["gemm_tcgen05"] > 0
+    assert y.shape == yr.shape and _rel(y, yr) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 2 * 14336, 4096), (100, 2 * 1792, 1024)])
+def test_gemm_tcgen05_norm_swiglu(M, N, K):
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16) * 2
+    g = (torch.randn(K, device=DEV) * 0.2 + 1).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    y = ops.linear(x, w, None, norm_weight=g, norm_eps=1e-5, act="silu_mul")
+    xn = ref.rmsnorm(x.float(), g.float(), 1e-5).to(torch.bfloat16).float()
+    yr = ref.linear(xn, w.float(), None, act="silu_mul")
+    assert y.shape == (M, N // 2) and _rel(y, yr) < 8e-3
