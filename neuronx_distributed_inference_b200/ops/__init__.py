@@ -75,16 +75,16 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
         N = w.shape[0]
         wq = w.dtype in (torch.int8, torch.float8_e4m3fn)
         ok_w = (w.dtype == x.dtype and scale is None) or (wq and scale is not None and scale.dim() == 1)
-        if ok_w and act in _ACT_CODES and K % 256 == 0 and w.is_contiguous():
+        if ok_w and act in _ACT_CODES and w.is_contiguous():
             x2 = x.reshape(T, K)
-            if T <= GEMV_MAX_TOKENS:
+            if T <= GEMV_MAX_TOKENS and K % 256 == 0:
                 stats["gemv"] += 1
                 r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
                 y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2)
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
             n_out = N // 2 if act is not None else N
-            if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM:
+            if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM and (T > GEMV_MAX_TOKENS or K % 256 != 0):
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
                 stats["gemm_tcgen05"] += 1
