@@ -280,9 +280,10 @@ def moe_route(router_logits, top_k: int, act: str = "softmax", normalize: bool =
 
 def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act: str = "silu_mul", expert_offset: int = 0,
                 gate_up_bias=None, down_bias=None, act_fn=None):
-    """Dropless expert MLPs.  x [N,H]; w_gate_up [E_local,H,2I] (gate | up on the last dim —
-    reference weight naming SURVEY §2.8); w_down [E_local,I,H]; experts owned here are
-    [expert_offset, expert_offset+E_local).  -> partial output [N,H] (sum over owned experts)."""
+    """Dropless expert MLPs.  x [N,H]; w_gate_up [E_local, 2I, H] ([gate; up] rows, K-major like nn.Linear — the
+    reference stores [E,H,2I]; K-major is what TMA/UMMA and the GEMV kernels stream); w_down
+    [E_local, H, I]; experts owned here are [expert_offset, expert_offset+E_local).
+    -> partial output [N,H] (sum over owned experts; all-reduce across expert/tensor shards outside)."""
     N, H = x.shape
     E = w_gate_up.shape[0]
     out = torch.zeros(N, H, dtype=torch.float32, device=x.device)
@@ -292,11 +293,11 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act: str = "silu_mul", exp
         if tok.numel() == 0:
             continue
         wt = (topk_w * sel).sum(-1)[tok]
-        h = x[tok] @ w_gate_up[e].to(x.dtype)
+        h = F.linear(x[tok], w_gate_up[e].to(x.dtype))
         if gate_up_bias is not None:
             h = h + gate_up_bias[e].to(h.dtype)
         h = act_fn(h) if act_fn is not None else activation(h, act)
-        y = h @ w_down[e].to(x.dtype)
+        y = F.linear(h, w_down[e].to(x.dtype))
         if down_bias is not None:
             y = y + down_bias[e].to(y.dtype)
         out[tok] += y.float() * wt.unsqueeze(-1)

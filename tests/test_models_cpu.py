@@ -35,7 +35,7 @@ def _hf_config(model_type):
     if model_type == "dbrx":
         return T.DbrxConfig(d_model=64, n_heads=4, n_layers=2, max_seq_len=256, vocab_size=160,
                             attn_config=dict(kv_n_heads=2, clip_qkv=8.0, rope_theta=10000.0),
-                            ffn_config=dict(ffn_hidden_size=64, moe_num_experts=4, moe_top_k=2))
+                            ffn_config=dict(ffn_hidden_size=64, moe_num_experts=4, moe_top_k=2, hidden_size=64))
     if model_type == "gpt_oss":
         return T.GptOssConfig(**{**BASE, "num_hidden_layers": 2}, head_dim=16, num_local_experts=4, num_experts_per_tok=2,
                               sliding_window=8, layer_types=["sliding_attention", "full_attention"])
@@ -51,11 +51,24 @@ def _hf_config(model_type):
     raise KeyError(model_type)
 
 
-FAMILIES = ["llama", "mistral", "qwen2", "qwen3", "gemma3"]
+FAMILIES = ["llama", "mistral", "qwen2", "qwen3", "gemma3", "mixtral", "qwen3_moe", "dbrx"]
+
+
+def _patch_hf_dbrx():
+    """transformers 5.x evaluates the DBRX experts as ``x @ w1`` / ``h @ w2.T`` on ``[I,H]`` slices, which only
+    type-checks when I == H and is the transpose of the released checkpoints' semantics (``x @ w1.T``, ``h @ w2``:
+    databricks/dbrx modeling code, reference modeling_dbrx.py:51-112).  Restore the checkpoint semantics for the oracle."""
+    from transformers.models.dbrx import modeling_dbrx as m
+
+    def forward(self, x, expert_w1, expert_v1, expert_w2):
+        return (self.activation_fn(x.matmul(expert_w1.t())) * x.matmul(expert_v1.t())).matmul(expert_w2)
+    m.DbrxExpertGLU.forward = forward
 
 
 def run_family(model_type, tmp_path, tol=2e-4, **nc_kw):
     from transformers import AutoModelForCausalLM
+    if model_type == "dbrx":
+        _patch_hf_dbrx()
     hf_cfg = _hf_config(model_type)
     ckpt = save_random_hf_checkpoint(hf_cfg, str(tmp_path / model_type), seed=1)
     hf = AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32).eval()
