@@ -24,7 +24,6 @@ namespace nxdi {
 enum { ATTN_DECODE = 0, ATTN_PAGED = 1, ATTN_PREFILL = 2 };
 constexpr int ATT_TILE = 64;
 constexpr int ATT_THREADS = 128;
-constexpr int ATT_STAGES = 4;  // cp.async ring depth: a <=256-key decode context is fetched in one go
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnArgs {
@@ -48,7 +47,9 @@ __device__ __forceinline__ int swz(int row, int chunk) {  // element offset of a
   return row * D + ((chunk ^ (row & 7)) << 3);
 }
 
-template <int D, int MODE>
+// ATT_STAGES: cp.async ring depth.  4 for short decode contexts (a <=256-key context is fetched in one go, the step is
+// latency bound); 2 elsewhere (80 KB of shared memory -> two CTAs per SM, which the bandwidth/FLOP-bound cases need).
+template <int D, int MODE, int ATT_STAGES>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p) {
   constexpr int CH = D / 8;  // 16-byte chunks per row
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -362,9 +363,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   if (tid == 0) p.tickets[bh] = 0;  // re-arm for the next launch / graph replay
 }
 
-template <int D, int MODE>
+template <int D, int MODE, int ATT_STAGES>
 static void launch_attn(const AttnArgs& a, dim3 grid, cudaStream_t stream) {
-  auto kern = attention_kernel<D, MODE>;
+  auto kern = attention_kernel<D, MODE, ATT_STAGES>;
   const size_t smem = (size_t)(64 * D + 2 * ATT_STAGES * 64 * D) * sizeof(__nv_bfloat16);
   static bool configured = false;
   if (!configured) {
@@ -393,10 +394,13 @@ void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream) {
   if (p.T * (p.Hq / p.Hkv) > 64) throw std::runtime_error("attention_decode: T * group size must be <= 64");
   dim3 grid(p.B * p.Hkv, p.nsplit);
   const bool paged = p.block_table != nullptr;
+  const bool deep = p.nsplit == 1;  // short context, single split: latency bound -> deep prefetch
   if (p.D == 128) {
-    if (paged) launch_attn<128, ATTN_PAGED>(a, grid, stream); else launch_attn<128, ATTN_DECODE>(a, grid, stream);
+    if (paged) { if (deep) launch_attn<128, ATTN_PAGED, 4>(a, grid, stream); else launch_attn<128, ATTN_PAGED, 2>(a, grid, stream); }
+    else { if (deep) launch_attn<128, ATTN_DECODE, 4>(a, grid, stream); else launch_attn<128, ATTN_DECODE, 2>(a, grid, stream); }
   } else if (p.D == 64) {
-    if (paged) launch_attn<64, ATTN_PAGED>(a, grid, stream); else launch_attn<64, ATTN_DECODE>(a, grid, stream);
+    if (paged) { if (deep) launch_attn<64, ATTN_PAGED, 4>(a, grid, stream); else launch_attn<64, ATTN_PAGED, 2>(a, grid, stream); }
+    else { if (deep) launch_attn<64, ATTN_DECODE, 4>(a, grid, stream); else launch_attn<64, ATTN_DECODE, 2>(a, grid, stream); }
   } else {
     throw std::runtime_error("attention_decode: head_dim must be 64 or 128");
   }
@@ -412,8 +416,8 @@ void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream) {
   a.B = p.B; a.T = p.T; a.Hq = p.Hq; a.Hkv = p.Hkv; a.nsplit = 1; a.window = p.window;
   a.scale_log2 = p.scale * kLog2e;
   dim3 grid(p.B * p.Hq * ((p.T + 63) / 64));
-  if (p.D == 128) launch_attn<128, ATTN_PREFILL>(a, grid, stream);
-  else if (p.D == 64) launch_attn<64, ATTN_PREFILL>(a, grid, stream);
+  if (p.D == 128) launch_attn<128, ATTN_PREFILL, 2>(a, grid, stream);
+  else if (p.D == 64) launch_attn<64, ATTN_PREFILL, 2>(a, grid, stream);
   else throw std::runtime_error("attention_prefill: head_dim must be 64 or 128");
 }
 

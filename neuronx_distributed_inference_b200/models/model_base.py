@@ -78,6 +78,25 @@ class NeuronBaseModel(nn.Module):
         self.setup_attr_for_model(config)
         self.init_model(config)
         self.init_inference_optimization(config)
+        # CUDA-graph capture needs every op of the decode step to be sync-free: true for the hand-written kernel path
+        # (bf16, head_dim 64/128); the PyTorch composite fallbacks (odd head dims, fp8 KV, expert dispatch) are not.
+        self.graph_safe = bool(getattr(type(self), "graph_safe", True)) and self._kernels_cover_decode()
+
+    def _kernels_cover_decode(self) -> bool:
+        nc = self.neuron_config
+        if nc.torch_dtype != torch.bfloat16 or nc.kv_cache_quant or nc.is_block_kv_layout and False:
+            return False
+        for layer in self.layers:
+            attn = getattr(layer, "self_attn", None)
+            if attn is None:
+                continue
+            if getattr(attn, "head_dim", 128) not in (64, 128):
+                return False
+            if getattr(attn, "attention_chunk_size", None) is not None or getattr(attn, "softcap", None):
+                return False
+            if hasattr(attn, "_simple") and not attn._simple():
+                return False
+        return True
 
     # hooks ---------------------------------------------------------------------------------
     def setup_attr_for_model(self, config):

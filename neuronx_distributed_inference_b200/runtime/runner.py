@@ -61,7 +61,8 @@ class SubModelRunner:
         self.is_prefill = is_prefill
         self.device = device
         self.forward_kwargs = forward_kwargs or {}
-        self.use_graphs = (device.type == "cuda" and nc.cuda_graphs and not is_prefill)
+        self.use_graphs = (device.type == "cuda" and nc.cuda_graphs and not is_prefill
+                           and bool(getattr(model, "graph_safe", True)))
         self._graphs: Dict[Tuple, _Graph] = {}
         self.pad_token_id = getattr(config, "pad_token_id", None) or nc.pad_token_id or 0
         self.batch_buckets = sorted(set((nc.token_generation_batches or []) + [batch_size])) \

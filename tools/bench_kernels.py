@@ -18,7 +18,7 @@ except Exception:
     pass
 
 
-def timeit(fn, iters=20, flush=None):
+def timeit(fn, iters=12, flush=None):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -59,6 +59,20 @@ def main():
                              frac_hbm=gb / ms * 1e3 / PEAKS["hbm_gbs"], cublas_ms=ms_t))
             print(f"gemv {name:14s} T={T} N={N:6d} K={K:5d}  {ms*1e3:8.1f} us  {gb/ms*1e3:7.0f} GB/s "
                   f"({gb/ms*1e3/PEAKS['hbm_gbs']*100:5.1f}% of measured HBM)   cuBLAS {ms_t*1e3:8.1f} us")
+    # prefill GEMM on tcgen05 vs cuBLAS
+    for (M, N, K, name) in [(256, 6144, 4096, "qkv"), (256, 28672, 4096, "gate_up+swiglu"), (256, 4096, 14336, "down"),
+                            (2048, 6144, 4096, "qkv"), (2048, 28672, 4096, "gate_up+swiglu"), (2048, 4096, 14336, "down"),
+                            (8192, 8192, 8192, "square")]:
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(torch.bfloat16)
+        act = "silu_mul" if "swiglu" in name else None
+        ms = timeit(lambda: ops.linear(x, w, None, act=act), iters=10)
+        ms_t = timeit(lambda: torch.nn.functional.linear(x, w), iters=10)
+        fl = 2.0 * M * N * K
+        rows.append(dict(kernel="gemm_tcgen05", shape=name, M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9,
+                         frac_bf16=fl / ms / 1e9 / PEAKS["bf16_tflops"], cublas_ms=ms_t, cublas_tflops=fl / ms_t / 1e9))
+        print(f"gemm {name:15s} M={M:5d} N={N:6d} K={K:6d} {ms*1e3:9.1f} us {fl/ms/1e9:7.1f} TFLOP/s "
+              f"({fl/ms/1e9/PEAKS['bf16_tflops']*100:5.1f}% of measured cuBLAS peak)   cuBLAS {ms_t*1e3:9.1f} us {fl/ms_t/1e9:7.1f}")
     # decode attention
     for (B, Hq, Hkv, S) in [(2, 32, 8, 256), (2, 32, 8, 4096), (2, 32, 8, 32768), (2, 4, 1, 4096), (32, 32, 8, 4096)]:
         D = 128
