@@ -167,7 +167,7 @@ class GroupQueryAttention_QKV(BaseParallelLinear):
         if self.sequence_parallel_enabled:
             x = mappings.all_gather(x, self.sequence_dimension, self.tensor_parallel_group)
         return ops.linear(x, self.weight, self.bias, norm_weight=norm_weight, norm_eps=norm_eps,
-                          norm_offset=norm_offset)
+                          norm_offset=norm_offset, scale=getattr(self, "scale", None))
 
 
 class GroupQueryAttention_O(BaseParallelLinear):
@@ -205,10 +205,12 @@ class GroupQueryAttention_O(BaseParallelLinear):
     def forward(self, x, residual=None):
         g = self.tensor_parallel_group
         if g.size == 1:
-            return ops.linear(x, self.weight, self.bias, residual=residual)
+            return ops.linear(x, self.weight, self.bias, residual=residual, scale=getattr(self, "scale", None))
         if self.sequence_parallel_enabled:
-            y = mappings.reduce_scatter(ops.linear(x, self.weight, None), self.sequence_dimension, g)
+            y = mappings.reduce_scatter(ops.linear(x, self.weight, None, scale=getattr(self, "scale", None)),
+                                        self.sequence_dimension, g)
             if self.bias is not None:
                 y = y + self.bias
             return y if residual is None else y + residual
-        return ops.linear_allreduce(x, self.weight, self.bias, g, residual=residual, reduce_dtype=self.reduce_dtype)
+        return ops.linear_allreduce(x, self.weight, self.bias, g, residual=residual, reduce_dtype=self.reduce_dtype,
+                                    scale=getattr(self, "scale", None))

@@ -79,7 +79,7 @@ class ColumnParallelLinear(BaseParallelLinear):
             x = mappings.all_gather(x, self.sequence_dimension, self.tensor_parallel_group)
         bias = None if self.skip_bias_add else self.bias
         y = ops.linear(x, self.weight, bias, norm_weight=norm_weight, norm_eps=norm_eps,
-                       norm_offset=norm_offset, act=act)
+                       norm_offset=norm_offset, act=act, scale=getattr(self, "scale", None))
         if self.gather_output:
             y = mappings.all_gather(y, -1, self.tensor_parallel_group)
             if self.pad_size:
@@ -126,15 +126,16 @@ class RowParallelLinear(BaseParallelLinear):
         if not self.input_is_parallel:
             x = mappings.scatter_to_region(x, -1, g)
         if g.size == 1 or not self.reduce_output:
-            return ops.linear(x, self.weight, self.bias if g.size == 1 or g.rank == 0 else None, residual=residual)
+            return ops.linear(x, self.weight, self.bias if g.size == 1 or g.rank == 0 else None, residual=residual,
+                              scale=getattr(self, "scale", None))
         if self.sequence_parallel_enabled:
-            y = ops.linear(x, self.weight, None)
+            y = ops.linear(x, self.weight, None, scale=getattr(self, "scale", None))
             y = mappings.reduce_scatter(y, self.sequence_dimension, g)
             if self.bias is not None:
                 y = y + self.bias
             return y if residual is None else y + residual
         return ops.linear_allreduce(x, self.weight, self.bias, g, residual=residual,
-                                    reduce_dtype=self.reduce_dtype)
+                                    reduce_dtype=self.reduce_dtype, scale=getattr(self, "scale", None))
 
 
 class ParallelEmbedding(nn.Module):
