@@ -177,6 +177,10 @@ def measure(app, batch, ctx, steps, warmup, n_ttft=9):
             pin_ids.copy_(tok.view(batch, 1)); pin_pos.copy_(pos)
             tok = app(pin_ids, position_ids=pin_pos).tokens.cpu()   # D2H read of the step result
             pos += 1
+    if os.environ.get("NXDI_BENCH_PROFILE_E2E"):
+        import cProfile, pstats
+        pr = cProfile.Profile(); pr.enable(); e2e_loop(); pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(18)
     e2e_ms = device_time_ms(e2e_loop)
     h2d = pin_ids.numel() * 8 + pin_pos.numel() * 4 + batch * 4 + batch * 12  # ids, positions, seq_ids, sampling params
     d2h = batch * 8

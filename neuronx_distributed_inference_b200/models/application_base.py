@@ -369,8 +369,8 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
                 position_ids = (attention_mask.long().cumsum(-1) - 1).clamp_min(0)
             else:
                 position_ids = torch.arange(input_ids.shape[-1]).unsqueeze(0).expand(B, -1)
-        if attention_mask is None:
-            attention_mask = self._infer_attention_mask(position_ids)
+        if attention_mask is None and input_ids.shape[-1] > 1 and position_ids.device.type == "cpu":
+            attention_mask = self._infer_attention_mask(position_ids)   # decode (T == 1) never needs a mask
         if seq_ids is None:
             seq_ids = torch.arange(B, dtype=torch.int32)
         if sampling_params is None:
@@ -414,7 +414,7 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
     def _is_prefill(position_ids, computed_context_lens=None) -> bool:
         if computed_context_lens is not None:
             return True
-        return bool(position_ids.min().item() == 0)
+        return min(position_ids[:, 0].tolist()) == 0
 
     def _construct_output(self, out: ModelOutput) -> CausalLMOutput:
         res = CausalLMOutput(logits=out.logits, tokens=out.tokens, hidden_states=out.hidden_states,

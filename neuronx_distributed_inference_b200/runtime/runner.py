@@ -201,7 +201,7 @@ class SubModelRunner:
                                   is_prefill=False, **kwargs)
         Bb = self._pick_batch_bucket(B)
         if position_ids.device.type == "cpu":
-            cur = int(position_ids.max()) + 1
+            cur = max(map(max, position_ids.tolist())) + 1   # plain Python: torch reductions on pinned tensors cost ms
         else:
             cur = self.seq_buckets[-1] - 1  # device-resident inputs: no sync, take the largest bucket
         sb = self.get_target_bucket(cur)
