@@ -152,13 +152,13 @@ class AttentionBase(nn.Module):
             k = v = None
             if meta.is_prefill:
                 # prefill attention consumes the fresh k/v directly (no cache read): split here
-                q, k, v = self._split_norm_rope(qkv, B, T, cos, sin)
+                q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
                 kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)
             else:
                 q = ops.rope_kv_append(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, nq, nkv, D,
                                        False, qn, kn, self.qk_norm_eps)
         else:
-            q, k, v = self._split_norm_rope(qkv, B, T, cos, sin)
+            q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
             if paged:
                 kv_mgr.update(self.layer_idx, k, v, meta.slot_mapping)
             else:
@@ -194,7 +194,7 @@ class AttentionBase(nn.Module):
         starts take the masked path."""
         return self.neuron_config.padding_side == "right" and not getattr(meta, "offset_positions", False)
 
-    def _split_norm_rope(self, qkv, B, T, cos, sin):
+    def _split_norm_rope(self, qkv, B, T, cos, sin, meta=None):
         D, nq, nkv = self.head_dim, self.n_q, self.n_kv
         q, k, v = qkv.reshape(B, T, nq + 2 * nkv, D).split([nq, nkv, nkv], dim=2)
         if self.qk_norm == "rms_pre_rope":

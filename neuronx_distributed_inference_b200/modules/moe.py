@@ -92,9 +92,9 @@ class ExpertMLPs(nn.Module):
         else:
             self.gate_up_bias = self.down_bias = None
 
-    def forward(self, x2: torch.Tensor, topk_w: torch.Tensor, topk_i: torch.Tensor) -> torch.Tensor:
+    def forward(self, x2: torch.Tensor, topk_w: torch.Tensor, topk_i: torch.Tensor, scale_input: bool = False) -> torch.Tensor:
         return ops.moe_experts(x2, self.gate_up_proj, self.down_proj, topk_w, topk_i, self.act, self.expert_offset,
-                               self.gate_up_bias, self.down_bias, self.act_fn)
+                               self.gate_up_bias, self.down_bias, self.act_fn, scale_input)
 
 
 class MoE(nn.Module):
@@ -125,9 +125,7 @@ class MoE(nn.Module):
         if self.return_expert_index:
             self.last_expert_index = idx
         if self.early_affinity_modulation:
-            # top-1 style (Llama-4): y = expert(x * affinity)
-            assert w.shape[-1] == 1
-            y = self.expert_mlps((x2.float() * w).to(x2.dtype), torch.ones_like(w), idx)
+            y = self.expert_mlps(x2, w.to(torch.float32), idx, scale_input=True)   # Llama-4: y = sum_j expert_j(x * w_j)
         else:
             y = self.expert_mlps(x2, w.to(torch.float32), idx)
         if self.shared_experts is not None:

@@ -224,16 +224,17 @@ def moe_route(router_logits, top_k, act="softmax", normalize=True, act_over_topk
 
 
 def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_offset=0,
-                gate_up_bias=None, down_bias=None, act_fn=None):
+                gate_up_bias=None, down_bias=None, act_fn=None, scale_input=False):
     N = x.shape[0]
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and w_gate_up.dtype == x.dtype and act == "silu_mul"
-            and act_fn is None and gate_up_bias is None and down_bias is None and N <= GEMV_MAX_TOKENS
+            and act_fn is None and gate_up_bias is None and down_bias is None and N <= GEMV_MAX_TOKENS and not scale_input
+            and hasattr(_C(), "moe_decode")
             and x.shape[1] % 256 == 0 and w_down.shape[1] % 256 == 0):
         stats["moe_decode"] += 1
         return _C().moe_decode(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(),
                                topk_i.to(torch.int32).contiguous(), int(expert_offset))
     return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias,
-                           act_fn)
+                           act_fn, scale_input)
 
 
 def rmsnorm_quant(x, weight, eps, clamp=float("inf")):

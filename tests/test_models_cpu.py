@@ -42,7 +42,8 @@ def _hf_config(model_type):
     if model_type == "llama4":
         return T.Llama4TextConfig(**{**BASE, "num_hidden_layers": 4}, head_dim=16, num_local_experts=4, num_experts_per_tok=1,
                                   intermediate_size_mlp=128, interleave_moe_layer_step=2, attention_chunk_size=8,
-                                  no_rope_layers=[1, 1, 1, 0], use_qk_norm=True)
+                                  no_rope_layers=[1, 1, 1, 0], use_qk_norm=True, attn_temperature_tuning=True, floor_scale=4,
+                                  attn_scale=0.1)
     if model_type == "deepseek":
         return T.DeepseekV3Config(**{**BASE, "num_hidden_layers": 2}, q_lora_rank=24, kv_lora_rank=16, qk_nope_head_dim=16,
                                   qk_rope_head_dim=8, v_head_dim=16, n_routed_experts=4, n_shared_experts=1,
@@ -51,7 +52,7 @@ def _hf_config(model_type):
     raise KeyError(model_type)
 
 
-FAMILIES = ["llama", "mistral", "qwen2", "qwen3", "gemma3", "mixtral", "qwen3_moe", "dbrx"]
+FAMILIES = ["llama", "mistral", "qwen2", "qwen3", "gemma3", "mixtral", "qwen3_moe", "dbrx", "gpt_oss", "llama4"]
 
 
 def _patch_hf_dbrx():
