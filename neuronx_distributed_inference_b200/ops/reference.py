@@ -173,7 +173,7 @@ def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
     ok = (line >= 0) & (line < L) & (pos >= 0) & (pos < S)
     line, pos = line[ok], pos[ok]
     kn = k_new.reshape(B * T, H, D)[ok].to(k_cache.dtype)
-    vn = v_new.reshape(B * T, H, D)[ok].to(v_cache.dtype)
+    vn = v_new.reshape(B * T, H, v_new.shape[-1])[ok].to(v_cache.dtype)   # V may have its own head dim (MLA)
     k_cache[line, :, pos] = kn
     v_cache[line, :, pos] = vn
 

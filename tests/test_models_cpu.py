@@ -52,7 +52,7 @@ def _hf_config(model_type):
     raise KeyError(model_type)
 
 
-FAMILIES = ["llama", "mistral", "qwen2", "qwen3", "gemma3", "mixtral", "qwen3_moe", "dbrx", "gpt_oss", "llama4"]
+FAMILIES = ["llama", "mistral", "qwen2", "qwen3", "gemma3", "mixtral", "qwen3_moe", "dbrx", "gpt_oss", "llama4", "deepseek"]
 
 
 def _patch_hf_dbrx():
