@@ -172,7 +172,14 @@ class SubModelRunner:
         dev = self.device
         if attention_mask is not None and attention_mask.shape[-1] != input_ids.shape[-1]:
             attention_mask = attention_mask[:, -input_ids.shape[-1]:]
+        T0 = input_ids.shape[1]
         ids, mask, pos, _ = self.pad_prefill(input_ids, attention_mask, position_ids)
+        sm = kw.get("slot_mapping")
+        if sm is not None and ids.shape[1] != T0:
+            # padded tokens must not be written: slot -1 (reference pads the slot mapping the same way)
+            fill = torch.full((sm.shape[0], ids.shape[1] - T0), -1, dtype=sm.dtype, device=sm.device)
+            left = self.neuron_config.padding_side == "left"
+            kw["slot_mapping"] = torch.cat([fill, sm], 1) if left else torch.cat([sm, fill], 1)
         if mask is not None and mask.device.type == "cpu" and bool(mask.all()):
             mask = None   # no padding anywhere: skip the mask plumbing (decided on the host, no device sync)
         self.n_launch += 1

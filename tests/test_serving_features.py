@@ -1,0 +1,106 @@
+"""Serving features at the application level: continuous batching by seq_ids, masked rows, paged KV cache with slot
+mapping / block tables, prefix caching, batch larger than the compiled batch, async token feedback flag."""
+import torch
+
+from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+
+TINY = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+            vocab_size=128, head_dim=16)
+
+
+def _greedy(app, ids, steps, seq_ids=None, **kw):
+    out = app(ids, attention_mask=torch.ones_like(ids), seq_ids=seq_ids, **kw)
+    toks = [out.tokens.clone()]
+    pos = torch.full((ids.shape[0], 1), ids.shape[1], dtype=torch.int32)
+    for _ in range(steps):
+        out = app(toks[-1].view(-1, 1), position_ids=pos, seq_ids=seq_ids)
+        toks.append(out.tokens.clone())
+        pos = pos + 1
+    return torch.stack(toks, 1)
+
+
+def test_continuous_batching_seq_ids_and_masked_rows():
+    app = build_random_llama(TINY, batch_size=3, seq_len=48, max_context_length=16, device="cpu", dtype="float32",
+                             is_continuous_batching=True, ctx_batch_size=1, kv_cache_batch_size=3, apply_seq_ids_mask=True)
+    ids = torch.randint(0, 128, (3, 8))
+    ref = _greedy(app, ids, 5)                     # lines 0,1,2 in order
+    app.reset()
+    # prefill one sequence at a time into shuffled cache lines, then decode them together in another order
+    order = [2, 0, 1]
+    first = {}
+    for b, line in enumerate(order):
+        o = app(ids[b:b + 1], attention_mask=torch.ones(1, 8, dtype=torch.long), seq_ids=torch.tensor([line], dtype=torch.int32))
+        first[line] = o.tokens
+    seq = torch.tensor([1, 2, 0], dtype=torch.int32)   # rows -> cache lines
+    tok = torch.cat([first[int(s)] for s in seq])
+    rows = {int(s): [int(first[int(s)])] for s in seq}
+    pos = torch.full((3, 1), 8, dtype=torch.int32)
+    for _ in range(5):
+        o = app(tok.view(3, 1), position_ids=pos, seq_ids=seq)
+        tok = o.tokens
+        for r, s in enumerate(seq.tolist()):
+            rows[s].append(int(tok[r]))
+        pos = pos + 1
+    for b, line in enumerate(order):
+        assert rows[line] == ref[b].tolist()
+    # a masked row (seq_id -1) must not disturb the live cache lines
+    o1 = app(tok.view(3, 1), position_ids=pos, seq_ids=torch.tensor([1, -1, 0], dtype=torch.int32))
+    o2 = app(tok.view(3, 1), position_ids=pos, seq_ids=torch.tensor([1, 2, 0], dtype=torch.int32))
+    assert o1.tokens[0] == o2.tokens[0] and o1.tokens[2] == o2.tokens[2]
+
+
+def test_batch_larger_than_compiled_batch_is_split():
+    app = build_random_llama(TINY, batch_size=2, seq_len=32, max_context_length=16, device="cpu", dtype="float32",
+                             kv_cache_batch_size=4, max_batch_size=4)
+    ids = torch.randint(0, 128, (4, 6))
+    seq = torch.arange(4, dtype=torch.int32)
+    big = _greedy(app, ids, 3, seq_ids=seq)
+    app.reset()
+    a = _greedy(app, ids[:2], 3, seq_ids=seq[:2])
+    b = _greedy(app, ids[2:], 3, seq_ids=seq[2:])
+    assert torch.equal(big, torch.cat([a, b]))
+
+
+def _slots(block_table, positions, bs):
+    blk = torch.gather(block_table.long(), 1, (positions.long() // bs))
+    return (blk * bs + positions.long() % bs).int()
+
+
+def test_paged_kv_matches_contiguous_and_prefix_caching():
+    cont = build_random_llama(TINY, batch_size=2, seq_len=64, max_context_length=32, device="cpu", dtype="float32", seed=5)
+    paged = build_random_llama(TINY, batch_size=2, seq_len=64, max_context_length=32, device="cpu", dtype="float32", seed=5,
+                               is_block_kv_layout=True, pa_block_size=8, pa_num_blocks=24)
+    ids = torch.randint(0, 128, (2, 12))
+    ref = _greedy(cont, ids, 6)
+    bt = torch.tensor([[3, 9, 1, 20, 7, 2, 0, 11], [5, 4, 13, 6, 8, 10, 12, 14]], dtype=torch.int32)
+    pos = torch.arange(12).unsqueeze(0).expand(2, 12)
+    out = paged(ids, attention_mask=torch.ones_like(ids), position_ids=pos, slot_mapping=_slots(bt, pos, 8), block_table=bt)
+    toks = [out.tokens.clone()]
+    p = torch.full((2, 1), 12, dtype=torch.int32)
+    for _ in range(6):
+        out = paged(toks[-1].view(2, 1), position_ids=p, slot_mapping=_slots(bt, p, 8), block_table=bt)
+        toks.append(out.tokens.clone())
+        p = p + 1
+    assert torch.equal(torch.stack(toks, 1), ref)
+    # prefix caching: the first 8 tokens are already cached in blocks; encode only the remaining 4
+    paged.reset()
+    pre = ids[:, :8]
+    ppos = torch.arange(8).unsqueeze(0).expand(2, 8)
+    paged(pre, attention_mask=torch.ones_like(pre), position_ids=ppos, slot_mapping=_slots(bt, ppos, 8), block_table=bt)
+    rest = ids[:, 8:]
+    rpos = (torch.arange(4) + 8).unsqueeze(0).expand(2, 4)
+    out = paged(rest, attention_mask=torch.ones_like(rest), position_ids=rpos, slot_mapping=_slots(bt, rpos, 8), block_table=bt,
+                computed_context_lens=torch.tensor([8, 8]), full_context_lens=torch.tensor([12, 12]))
+    assert torch.equal(out.tokens, ref[:, 0])
+
+
+def test_slot_mapping_generators():
+    from neuronx_distributed_inference_b200.modules.kvcache import (generate_fusedspec_slot_mapping,
+                                                                   generate_tokengen_slot_mapping, get_active_block_table)
+    bt = torch.tensor([[3, 9, 1], [5, 4, 13]], dtype=torch.int32)
+    pos = torch.tensor([[9], [17]])
+    sm = generate_tokengen_slot_mapping(pos, torch.zeros(2, 1, dtype=torch.int32), bt, 8)
+    assert sm.tolist() == [[9 * 8 + 1], [13 * 8 + 1]]
+    sm = generate_fusedspec_slot_mapping(torch.tensor([[6], [6]]), torch.zeros(2, 3, dtype=torch.int32), bt, 8, 3)
+    assert sm[0].tolist() == [3 * 8 + 6, 3 * 8 + 7, 9 * 8 + 0]
+    assert get_active_block_table(bt, torch.tensor([9, 3]), 8).tolist() == [3, 9, 5]
