@@ -225,7 +225,11 @@ class NeuronApplicationBase(nn.Module):
         pass
 
     def _post_load(self, model):
-        pass
+        lc = self.neuron_config.lora_config
+        if lc is not None and hasattr(model, "layers"):
+            from ..modules.lora import LoraModel, LoraModelManager
+            model.lora = LoraModel(model, lc, device=self.device)
+            self.lora_manager = LoraModelManager(model.lora, lc)
 
     def _attach_symmetric_workspace(self):
         nc = self.neuron_config

@@ -55,7 +55,11 @@ class DecoderLayer(nn.Module):
                            norm_offset=n1.offset, residual=h, lora=lora)
         if meta.capture is not None:
             meta.capture[f"layers.{self.layer_idx}.attn_out"] = h
-        h = self.mlp(h, norm_weight=n2.weight, norm_eps=n2.variance_epsilon, norm_offset=n2.offset, residual=h)
+        if lora is not None and not self.mlp_is_moe:
+            h = self.mlp(h, norm_weight=n2.weight, norm_eps=n2.variance_epsilon, norm_offset=n2.offset, residual=h, lora=lora,
+                         adapter_ids=meta.adapter_ids)
+        else:
+            h = self.mlp(h, norm_weight=n2.weight, norm_eps=n2.variance_epsilon, norm_offset=n2.offset, residual=h)
         if meta.capture is not None:
             meta.capture[f"layers.{self.layer_idx}.out"] = h
         return h
@@ -199,9 +203,9 @@ class NeuronBaseModel(nn.Module):
         h = self.embed(input_ids, inputs_embeds, vision_embeddings, vision_mask)
         if prev_hidden is not None and hasattr(self, "fuse_prev_hidden"):
             h = self.fuse_prev_hidden(h, prev_hidden)
-        lora = getattr(self, "lora", None)
-        for layer in self.layers:
-            h = layer(h, meta, self.kv_mgr, lora=lora) if lora is not None else layer(h, meta, self.kv_mgr)
+        lora = getattr(self, "lora", None) if meta.adapter_ids is not None else None
+        for i, layer in enumerate(self.layers):
+            h = layer(h, meta, self.kv_mgr, lora=lora.for_layer(i)) if lora is not None else layer(h, meta, self.kv_mgr)
         # ---- last-token gather (prefill) ------------------------------------------------------
         if is_prefill and not all_positions:
             if meta.key_valid is not None and self.padding_side == "right":

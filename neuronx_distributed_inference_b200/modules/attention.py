@@ -133,9 +133,10 @@ class AttentionBase(nn.Module):
         B, T, _ = hidden.shape
         D, nq, nkv = self.head_dim, self.n_q, self.n_kv
         qkv = self.qkv_proj(hidden, norm_weight, norm_eps if norm_eps is not None else self.rms_norm_eps, norm_offset)
-        if lora is not None:
-            qkv = qkv + lora("qkv_proj", ops.rmsnorm(hidden, norm_weight, norm_eps, norm_offset)
-                             if norm_weight is not None else hidden, meta.adapter_ids)
+        if lora is not None and lora.has("qkv_proj"):
+            xn = ops.rmsnorm(hidden, norm_weight, norm_eps if norm_eps is not None else self.rms_norm_eps, norm_offset) \
+                if norm_weight is not None else hidden
+            qkv = qkv + lora("qkv_proj", xn, meta.adapter_ids)
         if self.clip_qkv is not None:
             qkv = qkv.clamp(-self.clip_qkv, self.clip_qkv)
         cos, sin = self._rope(meta)
@@ -185,8 +186,9 @@ class AttentionBase(nn.Module):
                                      seq_hint=meta.seq_hint)
         o = o.reshape(B, T, nq * D)
         out = self.o_proj(o, residual)
-        if lora is not None:
-            out = out + lora("o_proj", o, meta.adapter_ids)
+        if lora is not None and lora.has("o_proj"):
+            from ..parallel import mappings as _m
+            out = out + _m.all_reduce(lora("o_proj", o, meta.adapter_ids), self.tp_group)
         return out
 
     def _arange_pos(self, meta: AttnMeta) -> bool:

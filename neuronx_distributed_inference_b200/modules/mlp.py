@@ -39,6 +39,17 @@ class GatedMLP(nn.Module):
                                            reduce_dtype=reduce_dtype)
 
     def forward(self, x, norm_weight=None, norm_eps=1e-6, norm_offset=0.0, residual=None, lora=None, adapter_ids=None):
+        if lora is not None and adapter_ids is not None and (lora.has("gate_up_proj") or lora.has("down_proj")):
+            # LoRA deltas enter before the activation / before the reduction: take the un-fused route
+            xn = ops.rmsnorm(x, norm_weight, norm_eps, norm_offset) if norm_weight is not None else x
+            gu = self.gate_up_proj(xn) + lora("gate_up_proj", xn, adapter_ids)
+            h = ops.activation(gu, self.act)
+            y = self.down_proj(h, residual)
+            d = lora("down_proj", h, adapter_ids)
+            if not isinstance(d, int):
+                from ..parallel import mappings
+                y = y + mappings.all_reduce(d, self.down_proj.tensor_parallel_group)
+            return y
         h = self.gate_up_proj(x, norm_weight=norm_weight, norm_eps=norm_eps, norm_offset=norm_offset, act=self.act)
         return self.down_proj(h, residual)
 
