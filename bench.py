@@ -241,6 +241,11 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
+    # Libraries (NCCL banner, HF progress bars) print to stdout; the contract is ONE JSON line there.  Route fd 1 to stderr
+    # for the whole run and keep the real stdout for the result line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from neuronx_distributed_inference_b200.parallel import state as pstate
@@ -296,7 +301,8 @@ def main():
     if ci is not None:
         out["ci_4layer"] = ci
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if dist.is_initialized():
         dist.barrier()
         _hard_exit()

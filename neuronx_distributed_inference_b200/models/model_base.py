@@ -84,7 +84,13 @@ class NeuronBaseModel(nn.Module):
         self.init_inference_optimization(config)
         # CUDA-graph capture needs every op of the decode step to be sync-free: true for the hand-written kernel path
         # (bf16, head_dim 64/128); the PyTorch composite fallbacks (odd head dims, fp8 KV, expert dispatch) are not.
-        self.graph_safe = bool(getattr(type(self), "graph_safe", True)) and self._kernels_cover_decode()
+        self.graph_safe = bool(getattr(type(self), "graph_safe", True)) and (self._kernels_cover_decode() or self._fallback_is_sync_free())
+
+    def _fallback_is_sync_free(self) -> bool:
+        """Dense decoder on the contiguous cache with a garbage line: the PyTorch composite path has no host sync either."""
+        nc = self.neuron_config
+        return (not nc.is_block_kv_layout and not nc.kv_cache_quant and getattr(self.kv_mgr, "garbage", 0) == 1
+                and not any(getattr(l, "mlp_is_moe", False) for l in self.layers))
 
     def _kernels_cover_decode(self) -> bool:
         nc = self.neuron_config

@@ -90,9 +90,26 @@ class KVCacheManager(nn.Module):
             fi = torch.finfo(self.store_dtype)
             k_new = k_new.float().clamp(fi.min, fi.max).to(self.store_dtype)
             v_new = v_new.float().clamp(fi.min, fi.max).to(self.store_dtype)
-            ops.ref.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
-        else:
+            self._append_torch(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
+        elif k_new.is_cuda and (self.head_dim * k_new.element_size()) % 16 == 0:
             ops.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
+        else:
+            self._append_torch(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
+
+    def _append_torch(self, k, v, k_new, v_new, lines, positions):
+        """PyTorch cache write without data-dependent shapes (CUDA-graph capturable): skipped entries (masked line or
+        padding position) are redirected to slot 0 of the garbage line instead of being filtered out."""
+        if not self.garbage:
+            return ops.ref.kv_append(k, v, k_new, v_new, lines, positions)
+        B, T = positions.shape
+        L, H, S, D = k.shape
+        line = lines.view(B, 1).expand(B, T).reshape(-1).long()
+        pos = positions.reshape(-1).long()
+        ok = (line >= 0) & (line < L) & (pos >= 0) & (pos < S)
+        line = torch.where(ok, line, torch.full_like(line, L - 1))
+        pos = torch.where(ok, pos, torch.zeros_like(pos))
+        k[line, :, pos] = k_new.reshape(B * T, H, D).to(k.dtype)
+        v[line, :, pos] = v_new.reshape(B * T, H, v_new.shape[-1]).to(v.dtype)
 
     def bytes(self) -> int:
         return sum(b.numel() * b.element_size() for b in self.buffers())

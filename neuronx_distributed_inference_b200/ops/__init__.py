@@ -142,12 +142,13 @@ def rope_kv_append(qkv, cos, sin, k_cache, v_cache, seq_ids, positions, n_q, n_k
         k = ref.rmsnorm(k, k_norm, norm_eps)
     q = ref.apply_rope(q, cos, sin, interleaved)
     k = ref.apply_rope(k, cos, sin, interleaved)
-    ref.kv_append(k_cache, v_cache, k, v, seq_ids, positions)
+    kv_append(k_cache, v_cache, k, v, seq_ids, positions)
     return q
 
 
 def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
-    if _use_cuda(k_new) and k_new.dtype in _FAST_DTYPES and k_cache.dtype == k_new.dtype:
+    if (_use_cuda(k_new) and k_new.dtype in _FAST_DTYPES and k_cache.dtype == k_new.dtype
+            and (k_new.shape[-1] * k_new.element_size()) % 16 == 0 and v_new.shape[-1] == k_new.shape[-1]):
         stats["kv_append"] += 1
         _C().kv_append(k_cache, v_cache, k_new.contiguous(), v_new.contiguous(), seq_ids.to(torch.int32),
                        positions.to(torch.int32))
