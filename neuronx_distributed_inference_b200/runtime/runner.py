@@ -72,6 +72,8 @@ class SubModelRunner:
         self.async_feedback = bool(nc.async_mode) and not is_prefill and n_active_tokens == 1
         self.n_launch = 0
         self.collector = None   # utils.benchmark.LatencyCollector while benchmarking
+        self.snapshot_hook = None   # utils.snapshot.SnapshotHook
+        self.on_new_request = None
 
     # ------------------------------------------------------------------------------------
     def reset(self):
@@ -145,6 +147,14 @@ class SubModelRunner:
 
     def _call(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, _warmup=False, **kw):
         B = input_ids.shape[0]
+        if self.snapshot_hook is not None and not _warmup:
+            if self.is_prefill and self.on_new_request is not None:
+                self.on_new_request()
+            h = self.snapshot_hook
+            if self.is_prefill:
+                h.request -= 1          # on_new_request advanced every runner; the hook itself advances on prefill
+            h(dict(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids, seq_ids=seq_ids,
+                   sampling_params=sampling_params), self.is_prefill)
         if B > self.batch_size:
             # request larger than the compiled batch: run chunks sequentially (model_wrapper.py:1358-1423)
             outs = []
