@@ -191,6 +191,7 @@ class NeuronApplicationBase(nn.Module):
             load_sharded(self.model, sd, nc.torch_dtype, strict=False)
         self._post_load(self.model)
         self._attach_symmetric_workspace()
+        self._build_speculation(random_weights, seed)
         self._build_runners()
         self.is_loaded_to_neuron = True
         logger.info("model loaded in %.1fs on %s", time.time() - t0, self.device)
@@ -230,6 +231,9 @@ class NeuronApplicationBase(nn.Module):
             from ..modules.lora import LoraModel, LoraModelManager
             model.lora = LoraModel(model, lc, device=self.device)
             self.lora_manager = LoraModelManager(model.lora, lc)
+
+    def _build_speculation(self, random_weights: bool = False, seed: int = 0):
+        pass
 
     def _attach_symmetric_workspace(self):
         nc = self.neuron_config
@@ -358,6 +362,64 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
             n_active_tokens=nc.speculation_length, is_prefill=False, device=self.device)
         self.models.append(self.speculation_model)
 
+    # ---- speculation ------------------------------------------------------------------------
+    def _build_speculation(self, random_weights: bool = False, seed: int = 0):
+        """Fused speculation (draft + target in one device step; reference ``enable_fused_spec`` model_base.py:3078-3105 and
+        the ``draft_model.`` / ``target_model.`` checkpoint split :3843-3900), EAGLE / EAGLE-3 / token tree, Medusa."""
+        nc = self.neuron_config
+        self.fused_spec_model = None
+        self.medusa_model = None
+        self.draft_model = None
+        if nc.is_medusa:
+            from ..generation.medusa import MedusaSpeculativeModel
+            self.medusa_model = MedusaSpeculativeModel(self.model, nc.medusa_tree)
+        fsc = getattr(self.config, "fused_spec_config", None)
+        if not nc.enable_fused_speculation or fsc is None:
+            return
+        dcfg = fsc.draft_config
+        draft_cls = fsc.draft_model_cls or fsc.worker_cls or self._model_cls
+        with torch.device(self.device):
+            draft = draft_cls(dcfg, device=self.device).eval()
+        if random_weights:
+            main, self.model = self.model, draft
+            try:
+                self.init_random_weights(seed + 17)
+            finally:
+                self.model = main
+        else:
+            sd = self._load_draft_state_dict(fsc, dcfg)
+            load_sharded(draft, sd, dcfg.neuron_config.torch_dtype, strict=False)
+        if dcfg.neuron_config.is_eagle_draft and not getattr(dcfg, "draft_vocab_size", None):
+            # EAGLE heads reuse the target's embedding and output projection (they ship without their own)
+            with torch.no_grad():
+                if random_weights or not getattr(self, "_draft_has_embed", False):
+                    draft.embed_tokens.load_state_dict(self.model.embed_tokens.state_dict())
+                if random_weights or not getattr(self, "_draft_has_lm_head", False):
+                    draft.lm_head.load_state_dict(self.model.lm_head.state_dict())
+        self.draft_model = draft
+        k = nc.speculation_length
+        if nc.enable_eagle_speculation:
+            from ..generation.eagle import EagleSpeculativeModel
+            tree = None
+            if nc.token_tree_config is not None:
+                from ..modules.eagle.token_tree import TokenTree
+                tree = TokenTree(nc.token_tree_config)
+            self.fused_spec_model = EagleSpeculativeModel(self.model, draft, k, nc.max_batch_size, tree)
+        else:
+            from ..generation.speculative import FusedSpeculativeModel
+            self.fused_spec_model = FusedSpeculativeModel(self.model, draft, k)
+
+    def _load_draft_state_dict(self, fsc, dcfg) -> dict:
+        from ..modules.checkpoint import load_state_dict as _load
+        sd = _load(fsc.draft_model_path)
+        sd = {self._strip(k): v for k, v in sd.items()}
+        self._draft_has_embed = any(k.startswith("embed_tokens.") for k in sd)
+        self._draft_has_lm_head = any(k.startswith("lm_head.") for k in sd)
+        sd = self.convert_hf_to_neuron_state_dict(sd, dcfg)
+        if getattr(dcfg, "tie_word_embeddings", False) and "lm_head.weight" not in sd and "embed_tokens.weight" in sd:
+            self.update_state_dict_for_tied_weights(sd)
+        return sd
+
     # ---- forward -----------------------------------------------------------------------------
     def _infer_attention_mask(self, position_ids):
         """mask[b, j] = j <= max position of row b (reference model_base.py:3485-3504)."""
@@ -431,6 +493,8 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
     def reset(self):
         super().reset()
         self.kv_cache_populated = False
+        if getattr(self, "fused_spec_model", None) is not None:
+            self.fused_spec_model.reset()
 
     def reset_kv_cache(self):
         self.reset()

@@ -134,7 +134,7 @@ class NeuronBaseModel(nn.Module):
         else:
             lines = nc.kv_cache_batch_size + nc.kv_cache_padding_size
             kw = dict(num_layers=n_layers, num_kv_heads=self.kv_heads_per_rank(), head_dim=self.kv_head_dim(),
-                      max_len=nc.max_length if not nc.speculation_length else nc.max_length + nc.speculation_length,
+                      max_len=nc.max_length + self._speculation_slack(),
                       num_lines=lines, dtype=dtype, device=self.device_,
                       quant_config=nc.kv_quant_config if nc.kv_cache_quant else None)
             if nc.attention_dp_degree > 1:
@@ -143,6 +143,20 @@ class NeuronBaseModel(nn.Module):
                 self.kv_mgr = DataParallelKVCacheManager(dp_rank=g.rank, dp_size=g.size, **kw)
             else:
                 self.kv_mgr = KVCacheManager(**kw)
+
+    def _speculation_slack(self) -> int:
+        """Extra cache slots past ``max_length``: a verify step writes every candidate (chain of k, or all tree nodes)
+        before acceptance."""
+        nc = self.neuron_config
+        extra = nc.speculation_length or 0
+        if nc.token_tree_config is not None or nc.is_medusa:
+            from ..modules.eagle.token_tree import TokenTree
+            if nc.token_tree_config is not None:
+                extra = max(extra, TokenTree(nc.token_tree_config).num_nodes)
+            if nc.is_medusa:
+                from ..generation.medusa import DEFAULT_MEDUSA_TREE
+                extra = max(extra, TokenTree(nc.medusa_tree or DEFAULT_MEDUSA_TREE).num_nodes)
+        return extra
 
     def lm_head_is_sharded(self) -> bool:
         return self.tp_group.size > 1 and not getattr(self.lm_head, "gather_output", True)
@@ -185,9 +199,11 @@ class NeuronBaseModel(nn.Module):
                 write = position_ids
         else:
             write = position_ids
+        if kw.get("write_positions") is not None:     # token trees: rotary position = depth, cache slot = node index
+            write = kw["write_positions"]
         meta = AttnMeta(is_prefill=is_prefill, position_ids=position_ids.to(torch.int32),
                         write_positions=write.to(torch.int32), seq_ids=seq_ids.to(torch.int32), key_valid=key_valid,
-                        active_mask=kw.get("active_mask"), slot_mapping=kw.get("slot_mapping"),
+                        active_mask=kw.get("active_mask"), active_base=kw.get("active_base"), slot_mapping=kw.get("slot_mapping"),
                         block_table=kw.get("block_table"), has_prefix=has_prefix,
                         adapter_ids=kw.get("adapter_ids"), rotary_position_ids=kw.get("rotary_position_ids"),
                         capture={} if kw.get("capture") else None)
@@ -200,7 +216,7 @@ class NeuronBaseModel(nn.Module):
                 sampling_params: Optional[torch.Tensor] = None, *, is_prefill: Optional[bool] = None,
                 prev_hidden: Optional[torch.Tensor] = None, inputs_embeds=None, vision_embeddings=None,
                 vision_mask=None, rand=None, output_logits: Optional[bool] = None, output_hidden: bool = False,
-                all_positions: bool = False, **kw) -> ModelOutput:
+                all_positions: bool = False, all_hidden: bool = False, **kw) -> ModelOutput:
         nc = self.neuron_config
         B, T = input_ids.shape[:2]
         if is_prefill is None:
@@ -210,8 +226,12 @@ class NeuronBaseModel(nn.Module):
         if prev_hidden is not None and hasattr(self, "fuse_prev_hidden"):
             h = self.fuse_prev_hidden(h, prev_hidden)
         lora = getattr(self, "lora", None) if meta.adapter_ids is not None else None
+        aux_layers = getattr(self, "aux_hidden_layers", None) if output_hidden else None
+        aux = []
         for i, layer in enumerate(self.layers):
             h = layer(h, meta, self.kv_mgr, lora=lora.for_layer(i)) if lora is not None else layer(h, meta, self.kv_mgr)
+            if aux_layers is not None and i in aux_layers:
+                aux.append(h)
         # ---- last-token gather (prefill) ------------------------------------------------------
         if is_prefill and not all_positions:
             if meta.key_valid is not None and self.padding_side == "right":
@@ -225,7 +245,15 @@ class NeuronBaseModel(nn.Module):
             h_out = h
         out = ModelOutput()
         if output_hidden:
-            out.hidden_states = self.final_hidden(h_out)
+            # EAGLE-3 targets export the concatenation of a low / middle / high layer (raw residual stream), EAGLE-1/2 the
+            # final normalised state; ``all_hidden`` keeps every prompt position (draft prefill) while logits stay last-only
+            src = h if all_hidden else h_out
+            if aux:
+                cat = torch.cat(aux, -1)
+                out.hidden_states = cat if (all_hidden or not (is_prefill and not all_positions)) else \
+                    cat[torch.arange(B, device=h.device), last.long()].unsqueeze(1)
+            else:
+                out.hidden_states = self.final_hidden(src)
         logits = self.compute_logits(h_out)
         want_logits = nc.output_logits if output_logits is None else output_logits
         if self.on_device_sampling:
@@ -237,7 +265,15 @@ class NeuronBaseModel(nn.Module):
         if want_logits or not self.on_device_sampling:
             out.logits = self.gather_logits(logits)
         out.captured = meta.capture
+        if getattr(self, "medusa_heads", None) is not None:
+            out.extras["medusa_logits"] = self.medusa_logits(h_out)
         return out
+
+    def medusa_logits(self, h_out):
+        """[num_heads, B, T, V]: every Medusa head = ResBlock(s) + its own vocab projection on the final hidden state
+        (reference model_base.py:478-508, modeling_llama.py:1172-1187)."""
+        hn = self.final_hidden(h_out)
+        return torch.stack([self.gather_logits(head(hn)) for head in self.medusa_heads], 0)
 
     def final_hidden(self, h):
         return self.norm(h)

@@ -47,7 +47,8 @@ class AttnMeta:
     cos: Optional[torch.Tensor] = None
     sin: Optional[torch.Tensor] = None
     rope_cache: dict = field(default_factory=dict)   # per-rotary-module (cos, sin)
-    active_mask: Optional[torch.Tensor] = None  # [B,T,T] token-tree visibility among active tokens
+    active_mask: Optional[torch.Tensor] = None  # [B,T,M] token-tree visibility of the M slots from active_base
+    active_base: Optional[torch.Tensor] = None  # [B,1] first slot covered by active_mask (default: first active slot)
     slot_mapping: Optional[torch.Tensor] = None  # paged: [B,T]
     block_table: Optional[torch.Tensor] = None   # paged: [B,max_blocks]
     prefix_len: Optional[torch.Tensor] = None    # [B] cached prefix tokens (prefix caching)
@@ -67,7 +68,7 @@ class AttentionBase(nn.Module):
                  learned_sinks: bool = False, softmax_scale: Optional[float] = None, rope_interleaved: bool = False,
                  use_rope: bool = True, logit_softcap: Optional[float] = None, layer_idx: int = 0,
                  tensor_model_parallel_group: Optional[Group] = None, sharding_strategy: Optional[GQA] = None,
-                 rms_norm_eps: float = 1e-6, device=None):
+                 rms_norm_eps: float = 1e-6, device=None, qkv_input_size: Optional[int] = None):
         super().__init__()
         nc = config.neuron_config
         self.config, self.neuron_config = config, nc
@@ -77,7 +78,7 @@ class AttentionBase(nn.Module):
         self.hidden_size, self.head_dim = hidden_size, head_dim
         self.num_attention_heads, self.num_key_value_heads = num_attention_heads, num_key_value_heads
         sp = nc.sequence_parallel_enabled
-        self.qkv_proj = GroupQueryAttention_QKV(hidden_size, head_dim, num_attention_heads, num_key_value_heads,
+        self.qkv_proj = GroupQueryAttention_QKV(qkv_input_size or hidden_size, head_dim, num_attention_heads, num_key_value_heads,
                                                 self.tp_group, dtype, qkv_bias, sharding_strategy, device,
                                                 sequence_parallel_enabled=sp)
         self.o_proj = GroupQueryAttention_O(hidden_size, head_dim, num_attention_heads, num_key_value_heads,
@@ -181,9 +182,11 @@ class AttentionBase(nn.Module):
         else:
             ks = getattr(kv_mgr, "k_scale", None)
             vs = getattr(kv_mgr, "v_scale", None)
-            o = ops.attention_decode(q, k_cache, v_cache, lines, meta.position_ids, self.scale, self.sliding_window,
+            # token trees: visibility is defined on cache slots (node index), rotary positions are depths
+            vis_pos = meta.write_positions if meta.active_mask is not None else meta.position_ids
+            o = ops.attention_decode(q, k_cache, v_cache, lines, vis_pos, self.scale, self.sliding_window,
                                      self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs,
-                                     seq_hint=meta.seq_hint)
+                                     seq_hint=meta.seq_hint, active_base=meta.active_base)
         o = o.reshape(B, T, nq * D)
         out = self.o_proj(o, residual)
         if lora is not None and lora.has("o_proj"):

@@ -111,6 +111,22 @@ class KVCacheManager(nn.Module):
         k[line, :, pos] = k_new.reshape(B * T, H, D).to(k.dtype)
         v[line, :, pos] = v_new.reshape(B * T, H, v_new.shape[-1]).to(v.dtype)
 
+    def move(self, seq_ids: torch.Tensor, src: torch.Tensor, dst: torch.Tensor):
+        """Compact accepted tree nodes: for every layer copy slot ``src[b,j]`` to ``dst[b,j]`` of line ``seq_ids[b]``
+        (negative src/dst => no-op, realised as a self-copy of slot 0 on the garbage line).  One gather + one scatter over
+        the whole ``[layers, 2, ...]`` allocation; static shapes, capture-safe.  Role of the reference's accepted-index KV
+        gather/scatter for Medusa / token trees (kv_cache_manager.py ``accepted_indices`` / ``current_length``)."""
+        B, n = src.shape
+        line = self.lines_for(seq_ids).view(B, 1).expand(B, n).long()
+        ok = (src >= 0) & (dst >= 0)
+        Lg = self.num_lines + self.garbage - 1
+        line = torch.where(ok, line, torch.full_like(line, Lg)).reshape(-1)
+        s = torch.where(ok, src, torch.zeros_like(src)).long().reshape(-1)
+        d = torch.where(ok, dst, torch.zeros_like(dst)).long().reshape(-1)
+        for c in ([self.cache] if hasattr(self, "cache") else [self.cache_k.unsqueeze(1), self.cache_v.unsqueeze(1)]):
+            vals = c[:, :, line, :, s]              # [B*n, layers, 2, H, D] (advanced indices first)
+            c[:, :, line, :, d] = vals
+
     def bytes(self) -> int:
         return sum(b.numel() * b.element_size() for b in self.buffers())
 

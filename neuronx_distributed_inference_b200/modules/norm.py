@@ -40,3 +40,14 @@ class LayerNorm(nn.LayerNorm):
     def forward(self, x):
         return nn.functional.layer_norm(x.float(), self.normalized_shape, self.weight.float(),
                                         None if self.bias is None else self.bias.float(), self.eps).to(x.dtype)
+
+
+class IdentityNorm(nn.Module):
+    """Placeholder with the RMSNorm interface (``weight is None`` => the fused projections skip the norm).  EAGLE draft
+    models have no input norm on their first layer and no final norm (reference modeling_llama.py:892-899,1155)."""
+    weight = None
+    variance_epsilon = 1e-6
+    offset = 0.0
+
+    def forward(self, x, residual=None):
+        return x if residual is None else x + residual

@@ -157,7 +157,7 @@ def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
 
 
 def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None, chunk=None, sinks=None,
-                     active_mask=None, softcap=None, k_scale=None, v_scale=None, seq_hint: int = 0):
+                     active_mask=None, softcap=None, k_scale=None, v_scale=None, seq_hint: int = 0, active_base=None):
     """``seq_hint``: upper bound on the live context (the TKG bucket) used only to size the split-KV grid."""
     D = q.shape[-1]
     if (_use_cuda(q) and q.dtype in _FAST_DTYPES and k_cache.dtype == q.dtype and D in (64, 128)
@@ -168,7 +168,7 @@ def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None
                                      positions.to(torch.int32).contiguous(), float(scale), int(window or 0), sinks,
                                      int(seq_hint))
     return ref.attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window, chunk, sinks,
-                                active_mask, softcap, k_scale, v_scale)
+                                active_mask, softcap, k_scale, v_scale, active_base)
 
 
 def attention_prefill(q, k, v, scale, causal: bool = True, window=None, chunk=None, key_valid=None,

@@ -179,11 +179,11 @@ def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
 
 
 def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None, chunk=None,
-                     sinks=None, active_mask=None, softcap=None, k_scale=None, v_scale=None):
+                     sinks=None, active_mask=None, softcap=None, k_scale=None, v_scale=None, active_base=None):
     """Attend q [B,T,Hq,D] over cache lines (already containing the active tokens).
-    Token t of row b sees cache slots j <= positions[b,t] (+window/chunk).  ``active_mask``
-    [B,T,T] (token-tree speculation) restricts visibility among the T active tokens, which sit
-    at slots positions[b,0] .. (tree nodes are stored at consecutive slots)."""
+    Token t of row b sees cache slots j <= positions[b,t] (+window/chunk).  ``active_mask`` [B,T,M] (token-tree
+    speculation, M >= T) gives the visibility of the M slots starting at ``active_base`` [B,1] (default: the slot of the
+    first active token); slots before the base are fully visible, slots after ``base+M`` are hidden."""
     B, T = positions.shape
     S = k_cache.shape[2]
     lines = seq_ids.long().clamp(0, k_cache.shape[0] - 1)
@@ -194,11 +194,12 @@ def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None
         v = v.to(q.dtype) * (1.0 if v_scale is None else v_scale)
     mask = build_mask(positions, S, window, chunk)
     if active_mask is not None:
-        base = positions[:, :1]  # slot of first active token
+        M = active_mask.shape[-1]
+        base = (positions[:, :1] if active_base is None else active_base.view(B, 1)).long().unsqueeze(-1)   # [B,1,1]
         j = torch.arange(S, device=q.device).view(1, 1, S)
-        prior = (j < base.unsqueeze(-1)).expand(B, T, S)
-        idx = (j - base.unsqueeze(-1)).clamp(0, T - 1).expand(B, T, S)
-        act = torch.gather(active_mask.bool(), 2, idx) & (j >= base.unsqueeze(-1)) & (j < base.unsqueeze(-1) + T)
+        prior = (j < base).expand(B, T, S)
+        idx = (j - base).clamp(0, M - 1).expand(B, T, S)
+        act = torch.gather(active_mask.bool().expand(B, T, M), 2, idx) & (j >= base) & (j < base + M)
         mask = (prior | act).unsqueeze(1)
         if window:
             mask = mask & build_mask(positions, S, window, None)

@@ -124,6 +124,10 @@ class HuggingFaceGenerationAdapter:
         pad_id = kwargs.pop("pad_token_id", getattr(gc, "pad_token_id", None) if gc else None)
         if pad_id is None:
             pad_id = eos[0] if eos else (getattr(self.config, "pad_token_id", 0) or 0)
+        if nc.is_medusa and getattr(model, "medusa_model", None) is not None:
+            from ..generation.medusa import medusa_generate
+            return medusa_generate(self, input_ids, attention_mask, max_length, eos, pad_id,
+                                   return_dict_in_generate=return_dict_in_generate)
         if nc.speculation_length > 0 or assistant_model is not None:
             from ..generation.speculative import assisted_generate
             return assisted_generate(self, input_ids, attention_mask, max_length, eos, pad_id, assistant_model,

@@ -12,8 +12,10 @@ import torch
 
 def build_random_llama(hf_overrides: dict, batch_size: int = 1, seq_len: int = 128, max_context_length: int = 64,
                        device: str = "cuda", tp_degree: int = 1, dtype="bfloat16", app_cls=None, config_cls=None,
-                       skip_warmup: bool = True, seed: int = 0, **neuron_kwargs):
-    """A Llama-architecture application with N(0,0.02) weights created directly on ``device``."""
+                       skip_warmup: bool = True, seed: int = 0, fused_draft: Optional[dict] = None, **neuron_kwargs):
+    """A Llama-architecture application with N(0,0.02) weights created directly on ``device``.
+    ``fused_draft``: ``dict(hf=<overrides of the draft architecture>, neuron=<draft NeuronConfig overrides>)`` builds the
+    application with fused speculation (draft inside the same application, reference FusedSpecNeuronConfig)."""
     from ..config import NeuronConfig, OnDeviceSamplingConfig
     from ..models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaForCausalLM
     app_cls = app_cls or NeuronLlamaForCausalLM
@@ -31,7 +33,23 @@ def build_random_llama(hf_overrides: dict, batch_size: int = 1, seq_len: int = 1
     def load_config(cfg):
         for k, v in hf.items():
             setattr(cfg, k, v)
-    cfg = config_cls(nc, load_config=load_config)
+    fsc = None
+    if fused_draft is not None:
+        from ..config import FusedSpecNeuronConfig
+        dhf = dict(hf)
+        dhf.update(fused_draft.get("hf", {}))
+        dnk = dict(nk)
+        dnk.update(fused_draft.get("neuron", {}))
+        for drop in ("enable_fused_speculation", "enable_eagle_speculation", "token_tree_config", "is_medusa",
+                     "num_medusa_heads", "medusa_speculation_length", "medusa_tree"):
+            dnk.pop(drop, None) if drop not in fused_draft.get("neuron", {}) else None
+        dnc = config_cls.get_neuron_config_cls()(**dnk)
+
+        def load_draft(c):
+            for k, v in dhf.items():
+                setattr(c, k, v)
+        fsc = FusedSpecNeuronConfig(app_cls._model_cls, draft_config=config_cls(dnc, load_config=load_draft))
+    cfg = config_cls(nc, load_config=load_config, fused_spec_config=fsc)
     app = app_cls("<random>", cfg)
     app.load(None, skip_warmup=skip_warmup, random_weights=True, seed=seed)
     return app

@@ -51,3 +51,17 @@ def test_perfect_draft_accepts_everything():
     target.neuron_config.speculation_length = 0
     ref = _plain(target, ids, torch.ones_like(ids), 20)
     assert out.sequences[0, :27].tolist() == ref[0, :27].tolist()
+
+
+def test_fused_speculation_inside_application():
+    """enable_fused_speculation: the application owns the draft (FusedSpecNeuronConfig) — no assistant_model argument."""
+    torch.manual_seed(1)
+    ids = torch.randint(1, 128, (2, 6))
+    base = build_random_llama(TINY, batch_size=2, seq_len=48, max_context_length=16, device="cpu", dtype="float32", seed=3)
+    ref = HuggingFaceGenerationAdapter(base).generate(ids, max_new_tokens=12)
+    app = build_random_llama(TINY, batch_size=2, seq_len=48, max_context_length=16, device="cpu", dtype="float32", seed=3,
+                             speculation_length=3, enable_fused_speculation=True,
+                             fused_draft=dict(hf=dict(num_hidden_layers=1)))
+    assert app.fused_spec_model is not None and app.draft_model is not None
+    out = HuggingFaceGenerationAdapter(app).generate(ids, max_new_tokens=12)
+    assert torch.equal(out[:, : ref.shape[1]], ref)
