@@ -190,6 +190,14 @@ class SubModelRunner:
             fill = torch.full((sm.shape[0], ids.shape[1] - T0), -1, dtype=sm.dtype, device=sm.device)
             left = self.neuron_config.padding_side == "left"
             kw["slot_mapping"] = torch.cat([fill, sm], 1) if left else torch.cat([sm, fill], 1)
+        if ids.shape[1] != T0:
+            padn = ids.shape[1] - T0
+            left = self.neuron_config.padding_side == "left"
+            for name, fill in (("vision_mask", 0), ("rotary_position_ids", 1)):
+                t = kw.get(name)
+                if t is not None and t.shape[-1] == T0:
+                    f = torch.full(tuple(t.shape[:-1]) + (padn,), fill, dtype=t.dtype, device=t.device)
+                    kw[name] = torch.cat([f, t], -1) if left else torch.cat([t, f], -1)
         if mask is not None and mask.device.type == "cpu" and bool(mask.all()):
             mask = None   # no padding anywhere: skip the mask plumbing (decided on the host, no device sync)
         self.n_launch += 1

@@ -1,0 +1,67 @@
+"""Image-to-text models on CPU vs Hugging Face (tiny random weights): vision tower output, prefill logits with images
+scattered into the prompt, and decode with M-RoPE position offsets."""
+import pytest
+import torch
+
+from neuronx_distributed_inference_b200.config import load_pretrained_config
+from neuronx_distributed_inference_b200.utils.constants import get_model_cls
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def _build(model_type, hf, ckpt, **nc_kw):
+    cls = get_model_cls(model_type, "image-text-to-text")
+    nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=64, max_context_length=32, torch_dtype="float32", on_cpu=True,
+                                     output_logits=True, **nc_kw)
+    cfg = cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt))
+    app = cls(ckpt, cfg)
+    app.load(None, skip_warmup=True)
+    return app
+
+
+def test_qwen2_vl_matches_hf(tmp_path):
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                         vocab_size=200, max_position_embeddings=512,
+                         rope_parameters=dict(rope_type="default", mrope_section=[2, 3, 3], rope_theta=10000.0)),
+        vision_config=dict(depth=2, embed_dim=32, hidden_size=64, num_heads=2, patch_size=4, spatial_merge_size=2,
+                           temporal_patch_size=2, in_channels=3, mlp_ratio=2),
+        image_token_id=150, video_token_id=151, vision_start_token_id=152, vision_end_token_id=153)
+    hf = Qwen2VLForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "qwen2vl")
+    hf.save_pretrained(ckpt)
+    app = _build("qwen2_vl", hf, ckpt)
+    # two images: 4x4 and 4x8 patches -> 4 and 8 merged tokens
+    grid = torch.tensor([[1, 4, 4], [1, 4, 8]])
+    pix = torch.randn(16 + 32, 3 * 2 * 4 * 4)
+    ids = torch.randint(1, 140, (2, 14))
+    ids[0, 2:6] = 150
+    ids[1, 1:9] = 150
+    mask = torch.ones_like(ids)
+    mask[0, 11:] = 0
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid, mm_token_type_ids=(ids == 150).int())
+        vis = hf.model.visual(pix, grid_thw=grid)
+        vis = vis.pooler_output if hasattr(vis, "pooler_output") else vis
+    got_vis = app.encode_images(pix, image_grid_thw=grid)
+    assert _rel(got_vis, vis) < 1e-4
+    out = app(ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid)
+    last = mask.sum(-1) - 1
+    exp_last = exp.logits[torch.arange(2), last]
+    assert _rel(out.logits[:, -1], exp_last) < 2e-4
+    # one decode step (positions continue after the image-compressed rope index)
+    nxt = exp_last.argmax(-1)
+    ids2 = ids.clone()
+    mask2 = torch.cat([mask, torch.zeros(2, 1, dtype=mask.dtype)], 1)
+    ids2 = torch.cat([ids2, torch.zeros(2, 1, dtype=ids.dtype)], 1)
+    ids2[torch.arange(2), last + 1] = nxt
+    mask2[torch.arange(2), last + 1] = 1
+    with torch.no_grad():
+        exp2 = hf(input_ids=ids2, attention_mask=mask2, pixel_values=pix, image_grid_thw=grid,
+                  mm_token_type_ids=(ids2 == 150).int()).logits[torch.arange(2), last + 1]
+    out2 = app(nxt.view(2, 1), position_ids=(last + 1).view(2, 1).to(torch.int32))
+    assert _rel(out2.logits[:, -1], exp2) < 2e-4
