@@ -94,6 +94,7 @@ class NeuronBaseForImageToText(NeuronBaseForCausalLM):
         sd = {cls._strip(k): v for k, v in sd.items()}
         text = {k[len(cls.text_prefix):] if k.startswith(cls.text_prefix) else k: v for k, v in sd.items()
                 if not k.startswith(cls.vision_prefix)}
+        text = {(k[len("model."):] if k.startswith("model.") else k): v for k, v in text.items()}   # legacy nested layout
         text = cls.convert_hf_to_neuron_state_dict(text, config.get_text_config())
         if getattr(config.get_text_config(), "tie_word_embeddings", False) or getattr(config, "tie_word_embeddings", False):
             if "lm_head.weight" not in text:

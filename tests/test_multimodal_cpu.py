@@ -65,3 +65,28 @@ def test_qwen2_vl_matches_hf(tmp_path):
                   mm_token_type_ids=(ids2 == 150).int()).logits[torch.arange(2), last + 1]
     out2 = app(nxt.view(2, 1), position_ids=(last + 1).view(2, 1).to(torch.int32))
     assert _rel(out2.logits[:, -1], exp2) < 2e-4
+
+
+def test_pixtral_matches_hf(tmp_path):
+    from transformers import LlavaConfig, LlavaForConditionalGeneration, MistralConfig, PixtralVisionConfig
+    torch.manual_seed(0)
+    cfg = LlavaConfig(
+        vision_config=PixtralVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2,
+                                          patch_size=4, image_size=32, num_channels=3, head_dim=16).to_dict(),
+        text_config=MistralConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                  num_key_value_heads=2, vocab_size=200, head_dim=16, sliding_window=None).to_dict(),
+        image_token_index=150, projector_hidden_act="gelu", vision_feature_layer=-1, vision_feature_select_strategy="full")
+    hf = LlavaForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "pixtral")
+    hf.save_pretrained(ckpt)
+    app = _build("pixtral", hf, ckpt)
+    pix = torch.randn(2, 3, 16, 16)
+    sizes = torch.tensor([[8, 16], [16, 8]])        # 2x4 and 4x2 patches -> 8 tokens each
+    ids = torch.randint(1, 140, (2, 14))
+    ids[0, 1:9] = 150
+    ids[1, 3:11] = 150
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes).logits
+    out = app(ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes)
+    assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
