@@ -232,6 +232,12 @@ class NeuronBaseModel(nn.Module):
             h = layer(h, meta, self.kv_mgr, lora=lora.for_layer(i)) if lora is not None else layer(h, meta, self.kv_mgr)
             if aux_layers is not None and i in aux_layers:
                 aux.append(h)
+            ds = kw.get("deepstack_embeds")
+            if ds is not None and is_prefill and i < len(ds) and vision_mask is not None:
+                # Qwen3-VL deepstack: intermediate vision features are added to the residual stream of the first layers
+                vm = vision_mask.bool().squeeze(-1) if vision_mask.dim() == 3 else vision_mask.bool()
+                h = h.clone()
+                h[vm] = h[vm] + ds[i].to(h.dtype)[: int(vm.sum())]
         # ---- last-token gather (prefill) ------------------------------------------------------
         if is_prefill and not all_positions:
             if meta.key_valid is not None and self.padding_side == "right":

@@ -106,14 +106,23 @@ class MRotaryEmbedding(RotaryEmbedding):
     """Multimodal RoPE (Qwen2-VL): position_ids [3,B,T] (t,h,w), frequency bands split by
     ``mrope_section``; falls back to ordinary RoPE for 2-D position ids."""
 
-    def __init__(self, dim, max_position_embeddings, base, mrope_section, scaling=None, device=None):
+    def __init__(self, dim, max_position_embeddings, base, mrope_section, scaling=None, device=None, interleaved: bool = False):
         super().__init__(dim, max_position_embeddings, base, None, device)
         self.mrope_section = list(mrope_section)
+        self.interleaved = interleaved
 
     def forward(self, position_ids):
         if position_ids.dim() == 2:
             return super().forward(position_ids)
         cs = [super(MRotaryEmbedding, self).forward(position_ids[i]) for i in range(3)]
+        if self.interleaved:
+            # Qwen3-VL: bands interleaved [T H W T H W ... T T] instead of chunked [T.. H.. W..]
+            cos, sin = cs[0][0].clone(), cs[0][1].clone()
+            for axis, off in ((1, 1), (2, 2)):
+                idx = slice(off, self.mrope_section[axis] * 3, 3)
+                cos[..., idx] = cs[axis][0][..., idx]
+                sin[..., idx] = cs[axis][1][..., idx]
+            return cos, sin
         cos_parts, sin_parts, o = [], [], 0
         for i, sec in enumerate(self.mrope_section):
             cos_parts.append(cs[i % 3][0][..., o:o + sec])

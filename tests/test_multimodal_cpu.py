@@ -90,3 +90,32 @@ def test_pixtral_matches_hf(tmp_path):
         exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes).logits
     out = app(ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes)
     assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
+
+
+def test_qwen3_vl_matches_hf(tmp_path):
+    from transformers import Qwen3VLConfig, Qwen3VLForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Qwen3VLConfig(
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+                         vocab_size=200, head_dim=16, max_position_embeddings=512,
+                         rope_parameters=dict(rope_type="default", mrope_section=[4, 2, 2], mrope_interleaved=True, rope_theta=10000.0)),
+        vision_config=dict(depth=3, hidden_size=32, intermediate_size=64, out_hidden_size=64, num_heads=2, patch_size=4,
+                           spatial_merge_size=2, temporal_patch_size=2, in_channels=3, num_position_embeddings=64,
+                           deepstack_visual_indexes=[0, 1]),
+        image_token_id=150, video_token_id=151, vision_start_token_id=152, vision_end_token_id=153)
+    hf = Qwen3VLForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "qwen3vl")
+    hf.save_pretrained(ckpt)
+    app = _build("qwen3_vl", hf, ckpt)
+    grid = torch.tensor([[1, 4, 4], [1, 4, 8]])
+    pix = torch.randn(16 + 32, 3 * 2 * 4 * 4)
+    ids = torch.randint(1, 140, (2, 14))
+    ids[0, 2:6] = 150
+    ids[1, 1:9] = 150
+    mask = torch.ones_like(ids)
+    mask[0, 11:] = 0
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid, mm_token_type_ids=(ids == 150).int())
+    out = app(ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid)
+    last = mask.sum(-1) - 1
+    assert _rel(out.logits[:, -1], exp.logits[torch.arange(2), last]) < 2e-4
