@@ -207,6 +207,9 @@ class NeuronBaseModel(nn.Module):
                         block_table=kw.get("block_table"), has_prefix=has_prefix,
                         adapter_ids=kw.get("adapter_ids"), rotary_position_ids=kw.get("rotary_position_ids"),
                         capture={} if kw.get("capture") else None)
+        for k in getattr(self, "meta_extra_keys", ()):
+            if kw.get(k) is not None:
+                meta.extras[k] = kw[k]
         if self.padding_side != "right" or kw.get("offset_positions"):
             meta.offset_positions = True
         return meta

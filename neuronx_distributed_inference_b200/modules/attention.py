@@ -58,6 +58,7 @@ class AttnMeta:
     capture: Optional[dict] = None               # tensor-capture sink
     lines: Optional[torch.Tensor] = None         # cache lines of seq_ids (computed once per forward)
     seq_hint: int = 0                            # upper bound on the live context (TKG bucket)
+    extras: dict = field(default_factory=dict)    # model-specific per-forward tensors (cross-attention states, ...)
 
 
 class AttentionBase(nn.Module):

@@ -42,7 +42,7 @@ class VisionAttention(nn.Module):
         self.scale = self.head_dim ** -0.5
 
     def forward(self, x: torch.Tensor, cos=None, sin=None, segment_ids: Optional[torch.Tensor] = None,
-                key_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+                key_valid: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x [B,N,C].  ``segment_ids`` [B,N]: tokens attend only within their own segment (several images packed in one
         row).  ``key_valid`` [B,N]: padding keys are hidden."""
         B, N, _ = x.shape
@@ -50,7 +50,6 @@ class VisionAttention(nn.Module):
         q, k, v = self.qkv_proj(x).view(B, N, 3, H, D).unbind(2) if False else self.qkv_proj(x).view(B, N, 3 * H, D).split(H, 2)
         if cos is not None:
             q, k = rotate_half_apply(q, cos, sin), rotate_half_apply(k, cos, sin)
-        mask = None
         if segment_ids is not None:
             mask = (segment_ids.unsqueeze(-1) == segment_ids.unsqueeze(-2)).unsqueeze(1)
         if key_valid is not None:

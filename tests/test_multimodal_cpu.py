@@ -119,3 +119,56 @@ def test_qwen3_vl_matches_hf(tmp_path):
     out = app(ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid)
     last = mask.sum(-1) - 1
     assert _rel(out.logits[:, -1], exp.logits[torch.arange(2), last]) < 2e-4
+
+
+def test_mllama_matches_hf(tmp_path):
+    from transformers import MllamaConfig, MllamaForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = MllamaConfig(
+        vision_config=dict(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_global_layers=1, attention_heads=2,
+                           patch_size=4, image_size=8, num_channels=3, max_num_tiles=2, vision_output_dim=96,
+                           intermediate_layers_indices=[0, 1], supported_aspect_ratios=[[1, 1], [1, 2], [2, 1]]),
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+                         vocab_size=200, cross_attention_layers=[1], max_position_embeddings=512,
+                         rope_parameters=dict(rope_type="default", rope_theta=10000.0), pad_token_id=0),
+        image_token_index=150)
+    hf = MllamaForConditionalGeneration(cfg)
+    with torch.no_grad():        # gates are zero-initialised: open them so the cross-attention path matters
+        for n, p in hf.named_parameters():
+            if "gate" in n and p.numel() == 1:
+                p.fill_(0.7)
+    hf = hf.eval()
+    ckpt = str(tmp_path / "mllama")
+    hf.save_pretrained(ckpt)
+    app = _build("mllama", hf, ckpt)
+    app.vision_model.intermediate_is_layer_output = True      # transformers 5.x oracle convention (see modeling_mllama.py)
+    pix = torch.randn(2, 1, 2, 3, 8, 8)
+    ar_ids = torch.tensor([[2], [1]])
+    ar_mask = torch.tensor([[[1, 1]], [[1, 0]]])
+    ids = torch.randint(1, 140, (2, 10))
+    ids[:, 1] = 150
+    mask = torch.ones_like(ids)
+    mask[1, 8:] = 0
+    cam = torch.zeros(2, 10, 1, 2, dtype=torch.long)
+    cam[0, 1:, 0, :] = 1
+    cam[1, 1:, 0, 0] = 1
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, aspect_ratio_ids=ar_ids, aspect_ratio_mask=ar_mask,
+                 cross_attention_mask=cam).logits
+    out = app(ids, attention_mask=mask, pixel_values=pix, aspect_ratio_ids=ar_ids, aspect_ratio_mask=ar_mask,
+              cross_attention_mask=cam)
+    last = mask.sum(-1) - 1
+    assert _rel(out.logits[:, -1], exp[torch.arange(2), last]) < 2e-4
+    # decode one token: cross K/V come from the per-line buffers
+    nxt = exp[torch.arange(2), last].argmax(-1)
+    ids2 = torch.cat([ids, torch.zeros(2, 1, dtype=ids.dtype)], 1)
+    mask2 = torch.cat([mask, torch.zeros(2, 1, dtype=mask.dtype)], 1)
+    ids2[torch.arange(2), last + 1] = nxt
+    mask2[torch.arange(2), last + 1] = 1
+    cam2 = torch.cat([cam, cam[:, -1:]], 1)
+    cam2[1, 8] = cam[1, 7]
+    with torch.no_grad():
+        exp2 = hf(input_ids=ids2, attention_mask=mask2, pixel_values=pix, aspect_ratio_ids=ar_ids, aspect_ratio_mask=ar_mask,
+                  cross_attention_mask=cam2).logits[torch.arange(2), last + 1]
+    out2 = app(nxt.view(2, 1), position_ids=(last + 1).view(2, 1).to(torch.int32))
+    assert _rel(out2.logits[:, -1], exp2) < 2e-4
