@@ -49,7 +49,10 @@ class VisionAttention(nn.Module):
         H, D = self.n_heads, self.head_dim
         q, k, v = self.qkv_proj(x).view(B, N, 3, H, D).unbind(2) if False else self.qkv_proj(x).view(B, N, 3 * H, D).split(H, 2)
         if cos is not None:
-            q, k = rotate_half_apply(q, cos, sin), rotate_half_apply(k, cos, sin)
+            if cos.shape[-1] == D // 2:       # interleaved (complex) rotary: Llama-4 vision
+                q, k = ops.apply_rope(q, cos, sin, True), ops.apply_rope(k, cos, sin, True)
+            else:
+                q, k = rotate_half_apply(q, cos, sin), rotate_half_apply(k, cos, sin)
         if segment_ids is not None:
             mask = (segment_ids.unsqueeze(-1) == segment_ids.unsqueeze(-2)).unsqueeze(1)
         if key_valid is not None:

@@ -172,3 +172,30 @@ def test_mllama_matches_hf(tmp_path):
                   cross_attention_mask=cam2).logits[torch.arange(2), last + 1]
     out2 = app(nxt.view(2, 1), position_ids=(last + 1).view(2, 1).to(torch.int32))
     assert _rel(out2.logits[:, -1], exp2) < 2e-4
+
+
+def test_llama4_multimodal_matches_hf(tmp_path):
+    from transformers import Llama4Config, Llama4ForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Llama4Config(
+        vision_config=dict(hidden_size=32, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, patch_size=4,
+                           image_size=16, num_channels=3, pixel_shuffle_ratio=0.5, projector_input_dim=48, projector_output_dim=48,
+                           vision_output_dim=48, rope_parameters=dict(rope_theta=10000.0, rope_type="default")),
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                         vocab_size=200, head_dim=16, num_local_experts=4, num_experts_per_tok=1, intermediate_size_mlp=128,
+                         interleave_moe_layer_step=2, attention_chunk_size=8, no_rope_layers=[1, 0], use_qk_norm=True,
+                         max_position_embeddings=256),
+        image_token_index=150)
+    hf = Llama4ForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "llama4mm")
+    hf.save_pretrained(ckpt)
+    app = _build("llama4", hf, ckpt)
+    pix = torch.randn(2, 3, 16, 16)           # two tiles -> 4 tokens each after the 0.5 pixel shuffle
+    ids = torch.randint(1, 140, (2, 12))
+    ids[0, 1:5] = 150
+    ids[1, 2:6] = 150
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix).logits
+    out = app(ids, attention_mask=mask, pixel_values=pix)
+    assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
