@@ -134,7 +134,7 @@ class NeuronBaseModel(nn.Module):
         else:
             lines = nc.kv_cache_batch_size + nc.kv_cache_padding_size
             kw = dict(num_layers=n_layers, num_kv_heads=self.kv_heads_per_rank(), head_dim=self.kv_head_dim(),
-                      max_len=nc.max_length + self._speculation_slack(),
+                      max_len=self._kv_len(config),
                       num_lines=lines, dtype=dtype, device=self.device_,
                       quant_config=nc.kv_quant_config if nc.kv_cache_quant else None)
             if nc.attention_dp_degree > 1:
@@ -143,6 +143,12 @@ class NeuronBaseModel(nn.Module):
                 self.kv_mgr = DataParallelKVCacheManager(dp_rank=g.rank, dp_size=g.size, **kw)
             else:
                 self.kv_mgr = KVCacheManager(**kw)
+
+    def _kv_len(self, config) -> int:
+        nc = self.neuron_config
+        n = nc.max_length + self._speculation_slack()
+        r = getattr(config, "num_cores_per_group", 1) if nc.flash_decoding_enabled else 1
+        return -(-n // r)          # flash decoding: each rank of a KV group keeps 1/r of the positions
 
     def _speculation_slack(self) -> int:
         """Extra cache slots past ``max_length``: a verify step writes every candidate (chain of k, or all tree nodes)
@@ -226,6 +232,12 @@ class NeuronBaseModel(nn.Module):
             is_prefill = T > 1 and T != nc.speculation_length and T != nc.medusa_speculation_length
         meta = self.build_meta(input_ids, attention_mask, position_ids, seq_ids, is_prefill, **kw)
         h = self.embed(input_ids, inputs_embeds, vision_embeddings, vision_mask)
+        sp = self._set_sequence_parallel(is_prefill and T % self.tp_group.size == 0 and T >= self.tp_group.size)
+        if sp:
+            # sequence parallel prefill (reference model_base.py:1471-1583): the residual stream is sharded along the
+            # sequence between blocks; column-parallel layers all-gather it, row-parallel layers reduce-scatter back
+            n = T // self.tp_group.size
+            h = h[:, self.tp_group.rank * n:(self.tp_group.rank + 1) * n].contiguous()
         if prev_hidden is not None and hasattr(self, "fuse_prev_hidden"):
             h = self.fuse_prev_hidden(h, prev_hidden)
         lora = getattr(self, "lora", None) if meta.adapter_ids is not None else None
@@ -241,6 +253,8 @@ class NeuronBaseModel(nn.Module):
                 vm = vision_mask.bool().squeeze(-1) if vision_mask.dim() == 3 else vision_mask.bool()
                 h = h.clone()
                 h[vm] = h[vm] + ds[i].to(h.dtype)[: int(vm.sum())]
+        if sp:
+            h = mappings.all_gather(h.contiguous(), 1, self.tp_group)
         # ---- last-token gather (prefill) ------------------------------------------------------
         if is_prefill and not all_positions:
             if meta.key_valid is not None and self.padding_side == "right":
@@ -283,6 +297,19 @@ class NeuronBaseModel(nn.Module):
         (reference model_base.py:478-508, modeling_llama.py:1172-1187)."""
         hn = self.final_hidden(h_out)
         return torch.stack([self.gather_logits(head(hn)) for head in self.medusa_heads], 0)
+
+    def _set_sequence_parallel(self, on: bool) -> bool:
+        """SP is a prefill-only layout; the parallel layers carry a static flag in the reference, here it is switched per
+        forward so that the same modules serve decode (T=1, nothing to shard)."""
+        if not self.neuron_config.sequence_parallel_enabled or self.tp_group.size == 1:
+            return False
+        if not hasattr(self, "_sp_modules"):
+            self._sp_modules = [m for m in self.layers.modules() if hasattr(m, "sequence_parallel_enabled")]
+        for m in self._sp_modules:
+            m.sequence_parallel_enabled = on
+            if getattr(m, "sequence_dimension", None) is None:
+                m.sequence_dimension = 1
+        return on
 
     def final_hidden(self, h):
         return self.norm(h)

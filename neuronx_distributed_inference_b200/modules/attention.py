@@ -112,6 +112,12 @@ class AttentionBase(nn.Module):
         else:
             self.sinks = None
         self.rms_norm_eps = rms_norm_eps
+        # flash decoding: KV sequence-sharded over the ranks that replicate this rank's KV head
+        self.kv_group = get_kv_shared_group() if nc.flash_decoding_enabled else None
+        if self.kv_group is not None and self.kv_group.size == 1:
+            self.kv_group = None
+        if self.kv_group is not None and (sliding_window or attention_chunk_size or learned_sinks):
+            raise NotImplementedError("flash decoding with sliding-window / chunked / sink attention")
 
     # ------------------------------------------------------------------------------------
     def _rope(self, meta: AttnMeta):
@@ -133,6 +139,8 @@ class AttentionBase(nn.Module):
         """hidden [B,T,H] -> attention block output [B,T,H] (+ residual when given).
         ``norm_weight``: the layer's input RMSNorm, fused into the QKV projection."""
         B, T, _ = hidden.shape
+        if self.qkv_proj.sequence_parallel_enabled:
+            T = T * self.tp_group.size            # hidden is the local sequence shard; qkv_proj gathers it
         D, nq, nkv = self.head_dim, self.n_q, self.n_kv
         qkv = self.qkv_proj(hidden, norm_weight, norm_eps if norm_eps is not None else self.rms_norm_eps, norm_offset)
         if lora is not None and lora.has("qkv_proj"):
@@ -143,6 +151,8 @@ class AttentionBase(nn.Module):
             qkv = qkv.clamp(-self.clip_qkv, self.clip_qkv)
         cos, sin = self._rope(meta)
         paged = meta.slot_mapping is not None
+        if self.kv_group is not None:
+            return self._forward_flash_decoding(qkv, meta, kv_mgr, cos, sin, residual, B, T)
         k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
         if meta.lines is None:
             meta.lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
@@ -194,6 +204,26 @@ class AttentionBase(nn.Module):
             from ..parallel import mappings as _m
             out = out + _m.all_reduce(lora("o_proj", o, meta.adapter_ids), self.tp_group)
         return out
+
+    def _forward_flash_decoding(self, qkv, meta, kv_mgr, cos, sin, residual, B, T):
+        from . import flashdecode as fd
+        g = self.kv_group
+        D, nq = self.head_dim, self.n_q
+        q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
+        lines = kv_mgr.lines_for(meta.seq_ids)
+        kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, fd.local_slots(meta.write_positions, g.rank, g.size), lines)
+        if meta.is_prefill and not meta.has_prefix:
+            right = self._arange_pos(meta)
+            o = ops.attention_prefill(q, k, v, self.scale, True, None, None, None if right else meta.key_valid,
+                                      None if right else meta.position_ids, None, self.softcap)
+        else:
+            k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
+            qa = mappings.all_gather(q.contiguous(), 2, g)                       # [B,T,r*nq,D]: all q heads of the KV group
+            li = lines.long().clamp(0, k_cache.shape[0] - 1)
+            po, pm, pl = fd.partial_attention(qa, k_cache[li], v_cache[li], fd.local_horizon(meta.position_ids, g.rank, g.size),
+                                              self.scale)
+            o = fd.combine(po, pm, pl, g)[:, :, g.rank * nq:(g.rank + 1) * nq].to(q.dtype)
+        return self.o_proj(o.reshape(B, T, nq * D), residual)
 
     def _arange_pos(self, meta: AttnMeta) -> bool:
         """Prefill kernels assume q position == token index (right padding).  Left padding / offset

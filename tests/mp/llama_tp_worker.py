@@ -33,10 +33,16 @@ def main():
     if dev == "cuda":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     nc = NeuronConfig(batch_size=2, seq_len=64, max_context_length=32, torch_dtype=dtype, tp_degree=world,
-                      on_cpu=(dev == "cpu"), output_logits=True, on_device_sampling_config=OnDeviceSamplingConfig(top_k=1))
+                      on_cpu=(dev == "cpu"), output_logits=True, on_device_sampling_config=OnDeviceSamplingConfig(top_k=1),
+                      flash_decoding_enabled=os.environ.get("FLASH_DECODING", "0") == "1",
+                      sequence_parallel_enabled=os.environ.get("SEQUENCE_PARALLEL", "0") == "1")
     cfg = LlamaInferenceConfig(nc, load_config=load_pretrained_config(ckpt))
     app = NeuronLlamaForCausalLM(ckpt, cfg)
     app.load(None, skip_warmup=True)
+    if nc.flash_decoding_enabled:
+        kvg = app.model.layers[0].self_attn.kv_group
+        assert kvg is not None and kvg.size == world // cfg.num_key_value_heads, "flash decoding group not formed"
+        assert app.model.kv_mgr.max_len == -(-nc.max_length // kvg.size), "KV cache is not sequence-sharded"
     g = torch.Generator().manual_seed(0)
     ids = torch.randint(0, cfg.vocab_size, (2, 12), generator=g)
     mask = torch.ones(2, 12, dtype=torch.int32)

@@ -18,10 +18,10 @@ def tiny_ckpt(tmp_path_factory):
     return save_random_hf_checkpoint(cfg, str(tmp_path_factory.mktemp("ckpt")))
 
 
-def _run(n, ckpt, port):
+def _run(n, ckpt, port, **env_extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp", "llama_tp_worker.py"), ckpt, "cpu"]
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", **env_extra)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
@@ -34,3 +34,13 @@ def test_llama_tp2_gloo_matches_hf(tiny_ckpt):
 def test_llama_tp4_gloo_kv_replication_matches_hf(tiny_ckpt):
     # 2 KV heads at TP=4 -> REPLICATE_TO_TP_DEGREE path of the GQA plan
     _run(4, tiny_ckpt, 29542)
+
+
+def test_llama_tp4_flash_decoding_matches_hf(tiny_ckpt):
+    # KV heads replicated on 2 ranks each -> the sequence is sharded inside each pair (flash decoding)
+    _run(4, tiny_ckpt, 29543, FLASH_DECODING="1")
+
+
+def test_llama_tp2_sequence_parallel_matches_hf(tiny_ckpt):
+    # residual stream sharded along the sequence during prefill (all-gather before column-, reduce-scatter after row-parallel)
+    _run(2, tiny_ckpt, 29544, SEQUENCE_PARALLEL="1")
