@@ -469,6 +469,9 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
         if computed_context_lens is not None:
             extra["has_prefix"] = bool((computed_context_lens > 0).any())
         is_prefill = T > 1 and self._is_prefill(position_ids, computed_context_lens)
+        w = nc.windowed_context_encoding_size
+        if is_prefill and w and T > w and computed_context_lens is None:
+            return self._windowed_context_encoding(input_ids, attention_mask, position_ids, seq_ids, sampling_params, w, extra)
         if is_prefill:
             out = self.context_encoding_model(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **extra)
             self.kv_cache_populated = True
@@ -477,6 +480,38 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
         else:
             out = self.token_generation_model(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **extra)
         return self._construct_output(out)
+
+    def _windowed_context_encoding(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, w, extra):
+        """Long prompts are encoded window by window (reference model_base.py windowed CTE loop, config.py
+        ``windowed_context_encoding_size``): window i attends to the cache written by windows < i plus itself, so the
+        activation footprint is that of a ``w``-token prefill whatever the prompt length.  Each row's result comes from the
+        window that contains its last real token."""
+        B, T = input_ids.shape
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        n_valid = attention_mask.long().sum(-1)
+        final = None
+        for s in range(0, T, w):
+            sl = slice(s, min(s + w, T))
+            m = attention_mask[:, sl]
+            if not bool(m.any()):
+                break
+            kw = dict(extra)
+            if s > 0:
+                kw["has_prefix"] = True
+            out = self.context_encoding_model(input_ids[:, sl], m, position_ids[:, sl], seq_ids, sampling_params, **kw)
+            res = self._construct_output(out)
+            if final is None:
+                final = res
+            else:
+                here = ((n_valid - 1) >= s).to(res.tokens.device if res.tokens is not None else res.logits.device)
+                for name in ("tokens", "logits", "hidden_states"):
+                    a, b = getattr(final, name), getattr(res, name)
+                    if a is not None and b is not None:
+                        sel = here.view(-1, *([1] * (a.dim() - 1)))
+                        setattr(final, name, torch.where(sel, b, a))
+        self.kv_cache_populated = True
+        return final
 
     @staticmethod
     def _is_prefill(position_ids, computed_context_lens=None) -> bool:

@@ -104,3 +104,44 @@ def test_slot_mapping_generators():
     sm = generate_fusedspec_slot_mapping(torch.tensor([[6], [6]]), torch.zeros(2, 3, dtype=torch.int32), bt, 8, 3)
     assert sm[0].tolist() == [3 * 8 + 6, 3 * 8 + 7, 9 * 8 + 0]
     assert get_active_block_table(bt, torch.tensor([9, 3]), 8).tolist() == [3, 9, 5]
+
+
+def test_async_session_equals_sync_decode_cpu():
+    import torch
+    from neuronx_distributed_inference_b200.modules.async_execution import causal_lm_async_execution
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    tiny = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                vocab_size=128, head_dim=16)
+    app = build_random_llama(tiny, batch_size=2, seq_len=48, max_context_length=16, device="cpu", dtype="float32", seed=2,
+                             async_mode=True)
+    ids = torch.randint(1, 128, (2, 6))
+    tok = app(ids, attention_mask=torch.ones_like(ids)).tokens.view(2, 1)
+    pos = torch.full((2, 1), 6, dtype=torch.int32)
+    got = causal_lm_async_execution(app, tok, pos, 5)
+    app.reset()
+    t = app(ids, attention_mask=torch.ones_like(ids)).tokens.view(2, 1)
+    ref = []
+    for i in range(5):
+        t = app(t, position_ids=pos + i).tokens.view(2, 1)
+        ref.append(t.view(-1))
+    assert torch.equal(got, torch.stack(ref, 1))
+
+
+def test_windowed_context_encoding_equals_single_shot():
+    import torch
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    tiny = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                vocab_size=128, head_dim=16)
+    kw = dict(batch_size=2, seq_len=64, max_context_length=32, device="cpu", dtype="float32", seed=2, output_logits=True)
+    ids = torch.randint(1, 128, (2, 20))
+    mask = torch.ones_like(ids)
+    mask[1, 7:] = 0            # row 1 ends inside the first window
+    ref_app = build_random_llama(tiny, **kw)
+    ref = ref_app(ids, attention_mask=mask)
+    app = build_random_llama(tiny, windowed_context_encoding_size=8, **kw)
+    out = app(ids, attention_mask=mask)
+    assert torch.allclose(out.logits, ref.logits, atol=1e-4) and torch.equal(out.tokens, ref.tokens)
+    pos = mask.sum(-1).view(2, 1).int()
+    a = app(out.tokens.view(2, 1), position_ids=pos)
+    b = ref_app(ref.tokens.view(2, 1), position_ids=pos)
+    assert torch.allclose(a.logits, b.logits, atol=1e-4)
