@@ -234,3 +234,33 @@ def test_cli_parsing_matches_readme_example():
                         "--speculation-length 5 --draft-model-path /d".split())
     nc = demo.create_neuron_config(get_model_cls("llama"), a)
     assert nc.quantized and nc.quantization_type == "per_channel_symmetric" and nc.speculation_length == 5
+
+
+def test_module_test_template_rmsnorm_and_env_helpers():
+    import torch
+    from neuronx_distributed_inference_b200.config import NeuronConfig
+    from neuronx_distributed_inference_b200.module_test import ModuleAdapter, ModuleTestOrchestrator
+    from neuronx_distributed_inference_b200.modules.norm import RMSNorm
+    from neuronx_distributed_inference_b200.utils import compile_env, runtime_env
+
+    class Golden(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.rand(64) + 0.5)
+
+        def forward(self, x):
+            return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * self.weight
+
+    class A(ModuleAdapter):
+        def build_golden(self):
+            return Golden()
+
+        def build_engine(self, device, dtype):
+            return RMSNorm(64, 1e-6, dtype, device=device)
+
+        def make_inputs(self):
+            return (torch.randn(2, 5, 64),)
+    rep = ModuleTestOrchestrator(A()).run(devices=("cpu",))
+    assert rep["cpu"] < 1e-5
+    env = runtime_env.get_env_vars(NeuronConfig(tp_degree=1))
+    assert isinstance(env, dict) and "NXDI_B200_ARCH" in compile_env.get_compile_env_vars(NeuronConfig())
