@@ -158,6 +158,7 @@ class AttentionBase(nn.Module):
             meta.lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
         lines = meta.lines
         fused = (self._simple() and not paged and qkv.is_cuda and k_cache.dtype == qkv.dtype
+                 and qkv.dtype in (torch.bfloat16, torch.float16)
                  and (not meta.is_prefill or not meta.has_prefix))
         if fused:
             qn = self.q_layernorm.weight if self.qk_norm == "rms_pre_rope" else None

@@ -91,7 +91,8 @@ class KVCacheManager(nn.Module):
             k_new = k_new.float().clamp(fi.min, fi.max).to(self.store_dtype)
             v_new = v_new.float().clamp(fi.min, fi.max).to(self.store_dtype)
             self._append_torch(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
-        elif k_new.is_cuda and (self.head_dim * k_new.element_size()) % 16 == 0:
+        elif (k_new.is_cuda and k_new.dtype in (torch.bfloat16, torch.float16)
+              and (self.head_dim * k_new.element_size()) % 16 == 0):
             ops.kv_append(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)
         else:
             self._append_torch(k, v, k_new, v_new, self.lines_for(seq_ids) if lines is None else lines, positions)

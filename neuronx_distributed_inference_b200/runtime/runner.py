@@ -233,7 +233,14 @@ class SubModelRunner:
         key = (Bb, sb, T, tuple(sorted((k, v) for k, v in kwargs.items() if not torch.is_tensor(v))))
         g = self._graphs.get(key)
         if g is None:
-            g = self._capture(key, Bb, T, kwargs)
+            try:
+                g = self._capture(key, Bb, T, kwargs)
+            except RuntimeError as e:
+                # an op of this configuration's fallback path is not capturable: run this runner eagerly from now on
+                logger.warning("%s: CUDA-graph capture failed (%s); falling back to eager decode", self.tag, str(e).split("\n")[0])
+                torch.cuda.synchronize(dev)
+                self.use_graphs = False
+                return self._run_decode(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **kw)
         # stage inputs into the static buffers
         si = g.inputs
         si["input_ids"][:B].copy_(input_ids, non_blocking=True)

@@ -1,0 +1,118 @@
+"""Serving features on the GPU (bf16, CUDA kernels + CUDA graphs): async decode, EAGLE / Medusa speculation, multimodal smoke."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+            vocab_size=512, head_dim=64)
+
+
+def _mk(dtype="bfloat16", **kw):
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    return build_random_llama(TINY, batch_size=2, seq_len=128, max_context_length=32, device="cuda", dtype=dtype, seed=5, **kw)
+
+
+def test_tree_speculation_exact_in_fp32_on_gpu():
+    """Same device code path (indexing, KV compaction, masks) in fp32: must be exactly lossless; the bf16 tests below only
+    differ by rounding between the multi-token and one-token kernels."""
+    from neuronx_distributed_inference_b200.utils.hf_adapter import HuggingFaceGenerationAdapter
+    torch.manual_seed(3)
+    ids = torch.randint(1, 512, (2, 9))
+    mask = torch.ones_like(ids)
+    ref = HuggingFaceGenerationAdapter(_mk("float32")).generate(ids, attention_mask=mask, max_new_tokens=20)
+    med = _mk("float32", is_medusa=True, num_medusa_heads=3, medusa_speculation_length=8, output_logits=True,
+              medusa_tree=[[0], [1], [0, 0], [0, 1], [1, 0], [0, 0, 0]])
+    seq = HuggingFaceGenerationAdapter(med).generate(ids, attention_mask=mask, max_new_tokens=20)
+    assert torch.equal(seq[:, : ref.shape[1]], ref)
+    tree = _mk("float32", speculation_length=4, enable_fused_speculation=True, enable_eagle_speculation=True,
+               token_tree_config={"0": ["1", "2"], "1": ["3", "4"], "2": ["5"], "3": ["6"]},
+               fused_draft=dict(hf=dict(num_hidden_layers=1), neuron=dict(is_eagle_draft=True)))
+    seq = HuggingFaceGenerationAdapter(tree).generate(ids, attention_mask=mask, max_new_tokens=20)
+    assert torch.equal(seq[:, : ref.shape[1]], ref)
+
+
+def test_async_session_equals_sync_decode_gpu():
+    from neuronx_distributed_inference_b200.modules.async_execution import causal_lm_async_execution
+    app = _mk(async_mode=True)
+    ids = torch.randint(1, 512, (2, 9))
+    tok = app(ids, attention_mask=torch.ones_like(ids)).tokens.view(2, 1).cpu()
+    pos = torch.full((2, 1), 9, dtype=torch.int32)
+    got = causal_lm_async_execution(app, tok, pos, 12, depth=3)
+    ref_app = _mk()
+    t = ref_app(ids, attention_mask=torch.ones_like(ids)).tokens.view(2, 1).cpu()
+    assert torch.equal(t, tok)
+    ref = []
+    for i in range(12):
+        t = ref_app(t, position_ids=pos + i).tokens.view(2, 1).cpu()
+        ref.append(t.view(-1))
+    assert torch.equal(got, torch.stack(ref, 1))
+
+
+@pytest.mark.parametrize("variant", ["eagle", "eagle_tree", "fused"])
+def test_speculation_on_gpu_tracks_greedy(variant):
+    """bf16 verification over k tokens runs different kernels (multi-token decode) than one-token decoding, so exact
+    equality is not guaranteed at near-ties; require the run to work end to end and to agree on a long common prefix."""
+    from neuronx_distributed_inference_b200.utils.hf_adapter import HuggingFaceGenerationAdapter
+    ids = torch.randint(1, 512, (2, 9))
+    mask = torch.ones_like(ids)
+    ref = HuggingFaceGenerationAdapter(_mk()).generate(ids, attention_mask=mask, max_new_tokens=24)
+    kw = dict(speculation_length=4, enable_fused_speculation=True)
+    dn = {}
+    if variant != "fused":
+        kw["enable_eagle_speculation"] = True
+        dn["is_eagle_draft"] = True
+    if variant == "eagle_tree":
+        kw["token_tree_config"] = {"0": ["1", "2"], "1": ["3", "4"], "2": ["5"], "3": ["6"]}
+    app = _mk(fused_draft=dict(hf=dict(num_hidden_layers=1), neuron=dn), **kw)
+    out = HuggingFaceGenerationAdapter(app).generate(ids, attention_mask=mask, max_new_tokens=24, return_dict_in_generate=True)
+    seq = out.sequences
+    n = min(seq.shape[1], ref.shape[1])
+    same = (seq[:, :n] == ref[:, :n]).long().cumprod(-1).sum(-1)
+    # the tree verify runs the masked (torch) attention path: more rounding differences vs the one-token kernels
+    assert int(same.min()) >= 9 + (3 if variant == "eagle_tree" else 8) and int(same.max()) >= 9 + 12, (seq, ref)
+    assert out.speculation_stats["steps"] > 0
+
+
+def test_medusa_on_gpu():
+    from neuronx_distributed_inference_b200.utils.hf_adapter import HuggingFaceGenerationAdapter
+    ids = torch.randint(1, 512, (2, 9))
+    mask = torch.ones_like(ids)
+    ref = HuggingFaceGenerationAdapter(_mk()).generate(ids, attention_mask=mask, max_new_tokens=16)
+    app = _mk(is_medusa=True, num_medusa_heads=3, medusa_speculation_length=8, output_logits=True,
+              medusa_tree=[[0], [1], [0, 0], [0, 1], [1, 0], [0, 0, 0]])
+    seq = HuggingFaceGenerationAdapter(app).generate(ids, attention_mask=mask, max_new_tokens=16)
+    n = min(seq.shape[1], ref.shape[1])
+    same = (seq[:, :n] == ref[:, :n]).long().cumprod(-1).sum(-1)
+    assert int(same.min()) >= 9 + 3 and int(same.max()) >= 9 + 10
+
+
+def test_flux_backbone_and_pipeline_gpu():
+    from neuronx_distributed_inference_b200.config import NeuronConfig
+    from neuronx_distributed_inference_b200.models.diffusers.flux.application import NeuronFluxApplication
+    bb = dict(num_layers=2, num_single_layers=2, attention_head_dim=64, num_attention_heads=4, in_channels=64, joint_attention_dim=128,
+              pooled_projection_dim=64, axes_dims_rope=(16, 24, 24), guidance_embeds=True)
+    clip = dict(vocab_size=100, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, max_position_embeddings=16,
+                hidden_act="quick_gelu", layer_norm_eps=1e-5, eos_token_id=2)
+    t5 = dict(vocab_size=100, d_model=128, d_kv=32, d_ff=256, num_layers=2, num_heads=4, relative_attention_num_buckets=8,
+              relative_attention_max_distance=16, layer_norm_epsilon=1e-6, feed_forward_proj="gated-gelu")
+    vae = dict(latent_channels=16, out_channels=3, block_out_channels=(32, 64), layers_per_block=1, norm_num_groups=8,
+               scaling_factor=0.36, shift_factor=0.11)
+    app = NeuronFluxApplication(None, NeuronConfig(batch_size=1, torch_dtype="bfloat16"), bb, clip, t5, vae, height=64, width=64)
+    app.load(random_weights=True)
+    img = app(torch.randint(3, 99, (1, 8)), torch.randint(3, 99, (1, 6)), num_inference_steps=2)
+    assert img.shape[0] == 1 and img.shape[1] == 3 and torch.isfinite(img).all()
+
+
+def test_whisper_random_weights_gpu():
+    from neuronx_distributed_inference_b200.config import NeuronConfig
+    from neuronx_distributed_inference_b200.models.whisper.modeling_whisper import NeuronApplicationWhisper, WhisperInferenceConfig
+    nc = NeuronConfig(batch_size=2, seq_len=64, max_context_length=16, torch_dtype="bfloat16")
+    hf = dict(vocab_size=512, num_mel_bins=16, encoder_layers=2, encoder_attention_heads=4, decoder_layers=2, decoder_attention_heads=4,
+              decoder_ffn_dim=512, encoder_ffn_dim=512, d_model=256, max_source_positions=64, max_target_positions=64, pad_token_id=0,
+              eos_token_id=2, decoder_start_token_id=3, activation_function="gelu")
+    cfg = WhisperInferenceConfig(nc, load_config=lambda c: [setattr(c, k, v) for k, v in hf.items()])
+    app = NeuronApplicationWhisper("<random>", cfg)
+    app.load(None, skip_warmup=True, random_weights=True)
+    toks = app.generate(torch.randn(2, 16, 128), max_new_tokens=6, eos_token_id=-1)
+    assert toks.shape == (2, 7)
