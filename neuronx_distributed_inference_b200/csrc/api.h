@@ -39,6 +39,12 @@ bool gemv2_supported(int T, int K);
 int gemv2_grid(int N, int K, bool glu);
 int gemv2_pmax(int N, int K, bool glu);
 void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* tickets, cudaStream_t stream);
+// chain of up to 4 dependent skinny GEMMs in one persistent launch (gemv2.cu)
+bool gemv_chain_supported(int T, int K_max);
+size_t gemv_chain_ws_floats(const GemvParams* ph, int n);
+size_t gemv_chain_tickets(const GemvParams* ph, int n);
+void gemv_chain_launch(const GemvParams* ph, const int* modes, int n, float* ws_part, unsigned* tickets, unsigned* bar,
+                       cudaStream_t stream);
 // tcgen05 / TMEM / TMA GEMM (gemm_tcgen05.cu): C[M,N_out] = epi(A[M,K] · B[N,K]^T)
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
                          int N, int K, int act, cudaStream_t stream);
@@ -72,6 +78,14 @@ struct AttnDecodeParams {
   unsigned* tickets;       // [B*Hkv]
   int B, T, Hq, Hkv, D, S, L, nsplit, window, block_size, max_blocks;
   float scale;
+  // fused prologue (contiguous decode): q unused; q/k/v taken from the QKV projection output
+  const void* qkv;        // [B, T, (Hq + 2 Hkv) * D] bf16 or null
+  const float* cos;       // [B, T, D/2]
+  const float* sin;
+  const void* q_norm;     // [D] bf16 or null (per-head RMSNorm before RoPE)
+  const void* k_norm;
+  const int* write_pos;   // [B, T] cache slot per active token
+  float norm_eps;
 };
 void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream);
 

@@ -40,6 +40,17 @@ struct AttnArgs {
   unsigned* tickets;
   int B, T, Hq, Hkv, S, L, nsplit, window, block_size, max_blocks;
   float scale_log2;
+  // fused decode prologue (ATTN_DECODE only): q/k/v come straight from the QKV projection; per-head RMSNorm + RoPE are
+  // applied here, the new K/V rows are written to the cache by this CTA before it reads the cache
+  const __nv_bfloat16* qkv;     // [B*T, (Hq + 2 Hkv) * D] or null
+  const float* cos;             // [B*T, D/2]
+  const float* sin;
+  const __nv_bfloat16* q_norm;  // [D] or null
+  const __nv_bfloat16* k_norm;
+  const int* write_pos;         // [B*T] cache slot of every active token (-1 = skip)
+  __nv_bfloat16* k_w;
+  __nv_bfloat16* v_w;
+  float norm_eps;
 };
 
 template <int D>
@@ -118,8 +129,75 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   const int t_beg = t_lo + split * tps;
   const int t_end = min(nt, t_beg + tps);
 
+  // ---- fused prologue: RMSNorm + RoPE on q (-> sQ) and on the new k rows; k/v appended to the cache ----------
+  // Every split-CTA of this (batch, kv head) writes the same rows (identical values), so whichever CTA owns the
+  // tile that contains the new positions reads its own writes: no inter-CTA ordering is needed.
+  const bool fused = (MODE == ATTN_DECODE) && p.qkv != nullptr;
+  if (fused) {
+    constexpr int HALF = D / 2, PPL = HALF / 32;
+    const int nrows = R + 2 * p.T;
+    for (int i = tid; i < (64 - R) * CH; i += ATT_THREADS)   // rows past R stay zero
+      *reinterpret_cast<uint4*>(sQ + swz<D>(R + i / CH, i % CH)) = make_uint4(0u, 0u, 0u, 0u);
+    for (int row = warp; row < nrows; row += ATT_THREADS / 32) {
+      int t, head, kind;
+      if (row < R) { t = row / G; head = kvh * G + row % G; kind = 0; }
+      else if (row < R + p.T) { t = row - R; head = p.Hq + kvh; kind = 1; }
+      else { t = row - R - p.T; head = p.Hq + p.Hkv + kvh; kind = 2; }
+      const size_t bt = (size_t)b * p.T + t;
+      const __nv_bfloat16* src = p.qkv + (bt * (p.Hq + 2 * p.Hkv) + head) * D;
+      float x1[PPL], x2[PPL];
+#pragma unroll
+      for (int j = 0; j < PPL; ++j) {
+        x1[j] = __bfloat162float(src[lane + 32 * j]);
+        x2[j] = __bfloat162float(src[lane + 32 * j + HALF]);
+      }
+      if (kind != 2) {
+        const __nv_bfloat16* nw = kind == 0 ? p.q_norm : p.k_norm;
+        if (nw != nullptr) {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) ss += x1[j] * x1[j] + x2[j] * x2[j];
+          ss = warp_sum(ss);
+          const float rstd = rsqrtf(ss / (float)D + p.norm_eps);
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {   // rounded to bf16 before the rotation, like the unfused path
+            x1[j] = __bfloat162float(__float2bfloat16(x1[j] * rstd * __bfloat162float(nw[lane + 32 * j])));
+            x2[j] = __bfloat162float(__float2bfloat16(x2[j] * rstd * __bfloat162float(nw[lane + 32 * j + HALF])));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+          const float cs = p.cos[bt * HALF + lane + 32 * j], sn = p.sin[bt * HALF + lane + 32 * j];
+          const float o1 = x1[j] * cs - x2[j] * sn, o2 = x2[j] * cs + x1[j] * sn;
+          x1[j] = o1;
+          x2[j] = o2;
+        }
+      }
+      if (kind == 0) {
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+          const int c1 = lane + 32 * j, c2 = c1 + HALF;
+          sQ[swz<D>(row, c1 >> 3) + (c1 & 7)] = __float2bfloat16(x1[j]);
+          sQ[swz<D>(row, c2 >> 3) + (c2 & 7)] = __float2bfloat16(x2[j]);
+        }
+      } else {
+        const int wp = p.write_pos[bt];
+        if (seq_ok && wp >= 0 && wp < p.S) {
+          __nv_bfloat16* dst = (kind == 1 ? p.k_w : p.v_w) + (((size_t)line * p.Hkv + kvh) * p.S + wp) * D;
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {
+            dst[lane + 32 * j] = __float2bfloat16(x1[j]);
+            dst[lane + 32 * j + HALF] = __float2bfloat16(x2[j]);
+          }
+        }
+      }
+    }
+    __threadfence();
+    __syncthreads();
+  }
+
   // ---- Q tile -> shared (swizzled), then A fragments ----------------------------------------------------
-  for (int i = tid; i < 64 * CH; i += ATT_THREADS) {
+  for (int i = tid; i < (fused ? 0 : 64 * CH); i += ATT_THREADS) {
     const int r = i / CH, c = i % CH;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (r < R) {
@@ -391,6 +469,14 @@ void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream) {
   a.B = p.B; a.T = p.T; a.Hq = p.Hq; a.Hkv = p.Hkv; a.S = p.S; a.L = p.L; a.nsplit = p.nsplit; a.window = p.window;
   a.block_size = p.block_size; a.max_blocks = p.max_blocks;
   a.scale_log2 = p.scale * kLog2e;
+  a.qkv = reinterpret_cast<const __nv_bfloat16*>(p.qkv);
+  a.cos = p.cos; a.sin = p.sin;
+  a.q_norm = reinterpret_cast<const __nv_bfloat16*>(p.q_norm);
+  a.k_norm = reinterpret_cast<const __nv_bfloat16*>(p.k_norm);
+  a.write_pos = p.write_pos;
+  a.k_w = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.k_cache));
+  a.v_w = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.v_cache));
+  a.norm_eps = p.norm_eps;
   if (p.T * (p.Hq / p.Hkv) > 64) throw std::runtime_error("attention_decode: T * group size must be <= 64");
   dim3 grid(p.B * p.Hkv, p.nsplit);
   const bool paged = p.block_table != nullptr;

@@ -176,6 +176,56 @@ at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::o
   return y;
 }
 
+// Chain of dependent skinny GEMMs in ONE persistent launch (decode layer tail: o_proj -> gate_up -> down -> next qkv).
+// Per phase i: y[i] = epi( norm?(x[i]) · w[i]^T ); modes[i] == 1 -> fused all-reduce with parity parities[i].
+void gemv_chain(const std::vector<at::Tensor>& xs, const std::vector<at::Tensor>& ws,
+                const std::vector<c10::optional<at::Tensor>>& biases, const std::vector<c10::optional<at::Tensor>>& norms,
+                const std::vector<c10::optional<at::Tensor>>& residuals, std::vector<at::Tensor>& ys,
+                const std::vector<int64_t>& acts, const std::vector<int64_t>& modes, const std::vector<double>& eps,
+                const std::vector<double>& offset,
+                const std::vector<int64_t>& recv_ptrs, const std::vector<int64_t>& flag_ptrs, int64_t rank,
+                const std::vector<int64_t>& parities, int64_t n_max) {
+  const int n = xs.size();
+  TORCH_CHECK(n >= 1 && n <= 4 && (int)ws.size() == n && (int)ys.size() == n && (int)acts.size() == n && (int)modes.size() == n);
+  c10::cuda::CUDAGuard guard(xs[0].device());
+  GemvParams ph[4];
+  int md[4];
+  int kmax = 0;
+  for (int i = 0; i < n; ++i) {
+    check_gemv_inputs(xs[i], ws[i]);
+    TORCH_CHECK(xs[i].size(0) == xs[0].size(0), "gemv_chain: all phases share the token count");
+    ph[i] = GemvParams{};
+    at::Tensor y = ys[i];
+    fill_params(ph[i], xs[i], ws[i], biases[i], norms[i], eps[i], offset[i], (int)acts[i], residuals[i], c10::nullopt, y, true);
+    md[i] = (int)modes[i];
+    if (md[i] == 1) {
+      const int world = recv_ptrs.size();
+      TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS && ph[i].N <= n_max);
+      for (int r = 0; r < world; ++r) {
+        ph[i].symm.recv[r] = reinterpret_cast<float*>(recv_ptrs[r]);
+        ph[i].symm.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+      }
+      ph[i].symm.rank = rank;
+      ph[i].symm.world = world;
+      ph[i].symm.parity = parities[i];
+      ph[i].symm.n_max = n_max;
+    }
+    kmax = std::max(kmax, ph[i].K);
+  }
+  TORCH_CHECK(gemv_chain_supported(ph[0].T, kmax), "gemv_chain: activations too wide for shared memory");
+  static std::unordered_map<int, std::array<at::Tensor, 3>> pool;   // per device: ws, tickets, barrier
+  auto& sl = pool[xs[0].device().index()];
+  auto o = at::TensorOptions().device(xs[0].device());
+  const int64_t need_ws = gemv_chain_ws_floats(ph, n), need_t = gemv_chain_tickets(ph, n);
+  if (!sl[0].defined() || sl[0].numel() < need_ws) sl[0] = at::empty({std::max<int64_t>(need_ws, 8 << 20)}, o.dtype(at::kFloat));
+  if (!sl[1].defined() || sl[1].numel() < need_t) sl[1] = at::zeros({std::max<int64_t>(need_t, 1 << 16)}, o.dtype(at::kInt));
+  if (!sl[2].defined()) sl[2] = at::zeros({4}, o.dtype(at::kInt));
+  gemv_chain_launch(ph, md, n, sl[0].data_ptr<float>(), reinterpret_cast<unsigned*>(sl[1].data_ptr<int>()),
+                    reinterpret_cast<unsigned*>(sl[2].data_ptr<int>()), cur_stream());
+}
+
+bool gemv_chain_ok(int64_t T, int64_t K_max) { return gemv_chain_supported((int)T, (int)K_max); }
+
 // ---- symmetric (peer-mapped) workspace ---------------------------------------------------------------------
 std::tuple<int64_t, pybind11::bytes> symm_alloc(int64_t nbytes) {
   void* p = nullptr;
@@ -325,6 +375,41 @@ at::Tensor attention_decode(const at::Tensor& q, const at::Tensor& k_cache, cons
   return out;
 }
 
+// q/k RMSNorm + RoPE + KV-cache append + split-KV flash decode in ONE kernel (the prologue of the attention kernel).
+at::Tensor rope_attention_decode(const at::Tensor& qkv, const at::Tensor& cos, const at::Tensor& sin, at::Tensor& k_cache,
+                                 at::Tensor& v_cache, const at::Tensor& lines, const at::Tensor& write_pos,
+                                 const at::Tensor& positions, int64_t nq, int64_t nkv, int64_t D, double scale, int64_t window,
+                                 const c10::optional<at::Tensor>& sinks, const c10::optional<at::Tensor>& q_norm,
+                                 const c10::optional<at::Tensor>& k_norm, double eps, int64_t s_hint) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.dim() == 3 && qkv.is_contiguous() && is_bf16(qkv) && is_bf16(k_cache));
+  const int B = qkv.size(0), T = qkv.size(1);
+  TORCH_CHECK(qkv.size(2) == (nq + 2 * nkv) * D && (D == 64 || D == 128) && nq % nkv == 0);
+  TORCH_CHECK(cos.scalar_type() == at::kFloat && cos.is_contiguous() && sin.is_contiguous() &&
+              cos.numel() == (int64_t)B * T * D / 2 && sin.numel() == cos.numel());
+  TORCH_CHECK(k_cache.dim() == 4 && k_cache.size(1) == nkv && k_cache.size(3) == D && k_cache.is_contiguous() &&
+              v_cache.is_contiguous());
+  TORCH_CHECK(lines.scalar_type() == at::kInt && positions.scalar_type() == at::kInt && write_pos.scalar_type() == at::kInt &&
+              positions.is_contiguous() && write_pos.is_contiguous() && lines.numel() == B && positions.numel() == B * T &&
+              write_pos.numel() == B * T);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  auto out = at::empty({B, T, nq, D}, qkv.options());
+  const int L = k_cache.size(0), S = k_cache.size(2);
+  AttnDecodeParams p{};
+  p.q = nullptr; p.k_cache = k_cache.data_ptr(); p.v_cache = v_cache.data_ptr(); p.out = out.data_ptr();
+  p.lines = lines.data_ptr<int>(); p.positions = positions.data_ptr<int>(); p.block_table = nullptr;
+  p.sinks = sinks.has_value() ? sinks->data_ptr<float>() : nullptr;
+  p.B = B; p.T = T; p.Hq = nq; p.Hkv = nkv; p.D = D; p.S = S; p.L = L; p.window = window; p.scale = (float)scale;
+  p.qkv = qkv.data_ptr(); p.cos = cos.data_ptr<float>(); p.sin = sin.data_ptr<float>();
+  p.q_norm = optr(q_norm); p.k_norm = optr(k_norm); p.write_pos = write_pos.data_ptr<int>(); p.norm_eps = (float)eps;
+  p.nsplit = pick_nsplit(B, nkv, s_hint > 0 ? (int)std::min<int64_t>(s_hint, S) : S);
+  auto& ws = scratch(qkv.device(), (int64_t)B * nkv * p.nsplit * 64 * (D + 2), 0, (int64_t)B * nkv);
+  p.ws_o = ws.f.data_ptr<float>();
+  p.ws_ml = p.ws_o + (int64_t)B * nkv * p.nsplit * 64 * D;
+  p.tickets = reinterpret_cast<unsigned*>(ws.tickets.data_ptr<int>());
+  attention_decode_launch(p, cur_stream());
+  return out;
+}
+
 at::Tensor paged_attention_decode(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& v_cache,
                                   const at::Tensor& block_table, const at::Tensor& positions, double scale, int64_t window,
                                   const c10::optional<at::Tensor>& sinks) {
@@ -374,6 +459,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm", &nxdi::rmsnorm);
   m.def("gemv", &nxdi::gemv);
   m.def("gemv_allreduce", &nxdi::gemv_allreduce);
+  m.def("gemv_chain", &nxdi::gemv_chain);
+  m.def("gemv_chain_ok", &nxdi::gemv_chain_ok);
   m.def("gemm", &nxdi::gemm);
   m.def("symm_alloc", &nxdi::symm_alloc);
   m.def("symm_open", &nxdi::symm_open);
@@ -387,5 +474,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("topk_sample", &nxdi::topk_sample);
   m.def("attention_decode", &nxdi::attention_decode);
   m.def("paged_attention_decode", &nxdi::paged_attention_decode);
+  m.def("rope_attention_decode", &nxdi::rope_attention_decode);
   m.def("attention_prefill", &nxdi::attention_prefill);
 }

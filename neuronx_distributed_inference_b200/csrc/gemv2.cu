@@ -21,6 +21,8 @@
 //     flag, no fence.sys round trip and no CTA barrier on the critical path.  Slots are self-resetting and
 //     double-buffered by call parity (see parallel/symm.py).
 #include <algorithm>
+#include <cstring>
+#include <stdexcept>
 #include <string>
 
 #include "api.h"
@@ -478,6 +480,428 @@ void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* ticke
   if (mode == 1) launch_gemv2<false, 1>(pp, stream);
   else if (glu) launch_gemv2<true, 0>(pp, stream);
   else launch_gemv2<false, 0>(pp, stream);
+}
+
+
+// =====================================================================================================================
+// GEMV CHAIN: up to 4 dependent skinny GEMMs in ONE persistent launch (one CTA per SM, grid barriers in between).
+//
+//   decode layer tail:   A  h1  = attn_out · Wo^T  (+ all-reduce) + h
+//                        B  u   = swiglu( rmsnorm(h1) · Wgu^T )
+//                        C  h2  = u · Wd^T        (+ all-reduce) + h1
+//                        D  qkv = rmsnorm(h2) · Wqkv(next layer)^T + b          (or the lm_head for the last layer)
+//
+// Why: at decode the four GEMVs of a layer are separate launches whose fixed cost (launch gap, x prologue, pipeline fill,
+// stream-K tail: ~7-10 us each) dwarfs their streaming time once the weights are sharded (TP4: 12 us of bytes, 70 us of
+// wall clock per layer).  Inside one kernel the TMA producer never stops: weights do not depend on activations, so while
+// the consumer warps sit in the grid barrier and rebuild x for the next phase the producer is already filling the ring
+// (192 KB/SM = ~28 MB chip-wide, ~4 us of HBM time) with the NEXT phase's weights.  A grid barrier costs ~2 us.
+// The body of a phase is gemv2_kernel's (same stage format, stream-K split, ticketed fix-up, LL all-reduce); GLU / MODE
+// are runtime flags here, the stage ring and its mbarrier phases run on across phase boundaries.
+constexpr int CHAIN_MAX_PHASES = 4;
+
+struct ChainPhase {
+  CUtensorMap tmap;
+  GemvParams g;
+  float* ws_part;
+  unsigned* tickets;
+  int p_max, glu, mode, pad_;
+};
+struct ChainParams {
+  ChainPhase ph[CHAIN_MAX_PHASES];
+  unsigned* bar;  // [0] arrival count, [1] generation
+  int n_phases, n_stages, xs_bytes, pad_;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(G2_THREADS, 1) gemv_chain_kernel(const __grid_constant__ ChainParams cp) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NS = cp.n_stages;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* xs = stage_base + (size_t)NS * G2_STAGE_BYTES;
+  float* red = reinterpret_cast<float*>(xs + cp.xs_bytes);
+  float* rstd_s = red + G2_CONSUMER_WARPS * 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(rstd_s + 64);
+  uint64_t* empty_bar = full_bar + G2_MAX_STAGES;
+  __shared__ int s_flag;
+  const int G = gridDim.x, c = blockIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == G2_CONSUMER_WARPS) {
+    // ======================= producer: streams the weights of ALL phases back to back =======================
+    pdl_launch_dependents();
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int pi = 0; pi < cp.n_phases; ++pi) {
+        const ChainPhase& P = cp.ph[pi];
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap) : "memory");
+        const int K = P.g.K, N = P.g.N;
+        const int n_chunks = K / G2_KC;
+        const int n_tiles = P.glu ? ((N >> 1) + 7) >> 3 : (N + 15) >> 4;
+        const long long U = (long long)n_tiles * n_chunks;
+        const long long u_beg = (U * c) / G, u_end = (U * (c + 1)) / G;
+        int tile = (int)(u_beg / n_chunks), chunk = (int)(u_beg % n_chunks);
+        const int count = (int)(u_end - u_beg);
+        for (int i = 0; i < count; ++i) {
+          mbar_wait(&empty_bar[stage], ph ^ 1u);
+          mbar_expect_tx(&full_bar[stage], G2_STAGE_BYTES);
+          uint8_t* dst = stage_base + (size_t)stage * G2_STAGE_BYTES;
+          if (P.glu) {
+            tma_load_3d(dst, &P.tmap, 0, chunk * 4, tile * 8, &full_bar[stage]);
+            tma_load_3d(dst + G2_STAGE_BYTES / 2, &P.tmap, 0, chunk * 4, (N >> 1) + tile * 8, &full_bar[stage]);
+          } else {
+            tma_load_3d(dst, &P.tmap, 0, chunk * 4, tile * 16, &full_bar[stage]);
+          }
+          if (++chunk == n_chunks) { chunk = 0; ++tile; }
+          if (++stage == NS) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================= consumer warps =================================
+  const int g = lane >> 2, t4 = lane & 3;
+  const int ctid = tid;  // 0..255
+  pdl_wait();
+  unsigned my_gen = 0;
+  if (ctid == 0) my_gen = ld_acquire_gpu(cp.bar + 1);
+  long long ibase = 0;  // running unit index of this CTA across phases (stage ring position)
+
+  for (int pi = 0; pi < cp.n_phases; ++pi) {
+    const ChainPhase& P = cp.ph[pi];
+    const GemvParams& p = P.g;
+    const bool GLU = P.glu != 0;
+    const int MODE = P.mode;
+    const int K = p.K, N = p.N, T = p.T;
+    const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(p.x);
+    const __nv_bfloat16* BIAS = reinterpret_cast<const __nv_bfloat16*>(p.bias);
+    const __nv_bfloat16* RES = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+    __nv_bfloat16* Y = reinterpret_cast<__nv_bfloat16*>(p.y);
+    const int xs_stride = K * 2 + 64;
+    const int n_chunks = K / G2_KC;
+    const int n_tiles = GLU ? ((N >> 1) + 7) >> 3 : (N + 15) >> 4;
+    const long long U = (long long)n_tiles * n_chunks;
+    const long long u_beg = (U * c) / G, u_end = (U * (c + 1)) / G;
+
+    // ---- X prologue (inputs of phases > 0 were written by other SMs in this launch: L2 loads only) ----
+    {
+      const int nvec = K >> 3;
+      for (int t = 0; t < T; ++t) {
+        const uint4* src = reinterpret_cast<const uint4*>(X + (size_t)t * p.ldx);
+        uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)t * xs_stride);
+        float acc = 0.f;
+        for (int v = ctid; v < nvec; v += 256) {
+          uint4 q = __ldcg(src + v);
+          dst[v] = q;
+          acc += bf16lo(q.x) * bf16lo(q.x) + bf16hi(q.x) * bf16hi(q.x) + bf16lo(q.y) * bf16lo(q.y) +
+                 bf16hi(q.y) * bf16hi(q.y) + bf16lo(q.z) * bf16lo(q.z) + bf16hi(q.z) * bf16hi(q.z) +
+                 bf16lo(q.w) * bf16lo(q.w) + bf16hi(q.w) * bf16hi(q.w);
+        }
+        if (p.norm_w != nullptr) {
+          acc = warp_sum(acc);
+          if (lane == 0) rstd_s[warp * 8 + t] = acc;
+        }
+      }
+      if (p.norm_w != nullptr) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int t = 0; t < T; ++t) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < G2_CONSUMER_WARPS; ++w) tot += rstd_s[w * 8 + t];
+          const float rstd = rsqrtf(tot / (float)K + p.eps);
+          uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)t * xs_stride);
+          const uint4* gw = reinterpret_cast<const uint4*>(p.norm_w);
+          const float o = p.norm_offset;
+          for (int v = ctid; v < nvec; v += 256) {
+            uint4 q = dst[v];
+            uint4 gm = ldg_cached(gw + v);
+            q.x = pack_bf16(bf16lo(q.x) * rstd * (bf16lo(gm.x) + o), bf16hi(q.x) * rstd * (bf16hi(gm.x) + o));
+            q.y = pack_bf16(bf16lo(q.y) * rstd * (bf16lo(gm.y) + o), bf16hi(q.y) * rstd * (bf16hi(gm.y) + o));
+            q.z = pack_bf16(bf16lo(q.z) * rstd * (bf16lo(gm.z) + o), bf16hi(q.z) * rstd * (bf16hi(gm.z) + o));
+            q.w = pack_bf16(bf16lo(q.w) * rstd * (bf16lo(gm.w) + o), bf16hi(q.w) * rstd * (bf16hi(gm.w) + o));
+            dst[v] = q;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+
+    const bool tok_ok = g < T;
+    const uint8_t* xrow = xs + (size_t)g * xs_stride;
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+
+    auto finalize = [&](int tile, float v_gate_or_val, float v_up) {
+      const int col = ctid >> 4, row = ctid & 15;
+      if (col >= T) return;
+      if (GLU) {
+        if (row >= 8) return;
+        const int n = tile * 8 + row, half = N >> 1;
+        if (n >= half) return;
+        float gate = v_gate_or_val, up = v_up;
+        if (BIAS != nullptr) {
+          gate += __bfloat162float(BIAS[n]);
+          up += __bfloat162float(BIAS[half + n]);
+        }
+        const float a = p.act == 1 ? silu(gate) : (p.act == 2 ? gelu_tanh(gate) : gelu_erf(gate));
+        Y[(size_t)col * p.ldy + n] = __float2bfloat16(a * up);
+      } else {
+        const int n = tile * 16 + row;
+        if (n >= N) return;
+        float v = v_gate_or_val;
+        if (MODE == 0) {
+          if (BIAS != nullptr) v += __bfloat162float(BIAS[n]);
+          if (RES != nullptr) v += bf16lo((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(RES) + (size_t)col * p.ldy + n));
+          Y[(size_t)col * p.ldy + n] = __float2bfloat16(v);
+        } else {
+          const SymmArgs& s = p.symm;
+          const size_t off = (((size_t)(s.parity * s.world + s.rank) * 8 + col) * s.n_max + n) * 2;
+#pragma unroll
+          for (int d = 0; d < SYMM_MAX_RANKS; ++d)
+            if (d < s.world) st_ll(s.recv[d] + off, v, 1u);
+        }
+      }
+    };
+
+    const int count = (int)(u_end - u_beg);
+    int cur_tile = (int)(u_beg / n_chunks);
+    int chunk_first = (int)(u_beg % n_chunks);
+    int seg_beg = 0;
+    long long tile_u0 = u_beg;
+    while (seg_beg < count) {
+      const int seg_len = min(n_chunks - chunk_first, count - seg_beg);
+      const long long u = u_beg + seg_beg + seg_len - 1;
+      // local unit i has ring index ibase + i; warp w owns ring indices == w (mod 8)
+      for (int i = seg_beg + (int)((warp - (ibase + seg_beg)) & 7); i < seg_beg + seg_len; i += G2_CONSUMER_WARPS) {
+        const int chunk = chunk_first + (i - seg_beg);
+        const long long ri = ibase + i;
+        const int stage = (int)(ri % NS);
+        const uint32_t ph = (uint32_t)((ri / NS) & 1);
+        mbar_wait(&full_bar[stage], ph);
+        const __nv_bfloat16* sA = reinterpret_cast<const __nv_bfloat16*>(stage_base + (size_t)stage * G2_STAGE_BYTES);
+        const uint8_t* xk = xrow + (size_t)(chunk * G2_KC + t4 * 8) * 2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kg = j >> 1, ch = ((j & 1) << 2) + t4;
+          const uint4 a0 = *reinterpret_cast<const uint4*>(sA + swz128(g * 4 + kg, ch));
+          const uint4 a1 = *reinterpret_cast<const uint4*>(sA + swz128((g + 8) * 4 + kg, ch));
+          uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+          if (tok_ok) xv = *reinterpret_cast<const uint4*>(xk + j * 64);
+          {
+            const uint32_t a[4] = {a0.x, a1.x, a0.y, a1.y};
+            const uint32_t b[2] = {xv.x, xv.y};
+            mma_bf16_16816(c0, a, b);
+          }
+          {
+            const uint32_t a[4] = {a0.z, a1.z, a0.w, a1.w};
+            const uint32_t b[2] = {xv.z, xv.w};
+            mma_bf16_16816(c1, a, b);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      }
+      {
+        float* r = red + warp * 128;
+        r[g * 8 + 2 * t4] = c0[0] + c1[0];
+        r[g * 8 + 2 * t4 + 1] = c0[1] + c1[1];
+        r[(g + 8) * 8 + 2 * t4] = c0[2] + c1[2];
+        r[(g + 8) * 8 + 2 * t4 + 1] = c0[3] + c1[3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c0[q] = c1[q] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const long long t_first = (long long)cur_tile * n_chunks, t_last = t_first + n_chunks;
+        const bool whole = (tile_u0 == t_first) && (u + 1 == t_last);
+        float va = 0.f, vb = 0.f;
+        if (ctid < 128) {
+          const int col = ctid >> 4, row = ctid & 15;
+#pragma unroll
+          for (int w = 0; w < G2_CONSUMER_WARPS; ++w) {
+            va += red[w * 128 + row * 8 + col];
+            if (GLU) vb += red[w * 128 + ((row + 8) & 15) * 8 + col];
+          }
+        }
+        if (whole) {
+          if (ctid < 128) finalize(cur_tile, va, vb);
+        } else {
+          long long cf = (t_first * G) / U;
+          while (((U * (cf + 1)) / G) <= t_first) ++cf;
+          while (((U * cf) / G) > t_first) --cf;
+          long long cl = ((t_last - 1) * G) / U;
+          while (((U * (cl + 1)) / G) <= t_last - 1) ++cl;
+          while (((U * cl) / G) > t_last - 1) --cl;
+          const int slot = (int)(c - cf), n_parts = (int)(cl - cf + 1);
+          float* my = P.ws_part + ((size_t)cur_tile * P.p_max + slot) * 128;
+          if (ctid < 128) {
+            const int col = ctid >> 4, row = ctid & 15;
+            my[row * 8 + col] = va;
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (ctid == 0) s_flag = (atomicAdd(&P.tickets[cur_tile], 1u) == (unsigned)(n_parts - 1)) ? 1 : 0;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (s_flag) {
+            __threadfence();
+            if (ctid < 128) {
+              const int col = ctid >> 4, row = ctid & 15;
+              float sa = 0.f, sb = 0.f;
+              for (int q = 0; q < n_parts; ++q) {
+                const float* pq = P.ws_part + ((size_t)cur_tile * P.p_max + q) * 128;
+                sa += __ldcg(pq + row * 8 + col);
+                if (GLU) sb += __ldcg(pq + ((row + 8) & 15) * 8 + col);
+              }
+              finalize(cur_tile, sa, sb);
+            }
+            if (ctid == 0) P.tickets[cur_tile] = 0;
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      cur_tile += 1;
+      tile_u0 = u + 1;
+      seg_beg += seg_len;
+      chunk_first = 0;
+    }
+    ibase += count;
+
+    if (MODE == 1) {
+      const SymmArgs& s = p.symm;
+      float* my_recv = s.recv[0];
+#pragma unroll
+      for (int d = 1; d < SYMM_MAX_RANKS; ++d)
+        if (d == s.rank) my_recv = s.recv[d];
+      const int total = T * N;
+      for (int e = c * 256 + ctid; e < total; e += G * 256) {
+        const int col = e / N, n = e % N;
+        float v = 0.f;
+        for (int r = 0; r < s.world; ++r) {
+          float* slot = my_recv + (((size_t)(s.parity * s.world + r) * 8 + col) * s.n_max + n) * 2;
+          float x;
+          uint32_t f;
+          const long long t0 = clock64();
+          while (true) {
+            ld_ll(slot, x, f);
+            if (f != 0u) break;
+            if (clock64() - t0 > 8000000000LL) {
+              printf("gemv_chain: rank %d timed out waiting for rank %d (phase %d col %d n %d)\n", s.rank, r, pi, col, n);
+              __trap();
+            }
+          }
+          st_ll(slot, 0.f, 0u);
+          v += x;
+        }
+        if (BIAS != nullptr) v += __bfloat162float(BIAS[n]);
+        if (RES != nullptr) v += bf16lo((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(RES) + (size_t)col * p.ldy + n));
+        Y[(size_t)col * p.ldy + n] = __float2bfloat16(v);
+      }
+    }
+
+    // ---- grid barrier: the next phase reads what every SM just wrote ----
+    if (pi + 1 < cp.n_phases) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ctid == 0) {
+        __threadfence();
+        const unsigned old = atomicAdd(cp.bar, 1u);
+        if (old == (unsigned)(G - 1)) {
+          atomicExch(cp.bar, 0u);
+          __threadfence();
+          atomicAdd(cp.bar + 1, 1u);
+        } else {
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(cp.bar + 1) == my_gen) {
+            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a grid that is not co-resident would spin forever
+              printf("gemv_chain: grid barrier timeout (cta %d phase %d)\n", c, pi);
+              __trap();
+            }
+          }
+        }
+        ++my_gen;
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+}
+
+// xs region + fixed part for a chain whose widest input has K_max columns
+static size_t chain_fixed_smem(int T, int K_max) {
+  return (size_t)T * (K_max * 2 + 64) + (G2_CONSUMER_WARPS * 128 + 64) * sizeof(float) + 2 * G2_MAX_STAGES * sizeof(uint64_t) + 128 +
+         1024;
+}
+
+bool gemv_chain_supported(int T, int K_max) { return chain_fixed_smem(T, K_max) + 8 * G2_STAGE_BYTES <= G2_SMEM_BUDGET; }
+
+size_t gemv_chain_ws_floats(const GemvParams* ph, int n) {
+  size_t tot = 0;
+  const int G = g2_num_sms();
+  for (int i = 0; i < n; ++i) {
+    const bool glu = ph[i].act != 0;
+    const int n_tiles = glu ? ((ph[i].N / 2) + 7) / 8 : (ph[i].N + 15) / 16;
+    tot += (size_t)n_tiles * (G / n_tiles + 3) * 128;
+  }
+  return tot;
+}
+
+size_t gemv_chain_tickets(const GemvParams* ph, int n) {
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) tot += ph[i].act != 0 ? ((ph[i].N / 2) + 7) / 8 : (ph[i].N + 15) / 16;
+  return tot;
+}
+
+void gemv_chain_launch(const GemvParams* ph, const int* modes, int n, float* ws_part, unsigned* tickets, unsigned* bar,
+                       cudaStream_t stream) {
+  if (n < 1 || n > CHAIN_MAX_PHASES) throw std::runtime_error("gemv_chain: 1..4 phases");
+  ChainParams cp;
+  memset(&cp, 0, sizeof(cp));
+  const int G = g2_num_sms();
+  int K_max = 0;
+  for (int i = 0; i < n; ++i) {
+    ChainPhase& P = cp.ph[i];
+    P.g = ph[i];
+    const bool glu = ph[i].act != 0;
+    make_weight_tmap(&P.tmap, ph[i].w, ph[i].N, ph[i].K, glu ? 8 : 16);
+    const int n_tiles = glu ? ((ph[i].N / 2) + 7) / 8 : (ph[i].N + 15) / 16;
+    P.p_max = G / n_tiles + 3;
+    P.glu = glu ? 1 : 0;
+    P.mode = modes[i];
+    P.ws_part = ws_part;
+    P.tickets = tickets;
+    ws_part += (size_t)n_tiles * P.p_max * 128;
+    tickets += n_tiles;
+    K_max = std::max(K_max, ph[i].K);
+    if (ph[i].K % G2_KC != 0) throw std::runtime_error("gemv_chain: K must be a multiple of 256");
+  }
+  cp.bar = bar;
+  cp.n_phases = n;
+  const size_t fixed = chain_fixed_smem(ph[0].T, K_max);
+  int ns = G2_SMEM_BUDGET > fixed ? (int)((G2_SMEM_BUDGET - fixed) / G2_STAGE_BYTES) : 0;
+  ns = std::min(ns, G2_MAX_STAGES) / 8 * 8;
+  if (ns < 8) throw std::runtime_error("gemv_chain: activations do not fit in shared memory");
+  cp.n_stages = ns;
+  cp.xs_bytes = ph[0].T * (K_max * 2 + 64);
+  auto kern = gemv_chain_kernel;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BUDGET);
+    configured = true;
+  }
+  const size_t smem = fixed + (size_t)ns * G2_STAGE_BYTES;
+  launch_pdl(kern, dim3(G), dim3(G2_THREADS), smem, stream, cp);
 }
 
 }  // namespace nxdi

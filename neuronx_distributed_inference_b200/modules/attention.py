@@ -168,6 +168,12 @@ class AttentionBase(nn.Module):
                 # prefill attention consumes the fresh k/v directly (no cache read): split here
                 q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
                 kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)
+            elif (meta.active_mask is None and self.attention_chunk_size is None and not self.softcap
+                  and getattr(kv_mgr, "k_scale", None) is None and meta.capture is None):
+                o = ops.rope_attention_decode(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, meta.position_ids,
+                                              nq, nkv, D, self.scale, self.sliding_window, self.sinks, qn, kn,
+                                              self.qk_norm_eps, seq_hint=meta.seq_hint)
+                return self._finish(o.reshape(B, T, nq * D), residual, lora, meta)
             else:
                 q = ops.rope_kv_append(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, nq, nkv, D,
                                        False, qn, kn, self.qk_norm_eps)
@@ -199,12 +205,36 @@ class AttentionBase(nn.Module):
             o = ops.attention_decode(q, k_cache, v_cache, lines, vis_pos, self.scale, self.sliding_window,
                                      self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs,
                                      seq_hint=meta.seq_hint, active_base=meta.active_base)
-        o = o.reshape(B, T, nq * D)
+        return self._finish(o.reshape(B, T, nq * D), residual, lora, meta)
+
+    def _finish(self, o, residual, lora, meta):
         out = self.o_proj(o, residual)
         if lora is not None and lora.has("o_proj"):
             from ..parallel import mappings as _m
             out = out + _m.all_reduce(lora("o_proj", o, meta.adapter_ids), self.tp_group)
         return out
+
+    def chain_eligible(self, kv_mgr, dtype) -> bool:
+        """This layer's decode step can run as [rope+append kernel, attention kernel] around the persistent GEMV chain."""
+        k_cache, _ = kv_mgr.get_kv_by_layer_id(self.layer_idx)
+        return (self._simple() and self.kv_group is None and k_cache.dtype == dtype and self.head_dim in (64, 128)
+                and getattr(self.qkv_proj, "scale", None) is None and getattr(self.o_proj, "scale", None) is None
+                and not self.qkv_proj.sequence_parallel_enabled and self.attention_chunk_size is None and not self.softcap)
+
+    def decode_core(self, qkv, meta: AttnMeta, kv_mgr, B: int, T: int) -> torch.Tensor:
+        """qkv [B,T,(nq+2nkv)D] (already projected) -> attention output [B,T,nq*D]: fused q/k norm + RoPE + cache append,
+        then split-KV flash decode."""
+        D, nq, nkv = self.head_dim, self.n_q, self.n_kv
+        cos, sin = self._rope(meta)
+        k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
+        if meta.lines is None:
+            meta.lines = kv_mgr.lines_for(meta.seq_ids)
+        qn = self.q_layernorm.weight if self.qk_norm == "rms_pre_rope" else None
+        kn = self.k_layernorm.weight if self.qk_norm == "rms_pre_rope" else None
+        o = ops.rope_attention_decode(qkv, cos, sin, k_cache, v_cache, meta.lines, meta.write_positions, meta.position_ids,
+                                      nq, nkv, D, self.scale, self.sliding_window, self.sinks, qn, kn, self.qk_norm_eps,
+                                      seq_hint=meta.seq_hint)
+        return o.reshape(B, T, nq * D)
 
     def _forward_flash_decoding(self, qkv, meta, kv_mgr, cos, sin, residual, B, T):
         from . import flashdecode as fd

@@ -119,6 +119,53 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
     return y
 
 
+def gemv_chain_supported(T: int, k_max: int) -> bool:
+    return bool(_C().gemv_chain_ok(int(T), int(k_max)))
+
+
+def gemv_chain(phases, group=None):
+    """Up to four DEPENDENT skinny GEMMs (T <= 8 tokens) in one persistent kernel launch with grid barriers in between
+    (csrc/gemv2.cu ``gemv_chain_kernel``).  ``phases``: list of dicts
+        x         tensor [T,K]  or  int j  (= output of phase j)
+        w         [N,K] bf16;  bias / norm (fused RMSNorm of x) / eps / offset optional
+        residual  tensor [T,N]  or  int j
+        act       None | "silu_mul" | "gelu_tanh_mul" | "gelu_mul"   (GLU epilogue: output N/2 wide)
+        allreduce bool: fused one-shot all-reduce over the group's symmetric workspace
+    Returns the list of outputs.  CUDA only (the decode fast path); callers fall back to ``linear`` otherwise."""
+    T = phases[0]["x"].shape[0]
+    ys, xs, ws, bs, ns, rs, acts, modes, eps, offs, pars = [], [], [], [], [], [], [], [], [], [], []
+    symm = group.symm if group is not None else None
+    for ph in phases:
+        w = ph["w"]
+        glu = ph.get("act") is not None
+        n_out = w.shape[0] // 2 if glu else w.shape[0]
+        ys.append(torch.empty(T, n_out, dtype=w.dtype, device=w.device))
+    for i, ph in enumerate(phases):
+        x = ph["x"]
+        xs.append(ys[x] if isinstance(x, int) else x)
+        ws.append(ph["w"])
+        bs.append(ph.get("bias"))
+        ns.append(ph.get("norm"))
+        r = ph.get("residual")
+        rs.append(ys[r] if isinstance(r, int) else r)
+        acts.append(_ACT_CODES[ph.get("act")])
+        ar = bool(ph.get("allreduce")) and symm is not None
+        modes.append(1 if ar else 0)
+        eps.append(float(ph.get("eps", 1e-6)))
+        offs.append(float(ph.get("offset", 0.0)))
+        if ar:
+            pars.append(symm.parity)
+            symm.parity ^= 1
+            symm.calls += 1
+        else:
+            pars.append(0)
+    stats["gemv_chain"] += 1
+    _C().gemv_chain(xs, ws, bs, ns, rs, ys, acts, modes, eps, offs, symm.recv_ptrs if symm is not None else [],
+                    symm.flag_ptrs if symm is not None else [], symm.rank if symm is not None else 0, pars,
+                    symm.n_max if symm is not None else 0)
+    return ys
+
+
 def apply_rope(x, cos, sin, interleaved: bool = False):
     return ref.apply_rope(x, cos, sin, interleaved)
 
@@ -169,6 +216,24 @@ def attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window=None
                                      int(seq_hint))
     return ref.attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window, chunk, sinks,
                                 active_mask, softcap, k_scale, v_scale, active_base)
+
+
+def rope_attention_decode(qkv, cos, sin, k_cache, v_cache, seq_ids, write_positions, positions, n_q, n_kv, head_dim, scale,
+                          window=None, sinks=None, q_norm=None, k_norm=None, norm_eps: float = 1e-6, seq_hint: int = 0):
+    """Decode attention straight from the QKV projection: per-head q/k RMSNorm, RoPE, cache append and split-KV flash
+    decode in ONE kernel (the append is the attention kernel's prologue).  qkv [B,T,(n_q+2n_kv)D] -> [B,T,n_q,D].
+    Falls back to ``rope_kv_append`` + ``attention_decode`` where the fused kernel does not apply."""
+    B, T = positions.shape
+    D = head_dim
+    if (_use_cuda(qkv) and qkv.dtype in _FAST_DTYPES and k_cache.dtype == qkv.dtype and D in (64, 128) and cos.shape[-1] * 2 == D
+            and T * (n_q // n_kv) <= 64 and os.environ.get("NXDI_B200_FUSED_ROPE_ATTN", "1") != "0"):
+        stats["rope_attn_decode"] += 1
+        return _C().rope_attention_decode(qkv.reshape(B, T, -1), cos.contiguous(), sin.contiguous(), k_cache, v_cache,
+                                          seq_ids.to(torch.int32), write_positions.to(torch.int32).contiguous(),
+                                          positions.to(torch.int32).contiguous(), n_q, n_kv, D, float(scale), int(window or 0),
+                                          sinks, q_norm, k_norm, norm_eps, int(seq_hint))
+    q = rope_kv_append(qkv, cos, sin, k_cache, v_cache, seq_ids, write_positions, n_q, n_kv, D, False, q_norm, k_norm, norm_eps)
+    return attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window, None, sinks, seq_hint=seq_hint)
 
 
 def attention_prefill(q, k, v, scale, causal: bool = True, window=None, chunk=None, key_valid=None,
