@@ -29,6 +29,8 @@ struct GemvParams {
   int act;        // 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up
   int x_in_smem;  // 0: read (already normalised) x through L1 from global
   int wdtype;     // 0 bf16, 1 int8, 2 fp8 e4m3
+  const void* pf_w;  // weights of the NEXT skinny GEMM in the stream (L2 prefetch of its first ring fill) or null
+  int pf_N, pf_K, pf_glu;
   SymmArgs symm;
 };
 

@@ -108,9 +108,18 @@ static void check_gemv_inputs(const at::Tensor& x, const at::Tensor& w) {
   TORCH_CHECK(x.size(1) % 256 == 0 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && w.is_contiguous());
 }
 
+static void set_prefetch(GemvParams& p, const c10::optional<at::Tensor>& next_w, bool next_glu) {
+  if (!next_w.has_value() || !is_bf16(*next_w) || next_w->dim() != 2 || !next_w->is_contiguous() || next_w->size(1) % 256 != 0) return;
+  p.pf_w = next_w->data_ptr();
+  p.pf_N = next_w->size(0);
+  p.pf_K = next_w->size(1);
+  p.pf_glu = next_glu ? 1 : 0;
+}
+
 at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                 const c10::optional<at::Tensor>& norm_w, double eps, double offset, int64_t act,
-                const c10::optional<at::Tensor>& scale, const c10::optional<at::Tensor>& residual) {
+                const c10::optional<at::Tensor>& scale, const c10::optional<at::Tensor>& residual,
+                const c10::optional<at::Tensor>& next_w, bool next_glu) {
   check_gemv_inputs(x, w);
   TORCH_CHECK(!scale.has_value(), "gemv: quantised weights are not wired yet");
   c10::cuda::CUDAGuard guard(x.device());
@@ -124,6 +133,7 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
     TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
   GemvParams p{};
   fill_params(p, xn, w, bias, norm_w, eps, offset, (int)act, residual, scale, y, x_in_smem);
+  set_prefetch(p, next_w, next_glu);
   run_gemv(p, 0, x.device());
   return y;
 }
@@ -150,7 +160,8 @@ at::Tensor gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
 // Row-parallel GEMV -> one-shot all-reduce over NVLink peer buffers -> +bias +residual.  ONE kernel.
 at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                           const c10::optional<at::Tensor>& residual, const std::vector<int64_t>& recv_ptrs,
-                          const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t parity, int64_t n_max) {
+                          const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t parity, int64_t n_max,
+                          const c10::optional<at::Tensor>& next_w, bool next_glu) {
   check_gemv_inputs(x, w);
   const int world = recv_ptrs.size();
   TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS && (int)flag_ptrs.size() == world);
@@ -172,6 +183,7 @@ at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::o
   p.symm.world = world;
   p.symm.parity = parity;
   p.symm.n_max = n_max;
+  set_prefetch(p, next_w, next_glu);
   run_gemv(p, 1, x.device());
   return y;
 }
@@ -219,7 +231,7 @@ void gemv_chain(const std::vector<at::Tensor>& xs, const std::vector<at::Tensor>
   const int64_t need_ws = gemv_chain_ws_floats(ph, n), need_t = gemv_chain_tickets(ph, n);
   if (!sl[0].defined() || sl[0].numel() < need_ws) sl[0] = at::empty({std::max<int64_t>(need_ws, 8 << 20)}, o.dtype(at::kFloat));
   if (!sl[1].defined() || sl[1].numel() < need_t) sl[1] = at::zeros({std::max<int64_t>(need_t, 1 << 16)}, o.dtype(at::kInt));
-  if (!sl[2].defined()) sl[2] = at::zeros({4}, o.dtype(at::kInt));
+  if (!sl[2].defined()) sl[2] = at::zeros({64}, o.dtype(at::kInt));
   gemv_chain_launch(ph, md, n, sl[0].data_ptr<float>(), reinterpret_cast<unsigned*>(sl[1].data_ptr<int>()),
                     reinterpret_cast<unsigned*>(sl[2].data_ptr<int>()), cur_stream());
 }

@@ -151,6 +151,38 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
         if (++stage == NS) { stage = 0; ph ^= 1u; }
       }
     }
+    // ---- warm L2 for the NEXT skinny GEMM of the stream ----
+    // Consecutive decode GEMVs cannot overlap (one 200 KB CTA per SM), so HBM idles for the ~5 us of kernel tail + launch +
+    // x prologue between them.  The producer is done issuing its own loads one ring ahead of the consumers: from here it
+    // asks L2 to fetch exactly what CTA c of the next kernel will request first (its first ring fill, 16-row x 256-col
+    // units of 512-byte row segments); the requests outlive this kernel.  Spread over the 32 lanes.
+    __syncwarp();  // lanes 1..31 wait here until lane 0 has issued the last of this kernel's own loads
+    if (p.pf_w != nullptr) {
+      const int K2 = p.pf_K, N2 = p.pf_N;
+      const int n_chunks2 = K2 / G2_KC;
+      const int n_tiles2 = p.pf_glu ? ((N2 >> 1) + 7) >> 3 : (N2 + 15) >> 4;
+      const long long U2 = (long long)n_tiles2 * n_chunks2;
+      const long long G2 = U2 / 4 < (long long)G ? (U2 / 4 > 0 ? U2 / 4 : 1) : (long long)G;   // gemv2_grid() of the next launch
+      if ((long long)c < G2) {
+        const long long b2 = (U2 * c) / G2, e2 = (U2 * (c + 1)) / G2;
+        const int cnt = (int)((e2 - b2) < (long long)G2_MAX_STAGES ? (e2 - b2) : (long long)G2_MAX_STAGES);
+        const char* W2 = reinterpret_cast<const char*>(p.pf_w);
+        for (int i = 0; i < cnt; ++i) {
+          const long long u2 = b2 + i;
+          const int tile2 = (int)(u2 / n_chunks2), chunk2 = (int)(u2 % n_chunks2);
+          // 16 row segments of 512 bytes (GLU: 8 gate rows + 8 up rows)
+          if (lane < 16) {
+            int row;
+            if (p.pf_glu) row = lane < 8 ? tile2 * 8 + lane : (N2 >> 1) + tile2 * 8 + (lane - 8);
+            else row = tile2 * 16 + lane;
+            if (row < N2) {
+              const char* a = W2 + ((size_t)row * K2 + (size_t)chunk2 * G2_KC) * 2;
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(512) : "memory");
+            }
+          }
+        }
+      }
+    }
     return;
   }
 
@@ -509,7 +541,7 @@ struct ChainPhase {
 };
 struct ChainParams {
   ChainPhase ph[CHAIN_MAX_PHASES];
-  unsigned* bar;  // [0] arrival count, [1] generation
+  unsigned* bar;  // [0] arrival count, [32] generation (separate 128-byte lines: pollers must not queue with arrivals)
   int n_phases, n_stages, xs_bytes, pad_;
 };
 
@@ -580,7 +612,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv_chain_kernel(const __grid_
   const int ctid = tid;  // 0..255
   pdl_wait();
   unsigned my_gen = 0;
-  if (ctid == 0) my_gen = ld_acquire_gpu(cp.bar + 1);
+  if (ctid == 0) my_gen = ld_acquire_gpu(cp.bar + 32);
   long long ibase = 0;  // running unit index of this CTA across phases (stage ring position)
 
   for (int pi = 0; pi < cp.n_phases; ++pi) {
@@ -820,10 +852,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv_chain_kernel(const __grid_
         if (old == (unsigned)(G - 1)) {
           atomicExch(cp.bar, 0u);
           __threadfence();
-          atomicAdd(cp.bar + 1, 1u);
+          atomicAdd(cp.bar + 32, 1u);
         } else {
           const long long t0 = clock64();
-          while (ld_acquire_gpu(cp.bar + 1) == my_gen) {
+          while (ld_acquire_gpu(cp.bar + 32) == my_gen) {
+            __nanosleep(64);
             if (clock64() - t0 > 4000000000LL) {  // ~2 s: a grid that is not co-resident would spin forever
               printf("gemv_chain: grid barrier timeout (cta %d phase %d)\n", c, pi);
               __trap();

@@ -243,6 +243,8 @@ class NeuronBaseModel(nn.Module):
         lora = getattr(self, "lora", None) if meta.adapter_ids is not None else None
         aux_layers = getattr(self, "aux_hidden_layers", None) if output_hidden else None
         aux = []
+        if not is_prefill and h.is_cuda and not getattr(self, "_prefetch_linked", False):
+            self._link_weight_prefetch()
         chain = (not is_prefill and lora is None and aux_layers is None and prev_hidden is None and self._chain_ok(h, meta, kw))
         if chain:
             h = self._decode_layers_chained(h, meta)
@@ -300,6 +302,23 @@ class NeuronBaseModel(nn.Module):
         (reference model_base.py:478-508, modeling_llama.py:1172-1187)."""
         hn = self.final_hidden(h_out)
         return torch.stack([self.gather_logits(head(hn)) for head in self.medusa_heads], 0)
+
+    def _link_weight_prefetch(self):
+        """Tell every decode GEMV which weight matrix the stream touches next (``w._nxdi_next = (next_w, next_is_glu)``):
+        the kernel warms L2 with the first ring fill of its successor while its own tail drains (csrc/gemv2.cu)."""
+        self._prefetch_linked = True
+        from ..modules.mlp import GatedMLP
+        seq = []
+        for layer in self.layers:
+            attn, mlp = getattr(layer, "self_attn", None), getattr(layer, "mlp", None)
+            if attn is None or not hasattr(attn, "qkv_proj") or not isinstance(mlp, GatedMLP):
+                return
+            seq += [(attn.qkv_proj.weight, False), (attn.o_proj.weight, False), (mlp.gate_up_proj.weight, True),
+                    (mlp.down_proj.weight, False)]
+        seq.append((self.lm_head.weight, False))
+        for (w, _), nxt in zip(seq[:-1], seq[1:]):
+            if nxt[0].dtype == torch.bfloat16 and nxt[0].dim() == 2:
+                w._nxdi_next = nxt
 
     # ---- persistent GEMV chain (decode fast path) ---------------------------------------------------------------------
     def _chain_ok(self, h, meta, kw) -> bool:

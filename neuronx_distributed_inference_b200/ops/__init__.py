@@ -63,6 +63,7 @@ def rmsnorm(x, weight, eps: float, offset: float = 0.0, residual=None):
     return ref.rmsnorm(x, weight, eps, offset, residual)
 
 
+_PREFETCH_NEXT = os.environ.get("NXDI_B200_PREFETCH_NEXT", "0") == "1"   # measured: L2 warm-up of the successor costs more than it hides
 _ACT_CODES = {None: 0, "silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
 
 
@@ -80,7 +81,9 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
             if T <= GEMV_MAX_TOKENS and K % 256 == 0:
                 stats["gemv"] += 1
                 r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
-                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2)
+                nxt = getattr(w, "_nxdi_next", None) if _PREFETCH_NEXT else None
+                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2,
+                              nxt[0] if nxt else None, bool(nxt[1]) if nxt else False)
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
             n_out = N // 2 if act is not None else N
@@ -108,7 +111,7 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
             and reduce_dtype in (None, torch.float32)):
         stats["gemv_allreduce"] += 1
         y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None,
-                                      scale)
+                                      scale, getattr(w, "_nxdi_next", None) if _PREFETCH_NEXT else None)
         return y.view(*x.shape[:-1], y.shape[-1])
     y = linear(x, w, None, scale=scale)
     y = mappings.all_reduce(y, group, reduce_dtype=reduce_dtype)

@@ -64,10 +64,10 @@ class SymmetricWorkspace:
         n_max = min((n_max + 15) // 16 * 16, SYMM_MAX_TILES * 16)
         return cls(group, device, n_max)
 
-    def gemv_allreduce(self, x, w, bias=None, residual=None, scale=None):
+    def gemv_allreduce(self, x, w, bias=None, residual=None, scale=None, nxt=None):
         assert scale is None, "quantised fused all-reduce not wired yet"
         y = self._C.gemv_allreduce(x, w, bias, residual, self.recv_ptrs, self.flag_ptrs, self.rank, self.parity,
-                                   self.n_max)
+                                   self.n_max, nxt[0] if nxt else None, bool(nxt[1]) if nxt else False)
         self.parity ^= 1
         self.calls += 1
         return y
