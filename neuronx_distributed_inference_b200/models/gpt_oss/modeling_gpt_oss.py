@@ -61,6 +61,9 @@ class NeuronGptOssForCausalLM(NeuronLlamaForCausalLM):
 
     @staticmethod
     def convert_hf_to_neuron_state_dict(state_dict, config):
+        if any(k.endswith("_blocks") for k in state_dict):      # released MXFP4 checkpoints
+            from .mx_layout_transform import dequantize_mxfp4_state_dict
+            state_dict = dequantize_mxfp4_state_dict(state_dict, config.neuron_config.torch_dtype)
         sd = fuse_qkv_and_gate_up(state_dict, config.num_hidden_layers, fuse_mlp=False)
         out = {}
         for k, v in sd.items():

@@ -114,5 +114,34 @@ class Sampler(nn.Module):
         return ops.sample(logits, top_k, top_p, temp, rand, self.global_topk)
 
 
+class DataParallelSampler(Sampler):
+    """Sampling DP (reference sampling.py:467-579): instead of every rank reducing the vocab-sharded logits of ALL batch rows,
+    an all-to-all hands rank r the full-vocab logits of rows ``r::tp`` — each rank samples ``B/tp`` rows locally (one top-k
+    kernel over the whole vocabulary, no staged distributed top-k) and the tokens are all-gathered back."""
+
+    def forward(self, logits: torch.Tensor, sampling_params: Optional[torch.Tensor] = None,
+                rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+        g = self.tp_group
+        B, Vl = logits.shape
+        if g.size == 1 or not self.vocab_shard or B % g.size != 0:
+            return super().forward(logits, sampling_params, rand)
+        n = B // g.size
+        # [B, V/tp] -> rows grouped by destination rank -> all-to-all -> [tp(source shard), n, V/tp] -> [n, V]
+        send = logits.view(g.size, n, Vl).contiguous()
+        recv = mappings.all_to_all(send, 0, 0, g)
+        full = recv.permute(1, 0, 2).reshape(n, g.size * Vl)
+        sl = slice(g.rank * n, (g.rank + 1) * n)
+        sp = None if sampling_params is None else sampling_params[sl]
+        rd = None if rand is None else rand[sl]
+        vs, self.vocab_shard = self.vocab_shard, False
+        try:
+            toks = super().forward(full, sp, rd)
+        finally:
+            self.vocab_shard = vs
+        return mappings.all_gather(toks.contiguous(), 0, g)
+
+
 def create_sampler(neuron_config, tp_group=None, vocab_shard=True):
+    if getattr(neuron_config.on_device_sampling_config, "sampling_dp_degree", 1) > 1:
+        return DataParallelSampler(neuron_config, tp_group, vocab_shard)
     return Sampler(neuron_config, tp_group, vocab_shard)

@@ -53,3 +53,21 @@ def test_llama_quantized_checkpoint_flow(tmp_path, qtype, qdtype):
     lf = fapp(ids).logits[:, -1].float()
     rel = ((lq - lf).norm() / lf.norm()).item()
     assert rel < (0.03 if qdtype == "int8" else 0.12), rel
+
+
+def test_mxfp4_roundtrip_and_gpt_oss_conversion():
+    import torch
+    from neuronx_distributed_inference_b200.models.gpt_oss.mx_layout_transform import (dequantize_mxfp4, dequantize_mxfp4_state_dict,
+                                                                                        pack_fp4_x4_uint16, quantize_mxfp4)
+    torch.manual_seed(0)
+    w = torch.randn(3, 8, 64)
+    blocks, scales = quantize_mxfp4(w)
+    assert blocks.shape == (3, 8, 2, 16) and scales.shape == (3, 8, 2)
+    back = dequantize_mxfp4(blocks, scales, torch.float32)
+    # e2m1 has 2 significant bits: relative error of a block is bounded by the grid spacing at its largest element
+    assert (back - w).abs().max() <= 0.26 * w.abs().max()
+    again = dequantize_mxfp4(*quantize_mxfp4(back), torch.float32)
+    assert torch.equal(again, back)                                  # values on the grid are reproduced exactly
+    sd = dequantize_mxfp4_state_dict({"layers.0.mlp.experts.down_proj_blocks": blocks, "layers.0.mlp.experts.down_proj_scales": scales})
+    assert sd["layers.0.mlp.experts.down_proj"].shape == (3, 64, 8)
+    assert pack_fp4_x4_uint16(torch.tensor([[1, 2, 3, 15]])).item() == 1 | (2 << 4) | (3 << 8) | (15 << 12)

@@ -44,3 +44,10 @@ def test_llama_tp4_flash_decoding_matches_hf(tiny_ckpt):
 def test_llama_tp2_sequence_parallel_matches_hf(tiny_ckpt):
     # residual stream sharded along the sequence during prefill (all-gather before column-, reduce-scatter after row-parallel)
     _run(2, tiny_ckpt, 29544, SEQUENCE_PARALLEL="1")
+
+
+def test_data_parallel_sampler_matches_distributed_sampler():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29545", os.path.join(ROOT, "tests", "mp", "dp_sampler_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0 and '"ok": true' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
