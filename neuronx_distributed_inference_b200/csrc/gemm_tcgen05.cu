@@ -17,10 +17,11 @@
 
 namespace nxdi {
 
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64, GM_STAGES = 4;
+// GM_BN is a template parameter: 128 for large grids; 64 when a 128-wide tiling would leave SMs idle (prefill with a few
+// hundred tokens: M/128 x N/128 tiles < 2 x #SMs) — twice the CTAs, 96 KB of shared memory so two CTAs share an SM.
+constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
 constexpr int GM_THREADS = 256;
-constexpr int GM_TMEM_COLS = 128;
-constexpr int GM_A_BYTES = GM_BM * GM_BK * 2, GM_B_BYTES = GM_BN * GM_BK * 2;
+constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;
 
 struct GemmParams {
   CUtensorMap tma_a;  // A [M,K]: dims {K, M}, box {64, 128}, SWIZZLE_128B
@@ -91,7 +92,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+template <int GM_BN>
+__global__ void __launch_bounds__(GM_THREADS, GM_BN == 64 ? 2 : 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int GM_B_BYTES = GM_BN * GM_BK * 2;
+  constexpr int GM_TMEM_COLS = GM_BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                  // [STAGES][128][64] bf16, swizzled
@@ -285,21 +289,39 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
   GemmParams p;
   const bool glu = act != 0;
   make_2d(&p.tma_a, a, M, K, lda, GM_BM);
-  make_2d(&p.tma_b, b, N, K, K, glu ? GM_BN / 2 : GM_BN);
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_out_ = glu ? N / 2 : N;
+  const long long tiles128 = (long long)((M + GM_BM - 1) / GM_BM) * ((n_out_ + (glu ? 63 : 127)) / (glu ? 64 : 128));
+  static int force_bn = -1;
+  if (force_bn < 0) {
+    const char* e = getenv("NXDI_B200_GEMM_BN");
+    force_bn = e ? atoi(e) : 0;
+  }
+  const int BN = force_bn ? force_bn : (tiles128 < 2LL * n_sms ? 64 : 128);
+  make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.c = reinterpret_cast<__nv_bfloat16*>(c);
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.act = act;
-  const size_t smem = GM_STAGES * (GM_A_BYTES + GM_B_BYTES) + 256 + 1024;
+  const size_t smem = GM_STAGES * (GM_A_BYTES + BN * GM_BK * 2) + 256 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GM_STAGES * (GM_A_BYTES + 128 * GM_BK * 2) + 256 + 1024);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GM_STAGES * (GM_A_BYTES + 64 * GM_BK * 2) + 256 + 1024);
     configured = true;
   }
   const int n_out = glu ? N / 2 : N;
-  const int tile_n = glu ? GM_BN / 2 : GM_BN;
+  const int tile_n = glu ? BN / 2 : BN;
   dim3 grid((M + GM_BM - 1) / GM_BM, (n_out + tile_n - 1) / tile_n);
-  launch_pdl(gemm_tcgen05_kernel, grid, dim3(GM_THREADS), smem, stream, p);
+  if (BN == 64) launch_pdl(gemm_tcgen05_kernel<64>, grid, dim3(GM_THREADS), smem, stream, p);
+  else launch_pdl(gemm_tcgen05_kernel<128>, grid, dim3(GM_THREADS), smem, stream, p);
 }
 
 }  // namespace nxdi

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
         if (++stage == NS) { stage = 0; ph ^= 1u; }
       }
     }
+#ifdef NXDI_GEMV_PREFETCH_NEXT
     // ---- warm L2 for the NEXT skinny GEMM of the stream ----
     // Consecutive decode GEMVs cannot overlap (one 200 KB CTA per SM), so HBM idles for the ~5 us of kernel tail + launch +
     // x prologue between them.  The producer is done issuing its own loads one ring ahead of the consumers: from here it
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
         }
       }
     }
+#endif
     return;
   }
 

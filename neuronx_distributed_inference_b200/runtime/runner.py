@@ -17,6 +17,7 @@ routing.  What remains of it on B200:
 from __future__ import annotations
 
 import logging
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -63,6 +64,12 @@ class SubModelRunner:
         self.forward_kwargs = forward_kwargs or {}
         self.use_graphs = (device.type == "cuda" and nc.cuda_graphs and not is_prefill
                            and bool(getattr(model, "graph_safe", True)))
+        # context encoding is host-launch bound for short prompts (hundreds of eager launches): replay it from a graph too
+        self.use_prefill_graphs = (device.type == "cuda" and nc.cuda_graphs and is_prefill and bool(getattr(model, "graph_safe", True))
+                                   and nc.torch_dtype == torch.bfloat16 and not nc.is_block_kv_layout and not nc.is_prefix_caching
+                                   and os.environ.get("NXDI_B200_PREFILL_GRAPHS", "1") != "0"
+                                   and hasattr(model, "_kernels_cover_decode") and model._kernels_cover_decode())
+        self._prefill_pool = None
         self._graphs: Dict[Tuple, _Graph] = {}
         self.pad_token_id = getattr(config, "pad_token_id", None) or nc.pad_token_id or 0
         self.batch_buckets = sorted(set((nc.token_generation_batches or []) + [batch_size])) \
@@ -201,10 +208,62 @@ class SubModelRunner:
         if mask is not None and mask.device.type == "cpu" and bool(mask.all()):
             mask = None   # no padding anywhere: skip the mask plumbing (decided on the host, no device sync)
         self.n_launch += 1
+        kwargs = self._common_kwargs(kw)
+        if self.use_prefill_graphs and not any(torch.is_tensor(v) for v in kwargs.values()) and not kwargs.get("has_prefix") \
+                and ids.shape[1] <= 2048:
+            return self._run_prefill_graph(ids, mask, pos, seq_ids, sampling_params, kwargs)
         with torch.no_grad():
             return self.model(_to_dev(ids, dev), _to_dev(mask, dev), _to_dev(pos, dev, torch.int32),
                               _to_dev(seq_ids, dev, torch.int32), _to_dev(sampling_params, dev, torch.float32),
-                              is_prefill=True, **self._common_kwargs(kw))
+                              is_prefill=True, **kwargs)
+
+    def _run_prefill_graph(self, ids, mask, pos, seq_ids, sampling_params, kwargs):
+        dev = self.device
+        B, T = ids.shape
+        key = ("cte", B, T, mask is not None, tuple(sorted((k, v) for k, v in kwargs.items())))
+        g = self._graphs.get(key)
+        if g is None:
+            g = _Graph()
+            g.inputs = dict(input_ids=torch.zeros(B, T, dtype=torch.long, device=dev),
+                            position_ids=torch.zeros(B, T, dtype=torch.int32, device=dev),
+                            seq_ids=torch.full((B,), -1, dtype=torch.int32, device=dev),
+                            sampling_params=torch.tensor([[1.0, 1.0, 1.0]], device=dev).repeat(B, 1))
+            if mask is not None:
+                g.inputs["mask"] = torch.ones(B, T, dtype=torch.int32, device=dev)
+            si = g.inputs
+            si["position_ids"].copy_(torch.arange(T, device=dev).view(1, T).expand(B, T))
+
+            def run():
+                return self.model(si["input_ids"], si.get("mask"), si["position_ids"], si["seq_ids"], si["sampling_params"],
+                                  is_prefill=True, **kwargs)
+            st = torch.cuda.Stream(device=dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.no_grad(), torch.cuda.stream(st):
+                run()          # warm-up outside capture (lazy tables, workspaces); writes go to the garbage line
+            torch.cuda.current_stream(dev).wait_stream(st)
+            torch.cuda.synchronize(dev)
+            self._symm_even()
+            graph = torch.cuda.CUDAGraph()
+            if self._prefill_pool is None:
+                self._prefill_pool = torch.cuda.graph_pool_handle()
+            with torch.no_grad(), torch.cuda.graph(graph, stream=st, pool=self._prefill_pool):
+                g.out = run()
+                self._symm_even()
+            g.graph = graph
+            self._graphs[key] = g
+            logger.debug("captured %s prefill graph B=%d T=%d", self.tag, B, T)
+        si = g.inputs
+        si["input_ids"].copy_(ids, non_blocking=True)
+        si["position_ids"].copy_(pos, non_blocking=True)
+        si["seq_ids"].copy_(seq_ids, non_blocking=True)
+        if mask is not None:
+            si["mask"].copy_(mask, non_blocking=True)
+        if sampling_params is not None:
+            si["sampling_params"].copy_(sampling_params, non_blocking=True)
+        self._symm_even()
+        g.graph.replay()
+        o = g.out
+        return ModelOutput(tokens=o.tokens, logits=o.logits, hidden_states=o.hidden_states)
 
     # ---- decode ------------------------------------------------------------------------------
     def _pick_batch_bucket(self, B):
