@@ -88,6 +88,8 @@ struct Gemv2Params {
   unsigned* tickets;  // [n_tiles]
   int p_max;
   int n_stages;
+  int whole_tiles;  // 1: CTAs own whole 16-row tiles (no stream-K fix-up); chosen for small weights where the fix-up
+                    // round trips (partials + ticket + re-read) cost more than the tile-count imbalance
 };
 
 template <bool GLU, int MODE>
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
   const int n_tiles = GLU ? ((N >> 1) + 7) >> 3 : (N + 15) >> 4;
   const long long U = (long long)n_tiles * n_chunks;
   const int G = gridDim.x, c = blockIdx.x;
-  const long long u_beg = (U * c) / G, u_end = (U * (c + 1)) / G;
+  const long long u_beg = pp.whole_tiles ? ((long long)n_tiles * c / G) * n_chunks : (U * c) / G;
+  const long long u_end = pp.whole_tiles ? ((long long)n_tiles * (c + 1) / G) * n_chunks : (U * (c + 1)) / G;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -192,12 +195,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
   const int g = lane >> 2, t4 = lane & 3;
   const int ctid = tid;  // 0..255
   pdl_wait();
-  // ---- X prologue: (optional RMSNorm) -> bf16 in shared memory ----
+  // ---- X prologue: x * gamma -> bf16 in shared memory, ONE pass; the per-token 1/rms is a scalar, so it is applied to the
+  //      fp32 accumulators in the epilogue instead of to x (saves the second pass over x and one CTA barrier).
+  //      All T rows are fetched in one flattened loop: the loads are independent, one L2 latency in total.
   {
     float ss[GEMV_MAX_T];
 #pragma unroll
     for (int t = 0; t < GEMV_MAX_T; ++t) ss[t] = 0.f;
     const int nvec = K >> 3;
+    const bool has_norm = p.norm_w != nullptr;
+    const uint4* gw = reinterpret_cast<const uint4*>(p.norm_w);
+    const float o = p.norm_offset;
 #pragma unroll
     for (int t = 0; t < GEMV_MAX_T; ++t) {
       if (t >= T) break;
@@ -206,14 +214,21 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
       float acc = 0.f;
       for (int v = ctid; v < nvec; v += 256) {
         uint4 q = ldg_cached(src + v);
+        if (has_norm) {
+          acc += bf16lo(q.x) * bf16lo(q.x) + bf16hi(q.x) * bf16hi(q.x) + bf16lo(q.y) * bf16lo(q.y) +
+                 bf16hi(q.y) * bf16hi(q.y) + bf16lo(q.z) * bf16lo(q.z) + bf16hi(q.z) * bf16hi(q.z) +
+                 bf16lo(q.w) * bf16lo(q.w) + bf16hi(q.w) * bf16hi(q.w);
+          const uint4 gm = ldg_cached(gw + v);
+          q.x = pack_bf16(bf16lo(q.x) * (bf16lo(gm.x) + o), bf16hi(q.x) * (bf16hi(gm.x) + o));
+          q.y = pack_bf16(bf16lo(q.y) * (bf16lo(gm.y) + o), bf16hi(q.y) * (bf16hi(gm.y) + o));
+          q.z = pack_bf16(bf16lo(q.z) * (bf16lo(gm.z) + o), bf16hi(q.z) * (bf16hi(gm.z) + o));
+          q.w = pack_bf16(bf16lo(q.w) * (bf16lo(gm.w) + o), bf16hi(q.w) * (bf16hi(gm.w) + o));
+        }
         dst[v] = q;
-        acc += bf16lo(q.x) * bf16lo(q.x) + bf16hi(q.x) * bf16hi(q.x) + bf16lo(q.y) * bf16lo(q.y) +
-               bf16hi(q.y) * bf16hi(q.y) + bf16lo(q.z) * bf16lo(q.z) + bf16hi(q.z) * bf16hi(q.z) +
-               bf16lo(q.w) * bf16lo(q.w) + bf16hi(q.w) * bf16hi(q.w);
       }
       ss[t] = acc;
     }
-    if (p.norm_w != nullptr) {
+    if (has_norm) {
 #pragma unroll
       for (int t = 0; t < GEMV_MAX_T; ++t) {
         if (t < T) {
@@ -221,28 +236,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
           if (lane == 0) rstd_s[warp * 8 + t] = v;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int t = 0; t < T; ++t) {
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < G2_CONSUMER_WARPS; ++w) tot += rstd_s[w * 8 + t];
-        const float rstd = rsqrtf(tot / (float)K + p.eps);
-        uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)t * xs_stride);
-        const uint4* gw = reinterpret_cast<const uint4*>(p.norm_w);
-        for (int v = ctid; v < nvec; v += 256) {
-          uint4 q = dst[v];
-          uint4 gm = ldg_cached(gw + v);
-          const float o = p.norm_offset;
-          q.x = pack_bf16(bf16lo(q.x) * rstd * (bf16lo(gm.x) + o), bf16hi(q.x) * rstd * (bf16hi(gm.x) + o));
-          q.y = pack_bf16(bf16lo(q.y) * rstd * (bf16lo(gm.y) + o), bf16hi(q.y) * rstd * (bf16hi(gm.y) + o));
-          q.z = pack_bf16(bf16lo(q.z) * rstd * (bf16lo(gm.z) + o), bf16hi(q.z) * rstd * (bf16hi(gm.z) + o));
-          q.w = pack_bf16(bf16lo(q.w) * rstd * (bf16lo(gm.w) + o), bf16hi(q.w) * rstd * (bf16hi(gm.w) + o));
-          dst[v] = q;
-        }
-      }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
+  // 1/rms of token `col` (valid after the barrier above; read in the epilogue)
+  auto rstd_of = [&](int col) -> float {
+    if (p.norm_w == nullptr) return 1.f;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < G2_CONSUMER_WARPS; ++w) tot += rstd_s[w * 8 + col];
+    return rsqrtf(tot / (float)K + p.eps);
+  };
 
   const bool tok_ok = g < T;
   const uint8_t* xrow = xs + (size_t)g * xs_stride;
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
       if (row >= 8) return;
       const int n = tile * 8 + row, half = N >> 1;
       if (n >= half) return;
-      float gate = v_gate_or_val, up = v_up;
+      const float rs = rstd_of(col);
+      float gate = v_gate_or_val * rs, up = v_up * rs;
       if (BIAS != nullptr) {
         gate += __bfloat162float(BIAS[n]);
         up += __bfloat162float(BIAS[half + n]);
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) gemv2_kernel(const __grid_const
     } else {
       const int n = tile * 16 + row;
       if (n >= N) return;
-      float v = v_gate_or_val;
+      float v = v_gate_or_val * rstd_of(col);
       if (MODE == 0) {
         if (BIAS != nullptr) v += __bfloat162float(BIAS[n]);
         if (RES != nullptr) v += __bfloat162float(RES[(size_t)col * p.ldy + n]);
@@ -439,8 +444,31 @@ bool gemv2_supported(int T, int K) {
   return K % G2_KC == 0 && g2_fixed_smem(T, K) + 8 * G2_STAGE_BYTES <= G2_SMEM_BUDGET;
 }
 
+// Small weights: whole tiles per CTA (no cross-CTA fix-up).  Large weights: stream-K (perfect byte balance matters more).
+static bool g2_whole_tiles(int N, int K, bool glu) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("NXDI_B200_GEMV_WHOLE_TILES");
+    mode = e ? atoi(e) : 2;   // 0 never, 1 always, 2 heuristic
+  }
+  if (mode != 2) return mode == 1;
+  const int n_tiles = glu ? ((N / 2) + 7) / 8 : (N + 15) / 16;
+  const int sms = g2_num_sms();
+  const int active = std::min(sms, n_tiles);
+  const int per = (n_tiles + active - 1) / active;            // tiles of the busiest CTA
+  const double tile_bytes = 16.0 * K * 2;
+  // one SM pulls at most ~100 GB/s; all of them together ~6 TB/s (bytes per microsecond below)
+  const double bw_sm = std::min(100e3, 6.0e6 / active);
+  const double t_whole = per * tile_bytes / bw_sm;
+  // stream-K: perfectly balanced bytes + the fix-up (partials, ticket, re-read: ~3.5-4 us; tools/bench_gemv_fixed.py:
+  // 4096x4096 11.1 -> 6.8 us, 1536x4096 10.4 -> 4.6 us once it is gone; Llama-8B decode 3.67 -> 3.19 ms/step)
+  const double t_streamk = (double)N * K * 2 / 6.0e6 + 4.0;
+  return t_whole <= t_streamk + 0.5;
+}
+
 int gemv2_grid(int N, int K, bool glu) {
   const int n_tiles = glu ? ((N / 2) + 7) / 8 : (N + 15) / 16;
+  if (g2_whole_tiles(N, K, glu)) return std::min(g2_num_sms(), n_tiles);
   const long long U = (long long)n_tiles * (K / G2_KC);
   return (int)std::min<long long>(g2_num_sms(), std::max<long long>(U / 4, 1));
 }
@@ -498,6 +526,7 @@ void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* ticke
   pp.tickets = tickets;
   const bool glu = p.act != 0;
   pp.p_max = gemv2_pmax(p.N, p.K, glu);
+  pp.whole_tiles = g2_whole_tiles(p.N, p.K, glu) ? 1 : 0;
   const size_t fixed = g2_fixed_smem(p.T, p.K);
   // Ring depth: a MULTIPLE OF 8 stages.  Consumer warp w owns the units i == w (mod 8); with NS % 8 == 0 it always
   // meets the same stages, lap after lap, so its mbarrier phase parity is unambiguous (with NS = 10 a warp could
