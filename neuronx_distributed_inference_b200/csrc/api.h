@@ -66,6 +66,10 @@ void argmax_launch(const void* logits, int dtype /*0 f32, 1 bf16*/, int64_t* out
 void topk_sample_launch(const void* logits, int dtype, const int* top_k, const float* top_p, const float* temperature,
                         const float* rand, int64_t* out, int B, int V, int ld, int K, cudaStream_t stream);
 
+// MoE decode: routed experts for T <= 8 tokens as two batched streaming launches (moe_decode.cu)
+void moe_decode_launch(const void* x, const void* w_gate_up, const void* w_down, const float* topk_w, const int* topk_i, void* u,
+                       float* y_acc, int T, int topk, int H, int I, int E, int expert_offset, int n_sms, cudaStream_t stream);
+
 struct AttnDecodeParams {
   const void* q;        // [B, T, Hq, D] bf16
   const void* k_cache;  // contiguous [L, Hkv, S, D] or paged [nblk, bs, Hkv, D]

@@ -238,6 +238,26 @@ void gemv_chain(const std::vector<at::Tensor>& xs, const std::vector<at::Tensor>
 
 bool gemv_chain_ok(int64_t T, int64_t K_max) { return gemv_chain_supported((int)T, (int)K_max); }
 
+// Routed experts of a decode step: x [T,H], w_gate_up [E,2I,H], w_down [E,H,I], topk_w/topk_i [T,k] -> [T,H] (local experts only;
+// the caller all-reduces across EP/TP ranks).
+at::Tensor moe_decode(const at::Tensor& x, const at::Tensor& w_gate_up, const at::Tensor& w_down, const at::Tensor& topk_w,
+                      const at::Tensor& topk_i, int64_t expert_offset) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && is_bf16(x) && is_bf16(w_gate_up) && is_bf16(w_down));
+  TORCH_CHECK(w_gate_up.dim() == 3 && w_down.dim() == 3 && w_gate_up.is_contiguous() && w_down.is_contiguous());
+  const int T = x.size(0), H = x.size(1), E = w_gate_up.size(0), I = w_gate_up.size(1) / 2, k = topk_i.size(1);
+  TORCH_CHECK(w_gate_up.size(2) == H && w_down.size(0) == E && w_down.size(1) == H && w_down.size(2) == I);
+  TORCH_CHECK(topk_w.scalar_type() == at::kFloat && topk_i.scalar_type() == at::kInt && topk_w.is_contiguous() &&
+              topk_i.is_contiguous() && topk_w.numel() == (int64_t)T * k && topk_i.size(0) == T);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto u = at::empty({(int64_t)T * k, I}, x.options());
+  auto y = at::zeros({T, H}, x.options().dtype(at::kFloat));
+  static int n_sms = 0;
+  if (n_sms == 0) n_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  moe_decode_launch(x.data_ptr(), w_gate_up.data_ptr(), w_down.data_ptr(), topk_w.data_ptr<float>(), topk_i.data_ptr<int>(),
+                    u.data_ptr(), y.data_ptr<float>(), T, k, H, I, E, (int)expert_offset, n_sms, cur_stream());
+  return y.to(x.scalar_type());
+}
+
 // ---- symmetric (peer-mapped) workspace ---------------------------------------------------------------------
 std::tuple<int64_t, pybind11::bytes> symm_alloc(int64_t nbytes) {
   void* p = nullptr;
@@ -472,6 +492,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemv", &nxdi::gemv);
   m.def("gemv_allreduce", &nxdi::gemv_allreduce);
   m.def("gemv_chain", &nxdi::gemv_chain);
+  m.def("moe_decode", &nxdi::moe_decode);
   m.def("gemv_chain_ok", &nxdi::gemv_chain_ok);
   m.def("gemm", &nxdi::gemm);
   m.def("symm_alloc", &nxdi::symm_alloc);

@@ -60,7 +60,8 @@ class DbrxBlock(nn.Module):
 
 
 class NeuronDbrxModel(NeuronBaseModel):
-    graph_safe = False
+    graph_safe = False            # the torch expert dispatch synchronises ...
+    moe_decode_graph_safe = True  # ... but decode (T <= 8) runs the moe_decode kernels: CUDA graphs allowed when they apply
 
     def setup_attr_for_model(self, config):
         nc = config.neuron_config

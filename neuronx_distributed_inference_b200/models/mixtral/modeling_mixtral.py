@@ -22,7 +22,8 @@ class MixtralInferenceConfig(LlamaInferenceConfig):
 
 
 class NeuronMixtralModel(NeuronLlamaModel):
-    graph_safe = False   # expert dispatch of the torch fallback synchronises; the MoE decode kernel lifts this
+    graph_safe = False            # the torch expert dispatch synchronises ...
+    moe_decode_graph_safe = True  # ... but decode (T <= 8) runs the moe_decode kernels: CUDA graphs allowed when they apply
 
     def make_layer(self, config, i, rotary, device):
         nc = config.neuron_config

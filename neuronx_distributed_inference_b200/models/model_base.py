@@ -85,12 +85,28 @@ class NeuronBaseModel(nn.Module):
         # CUDA-graph capture needs every op of the decode step to be sync-free: true for the hand-written kernel path
         # (bf16, head_dim 64/128); the PyTorch composite fallbacks (odd head dims, fp8 KV, expert dispatch) are not.
         self.graph_safe = bool(getattr(type(self), "graph_safe", True)) and (self._kernels_cover_decode() or self._fallback_is_sync_free())
+        if not self.graph_safe and getattr(type(self), "moe_decode_graph_safe", False):
+            # MoE families whose routed experts run through the moe_decode kernels (no host-side dispatch)
+            self.graph_safe = self._kernels_cover_decode() and self._moe_kernels_cover_decode()
 
     def _fallback_is_sync_free(self) -> bool:
         """Dense decoder on the contiguous cache with a garbage line: the PyTorch composite path has no host sync either."""
         nc = self.neuron_config
         return (not nc.is_block_kv_layout and not nc.kv_cache_quant and getattr(self.kv_mgr, "garbage", 0) == 1
                 and not any(getattr(l, "mlp_is_moe", False) for l in self.layers))
+
+    def _moe_kernels_cover_decode(self) -> bool:
+        if self.device_ is None or torch.device(self.device_).type != "cuda":
+            return False
+        for layer in self.layers:
+            if not getattr(layer, "mlp_is_moe", False):
+                continue
+            moe = layer.mlp
+            ex = getattr(moe, "expert_mlps", None)
+            if ex is None or getattr(moe, "early_affinity_modulation", False) or ex.act != "silu_mul" or ex.act_fn is not None \
+                    or ex.gate_up_bias is not None or ex.down_bias is not None or ex.gate_up_proj.dtype != torch.bfloat16:
+                return False
+        return True
 
     def _kernels_cover_decode(self) -> bool:
         nc = self.neuron_config

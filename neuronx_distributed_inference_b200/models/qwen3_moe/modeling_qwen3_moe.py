@@ -31,7 +31,8 @@ def _is_moe_layer(config, i):
 
 
 class NeuronQwen3MoeModel(NeuronLlamaModel):
-    graph_safe = False
+    graph_safe = False            # the torch expert dispatch synchronises ...
+    moe_decode_graph_safe = True  # ... but decode (T <= 8) runs the moe_decode kernels: CUDA graphs allowed when they apply
 
     def make_layer(self, config, i, rotary, device):
         nc = config.neuron_config

@@ -297,8 +297,8 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
     N = x.shape[0]
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and w_gate_up.dtype == x.dtype and act == "silu_mul"
             and act_fn is None and gate_up_bias is None and down_bias is None and N <= GEMV_MAX_TOKENS and not scale_input
-            and hasattr(_C(), "moe_decode")
-            and x.shape[1] % 256 == 0 and w_down.shape[1] % 256 == 0):
+            and w_gate_up.is_contiguous() and w_down.is_contiguous() and topk_i.dim() == 2
+            and x.shape[1] % 8 == 0 and w_down.shape[2] % 8 == 0 and max(x.shape[1], w_down.shape[2]) * 2 <= 65536):
         stats["moe_decode"] += 1
         return _C().moe_decode(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(),
                                topk_i.to(torch.int32).contiguous(), int(expert_offset))

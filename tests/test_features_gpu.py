@@ -116,3 +116,32 @@ def test_whisper_random_weights_gpu():
     app.load(None, skip_warmup=True, random_weights=True)
     toks = app.generate(torch.randn(2, 16, 128), max_new_tokens=6, eos_token_id=-1)
     assert toks.shape == (2, 7)
+
+
+def test_mixtral_decode_runs_under_cuda_graphs_with_moe_kernels():
+    """MoE decode: routed experts through the moe_decode kernels, whole step replayed from a CUDA graph, tokens equal the
+    eager (graph-free) run of the same model."""
+    from neuronx_distributed_inference_b200 import ops
+    from neuronx_distributed_inference_b200.models.mixtral.modeling_mixtral import NeuronMixtralForCausalLM
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    hf = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+              head_dim=64, num_local_experts=4, num_experts_per_tok=2)
+
+    def mk(graphs):
+        return build_random_llama(hf, batch_size=2, seq_len=128, max_context_length=32, device="cuda", dtype="bfloat16", seed=9,
+                                  app_cls=NeuronMixtralForCausalLM, cuda_graphs=graphs)
+    app = mk(True)
+    assert app.model.graph_safe and app.token_generation_model.use_graphs
+    ids = torch.randint(1, 512, (2, 9))
+
+    def run(a):
+        t = a(ids, attention_mask=torch.ones_like(ids)).tokens.view(2, 1).cpu()
+        out = [t]
+        for i in range(6):
+            t = a(t, position_ids=torch.full((2, 1), 9 + i, dtype=torch.int32)).tokens.view(2, 1).cpu()
+            out.append(t)
+        return torch.cat(out, 1)
+    before = ops.stats["moe_decode"]
+    got = run(app)
+    assert ops.stats["moe_decode"] > before and len(app.token_generation_model._graphs) > 0
+    assert torch.equal(got, run(mk(False)))

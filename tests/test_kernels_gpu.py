@@ -276,3 +276,21 @@ def test_rope_attention_decode_equals_two_kernel_path(D, nq, nkv, T, ctx, qk_nor
     assert ops.stats["rope_attn_decode"] > 0
     assert torch.equal(k1, k2) and torch.equal(v1, v2)
     assert (got.float() - exp.float()).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("T,k,E,H,I,off", [(2, 2, 8, 4096, 1792, 0), (1, 4, 16, 2048, 768, 0), (8, 2, 4, 1024, 512, 2), (3, 8, 64, 2048, 256, 16)])
+def test_moe_decode_kernels_match_reference(T, k, E, H, I, off):
+    torch.manual_seed(0)
+    dev, dt = "cuda", torch.bfloat16
+    x = torch.randn(T, H, device=dev, dtype=dt)
+    wgu = (torch.randn(E, 2 * I, H, device=dev) * 0.03).to(dt)
+    wd = (torch.randn(E, H, I, device=dev) * 0.03).to(dt)
+    n_global = E + 2 * off                     # some slots route to experts owned by other ranks
+    idx = torch.stack([torch.randperm(n_global, device=dev)[:k] for _ in range(T)])
+    w = torch.rand(T, k, device=dev)
+    before = ops.stats["moe_decode"]
+    got = ops.moe_experts(x, wgu, wd, w, idx, "silu_mul", off)
+    assert ops.stats["moe_decode"] == before + 1
+    exp = ref.moe_experts(x, wgu, wd, w, idx, "silu_mul", off)
+    err = (got.float() - exp.float()).abs().max().item()
+    assert err <= 0.02 * exp.float().abs().max().item() + 0.02, err
