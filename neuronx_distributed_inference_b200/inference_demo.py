@@ -232,6 +232,9 @@ def run_inference(model_cls, args):
         dnc.enable_fused_speculation = False
         dnc.speculation_length = 0
         dnc.is_draft_model = True
+        dnc.is_eagle_draft = bool(nc.enable_eagle_speculation)   # EAGLE: the draft consumes target features
+        dnc.enable_eagle_speculation = False
+        dnc.token_tree_config, dnc.enable_token_tree, dnc.is_medusa = None, False, False
         dcfg = cfg_cls(dnc, load_config=load_pretrained_config(args.draft_model_path))
         config.fused_spec_config = FusedSpecNeuronConfig(model_cls._model_cls, draft_config=dcfg,
                                                          draft_model_path=args.draft_model_path)

@@ -128,7 +128,7 @@ class NeuronApplicationBase(nn.Module):
                 expert_model_parallel_size=ep, context_parallel_size=nc.cp_degree,
                 attention_dp_size=nc.attention_dp_degree, moe_tp_size=getattr(nc, "moe_tp_degree", None),
                 kv_shared_size=(getattr(self.config.get_text_config(), "num_cores_per_group", 1)
-                                if nc.flash_decoding_enabled else 1))
+                                if (nc.flash_decoding_enabled or nc.attention_dp_degree > 1 or nc.cp_degree > 1) else 1))
 
     # ---- compile / load -----------------------------------------------------------------------
     def compile(self, compiled_model_path: str, debug: bool = False, pre_shard_weights_hook=None,

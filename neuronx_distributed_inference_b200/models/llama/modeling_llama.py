@@ -34,7 +34,8 @@ class LlamaInferenceConfig(InferenceConfig):
             self.head_dim = self.hidden_size // self.num_attention_heads
         if not hasattr(self, "hidden_act"):
             self.hidden_act = "silu"
-        if self.neuron_config.flash_decoding_enabled:
+        nc_ = self.neuron_config
+        if nc_.flash_decoding_enabled or nc_.attention_dp_degree > 1 or nc_.cp_degree > 1:
             from ...modules.flashdecode import calculate_num_cores_per_group
             self.num_cores_per_group = calculate_num_cores_per_group(
                 self.num_attention_heads, self.num_key_value_heads, self.neuron_config.tp_degree)

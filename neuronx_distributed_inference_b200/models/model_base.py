@@ -154,8 +154,12 @@ class NeuronBaseModel(nn.Module):
                       num_lines=lines, dtype=dtype, device=self.device_,
                       quant_config=nc.kv_quant_config if nc.kv_cache_quant else None)
             if nc.attention_dp_degree > 1:
-                from ..parallel.state import get_data_parallel_attention_group
-                g = get_data_parallel_attention_group()
+                # attention DP lives inside the KV-replication group (ranks that would otherwise hold identical KV)
+                from ..parallel.state import get_kv_shared_group
+                g = get_kv_shared_group()
+                if g.size != nc.attention_dp_degree:
+                    raise NotImplementedError(f"attention_dp_degree ({nc.attention_dp_degree}) must equal the KV replication "
+                                              f"factor tp/num_kv_heads ({g.size}) — see DESIGN.md §5")
                 self.kv_mgr = DataParallelKVCacheManager(dp_rank=g.rank, dp_size=g.size, **kw)
             else:
                 self.kv_mgr = KVCacheManager(**kw)

@@ -118,6 +118,14 @@ class AttentionBase(nn.Module):
             self.kv_group = None
         if self.kv_group is not None and (sliding_window or attention_chunk_size or learned_sinks):
             raise NotImplementedError("flash decoding with sliding-window / chunked / sink attention")
+        # attention DP (decode) and context parallelism (prefill) inside the KV-replication group: the ranks that hold the same
+        # KV head split the BATCH (DP: each keeps batch/r cache lines) or the QUERY SEQUENCE (CP) instead of duplicating work
+        rep = get_kv_shared_group()
+        self.dp_group = rep if (nc.attention_dp_degree > 1 and rep.size == nc.attention_dp_degree) else None
+        self.cp_group = rep if (nc.cp_degree > 1 and rep.size == nc.cp_degree) else None
+        if nc.cp_degree > 1 and self.cp_group is None:
+            raise NotImplementedError(f"cp_degree ({nc.cp_degree}) must equal the KV replication factor tp/num_kv_heads "
+                                      f"({rep.size}) — see DESIGN.md §5")
 
     # ------------------------------------------------------------------------------------
     def _rope(self, meta: AttnMeta):
@@ -153,6 +161,9 @@ class AttentionBase(nn.Module):
         paged = meta.slot_mapping is not None
         if self.kv_group is not None:
             return self._forward_flash_decoding(qkv, meta, kv_mgr, cos, sin, residual, B, T)
+        if (self.dp_group is not None and not meta.is_prefill) or \
+                (self.cp_group is not None and meta.is_prefill and not meta.has_prefix and T % self.cp_group.size == 0):
+            return self._forward_group_parallel(qkv, meta, kv_mgr, cos, sin, residual, B, T)
         k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
         if meta.lines is None:
             meta.lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
@@ -235,6 +246,39 @@ class AttentionBase(nn.Module):
                                       nq, nkv, D, self.scale, self.sliding_window, self.sinks, qn, kn, self.qk_norm_eps,
                                       seq_hint=meta.seq_hint)
         return o.reshape(B, T, nq * D)
+
+    def _forward_group_parallel(self, qkv, meta, kv_mgr, cos, sin, residual, B, T):
+        """Attention DP (decode) / CP (prefill) among the r ranks that replicate this rank's KV head.
+        Both start by all-gathering the q heads of the group, so any member can serve any of the group's heads:
+          * DP decode: rank j owns the cache lines of batch rows ``seq_id in [j*n, (j+1)*n)`` (DataParallelKVCacheManager);
+            it attends ALL group heads for ITS rows, zeros elsewhere, and one all-reduce inside the group assembles the rows;
+          * CP prefill: rank j attends all group heads for the j-th slice of the query sequence against the full fresh K/V
+            (replicated anyway), slices are all-gathered along the sequence.
+        reference: attention_base.py:1709-1727 (DP) / :603-630 (CP, all-gather-KV); there both need a second, tp/dp- or
+        tp/cp-sharded copy of the attention weights — here the existing head sharding is reused as is."""
+        D, nq = self.head_dim, self.n_q
+        q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
+        lines = kv_mgr.lines_for(meta.seq_ids)
+        kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)     # non-owned rows -> garbage line
+        if meta.is_prefill:
+            g = self.cp_group
+            n = T // g.size
+            qa = mappings.all_gather(q.contiguous(), 2, g)[:, g.rank * n:(g.rank + 1) * n]       # [B, T/r, r*nq, D]
+            qpos = meta.position_ids[:, g.rank * n:(g.rank + 1) * n]
+            o = ops.attention_prefill(qa.contiguous(), k, v, self.scale, True, self.sliding_window, self.attention_chunk_size,
+                                      meta.key_valid, qpos, self.sinks, self.softcap)
+            o = mappings.all_gather(o.contiguous(), 1, g)                                          # [B, T, r*nq, D]
+        else:
+            g = self.dp_group
+            k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
+            qa = mappings.all_gather(q.contiguous(), 2, g)
+            o = ops.attention_decode(qa, k_cache, v_cache, lines, meta.position_ids, self.scale, self.sliding_window,
+                                     self.attention_chunk_size, None, None, self.softcap, seq_hint=meta.seq_hint)
+            owned = (lines < kv_mgr.num_lines).view(B, 1, 1, 1)
+            o = torch.where(owned, o, torch.zeros_like(o))
+            o = mappings.all_reduce(o.float(), g).to(q.dtype)
+        o = o[:, :, g.rank * nq:(g.rank + 1) * nq]
+        return self.o_proj(o.reshape(B, T, nq * D), residual)
 
     def _forward_flash_decoding(self, qkv, meta, kv_mgr, cos, sin, residual, B, T):
         from . import flashdecode as fd

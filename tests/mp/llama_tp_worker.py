@@ -35,7 +35,9 @@ def main():
     nc = NeuronConfig(batch_size=2, seq_len=64, max_context_length=32, torch_dtype=dtype, tp_degree=world,
                       on_cpu=(dev == "cpu"), output_logits=True, on_device_sampling_config=OnDeviceSamplingConfig(top_k=1),
                       flash_decoding_enabled=os.environ.get("FLASH_DECODING", "0") == "1",
-                      sequence_parallel_enabled=os.environ.get("SEQUENCE_PARALLEL", "0") == "1")
+                      sequence_parallel_enabled=os.environ.get("SEQUENCE_PARALLEL", "0") == "1",
+                      attention_dp_degree=int(os.environ.get("ATTENTION_DP", "1")), cp_degree=int(os.environ.get("CP", "1")),
+                      is_continuous_batching=int(os.environ.get("ATTENTION_DP", "1")) > 1)
     cfg = LlamaInferenceConfig(nc, load_config=load_pretrained_config(ckpt))
     app = NeuronLlamaForCausalLM(ckpt, cfg)
     app.load(None, skip_warmup=True)
@@ -43,6 +45,12 @@ def main():
         kvg = app.model.layers[0].self_attn.kv_group
         assert kvg is not None and kvg.size == world // cfg.num_key_value_heads, "flash decoding group not formed"
         assert app.model.kv_mgr.max_len == -(-nc.max_length // kvg.size), "KV cache is not sequence-sharded"
+    if nc.attention_dp_degree > 1:
+        a0 = app.model.layers[0].self_attn
+        assert a0.dp_group is not None and a0.dp_group.size == nc.attention_dp_degree
+        assert type(app.model.kv_mgr).__name__ == "DataParallelKVCacheManager" and app.model.kv_mgr.num_lines == 2 // nc.attention_dp_degree
+    if nc.cp_degree > 1:
+        assert app.model.layers[0].self_attn.cp_group is not None
     g = torch.Generator().manual_seed(0)
     ids = torch.randint(0, cfg.vocab_size, (2, 12), generator=g)
     mask = torch.ones(2, 12, dtype=torch.int32)

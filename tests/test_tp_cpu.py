@@ -51,3 +51,8 @@ def test_data_parallel_sampler_matches_distributed_sampler():
            "--master-port", "29545", os.path.join(ROOT, "tests", "mp", "dp_sampler_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0 and '"ok": true' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_llama_tp4_attention_dp_and_cp_match_hf(tiny_ckpt):
+    # ranks replicating a KV head split the batch (decode) and the query sequence (prefill) instead of duplicating work
+    _run(4, tiny_ckpt, 29546, ATTENTION_DP="2", CP="2")
