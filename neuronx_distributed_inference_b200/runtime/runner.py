@@ -68,7 +68,9 @@ class SubModelRunner:
         self.use_prefill_graphs = (device.type == "cuda" and nc.cuda_graphs and is_prefill and bool(getattr(model, "graph_safe", True))
                                    and nc.torch_dtype == torch.bfloat16 and not nc.is_block_kv_layout and not nc.is_prefix_caching
                                    and os.environ.get("NXDI_B200_PREFILL_GRAPHS", "1") != "0"
-                                   and hasattr(model, "_kernels_cover_decode") and model._kernels_cover_decode())
+                                   and hasattr(model, "_kernels_cover_decode") and model._kernels_cover_decode()
+                                   # MoE prefill dispatches tokens to experts with data-dependent shapes
+                                   and not any(getattr(l, "mlp_is_moe", False) for l in getattr(model, "layers", [])))
         self._prefill_pool = None
         self._graphs: Dict[Tuple, _Graph] = {}
         self.pad_token_id = getattr(config, "pad_token_id", None) or nc.pad_token_id or 0
