@@ -66,6 +66,11 @@ void argmax_launch(const void* logits, int dtype /*0 f32, 1 bf16*/, int64_t* out
 void topk_sample_launch(const void* logits, int dtype, const int* top_k, const float* top_p, const float* temperature,
                         const float* rand, int64_t* out, int B, int V, int ld, int K, cudaStream_t stream);
 
+// weight-only int8 / fp8-e4m3 skinny GEMM (qgemv.cu): wdtype 1 = int8, 2 = fp8 e4m3; scale fp32 [N] or [1]
+void qgemv_launch(const void* x, const void* w, const float* scale, int scale_n, const void* bias, const void* norm_w,
+                  const void* residual, void* y, int T, int N, int K, int ldx, int ldy, int act, int wdtype, float eps,
+                  float norm_offset, int n_sms, cudaStream_t stream);
+
 // MoE decode: routed experts for T <= 8 tokens as two batched streaming launches (moe_decode.cu)
 void moe_decode_launch(const void* x, const void* w_gate_up, const void* w_down, const float* topk_w, const int* topk_i, void* u,
                        float* y_acc, int T, int topk, int H, int I, int E, int expert_offset, int n_sms, cudaStream_t stream);

@@ -120,8 +120,26 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
                 const c10::optional<at::Tensor>& norm_w, double eps, double offset, int64_t act,
                 const c10::optional<at::Tensor>& scale, const c10::optional<at::Tensor>& residual,
                 const c10::optional<at::Tensor>& next_w, bool next_glu) {
+  if (scale.has_value()) {
+    // weight-only quantised path (int8 / fp8-e4m3, per-channel or per-tensor scale)
+    TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && is_bf16(x));
+    TORCH_CHECK(w.is_contiguous() && x.stride(1) == 1 && x.size(0) >= 1 && x.size(0) <= GEMV_MAX_T && x.size(1) % 16 == 0);
+    const bool i8 = w.scalar_type() == at::kChar, f8 = w.scalar_type() == at::kFloat8_e4m3fn;
+    TORCH_CHECK(i8 || f8, "qgemv: int8 or float8_e4m3fn weights");
+    TORCH_CHECK(scale->scalar_type() == at::kFloat && scale->is_contiguous() && (scale->numel() == 1 || scale->numel() == w.size(0)));
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = w.size(0);
+    const bool glu = act != 0;
+    auto y = at::empty({x.size(0), glu ? N / 2 : N}, x.options());
+    if (residual.has_value()) TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(1) == N && is_bf16(*residual));
+    static int n_sms = 0;
+    if (n_sms == 0) n_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+    qgemv_launch(x.data_ptr(), w.data_ptr(), scale->data_ptr<float>(), (int)scale->numel(), optr(bias), optr(norm_w), optr(residual),
+                 y.data_ptr(), x.size(0), N, x.size(1), x.stride(0), y.stride(0), (int)act, i8 ? 1 : 2, (float)eps, (float)offset,
+                 n_sms, cur_stream());
+    return y;
+  }
   check_gemv_inputs(x, w);
-  TORCH_CHECK(!scale.has_value(), "gemv: quantised weights are not wired yet");
   c10::cuda::CUDAGuard guard(x.device());
   const int N = w.size(0);
   const bool glu = act != 0;

@@ -78,7 +78,14 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
         ok_w = (w.dtype == x.dtype and scale is None) or (wq and scale is not None and scale.dim() == 1)
         if ok_w and act in _ACT_CODES and w.is_contiguous():
             x2 = x.reshape(T, K)
-            if T <= GEMV_MAX_TOKENS and K % 256 == 0:
+            if wq and T <= GEMV_MAX_TOKENS and K % 16 == 0 and w.dim() == 2:
+                stats["qgemv"] += 1
+                r2 = residual.reshape(T, -1).contiguous() if (residual is not None and act is None) else None
+                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale.float().contiguous(), r2,
+                              None, False)
+                y = y.view(*x.shape[:-1], y.shape[-1])
+                return y if (residual is None or r2 is not None) else y + residual
+            if not wq and T <= GEMV_MAX_TOKENS and K % 256 == 0:
                 stats["gemv"] += 1
                 r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
                 nxt = getattr(w, "_nxdi_next", None) if _PREFETCH_NEXT else None
@@ -107,7 +114,7 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
     K = x.shape[-1]
     T = x.numel() // K
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and group.symm is not None and T <= GEMV_MAX_TOKENS
-            and K % 256 == 0 and w.is_contiguous() and (w.dtype == x.dtype or scale is not None)
+            and K % 256 == 0 and w.is_contiguous() and w.dtype == x.dtype and scale is None
             and reduce_dtype in (None, torch.float32)):
         stats["gemv_allreduce"] += 1
         y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None,

@@ -294,3 +294,32 @@ def test_moe_decode_kernels_match_reference(T, k, E, H, I, off):
     exp = ref.moe_experts(x, wgu, wd, w, idx, "silu_mul", off)
     err = (got.float() - exp.float()).abs().max().item()
     assert err <= 0.02 * exp.float().abs().max().item() + 0.02, err
+
+
+@pytest.mark.parametrize("wdtype", [torch.int8, torch.float8_e4m3fn])
+@pytest.mark.parametrize("T,N,K,act,norm,res,per_tensor", [(2, 4096, 4096, None, True, False, False), (1, 6144, 4096, None, False, True, False),
+                                                           (8, 2048, 14336, None, False, True, True), (4, 7168, 4096, "silu_mul", True, False, False),
+                                                           (3, 1000, 1040, None, False, False, False)])
+def test_quantized_gemv_matches_dequantized_reference(wdtype, T, N, K, act, norm, res, per_tensor):
+    """Weight-only int8 / fp8 decode GEMV (csrc/qgemv.cu) == dequantise-then-matmul."""
+    torch.manual_seed(0)
+    dev, dt = "cuda", torch.bfloat16
+    w = torch.randn(N, K, device=dev) * 0.05
+    if per_tensor:
+        q, s = ref.quantize_per_tensor(w, wdtype)
+        s = s.reshape(1).float()
+    else:
+        q, s = ref.quantize_per_channel(w, wdtype)
+    x = torch.randn(T, K, device=dev, dtype=dt)
+    nw = (1 + 0.1 * torch.randn(K, device=dev)).to(dt) if norm else None
+    n_out = N // 2 if act else N
+    r = torch.randn(T, n_out, device=dev, dtype=dt) if res else None
+    bias = (torch.randn(N, device=dev) * 0.1).to(dt)
+    before = ops.stats["qgemv"]
+    got = ops.linear(x, q, bias, norm_weight=nw, norm_eps=1e-5, act=act, scale=s, residual=r)
+    assert ops.stats["qgemv"] == before + 1
+    exp = ref.linear(x.float(), q, bias.float(), nw.float() if norm else None, 1e-5, 0.0, act, s)
+    if r is not None:
+        exp = exp + r.float()
+    err = (got.float() - exp.float()).abs().max().item()
+    assert err <= 0.02 * exp.abs().max().item() + 0.03, err
