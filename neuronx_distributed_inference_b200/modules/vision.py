@@ -47,7 +47,7 @@ class VisionAttention(nn.Module):
         row).  ``key_valid`` [B,N]: padding keys are hidden."""
         B, N, _ = x.shape
         H, D = self.n_heads, self.head_dim
-        q, k, v = self.qkv_proj(x).view(B, N, 3, H, D).unbind(2) if False else self.qkv_proj(x).view(B, N, 3 * H, D).split(H, 2)
+        q, k, v = self.qkv_proj(x).view(B, N, 3 * H, D).split(H, 2)
         if cos is not None:
             if cos.shape[-1] == D // 2:       # interleaved (complex) rotary: Llama-4 vision
                 q, k = ops.apply_rope(q, cos, sin, True), ops.apply_rope(k, cos, sin, True)
