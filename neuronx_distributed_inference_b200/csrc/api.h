@@ -108,6 +108,7 @@ struct AttnPrefillParams {
   const float* sinks;
   int B, T, Hq, Hkv, D, window;
   float scale;
+  int causal;
 };
 void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream);
 

@@ -51,6 +51,7 @@ struct AttnArgs {
   __nv_bfloat16* k_w;
   __nv_bfloat16* v_w;
   float norm_eps;
+  int causal;  // prefill: 1 = causal (default), 0 = bidirectional (encoders: vision towers, Whisper, diffusion)
 };
 
 template <int D>
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   int pos_max = -1, pos_min = 0x7fffffff;
   for (int r = tid; r < 64; r += ATT_THREADS) {
     int ps = -1;
-    if (r < R) ps = (MODE == ATTN_PREFILL) ? tok0 + r : p.positions[b * p.T + r / G];
+    if (r < R) ps = (MODE == ATTN_PREFILL) ? (p.causal ? tok0 + r : p.T - 1) : p.positions[b * p.T + r / G];
     s_pos[r] = ps;
   }
   __syncthreads();
@@ -500,6 +501,7 @@ void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream) {
   a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
   a.sinks = p.sinks;
   a.B = p.B; a.T = p.T; a.Hq = p.Hq; a.Hkv = p.Hkv; a.nsplit = 1; a.window = p.window;
+  a.causal = p.causal;
   a.scale_log2 = p.scale * kLog2e;
   dim3 grid(p.B * p.Hq * ((p.T + 63) / 64));
   if (p.D == 128) launch_attn<128, ATTN_PREFILL, 2>(a, grid, stream);

@@ -488,7 +488,7 @@ at::Tensor paged_attention_decode(const at::Tensor& q, const at::Tensor& k_cache
 }
 
 at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, double scale, int64_t window,
-                             const c10::optional<at::Tensor>& sinks) {
+                             const c10::optional<at::Tensor>& sinks, bool causal) {
   TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous() && is_bf16(q) &&
               is_bf16(k) && is_bf16(v));
   const int B = q.size(0), T = q.size(1), Hq = q.size(2), D = q.size(3), Hkv = k.size(2);
@@ -499,6 +499,7 @@ at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at:
   p.q = q.data_ptr(); p.k = k.data_ptr(); p.v = v.data_ptr(); p.out = out.data_ptr();
   p.sinks = sinks.has_value() ? sinks->data_ptr<float>() : nullptr;
   p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.D = D; p.window = window; p.scale = (float)scale;
+  p.causal = causal ? 1 : 0;
   attention_prefill_launch(p, cur_stream());
   return out;
 }

@@ -43,8 +43,8 @@ def _rope(x, cos, sin):
 
 
 def _attend(q, k, v, scale):
-    mask = torch.ones(1, 1, 1, k.shape[1], dtype=torch.bool, device=q.device)
-    return ops.ref.attention_with_mask(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), mask, scale).transpose(1, 2)
+    """Joint bidirectional attention over [text | image] tokens: the flash kernel's non-causal mode on CUDA."""
+    return ops.attention_prefill(q.contiguous(), k.contiguous(), v.contiguous(), scale, causal=False)
 
 
 class _QKV(nn.Module):

@@ -249,11 +249,11 @@ def rope_attention_decode(qkv, cos, sin, k_cache, v_cache, seq_ids, write_positi
 def attention_prefill(q, k, v, scale, causal: bool = True, window=None, chunk=None, key_valid=None,
                       q_pos=None, sinks=None, softcap=None):
     D = q.shape[-1]
-    if (_use_cuda(q) and q.dtype in _FAST_DTYPES and D in (64, 128) and causal and chunk is None
+    if (_use_cuda(q) and q.dtype in _FAST_DTYPES and D in (64, 128) and chunk is None and (causal or not window)
             and key_valid is None and q_pos is None and softcap is None and q.shape[1] == k.shape[1]):
         stats["attn_prefill"] += 1
         return _C().attention_prefill(q.contiguous(), k.contiguous(), v.contiguous(), float(scale),
-                                      int(window or 0), sinks)
+                                      int(window or 0), sinks, bool(causal))
     return ref.attention_prefill(q, k, v, scale, causal, window, chunk, key_valid, q_pos, sinks, softcap)
 
 

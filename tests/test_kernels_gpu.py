@@ -323,3 +323,17 @@ def test_quantized_gemv_matches_dequantized_reference(wdtype, T, N, K, act, norm
         exp = exp + r.float()
     err = (got.float() - exp.float()).abs().max().item()
     assert err <= 0.02 * exp.abs().max().item() + 0.03, err
+
+
+@pytest.mark.parametrize("B,T,Hq,Hkv,D", [(2, 200, 8, 8, 64), (1, 1500, 4, 4, 128), (3, 77, 16, 4, 128)])
+def test_bidirectional_flash_attention_matches_reference(B, T, Hq, Hkv, D):
+    """Encoder (non-causal) mode of the flash kernel: vision towers, Whisper encoder, FLUX joint attention."""
+    torch.manual_seed(0)
+    q = torch.randn(B, T, Hq, D, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(B, T, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(B, T, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    before = ops.stats["attn_prefill"]
+    got = ops.attention_prefill(q, k, v, D ** -0.5, causal=False)
+    assert ops.stats["attn_prefill"] == before + 1
+    exp = ref.attention_prefill(q.float(), k.float(), v.float(), D ** -0.5, causal=False)
+    assert (got.float() - exp).abs().max().item() < 2e-2
