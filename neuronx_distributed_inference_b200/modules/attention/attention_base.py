@@ -26,13 +26,13 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .. import ops
-from ..parallel import mappings
-from ..parallel.state import (Group, get_context_parallel_group, get_context_parallel_tp_group,
+from ... import ops
+from ...parallel import mappings
+from ...parallel.state import (Group, get_context_parallel_group, get_context_parallel_tp_group,
                               get_data_parallel_attention_group, get_kv_shared_group,
                               get_tensor_model_parallel_group)
-from .gqa import GQA, GroupQueryAttention_O, GroupQueryAttention_QKV
-from .norm import L2Norm, RMSNorm
+from ..gqa import GQA, GroupQueryAttention_O, GroupQueryAttention_QKV
+from ..norm import L2Norm, RMSNorm
 
 
 @dataclass
@@ -221,7 +221,7 @@ class AttentionBase(nn.Module):
     def _finish(self, o, residual, lora, meta):
         out = self.o_proj(o, residual)
         if lora is not None and lora.has("o_proj"):
-            from ..parallel import mappings as _m
+            from ...parallel import mappings as _m
             out = out + _m.all_reduce(lora("o_proj", o, meta.adapter_ids), self.tp_group)
         return out
 
@@ -281,7 +281,7 @@ class AttentionBase(nn.Module):
         return self.o_proj(o.reshape(B, T, nq * D), residual)
 
     def _forward_flash_decoding(self, qkv, meta, kv_mgr, cos, sin, residual, B, T):
-        from . import flashdecode as fd
+        from .. import flashdecode as fd
         g = self.kv_group
         D, nq = self.head_dim, self.n_q
         q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)

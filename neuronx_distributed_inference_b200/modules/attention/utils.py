@@ -1,0 +1,71 @@
+"""Attention helpers under the reference's names (modules/attention/utils.py): head layout moves, KV repetition, rotary
+application, the fp32 "manual" softmax over prior + active scores, distributed softmax statistics, mask builders."""
+from __future__ import annotations
+
+import torch
+
+from ... import ops
+from ...ops import reference as ref
+from ..rope import RotaryEmbedding  # noqa: F401
+
+
+def move_heads_front(t: torch.Tensor, bsz: int, seq_len: int, num_head: int, head_dim: int, layernorm=None) -> torch.Tensor:
+    """[B, S, H*D] -> [B, H, S, D] (optionally per-head layernorm first)."""
+    t = t.view(bsz, seq_len, num_head, head_dim)
+    if layernorm is not None:
+        t = layernorm(t)
+    return t.permute(0, 2, 1, 3).contiguous()
+
+
+def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
+    """[B, Hkv, S, D] -> [B, Hkv*n_rep, S, D]."""
+    return hidden_states if n_rep == 1 else hidden_states.repeat_interleave(n_rep, dim=1)
+
+
+def rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim: int = 1):
+    """HF convention: q/k [B, H, S, D], cos/sin [B, S, D] (full width)."""
+    cos, sin = cos.unsqueeze(unsqueeze_dim), sin.unsqueeze(unsqueeze_dim)
+    return (q * cos + rotate_half(q) * sin), (k * cos + rotate_half(k) * sin)
+
+
+def manual_softmax(prior_scores, active_scores, is_speculation: bool = False):
+    """Joint softmax over the cached ("prior") and the new ("active") keys, fp32 (reference attention/utils.py)."""
+    mx = torch.maximum(prior_scores.amax(-1, keepdim=True), active_scores.amax(-1, keepdim=True))
+    ep, ea = torch.exp(prior_scores.float() - mx), torch.exp(active_scores.float() - mx)
+    den = ep.sum(-1, keepdim=True) + ea.sum(-1, keepdim=True)
+    return ep / den, ea / den
+
+
+def distributed_softmax(prior_scores, active_scores, group=None):
+    """Flash-decoding flavour: max / sum statistics are all-reduced across the KV-shard group."""
+    from ...parallel import mappings
+    from ...parallel.state import get_kv_shared_group
+    g = group or get_kv_shared_group()
+    mx = torch.maximum(prior_scores.amax(-1, keepdim=True), active_scores.amax(-1, keepdim=True)).float()
+    if g.size > 1:
+        mx = mappings.all_gather(mx.unsqueeze(0), 0, g).amax(0)
+    ep, ea = torch.exp(prior_scores.float() - mx), torch.exp(active_scores.float() - mx)
+    den = ep.sum(-1, keepdim=True) + ea.sum(-1, keepdim=True)
+    if g.size > 1:
+        den = mappings.all_reduce(den, g)
+    return ep / den, ea / den
+
+
+def create_block_diagonal_attn_mask(query_lens, key_lens, max_query_len: int, max_key_len: int) -> torch.Tensor:
+    """Chunked-prefill mask: sequence i's queries see only sequence i's keys, causally aligned at the end."""
+    m = torch.zeros(max_query_len, max_key_len, dtype=torch.bool)
+    qo = ko = 0
+    for ql, kl in zip(query_lens.tolist(), key_lens.tolist()):
+        for i in range(ql):
+            m[qo + i, ko: ko + kl - ql + i + 1] = True
+        qo, ko = qo + ql, ko + kl
+    return m
+
+
+build_mask = ref.build_mask
+attention_with_mask = ops.attention_with_mask

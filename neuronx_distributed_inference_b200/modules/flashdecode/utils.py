@@ -18,7 +18,7 @@ from typing import Tuple
 
 import torch
 
-from ..parallel import mappings
+from ...parallel import mappings
 
 
 def calculate_num_cores_per_group(num_attention_heads: int, num_key_value_heads: int, tp_degree: int) -> int:

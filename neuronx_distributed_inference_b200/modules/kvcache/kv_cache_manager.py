@@ -20,7 +20,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from .. import ops
+from ... import ops
 
 
 class KVCacheManager(nn.Module):
@@ -35,7 +35,7 @@ class KVCacheManager(nn.Module):
         self.store_dtype = dtype
         self.k_scale = self.v_scale = None
         if quant_config is not None:
-            from ..config import to_torch_dtype
+            from ...config import to_torch_dtype
             self.store_dtype = to_torch_dtype(quant_config.dtype)
             if quant_config.scale_mode != "direct_cast":
                 self.k_scale = float(quant_config.k_scale)

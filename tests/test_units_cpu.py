@@ -264,3 +264,58 @@ def test_module_test_template_rmsnorm_and_env_helpers():
     assert rep["cpu"] < 1e-5
     env = runtime_env.get_env_vars(NeuronConfig(tp_degree=1))
     assert isinstance(env, dict) and "NXDI_B200_ARCH" in compile_env.get_compile_env_vars(NeuronConfig())
+
+
+def test_reference_import_paths_resolve():
+    """A user switching from the reference keeps its module paths (package name aside)."""
+    import importlib
+    P = "neuronx_distributed_inference_b200."
+    for mod, names in {
+        "models.config": ["NeuronConfig", "InferenceConfig", "MoENeuronConfig", "OnDeviceSamplingConfig", "FusedSpecNeuronConfig"],
+        "models.model_wrapper": ["ModelWrapper", "CONTEXT_ENCODING_MODEL_TAG", "TOKEN_GENERATION_MODEL_TAG", "FUSED_SPECULATION_MODEL_TAG"],
+        "models.model_base": ["NeuronBaseModel"],
+        "models.application_base": ["NeuronApplicationBase", "NeuronBaseForCausalLM"],
+        "models.image_to_text_model_base": ["NeuronBaseForImageToText", "ImageToTextInferenceConfig"],
+        "models.encoder_base": ["NeuronEncoderBase", "NeuronEncoderApplication"],
+        "modules.attention.attention_base": ["NeuronAttentionBase" if False else "AttentionBase"],
+        "modules.attention": ["NeuronAttentionBase"],
+        "modules.attention.gqa": ["GQA", "GroupQueryAttention_QKV", "GroupQueryAttention_O"],
+        "modules.attention.utils": ["move_heads_front", "repeat_kv", "apply_rotary_pos_emb", "manual_softmax", "RotaryEmbedding"],
+        "modules.attention.attention_process_groups": ["get_context_parallel_attention_cp_group", "get_data_parallel_attention_dp_group"],
+        "modules.kvcache.kv_cache_manager": ["KVCacheManager"],
+        "modules.kvcache.block_kv_cache_manager": ["BlockKVCacheManager", "generate_tokengen_slot_mapping"],
+        "modules.kvcache.data_parallel_kv_cache_manager": ["DataParallelKVCacheManager"],
+        "modules.kvcache.utils": ["write_kv_cache_at_batch", "get_active_block_table"],
+        "modules.generation.sampling": ["Sampler", "prepare_sampling_params", "validate_sampling_params", "mask_padded_logits"],
+        "modules.generation.seq_parallel_logits_slice": ["seq_parallel_slice_last_token"],
+        "modules.flashdecode.utils": ["calculate_num_cores_per_group"],
+        "modules.eagle.hidden_state": ["HiddenStateRollingBuffer"],
+        "modules.eagle.token_tree": ["TokenTree"],
+        "modules.eagle.dynamic_token_tree": ["DynamicTokenTree"],
+        "modules.lora_serving": ["LoraModelManager", "LoraServingConfig"],
+        "modules.moe_v2": ["initialize_moe_module"],
+        "modules.custom_calls": ["CustomRMSNorm", "neuron_cumsum"],
+        "modules.async_execution": ["causal_lm_async_execution"],
+        "modules.autobucketing": ["generate_buckets"],
+        "modules.padding": ["pad_tensor", "unpad_tensor"],
+        "modules.checkpoint": ["load_state_dict", "save_state_dict_safetensors", "create_n_layer_checkpoint"],
+        "modules.sliding_window.attention": ["flash_fwd"],
+        "utils.hf_adapter": ["HuggingFaceGenerationAdapter", "load_pretrained_config"],
+        "utils.accuracy": ["check_accuracy", "check_accuracy_logits", "generate_expected_logits"],
+        "utils.benchmark": ["benchmark_sampling", "LatencyCollector"],
+        "utils.snapshot": ["SnapshotOutputFormat", "register_snapshot_hooks"],
+        "utils.tensor_capture_utils": ["capture_model_tensors", "get_available_modules"],
+        "utils.tensor_replacement.registry": ["TensorReplacementRegistry"],
+        "utils.kv_cache_reconstruct_utils": ["reconstruct_kv_cache"],
+        "utils.debug_utils": ["capture_model_inputs"],
+        "utils.runtime_env": ["set_env_vars"], "utils.compile_env": ["set_compile_env_vars"],
+        "utils.distributed": ["get_init_world_size", "get_init_rank"], "utils.random": ["set_random_seed"],
+        "utils.exceptions": ["LogitMatchingValidationError"], "utils.constants": ["MODEL_TYPES", "TEST_PROMPT"],
+        "scripts.nxdi_distributed_launcher": ["main"], "inference_demo": ["main"],
+        "models.llama.modeling_llama": ["NeuronLlamaForCausalLM", "NeuronLlamaModel", "LlamaInferenceConfig", "NeuronLlamaMLP", "NeuronLlamaAttention"],
+        "models.diffusers.flux.application": ["NeuronFluxApplication"], "models.whisper.modeling_whisper": ["NeuronApplicationWhisper"],
+        "experimental.functional": ["qkv_proj", "gated_mlp_fused", "tokengen_attention_megakernel_standard_kv"],
+    }.items():
+        m = importlib.import_module(P + mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"
