@@ -26,6 +26,13 @@ MODEL_TYPES = {
     "whisper": {"speech-to-text": f"{_P}.whisper.modeling_whisper:NeuronApplicationWhisper"},
     "flux": {"text-to-image": f"{_P}.diffusers.flux.application:NeuronFluxApplication"},
 }
+_C = "neuronx_distributed_inference_b200.contrib.models.llama_family"
+MODEL_TYPES.update({
+    "phi3": {"causal-lm": f"{_C}:NeuronPhi3ForCausalLM"}, "granite": {"causal-lm": f"{_C}:NeuronGraniteForCausalLM"},
+    "smollm3": {"causal-lm": f"{_C}:NeuronSmolLM3ForCausalLM"}, "seed_oss": {"causal-lm": f"{_C}:NeuronSeedOssForCausalLM"},
+    "olmo2": {"causal-lm": f"{_C}:NeuronOlmo2ForCausalLM"}, "olmo3": {"causal-lm": f"{_C}:NeuronOlmo3ForCausalLM"},
+    "gemma2": {"causal-lm": f"{_C}:NeuronGemma2ForCausalLM"}, "glm4": {"causal-lm": f"{_C}:NeuronGlm4ForCausalLM"},
+})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

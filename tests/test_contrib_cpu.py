@@ -1,0 +1,52 @@
+"""Community-hub families vs Hugging Face (tiny random checkpoints, CPU fp32): prefill + teacher-forced decode logits."""
+import pytest
+import torch
+
+from neuronx_distributed_inference_b200.config import load_pretrained_config
+from neuronx_distributed_inference_b200.utils.accuracy import generate_expected_logits, teacher_forced_logits
+from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+
+BASE = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, vocab_size=160,
+            max_position_embeddings=256)
+
+
+def _cfg(name):
+    import transformers as T
+    if name == "phi3":
+        return T.Phi3Config(**BASE, pad_token_id=0)
+    if name == "granite":
+        return T.GraniteConfig(**BASE, embedding_multiplier=3.0, attention_multiplier=0.2, residual_multiplier=0.5, logits_scaling=4.0,
+                               tie_word_embeddings=False)
+    if name == "smollm3":
+        return T.SmolLM3Config(**{**BASE, "num_hidden_layers": 4}, no_rope_layers=[1, 1, 0, 1], pad_token_id=0)
+    if name == "seed_oss":
+        return T.SeedOssConfig(**BASE, head_dim=16, attention_bias=True, attention_out_bias=False)
+    if name == "olmo2":
+        return T.Olmo2Config(**BASE, pad_token_id=0)
+    if name == "gemma2":
+        return T.Gemma2Config(**{**BASE, "num_hidden_layers": 4}, head_dim=16, sliding_window=8, query_pre_attn_scalar=16,
+                              attn_logit_softcapping=20.0, final_logit_softcapping=10.0)
+    if name == "glm4":
+        return T.Glm4Config(**BASE, head_dim=16, partial_rotary_factor=0.5, pad_token_id=0)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4"])
+def test_contrib_family_matches_hf(name, tmp_path):
+    from transformers import AutoModelForCausalLM
+    from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
+    hf_cfg = _cfg(name)
+    ckpt = save_random_hf_checkpoint(hf_cfg, str(tmp_path / name), seed=2)
+    hf = AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32).eval()
+    cls = CONTRIB_MODEL_TYPES[name]
+    nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
+    app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
+    app.load(None, skip_warmup=True)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1, hf_cfg.vocab_size, (2, 14), generator=g)
+    mask = torch.ones_like(ids)
+    mask[1, 10:] = 0
+    exp, toks = generate_expected_logits(hf, ids, mask, 10)
+    got = teacher_forced_logits(app, ids, mask, toks)
+    err = ((got - exp).norm() / exp.norm()).item()
+    assert err < 3e-4, f"{name}: relative logit error {err}"
