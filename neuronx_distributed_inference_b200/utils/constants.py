@@ -33,6 +33,12 @@ MODEL_TYPES.update({
     "olmo2": {"causal-lm": f"{_C}:NeuronOlmo2ForCausalLM"}, "olmo3": {"causal-lm": f"{_C}:NeuronOlmo3ForCausalLM"},
     "gemma2": {"causal-lm": f"{_C}:NeuronGemma2ForCausalLM"}, "glm4": {"causal-lm": f"{_C}:NeuronGlm4ForCausalLM"},
 })
+_K = "neuronx_distributed_inference_b200.contrib.models.classic_family"
+MODEL_TYPES.update({
+    "starcoder2": {"causal-lm": f"{_K}:NeuronStarcoder2ForCausalLM"}, "stablelm": {"causal-lm": f"{_K}:NeuronStableLmForCausalLM"},
+    "cohere": {"causal-lm": f"{_K}:NeuronCohereForCausalLM"}, "gpt_neox": {"causal-lm": f"{_K}:NeuronGPTNeoXForCausalLM"},
+    "gpt2": {"causal-lm": f"{_K}:NeuronGPT2ForCausalLM"},
+})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

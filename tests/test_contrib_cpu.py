@@ -28,17 +28,30 @@ def _cfg(name):
                               attn_logit_softcapping=20.0, final_logit_softcapping=10.0)
     if name == "glm4":
         return T.Glm4Config(**BASE, head_dim=16, partial_rotary_factor=0.5, pad_token_id=0)
+    if name == "starcoder2":
+        return T.Starcoder2Config(**BASE, sliding_window=None)
+    if name == "stablelm":
+        return T.StableLmConfig(**BASE, partial_rotary_factor=0.25, use_qkv_bias=True)
+    if name == "cohere":
+        return T.CohereConfig(**BASE, logit_scale=0.25, pad_token_id=0)
+    if name == "gpt_neox":
+        return T.GPTNeoXConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, vocab_size=160,
+                               max_position_embeddings=256, rotary_pct=0.25)
+    if name == "gpt2":
+        return T.GPT2Config(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256)
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4"])
+@pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
+                                  "gpt_neox", "gpt2"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
     hf_cfg = _cfg(name)
     ckpt = save_random_hf_checkpoint(hf_cfg, str(tmp_path / name), seed=2)
     hf = AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32).eval()
-    cls = CONTRIB_MODEL_TYPES[name]
+    from neuronx_distributed_inference_b200.contrib.models.classic_family import CLASSIC_MODEL_TYPES
+    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES}[name]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
