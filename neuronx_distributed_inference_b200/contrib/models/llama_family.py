@@ -268,7 +268,59 @@ class NeuronGlm4ForCausalLM(NeuronLlamaForCausalLM):
         return sd
 
 
+# ---------------------------------------------------------------------------------------------------------- Helium / ERNIE-4.5
+class _InterleavedRopeAttention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        super().__init__(config, layer_idx, rotary_emb, device=device, rope_interleaved=True, **over)
+
+
+class NeuronHeliumModel(NeuronLlamaModel):
+    """Llama block with GPT-J style (pairwise / interleaved) rotary."""
+    attention_cls = _InterleavedRopeAttention
+    graph_safe = False
+
+
+class NeuronHeliumForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronHeliumModel
+
+
+NeuronErnie4_5ForCausalLM = NeuronHeliumForCausalLM
+
+
+# ---------------------------------------------------------------------------------------------------------- Arcee AFM
+class _Relu2MLP(nn.Module):
+    """Non-gated ``down(relu(up(x))^2)`` (AFM-4.5B); keeps the GatedMLP calling convention (fused norm, residual)."""
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        from ...modules.mlp import PlainMLP
+        self.inner = PlainMLP(config.hidden_size, config.intermediate_size, "relu2", config.neuron_config.torch_dtype,
+                              bias=getattr(config, "mlp_bias", False), device=device)
+
+    def forward(self, x, norm_weight=None, norm_eps=1e-6, norm_offset=0.0, residual=None, **kw):
+        xn = ops.rmsnorm(x, norm_weight, norm_eps, norm_offset) if norm_weight is not None else x
+        return self.inner(xn, residual)
+
+
+class NeuronArceeModel(NeuronLlamaModel):
+    mlp_cls = _Relu2MLP
+    graph_safe = False
+
+
+class NeuronArceeForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronArceeModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+        return {k.replace(".mlp.up_proj.", ".mlp.inner.fc1.").replace(".mlp.down_proj.", ".mlp.inner.fc2."): v for k, v in sd.items()}
+
+
+from ...models.qwen3.modeling_qwen3 import NeuronQwen3ForCausalLM as NeuronHunYuanDenseForCausalLM  # noqa: E402  (same block: per-head q/k RMSNorm)
+
 CONTRIB_MODEL_TYPES = {
+    "helium": NeuronHeliumForCausalLM, "ernie4_5": NeuronErnie4_5ForCausalLM, "arcee": NeuronArceeForCausalLM,
+    "hunyuan_v1_dense": NeuronHunYuanDenseForCausalLM,
     "phi3": NeuronPhi3ForCausalLM, "granite": NeuronGraniteForCausalLM, "smollm3": NeuronSmolLM3ForCausalLM,
     "seed_oss": NeuronSeedOssForCausalLM, "olmo2": NeuronOlmo2ForCausalLM, "olmo3": NeuronOlmo3ForCausalLM,
     "gemma2": NeuronGemma2ForCausalLM, "glm4": NeuronGlm4ForCausalLM,

@@ -21,7 +21,7 @@ from ..parallel.state import Group
 _GLU_ACT = {"silu": "silu_mul", "swish": "silu_mul", "gelu": "gelu_mul", "gelu_pytorch_tanh": "gelu_tanh_mul",
             "gelu_new": "gelu_tanh_mul", "gelu_tanh": "gelu_tanh_mul"}
 _PLAIN_ACT = {"silu": "silu", "gelu": "gelu", "gelu_pytorch_tanh": "gelu_tanh", "gelu_new": "gelu_tanh",
-              "relu": "relu"}
+              "relu": "relu", "relu2": "relu2"}
 
 
 class GatedMLP(nn.Module):

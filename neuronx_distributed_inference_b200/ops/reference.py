@@ -74,6 +74,8 @@ def activation(y, act: str):
         return F.gelu(y, approximate="tanh")
     if act == "relu":
         return F.relu(y)
+    if act == "relu2":
+        return F.relu(y).square()
     raise ValueError(act)
 
 

@@ -28,6 +28,14 @@ def _cfg(name):
                               attn_logit_softcapping=20.0, final_logit_softcapping=10.0)
     if name == "glm4":
         return T.Glm4Config(**BASE, head_dim=16, partial_rotary_factor=0.5, pad_token_id=0)
+    if name == "helium":
+        return T.HeliumConfig(**BASE, head_dim=16)
+    if name == "ernie4_5":
+        return T.Ernie4_5Config(**BASE, head_dim=16)
+    if name == "arcee":
+        return T.ArceeConfig(**BASE, head_dim=16)
+    if name == "hunyuan_v1_dense":
+        return T.HunYuanDenseV1Config(**BASE, head_dim=16)
     if name == "starcoder2":
         return T.Starcoder2Config(**BASE, sliding_window=None)
     if name == "stablelm":
@@ -43,7 +51,7 @@ def _cfg(name):
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
-                                  "gpt_neox", "gpt2"])
+                                  "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
