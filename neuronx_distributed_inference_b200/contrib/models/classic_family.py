@@ -110,8 +110,8 @@ class NeuronClassicModel(NeuronBaseModel):
         self.norm = nn.LayerNorm(config.hidden_size, eps=config.rms_norm_eps, bias=self.SPEC["norm_bias"], dtype=dt, device=dev)
         for p in self.norm.parameters():
             p.requires_grad_(False)
-        self.lm_head = ColumnParallelLinear(config.hidden_size, config.vocab_size, bias=False, gather_output=False, dtype=dt, device=dev,
-                                            pad=True, tensor_model_parallel_group=self.tp_group)
+        self.lm_head = ColumnParallelLinear(config.hidden_size, config.vocab_size, bias=bool(getattr(self, "lm_head_bias", False)),
+                                            gather_output=False, dtype=dt, device=dev, pad=True, tensor_model_parallel_group=self.tp_group)
         self.logit_scale = float(getattr(config, "logit_scale", 1.0) or 1.0)
 
     def forward(self, input_ids, attention_mask=None, position_ids=None, *a, **kw):
@@ -276,5 +276,147 @@ class NeuronGPT2ForCausalLM(_ClassicCausalLM):
         return out
 
 
-CLASSIC_MODEL_TYPES = {"starcoder2": NeuronStarcoder2ForCausalLM, "stablelm": NeuronStableLmForCausalLM, "cohere": NeuronCohereForCausalLM,
+# ---- OPT -----------------------------------------------------------------------------------------------------------------
+class OPTInferenceConfig(ClassicInferenceConfig):
+    def add_derived_config(self):
+        self.intermediate_size = getattr(self, "ffn_dim", 4 * self.hidden_size)
+        super().add_derived_config()
+
+
+class NeuronOPTModel(NeuronClassicModel):
+    learned_positions = True
+    position_offset = 2          # OPT reserves the first two rows of its position table
+
+    def layer_spec(self, config, i):
+        b = bool(getattr(config, "enable_bias", True))
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "activation_function", "relu"), qkv_bias=b, o_bias=b, mlp_bias=b)
+
+
+class NeuronOPTForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronOPTModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return OPTInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = {(k[len("decoder."):] if k.startswith("decoder.") else k): v for k, v in sd.items()}
+        out = {}
+        for k, v in sd.items():
+            if k.startswith("layers."):
+                k = (k.replace(".self_attn.out_proj.", ".self_attn.o_proj.").replace(".self_attn_layer_norm.", ".input_layernorm.")
+                     .replace(".final_layer_norm.", ".post_attention_layernorm.").replace(".fc1.", ".mlp.fc1.").replace(".fc2.", ".mlp.fc2."))
+            elif k.startswith("final_layer_norm."):
+                k = k.replace("final_layer_norm.", "norm.")
+            out[k] = v
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+# ---- GPT-J ---------------------------------------------------------------------------------------------------------------
+class GPTJInferenceConfig(GPT2InferenceConfig):
+    pass
+
+
+class NeuronGPTJModel(NeuronClassicModel):
+    lm_head_bias = True
+
+    def make_rotary(self, config, device):
+        rot = int(getattr(config, "rotary_dim", None) or config.head_dim)
+        return RotaryEmbedding(rot, max(config.max_position_embeddings, config.neuron_config.seq_len), rope_theta_of(config), None, device=device)
+
+    def layer_spec(self, config, i):
+        return dict(parallel=True, shared_norm=True, norm_bias=True, mlp="plain", act=getattr(config, "activation_function", "gelu_new"),
+                    qkv_bias=False, o_bias=False, mlp_bias=True, rope_interleaved=True)
+
+
+class NeuronGPTJForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronGPTJModel
+    _STATE_DICT_MODEL_PREFIX = "transformer."
+
+    @classmethod
+    def get_config_cls(cls):
+        return GPTJInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"):
+                continue
+            k = k.replace("h.", "layers.", 1) if k.startswith("h.") else k
+            k = (k.replace(".attn.q_proj.", ".self_attn.q_proj.").replace(".attn.k_proj.", ".self_attn.k_proj.").replace(".attn.v_proj.", ".self_attn.v_proj.")
+                 .replace(".attn.out_proj.", ".self_attn.o_proj.").replace(".mlp.fc_in.", ".mlp.fc1.").replace(".mlp.fc_out.", ".mlp.fc2.")
+                 .replace(".ln_1.", ".input_layernorm."))
+            k = k.replace("wte.", "embed_tokens.").replace("ln_f.", "norm.")
+            out[k] = v
+        return fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+
+
+# ---- Phi-1 / Phi-1.5 / Phi-2 -------------------------------------------------------------------------------------------------
+class NeuronPhiModel(NeuronClassicModel):
+    lm_head_bias = True
+
+    def layer_spec(self, config, i):
+        return dict(parallel=True, shared_norm=True, norm_bias=True, mlp="plain", act=getattr(config, "hidden_act", "gelu_new"), qkv_bias=True,
+                    o_bias=True, mlp_bias=True)
+
+
+class NeuronPhiForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronPhiModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = {k.replace(".self_attn.dense.", ".self_attn.o_proj.").replace("final_layernorm.", "norm."): v for k, v in sd.items()}
+        return fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+
+
+# ---- Falcon (7B-style: multi-query, parallel attention + MLP behind one LayerNorm) ---------------------------------------------------
+class FalconInferenceConfig(ClassicInferenceConfig):
+    def add_derived_config(self):
+        if getattr(self, "new_decoder_architecture", False):
+            self.num_key_value_heads = getattr(self, "num_kv_heads", self.num_attention_heads)
+        else:
+            self.num_key_value_heads = 1 if getattr(self, "multi_query", True) else self.num_attention_heads
+        self.intermediate_size = getattr(self, "ffn_hidden_size", None) or 4 * self.hidden_size
+        super().add_derived_config()
+
+    def validate_config(self):
+        super().validate_config()
+        if getattr(self, "alibi", False) or getattr(self, "new_decoder_architecture", False) or not getattr(self, "parallel_attn", True):
+            raise NotImplementedError("Falcon: only the rotary, parallel-attention, classic (7B-style) layout is implemented")
+
+
+class NeuronFalconModel(NeuronClassicModel):
+    def layer_spec(self, config, i):
+        b = bool(getattr(config, "bias", False))
+        return dict(parallel=True, shared_norm=True, norm_bias=True, mlp="plain", act="gelu", qkv_bias=b, o_bias=b, mlp_bias=b)
+
+
+class NeuronFalconForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronFalconModel
+    _STATE_DICT_MODEL_PREFIX = "transformer."
+
+    @classmethod
+    def get_config_cls(cls):
+        return FalconInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            k = k.replace("h.", "layers.", 1) if k.startswith("h.") else k
+            k = (k.replace(".self_attention.query_key_value.", ".self_attn.qkv_proj.").replace(".self_attention.dense.", ".self_attn.o_proj.")
+                 .replace(".mlp.dense_h_to_4h.", ".mlp.fc1.").replace(".mlp.dense_4h_to_h.", ".mlp.fc2."))
+            k = k.replace("word_embeddings.", "embed_tokens.").replace("ln_f.", "norm.")
+            out[k] = v        # multi-query fused QKV is already [q heads; k; v]
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+CLASSIC_MODEL_TYPES = {"opt": NeuronOPTForCausalLM, "gptj": NeuronGPTJForCausalLM, "phi": NeuronPhiForCausalLM, "falcon": NeuronFalconForCausalLM,"starcoder2": NeuronStarcoder2ForCausalLM, "stablelm": NeuronStableLmForCausalLM, "cohere": NeuronCohereForCausalLM,
                        "gpt_neox": NeuronGPTNeoXForCausalLM, "gpt2": NeuronGPT2ForCausalLM}

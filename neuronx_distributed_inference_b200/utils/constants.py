@@ -39,7 +39,9 @@ _K = "neuronx_distributed_inference_b200.contrib.models.classic_family"
 MODEL_TYPES.update({
     "starcoder2": {"causal-lm": f"{_K}:NeuronStarcoder2ForCausalLM"}, "stablelm": {"causal-lm": f"{_K}:NeuronStableLmForCausalLM"},
     "cohere": {"causal-lm": f"{_K}:NeuronCohereForCausalLM"}, "gpt_neox": {"causal-lm": f"{_K}:NeuronGPTNeoXForCausalLM"},
-    "gpt2": {"causal-lm": f"{_K}:NeuronGPT2ForCausalLM"},
+    "gpt2": {"causal-lm": f"{_K}:NeuronGPT2ForCausalLM"}, "opt": {"causal-lm": f"{_K}:NeuronOPTForCausalLM"},
+    "gptj": {"causal-lm": f"{_K}:NeuronGPTJForCausalLM"}, "phi": {"causal-lm": f"{_K}:NeuronPhiForCausalLM"},
+    "falcon": {"causal-lm": f"{_K}:NeuronFalconForCausalLM"},
 })
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 

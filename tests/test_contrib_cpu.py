@@ -36,6 +36,17 @@ def _cfg(name):
         return T.ArceeConfig(**BASE, head_dim=16)
     if name == "hunyuan_v1_dense":
         return T.HunYuanDenseV1Config(**BASE, head_dim=16)
+    if name == "opt":
+        return T.OPTConfig(hidden_size=64, ffn_dim=128, num_hidden_layers=3, num_attention_heads=4, vocab_size=160, max_position_embeddings=256,
+                           word_embed_proj_dim=64)
+    if name == "gptj":
+        return T.GPTJConfig(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256, rotary_dim=8)
+    if name == "phi":
+        return T.PhiConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, vocab_size=160,
+                           max_position_embeddings=256, partial_rotary_factor=0.5)
+    if name == "falcon":
+        return T.FalconConfig(hidden_size=64, num_hidden_layers=3, num_attention_heads=4, vocab_size=160, new_decoder_architecture=False,
+                              multi_query=True, parallel_attn=True, bias=False, alibi=False, max_position_embeddings=256)
     if name == "starcoder2":
         return T.Starcoder2Config(**BASE, sliding_window=None)
     if name == "stablelm":
@@ -51,7 +62,8 @@ def _cfg(name):
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
-                                  "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense"])
+                                  "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
+                                  "falcon"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
