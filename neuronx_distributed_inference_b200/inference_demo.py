@@ -254,6 +254,12 @@ def run_inference(model_cls, args):
     model.load(args.compiled_model_path)
     if draft_model is not None:
         draft_model.load(args.compiled_draft_model_path)
+    # debug hooks (reference :616-649 and application_base.py:423-554)
+    if args.capture_indices:
+        from .utils.debug_utils import capture_model_inputs
+        capture_model_inputs(model, args.capture_indices, args.input_capture_save_dir or "saved_inputs")
+    from .utils.snapshot import maybe_register_from_env
+    maybe_register_from_env(model)          # NXD_INFERENCE_CAPTURE_SNAPSHOT=1 ...
     tokenizer = AutoTokenizer.from_pretrained(args.model_path, padding_side=nc.padding_side)
     if tokenizer.pad_token_id is None:
         tokenizer.pad_token_id = args.pad_token_id
@@ -292,6 +298,17 @@ def run_accuracy_check(model, tokenizer, gc, args, draft_model=None):
         accuracy.check_accuracy_logits(model, tokenizer, gc, expected_logits=expected, prompts=args.prompts,
                                        divergence_difference_tol=args.divergence_difference_tol, tol_map=tol,
                                        num_tokens_to_check=args.num_tokens_to_check)
+    elif mode == CheckAccuracyMode.DRAFT_LOGIT_MATCHING:
+        # fused speculation: the draft's logits against golden draft logits (reference utils/accuracy.py:1222-1277)
+        assert expected is not None, "--expected-outputs-path with golden draft logits is required"
+        ids = tokenizer(args.prompts, padding=True, return_tensors="pt")
+        draft = getattr(model, "draft_model", None)
+        assert draft is not None, "draft-logit-matching needs a fused-speculation model"
+        pos = (ids.attention_mask.long().cumsum(-1) - 1).clamp_min(0).to(torch.int32)
+        out = draft(ids.input_ids.to(model.device), ids.attention_mask.to(model.device), pos.to(model.device), None, None,
+                    is_prefill=True, all_positions=True, output_logits=True)
+        tol = ast.literal_eval(args.tol_map) if args.tol_map else None
+        accuracy.check_draft_logits(out.logits.float().cpu().transpose(0, 1), expected, tol_map=tol)      # [steps, B, V]
     else:
         raise NotImplementedError(f"accuracy mode {mode}")
     print("Accuracy check passed")
