@@ -92,3 +92,38 @@ def causal_lm_async_execution(app, tokens, positions, n_steps: int, seq_ids=None
     outs = [s.read() for _ in range(n_steps)]
     s.stop()
     return torch.stack(outs, 1)
+
+
+# ---- reference helper names (modules/async_execution.py:10-187) --------------------------------------------------------------
+class AsyncTensorWrapper:
+    """A device result plus the CUDA event that marks it ready (the reference wraps ranked XLA outputs the same way so that the
+    host can defer the synchronisation)."""
+
+    def __init__(self, tensor: torch.Tensor, event: Optional["torch.cuda.Event"] = None):
+        self.tensor, self.event = tensor, event
+
+    def sync_async_result_to_cpu(self) -> torch.Tensor:
+        if self.event is not None:
+            self.event.synchronize()
+        return self.tensor.cpu()
+
+    get = sync_async_result_to_cpu
+
+
+def is_ranked_io(x) -> bool:
+    """Ranked IO = per-rank device-resident inputs (no host staging needed).  Here: any CUDA tensor."""
+    return torch.is_tensor(x) and x.is_cuda
+
+
+def will_hit_bucket_boundary(position_ids: torch.Tensor, buckets, look_ahead: int = 1) -> bool:
+    """True when one of the next ``look_ahead`` steps needs a larger sequence bucket than the current one — the async
+    pipeline then picks the next bucket ahead of time (``second_fit``) instead of re-launching (reference :172-187)."""
+    cur = int(position_ids.max()) + 1
+    now = next((b for b in sorted(buckets) if b > cur), None)
+    later = next((b for b in sorted(buckets) if b > cur + look_ahead), None)
+    return now != later
+
+
+def execute_model(app, *args, **kwargs):
+    """Synchronous single step through the application (reference ``execute_model`` :131-146)."""
+    return app(*args, **kwargs)
