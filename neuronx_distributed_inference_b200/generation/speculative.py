@@ -35,6 +35,66 @@ def greedy_accept(draft_tokens: torch.Tensor, target_tokens: torch.Tensor) -> Tu
     return accepted, n_acc
 
 
+@torch.no_grad()
+def adjust_target_probs(target_probs: torch.Tensor, draft_probs: torch.Tensor) -> torch.Tensor:
+    """Residual distribution ``norm(max(0, p_target - p_draft))`` sampled after a rejection (reference
+    ``_adjust_target_probs`` model_base.py:1678-1695)."""
+    r = (target_probs - draft_probs).clamp_min(0)
+    z = r.sum(-1, keepdim=True)
+    return torch.where(z > 0, r / z.clamp_min(1e-30), target_probs)
+
+
+@torch.no_grad()
+def speculative_sample_accept(draft_tokens: torch.Tensor, draft_probs: torch.Tensor, target_probs: torch.Tensor,
+                              rand_accept: torch.Tensor, rand_sample: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Stochastic (rejection-sampling) acceptance — the output follows the TARGET distribution exactly.
+    draft_tokens [B,k-1]; draft_probs [B,k-1,V] (distribution each draft token was drawn from); target_probs [B,k,V] (target
+    distribution after each of the k inputs); rand_accept [B,k-1], rand_sample [B,k] uniforms.
+    Token i is kept iff ``u_i < p_t(x_i) / p_d(x_i)``; at the first rejection a replacement is drawn from the residual
+    distribution, after k-1 acceptances a bonus token is drawn from the last target distribution.
+    -> (accepted [B,k] padded with -1, n_accepted [B] in 1..k).  Static shapes, no host sync."""
+    B, km1, V = draft_probs.shape
+    k = km1 + 1
+    dev = draft_tokens.device
+    idx = draft_tokens.unsqueeze(-1)
+    pt = target_probs[:, :km1].gather(-1, idx).squeeze(-1)
+    pd = draft_probs.gather(-1, idx).squeeze(-1).clamp_min(1e-30)
+    ok = rand_accept < (pt / pd)
+    n_match = ok.long().cumprod(-1).sum(-1)                                   # 0..k-1 draft tokens kept
+    # distribution of the token that follows the kept prefix
+    resid = adjust_target_probs(target_probs[:, :km1], draft_probs)           # used when a rejection happened at that slot
+    nxt = torch.cat([resid, target_probs[:, km1:]], 1)                        # [B,k,V]; slot k-1 = bonus (no rejection)
+    dist = nxt.gather(1, n_match.view(B, 1, 1).expand(B, 1, V)).squeeze(1)
+    u = rand_sample.gather(1, n_match.view(B, 1))
+    cdf = dist.cumsum(-1)
+    new_tok = (cdf < u * cdf[:, -1:]).sum(-1).clamp_max(V - 1)
+    ar = torch.arange(k, device=dev).view(1, k)
+    toks = torch.cat([draft_tokens, draft_tokens.new_zeros(B, 1)], 1)
+    accepted = torch.where(ar < n_match.view(B, 1), toks, torch.full_like(toks, -1))
+    accepted = torch.where(ar == n_match.view(B, 1), new_tok.view(B, 1), accepted)
+    return accepted, n_match + 1
+
+
+@torch.no_grad()
+def filtered_probs(logits: torch.Tensor, sampling_params: torch.Tensor) -> torch.Tensor:
+    """Per-request sampling distribution: temperature, top-k, top-p (the on-device sampler's rules, modules/sampling.py) as a
+    dense probability vector.  logits [B,T,V], sampling_params [B,3] = (top_k, top_p, temperature)."""
+    B, T, V = logits.shape
+    top_k = sampling_params[:, 0].view(B, 1, 1)
+    top_p = sampling_params[:, 1].view(B, 1, 1)
+    temp = sampling_params[:, 2].view(B, 1, 1)
+    greedy = (temp == 0) | (top_k == 1)
+    x = logits.float() / torch.where(temp > 0, temp, torch.ones_like(temp))
+    sv, si = x.sort(-1, descending=True)
+    rank = torch.arange(V, device=logits.device).view(1, 1, V)
+    keep = torch.where(top_k > 0, rank < top_k, torch.ones_like(rank, dtype=torch.bool)).expand(B, T, V)
+    p = torch.softmax(sv.masked_fill(~keep, float("-inf")), -1)
+    keep = (keep & ((p.cumsum(-1) - p) < top_p)) | (rank == 0)
+    keep = torch.where(greedy, rank == 0, keep)
+    p = torch.softmax(sv.masked_fill(~keep, float("-inf")), -1)
+    return torch.zeros_like(p).scatter(-1, si, p)
+
+
 class FusedSpeculativeModel(nn.Module):
     """Draft + target in one step (role of ``NeuronFusedSpecModel``).  ``forward`` runs k-1 greedy draft steps, one
     target verify over k tokens, the acceptance rule and the next-input derivation without any host
@@ -58,8 +118,49 @@ class FusedSpeculativeModel(nn.Module):
         return out_t
 
     @torch.no_grad()
+    def forward_sampling(self, last_token, position, seq_ids, prev_token, sampling_params, generator=None):
+        """Stochastic variant (``do_sample``): draft tokens are SAMPLED from the filtered draft distribution, the target verifies
+        with rejection sampling (``speculative_sample_accept``) — the emitted tokens follow the target's sampling distribution
+        (reference ``_token_gen_forward`` with ``_adjust_target_probs``, model_base.py:1678-1695,1812-1929)."""
+        k, B, dev = self.k, last_token.shape[0], last_token.device
+        sp = sampling_params.to(dev).float()
+        u = lambda *shape: torch.rand(*shape, device=dev, generator=generator)   # noqa: E731
+
+        def draw(probs, r):
+            cdf = probs.cumsum(-1)
+            return (cdf < r.unsqueeze(-1) * cdf[..., -1:]).sum(-1).clamp_max(probs.shape[-1] - 1)
+        ids = torch.cat([prev_token, last_token], 1)
+        out = self.draft_model(ids, None, torch.cat([position - 1, position], 1), seq_ids, None, is_prefill=False,
+                               all_positions=True, output_logits=True)
+        dprobs, dtoks = [], []
+        pd = filtered_probs(out.logits[:, -1:], sp)
+        pos = position + 1
+        for i in range(k - 1):
+            tok = draw(pd, u(B, 1))
+            dprobs.append(pd)
+            dtoks.append(tok)
+            if i == k - 2:
+                break
+            out = self.draft_model(tok, None, pos, seq_ids, None, is_prefill=False, output_logits=True)
+            pd = filtered_probs(out.logits[:, -1:], sp)
+            pos = pos + 1
+        draft_tokens = torch.cat(dtoks, 1)
+        cand_ids = torch.cat([last_token, draft_tokens], 1)
+        cand_pos = position + torch.arange(k, device=dev, dtype=position.dtype).view(1, k)
+        out_t = self.target_model(cand_ids, None, cand_pos, seq_ids, None, is_prefill=False, all_positions=True, output_logits=True)
+        pt = filtered_probs(out_t.logits, sp)
+        accepted, n_acc = speculative_sample_accept(draft_tokens, torch.cat(dprobs, 1), pt, u(B, k - 1), u(B, k))
+        next_token = accepted.gather(1, (n_acc - 1).view(B, 1))
+        next_pos = position + n_acc.view(B, 1).to(position.dtype)
+        prev_in_step = accepted.gather(1, (n_acc - 2).clamp_min(0).view(B, 1))
+        next_prev = torch.where(n_acc.view(B, 1) >= 2, prev_in_step, last_token)
+        return accepted, n_acc, next_token, next_pos, next_prev, out_t
+
+    @torch.no_grad()
     def forward(self, last_token: torch.Tensor, position: torch.Tensor, seq_ids: torch.Tensor,
-                prev_token: torch.Tensor):
+                prev_token: torch.Tensor, sampling_params: Optional[torch.Tensor] = None, generator=None):
+        if sampling_params is not None and bool(getattr(self.target_model.neuron_config.on_device_sampling_config, "do_sample", False)):
+            return self.forward_sampling(last_token, position, seq_ids, prev_token, sampling_params, generator)
         """last_token [B,1] at absolute ``position`` [B,1]; ``prev_token`` [B,1] is the token at ``position-1``.
         The first draft step always feeds ``[prev_token, last_token]``: when the previous step accepted every
         draft token the draft has not seen ``prev_token`` yet; otherwise it rewrites an identical KV entry, so no
@@ -131,7 +232,10 @@ def assisted_generate(adapter, input_ids, attention_mask, max_length, eos: List[
     done = [int(tok[b]) in eos for b in range(B)]
     stats = {"steps": 0, "accepted": 0}
     while not all(done) and min(len(r) for r, d in zip(rows, done) if not d) < max_length:
-        accepted, n_acc, tok, position, prev, _ = fused(tok, position, seq_ids, prev)
+        if sampling_params is not None and isinstance(fused, FusedSpeculativeModel):
+            accepted, n_acc, tok, position, prev, _ = fused(tok, position, seq_ids, prev, sampling_params)
+        else:
+            accepted, n_acc, tok, position, prev, _ = fused(tok, position, seq_ids, prev)
         acc = accepted.cpu()
         stats["steps"] += 1
         stats["accepted"] += int(n_acc.sum())

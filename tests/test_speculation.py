@@ -65,3 +65,44 @@ def test_fused_speculation_inside_application():
     assert app.fused_spec_model is not None and app.draft_model is not None
     out = HuggingFaceGenerationAdapter(app).generate(ids, max_new_tokens=12)
     assert torch.equal(out[:, : ref.shape[1]], ref)
+
+
+def test_speculative_sampling_follows_the_target_distribution():
+    """Rejection-sampling acceptance: whatever the draft proposes, the first emitted token is distributed like the target."""
+    from neuronx_distributed_inference_b200.generation.speculative import adjust_target_probs, speculative_sample_accept
+    torch.manual_seed(0)
+    V, N, k = 6, 60000, 3
+    p_t = torch.tensor([0.05, 0.4, 0.1, 0.25, 0.15, 0.05])
+    p_d = torch.tensor([0.3, 0.1, 0.3, 0.1, 0.1, 0.1])
+    dprobs = p_d.expand(N, k - 1, V).contiguous()
+    tprobs = p_t.expand(N, k, V).contiguous()
+    dtok = torch.multinomial(p_d, N * (k - 1), replacement=True).view(N, k - 1)
+    acc, n_acc = speculative_sample_accept(dtok, dprobs, tprobs, torch.rand(N, k - 1), torch.rand(N, k))
+    first = acc[:, 0]
+    emp = torch.bincount(first, minlength=V).float() / N
+    assert (emp - p_t).abs().max() < 0.01, emp
+    assert int(n_acc.min()) >= 1 and int(n_acc.max()) <= k and (acc.gather(1, (n_acc - 1).view(-1, 1)) >= 0).all()
+    assert ((acc >= 0).sum(-1) == n_acc).all()
+    # identical distributions: every draft token is accepted
+    acc2, n2 = speculative_sample_accept(dtok, dprobs, dprobs.new_tensor(p_d).expand(N, k, V).contiguous(), torch.rand(N, k - 1), torch.rand(N, k))
+    assert (n2 == k).all() and torch.equal(acc2[:, : k - 1], dtok)
+    r = adjust_target_probs(p_t.view(1, V), p_d.view(1, V))
+    assert torch.allclose(r.sum(-1), torch.ones(1)) and float(r[0, 0]) == 0.0
+
+
+def test_fused_speculation_sampling_path_degenerates_to_greedy_and_samples_valid_tokens():
+    from neuronx_distributed_inference_b200.config import OnDeviceSamplingConfig
+    from neuronx_distributed_inference_b200.modules.sampling import prepare_sampling_params
+    torch.manual_seed(2)
+    ids = torch.randint(1, 128, (2, 6))
+    kw = dict(batch_size=2, seq_len=48, max_context_length=16, device="cpu", dtype="float32", seed=3)
+    ref = HuggingFaceGenerationAdapter(build_random_llama(TINY, **kw)).generate(ids, max_new_tokens=10)
+    app = build_random_llama(TINY, speculation_length=3, enable_fused_speculation=True, fused_draft=dict(hf=dict(num_hidden_layers=1)),
+                             on_device_sampling_config=OnDeviceSamplingConfig(do_sample=True, dynamic=True), **kw)
+    ad = HuggingFaceGenerationAdapter(app)
+    # top_k = 1: the sampling machinery must reproduce greedy decoding exactly
+    out = ad.generate(ids, max_new_tokens=10, sampling_params=prepare_sampling_params(2, 1, 1.0, 1.0))
+    assert torch.equal(out[:, : ref.shape[1]], ref)
+    # genuine sampling: valid tokens, right length, different draws across seeds are allowed
+    out = ad.generate(ids, max_new_tokens=10, sampling_params=prepare_sampling_params(2, 20, 0.9, 1.2))
+    assert out.shape[1] >= ids.shape[1] + 10 and int(out.min()) >= 0 and int(out.max()) < 128
