@@ -69,3 +69,38 @@ def create_block_diagonal_attn_mask(query_lens, key_lens, max_query_len: int, ma
 
 build_mask = ref.build_mask
 attention_with_mask = ops.attention_with_mask
+
+
+def get_last_kv_window(window_size: int, position_ids: torch.Tensor, k: torch.Tensor, v: torch.Tensor, windowed_context_encoding: bool = False):
+    """Last ``window_size`` keys/values of every row (k/v [B,H,S,D]; rows right padded, last real token = max position)."""
+    B, H, S, D = k.shape
+    last = position_ids.long().amax(-1)                                   # [B]
+    start = (last + 1 - window_size).clamp_min(0)
+    idx = (start.view(B, 1) + torch.arange(window_size, device=k.device).view(1, -1)).clamp_max(S - 1)
+    gi = idx.view(B, 1, window_size, 1).expand(B, H, window_size, D)
+    return k.gather(2, gi), v.gather(2, gi)
+
+
+def get_last_kv_chunk(chunk_size: int, position_ids: torch.Tensor, k: torch.Tensor, v: torch.Tensor):
+    """Keys/values of the chunk that contains each row's last token (Llama-4 chunked attention)."""
+    B, H, S, D = k.shape
+    last = position_ids.long().amax(-1)
+    start = (last // chunk_size) * chunk_size
+    idx = (start.view(B, 1) + torch.arange(chunk_size, device=k.device).view(1, -1)).clamp_max(S - 1)
+    gi = idx.view(B, 1, chunk_size, 1).expand(B, H, chunk_size, D)
+    return k.gather(2, gi), v.gather(2, gi)
+
+
+def stride_tensor(t: torch.Tensor, dim: int, stride: int) -> torch.Tensor:
+    """Strided context parallelism: reorder so that rank r's contiguous shard holds positions r, r+stride, ... (load balance of
+    causal attention across CP ranks)."""
+    n = t.shape[dim]
+    order = torch.arange(n, device=t.device).view(n // stride, stride).t().reshape(-1)
+    return t.index_select(dim, order)
+
+
+def order_strided_tensor(t: torch.Tensor, dim: int, stride: int) -> torch.Tensor:
+    """Inverse of :func:`stride_tensor`."""
+    n = t.shape[dim]
+    order = torch.arange(n, device=t.device).view(stride, n // stride).t().reshape(-1)
+    return t.index_select(dim, order)
