@@ -42,6 +42,14 @@ class EagleSpeculativeModel(nn.Module):
         self.tok_buf = TokenRollingBuffer(max_batch_size, L, dev)
         if token_tree is not None:
             token_tree.to(dev)
+            # per-level index tensors, created once (no host->device copies inside the step: it is graph captured)
+            self._lvl = []
+            for d in range(1, token_tree.max_depth + 1):
+                nodes = token_tree.level_nodes[d]
+                first_prev = token_tree.level_nodes[d - 1][0]
+                self._lvl.append(dict(nodes=torch.tensor(nodes, device=dev), par=torch.tensor([token_tree.parent[n] - first_prev for n in nodes], device=dev),
+                                      rank=torch.tensor([token_tree.child_rank[n] for n in nodes], device=dev)))
+            self._pos_off = token_tree.position_offsets.to(dev)
 
     def reset(self):
         self.target_model.reset()
@@ -130,24 +138,23 @@ class EagleSpeculativeModel(nn.Module):
         mask_all = tree.attn_mask.to(dev)
         for d in range(1, tree.max_depth + 1):
             nodes = tree.level_nodes[d]
-            first_prev = tree.level_nodes[d - 1][0]
-            par = torch.tensor([tree.parent[n] - first_prev for n in nodes], device=dev)
-            rank = torch.tensor([tree.child_rank[n] for n in nodes], device=dev)
+            lv = self._lvl[d - 1]
+            par, rank = lv["par"], lv["rank"]
             topk = logits.topk(max(tree.max_children[d - 1], 1), -1).indices      # [B,W_{d-1},K]
             toks = topk[:, par, rank]                                             # [B,W_d]
             if hasattr(self.draft_model, "map_draft_tokens"):
                 toks = self.draft_model.map_draft_tokens(toks)
-            cand[:, nodes] = toks
+            cand[:, lv["nodes"]] = toks
             if d == tree.max_depth:
                 break
-            node_t = torch.tensor(nodes, device=dev, dtype=position.dtype).view(1, -1)
+            node_t = lv["nodes"].to(position.dtype).view(1, -1)
             out = self.draft_model(toks, None, (root_slot + d).expand(B, len(nodes)), seq_ids, None, is_prefill=False,
                                    all_positions=True, prev_hidden=feats[:, par], output_hidden=True, output_logits=True,
-                                   write_positions=root_slot + node_t, active_mask=mask_all[nodes].unsqueeze(0),
+                                   write_positions=root_slot + node_t, active_mask=mask_all[lv["nodes"]].unsqueeze(0),
                                    active_base=root_slot)
             logits, feats = out.logits.float(), out.hidden_states
         node_ids = torch.arange(N, device=dev, dtype=position.dtype).view(1, N)
-        out_t = self.target_model(cand, None, position + tree.position_offsets.to(dev).view(1, N).to(position.dtype), seq_ids,
+        out_t = self.target_model(cand, None, position + self._pos_off.view(1, N).to(position.dtype), seq_ids,
                                   None, is_prefill=False, all_positions=True, output_hidden=True,
                                   write_positions=position + node_ids, active_mask=mask_all.unsqueeze(0), active_base=position)
         tgt = _last_tokens(out_t).view(B, N)

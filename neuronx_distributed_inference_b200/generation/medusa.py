@@ -46,6 +46,9 @@ class MedusaSpeculativeModel(nn.Module):
         if self.tree.max_depth > nh:
             raise ValueError(f"medusa tree depth {self.tree.max_depth} exceeds num_medusa_heads {nh}")
         self.K = max(max(self.tree.max_children), 1)
+        dev = target.device_
+        self._depth = torch.tensor(self.tree.depth, device=dev)
+        self._rank = self.tree.child_rank_t.to(dev)
 
     def reset(self):
         self.target_model.reset()
@@ -71,11 +74,11 @@ class MedusaSpeculativeModel(nn.Module):
         -> (accepted tokens [B,L] padded -1, n_acc [B], next_root [B], next_head_topk, next_position)."""
         tree, B, dev = self.tree, root_token.shape[0], root_token.device
         N = tree.num_nodes
-        depth = torch.tensor(tree.depth, device=dev)
+        depth = self._depth
         cand = torch.empty(B, N, dtype=torch.long, device=dev)
         cand[:, 0] = root_token
         if N > 1:
-            cand[:, 1:] = head_topk[:, depth[1:] - 1, tree.child_rank_t.to(dev)[1:]]
+            cand[:, 1:] = head_topk[:, depth[1:] - 1, self._rank[1:]]
         node_ids = torch.arange(N, device=dev, dtype=position.dtype).view(1, N)
         out = self.target_model(cand, None, position + depth.view(1, N).to(position.dtype), seq_ids, None, is_prefill=False,
                                 all_positions=True, output_logits=True, write_positions=position + node_ids,
@@ -110,8 +113,10 @@ def medusa_generate(adapter, input_ids, attention_mask, max_length, eos: List[in
     rows = [input_ids[b, : int(n_valid[b])].tolist() + [int(root[b])] for b in range(B)]
     done = [int(root[b]) in eos for b in range(B)]
     stats = {"steps": 0, "accepted": 0}
+    from .speculative import maybe_graph_step
+    step = maybe_graph_step(med, lambda r, h, s, p: med(r, h, p, s), [root, heads, seq_ids, position], 5, ("medusa", B))
     while not all(done) and min(len(r) for r, d in zip(rows, done) if not d) < max_length:
-        acc, n_acc, root, heads, position = med(root, heads, position, seq_ids)
+        acc, n_acc, root, heads, position = step(root, heads, seq_ids, position)
         stats["steps"] += 1
         stats["accepted"] += int(n_acc.sum())
         for b, toks in enumerate(acc.cpu().tolist()):

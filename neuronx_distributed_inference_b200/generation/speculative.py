@@ -202,6 +202,55 @@ def _last_tokens(out) -> torch.Tensor:
     return out.logits.argmax(-1)
 
 
+class GraphedStep:
+    """One fused speculation step captured as a CUDA graph: static input buffers, one ``replay()`` per step.
+
+    The reference compiles draft + verify + acceptance into ONE device graph (``NeuronFusedSpecModel``); here the step functions
+    are already free of host synchronisation (acceptance, KV compaction and rolling-buffer updates are tensor code), so the
+    eager Python that issues their ~hundreds of launches is replaced by a graph replay.  Warm-up and capture run with
+    ``seq_ids = -1`` so that every cache / buffer write lands on the garbage line."""
+
+    def __init__(self, fn, example_inputs, n_outputs: int, seq_ids_index: int = 2):
+        self.fn, self.n_out = fn, n_outputs
+        dev = example_inputs[0].device
+        self.static_in = [t.clone() for t in example_inputs]
+        warm = [t.clone() for t in example_inputs]
+        warm[seq_ids_index] = torch.full_like(warm[seq_ids_index], -1)
+        st = torch.cuda.Stream(device=dev)
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(st):
+            for _ in range(2):
+                fn(*warm)
+        torch.cuda.current_stream(dev).wait_stream(st)
+        torch.cuda.synchronize(dev)
+        for dst, src in zip(self.static_in, warm):
+            dst.copy_(src)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=st):
+            out = fn(*self.static_in)
+        self.static_out = tuple(out[: n_outputs])
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
+def maybe_graph_step(owner, fn, example_inputs, n_outputs: int, key):
+    """Graph ``fn`` when the device / model allow it (cached on ``owner`` per ``key``); otherwise return ``fn`` itself."""
+    import os
+    dev = example_inputs[0].device
+    tm = getattr(owner, "target_model", None)
+    if (dev.type != "cuda" or os.environ.get("NXDI_B200_SPEC_GRAPH", "1") == "0" or tm is None or not getattr(tm, "graph_safe", False)
+            or not tm.neuron_config.cuda_graphs):
+        return fn
+    cache = owner.__dict__.setdefault("_graphed_steps", {})
+    if key not in cache:
+        cache[key] = GraphedStep(fn, example_inputs, n_outputs)
+    return cache[key]
+
+
 # ---- host loops ----------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def assisted_generate(adapter, input_ids, attention_mask, max_length, eos: List[int], pad_id: int, assistant_model=None,
@@ -231,11 +280,15 @@ def assisted_generate(adapter, input_ids, attention_mask, max_length, eos: List[
     rows = [input_ids[b, : int(n_valid[b])].tolist() + [int(tok[b])] for b in range(B)]
     done = [int(tok[b]) in eos for b in range(B)]
     stats = {"steps": 0, "accepted": 0}
+    sampled = (sampling_params is not None and isinstance(fused, FusedSpeculativeModel)
+               and bool(getattr(nc.on_device_sampling_config, "do_sample", False)))
+    step = fused if sampled else maybe_graph_step(fused, lambda t, p, s, pv: fused(t, p, s, pv), [tok, position, seq_ids, prev], 5,
+                                                  ("greedy", B))
     while not all(done) and min(len(r) for r, d in zip(rows, done) if not d) < max_length:
-        if sampling_params is not None and isinstance(fused, FusedSpeculativeModel):
+        if sampled:
             accepted, n_acc, tok, position, prev, _ = fused(tok, position, seq_ids, prev, sampling_params)
         else:
-            accepted, n_acc, tok, position, prev, _ = fused(tok, position, seq_ids, prev)
+            accepted, n_acc, tok, position, prev = step(tok, position, seq_ids, prev)[:5]
         acc = accepted.cpu()
         stats["steps"] += 1
         stats["accepted"] += int(n_acc.sum())
