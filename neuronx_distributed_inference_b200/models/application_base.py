@@ -469,6 +469,8 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
         if computed_context_lens is not None:
             extra["has_prefix"] = bool((computed_context_lens > 0).any())
         is_prefill = T > 1 and self._is_prefill(position_ids, computed_context_lens)
+        if getattr(self, "fused_spec_model", None) is not None and adapter_ids is None:
+            return self._fused_speculation_forward(input_ids, attention_mask, position_ids, seq_ids, sampling_params, is_prefill)
         w = nc.windowed_context_encoding_size
         if is_prefill and w and T > w and computed_context_lens is None:
             return self._windowed_context_encoding(input_ids, attention_mask, position_ids, seq_ids, sampling_params, w, extra)
@@ -480,6 +482,29 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
         else:
             out = self.token_generation_model(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **extra)
         return self._construct_output(out)
+
+    def _fused_speculation_forward(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, is_prefill):
+        """``forward`` of an application built with ``enable_fused_speculation`` (reference model_base.py:2857-3021,3821-3862):
+        the prompt goes through both models; every later call takes the last accepted token ``[B,1]`` at ``position_ids`` and
+        returns ``tokens`` = accepted tokens padded with -1 ``[B,k]`` plus
+        ``fused_outputs = [accepted_tokens, next_input_ids, None, next_position_ids, n_accepted]`` (device tensors)."""
+        dev = self.device
+        fused = self.fused_spec_model
+        ids = input_ids.to(dev)
+        pos = position_ids.to(dev, torch.int32)
+        sid = seq_ids.to(dev, torch.int32)
+        if is_prefill:
+            mask = attention_mask.to(dev) if attention_mask is not None else torch.ones_like(ids)
+            out = fused.prefill(ids, mask, pos, sid, sampling_params.to(dev) if sampling_params is not None else None)
+            n = mask.long().sum(-1, keepdim=True)
+            self._spec_prev = ids.gather(1, (n - 1).clamp_min(0))
+            self.kv_cache_populated = True
+            return self._construct_output(out)
+        accepted, n_acc, nxt, npos, prev, out_t = fused(ids, pos, sid, self._spec_prev)
+        self._spec_prev = prev
+        res = CausalLMOutput(tokens=accepted, logits=out_t.logits, hidden_states=None)
+        res.fused_outputs = [accepted, nxt, None, npos, n_acc]
+        return res
 
     def _windowed_context_encoding(self, input_ids, attention_mask, position_ids, seq_ids, sampling_params, w, extra):
         """Long prompts are encoded window by window (reference model_base.py windowed CTE loop, config.py

@@ -106,3 +106,24 @@ def test_fused_speculation_sampling_path_degenerates_to_greedy_and_samples_valid
     # genuine sampling: valid tokens, right length, different draws across seeds are allowed
     out = ad.generate(ids, max_new_tokens=10, sampling_params=prepare_sampling_params(2, 20, 0.9, 1.2))
     assert out.shape[1] >= ids.shape[1] + 10 and int(out.min()) >= 0 and int(out.max()) < 128
+
+
+def test_fused_speculation_through_application_forward():
+    """The reference's calling convention: app.forward returns accepted tokens (padded with -1) and ``fused_outputs``."""
+    torch.manual_seed(4)
+    ids = torch.randint(1, 128, (2, 6))
+    kw = dict(batch_size=2, seq_len=48, max_context_length=16, device="cpu", dtype="float32", seed=3)
+    ref = HuggingFaceGenerationAdapter(build_random_llama(TINY, **kw)).generate(ids, max_new_tokens=9)
+    app = build_random_llama(TINY, speculation_length=3, enable_fused_speculation=True, fused_draft=dict(hf=dict(num_hidden_layers=1)), **kw)
+    out = app(ids, attention_mask=torch.ones_like(ids))
+    tok, pos = out.tokens.view(2, 1), torch.full((2, 1), 6, dtype=torch.int32)
+    rows = [[int(t)] for t in tok.view(-1)]
+    while min(len(r) for r in rows) < 9:
+        out = app(tok, position_ids=pos)
+        acc, nxt, _, npos, n_acc = out.fused_outputs
+        assert out.tokens.shape == (2, 3) and int(n_acc.min()) >= 1
+        for b in range(2):
+            rows[b] += [t for t in acc[b].tolist() if t >= 0]
+        tok, pos = nxt, npos
+    for b in range(2):
+        assert rows[b][:9] == ref[b, 6:15].tolist()
