@@ -50,7 +50,8 @@ class ClassicDecoderLayer(nn.Module):
                                        num_key_value_heads=config.num_key_value_heads, head_dim=config.head_dim, rotary_emb=rotary,
                                        qkv_bias=spec["qkv_bias"], o_bias=spec["o_bias"], use_rope=rotary is not None,
                                        rope_interleaved=spec.get("rope_interleaved", False),
-                                       sliding_window=spec.get("sliding_window"), layer_idx=i, device=device)
+                                       sliding_window=spec.get("sliding_window"), softmax_scale=spec.get("softmax_scale"),
+                                       layer_idx=i, device=device)
         if spec["mlp"] == "gated":
             self.mlp = GatedMLP(H, config.intermediate_size, spec["act"], dt, bias=spec["mlp_bias"], device=device)
         else:
@@ -418,5 +419,133 @@ class NeuronFalconForCausalLM(_ClassicCausalLM):
         return out
 
 
-CLASSIC_MODEL_TYPES = {"opt": NeuronOPTForCausalLM, "gptj": NeuronGPTJForCausalLM, "phi": NeuronPhiForCausalLM, "falcon": NeuronFalconForCausalLM,"starcoder2": NeuronStarcoder2ForCausalLM, "stablelm": NeuronStableLmForCausalLM, "cohere": NeuronCohereForCausalLM,
+# ---- GPT-BigCode (SantaCoder / StarCoder-1): GPT-2 block with multi-query attention and nn.Linear weights --------------------------
+class GPTBigCodeInferenceConfig(GPT2InferenceConfig):
+    def add_derived_config(self):
+        self.num_key_value_heads = 1 if getattr(self, "multi_query", True) else self.num_attention_heads
+        super().add_derived_config()
+
+
+class NeuronGPTBigCodeModel(NeuronClassicModel):
+    learned_positions = True
+
+    def layer_spec(self, config, i):
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "activation_function", "gelu_pytorch_tanh"), qkv_bias=True,
+                    o_bias=True, mlp_bias=True)
+
+
+class NeuronGPTBigCodeForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronGPTBigCodeModel
+    _STATE_DICT_MODEL_PREFIX = "transformer."
+
+    @classmethod
+    def get_config_cls(cls):
+        return GPTBigCodeInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"):
+                continue
+            k = k.replace("h.", "layers.", 1) if k.startswith("h.") else k
+            k = (k.replace(".attn.c_attn.", ".self_attn.qkv_proj.").replace(".attn.c_proj.", ".self_attn.o_proj.").replace(".mlp.c_fc.", ".mlp.fc1.")
+                 .replace(".mlp.c_proj.", ".mlp.fc2.").replace(".ln_1.", ".input_layernorm.").replace(".ln_2.", ".post_attention_layernorm."))
+            out[k.replace("wte.", "embed_tokens.").replace("wpe.", "embed_positions.").replace("ln_f.", "norm.")] = v
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+# ---- GPT-Neo: unscaled attention logits, alternating global / local (windowed) layers ----------------------------------------------
+class GPTNeoInferenceConfig(ClassicInferenceConfig):
+    attribute_map = {"num_layers": "num_hidden_layers", "num_heads": "num_attention_heads"}
+
+    def add_derived_config(self):
+        if getattr(self, "intermediate_size", None) is None:
+            self.intermediate_size = 4 * self.hidden_size
+        super().add_derived_config()
+
+
+class NeuronGPTNeoModel(NeuronClassicModel):
+    learned_positions = True
+
+    def layer_spec(self, config, i):
+        kinds = getattr(config, "attention_layers", None)
+        if not kinds:
+            kinds = []
+            for pattern, n in getattr(config, "attention_types", [[["global"], config.num_hidden_layers]]):
+                kinds += list(pattern) * n
+        local = kinds[i] == "local"
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "activation_function", "gelu_new"), qkv_bias=False, o_bias=True,
+                    mlp_bias=True, softmax_scale=1.0, sliding_window=getattr(config, "window_size", 256) if local else None)
+
+
+class NeuronGPTNeoForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronGPTNeoModel
+    _STATE_DICT_MODEL_PREFIX = "transformer."
+
+    @classmethod
+    def get_config_cls(cls):
+        return GPTNeoInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".attention.bias") or k.endswith(".attention.masked_bias"):
+                continue
+            k = k.replace("h.", "layers.", 1) if k.startswith("h.") else k
+            k = (k.replace(".attn.attention.out_proj.", ".self_attn.o_proj.").replace(".attn.attention.", ".self_attn.").replace(".mlp.c_fc.", ".mlp.fc1.")
+                 .replace(".mlp.c_proj.", ".mlp.fc2.").replace(".ln_1.", ".input_layernorm.").replace(".ln_2.", ".post_attention_layernorm."))
+            out[k.replace("wte.", "embed_tokens.").replace("wpe.", "embed_positions.").replace("ln_f.", "norm.")] = v
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+# ---- BioGPT: OPT-style block, sqrt(H)-scaled embeddings -------------------------------------------------------------------------------
+class NeuronBioGptModel(NeuronClassicModel):
+    learned_positions = True
+    position_offset = 2
+
+    def init_model(self, config):
+        super().init_model(config)
+        if getattr(config, "scale_embedding", True):
+            self.embed_scale = float(config.hidden_size ** 0.5)
+
+    def embed(self, input_ids, inputs_embeds=None, vision_embeddings=None, vision_mask=None):
+        h = self.embed_tokens(input_ids) * getattr(self, "embed_scale", 1.0)
+        pos = self._pos if self._pos is not None else torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0)
+        return h + self.embed_positions((pos.long() + self.position_offset).clamp(0, self.embed_positions.num_embeddings - 1))
+
+    def layer_spec(self, config, i):
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "hidden_act", "gelu"), qkv_bias=True, o_bias=True, mlp_bias=True)
+
+
+class NeuronBioGptForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronBioGptModel
+    _STATE_DICT_MODEL_PREFIX = "biogpt."
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            if k.startswith("layers."):
+                k = (k.replace(".self_attn.out_proj.", ".self_attn.o_proj.").replace(".self_attn_layer_norm.", ".input_layernorm.")
+                     .replace(".final_layer_norm.", ".post_attention_layernorm.").replace(".fc1.", ".mlp.fc1.").replace(".fc2.", ".mlp.fc2."))
+            elif k.startswith("layer_norm."):
+                k = k.replace("layer_norm.", "norm.")
+            elif k.startswith("output_projection."):
+                k = k.replace("output_projection.", "lm_head.")
+            out[k] = v
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+CLASSIC_MODEL_TYPES = {"gpt_bigcode": NeuronGPTBigCodeForCausalLM, "gpt_neo": NeuronGPTNeoForCausalLM, "biogpt": NeuronBioGptForCausalLM,
+                       "opt": NeuronOPTForCausalLM, "gptj": NeuronGPTJForCausalLM, "phi": NeuronPhiForCausalLM, "falcon": NeuronFalconForCausalLM,"starcoder2": NeuronStarcoder2ForCausalLM, "stablelm": NeuronStableLmForCausalLM, "cohere": NeuronCohereForCausalLM,
                        "gpt_neox": NeuronGPTNeoXForCausalLM, "gpt2": NeuronGPT2ForCausalLM}

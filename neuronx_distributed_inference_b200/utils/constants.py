@@ -41,7 +41,8 @@ MODEL_TYPES.update({
     "cohere": {"causal-lm": f"{_K}:NeuronCohereForCausalLM"}, "gpt_neox": {"causal-lm": f"{_K}:NeuronGPTNeoXForCausalLM"},
     "gpt2": {"causal-lm": f"{_K}:NeuronGPT2ForCausalLM"}, "opt": {"causal-lm": f"{_K}:NeuronOPTForCausalLM"},
     "gptj": {"causal-lm": f"{_K}:NeuronGPTJForCausalLM"}, "phi": {"causal-lm": f"{_K}:NeuronPhiForCausalLM"},
-    "falcon": {"causal-lm": f"{_K}:NeuronFalconForCausalLM"},
+    "falcon": {"causal-lm": f"{_K}:NeuronFalconForCausalLM"}, "gpt_bigcode": {"causal-lm": f"{_K}:NeuronGPTBigCodeForCausalLM"},
+    "gpt_neo": {"causal-lm": f"{_K}:NeuronGPTNeoForCausalLM"}, "biogpt": {"causal-lm": f"{_K}:NeuronBioGptForCausalLM"},
 })
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 

@@ -47,6 +47,14 @@ def _cfg(name):
     if name == "falcon":
         return T.FalconConfig(hidden_size=64, num_hidden_layers=3, num_attention_heads=4, vocab_size=160, new_decoder_architecture=False,
                               multi_query=True, parallel_attn=True, bias=False, alibi=False, max_position_embeddings=256)
+    if name == "gpt_bigcode":
+        return T.GPTBigCodeConfig(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256, multi_query=True)
+    if name == "gpt_neo":
+        return T.GPTNeoConfig(hidden_size=64, num_layers=4, num_heads=4, vocab_size=160, max_position_embeddings=256,
+                              attention_types=[[["global", "local"], 2]], window_size=8)
+    if name == "biogpt":
+        return T.BioGptConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, vocab_size=160,
+                              max_position_embeddings=256)
     if name == "starcoder2":
         return T.Starcoder2Config(**BASE, sliding_window=None)
     if name == "stablelm":
@@ -63,7 +71,7 @@ def _cfg(name):
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
-                                  "falcon"])
+                                  "falcon", "gpt_bigcode", "gpt_neo", "biogpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
