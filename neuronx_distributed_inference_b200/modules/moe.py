@@ -112,6 +112,7 @@ class MoE(nn.Module):
         self.return_expert_index = return_expert_index
         self.early_affinity_modulation = early_affinity_modulation   # Llama-4: scale the expert INPUT by the affinity
         self.tp_all = get_tensor_model_parallel_group()
+        self.shared_expert_gate = None     # optional [1,H] linear: sigmoid gate on the shared expert (Qwen2-MoE)
         self.last_router_logits = None
         self.last_expert_index = None
 
@@ -129,7 +130,10 @@ class MoE(nn.Module):
         else:
             y = self.expert_mlps(x2, w.to(torch.float32), idx)
         if self.shared_experts is not None:
-            y = y + self.shared_experts(x2, reduce=False)
+            sh = self.shared_experts(x2, reduce=False)
+            if self.shared_expert_gate is not None:    # same scalar on every rank: commutes with the TP reduction below
+                sh = sh * torch.sigmoid(torch.nn.functional.linear(x2.float(), self.shared_expert_gate.weight.float())).to(sh.dtype)
+            y = y + sh
         if self.tp_all.size > 1:
             y = mappings.all_reduce(y, self.tp_all)
         y = y.view(shape)

@@ -44,6 +44,11 @@ MODEL_TYPES.update({
     "falcon": {"causal-lm": f"{_K}:NeuronFalconForCausalLM"}, "gpt_bigcode": {"causal-lm": f"{_K}:NeuronGPTBigCodeForCausalLM"},
     "gpt_neo": {"causal-lm": f"{_K}:NeuronGPTNeoForCausalLM"}, "biogpt": {"causal-lm": f"{_K}:NeuronBioGptForCausalLM"},
 })
+_M = "neuronx_distributed_inference_b200.contrib.models.moe_family"
+MODEL_TYPES.update({
+    "qwen2_moe": {"causal-lm": f"{_M}:NeuronQwen2MoeForCausalLM"}, "olmoe": {"causal-lm": f"{_M}:NeuronOlmoeForCausalLM"},
+    "exaone4": {"causal-lm": f"{_M}:NeuronExaone4ForCausalLM"},
+})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

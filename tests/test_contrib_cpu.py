@@ -55,6 +55,14 @@ def _cfg(name):
     if name == "biogpt":
         return T.BioGptConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, vocab_size=160,
                               max_position_embeddings=256)
+    if name == "qwen2_moe":
+        return T.Qwen2MoeConfig(**BASE, moe_intermediate_size=32, shared_expert_intermediate_size=64, num_experts=4, num_experts_per_tok=2,
+                                decoder_sparse_step=1)
+    if name == "olmoe":
+        return T.OlmoeConfig(**BASE, num_experts=4, num_experts_per_tok=2, pad_token_id=0)
+    if name == "exaone4":
+        return T.Exaone4Config(**{**BASE, "num_hidden_layers": 4}, head_dim=16, sliding_window=8, sliding_window_pattern=2,
+                               layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"])
     if name == "starcoder2":
         return T.Starcoder2Config(**BASE, sliding_window=None)
     if name == "stablelm":
@@ -71,7 +79,7 @@ def _cfg(name):
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
-                                  "falcon", "gpt_bigcode", "gpt_neo", "biogpt"])
+                                  "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
@@ -79,7 +87,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     ckpt = save_random_hf_checkpoint(hf_cfg, str(tmp_path / name), seed=2)
     hf = AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32).eval()
     from neuronx_distributed_inference_b200.contrib.models.classic_family import CLASSIC_MODEL_TYPES
-    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES}[name]
+    from neuronx_distributed_inference_b200.contrib.models.moe_family import MOE_MODEL_TYPES
+    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES}[name]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
