@@ -48,6 +48,7 @@ _M = "neuronx_distributed_inference_b200.contrib.models.moe_family"
 MODEL_TYPES.update({
     "qwen2_moe": {"causal-lm": f"{_M}:NeuronQwen2MoeForCausalLM"}, "olmoe": {"causal-lm": f"{_M}:NeuronOlmoeForCausalLM"},
     "exaone4": {"causal-lm": f"{_M}:NeuronExaone4ForCausalLM"},
+    "llava": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.llava:NeuronLlavaForCausalLM"},
 })
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 

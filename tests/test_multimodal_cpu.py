@@ -199,3 +199,31 @@ def test_llama4_multimodal_matches_hf(tmp_path):
         exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix).logits
     out = app(ids, attention_mask=mask, pixel_values=pix)
     assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
+
+
+def test_llava_1_5_matches_hf(tmp_path):
+    from transformers import CLIPVisionConfig, LlamaConfig, LlavaConfig, LlavaForConditionalGeneration
+    from neuronx_distributed_inference_b200.contrib.models.llava import NeuronLlavaForCausalLM
+    torch.manual_seed(0)
+    cfg = LlavaConfig(
+        vision_config=CLIPVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, patch_size=4,
+                                       image_size=16, projection_dim=16).to_dict(),
+        text_config=LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                vocab_size=200).to_dict(),
+        image_token_index=150, vision_feature_layer=-2, vision_feature_select_strategy="default")
+    hf = LlavaForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "llava")
+    hf.save_pretrained(ckpt)
+    cls = NeuronLlavaForCausalLM
+    nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=64, max_context_length=32, torch_dtype="float32", on_cpu=True, output_logits=True)
+    app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
+    app.load(None, skip_warmup=True)
+    pix = torch.randn(2, 3, 16, 16)                      # 16 patches each
+    ids = torch.randint(1, 140, (2, 22))
+    ids[0, 1:17] = 150
+    ids[1, 4:20] = 150
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix).logits
+    out = app(ids, attention_mask=mask, pixel_values=pix)
+    assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
