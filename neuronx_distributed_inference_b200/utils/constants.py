@@ -49,6 +49,7 @@ MODEL_TYPES.update({
     "qwen2_moe": {"causal-lm": f"{_M}:NeuronQwen2MoeForCausalLM"}, "olmoe": {"causal-lm": f"{_M}:NeuronOlmoeForCausalLM"},
     "exaone4": {"causal-lm": f"{_M}:NeuronExaone4ForCausalLM"},
     "llava": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.llava:NeuronLlavaForCausalLM"},
+    "qwen2_5_vl": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.qwen2_5_vl:NeuronQwen25VLForCausalLM"},
 })
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 

@@ -227,3 +227,38 @@ def test_llava_1_5_matches_hf(tmp_path):
         exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix).logits
     out = app(ids, attention_mask=mask, pixel_values=pix)
     assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
+
+
+def test_qwen2_5_vl_matches_hf(tmp_path):
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+    from neuronx_distributed_inference_b200.contrib.models.qwen2_5_vl import NeuronQwen25VLForCausalLM
+    torch.manual_seed(0)
+    cfg = Qwen2_5_VLConfig(
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                         vocab_size=200, max_position_embeddings=512,
+                         rope_parameters=dict(rope_type="default", mrope_section=[2, 3, 3], rope_theta=10000.0)),
+        vision_config=dict(depth=3, hidden_size=32, intermediate_size=64, out_hidden_size=64, num_heads=2, patch_size=4, spatial_merge_size=2,
+                           temporal_patch_size=2, in_channels=3, window_size=16, fullatt_block_indexes=[1],
+                           tokens_per_second=1),      # transformers 5.5 multiplies an IMAGE's start position by this interval;
+        # the released model uses t = start for images (interval only spaces video frames): 1 makes both agree
+        image_token_id=150, video_token_id=151, vision_start_token_id=152, vision_end_token_id=153)
+    hf = Qwen2_5_VLForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "qwen25vl")
+    hf.save_pretrained(ckpt)
+    cls = NeuronQwen25VLForCausalLM
+    nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=64, max_context_length=32, torch_dtype="float32", on_cpu=True, output_logits=True)
+    app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
+    app.load(None, skip_warmup=True)
+    grid = torch.tensor([[1, 4, 8], [1, 8, 4]])             # 8 merged tokens each; 2x2-unit windows
+    pix = torch.randn(64, 3 * 2 * 4 * 4)
+    ids = torch.randint(1, 140, (2, 14))
+    ids[0, 2:10] = 150
+    ids[1, 1:9] = 150
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        vis = hf.model.visual(pix, grid_thw=grid)
+        vis = vis.pooler_output if hasattr(vis, "pooler_output") else vis
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid, mm_token_type_ids=(ids == 150).int())
+    assert _rel(app.encode_images(pix, image_grid_thw=grid), vis) < 1e-4
+    out = app(ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid)
+    assert _rel(out.logits[:, -1], exp.logits[:, -1]) < 2e-4
