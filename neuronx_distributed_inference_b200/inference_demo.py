@@ -204,7 +204,7 @@ def _maybe_relaunch(args, argv):
     tp = args.tp_degree or 1
     if tp <= 1 or args.on_cpu and tp <= 1 or "RANK" in os.environ or args.no_launch:
         return False
-    n = tp * (args.ep_degree or 1) if False else tp
+    n = tp          # experts are sharded INSIDE the tensor-parallel world (ep x moe_tp == tp): no extra processes
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", os.environ.get("MASTER_PORT", "29533"), "-m", "neuronx_distributed_inference_b200.inference_demo"] + list(argv)
     logger.info("launching %d ranks: %s", n, " ".join(cmd))

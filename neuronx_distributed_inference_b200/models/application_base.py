@@ -335,8 +335,7 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
         nc = self.neuron_config
         self.models = []
         self.enable_context_encoding()
-        if nc.max_new_tokens is None or nc.max_length > nc.max_context_length or True:
-            self.enable_token_generation()
+        self.enable_token_generation()
         if nc.speculation_length > 0 and not nc.enable_fused_speculation:
             self.enable_speculation()
 

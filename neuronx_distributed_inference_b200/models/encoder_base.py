@@ -15,7 +15,7 @@ import torch.nn as nn
 from ..modules.checkpoint import load_sharded
 from .application_base import NeuronApplicationBase
 
-logger = logging.getLogger("nxdi_b200")
+logger = logging.getLogger("b200infer")
 
 VISION_ENCODER_MODEL_TAG = "vision_encoder_model"
 

@@ -110,7 +110,7 @@ class NeuronBaseModel(nn.Module):
 
     def _kernels_cover_decode(self) -> bool:
         nc = self.neuron_config
-        if nc.torch_dtype != torch.bfloat16 or nc.kv_cache_quant or nc.is_block_kv_layout and False:
+        if nc.torch_dtype != torch.bfloat16 or nc.kv_cache_quant:
             return False
         for layer in self.layers:
             attn = getattr(layer, "self_attn", None)
