@@ -51,6 +51,12 @@ MODEL_TYPES.update({
     "llava": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.llava:NeuronLlavaForCausalLM"},
     "qwen2_5_vl": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.qwen2_5_vl:NeuronQwen25VLForCausalLM"},
 })
+_X = "neuronx_distributed_inference_b200.contrib.models.more_families"
+MODEL_TYPES.update({
+    "gemma": {"causal-lm": f"{_X}:NeuronGemmaForCausalLM"}, "vaultgemma": {"causal-lm": f"{_X}:NeuronVaultGemmaForCausalLM"},
+    "glm": {"causal-lm": f"{_X}:NeuronGlmForCausalLM"}, "cohere2": {"causal-lm": f"{_X}:NeuronCohere2ForCausalLM"},
+    "apertus": {"causal-lm": f"{_X}:NeuronApertusForCausalLM"}, "nemotron": {"causal-lm": f"{_X}:NeuronNemotronForCausalLM"},
+})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

@@ -74,12 +74,28 @@ def _cfg(name):
                                max_position_embeddings=256, rotary_pct=0.25)
     if name == "gpt2":
         return T.GPT2Config(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256)
+    if name == "gemma":
+        return T.GemmaConfig(**BASE, head_dim=16)
+    if name == "vaultgemma":
+        return T.VaultGemmaConfig(**{**BASE, "num_hidden_layers": 4}, head_dim=16, sliding_window=8, query_pre_attn_scalar=16,
+                                  attn_logit_softcapping=20.0, final_logit_softcapping=10.0,
+                                  layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"])
+    if name == "glm":
+        return T.GlmConfig(**BASE, head_dim=16, pad_token_id=0)
+    if name == "cohere2":
+        return T.Cohere2Config(**{**BASE, "num_hidden_layers": 4}, logit_scale=0.25, pad_token_id=0, sliding_window=8,
+                               layer_types=["sliding_attention", "sliding_attention", "sliding_attention", "full_attention"])
+    if name == "apertus":
+        return T.ApertusConfig(**BASE, pad_token_id=0)
+    if name == "nemotron":
+        return T.NemotronConfig(**BASE, head_dim=16, partial_rotary_factor=0.5)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
-                                  "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4"])
+                                  "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
+                                  "glm", "cohere2", "apertus", "nemotron"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
@@ -88,7 +104,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     hf = AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32).eval()
     from neuronx_distributed_inference_b200.contrib.models.classic_family import CLASSIC_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.moe_family import MOE_MODEL_TYPES
-    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES}[name]
+    from neuronx_distributed_inference_b200.contrib.models.more_families import MORE_MODEL_TYPES
+    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES}[name]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
