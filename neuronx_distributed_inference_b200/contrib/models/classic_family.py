@@ -46,7 +46,7 @@ class ClassicDecoderLayer(nn.Module):
         dt = config.neuron_config.torch_dtype
         H, eps = config.hidden_size, config.rms_norm_eps
         self.parallel, self.shared_norm = spec["parallel"], spec.get("shared_norm", False)
-        self.self_attn = AttentionBase(config, hidden_size=H, num_attention_heads=config.num_attention_heads,
+        self.self_attn = spec.get("attn_cls", AttentionBase)(config, hidden_size=H, num_attention_heads=config.num_attention_heads,
                                        num_key_value_heads=config.num_key_value_heads, head_dim=config.head_dim, rotary_emb=rotary,
                                        qkv_bias=spec["qkv_bias"], o_bias=spec["o_bias"], use_rope=rotary is not None and spec.get("use_rope", True),
                                        rope_interleaved=spec.get("rope_interleaved", False),

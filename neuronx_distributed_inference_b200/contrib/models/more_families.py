@@ -5,6 +5,9 @@
 * **GLM-4-9B-chat (``glm``)** — partial (50 %) interleaved rotary, q/k/v biases, fused gate_up in the checkpoint.
 * **Cohere2 / Command-R7B** — Cohere block; sliding-window layers use RoPE, full-attention layers have NO position encoding.
 * **Apertus** — per-head q/k RMSNorm, non-gated MLP with the learned xIELU activation.
+* **Persimmon** — per-head LayerNorm (with bias) on q and k, head-interleaved fused QKV, partial rotary, squared-ReLU MLP.
+* **XGLM** — fairseq-style sinusoidal position table (offset 2), sqrt(H)-scaled embeddings, pre-LN GELU block.
+* **CodeGen** — GPT-J block whose fused QKV is laid out in 4 "logical core" groups of [q | v | k].
 * **Nemotron** — LayerNorm1P (1 + w, folded into the weight at load), partial rotary, squared-ReLU non-gated MLP.
 reference ports: contrib/models/{gemma-2b-it, vaultgemma-1b, glm-4-9b-chat-hf, c4ai-command-r7b-12-2024, Apertus-8B-Instruct-2509}/src."""
 from __future__ import annotations
@@ -20,10 +23,12 @@ from ...models.gemma3.modeling_gemma3 import Gemma3InferenceConfig, _is_sliding
 from ...models.llama.modeling_llama import NeuronLlamaAttention, NeuronLlamaForCausalLM, NeuronLlamaModel, rope_scaling_of, rope_theta_of
 from ...models.model_base import DecoderLayer
 from ...models.state_dict_utils import fuse_qkv_and_gate_up
+from ...modules.attention import AttentionBase
 from ...modules.mlp import PlainMLP
 from ...modules.norm import RMSNorm
 from ...modules.rope import RotaryEmbedding
-from .classic_family import NeuronClassicModel, _ClassicCausalLM, _rename_plain_mlp
+from .classic_family import (ClassicInferenceConfig, GPTJInferenceConfig, NeuronClassicModel, NeuronGPTJForCausalLM, NeuronGPTJModel,
+                             _ClassicCausalLM, _rename_plain_mlp)
 
 
 def _partial_rotary(config, default=1.0):
@@ -221,5 +226,140 @@ class NeuronNemotronForCausalLM(_ClassicCausalLM):
         sd["lm_head.weight"] = sd["embed_tokens.weight"].clone()
 
 
-MORE_MODEL_TYPES = {"gemma": NeuronGemmaForCausalLM, "vaultgemma": NeuronVaultGemmaForCausalLM, "glm": NeuronGlmForCausalLM,
+# ---------------------------------------------------------------------------------------------------------- Persimmon
+class _PersimmonAttention(AttentionBase):
+    def __init__(self, config, **kw):
+        super().__init__(config, **kw)
+        dt, eps = config.neuron_config.torch_dtype, config.rms_norm_eps
+        self.q_layernorm = nn.LayerNorm(self.head_dim, eps=eps, dtype=dt, device=kw.get("device"))
+        self.k_layernorm = nn.LayerNorm(self.head_dim, eps=eps, dtype=dt, device=kw.get("device"))
+        self.per_head_ln = bool(getattr(config, "qk_layernorm", True))
+        for p in (*self.q_layernorm.parameters(), *self.k_layernorm.parameters()):
+            p.requires_grad_(False)
+
+    def _simple(self):
+        return False
+
+    def _split_norm_rope(self, qkv, B, T, cos, sin, meta=None):
+        D, nq, nkv = self.head_dim, self.n_q, self.n_kv
+        q, k, v = qkv.reshape(B, T, nq + 2 * nkv, D).split([nq, nkv, nkv], dim=2)
+        if self.per_head_ln:
+            q, k = self.q_layernorm(q), self.k_layernorm(k)
+        if cos is not None:
+            q, k = ops.apply_rope(q, cos, sin, False), ops.apply_rope(k, cos, sin, False)
+        return q, k, v
+
+
+class NeuronPersimmonModel(NeuronClassicModel):
+    def layer_spec(self, config, i):
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "hidden_act", "relu2"), qkv_bias=True, o_bias=True,
+                    mlp_bias=True, attn_cls=_PersimmonAttention)
+
+
+class NeuronPersimmonForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronPersimmonModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        nh, D = config.num_attention_heads, config.hidden_size // config.num_attention_heads
+        out = {}
+        for k, v in sd.items():
+            if ".self_attn.query_key_value." in k:        # [heads, (q,k,v), D, ...] -> [q heads; k heads; v heads]
+                w = v.view(nh, 3, D, *v.shape[1:])
+                v = torch.cat([w[:, j].reshape(nh * D, *v.shape[1:]) for j in range(3)], 0)
+                k = k.replace(".query_key_value.", ".qkv_proj.")
+            k = (k.replace(".self_attn.dense.", ".self_attn.o_proj.").replace(".mlp.dense_h_to_4h.", ".mlp.fc1.")
+                 .replace(".mlp.dense_4h_to_h.", ".mlp.fc2.").replace("final_layernorm.", "norm."))
+            out[k] = v
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------- XGLM
+class XGLMInferenceConfig(ClassicInferenceConfig):
+    attribute_map = {"d_model": "hidden_size", "attention_heads": "num_attention_heads", "num_layers": "num_hidden_layers",
+                     "ffn_dim": "intermediate_size"}
+
+
+def _fairseq_sinusoids(n, dim, padding_idx=None):
+    half = dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    ang = torch.arange(n, dtype=torch.float32).unsqueeze(1) * freq.unsqueeze(0)
+    tab = torch.cat([ang.sin(), ang.cos()], 1)
+    if dim % 2:
+        tab = torch.cat([tab, torch.zeros(n, 1)], 1)
+    if padding_idx is not None:
+        tab[padding_idx] = 0
+    return tab
+
+
+class NeuronXGLMModel(NeuronClassicModel):
+    learned_positions = True          # a fixed table, but looked up the same way
+    position_offset = 2
+
+    def init_model(self, config):
+        super().init_model(config)
+        self.embed_scale = float(config.hidden_size ** 0.5) if getattr(config, "scale_embedding", True) else 1.0
+
+    def embed(self, input_ids, inputs_embeds=None, vision_embeddings=None, vision_mask=None):
+        h = self.embed_tokens(input_ids) * self.embed_scale
+        pos = self._pos if self._pos is not None else torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0)
+        return h + self.embed_positions((pos.long() + self.position_offset).clamp(0, self.embed_positions.num_embeddings - 1))
+
+    def layer_spec(self, config, i):
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "activation_function", "gelu"), qkv_bias=True, o_bias=True,
+                    mlp_bias=True)
+
+
+class NeuronXGLMForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronXGLMModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return XGLMInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            if k.startswith("layers."):
+                k = (k.replace(".self_attn.out_proj.", ".self_attn.o_proj.").replace(".self_attn_layer_norm.", ".input_layernorm.")
+                     .replace(".final_layer_norm.", ".post_attention_layernorm.").replace(".fc1.", ".mlp.fc1.").replace(".fc2.", ".mlp.fc2."))
+            elif k.startswith("layer_norm."):
+                k = k.replace("layer_norm.", "norm.")
+            elif k.startswith("embed_positions."):
+                continue
+            out[k] = v
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+        tab = _fairseq_sinusoids(config.max_position_embeddings + 2, config.hidden_size, getattr(config, "pad_token_id", 1))
+        out["embed_positions.weight"] = tab.to(out["embed_tokens.weight"].dtype)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------- CodeGen
+class NeuronCodeGenForCausalLM(NeuronGPTJForCausalLM):
+    _model_cls = NeuronGPTJModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return GPTJInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        mp = 4
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".attn.qkv_proj.weight"):
+                H = v.shape[1]
+                w = v.view(mp, 3, H // mp, H)                  # per logical core: [q | v | k]
+                q, vv, kk = (w[:, j].reshape(H, H) for j in range(3))
+                v = torch.cat([q, kk, vv], 0)
+                k = k.replace(".attn.qkv_proj.", ".self_attn.qkv_proj.")
+            out[k] = v
+        return NeuronGPTJForCausalLM.convert_hf_to_neuron_state_dict(out, config)
+
+
+MORE_MODEL_TYPES = {"persimmon": NeuronPersimmonForCausalLM, "xglm": NeuronXGLMForCausalLM, "codegen": NeuronCodeGenForCausalLM,
+                    "gemma": NeuronGemmaForCausalLM, "vaultgemma": NeuronVaultGemmaForCausalLM, "glm": NeuronGlmForCausalLM,
                     "cohere2": NeuronCohere2ForCausalLM, "apertus": NeuronApertusForCausalLM, "nemotron": NeuronNemotronForCausalLM}

@@ -56,6 +56,8 @@ MODEL_TYPES.update({
     "gemma": {"causal-lm": f"{_X}:NeuronGemmaForCausalLM"}, "vaultgemma": {"causal-lm": f"{_X}:NeuronVaultGemmaForCausalLM"},
     "glm": {"causal-lm": f"{_X}:NeuronGlmForCausalLM"}, "cohere2": {"causal-lm": f"{_X}:NeuronCohere2ForCausalLM"},
     "apertus": {"causal-lm": f"{_X}:NeuronApertusForCausalLM"}, "nemotron": {"causal-lm": f"{_X}:NeuronNemotronForCausalLM"},
+    "persimmon": {"causal-lm": f"{_X}:NeuronPersimmonForCausalLM"}, "xglm": {"causal-lm": f"{_X}:NeuronXGLMForCausalLM"},
+    "codegen": {"causal-lm": f"{_X}:NeuronCodeGenForCausalLM"},
 })
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 

@@ -89,13 +89,20 @@ def _cfg(name):
         return T.ApertusConfig(**BASE, pad_token_id=0)
     if name == "nemotron":
         return T.NemotronConfig(**BASE, head_dim=16, partial_rotary_factor=0.5)
+    if name == "persimmon":
+        return T.PersimmonConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, vocab_size=160,
+                                 max_position_embeddings=256, partial_rotary_factor=0.5, qk_layernorm=True)
+    if name == "xglm":
+        return T.XGLMConfig(d_model=64, ffn_dim=128, num_layers=3, attention_heads=4, vocab_size=160, max_position_embeddings=256)
+    if name == "codegen":
+        return T.CodeGenConfig(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256, rotary_dim=8)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
