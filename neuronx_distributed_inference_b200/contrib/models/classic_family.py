@@ -52,7 +52,10 @@ class ClassicDecoderLayer(nn.Module):
                                        rope_interleaved=spec.get("rope_interleaved", False),
                                        sliding_window=spec.get("sliding_window"), softmax_scale=spec.get("softmax_scale"),
                                        layer_idx=i, device=device)
-        if spec["mlp"] == "gated":
+        if callable(spec["mlp"]):                     # MoE (or any custom) feed-forward: factory(config, device)
+            self.mlp = spec["mlp"](config, device)
+            self.mlp_is_moe = True
+        elif spec["mlp"] == "gated":
             self.mlp = GatedMLP(H, config.intermediate_size, spec["act"], dt, bias=spec["mlp_bias"], device=device)
         else:
             self.mlp = PlainMLP(H, config.intermediate_size, spec["act"], dt, bias=spec["mlp_bias"], device=device)

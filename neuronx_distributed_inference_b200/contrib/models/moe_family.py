@@ -4,7 +4,9 @@
 * **OLMoE** — Llama block with q/k RMSNorm over the whole projection, 64-expert style router without renormalisation.
 * **EXAONE-4** (dense, listed here because it shares the post-norm block) — post-norm residuals, per-head q/k RMSNorm, hybrid
   sliding / global layers with rotary only on the sliding ones.
-reference ports: contrib/models/{EXAONE-4.0-1.2B}/src and the MoE glue of modules/moe_v2.py."""
+* **GraniteMoE** — Granite multipliers around a top-k MoE whose experts ship as fused ``input_linear`` / ``output_linear``.
+* **Phi-3.5-MoE** — LayerNorm block, biased attention / head, SparseMixer top-2 routing (jitter-thresholded softmax per pick).
+reference ports: contrib/models/{EXAONE-4.0-1.2B, Phi-3.5-MoE-instruct}/src and the MoE glue of modules/moe_v2.py."""
 from __future__ import annotations
 
 import torch
@@ -19,6 +21,7 @@ from ...modules.attention import AttentionBase
 from ...modules.mlp import GatedMLP
 from ...modules.moe import initialize_moe_module
 from ...modules.norm import RMSNorm
+from .classic_family import NeuronClassicModel, _ClassicCausalLM
 from .llama_family import Olmo2Attention
 
 
@@ -151,4 +154,115 @@ class NeuronExaone4ForCausalLM(NeuronLlamaForCausalLM):
                 for k, v in sd.items()}
 
 
-MOE_MODEL_TYPES = {"qwen2_moe": NeuronQwen2MoeForCausalLM, "olmoe": NeuronOlmoeForCausalLM, "exaone4": NeuronExaone4ForCausalLM}
+# ---- GraniteMoE -------------------------------------------------------------------------------------------------------------------
+class NeuronGraniteMoeModel(NeuronLlamaModel):
+    graph_safe = False
+
+    def init_model(self, config):
+        super().init_model(config)
+        self.embed_scale = float(getattr(config, "embedding_multiplier", 1.0))
+
+    def make_layer(self, config, i, rotary, device):
+        dt = config.neuron_config.torch_dtype
+        attn = self.attention_cls(config, i, rotary, device=device, softmax_scale=float(getattr(config, "attention_multiplier", None)
+                                                                                        or config.head_dim ** -0.5))
+        moe = initialize_moe_module(config, device=device, normalize=True)      # softmax over the selected logits == renormalised top-k
+        return DecoderLayer(attn, moe, RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device),
+                            RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device), i, mlp_is_moe=True)
+
+
+class NeuronGraniteMoeForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronGraniteMoeModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return _MoeConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        """The residual multiplier scales linear outputs (o_proj, expert down projections) and the logits scaling divides the head:
+        both are folded into the weights (same trick as dense Granite)."""
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+        rm, ls = float(getattr(config, "residual_multiplier", 1.0)), float(getattr(config, "logits_scaling", 1.0))
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".self_attn.o_proj.weight"):
+                v = (v.float() * rm).to(v.dtype)
+            elif k.endswith(".block_sparse_moe.output_linear.weight"):
+                k, v = k.replace(".block_sparse_moe.output_linear.weight", ".mlp.expert_mlps.down_proj"), (v.float() * rm).to(v.dtype)
+            elif k.endswith(".block_sparse_moe.input_linear.weight"):
+                k = k.replace(".block_sparse_moe.input_linear.weight", ".mlp.expert_mlps.gate_up_proj")
+            elif k.endswith(".block_sparse_moe.router.layer.weight"):
+                k, v = k.replace(".block_sparse_moe.router.layer.weight", ".mlp.router.linear_router.weight"), v.float()
+            out[k] = v
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        out["lm_head.weight"] = (out["lm_head.weight"].float() / ls).to(out["lm_head.weight"].dtype)
+        return out
+
+    @staticmethod
+    def update_state_dict_for_tied_weights(sd):
+        pass
+
+
+# ---- Phi-3.5-MoE ------------------------------------------------------------------------------------------------------------------
+class SparseMixerRouter(nn.Module):
+    """Inference form of SparseMixer (arXiv 2409.12136): pick the arg-max expert, weight it by a softmax over the logits that lie
+    within a relative ``2 * jitter`` band of the maximum; remove it and repeat once for the second expert."""
+
+    def __init__(self, num_experts, hidden_size, jitter_eps, device=None):
+        super().__init__()
+        self.num_experts, self.top_k, self.jitter_eps = num_experts, 2, float(jitter_eps)
+        self.linear_router = nn.Linear(hidden_size, num_experts, bias=False, dtype=torch.float32, device=device)
+        self.linear_router.weight.requires_grad_(False)
+
+    def _pick(self, scores, pool):
+        top, idx = pool.max(-1, keepdim=True)
+        factor = scores.abs().clamp(min=top)
+        gates = torch.softmax(pool.masked_fill(((top - scores) / factor) > 2 * self.jitter_eps, float("-inf")), -1)
+        return gates.gather(-1, idx), idx
+
+    def forward(self, x):
+        scores = nn.functional.linear(x.float(), self.linear_router.weight)
+        w1, i1 = self._pick(scores, scores)
+        w2, i2 = self._pick(scores, scores.scatter(-1, i1, float("-inf")))
+        return scores, torch.cat([w1, w2], -1), torch.cat([i1, i2], -1)
+
+
+def _phimoe_block(config, device):
+    moe = initialize_moe_module(config, device=device, normalize=False)
+    moe.router = SparseMixerRouter(config.num_local_experts, config.hidden_size, getattr(config, "router_jitter_noise", 0.01), device)
+    return moe
+
+
+class _PhimoeConfig(_MoeConfig):
+    pass
+
+
+class NeuronPhimoeModel(NeuronClassicModel):
+    def init_model(self, config):
+        self.lm_head_bias = bool(getattr(config, "lm_head_bias", False))
+        super().init_model(config)
+
+    def layer_spec(self, config, i):
+        b = bool(getattr(config, "attention_bias", False))
+        return dict(parallel=False, norm_bias=True, mlp=_phimoe_block, act=config.hidden_act, qkv_bias=b, o_bias=b, mlp_bias=False,
+                    sliding_window=getattr(config, "sliding_window", None))
+
+
+class NeuronPhimoeForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronPhimoeModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return _PhimoeConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+        return convert_moe_experts(sd, config.num_hidden_layers, config.num_local_experts, moe_prefixes=("mlp", "block_sparse_moe"),
+                                   gate_names=("router", "gate"), w_names=("w1", "w3", "w2"))
+
+
+MOE_MODEL_TYPES = {"granitemoe": NeuronGraniteMoeForCausalLM, "phimoe": NeuronPhimoeForCausalLM,
+                   "qwen2_moe": NeuronQwen2MoeForCausalLM, "olmoe": NeuronOlmoeForCausalLM, "exaone4": NeuronExaone4ForCausalLM}

@@ -47,7 +47,8 @@ MODEL_TYPES.update({
 _M = "neuronx_distributed_inference_b200.contrib.models.moe_family"
 MODEL_TYPES.update({
     "qwen2_moe": {"causal-lm": f"{_M}:NeuronQwen2MoeForCausalLM"}, "olmoe": {"causal-lm": f"{_M}:NeuronOlmoeForCausalLM"},
-    "exaone4": {"causal-lm": f"{_M}:NeuronExaone4ForCausalLM"},
+    "exaone4": {"causal-lm": f"{_M}:NeuronExaone4ForCausalLM"}, "granitemoe": {"causal-lm": f"{_M}:NeuronGraniteMoeForCausalLM"},
+    "phimoe": {"causal-lm": f"{_M}:NeuronPhimoeForCausalLM"},
     "llava": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.llava:NeuronLlavaForCausalLM"},
     "qwen2_5_vl": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.qwen2_5_vl:NeuronQwen25VLForCausalLM"},
 })

@@ -96,13 +96,18 @@ def _cfg(name):
         return T.XGLMConfig(d_model=64, ffn_dim=128, num_layers=3, attention_heads=4, vocab_size=160, max_position_embeddings=256)
     if name == "codegen":
         return T.CodeGenConfig(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256, rotary_dim=8)
+    if name == "granitemoe":
+        return T.GraniteMoeConfig(**BASE, num_local_experts=4, num_experts_per_tok=2, embedding_multiplier=3.0, attention_multiplier=0.2,
+                                  residual_multiplier=0.5, logits_scaling=4.0, tie_word_embeddings=False)
+    if name == "phimoe":
+        return T.PhimoeConfig(**BASE, num_local_experts=4, num_experts_per_tok=2, attention_bias=True, lm_head_bias=True, sliding_window=None)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
