@@ -6,6 +6,9 @@
   sliding / global layers with rotary only on the sliding ones.
 * **GraniteMoE** — Granite multipliers around a top-k MoE whose experts ship as fused ``input_linear`` / ``output_linear``.
 * **Phi-3.5-MoE** — LayerNorm block, biased attention / head, SparseMixer top-2 routing (jitter-thresholded softmax per pick).
+* **GLM-4.5 (``glm4_moe``) / dots.llm1 (``dots1``)** — GQA attention (partial rotary / per-head q,k RMSNorm) in front of the
+  DeepSeek-V3 MoE block (sigmoid scores, selection-only correction bias, group-limited top-k, shared experts, dense first layers).
+* **ERNIE-4.5-MoE** — interleaved rotary, softmax router whose correction bias steers selection only, shared experts, MoE layer window.
 reference ports: contrib/models/{EXAONE-4.0-1.2B, Phi-3.5-MoE-instruct}/src and the MoE glue of modules/moe_v2.py."""
 from __future__ import annotations
 
@@ -13,7 +16,8 @@ import torch
 import torch.nn as nn
 
 from ...config import MoENeuronConfig
-from ...models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaForCausalLM, NeuronLlamaMLP, NeuronLlamaModel
+from ...models.llama.modeling_llama import (LlamaInferenceConfig, NeuronLlamaAttention, NeuronLlamaForCausalLM, NeuronLlamaMLP,
+                                            NeuronLlamaModel)
 from ...models.model_base import DecoderLayer
 from ...models.qwen2.modeling_qwen2 import NeuronQwen2Attention
 from ...models.state_dict_utils import convert_moe_experts, fuse_qkv_and_gate_up
@@ -264,5 +268,145 @@ class NeuronPhimoeForCausalLM(_ClassicCausalLM):
                                    gate_names=("router", "gate"), w_names=("w1", "w3", "w2"))
 
 
-MOE_MODEL_TYPES = {"granitemoe": NeuronGraniteMoeForCausalLM, "phimoe": NeuronPhimoeForCausalLM,
+# ---- GLM-4.5-MoE / dots.llm1: GQA attention + DeepSeek-V3 MoE ----------------------------------------------------------------------
+def _deepseek_moe(config, device):
+    from ...models.deepseek.modeling_deepseek import DeepseekRouter
+    from ...modules.moe import ExpertMLPs, MoE, SharedExperts
+    dt = config.neuron_config.torch_dtype
+    experts = ExpertMLPs(config.n_routed_experts, config.hidden_size, config.moe_intermediate_size, config.hidden_act, dt, device=device)
+    n_sh = getattr(config, "n_shared_experts", 0) or 0
+    shared = SharedExperts(config.hidden_size, config.moe_intermediate_size * n_sh, config.hidden_act, dt, device) if n_sh else None
+    return MoE(DeepseekRouter(config, device), experts, shared)
+
+
+class _Glm4MoeAttention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        if getattr(config, "use_qk_norm", False):
+            over = dict(over, qk_norm="rms_pre_rope", qk_norm_eps=config.rms_norm_eps)
+        super().__init__(config, layer_idx, rotary_emb, device=device, qkv_bias=bool(getattr(config, "attention_bias", False)),
+                         o_bias=False, **over)
+
+
+class _Dots1Attention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        lt = getattr(config, "layer_types", None)
+        sw = getattr(config, "sliding_window", None) if (lt and lt[layer_idx] == "sliding_attention") else None
+        super().__init__(config, layer_idx, rotary_emb, device=device, qk_norm="rms_pre_rope", qk_norm_eps=config.rms_norm_eps,
+                         sliding_window=sw, **over)
+
+
+class NeuronGlm4MoeModel(NeuronLlamaModel):
+    attention_cls = _Glm4MoeAttention
+    graph_safe = False
+
+    def make_rotary(self, config, device):
+        from ...models.llama.modeling_llama import rope_scaling_of, rope_theta_of
+        from ...modules.rope import RotaryEmbedding
+        rp = getattr(config, "rope_parameters", None) or {}
+        frac = getattr(config, "partial_rotary_factor", None) or (rp.get("partial_rotary_factor") if isinstance(rp, dict) else None) or 1.0
+        return RotaryEmbedding(int(config.head_dim * float(frac)), max(config.max_position_embeddings, config.neuron_config.seq_len),
+                               rope_theta_of(config), rope_scaling_of(config), device=device)
+
+    def make_layer(self, config, i, rotary, device):
+        dt = config.neuron_config.torch_dtype
+        moe = i >= getattr(config, "first_k_dense_replace", 0)
+        mlp = _deepseek_moe(config, device) if moe else NeuronLlamaMLP(config, device=device)
+        return DecoderLayer(self.attention_cls(config, i, rotary, device=device), mlp,
+                            RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device),
+                            RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device), i, mlp_is_moe=moe)
+
+
+class NeuronGlm4MoeForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronGlm4MoeModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return _MoeConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        from ...models.deepseek.modeling_deepseek import NeuronDeepseekForCausalLM
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+        sd = NeuronDeepseekForCausalLM.convert_hf_to_neuron_state_dict(sd, config)
+        return {k.replace("self_attn.q_norm.", "self_attn.q_layernorm.").replace("self_attn.k_norm.", "self_attn.k_layernorm."): v
+                for k, v in sd.items()}
+
+
+class NeuronDots1Model(NeuronGlm4MoeModel):
+    attention_cls = _Dots1Attention
+
+
+class NeuronDots1ForCausalLM(NeuronGlm4MoeForCausalLM):
+    _model_cls = NeuronDots1Model
+
+
+# ---- ERNIE-4.5-MoE ----------------------------------------------------------------------------------------------------------------
+class ErnieMoeRouter(nn.Module):
+    """softmax(logits); the correction bias is added for the top-k SELECTION only; selected probabilities are renormalised."""
+
+    def __init__(self, num_experts, top_k, hidden_size, norm_min=1e-12, device=None):
+        super().__init__()
+        self.num_experts, self.top_k, self.norm_min = num_experts, top_k, float(norm_min)
+        self.linear_router = nn.Linear(hidden_size, num_experts, bias=False, dtype=torch.float32, device=device)
+        self.linear_router.weight.requires_grad_(False)
+        self.register_buffer("e_score_correction_bias", torch.zeros(num_experts, dtype=torch.float32, device=device))
+
+    def forward(self, x):
+        logits = nn.functional.linear(x.float(), self.linear_router.weight)
+        p = torch.softmax(logits, -1)
+        idx = (p + self.e_score_correction_bias).topk(self.top_k, -1)[1]
+        w = p.gather(-1, idx)
+        return logits, w / w.sum(-1, keepdim=True).clamp(min=self.norm_min), idx
+
+
+def _ernie_is_moe(config, i):
+    return ((i + 1) % getattr(config, "moe_layer_interval", 1) == 0 and i >= getattr(config, "moe_layer_start_index", 0)
+            and i <= getattr(config, "moe_layer_end_index", config.num_hidden_layers - 1))
+
+
+class NeuronErnie4_5MoeModel(NeuronLlamaModel):
+    graph_safe = False
+
+    def make_layer(self, config, i, rotary, device):
+        from ...modules.moe import ExpertMLPs, MoE, SharedExperts
+        dt = config.neuron_config.torch_dtype
+        b = bool(getattr(config, "use_bias", False))
+        attn = NeuronLlamaAttention(config, i, rotary, device=device, rope_interleaved=True, qkv_bias=b, o_bias=b)
+        moe = _ernie_is_moe(config, i)
+        if moe:
+            experts = ExpertMLPs(config.moe_num_experts, config.hidden_size, config.moe_intermediate_size, config.hidden_act, dt, device=device)
+            n_sh = getattr(config, "moe_num_shared_experts", 0) or 0
+            shared = SharedExperts(config.hidden_size, config.moe_intermediate_size * n_sh, config.hidden_act, dt, device) if n_sh else None
+            mlp = MoE(ErnieMoeRouter(config.moe_num_experts, config.moe_k, config.hidden_size, getattr(config, "moe_norm_min", 1e-12), device),
+                      experts, shared)
+        else:
+            mlp = NeuronLlamaMLP(config, device=device)
+        return DecoderLayer(attn, mlp, RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device),
+                            RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device), i, mlp_is_moe=moe)
+
+
+class NeuronErnie4_5MoeForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronErnie4_5MoeModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return _MoeConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=True)
+        for i in range(config.num_hidden_layers):
+            m = f"layers.{i}.mlp."
+            b = sd.pop(m + "gate.moe_statics.e_score_correction_bias", None)
+            if b is not None:
+                sd[m + "router.e_score_correction_bias"] = b.float().reshape(-1)
+            g, u = m + "shared_experts.gate_proj.weight", m + "shared_experts.up_proj.weight"
+            if g in sd:
+                sd[m + "shared_experts.gate_up_proj.weight"] = torch.cat([sd.pop(g), sd.pop(u)], 0)
+        return convert_moe_experts(sd, config.num_hidden_layers, config.moe_num_experts, moe_prefixes=("mlp",), gate_names=("gate",),
+                                   w_names=("gate_proj", "up_proj", "down_proj"))
+
+
+MOE_MODEL_TYPES = {"glm4_moe": NeuronGlm4MoeForCausalLM, "dots1": NeuronDots1ForCausalLM, "ernie4_5_moe": NeuronErnie4_5MoeForCausalLM,
+                   "granitemoe": NeuronGraniteMoeForCausalLM, "phimoe": NeuronPhimoeForCausalLM,
                    "qwen2_moe": NeuronQwen2MoeForCausalLM, "olmoe": NeuronOlmoeForCausalLM, "exaone4": NeuronExaone4ForCausalLM}

@@ -101,13 +101,22 @@ def _cfg(name):
                                   residual_multiplier=0.5, logits_scaling=4.0, tie_word_embeddings=False)
     if name == "phimoe":
         return T.PhimoeConfig(**BASE, num_local_experts=4, num_experts_per_tok=2, attention_bias=True, lm_head_bias=True, sliding_window=None)
+    if name == "glm4_moe":
+        return T.Glm4MoeConfig(**BASE, head_dim=16, moe_intermediate_size=32, n_routed_experts=8, n_shared_experts=1, num_experts_per_tok=2,
+                               first_k_dense_replace=1, n_group=2, topk_group=1, use_qk_norm=True, attention_bias=True, pad_token_id=0)
+    if name == "dots1":
+        return T.Dots1Config(**BASE, moe_intermediate_size=32, n_routed_experts=8, n_shared_experts=2, num_experts_per_tok=2,
+                             first_k_dense_replace=1, n_group=2, topk_group=1, routed_scaling_factor=1.5)
+    if name == "ernie4_5_moe":
+        return T.Ernie4_5_MoeConfig(**BASE, moe_intermediate_size=32, moe_num_experts=4, moe_k=2, moe_num_shared_experts=1,
+                                    moe_layer_start_index=1, tie_word_embeddings=False)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
