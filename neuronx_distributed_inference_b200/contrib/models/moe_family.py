@@ -8,6 +8,8 @@
 * **Phi-3.5-MoE** — LayerNorm block, biased attention / head, SparseMixer top-2 routing (jitter-thresholded softmax per pick).
 * **GLM-4.5 (``glm4_moe``) / dots.llm1 (``dots1``)** — GQA attention (partial rotary / per-head q,k RMSNorm) in front of the
   DeepSeek-V3 MoE block (sigmoid scores, selection-only correction bias, group-limited top-k, shared experts, dense first layers).
+* **DeepSeek-V2 / V2-Lite** — the MLA attention of the DeepSeek-V3 model with the V2 router (softmax scores, greedy or
+  group-limited-greedy selection by group maximum, no renormalisation).
 * **ERNIE-4.5-MoE** — interleaved rotary, softmax router whose correction bias steers selection only, shared experts, MoE layer window.
 reference ports: contrib/models/{EXAONE-4.0-1.2B, Phi-3.5-MoE-instruct}/src and the MoE glue of modules/moe_v2.py."""
 from __future__ import annotations
@@ -16,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from ...config import MoENeuronConfig
+from ...models.deepseek.modeling_deepseek import NeuronDeepseekForCausalLM, NeuronDeepseekModel
 from ...models.llama.modeling_llama import (LlamaInferenceConfig, NeuronLlamaAttention, NeuronLlamaForCausalLM, NeuronLlamaMLP,
                                             NeuronLlamaModel)
 from ...models.model_base import DecoderLayer
@@ -340,6 +343,41 @@ class NeuronDots1ForCausalLM(NeuronGlm4MoeForCausalLM):
     _model_cls = NeuronDots1Model
 
 
+# ---- DeepSeek-V2 ------------------------------------------------------------------------------------------------------------------
+class DeepseekV2Router(nn.Module):
+    def __init__(self, config, device=None):
+        super().__init__()
+        self.E, self.top_k = config.n_routed_experts, config.num_experts_per_tok
+        self.method = getattr(config, "topk_method", "greedy")
+        self.n_group, self.topk_group = getattr(config, "n_group", 1) or 1, getattr(config, "topk_group", 1) or 1
+        self.norm = bool(getattr(config, "norm_topk_prob", False))
+        self.scaling = float(getattr(config, "routed_scaling_factor", 1.0))
+        self.linear_router = nn.Linear(config.hidden_size, self.E, bias=False, dtype=torch.float32, device=device)
+        self.linear_router.weight.requires_grad_(False)
+
+    def forward(self, x):
+        logits = nn.functional.linear(x.float(), self.linear_router.weight)
+        p = torch.softmax(logits, -1)
+        pool = p
+        if self.method == "group_limited_greedy":
+            N = p.shape[0]
+            gmax = p.view(N, self.n_group, -1).max(-1).values
+            keep = torch.zeros_like(gmax).scatter_(1, gmax.topk(self.topk_group, -1)[1], 1.0).bool()
+            pool = p.masked_fill(~keep.unsqueeze(-1).expand(N, self.n_group, self.E // self.n_group).reshape(N, self.E), 0.0)
+        w, idx = pool.topk(self.top_k, -1)
+        if self.norm:
+            w = w / (w.sum(-1, keepdim=True) + 1e-20)
+        return logits, w * self.scaling, idx
+
+
+class NeuronDeepseekV2Model(NeuronDeepseekModel):
+    router_cls = DeepseekV2Router
+
+
+class NeuronDeepseekV2ForCausalLM(NeuronDeepseekForCausalLM):
+    _model_cls = NeuronDeepseekV2Model
+
+
 # ---- ERNIE-4.5-MoE ----------------------------------------------------------------------------------------------------------------
 class ErnieMoeRouter(nn.Module):
     """softmax(logits); the correction bias is added for the top-k SELECTION only; selected probabilities are renormalised."""
@@ -407,6 +445,6 @@ class NeuronErnie4_5MoeForCausalLM(NeuronLlamaForCausalLM):
                                    w_names=("gate_proj", "up_proj", "down_proj"))
 
 
-MOE_MODEL_TYPES = {"glm4_moe": NeuronGlm4MoeForCausalLM, "dots1": NeuronDots1ForCausalLM, "ernie4_5_moe": NeuronErnie4_5MoeForCausalLM,
+MOE_MODEL_TYPES = {"deepseek_v2": NeuronDeepseekV2ForCausalLM, "glm4_moe": NeuronGlm4MoeForCausalLM, "dots1": NeuronDots1ForCausalLM, "ernie4_5_moe": NeuronErnie4_5MoeForCausalLM,
                    "granitemoe": NeuronGraniteMoeForCausalLM, "phimoe": NeuronPhimoeForCausalLM,
                    "qwen2_moe": NeuronQwen2MoeForCausalLM, "olmoe": NeuronOlmoeForCausalLM, "exaone4": NeuronExaone4ForCausalLM}

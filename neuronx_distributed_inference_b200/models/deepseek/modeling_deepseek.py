@@ -156,6 +156,7 @@ class DeepseekRouter(nn.Module):
 
 class NeuronDeepseekModel(NeuronBaseModel):
     graph_safe = False
+    router_cls = DeepseekRouter
 
     def setup_attr_for_model(self, config):
         nc = config.neuron_config
@@ -196,7 +197,7 @@ class NeuronDeepseekModel(NeuronBaseModel):
                                      device=dev)
                 shared = SharedExperts(config.hidden_size, config.moe_intermediate_size * (getattr(config, "n_shared_experts", 1) or 1),
                                        config.hidden_act, dt, dev) if getattr(config, "n_shared_experts", 0) else None
-                mlp = MoE(DeepseekRouter(config, dev), experts, shared)
+                mlp = MoE(self.router_cls(config, dev), experts, shared)
             else:
                 mlp = GatedMLP(config.hidden_size, config.intermediate_size, config.hidden_act, dt, device=dev)
             layers.append(DecoderLayer(attn, mlp, RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=dev),

@@ -49,6 +49,7 @@ MODEL_TYPES.update({
     "qwen2_moe": {"causal-lm": f"{_M}:NeuronQwen2MoeForCausalLM"}, "olmoe": {"causal-lm": f"{_M}:NeuronOlmoeForCausalLM"},
     "exaone4": {"causal-lm": f"{_M}:NeuronExaone4ForCausalLM"}, "granitemoe": {"causal-lm": f"{_M}:NeuronGraniteMoeForCausalLM"},
     "phimoe": {"causal-lm": f"{_M}:NeuronPhimoeForCausalLM"}, "glm4_moe": {"causal-lm": f"{_M}:NeuronGlm4MoeForCausalLM"},
+    "deepseek_v2": {"causal-lm": f"{_M}:NeuronDeepseekV2ForCausalLM"},
     "dots1": {"causal-lm": f"{_M}:NeuronDots1ForCausalLM"}, "ernie4_5_moe": {"causal-lm": f"{_M}:NeuronErnie4_5MoeForCausalLM"},
     "llava": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.llava:NeuronLlavaForCausalLM"},
     "qwen2_5_vl": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.qwen2_5_vl:NeuronQwen25VLForCausalLM"},

@@ -110,13 +110,19 @@ def _cfg(name):
     if name == "ernie4_5_moe":
         return T.Ernie4_5_MoeConfig(**BASE, moe_intermediate_size=32, moe_num_experts=4, moe_k=2, moe_num_shared_experts=1,
                                     moe_layer_start_index=1, tie_word_embeddings=False)
+    if name == "deepseek_v2":
+        return T.DeepseekV2Config(hidden_size=64, intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4,
+                                  num_key_value_heads=4, vocab_size=160, max_position_embeddings=256, n_routed_experts=8, n_shared_experts=1,
+                                  num_experts_per_tok=2, first_k_dense_replace=1, n_group=2, topk_group=1, topk_method="greedy",
+                                  kv_lora_rank=16, q_lora_rank=None, qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16, head_dim=8,
+                                  routed_scaling_factor=2.0, rms_norm_eps=1e-6)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
@@ -138,3 +144,24 @@ def test_contrib_family_matches_hf(name, tmp_path):
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"
+
+
+def test_deepseek_v2_group_limited_router():
+    """transformers 5.5's group_limited_greedy branch is broken (reads a missing attribute), so the routing rule is checked directly:
+    experts outside the ``topk_group`` best groups (ranked by their maximum probability) can never be selected."""
+    from types import SimpleNamespace
+    from neuronx_distributed_inference_b200.contrib.models.moe_family import DeepseekV2Router
+    cfg = SimpleNamespace(n_routed_experts=8, num_experts_per_tok=3, topk_method="group_limited_greedy", n_group=4, topk_group=2,
+                          routed_scaling_factor=2.0, hidden_size=16)
+    r = DeepseekV2Router(cfg)
+    torch.manual_seed(0)
+    r.linear_router.weight.copy_(torch.randn(8, 16))
+    x = torch.randn(32, 16)
+    logits, w, idx = r(x)
+    p = torch.softmax(logits, -1)
+    best_groups = p.view(32, 4, 2).max(-1).values.topk(2, -1)[1]
+    for n in range(32):
+        allowed = {int(g) * 2 + j for g in best_groups[n] for j in range(2)}
+        assert set(idx[n].tolist()) <= allowed
+        exp = torch.tensor([p[n, e] if e in allowed else 0.0 for e in range(8)]).topk(3)[0] * 2.0
+        assert torch.allclose(w[n].sort(descending=True)[0], exp, atol=1e-6)
