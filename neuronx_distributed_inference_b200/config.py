@@ -286,6 +286,9 @@ class NeuronConfig:
         self.windowed_context_encoding_size = g("windowed_context_encoding_size", None)
         self.chunked_prefill_config = _nest("chunked_prefill_config", g("chunked_prefill_config", None))
         self.is_chunked_prefill = self.chunked_prefill_config is not None
+        # sliding-window layers keep only `sliding_window` KV slots per line, written modulo the window
+        # (reference sizes SWA caches by the window: kv_cache_manager.py:194-236, gpt_oss_kv_cache_manager.py:30-396)
+        self.rolling_sliding_window_cache = g("rolling_sliding_window_cache", False)
         self.k_cache_transposed = g("k_cache_transposed", False)
         self.flash_decoding_enabled = g("flash_decoding_enabled", False)
         self.attn_kernel_enabled = g("attn_kernel_enabled", None)
@@ -352,6 +355,15 @@ class NeuronConfig:
             # decode attention is data parallel: each DP group keeps batch/dp cache lines
             # (reference config.py:513-520)
             self.kv_cache_batch_size = self.tkg_batch_size // self.attention_dp_degree
+        if self.rolling_sliding_window_cache:
+            bad = [n for n, v in (("is_block_kv_layout", self.is_block_kv_layout), ("is_prefix_caching", self.is_prefix_caching),
+                                  ("chunked_prefill_config", self.is_chunked_prefill), ("flash_decoding_enabled", self.flash_decoding_enabled),
+                                  ("windowed_context_encoding_size", self.windowed_context_encoding_size),
+                                  ("speculation_length", self.speculation_length), ("is_medusa", self.is_medusa),
+                                  ("attention_dp_degree", self.attention_dp_degree > 1)) if v]
+            if bad:
+                raise ValueError(f"rolling_sliding_window_cache cannot be combined with {bad}: these read a positional prefix back "
+                                 "from the cache or write several tokens per step")
         if self.is_prefix_caching:
             self.is_block_kv_layout = True
         if self.enable_fused_speculation and self.speculation_length == 0:

@@ -142,26 +142,11 @@ class MllamaCrossAttentionLayer(nn.Module):
         self.mlp = NeuronLlamaMLP(config, device=device)
         self.cross_attn_attn_gate = nn.Parameter(torch.zeros(1, dtype=dt, device=device), requires_grad=False)
         self.cross_attn_mlp_gate = nn.Parameter(torch.zeros(1, dtype=dt, device=device), requires_grad=False)
-        self.num_lines = nc.kv_cache_batch_size + nc.kv_cache_padding_size + 1
-        self.k_cross = self.v_cross = self.row_mask = None
-        self.has_vision = False
-
-    def reset(self):
-        self.has_vision = False
-
-    def _store(self, lines, k, v, last_mask):
-        B, Hkv, Nv, D = k.shape
-        if self.k_cross is None or self.k_cross.shape[2] != Nv:
-            self.k_cross = k.new_zeros(self.num_lines, Hkv, Nv, D)
-            self.v_cross = v.new_zeros(self.num_lines, Hkv, Nv, D)
-            self.row_mask = torch.zeros(self.num_lines, Nv, dtype=torch.bool, device=k.device)
-        li = lines.long().clamp(0, self.num_lines - 1)
-        self.k_cross[li], self.v_cross[li], self.row_mask[li] = k, v, last_mask
-        self.has_vision = True
 
     def forward(self, h, meta, kv_mgr, lora=None):
+        """``kv_mgr``: a MultimodalKVCacheManager — holds this layer's vision K/V per cache line."""
         states = meta.extras.get("cross_attention_states")
-        if states is None and not self.has_vision:
+        if states is None and not kv_mgr.has_vision(self.layer_idx):
             return h                                                             # text-only request: layer is skipped
         B, T, _ = h.shape
         D, nq, nkv = self.head_dim, self.n_q, self.n_kv
@@ -180,11 +165,10 @@ class MllamaCrossAttentionLayer(nn.Module):
                 cm = torch.cat([cm, cm.new_zeros(B, T - cm.shape[1], Nv)], 1)
             last = (meta.key_valid.long().sum(-1).clamp_min(1) - 1) if meta.key_valid is not None else \
                 torch.full((B,), T - 1, device=h.device)
-            self._store(lines, k, v, cm[torch.arange(B, device=h.device), last])
+            kv_mgr.update_vision(self.layer_idx, lines, k, v, cm[torch.arange(B, device=h.device), last])
         else:
-            li = lines.long().clamp(0, self.num_lines - 1)
-            k, v = self.k_cross[li], self.v_cross[li]
-            cm = self.row_mask[li].unsqueeze(1).expand(B, T, -1)
+            k, v, rm = kv_mgr.get_vision(self.layer_idx, lines)
+            cm = rm.unsqueeze(1).expand(B, T, -1)
         row_on = cm.any(-1, keepdim=True)                                        # rows that see at least one vision token
         mask = (cm | ~row_on).unsqueeze(1)                                       # fully masked rows attend uniformly (HF)
         o = ops.ref.attention_with_mask(q.transpose(1, 2), k, v, mask, 1.0 / math.sqrt(D))
@@ -216,11 +200,22 @@ class NeuronMllamaTextModel(NeuronLlamaModel):
     def kv_head_dim(self):
         return next(l.self_attn.head_dim for l in self.layers if hasattr(l, "self_attn"))
 
+    def init_inference_optimization(self, config):
+        super().init_inference_optimization(config)
+        nc = self.neuron_config
+        if nc.is_block_kv_layout or nc.attention_dp_degree > 1:
+            raise NotImplementedError("Mllama: contiguous KV layout only (vision K/V are stored per cache line)")
+        from ...modules.kvcache.multimodal_kv_cache_manager import MultimodalKVCacheManager
+        base = self.kv_mgr
+        self.kv_mgr = MultimodalKVCacheManager(base.num_layers, base.num_kv_heads, base.head_dim, base.max_len, base.num_lines,
+                                               nc.attention_dtype or nc.torch_dtype, self.device_,
+                                               quant_config=nc.kv_quant_config if nc.kv_cache_quant else None,
+                                               cross_attention_layers=[i for i, l in enumerate(self.layers)
+                                                                       if isinstance(l, MllamaCrossAttentionLayer)])
+
     def reset(self):
         super().reset()
-        for l in self.layers:
-            if isinstance(l, MllamaCrossAttentionLayer):
-                l.reset()
+        self.kv_mgr.reset_vision()
 
 
 class NeuronMllamaForCausalLM(NeuronBaseForImageToText):

@@ -161,8 +161,16 @@ class NeuronBaseModel(nn.Module):
                     raise NotImplementedError(f"attention_dp_degree ({nc.attention_dp_degree}) must equal the KV replication "
                                               f"factor tp/num_kv_heads ({g.size}) — see DESIGN.md §5")
                 self.kv_mgr = DataParallelKVCacheManager(dp_rank=g.rank, dp_size=g.size, **kw)
+            elif nc.rolling_sliding_window_cache and any(self._layer_windows()):
+                from ..modules.kvcache.gpt_oss_kv_cache_manager import HybridKVCacheManager
+                kw.pop("num_layers")
+                self.kv_mgr = HybridKVCacheManager(self._layer_windows(), **kw)
             else:
                 self.kv_mgr = KVCacheManager(**kw)
+
+    def _layer_windows(self):
+        """Per-layer sliding window (None for full-attention layers)."""
+        return [getattr(getattr(layer, "self_attn", None), "sliding_window", None) for layer in self.layers]
 
     def _kv_len(self, config) -> int:
         nc = self.neuron_config

@@ -168,6 +168,16 @@ class AttentionBase(nn.Module):
         if meta.lines is None:
             meta.lines = meta.seq_ids if paged else kv_mgr.lines_for(meta.seq_ids)
         lines = meta.lines
+        # rolling (window-sized) caches: slots are positions modulo the window, the horizon saturates at W-1 and every
+        # resident slot is inside the window (modules/kvcache/gpt_oss_kv_cache_manager.py)
+        wpos, hpos, window, hint = meta.write_positions, meta.position_ids, self.sliding_window, meta.seq_hint
+        roll = kv_mgr.rolling_window(self.layer_idx) if hasattr(kv_mgr, "rolling_window") else None
+        if roll:
+            if paged or meta.has_prefix or meta.active_mask is not None:
+                raise NotImplementedError("rolling sliding-window cache with paged KV / cached prefixes / token trees")
+            wpos, hpos = kv_mgr.rolling_positions(roll, meta.write_positions, meta.position_ids, meta.is_prefill)
+            if not meta.is_prefill:
+                window, hint = None, min(hint, roll) if hint else hint
         fused = (self._simple() and not paged and qkv.is_cuda and k_cache.dtype == qkv.dtype
                  and qkv.dtype in (torch.bfloat16, torch.float16)
                  and (not meta.is_prefill or not meta.has_prefix))
@@ -178,22 +188,22 @@ class AttentionBase(nn.Module):
             if meta.is_prefill:
                 # prefill attention consumes the fresh k/v directly (no cache read): split here
                 q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
-                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)
+                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, wpos, lines)
             elif (meta.active_mask is None and self.attention_chunk_size is None and not self.softcap
                   and getattr(kv_mgr, "k_scale", None) is None and meta.capture is None):
-                o = ops.rope_attention_decode(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, meta.position_ids,
-                                              nq, nkv, D, self.scale, self.sliding_window, self.sinks, qn, kn,
-                                              self.qk_norm_eps, seq_hint=meta.seq_hint)
+                o = ops.rope_attention_decode(qkv, cos, sin, k_cache, v_cache, lines, wpos, hpos,
+                                              nq, nkv, D, self.scale, window, self.sinks, qn, kn,
+                                              self.qk_norm_eps, seq_hint=hint)
                 return self._finish(o.reshape(B, T, nq * D), residual, lora, meta)
             else:
-                q = ops.rope_kv_append(qkv, cos, sin, k_cache, v_cache, lines, meta.write_positions, nq, nkv, D,
+                q = ops.rope_kv_append(qkv, cos, sin, k_cache, v_cache, lines, wpos, nq, nkv, D,
                                        False, qn, kn, self.qk_norm_eps)
         else:
             q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
             if paged:
                 kv_mgr.update(self.layer_idx, k, v, meta.slot_mapping)
             else:
-                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)
+                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, wpos, lines)
         if meta.capture is not None:
             meta.capture[f"layers.{self.layer_idx}.self_attn.q"] = q
 
@@ -212,10 +222,10 @@ class AttentionBase(nn.Module):
             ks = getattr(kv_mgr, "k_scale", None)
             vs = getattr(kv_mgr, "v_scale", None)
             # token trees: visibility is defined on cache slots (node index), rotary positions are depths
-            vis_pos = meta.write_positions if meta.active_mask is not None else meta.position_ids
-            o = ops.attention_decode(q, k_cache, v_cache, lines, vis_pos, self.scale, self.sliding_window,
+            vis_pos = meta.write_positions if meta.active_mask is not None else hpos
+            o = ops.attention_decode(q, k_cache, v_cache, lines, vis_pos, self.scale, window,
                                      self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs,
-                                     seq_hint=meta.seq_hint, active_base=meta.active_base)
+                                     seq_hint=hint, active_base=meta.active_base)
         return self._finish(o.reshape(B, T, nq * D), residual, lora, meta)
 
     def _finish(self, o, residual, lora, meta):

@@ -93,3 +93,29 @@ def run_family(model_type, tmp_path, tol=2e-4, **nc_kw):
 @pytest.mark.parametrize("model_type", FAMILIES)
 def test_family_matches_hf(model_type, tmp_path):
     run_family(model_type, tmp_path)
+
+
+@pytest.mark.parametrize("model_type", ["mistral", "gemma3", "gpt_oss"])
+def test_rolling_sliding_window_cache(model_type, tmp_path, monkeypatch):
+    """Sliding layers keep only ``window`` (8) KV slots written modulo the window; the 14-token prompts and 12 decode steps wrap
+    the window three times.  Logits must still match Hugging Face (reference gpt_oss_kv_cache_manager.py:30-396)."""
+    from neuronx_distributed_inference_b200.modules.kvcache.gpt_oss_kv_cache_manager import HybridKVCacheManager
+    seen = []
+    orig = HybridKVCacheManager.__init__
+
+    def spy(self, *a, **kw):
+        orig(self, *a, **kw)
+        seen.append(self)
+    monkeypatch.setattr(HybridKVCacheManager, "__init__", spy)
+    run_family(model_type, tmp_path, rolling_sliding_window_cache=True)
+    assert seen, "the hybrid manager was not selected"
+    for m in seen:
+        assert m.window == 8 and m.windowed.max_len == 8
+        k, _ = m.get_kv_by_layer_id(0)                      # layer 0 slides in all three configs
+        assert k.shape[2] == 8
+
+
+def test_rolling_cache_rejects_prefix_features():
+    from neuronx_distributed_inference_b200.config import NeuronConfig
+    with pytest.raises(ValueError):
+        NeuronConfig(batch_size=1, seq_len=64, rolling_sliding_window_cache=True, speculation_length=4)

@@ -239,3 +239,48 @@ def test_input_truncation_and_bucket_overflow_errors():
         app(torch.randint(1, 64, (1, 12)), attention_mask=torch.ones(1, 12, dtype=torch.long))
     out = app(torch.randint(1, 64, (1, 5)), attention_mask=torch.ones(1, 5, dtype=torch.long))
     assert out.tokens.shape == (1,)
+
+
+def test_hybrid_kv_cache_manager_rolling_slots():
+    """Sliding layers live in a window-sized allocation written modulo the window (reference gpt_oss_kv_cache_manager.py:30-396)."""
+    from neuronx_distributed_inference_b200.modules.kvcache.gpt_oss_kv_cache_manager import GptOssKVCacheManager, HybridKVCacheManager
+    assert GptOssKVCacheManager is HybridKVCacheManager
+    m = HybridKVCacheManager([4, None, 4], num_kv_heads=2, head_dim=8, max_len=32, num_lines=2, dtype=torch.float32)
+    assert m.rolling_window(0) == 4 and m.rolling_window(1) is None
+    assert m.get_kv_by_layer_id(0)[0].shape == (3, 2, 4, 8) and m.get_kv_by_layer_id(1)[0].shape == (3, 2, 32, 8)
+    assert len(m.past_key_values) == 6 and m.bytes() == (2 * 2 * 3 * 2 * 4 * 8 + 2 * 3 * 2 * 32 * 8) * 4
+    # prefill of 7 tokens (row 1 has 5 valid): only the last 4 positions of each row are written, at pos % 4
+    wp = torch.tensor([[0, 1, 2, 3, 4, 5, 6], [0, 1, 2, 3, 4, -1, -1]])
+    slots, hor = m.rolling_positions(4, wp, wp.clamp(min=0), True)
+    assert slots.tolist() == [[-1, -1, -1, 3, 0, 1, 2], [-1, 1, 2, 3, 0, -1, -1]]
+    k = torch.arange(2 * 7, dtype=torch.float32).view(2, 7, 1, 1).expand(2, 7, 2, 8).contiguous()
+    m.update(0, k, k, torch.tensor([0, 1]), slots)
+    kc = m.get_kv_by_layer_id(0)[0]
+    assert kc[0, 0, :, 0].tolist() == [4.0, 5.0, 6.0, 3.0] and kc[1, 0, :, 0].tolist() == [11.0, 8.0, 9.0, 10.0]
+    # decode: slot = pos % W, horizon saturates at W - 1
+    slots, hor = m.rolling_positions(4, torch.tensor([[7], [2]]), torch.tensor([[7], [2]]), False)
+    assert slots.tolist() == [[3], [2]] and hor.tolist() == [[3], [2]]
+    with pytest.raises(NotImplementedError):
+        m.rolling_positions(4, torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 2, dtype=torch.long), False)
+    with pytest.raises(NotImplementedError):
+        HybridKVCacheManager([4, 8], 2, 8, 32, 2)
+
+
+def test_multimodal_kv_cache_manager_vision_lines():
+    """Vision K/V are written once per cache line and read back by line at decode (reference multimodal_kv_cache_manager.py:11-134)."""
+    from neuronx_distributed_inference_b200.modules.kvcache.multimodal_kv_cache_manager import MultimodalKVCacheManager
+    m = MultimodalKVCacheManager(4, 2, 8, 16, 3, torch.float32, cross_attention_layers=[1, 3])
+    assert not m.has_vision(1)
+    k, v = torch.randn(2, 2, 5, 8), torch.randn(2, 2, 5, 8)
+    rm = torch.tensor([[1, 1, 0, 0, 0], [1, 1, 1, 1, 0]], dtype=torch.bool)
+    m.update_vision(1, torch.tensor([2, 0]), k, v, rm)
+    assert m.has_vision(1) and not m.has_vision(3)
+    k2, v2, rm2 = m.get_vision(1, torch.tensor([0, 2]))
+    assert torch.equal(k2, k.flip(0)) and torch.equal(v2, v.flip(0)) and torch.equal(rm2, rm.flip(0))
+    assert m.bytes() > KVBYTES(m)
+    m.reset()
+    assert not m.has_vision(1)
+
+
+def KVBYTES(m):
+    return sum(b.numel() * b.element_size() for b in m.buffers())
