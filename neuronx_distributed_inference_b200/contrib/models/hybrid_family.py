@@ -1,0 +1,359 @@
+"""Hybrid decoders: attention layers on the engine's KV cache interleaved with fixed-state sequence mixers whose state lives in a
+:class:`RecurrentStateCache` attached to the KV manager (same cache lines, same reset).
+
+* **LFM2** — double-gated short causal convolution (``y = C * conv_L(B * x)``, depthwise, L = 3) in most layers, GQA attention with
+  per-head q/k RMSNorm in the rest; SwiGLU with the auto-adjusted width.
+* **RecurrentGemma (Griffin)** — two recurrent blocks (``linear_x -> causal conv4 -> RG-LRU``, gated by ``gelu(linear_y)``) per local
+  (sliding-window, MQA, half-rotary) attention block; Gemma norms / embedding scale / GeGLU with biases / logit soft-cap.
+  RG-LRU: ``a = exp(-8 * sigmoid(W_a x) * softplus(L))``, ``h_t = a_t h_{t-1} + sqrt(1 - a_t^2) * (sigmoid(W_i x) * x_t)`` with
+  block-diagonal (per head) gate matrices; the state is fp32 and reset at position 0.
+reference ports: contrib/models/{lfm2-2.6b, recurrentgemma-2b-it}/src."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ...models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaAttention, NeuronLlamaForCausalLM, NeuronLlamaModel
+from ...models.model_base import DecoderLayer
+from ...models.state_dict_utils import fuse_qkv_and_gate_up
+from ...modules.kvcache.recurrent_state_cache import RecurrentStateCache
+from ...modules.mlp import GatedMLP
+from ...modules.norm import RMSNorm
+from ...parallel.layers import ColumnParallelLinear, RowParallelLinear
+
+
+def _last_valid(meta, B, T, device):
+    """Number of valid (non-padding) tokens per row of a right-padded prefill."""
+    if getattr(meta, "key_valid", None) is not None:
+        return meta.key_valid.long().sum(-1).clamp(min=1)
+    return torch.full((B,), T, dtype=torch.long, device=device)
+
+
+class _HybridModel(NeuronLlamaModel):
+    """Adds the recurrent-state cache.  Layers declare ``state_specs() -> {name: per-line shape}``."""
+    graph_safe = False
+
+    def kv_heads_per_rank(self):
+        return next(l.self_attn.n_kv for l in self.layers if hasattr(l, "self_attn"))
+
+    def kv_head_dim(self):
+        return next(l.self_attn.head_dim for l in self.layers if hasattr(l, "self_attn"))
+
+    def init_inference_optimization(self, config):
+        super().init_inference_optimization(config)
+        nc = self.neuron_config
+        if nc.is_block_kv_layout or nc.speculation_length or nc.is_medusa or nc.is_chunked_prefill or nc.attention_dp_degree > 1:
+            raise NotImplementedError("hybrid recurrent layers: contiguous KV cache, one token per decode step")
+        specs = {}
+        for layer in self.layers:
+            specs.update(getattr(layer, "state_specs", dict)())
+        self.kv_mgr.states = RecurrentStateCache(specs, self.kv_mgr.num_lines, nc.torch_dtype, self.device_)
+
+
+# ---------------------------------------------------------------------------------------------------------------------- LFM2
+class Lfm2InferenceConfig(LlamaInferenceConfig):
+    def get_required_attributes(self):
+        return ["hidden_size", "num_attention_heads", "num_hidden_layers", "num_key_value_heads", "vocab_size", "layer_types"]
+
+    def add_derived_config(self):
+        self.rms_norm_eps = getattr(self, "norm_eps", 1e-5)
+        self.hidden_act = "silu"
+        I = self.intermediate_size
+        if getattr(self, "block_auto_adjust_ff_dim", True):
+            I = int(2 * I / 3)
+            mult = getattr(self, "block_ffn_dim_multiplier", None)
+            if mult is not None:
+                I = int(mult * I)
+                m = getattr(self, "block_multiple_of", 256)
+                I = m * ((I + m - 1) // m)
+        self.intermediate_size = I
+        self.block_auto_adjust_ff_dim = False         # idempotent across save / load of the derived config
+        super().add_derived_config()
+
+
+class Lfm2ShortConvLayer(nn.Module):
+    mlp_is_moe = False
+
+    def __init__(self, config, i, device=None):
+        super().__init__()
+        nc = config.neuron_config
+        dt, H, self.L = nc.torch_dtype, config.hidden_size, int(getattr(config, "conv_L_cache", 3))
+        bias = bool(getattr(config, "conv_bias", False))
+        self.in_proj = ColumnParallelLinear(H, 3 * H, bias=bias, gather_output=False, dtype=dt, device=device, stride=3)
+        self.out_proj = RowParallelLinear(H, H, bias=bias, input_is_parallel=True, dtype=dt, device=device)
+        tp = self.in_proj.tensor_parallel_group
+        self.Hl = H // tp.size
+        self.conv_weight = nn.Parameter(torch.zeros(self.Hl, self.L, dtype=dt, device=device), requires_grad=False)
+        self.conv_weight.partition_dim, self.conv_weight.tp_group = 0, tp
+        self.conv_bias = None
+        if bias:
+            self.conv_bias = nn.Parameter(torch.zeros(self.Hl, dtype=dt, device=device), requires_grad=False)
+            self.conv_bias.partition_dim, self.conv_bias.tp_group = 0, tp
+        self.mlp = GatedMLP(H, config.intermediate_size, "silu", dt, device=device)
+        self.operator_norm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.ffn_norm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.layer_idx, self.state = i, f"conv{i}"
+
+    def state_specs(self):
+        return {self.state: (self.L - 1, self.Hl)}
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        B, T, _ = h.shape
+        L = self.L
+        Bm, C, x = self.in_proj(self.operator_norm(h)).chunk(3, dim=-1)
+        Bx = Bm * x                                                            # [B, T, Hl]
+        lines = kv_mgr.lines_for(meta.seq_ids)
+        w = self.conv_weight.t().unsqueeze(0)                                  # [1, L, Hl]
+        if meta.is_prefill:
+            if meta.has_prefix:
+                raise NotImplementedError("LFM2 short convolution with a cached prefix")
+            pad = F.pad(Bx, (0, 0, L - 1, 0))                                  # causal: L-1 zeros in front
+            conv = sum(pad[:, j:j + T] * w[:, j:j + 1] for j in range(L))
+            n = _last_valid(meta, B, T, h.device)                              # state = the last L-1 VALID inputs of every row
+            idx = (n.view(B, 1) + torch.arange(L - 1, device=h.device).view(1, -1)).unsqueeze(-1).expand(B, L - 1, Bx.shape[-1])
+            kv_mgr.states.write(self.state, lines, pad.gather(1, idx))
+        else:
+            if T != 1:
+                raise NotImplementedError("LFM2 short convolution takes one new token per decode step")
+            win = torch.cat([kv_mgr.states.read(self.state, lines).to(Bx.dtype), Bx], 1)      # [B, L, Hl]
+            conv = (win * w).sum(1, keepdim=True)
+            kv_mgr.states.write(self.state, lines, win[:, 1:])
+        if self.conv_bias is not None:
+            conv = conv + self.conv_bias
+        h = self.out_proj(C * conv, h)
+        n2 = self.ffn_norm
+        return self.mlp(h, norm_weight=n2.weight, norm_eps=n2.variance_epsilon, residual=h)
+
+
+class _Lfm2Attention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        super().__init__(config, layer_idx, rotary_emb, device=device, qk_norm="rms_pre_rope", qk_norm_eps=config.rms_norm_eps, **over)
+
+
+class NeuronLfm2Model(_HybridModel):
+    attention_cls = _Lfm2Attention
+
+    def make_layer(self, config, i, rotary, device):
+        if config.layer_types[i] != "full_attention":
+            return Lfm2ShortConvLayer(config, i, device)
+        dt = config.neuron_config.torch_dtype
+        return DecoderLayer(self.attention_cls(config, i, rotary, device=device),
+                            GatedMLP(config.hidden_size, config.intermediate_size, "silu", dt, device=device),
+                            RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device),
+                            RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device), i)
+
+
+class NeuronLfm2ForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronLfm2Model
+
+    @classmethod
+    def get_config_cls(cls):
+        return Lfm2InferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        ren = ((".feed_forward.w1.", ".mlp.gate_proj."), (".feed_forward.w3.", ".mlp.up_proj."), (".feed_forward.w2.", ".mlp.down_proj."),
+               (".self_attn.out_proj.", ".self_attn.o_proj."), (".conv.in_proj.", ".in_proj."), (".conv.out_proj.", ".out_proj."),
+               ("embedding_norm.", "norm."))
+        out = {}
+        for k, v in sd.items():
+            for a, b in ren:
+                k = k.replace(a, b)
+            if k.endswith(".conv.conv.weight"):
+                k, v = k.replace(".conv.conv.weight", ".conv_weight"), v.squeeze(1)            # [H, 1, L] -> [H, L]
+            elif k.endswith(".conv.conv.bias"):
+                k = k.replace(".conv.conv.bias", ".conv_bias")
+            out[k] = v
+        for i, kind in enumerate(config.layer_types):
+            if kind == "full_attention":                                                        # attention layers use the Llama names
+                for a, b in ((f"layers.{i}.operator_norm.", f"layers.{i}.input_layernorm."),
+                             (f"layers.{i}.ffn_norm.", f"layers.{i}.post_attention_layernorm.")):
+                    for k in [k for k in out if k.startswith(a)]:
+                        out[b + k[len(a):]] = out.pop(k)
+        return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
+
+
+# ---------------------------------------------------------------------------------------------------------------------- RecurrentGemma
+class RecurrentGemmaInferenceConfig(LlamaInferenceConfig):
+    def get_required_attributes(self):
+        return ["hidden_size", "num_attention_heads", "num_hidden_layers", "vocab_size", "lru_width"]
+
+    def add_derived_config(self):
+        self.hidden_act = getattr(self, "hidden_activation", "gelu_pytorch_tanh")
+        if getattr(self, "num_key_value_heads", None) is None:
+            self.num_key_value_heads = 1
+        if not getattr(self, "layers_block_type", None):
+            pat = list(getattr(self, "block_types", ("recurrent", "recurrent", "attention")))
+            self.layers_block_type = [pat[i % len(pat)] for i in range(self.num_hidden_layers)]
+        super().add_derived_config()
+
+
+def _head_sharded(t: nn.Parameter, group):
+    t.partition_dim, t.tp_group = 0, group
+    return t
+
+
+class GriffinRecurrentBlock(nn.Module):
+    """x/y branches -> depthwise causal conv (width 4) on x -> RG-LRU -> gate by gelu(y) -> output projection."""
+
+    def __init__(self, config, i, device=None):
+        super().__init__()
+        nc = config.neuron_config
+        dt, H, W = nc.torch_dtype, config.hidden_size, config.lru_width
+        self.linear_x = ColumnParallelLinear(H, W, bias=True, gather_output=False, dtype=dt, device=device)
+        self.linear_y = ColumnParallelLinear(H, W, bias=True, gather_output=False, dtype=dt, device=device)
+        self.linear_out = RowParallelLinear(W, H, bias=True, input_is_parallel=True, dtype=dt, device=device)
+        g = self.linear_x.tensor_parallel_group
+        nh = config.num_attention_heads
+        assert nh % g.size == 0, "RG-LRU gate blocks are sharded by head"
+        self.nh, self.bw, self.Wl, self.K = nh // g.size, W // nh, W // g.size, int(getattr(config, "conv1d_width", 4))
+        mk = lambda *shape: _head_sharded(nn.Parameter(torch.zeros(*shape, dtype=dt, device=device), requires_grad=False), g)  # noqa: E731
+        self.conv_weight, self.conv_bias = mk(self.Wl, self.K), mk(self.Wl)
+        self.recurrent_param = mk(self.Wl)
+        self.input_gate_weight, self.input_gate_bias = mk(self.nh, self.bw, self.bw), mk(self.nh, self.bw)
+        self.recurrent_gate_weight, self.recurrent_gate_bias = mk(self.nh, self.bw, self.bw), mk(self.nh, self.bw)
+        self.conv_state, self.lru_state = f"rg_conv{i}", f"rg_lru{i}"
+
+    def state_specs(self):
+        return {self.conv_state: (self.K - 1, self.Wl), self.lru_state: (self.Wl,)}
+
+    def _gates(self, x):
+        B, T, _ = x.shape
+        xh = x.reshape(B * T, self.nh, self.bw).transpose(0, 1).float()                     # [nh, B*T, bw]
+        gi = torch.baddbmm(self.input_gate_bias.float().unsqueeze(1), xh, self.input_gate_weight.float())
+        gr = torch.baddbmm(self.recurrent_gate_bias.float().unsqueeze(1), xh, self.recurrent_gate_weight.float())
+        back = lambda t: t.transpose(0, 1).reshape(B, T, self.Wl)                           # noqa: E731
+        return torch.sigmoid(back(gi)), torch.sigmoid(back(gr))
+
+    def forward(self, xn, meta, kv_mgr):
+        """xn: normed hidden [B, T, H] -> block output before the residual [B, T, H]."""
+        B, T, _ = xn.shape
+        K = self.K
+        y = ops.activation(self.linear_y(xn), "gelu_tanh")
+        x = self.linear_x(xn)                                                               # [B, T, Wl]
+        lines = kv_mgr.lines_for(meta.seq_ids)
+        states = kv_mgr.states
+        w = self.conv_weight.t().unsqueeze(0)                                               # [1, K, Wl]
+        pos = meta.position_ids.long()
+        if meta.is_prefill:
+            if meta.has_prefix:
+                raise NotImplementedError("RG-LRU with a cached prefix")
+            n = _last_valid(meta, B, T, xn.device)
+            pad = F.pad(x, (0, 0, K - 1, 0))
+            conv = sum(pad[:, j:j + T] * w[:, j:j + 1] for j in range(K)) + self.conv_bias
+            idx = (n.view(B, 1) + torch.arange(K - 1, device=xn.device).view(1, -1)).unsqueeze(-1).expand(B, K - 1, self.Wl)
+            states.write(self.conv_state, lines, pad.gather(1, idx))
+            valid = (torch.arange(T, device=xn.device).view(1, T) < n.view(B, 1)).unsqueeze(-1)
+            h0 = torch.zeros(B, self.Wl, dtype=torch.float32, device=xn.device)
+        else:
+            if T != 1:
+                raise NotImplementedError("RG-LRU takes one new token per decode step")
+            win = torch.cat([states.read(self.conv_state, lines).to(x.dtype), x], 1)
+            conv = (win * w).sum(1, keepdim=True) + self.conv_bias
+            states.write(self.conv_state, lines, win[:, 1:])
+            valid = torch.ones(B, 1, 1, dtype=torch.bool, device=xn.device)
+            h0 = states.read(self.lru_state, lines).float()
+        gi, gr = self._gates(conv)
+        log_a = -8.0 * gr * F.softplus(self.recurrent_param.float())
+        a = torch.exp(log_a)
+        reset = (pos == 0).unsqueeze(-1)
+        mult = torch.where(reset, torch.ones_like(a), torch.sqrt((1.0 - torch.exp(2.0 * log_a)).clamp(min=0.0)))
+        u = (conv * gi.to(conv.dtype) * mult.to(conv.dtype)).float()                        # HF rounds the gated input to the model dtype
+        a = torch.where(reset, torch.zeros_like(a), a)
+        a = torch.where(valid, a, torch.ones_like(a))                                       # padding steps carry the state through
+        u = torch.where(valid, u, torch.zeros_like(u))
+        hs, h = [], h0
+        for t in range(T):
+            h = a[:, t] * h + u[:, t]
+            hs.append(h)
+        states.write(self.lru_state, lines, h)
+        out = torch.stack(hs, 1).to(xn.dtype)
+        return self.linear_out(out * y)
+
+
+class _GriffinAttention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        super().__init__(config, layer_idx, rotary_emb, device=device, qkv_bias=bool(getattr(config, "attention_bias", False)), o_bias=True,
+                         sliding_window=getattr(config, "attention_window_size", None), **over)
+
+
+class GriffinLayer(nn.Module):
+    mlp_is_moe = False
+
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        dt = config.neuron_config.torch_dtype
+        self.recurrent = config.layers_block_type[i] == "recurrent"
+        if self.recurrent:
+            self.temporal_block = GriffinRecurrentBlock(config, i, device)
+        else:
+            self.self_attn = _GriffinAttention(config, i, rotary, device=device)
+        mk = lambda: RMSNorm(config.hidden_size, config.rms_norm_eps, dt, offset=1.0, device=device)   # noqa: E731
+        self.temporal_pre_norm, self.channel_pre_norm = mk(), mk()
+        self.mlp = GatedMLP(config.hidden_size, config.intermediate_size // 2, config.hidden_act, dt, bias=True, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return self.temporal_block.state_specs() if self.recurrent else {}
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.temporal_pre_norm
+        if self.recurrent:
+            h = h + self.temporal_block(n(h), meta, kv_mgr)
+        else:
+            h = self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon, norm_offset=n.offset, residual=h)
+        n = self.channel_pre_norm
+        return self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, norm_offset=n.offset, residual=h)
+
+
+class NeuronRecurrentGemmaModel(_HybridModel):
+    def make_rotary(self, config, device):
+        from ...models.llama.modeling_llama import rope_theta_of
+        from ...modules.rope import RotaryEmbedding
+        rp = getattr(config, "rope_parameters", None) or {}
+        frac = getattr(config, "partial_rotary_factor", None) or (rp.get("partial_rotary_factor") if isinstance(rp, dict) else None) or 0.5
+        return RotaryEmbedding(int(config.head_dim * float(frac)), max(config.max_position_embeddings, config.neuron_config.seq_len),
+                               rope_theta_of(config), None, device=device)
+
+    def make_layer(self, config, i, rotary, device):
+        return GriffinLayer(config, i, rotary, device)
+
+    def init_model(self, config):
+        if not hasattr(config, "max_position_embeddings"):
+            config.max_position_embeddings = config.neuron_config.seq_len
+        super().init_model(config)
+        dt = config.neuron_config.torch_dtype
+        self.norm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, offset=1.0, device=self.device_)
+        self.embed_scale = float(torch.tensor(config.hidden_size ** 0.5, dtype=torch.bfloat16))
+        self.final_logit_softcap = getattr(config, "logits_soft_cap", None)
+
+
+class NeuronRecurrentGemmaForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronRecurrentGemmaModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return RecurrentGemmaInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            k = k.replace("final_norm.", "norm.").replace(".mlp_block.", ".mlp.")
+            if ".temporal_block." in k:
+                i = int(k.split(".")[1])
+                if config.layers_block_type[i] == "attention":
+                    k = k.replace(".temporal_block.", ".self_attn.")
+                else:
+                    k = k.replace(".rg_lru.", ".")
+                    if k.endswith(".conv_1d.weight"):
+                        k, v = k.replace(".conv_1d.weight", ".conv_weight"), v.squeeze(1)
+                    elif k.endswith(".conv_1d.bias"):
+                        k = k.replace(".conv_1d.bias", ".conv_bias")
+            out[k] = v
+        return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
+
+
+HYBRID_MODEL_TYPES = {"lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

@@ -55,7 +55,12 @@ def generate_expected_logits(hf_model, input_ids: torch.Tensor, attention_mask: 
         cur = seq
         for _ in range(num_tokens):
             out = hf_model(cur, past_key_values=past, use_cache=True)
-            past = out.past_key_values
+            if past is None and getattr(out, "past_key_values", None) is None:
+                # models whose output type carries no cache (RecurrentGemma): hand in a cache object that is updated in place
+                from transformers import DynamicCache
+                past = DynamicCache(config=hf_model.config)
+                out = hf_model(cur, past_key_values=past, use_cache=True)
+            past = getattr(out, "past_key_values", None) or past
             l = out.logits[0, -1].float()
             t = int(l.argmax())
             lg.append(l)

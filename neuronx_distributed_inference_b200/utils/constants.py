@@ -62,6 +62,9 @@ MODEL_TYPES.update({
     "persimmon": {"causal-lm": f"{_X}:NeuronPersimmonForCausalLM"}, "xglm": {"causal-lm": f"{_X}:NeuronXGLMForCausalLM"},
     "codegen": {"causal-lm": f"{_X}:NeuronCodeGenForCausalLM"},
 })
+_H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"
+MODEL_TYPES.update({"lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"},
+                    "recurrent_gemma": {"causal-lm": f"{_H}:NeuronRecurrentGemmaForCausalLM"}})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

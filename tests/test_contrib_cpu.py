@@ -116,13 +116,19 @@ def _cfg(name):
                                   num_experts_per_tok=2, first_k_dense_replace=1, n_group=2, topk_group=1, topk_method="greedy",
                                   kv_lora_rank=16, q_lora_rank=None, qk_nope_head_dim=16, qk_rope_head_dim=8, v_head_dim=16, head_dim=8,
                                   routed_scaling_factor=2.0, rms_norm_eps=1e-6)
+    if name == "lfm2":
+        return T.Lfm2Config(**{**BASE, "num_hidden_layers": 4}, layer_types=["conv", "conv", "full_attention", "conv"], block_multiple_of=16,
+                            tie_word_embeddings=False)
+    if name == "recurrent_gemma":
+        return T.RecurrentGemmaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=1,
+                                      vocab_size=160, lru_width=64, attention_window_size=8, head_dim=16, tie_word_embeddings=False)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
@@ -132,7 +138,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     from neuronx_distributed_inference_b200.contrib.models.classic_family import CLASSIC_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.moe_family import MOE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.more_families import MORE_MODEL_TYPES
-    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES}[name]
+    from neuronx_distributed_inference_b200.contrib.models.hybrid_family import HYBRID_MODEL_TYPES
+    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)

@@ -284,3 +284,15 @@ def test_multimodal_kv_cache_manager_vision_lines():
 
 def KVBYTES(m):
     return sum(b.numel() * b.element_size() for b in m.buffers())
+
+
+def test_recurrent_state_cache_lines_and_garbage():
+    from neuronx_distributed_inference_b200.modules.kvcache.recurrent_state_cache import RecurrentStateCache
+    c = RecurrentStateCache({"conv0": (2, 4), "lru0": (4,)}, num_lines=3, dtype=torch.float32)
+    c.write("conv0", torch.tensor([2, 0]), torch.arange(16.0).view(2, 2, 4))
+    c.write("lru0", torch.tensor([1, -1]), torch.ones(2, 4))            # -1 -> garbage line, never read back by a live row
+    assert torch.equal(c.read("conv0", torch.tensor([0, 2])), torch.arange(16.0).view(2, 2, 4).flip(0))
+    assert c.read("lru0", torch.tensor([1]))[0].sum() == 4 and c.read("lru0", torch.tensor([0]))[0].sum() == 0
+    assert c.bytes() == (4 * 2 * 4 + 4 * 4) * 4
+    c.reset()
+    assert c.read("conv0", torch.tensor([2])).abs().sum() == 0
