@@ -7,7 +7,10 @@
   (sliding-window, MQA, half-rotary) attention block; Gemma norms / embedding scale / GeGLU with biases / logit soft-cap.
   RG-LRU: ``a = exp(-8 * sigmoid(W_a x) * softplus(L))``, ``h_t = a_t h_{t-1} + sqrt(1 - a_t^2) * (sigmoid(W_i x) * x_t)`` with
   block-diagonal (per head) gate matrices; the state is fp32 and reset at position 0.
-reference ports: contrib/models/{lfm2-2.6b, recurrentgemma-2b-it}/src."""
+* **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
+  multipliers everywhere (all linear, folded into the weights at load).  Mamba-2: ``h_t = exp(dt_t A) h_{t-1} + dt_t B_t x_t``,
+  ``y_t = C_t h_t + D x_t`` per head with grouped B/C, causal conv4 + SiLU in front, gated (grouped) RMSNorm or SiLU gate behind.
+reference ports: contrib/models/{lfm2-2.6b, recurrentgemma-2b-it, Falcon-H1-0.5B-Instruct}/src."""
 from __future__ import annotations
 
 import torch
@@ -217,7 +220,7 @@ class GriffinRecurrentBlock(nn.Module):
         self.conv_state, self.lru_state = f"rg_conv{i}", f"rg_lru{i}"
 
     def state_specs(self):
-        return {self.conv_state: (self.K - 1, self.Wl), self.lru_state: (self.Wl,)}
+        return {self.conv_state: (self.K - 1, self.Wl), self.lru_state: ((self.Wl,), torch.float32)}
 
     def _gates(self, x):
         B, T, _ = x.shape
@@ -356,4 +359,181 @@ class NeuronRecurrentGemmaForCausalLM(NeuronLlamaForCausalLM):
         return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
 
 
-HYBRID_MODEL_TYPES = {"lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Falcon-H1
+class Mamba2Mixer(nn.Module):
+    """Mamba-2 (SSD) block in recurrent form.  The mixer is small next to attention + MLP in these hybrids and its head / group
+    layout does not divide evenly in general, so it is REPLICATED across tensor-parallel ranks (no collective inside)."""
+
+    def __init__(self, config, i, device=None):
+        super().__init__()
+        dt = config.neuron_config.torch_dtype
+        H = config.hidden_size
+        self.nh, self.hd, self.G, self.N = config.mamba_n_heads, config.mamba_d_head, config.mamba_n_groups, config.mamba_d_state
+        self.I = config.mamba_d_ssm if getattr(config, "mamba_d_ssm", None) is not None else int(config.mamba_expand * H)
+        assert self.I == self.nh * self.hd
+        self.K = config.mamba_d_conv
+        self.conv_dim = self.I + 2 * self.G * self.N
+        mk = lambda *shape: nn.Parameter(torch.zeros(*shape, dtype=dt, device=device), requires_grad=False)   # noqa: E731
+        self.in_proj = nn.Linear(H, self.I + self.conv_dim + self.nh, bias=bool(getattr(config, "mamba_proj_bias", False)), dtype=dt, device=device)
+        self.out_proj = nn.Linear(self.I, H, bias=bool(getattr(config, "projectors_bias", False)), dtype=dt, device=device)
+        self.conv_weight = mk(self.conv_dim, self.K)
+        self.conv_bias = mk(self.conv_dim) if getattr(config, "mamba_conv_bias", True) else None
+        self.dt_bias, self.A_log, self.D = mk(self.nh), mk(self.nh), mk(self.nh)
+        self.gated_norm = bool(getattr(config, "mamba_rms_norm", False))
+        self.norm_before_gate = bool(getattr(config, "mamba_norm_before_gate", True))
+        if self.gated_norm:
+            self.norm_weight = mk(self.I)
+        self.eps = config.rms_norm_eps
+        lim = getattr(config, "time_step_limit", (0.0, float("inf")))
+        self.dt_min, self.dt_max = float(lim[0]), float(lim[1])
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.conv_state, self.ssm_state = f"m2_conv{i}", f"m2_ssm{i}"
+
+    def state_specs(self):
+        return {self.conv_state: (self.K - 1, self.conv_dim), self.ssm_state: ((self.nh, self.hd, self.N), torch.float32)}
+
+    def forward(self, xn, meta, kv_mgr):
+        B, T, _ = xn.shape
+        K, nh, hd, G, N = self.K, self.nh, self.hd, self.G, self.N
+        gate, xBC, dt = self.in_proj(xn).split([self.I, self.conv_dim, nh], -1)
+        lines = kv_mgr.lines_for(meta.seq_ids)
+        states = kv_mgr.states
+        w = self.conv_weight.t().unsqueeze(0)
+        if meta.is_prefill:
+            if meta.has_prefix:
+                raise NotImplementedError("Mamba-2 with a cached prefix")
+            n = _last_valid(meta, B, T, xn.device)
+            pad = F.pad(xBC, (0, 0, K - 1, 0))
+            conv = sum(pad[:, j:j + T] * w[:, j:j + 1] for j in range(K))
+            idx = (n.view(B, 1) + torch.arange(K - 1, device=xn.device).view(1, -1)).unsqueeze(-1).expand(B, K - 1, self.conv_dim)
+            states.write(self.conv_state, lines, pad.gather(1, idx))
+            valid = torch.arange(T, device=xn.device).view(1, T) < n.view(B, 1)
+            h = torch.zeros(B, nh, hd, N, dtype=torch.float32, device=xn.device)
+        else:
+            if T != 1:
+                raise NotImplementedError("Mamba-2 takes one new token per decode step")
+            win = torch.cat([states.read(self.conv_state, lines).to(xBC.dtype), xBC], 1)
+            conv = (win * w).sum(1, keepdim=True)
+            states.write(self.conv_state, lines, win[:, 1:])
+            valid = torch.ones(B, 1, dtype=torch.bool, device=xn.device)
+            h = states.read(self.ssm_state, lines).float()
+        if self.conv_bias is not None:
+            conv = conv + self.conv_bias
+        x, Bm, Cm = F.silu(conv).split([self.I, G * N, G * N], -1)
+        dt = F.softplus(dt.float() + self.dt_bias.float()).clamp(self.dt_min, self.dt_max)                   # [B, T, nh]
+        dt = torch.where(valid.unsqueeze(-1), dt, torch.zeros_like(dt))                                          # padding: state carried through
+        A = -torch.exp(self.A_log.float())
+        xh = x.float().view(B, T, nh, hd)
+        rep = nh // G
+        Bh = Bm.float().view(B, T, G, N).repeat_interleave(rep, 2)                                               # [B, T, nh, N]
+        Ch = Cm.float().view(B, T, G, N).repeat_interleave(rep, 2)
+        dA = torch.exp(dt * A)                                                                                    # [B, T, nh]
+        ys = []
+        for t in range(T):
+            h = h * dA[:, t, :, None, None] + (dt[:, t, :, None] * xh[:, t])[..., None] * Bh[:, t, :, None, :]
+            ys.append((h * Ch[:, t, :, None, :]).sum(-1))
+        states.write(self.ssm_state, lines, h)
+        y = (torch.stack(ys, 1) + xh * self.D.float().view(1, 1, nh, 1)).reshape(B, T, self.I)
+        if self.gated_norm:
+            if not self.norm_before_gate:
+                y = y * F.silu(gate.float())
+            yg = y.view(B, T, G, self.I // G)
+            yg = yg * torch.rsqrt(yg.pow(2).mean(-1, keepdim=True) + self.eps)
+            y = yg.reshape(B, T, self.I) * self.norm_weight.float()
+            if self.norm_before_gate:
+                y = y * F.silu(gate.float())
+        else:
+            y = y * F.silu(gate.float())
+        return self.out_proj(y.to(xn.dtype))
+
+
+class FalconH1Layer(nn.Module):
+    mlp_is_moe = False
+
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        dt = config.neuron_config.torch_dtype
+        b = bool(getattr(config, "attention_bias", False))
+        self.mamba = Mamba2Mixer(config, i, device)
+        self.self_attn = NeuronLlamaAttention(config, i, rotary, device=device, qkv_bias=b, o_bias=b)
+        self.mlp = GatedMLP(config.hidden_size, config.intermediate_size, config.hidden_act, dt, bias=bool(getattr(config, "mlp_bias", False)),
+                            device=device)
+        self.input_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)
+        self.pre_ff_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return self.mamba.state_specs()
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.input_layernorm
+        m = self.mamba(n(h), meta, kv_mgr)
+        h = self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h) + m
+        n = self.pre_ff_layernorm
+        return self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+
+
+class NeuronFalconH1Model(_HybridModel):
+    def make_layer(self, config, i, rotary, device):
+        return FalconH1Layer(config, i, rotary, device)
+
+    def init_model(self, config):
+        super().init_model(config)
+        self.embed_scale = float(getattr(config, "embedding_multiplier", 1.0))
+
+
+class NeuronFalconH1ForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronFalconH1Model
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        """Every muP multiplier scales the input or the output of a linear map: fold them into the weights once."""
+        I = config.mamba_d_ssm if getattr(config, "mamba_d_ssm", None) is not None else int(config.mamba_expand * config.hidden_size)
+        gn = config.mamba_n_groups * config.mamba_d_state
+        z = [float(v) for v in getattr(config, "ssm_multipliers", [1.0] * 5)]
+        mup = torch.cat([torch.full((I,), z[0]), torch.full((I,), z[1]), torch.full((gn,), z[2]), torch.full((gn,), z[3]),
+                         torch.full((config.mamba_n_heads,), z[4])])
+        g = lambda name, d=1.0: float(getattr(config, name, d))                                                  # noqa: E731
+        gate_m, down_m = [float(v) for v in getattr(config, "mlp_multipliers", [1.0, 1.0])]
+        sc = lambda t, f: (t.float() * f).to(t.dtype)                                                             # noqa: E731
+        out = {}
+        for k, v in sd.items():
+            k = k.replace(".feed_forward.", ".mlp.").replace("final_layernorm.", "norm.")
+            if k.endswith(".mamba.in_proj.weight"):
+                v = sc(v, mup.view(-1, 1) * g("ssm_in_multiplier"))
+            elif k.endswith(".mamba.in_proj.bias"):
+                v = sc(v, mup)
+            elif k.endswith(".mamba.out_proj.weight") or k.endswith(".mamba.out_proj.bias"):
+                v = sc(v, g("ssm_out_multiplier"))
+            elif k.endswith(".mamba.conv1d.weight"):
+                k, v = k.replace(".conv1d.weight", ".conv_weight"), v.squeeze(1)
+            elif k.endswith(".mamba.conv1d.bias"):
+                k = k.replace(".conv1d.bias", ".conv_bias")
+            elif k.endswith(".mamba.norm.weight"):
+                k = k.replace(".mamba.norm.weight", ".mamba.norm_weight")
+            elif ".self_attn.q_proj.weight" in k or ".self_attn.v_proj.weight" in k:
+                v = sc(v, g("attention_in_multiplier"))
+            elif ".self_attn.k_proj.weight" in k:
+                v = sc(v, g("attention_in_multiplier") * g("key_multiplier"))
+            elif ".self_attn.k_proj.bias" in k:
+                v = sc(v, g("key_multiplier"))
+            elif ".self_attn.o_proj." in k:
+                v = sc(v, g("attention_out_multiplier"))
+            elif ".mlp.gate_proj." in k:
+                v = sc(v, gate_m)
+            elif ".mlp.down_proj." in k:
+                v = sc(v, down_m)
+            elif k == "lm_head.weight":
+                v = sc(v, g("lm_head_multiplier"))
+            out[k] = v
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = sc(out["embed_tokens.weight"], g("lm_head_multiplier"))
+        return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
+
+    @staticmethod
+    def update_state_dict_for_tied_weights(sd):
+        pass
+
+
+HYBRID_MODEL_TYPES = {"falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

@@ -15,14 +15,17 @@ import torch.nn as nn
 
 class RecurrentStateCache(nn.Module):
     def __init__(self, specs: Dict[str, Sequence[int]], num_lines: int, dtype=torch.float32, device=None):
-        """``specs``: state name -> per-line shape.  One garbage line is appended."""
+        """``specs``: state name -> per-line shape, or ``(shape, dtype)`` to override the cache dtype (fp32 SSM / LRU states next to
+        bf16 activations).  One garbage line is appended."""
         super().__init__()
         self.num_lines = num_lines
         self._names = {}
         for i, (name, shape) in enumerate(specs.items()):
-            buf = f"state_{i}"
+            buf, dt = f"state_{i}", dtype
+            if len(shape) == 2 and isinstance(shape[1], torch.dtype):
+                shape, dt = shape
             self._names[name] = buf
-            self.register_buffer(buf, torch.zeros(num_lines + 1, *shape, dtype=dtype, device=device), persistent=False)
+            self.register_buffer(buf, torch.zeros(num_lines + 1, *shape, dtype=dt, device=device), persistent=False)
 
     def _lines(self, lines: torch.Tensor) -> torch.Tensor:
         lines = lines.long()

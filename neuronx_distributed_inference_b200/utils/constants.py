@@ -63,7 +63,7 @@ MODEL_TYPES.update({
     "codegen": {"causal-lm": f"{_X}:NeuronCodeGenForCausalLM"},
 })
 _H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"
-MODEL_TYPES.update({"lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"},
+MODEL_TYPES.update({"lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"}, "falcon_h1": {"causal-lm": f"{_H}:NeuronFalconH1ForCausalLM"},
                     "recurrent_gemma": {"causal-lm": f"{_H}:NeuronRecurrentGemmaForCausalLM"}})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
