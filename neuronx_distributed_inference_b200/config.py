@@ -619,7 +619,16 @@ def load_pretrained_config(model_path_or_name: Optional[str] = None, hf_config=N
         cfg = hf_config
         if cfg is None:
             from transformers import AutoConfig
-            cfg = AutoConfig.from_pretrained(model_path_or_name)
+            try:
+                cfg = AutoConfig.from_pretrained(model_path_or_name)
+            except (ValueError, KeyError) as e:
+                # architectures that ship as remote code on the hub (MiniCPM, InternLM3, Orion...): read config.json as is
+                path = os.path.join(str(model_path_or_name), "config.json")
+                if not os.path.isfile(path):
+                    raise
+                logger.info("AutoConfig does not know this model type (%s); using raw config.json", e)
+                with open(path) as f:
+                    cfg = json.load(f)
         d = cfg.to_dict() if hasattr(cfg, "to_dict") else dict(cfg)
         td = d.get("torch_dtype", d.get("dtype"))
         if td is not None and not self.neuron_config.overrides_torch_dtype:

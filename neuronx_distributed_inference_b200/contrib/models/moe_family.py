@@ -10,6 +10,9 @@
   DeepSeek-V3 MoE block (sigmoid scores, selection-only correction bias, group-limited top-k, shared experts, dense first layers).
 * **DeepSeek-V2 / V2-Lite** — the MLA attention of the DeepSeek-V3 model with the V2 router (softmax scores, greedy or
   group-limited-greedy selection by group maximum, no renormalisation).
+* **Trinity (Arcee AFMoE)** — sandwich norms, per-head q/k RMSNorm, RoPE only on the sliding-window layers, a sigmoid OUTPUT GATE on
+  the attention (``o * sigmoid(W_g x)`` before o_proj), dense first layers then sigmoid-routed MoE with a selection-only expert bias
+  and shared experts, muP embedding scale.
 * **ERNIE-4.5-MoE** — interleaved rotary, softmax router whose correction bias steers selection only, shared experts, MoE layer window.
 reference ports: contrib/models/{EXAONE-4.0-1.2B, Phi-3.5-MoE-instruct}/src and the MoE glue of modules/moe_v2.py."""
 from __future__ import annotations
@@ -17,6 +20,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ... import ops
 from ...config import MoENeuronConfig
 from ...models.deepseek.modeling_deepseek import NeuronDeepseekForCausalLM, NeuronDeepseekModel
 from ...models.llama.modeling_llama import (LlamaInferenceConfig, NeuronLlamaAttention, NeuronLlamaForCausalLM, NeuronLlamaMLP,
@@ -343,6 +347,97 @@ class NeuronDots1ForCausalLM(NeuronGlm4MoeForCausalLM):
     _model_cls = NeuronDots1Model
 
 
+# ---- Trinity (AFMoE) --------------------------------------------------------------------------------------------------------------
+class _AfmoeAttention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        lt = getattr(config, "layer_types", None)
+        local = bool(lt and lt[layer_idx] == "sliding_attention")
+        super().__init__(config, layer_idx, rotary_emb, device=device, qk_norm="rms_pre_rope", qk_norm_eps=config.rms_norm_eps,
+                         use_rope=local, sliding_window=getattr(config, "sliding_window", None) if local else None, **over)
+        dt, D = config.neuron_config.torch_dtype, self.head_dim
+        plan = self.qkv_proj.plan
+        self.gate_weight = nn.Parameter(torch.zeros(self.n_q * D, config.hidden_size, dtype=dt, device=device), requires_grad=False)
+        from ...modules.gqa import _gather_heads
+        self.gate_weight.shard_fn = lambda full, rank: _gather_heads(full, plan.q_idx[rank], D, 0)
+        self.gate_weight.partition_dim, self.gate_weight.tp_group = 0, self.tp_group
+        self._gate = None
+
+    def forward(self, hidden, meta, kv_mgr, norm_weight=None, norm_eps=None, norm_offset=0.0, residual=None, lora=None):
+        xn = ops.rmsnorm(hidden, norm_weight, norm_eps if norm_eps is not None else self.rms_norm_eps, norm_offset) \
+            if norm_weight is not None else hidden
+        self._gate = torch.sigmoid(ops.linear(xn, self.gate_weight))
+        return super().forward(hidden, meta, kv_mgr, norm_weight, norm_eps, norm_offset, residual, lora)
+
+    def _finish(self, o, residual, lora, meta):
+        return super()._finish(o * self._gate.to(o.dtype), residual, lora, meta)
+
+
+class AfmoeDecoderLayer(nn.Module):
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        dt = config.neuron_config.torch_dtype
+        self.self_attn = _AfmoeAttention(config, i, rotary, device=device)
+        self.mlp_is_moe = i >= getattr(config, "num_dense_layers", 0)
+        self.mlp = _deepseek_moe(config, device) if self.mlp_is_moe else NeuronLlamaMLP(config, device=device)
+        mk = lambda: RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)   # noqa: E731
+        self.input_layernorm, self.post_attention_layernorm, self.pre_mlp_layernorm, self.post_mlp_layernorm = mk(), mk(), mk(), mk()
+        self.layer_idx = i
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.input_layernorm
+        h = h + self.post_attention_layernorm(self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon))
+        n = self.pre_mlp_layernorm
+        return h + self.post_mlp_layernorm(self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon))
+
+
+class AfmoeInferenceConfig(_MoeConfig):
+    def add_derived_config(self):
+        # names the shared DeepSeek-style MoE block reads
+        self.n_routed_experts, self.n_shared_experts = self.num_experts, getattr(self, "num_shared_experts", 0)
+        self.routed_scaling_factor, self.norm_topk_prob, self.n_group, self.topk_group = getattr(self, "route_scale", 1.0), True, 1, 1
+        super().add_derived_config()
+
+
+class NeuronTrinityModel(NeuronLlamaModel):
+    graph_safe = False
+
+    def make_layer(self, config, i, rotary, device):
+        return AfmoeDecoderLayer(config, i, rotary, device)
+
+    def init_model(self, config):
+        super().init_model(config)
+        if getattr(config, "mup_enabled", False):
+            self.embed_scale = float(config.hidden_size ** 0.5)
+
+
+class NeuronTrinityForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronTrinityModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return AfmoeInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=True)
+        for i in range(config.num_hidden_layers):
+            m = f"layers.{i}.mlp."
+            if m + "expert_bias" in sd:
+                sd[m + "router.e_score_correction_bias"] = sd.pop(m + "expert_bias").float()
+            if m + "router.gate.weight" in sd:
+                sd[m + "router.linear_router.weight"] = sd.pop(m + "router.gate.weight").float()
+            g, u = m + "shared_experts.gate_proj.weight", m + "shared_experts.up_proj.weight"
+            if g in sd:
+                sd[m + "shared_experts.gate_up_proj.weight"] = torch.cat([sd.pop(g), sd.pop(u)], 0)
+            a = f"layers.{i}.self_attn."
+            if a + "gate_proj.weight" in sd:
+                sd[a + "gate_weight"] = sd.pop(a + "gate_proj.weight")
+        sd = convert_moe_experts(sd, config.num_hidden_layers, config.num_experts, moe_prefixes=("mlp",), gate_names=(),
+                                 w_names=("gate_proj", "up_proj", "down_proj"))
+        return {k.replace("self_attn.q_norm.", "self_attn.q_layernorm.").replace("self_attn.k_norm.", "self_attn.k_layernorm."): v
+                for k, v in sd.items()}
+
+
 # ---- DeepSeek-V2 ------------------------------------------------------------------------------------------------------------------
 class DeepseekV2Router(nn.Module):
     def __init__(self, config, device=None):
@@ -445,6 +540,6 @@ class NeuronErnie4_5MoeForCausalLM(NeuronLlamaForCausalLM):
                                    w_names=("gate_proj", "up_proj", "down_proj"))
 
 
-MOE_MODEL_TYPES = {"deepseek_v2": NeuronDeepseekV2ForCausalLM, "glm4_moe": NeuronGlm4MoeForCausalLM, "dots1": NeuronDots1ForCausalLM, "ernie4_5_moe": NeuronErnie4_5MoeForCausalLM,
+MOE_MODEL_TYPES = {"afmoe": NeuronTrinityForCausalLM, "deepseek_v2": NeuronDeepseekV2ForCausalLM, "glm4_moe": NeuronGlm4MoeForCausalLM, "dots1": NeuronDots1ForCausalLM, "ernie4_5_moe": NeuronErnie4_5MoeForCausalLM,
                    "granitemoe": NeuronGraniteMoeForCausalLM, "phimoe": NeuronPhimoeForCausalLM,
                    "qwen2_moe": NeuronQwen2MoeForCausalLM, "olmoe": NeuronOlmoeForCausalLM, "exaone4": NeuronExaone4ForCausalLM}

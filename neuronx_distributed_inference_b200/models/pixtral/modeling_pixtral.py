@@ -63,6 +63,11 @@ class NeuronPixtralVisionModel(nn.Module):
             p.requires_grad_(False)
 
     def forward(self, pixel_values: torch.Tensor, image_sizes=None):
+        feat, _ = self.features(pixel_values, image_sizes)
+        return self.proj2(ACT[self.proj_act](self.proj1(feat)))                 # [n_patches_total, H_text]
+
+    def features(self, pixel_values: torch.Tensor, image_sizes=None):
+        """-> (selected tower features [n_patches_total, H_vision(*n_feature_layers)], per-image patch grids [(gh, gw)])."""
         n, C, H, W = pixel_values.shape
         P = self.patch
         if image_sizes is None:
@@ -86,7 +91,7 @@ class NeuronPixtralVisionModel(nn.Module):
             x = layer(x, cos, sin, seg)
             hs.append(x)
         feat = hs[self.feature_layer] if isinstance(self.feature_layer, int) else torch.cat([hs[i] for i in self.feature_layer], -1)
-        return self.proj2(ACT[self.proj_act](self.proj1(feat))).squeeze(0)     # [n_patches_total, H_text]
+        return feat.squeeze(0), sizes
 
 
 class NeuronPixtralForCausalLM(NeuronBaseForImageToText):

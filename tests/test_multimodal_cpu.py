@@ -262,3 +262,29 @@ def test_qwen2_5_vl_matches_hf(tmp_path):
     assert _rel(app.encode_images(pix, image_grid_thw=grid), vis) < 1e-4
     out = app(ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid)
     assert _rel(out.logits[:, -1], exp.logits[:, -1]) < 2e-4
+
+
+def test_mistral3_matches_hf(tmp_path):
+    """Mistral-Small-3.1: Pixtral tower + RMSNorm / 2x2 patch-merger projector + Mistral decoder."""
+    from transformers import Mistral3Config, Mistral3ForConditionalGeneration, MistralConfig, PixtralVisionConfig
+    torch.manual_seed(0)
+    cfg = Mistral3Config(
+        vision_config=PixtralVisionConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2,
+                                          patch_size=4, image_size=32, num_channels=3, head_dim=16).to_dict(),
+        text_config=MistralConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                  num_key_value_heads=2, vocab_size=200, head_dim=16, sliding_window=None).to_dict(),
+        image_token_index=150, projector_hidden_act="gelu", vision_feature_layer=-1, spatial_merge_size=2)
+    hf = Mistral3ForConditionalGeneration(cfg).eval()
+    ckpt = str(tmp_path / "mistral3")
+    hf.save_pretrained(ckpt)
+    app = _build("mistral3", hf, ckpt)
+    pix = torch.randn(2, 3, 16, 16)
+    sizes = torch.tensor([[8, 16], [16, 8]])        # 2x4 and 4x2 patches -> merged 1x2 and 2x1 -> 2 tokens each
+    ids = torch.randint(1, 140, (2, 14))
+    ids[0, 1:3] = 150
+    ids[1, 5:7] = 150
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes).logits
+    out = app(ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes)
+    assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
