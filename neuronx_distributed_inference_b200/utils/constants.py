@@ -71,6 +71,10 @@ MODEL_TYPES.update({
     # Chandra OCR is a Qwen3-VL fine-tune (reference contrib/models/chandra uses the stock Qwen3-VL application)
     "chandra": {"image-text-to-text": f"{_P}.qwen3_vl.modeling_qwen3_vl:NeuronQwen3VLForCausalLM"},
 })
+_B = "neuronx_distributed_inference_b200.contrib.models.backbone_ports"
+MODEL_TYPES.update({"minicpm": {"causal-lm": f"{_B}:NeuronMiniCPMForCausalLM"}, "internlm3": {"causal-lm": f"{_B}:NeuronInternLM3ForCausalLM"},
+                    "orion": {"causal-lm": f"{_B}:NeuronOrionForCausalLM"}, "janus": {"causal-lm": f"{_B}:NeuronJanusForCausalLM"},
+                    "ovis2_5": {"causal-lm": f"{_B}:NeuronOvis2_5ForCausalLM"}})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

@@ -1,0 +1,95 @@
+"""Contrib ports of architectures that exist on the hub only as remote code (MiniCPM4, InternLM3, Orion) or as the text backbone of
+a multimodal checkpoint (Janus, Ovis2.5).  Oracle: the Hugging Face class that implements the same maths, with the checkpoint's
+config.json / weight names rewritten to the port's layout."""
+import json
+import os
+
+import pytest
+import torch
+
+from neuronx_distributed_inference_b200.config import load_pretrained_config
+from neuronx_distributed_inference_b200.contrib.models.backbone_ports import PORT_MODEL_TYPES
+from neuronx_distributed_inference_b200.utils.accuracy import generate_expected_logits, teacher_forced_logits
+from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+
+BASE = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, vocab_size=160,
+            max_position_embeddings=256)
+
+
+def _rewrite_config(ckpt, **changes):
+    """config.json only: the weights file stays untouched (the oracle memory-maps it)."""
+    p = os.path.join(ckpt, "config.json")
+    cfg = json.load(open(p))
+    drop = changes.pop("_drop", ())
+    cfg.update(changes)
+    for k in drop:
+        cfg.pop(k, None)
+    json.dump(cfg, open(p, "w"))
+
+
+def _check(name, hf, ckpt):
+    cls = PORT_MODEL_TYPES[name]
+    nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
+    app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
+    app.load(None, skip_warmup=True)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1, 160, (2, 14), generator=g)
+    mask = torch.ones_like(ids)
+    mask[1, 10:] = 0
+    exp, toks = generate_expected_logits(hf, ids, mask, 8)
+    got = teacher_forced_logits(app, ids, mask, toks)
+    err = ((got - exp).norm() / exp.norm()).item()
+    assert err < 3e-4, f"{name}: relative logit error {err}"
+
+
+def _hf(cfg, path):
+    from transformers import AutoModelForCausalLM
+    ckpt = save_random_hf_checkpoint(cfg, path, seed=3)
+    return AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32).eval(), ckpt
+
+
+def test_minicpm_is_granite_with_mup_names(tmp_path):
+    import transformers as T
+    L, H = 3, 64
+    hf, ckpt = _hf(T.GraniteConfig(**BASE, embedding_multiplier=12.0, residual_multiplier=1.4 / L ** 0.5, logits_scaling=H / 32,
+                                   attention_multiplier=16 ** -0.5, tie_word_embeddings=False), str(tmp_path / "m"))
+    _rewrite_config(ckpt, model_type="minicpm", architectures=["MiniCPMForCausalLM"], scale_emb=12.0, scale_depth=1.4, dim_model_base=32,
+                    _drop=("embedding_multiplier", "residual_multiplier", "logits_scaling", "attention_multiplier"))
+    _check("minicpm", hf, ckpt)
+
+
+def test_internlm3_bias_switches(tmp_path):
+    import transformers as T
+    hf, ckpt = _hf(T.LlamaConfig(**BASE, attention_bias=True, mlp_bias=True), str(tmp_path / "i"))
+    _rewrite_config(ckpt, model_type="internlm3", architectures=["InternLM3ForCausalLM"], qkv_bias=True, bias=True,
+                    _drop=("attention_bias", "mlp_bias"))
+    _check("internlm3", hf, ckpt)
+
+
+def test_orion_layernorm_llama(tmp_path):
+    import transformers as T
+    hf, ckpt = _hf(T.StableLmConfig(**BASE, partial_rotary_factor=1.0, use_qkv_bias=False, layer_norm_eps=1e-5), str(tmp_path / "o"))
+    _rewrite_config(ckpt, model_type="orion", architectures=["OrionForCausalLM"], rms_norm_eps=1e-5,
+                    _drop=("layer_norm_eps", "partial_rotary_factor", "use_qkv_bias", "rope_parameters"))
+    _check("orion", hf, ckpt)
+
+
+@pytest.mark.parametrize("name,prefix,nest", [("janus", "model.language_model.", "text_config"), ("ovis2_5", "llm.model.", "llm_config")])
+def test_text_backbone_of_multimodal_checkpoint(name, prefix, nest, tmp_path):
+    """Causal-LM weights moved under the multimodal prefix, hyper-parameters nested under ``text_config`` / ``llm_config``, plus a
+    vision tensor the port has to ignore.  Written to a NEW directory: the oracle's weights are memory-mapped from the original."""
+    import transformers as T
+    from safetensors.torch import load_file, save_file
+    cfg = T.LlamaConfig(**BASE) if name == "janus" else T.Qwen3Config(**BASE, head_dim=16)
+    hf, ckpt = _hf(cfg, str(tmp_path / name))
+    outer = prefix[: -len("model.")] if prefix.endswith(".model.") else prefix          # where lm_head lives
+    new = {}
+    for k, v in load_file(os.path.join(ckpt, "model.safetensors")).items():
+        new[(prefix + k[len("model."):]) if k.startswith("model.") else (outer + k)] = v.clone()
+    new["vision_model.dummy.weight"] = torch.zeros(2, 2)
+    dst = str(tmp_path / (name + "_mm"))
+    os.makedirs(dst)
+    save_file(new, os.path.join(dst, "model.safetensors"))
+    inner = json.load(open(os.path.join(ckpt, "config.json")))
+    json.dump({"model_type": "composite", nest: inner, "vision_config": {"hidden_size": 8}}, open(os.path.join(dst, "config.json"), "w"))
+    _check(name, hf, dst)
