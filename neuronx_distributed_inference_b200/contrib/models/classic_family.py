@@ -45,7 +45,7 @@ class ClassicDecoderLayer(nn.Module):
         super().__init__()
         dt = config.neuron_config.torch_dtype
         H, eps = config.hidden_size, config.rms_norm_eps
-        self.parallel, self.shared_norm = spec["parallel"], spec.get("shared_norm", False)
+        self.parallel, self.shared_norm, self.post_ln = spec["parallel"], spec.get("shared_norm", False), spec.get("post_ln", False)
         self.self_attn = spec.get("attn_cls", AttentionBase)(config, hidden_size=H, num_attention_heads=config.num_attention_heads,
                                        num_key_value_heads=config.num_key_value_heads, head_dim=config.head_dim, rotary_emb=rotary,
                                        qkv_bias=spec["qkv_bias"], o_bias=spec["o_bias"], use_rope=rotary is not None and spec.get("use_rope", True),
@@ -66,6 +66,9 @@ class ClassicDecoderLayer(nn.Module):
         self.layer_idx = i
 
     def forward(self, h, meta, kv_mgr, lora=None):
+        if self.post_ln:                                   # GPT-1: norms AFTER the residual sums
+            h = self.input_layernorm(h + self.self_attn(h, meta, kv_mgr))
+            return self.post_attention_layernorm(h + self.mlp(h))
         x1 = self.input_layernorm(h)
         a = self.self_attn(x1, meta, kv_mgr)
         if self.parallel:

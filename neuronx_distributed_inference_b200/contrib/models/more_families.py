@@ -8,6 +8,7 @@
 * **Persimmon** — per-head LayerNorm (with bias) on q and k, head-interleaved fused QKV, partial rotary, squared-ReLU MLP.
 * **XGLM** — fairseq-style sinusoidal position table (offset 2), sqrt(H)-scaled embeddings, pre-LN GELU block.
 * **CodeGen** — GPT-J block whose fused QKV is laid out in 4 "logical core" groups of [q | v | k].
+* **OpenAI GPT (GPT-1)** — post-LayerNorm blocks, learned positions, Conv1D weights, no final norm, tied head.
 * **Nemotron** — LayerNorm1P (1 + w, folded into the weight at load), partial rotary, squared-ReLU non-gated MLP.
 reference ports: contrib/models/{gemma-2b-it, vaultgemma-1b, glm-4-9b-chat-hf, c4ai-command-r7b-12-2024, Apertus-8B-Instruct-2509}/src."""
 from __future__ import annotations
@@ -360,6 +361,45 @@ class NeuronCodeGenForCausalLM(NeuronGPTJForCausalLM):
         return NeuronGPTJForCausalLM.convert_hf_to_neuron_state_dict(out, config)
 
 
-MORE_MODEL_TYPES = {"persimmon": NeuronPersimmonForCausalLM, "xglm": NeuronXGLMForCausalLM, "codegen": NeuronCodeGenForCausalLM,
+# ---------------------------------------------------------------------------------------------------------- OpenAI GPT (GPT-1)
+class NeuronOpenAIGPTModel(NeuronClassicModel):
+    learned_positions = True
+
+    def layer_spec(self, config, i):
+        return dict(parallel=False, post_ln=True, norm_bias=True, mlp="plain", act=getattr(config, "afn", "gelu_new"), qkv_bias=True, o_bias=True,
+                    mlp_bias=True)
+
+    def init_model(self, config):
+        super().init_model(config)
+        self.norm = nn.Identity()
+
+
+class NeuronOpenAIGPTForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronOpenAIGPTModel
+    _STATE_DICT_MODEL_PREFIX = "transformer."
+
+    @classmethod
+    def get_config_cls(cls):
+        return GPTJInferenceConfig          # n_embd / n_head / n_layer / n_positions aliases
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".attn.bias") or k.endswith(".attn.masked_bias"):
+                continue
+            if any(k.endswith(s) for s in ("c_attn.weight", "attn.c_proj.weight", "c_fc.weight", "mlp.c_proj.weight")):
+                v = v.t().contiguous()                      # Conv1D stores [in, out]
+            k = k.replace("h.", "layers.", 1) if k.startswith("h.") else k
+            k = (k.replace(".attn.c_attn.", ".self_attn.qkv_proj.").replace(".attn.c_proj.", ".self_attn.o_proj.").replace(".mlp.c_fc.", ".mlp.fc1.")
+                 .replace(".mlp.c_proj.", ".mlp.fc2.").replace(".ln_1.", ".input_layernorm.").replace(".ln_2.", ".post_attention_layernorm."))
+            out[k.replace("tokens_embed.", "embed_tokens.").replace("positions_embed.", "embed_positions.")] = v
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+MORE_MODEL_TYPES = {"openai-gpt": NeuronOpenAIGPTForCausalLM,
+                    "persimmon": NeuronPersimmonForCausalLM, "xglm": NeuronXGLMForCausalLM, "codegen": NeuronCodeGenForCausalLM,
                     "gemma": NeuronGemmaForCausalLM, "vaultgemma": NeuronVaultGemmaForCausalLM, "glm": NeuronGlmForCausalLM,
                     "cohere2": NeuronCohere2ForCausalLM, "apertus": NeuronApertusForCausalLM, "nemotron": NeuronNemotronForCausalLM}

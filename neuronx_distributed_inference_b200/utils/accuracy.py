@@ -46,10 +46,22 @@ def generate_expected_logits(hf_model, input_ids: torch.Tensor, attention_mask: 
     B = input_ids.shape[0]
     if attention_mask is None:
         attention_mask = torch.ones_like(input_ids)
+    import inspect
+    has_cache = "past_key_values" in inspect.signature(hf_model.forward).parameters
     all_logits, all_tokens = [], []
     for b in range(B):
         n = int(attention_mask[b].sum())
         seq = input_ids[b:b + 1, :n]
+        if not has_cache:                                   # cache-less architectures (GPT-1): recompute the whole prefix every step
+            lg, tk = [], []
+            for _ in range(num_tokens):
+                l = hf_model(seq).logits[0, -1].float()
+                lg.append(l)
+                tk.append(int(l.argmax()))
+                seq = torch.cat([seq, torch.tensor([[tk[-1]]])], 1)
+            all_logits.append(torch.stack(lg))
+            all_tokens.append(torch.tensor(tk))
+            continue
         lg, tk = [], []
         past = None
         cur = seq

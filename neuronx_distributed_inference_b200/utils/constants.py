@@ -60,7 +60,7 @@ MODEL_TYPES.update({
     "glm": {"causal-lm": f"{_X}:NeuronGlmForCausalLM"}, "cohere2": {"causal-lm": f"{_X}:NeuronCohere2ForCausalLM"},
     "apertus": {"causal-lm": f"{_X}:NeuronApertusForCausalLM"}, "nemotron": {"causal-lm": f"{_X}:NeuronNemotronForCausalLM"},
     "persimmon": {"causal-lm": f"{_X}:NeuronPersimmonForCausalLM"}, "xglm": {"causal-lm": f"{_X}:NeuronXGLMForCausalLM"},
-    "codegen": {"causal-lm": f"{_X}:NeuronCodeGenForCausalLM"},
+    "codegen": {"causal-lm": f"{_X}:NeuronCodeGenForCausalLM"}, "openai-gpt": {"causal-lm": f"{_X}:NeuronOpenAIGPTForCausalLM"},
 })
 _H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"
 MODEL_TYPES.update({"lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"}, "falcon_h1": {"causal-lm": f"{_H}:NeuronFalconH1ForCausalLM"},

@@ -132,13 +132,15 @@ def _cfg(name):
         return T.AfmoeConfig(**{**BASE, "num_hidden_layers": 4}, head_dim=16, moe_intermediate_size=32, num_experts=8, num_experts_per_tok=2,
                              num_shared_experts=1, num_dense_layers=1, sliding_window=8, global_attn_every_n_layers=2, mup_enabled=True,
                              route_scale=1.5, layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"])
+    if name == "openai-gpt":
+        return T.OpenAIGPTConfig(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "afmoe"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "afmoe", "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
