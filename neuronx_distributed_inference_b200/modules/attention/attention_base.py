@@ -207,7 +207,9 @@ class AttentionBase(nn.Module):
         if meta.capture is not None:
             meta.capture[f"layers.{self.layer_idx}.self_attn.q"] = q
 
-        if meta.is_prefill and not meta.has_prefix:
+        if meta.is_prefill and not meta.has_prefix and meta.extras.get("bidir_group_ids") is not None:
+            o = self._prefill_bidirectional_groups(q, k, v, meta)
+        elif meta.is_prefill and not meta.has_prefix:
             right = self._arange_pos(meta)
             # right padding: pad keys sit after every real token, causality alone hides them
             o = ops.attention_prefill(q, k, v, self.scale, True, self.sliding_window, self.attention_chunk_size,
@@ -227,6 +229,21 @@ class AttentionBase(nn.Module):
                                      self.attention_chunk_size, self.sinks, meta.active_mask, self.softcap, ks, vs,
                                      seq_hint=hint, active_base=meta.active_base)
         return self._finish(o.reshape(B, T, nq * D), residual, lora, meta)
+
+    def _prefill_bidirectional_groups(self, q, k, v, meta):
+        """Causal (+ window / chunk) prefill where tokens sharing a non-negative group id (the soft tokens of one image) also see
+        each other in BOTH directions — Gemma-3's image attention.  Masked fp32 path; image prompts are prefill-only work."""
+        grp = meta.extras["bidir_group_ids"].to(q.device)
+        B, T = q.shape[:2]
+        if grp.shape[1] < T:                                  # the runner padded the prompt to its bucket
+            grp = torch.nn.functional.pad(grp, (0, T - grp.shape[1]), value=-1)
+        right = self._arange_pos(meta)
+        pos = torch.arange(T, device=q.device).unsqueeze(0).expand(B, T) if right else meta.position_ids
+        mask = ops.ref.build_mask(pos, T, self.sliding_window, self.attention_chunk_size, None if right else meta.key_valid)
+        same = (grp.unsqueeze(2) == grp.unsqueeze(1)) & (grp.unsqueeze(2) >= 0)
+        o = ops.ref.attention_with_mask(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), mask | same.unsqueeze(1), self.scale,
+                                        self.sinks, self.softcap)
+        return o.transpose(1, 2)
 
     def _finish(self, o, residual, lora, meta):
         out = self.o_proj(o, residual)

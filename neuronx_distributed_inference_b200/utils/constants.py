@@ -11,7 +11,8 @@ MODEL_TYPES = {
     "mistral": {"causal-lm": f"{_P}.mistral.modeling_mistral:NeuronMistralForCausalLM"},
     "qwen2": {"causal-lm": f"{_P}.qwen2.modeling_qwen2:NeuronQwen2ForCausalLM"},
     "qwen3": {"causal-lm": f"{_P}.qwen3.modeling_qwen3:NeuronQwen3ForCausalLM"},
-    "gemma3": {"causal-lm": f"{_P}.gemma3.modeling_gemma3:NeuronGemma3ForCausalLM"},
+    "gemma3": {"causal-lm": f"{_P}.gemma3.modeling_gemma3:NeuronGemma3ForCausalLM",
+               "image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.gemma3_vision:NeuronGemma3ForConditionalGeneration"},
     "mixtral": {"causal-lm": f"{_P}.mixtral.modeling_mixtral:NeuronMixtralForCausalLM"},
     "dbrx": {"causal-lm": f"{_P}.dbrx.modeling_dbrx:NeuronDbrxForCausalLM"},
     "qwen3_moe": {"causal-lm": f"{_P}.qwen3_moe.modeling_qwen3_moe:NeuronQwen3MoeForCausalLM"},

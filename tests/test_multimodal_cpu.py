@@ -288,3 +288,43 @@ def test_mistral3_matches_hf(tmp_path):
         exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes).logits
     out = app(ids, attention_mask=mask, pixel_values=pix, image_sizes=sizes)
     assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
+
+
+def test_gemma3_vision_matches_hf(tmp_path):
+    """SigLIP tower + pooled projector + Gemma-3 decoder with bidirectional attention inside each image's soft tokens (incl. the
+    sliding-window layers), then a decode step."""
+    from transformers import Gemma3Config, Gemma3ForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Gemma3Config(
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+                         vocab_size=200, head_dim=16, sliding_window=4, query_pre_attn_scalar=16, max_position_embeddings=256,
+                         layer_types=["sliding_attention", "sliding_attention", "full_attention"]),
+        vision_config=dict(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, image_size=16, patch_size=4,
+                           num_channels=3),
+        mm_tokens_per_image=4, image_token_index=150, boi_token_index=151, eoi_token_index=152)
+    hf = Gemma3ForConditionalGeneration(cfg).eval()
+    hf.model.multi_modal_projector.mm_input_projection_weight.data.normal_(0, 0.1)      # HF initialises the projector to zeros
+    hf.model.multi_modal_projector.mm_soft_emb_norm.weight.data.normal_(0, 0.1)
+    ckpt = str(tmp_path / "gemma3v")
+    hf.save_pretrained(ckpt)
+    app = _build("gemma3", hf, ckpt)
+    pix = torch.randn(3, 3, 16, 16)
+    ids = torch.randint(1, 140, (2, 16))
+    ids[0, 2:6] = 150                      # row 0: one image
+    ids[1, 1:5] = 150                      # row 1: two images separated by a text token
+    ids[1, 6:10] = 150
+    mask = torch.ones_like(ids)
+    tt = (ids == 150).int()
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, token_type_ids=tt).logits
+        feats = hf.model.get_image_features(pix)
+        feats = feats.pooler_output if hasattr(feats, "pooler_output") else feats
+    assert _rel(app.encode_images(pix), torch.cat([f for f in feats]).reshape(-1, 64)) < 1e-4
+    out = app(ids, attention_mask=mask, pixel_values=pix)
+    assert _rel(out.logits[:, -1], exp[:, -1]) < 2e-4
+    nxt = exp[:, -1].argmax(-1)
+    ids2 = torch.cat([ids, nxt.view(2, 1)], 1)
+    with torch.no_grad():
+        exp2 = hf(input_ids=ids2, attention_mask=torch.ones_like(ids2), pixel_values=pix, token_type_ids=(ids2 == 150).int()).logits[:, -1]
+    out2 = app(nxt.view(2, 1), position_ids=torch.full((2, 1), 16, dtype=torch.int32))
+    assert _rel(out2.logits[:, -1], exp2) < 2e-4
