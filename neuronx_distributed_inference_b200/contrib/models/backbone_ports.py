@@ -4,14 +4,15 @@
   hidden states divided by ``hidden_size / dim_model_base`` before the head  ==  Granite's four multipliers.
 * **InternLM3** — Llama with separately switchable q/k/v bias (``qkv_bias``) and o_proj / MLP bias (``bias``).
 * **Orion** — Llama layout with LayerNorm (+bias) instead of RMSNorm.
-* **Janus / Ovis2.5 (text backbones)** — Llama / Qwen3 decoders nested in a multimodal checkpoint (``language_model.*`` / ``llm.*``
+* **Janus / Ovis2.5 / Qwen2.5-Omni thinker (text backbones)** — Llama / Qwen3 / Qwen2.5 decoders nested in a multimodal checkpoint (``language_model.*`` / ``llm.*``
   weights, ``text_config`` / ``llm_config`` hyper-parameters); like the reference ports, only the language path is served.
-reference ports: contrib/models/{MiniCPM4-8B, internlm3-8b-instruct, orion-14b-chat, Janus-1.3B, Ovis2.5-9B}/src."""
+reference ports: contrib/models/{MiniCPM4-8B, internlm3-8b-instruct, orion-14b-chat, Janus-1.3B, Ovis2.5-9B, Qwen2.5-Omni-7B}/src."""
 from __future__ import annotations
 
 import math
 
 from ...models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaAttention, NeuronLlamaForCausalLM, NeuronLlamaModel
+from ...models.qwen2.modeling_qwen2 import NeuronQwen2ForCausalLM
 from ...models.qwen3.modeling_qwen3 import NeuronQwen3ForCausalLM
 from ...models.state_dict_utils import fuse_qkv_and_gate_up
 from ...modules.mlp import GatedMLP
@@ -78,12 +79,17 @@ class NeuronOrionForCausalLM(_ClassicCausalLM):
 
 
 # ---------------------------------------------------------------------------------------------------------------------- text backbones
-_TEXT_PREFIXES = ("model.language_model.", "language_model.model.", "language_model.", "llm.model.", "llm.")
+_TEXT_PREFIXES = ("thinker.model.", "thinker.", "model.language_model.", "language_model.model.", "language_model.", "llm.model.", "llm.")
 _TEXT_CONFIG_KEYS = ("text_config", "llm_config", "language_config")
 
 
 def _hoist_text_config(cfg):
     """Copy the nested text hyper-parameters to the top level (only names the top level does not define)."""
+    thinker = getattr(cfg, "thinker_config", None)           # Qwen2.5-Omni: thinker_config.text_config
+    if thinker is not None:
+        sub = thinker.get("text_config") if isinstance(thinker, dict) else getattr(thinker, "text_config", None)
+        if sub is not None:
+            object.__setattr__(cfg, "text_config", sub)
     for key in _TEXT_CONFIG_KEYS:
         sub = getattr(cfg, key, None)
         if sub is None:
@@ -119,6 +125,11 @@ def _text_backbone(base_cls, name):
                     return k[len(p):]
             return super()._strip(k)
 
+        @staticmethod
+        def update_state_dict_for_tied_weights(sd):
+            if "lm_head.weight" not in sd:       # composite configs often say "tied" while the checkpoint ships its own head
+                sd["lm_head.weight"] = sd["embed_tokens.weight"].clone()
+
         @classmethod
         def get_state_dict(cls, path, config):
             sd = super().get_state_dict(path, config)
@@ -131,6 +142,7 @@ def _text_backbone(base_cls, name):
 
 NeuronJanusForCausalLM = _text_backbone(NeuronLlamaForCausalLM, "Janus")
 NeuronOvis2_5ForCausalLM = _text_backbone(NeuronQwen3ForCausalLM, "Ovis2_5")
+NeuronQwen2_5OmniForCausalLM = _text_backbone(NeuronQwen2ForCausalLM, "Qwen2_5Omni")      # text-only prompts: M-RoPE == RoPE
 
 PORT_MODEL_TYPES = {"minicpm": NeuronMiniCPMForCausalLM, "internlm3": NeuronInternLM3ForCausalLM, "orion": NeuronOrionForCausalLM,
-                    "janus": NeuronJanusForCausalLM, "ovis2_5": NeuronOvis2_5ForCausalLM}
+                    "janus": NeuronJanusForCausalLM, "ovis2_5": NeuronOvis2_5ForCausalLM, "qwen2_5_omni": NeuronQwen2_5OmniForCausalLM}

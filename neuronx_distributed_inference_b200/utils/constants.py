@@ -75,7 +75,8 @@ MODEL_TYPES.update({
 _B = "neuronx_distributed_inference_b200.contrib.models.backbone_ports"
 MODEL_TYPES.update({"minicpm": {"causal-lm": f"{_B}:NeuronMiniCPMForCausalLM"}, "internlm3": {"causal-lm": f"{_B}:NeuronInternLM3ForCausalLM"},
                     "orion": {"causal-lm": f"{_B}:NeuronOrionForCausalLM"}, "janus": {"causal-lm": f"{_B}:NeuronJanusForCausalLM"},
-                    "ovis2_5": {"causal-lm": f"{_B}:NeuronOvis2_5ForCausalLM"}})
+                    "ovis2_5": {"causal-lm": f"{_B}:NeuronOvis2_5ForCausalLM"},
+                    "qwen2_5_omni": {"causal-lm": f"{_B}:NeuronQwen2_5OmniForCausalLM"}})
 TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
 
 

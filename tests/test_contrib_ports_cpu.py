@@ -93,3 +93,23 @@ def test_text_backbone_of_multimodal_checkpoint(name, prefix, nest, tmp_path):
     inner = json.load(open(os.path.join(ckpt, "config.json")))
     json.dump({"model_type": "composite", nest: inner, "vision_config": {"hidden_size": 8}}, open(os.path.join(dst, "config.json"), "w"))
     _check(name, hf, dst)
+
+
+def test_qwen2_5_omni_thinker_text_backbone(tmp_path):
+    """The thinker's text decoder out of a full Omni checkpoint layout (``thinker.model.*``, ``thinker_config.text_config``);
+    the oracle is the Hugging Face thinker itself on a text-only prompt."""
+    import transformers as T
+    from safetensors.torch import save_file
+    from transformers.models.qwen2_5_omni import modeling_qwen2_5_omni as M
+    torch.manual_seed(0)
+    tc = T.Qwen2_5OmniThinkerConfig(
+        text_config=dict(**BASE, rope_parameters=dict(rope_type="default", mrope_section=[2, 3, 3], rope_theta=10000.0)),
+        audio_config=dict(d_model=16, encoder_layers=1, encoder_attention_heads=2, encoder_ffn_dim=32, num_mel_bins=8, output_dim=64),
+        vision_config=dict(depth=1, hidden_size=16, intermediate_size=32, num_heads=2, out_hidden_size=64, patch_size=4, spatial_merge_size=2,
+                           temporal_patch_size=2))
+    hf = M.Qwen2_5OmniThinkerForConditionalGeneration(tc).eval()
+    dst = str(tmp_path / "omni")
+    os.makedirs(dst)
+    save_file({"thinker." + k: v.clone().contiguous() for k, v in hf.state_dict().items()}, os.path.join(dst, "model.safetensors"))
+    json.dump({"model_type": "qwen2_5_omni_test", "thinker_config": tc.to_dict()}, open(os.path.join(dst, "config.json"), "w"))
+    _check("qwen2_5_omni", hf, dst)
