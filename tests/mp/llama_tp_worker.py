@@ -26,20 +26,22 @@ def main():
     ckpt, dev = sys.argv[1], sys.argv[2]
     dtype = sys.argv[3] if len(sys.argv) > 3 else ("float32" if dev == "cpu" else "bfloat16")
     from neuronx_distributed_inference_b200.config import NeuronConfig, OnDeviceSamplingConfig, load_pretrained_config
-    from neuronx_distributed_inference_b200.models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaForCausalLM
+    from neuronx_distributed_inference_b200.utils.constants import get_model_cls
+    app_cls = get_model_cls(os.environ.get("MODEL_TYPE", "llama"))          # any registered causal-lm family
     from neuronx_distributed_inference_b200.parallel import state as pstate
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if dev == "cuda":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    nc = NeuronConfig(batch_size=2, seq_len=64, max_context_length=32, torch_dtype=dtype, tp_degree=world,
+    nc = app_cls.get_neuron_config_cls()(batch_size=2, seq_len=64, max_context_length=32, torch_dtype=dtype, tp_degree=world,
                       on_cpu=(dev == "cpu"), output_logits=True, on_device_sampling_config=OnDeviceSamplingConfig(top_k=1),
                       flash_decoding_enabled=os.environ.get("FLASH_DECODING", "0") == "1",
                       sequence_parallel_enabled=os.environ.get("SEQUENCE_PARALLEL", "0") == "1",
+                      rolling_sliding_window_cache=os.environ.get("ROLLING_SWA", "0") == "1",
                       attention_dp_degree=int(os.environ.get("ATTENTION_DP", "1")), cp_degree=int(os.environ.get("CP", "1")),
                       is_continuous_batching=int(os.environ.get("ATTENTION_DP", "1")) > 1)
-    cfg = LlamaInferenceConfig(nc, load_config=load_pretrained_config(ckpt))
-    app = NeuronLlamaForCausalLM(ckpt, cfg)
+    cfg = app_cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt))
+    app = app_cls(ckpt, cfg)
     app.load(None, skip_warmup=True)
     if nc.flash_decoding_enabled:
         kvg = app.model.layers[0].self_attn.kv_group

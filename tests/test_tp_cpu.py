@@ -56,3 +56,32 @@ def test_data_parallel_sampler_matches_distributed_sampler():
 def test_llama_tp4_attention_dp_and_cp_match_hf(tiny_ckpt):
     # ranks replicating a KV head split the batch (decode) and the query sequence (prefill) instead of duplicating work
     _run(4, tiny_ckpt, 29546, ATTENTION_DP="2", CP="2")
+
+
+def _contrib_cfg(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_contrib_cfgs", os.path.join(ROOT, "tests", "test_contrib_cpu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod._cfg(name)
+
+
+@pytest.mark.parametrize("i,name", list(enumerate(["lfm2", "recurrent_gemma", "falcon_h1", "afmoe", "phimoe", "persimmon"])))
+def test_contrib_family_tp2_gloo_matches_hf(i, name, tmp_path):
+    """The sharding metadata of the contrib blocks (3-way fused conv projection, head-sharded RG-LRU gates, replicated Mamba-2 mixer,
+    q-head-aligned attention gate, expert sharding, per-head LayerNorm) under a real 2-rank gloo group."""
+    from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+    ckpt = save_random_hf_checkpoint(_contrib_cfg(name), str(tmp_path / name), seed=4)
+    _run(2, ckpt, 29560 + i, MODEL_TYPE={"afmoe": "afmoe"}.get(name, name))
+
+
+def test_gemma3_tp2_rolling_sliding_window_cache(tmp_path):
+    """Mixed sliding / global layers with the window-sized rolling cache, sharded over 2 ranks: prompts (12 tokens) and decode steps
+    wrap the 8-slot window."""
+    import transformers as T
+    from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+    cfg = T.Gemma3TextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+                             vocab_size=160, max_position_embeddings=256, head_dim=16, sliding_window=8, query_pre_attn_scalar=16,
+                             layer_types=["sliding_attention", "sliding_attention", "full_attention"])
+    ckpt = save_random_hf_checkpoint(cfg, str(tmp_path / "g3"), seed=4)
+    _run(2, ckpt, 29570, MODEL_TYPE="gemma3", ROLLING_SWA="1")
