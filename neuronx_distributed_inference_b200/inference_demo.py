@@ -51,7 +51,7 @@ CONFIG_FLAGS = [
     ("output-logits", _FLAG), ("vocab-parallel", _FLAG), ("layer-boundary-markers", _FLAG),
     # attention (:143-147)
     ("fused-qkv", _FLAG), ("sequence-parallel-enabled", _FLAG), ("weight-gather-seq-len-threshold", _INT),
-    ("flash-decoding-enabled", _FLAG),
+    ("flash-decoding-enabled", _FLAG), ("rolling-sliding-window-cache", _FLAG),
     # continuous batching (:149-153)
     ("ctx-batch-size", _INT), ("tkg-batch-size", _INT), ("max-batch-size", _INT), ("is-continuous-batching", _FLAG),
     # KV (:155-158)
