@@ -296,3 +296,56 @@ def test_recurrent_state_cache_lines_and_garbage():
     assert c.bytes() == (4 * 2 * 4 + 4 * 4) * 4
     c.reset()
     assert c.read("conv0", torch.tensor([2])).abs().sum() == 0
+
+
+def test_moe_v2_config_objects_drive_expert_mlps():
+    """RoutedExpertsMLPOpsConfig (GLU flavour, activation scale / bias, clamps) and MoEFusedTKGConfig (kernel switches) on
+    ExpertMLPsV2 (reference moe_v2.py:23-128)."""
+    from neuronx_distributed_inference_b200.modules.moe_v2 import (BlockwiseMatmulConfig, ExpertMLPsV2, MoEFusedTKGConfig,
+                                                                  RoutedExpertsMLPOpsConfig)
+    torch.manual_seed(0)
+    E, H, I, k = 4, 16, 8, 2
+    rc = RoutedExpertsMLPOpsConfig(num_experts=E, hidden_size=H, intermediate_size=I, top_k=k, glu_type="swiglu", hidden_act_scaling_factor=1.702,
+                                   hidden_act_bias=1.0, gate_clamp_upper_limit=7.0, up_clamp_upper_limit=7.0, up_clamp_lower_limit=-7.0)
+    assert RoutedExpertsMLPOpsConfig(E, H, I, k).activation() is None            # plain SwiGLU stays on the fused epilogue
+    m = ExpertMLPsV2(rc, BlockwiseMatmulConfig(block_size=256), tkg_config=MoEFusedTKGConfig(expert_mlp_kernel_enabled=False))
+    m.gate_up_proj.copy_(torch.randn(E, 2 * I, H) * 3)
+    m.down_proj.copy_(torch.randn(E, H, I))
+    x = torch.randn(5, H)
+    w, idx = torch.rand(5, k), torch.randint(0, E, (5, k))
+    y = m(x, w, idx)
+    ref = torch.zeros(5, H)
+    for n in range(5):
+        for j in range(k):
+            e = int(idx[n, j])
+            g, u = (m.gate_up_proj[e] @ x[n]).chunk(2)
+            g, u = g.clamp(max=7.0), u.clamp(-7.0, 7.0)
+            ref[n] += w[n, j] * (m.down_proj[e] @ ((u + 1.0) * g * torch.sigmoid(1.702 * g)))
+    assert torch.allclose(y, ref, atol=1e-4, rtol=1e-4)
+    assert m.blockwise_matmul_config.block_size == 256 and not m.tkg_config.decode_kernel_allowed()
+    assert BlockwiseMatmulConfig.from_kwargs(block_size=128, not_a_field=1).block_size == 128
+
+
+def test_kvcache_utils_reference_names():
+    from neuronx_distributed_inference_b200.modules.kvcache import utils as U
+    c = torch.zeros(3, 2, 8, 4)
+    U.fill_prefix(c, torch.ones(2, 2, 3, 4))
+    assert c[:2, :, :3].sum() == 2 * 2 * 3 * 4 and c[2].sum() == 0 and c[:, :, 3:].sum() == 0
+    t = torch.zeros(4, 6)
+    U.dynamic_update_slice(t, torch.ones(2, 3), [3, 5])                       # clamped to fit: rows 2-3, cols 3-5
+    assert t[2:, 3:].sum() == 6 and t.sum() == 6
+    c = torch.zeros(3, 2, 8, 4)
+    U.update_cache_const_indices(c, torch.full((2, 2, 5, 4), 2.0), torch.tensor([2, 7]))     # line 7 does not exist: skipped
+    assert c[2, :, :5].sum() == 2 * 5 * 4 * 2 and c[:2].sum() == 0
+    assert U.get_layer_to_kv_cache_size_mapping_for_mixed_attn(128, 4096, [True, False, True]) == [128, 4096, 128]
+    k, v = U.get_kv_shapes(256, 2, 4, 64, k_cache_transposed=True)
+    assert k == (2, 4, 64, 256) and v == (2, 4, 256, 64)
+    assert U.get_kv_shapes(256, 2, 4, 64, is_kv_cache_tiled=True)[1] == (2, 4, 2, 128, 64)
+    # chunked prefill stitching: seq0 has 3 cached + 2 new tokens, seq1 0 cached + 3 new; block size 2
+    cache = torch.arange(6 * 2, dtype=torch.float32).view(6, 2, 1, 1).expand(6, 2, 1, 4).contiguous()     # slot id in every element
+    bt = torch.tensor([[4, 1, 0], [2, 0, 0]])
+    slots, dc, dn = U.contexted_kv_indexing(torch.tensor([2, 3]), torch.tensor([5, 3]), bt, 2)
+    assert slots.tolist() == [8, 9, 2] and dc.tolist() == [0, 1, 2] and dn.tolist() == [3, 4, 5, 6, 7]
+    cur = torch.full((5, 1, 4), -1.0)
+    out = U.contexted_kv(cache, cur, slots, dc, dn)
+    assert out[:, 0, 0].tolist() == [8.0, 9.0, 2.0, -1.0, -1.0, -1.0, -1.0, -1.0]

@@ -85,3 +85,12 @@ def test_gemma3_tp2_rolling_sliding_window_cache(tmp_path):
                              layer_types=["sliding_attention", "sliding_attention", "full_attention"])
     ckpt = save_random_hf_checkpoint(cfg, str(tmp_path / "g3"), seed=4)
     _run(2, ckpt, 29570, MODEL_TYPE="gemma3", ROLLING_SWA="1")
+
+
+def test_weight_gathered_matmul_gloo():
+    """EAGLE weight-gather projections (reference eagle/utils.py:65-205): y = x @ all_gather(W)^T tiled over K / looped over N."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29575", os.path.join(ROOT, "tests", "mp", "weight_gather_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
