@@ -127,3 +127,21 @@ def will_hit_bucket_boundary(position_ids: torch.Tensor, buckets, look_ahead: in
 def execute_model(app, *args, **kwargs):
     """Synchronous single step through the application (reference ``execute_model`` :131-146)."""
     return app(*args, **kwargs)
+
+
+def execute_model_prefix_caching(app, input_dict: dict, pad_type: str = "first_fit"):
+    """One step of a prefix-caching request from the dict a serving engine hands over (reference :73-128): derives
+    ``num_queries = full_context_lens - computed_context_lens`` when absent and forwards the paged-cache plumbing
+    (``slot_mapping``, ``block_table``, context lengths).  -> (AsyncTensorWrapper around the output tokens / logits, is_device)."""
+    d = dict(input_dict)
+    if "num_queries" not in d and d.get("full_context_lens") is not None:
+        d["num_queries"] = d["full_context_lens"] - d["computed_context_lens"]
+    out = app(d["input_ids"], d.get("attention_mask"), d.get("position_ids"), d.get("seq_ids"), d.get("sampling_params"),
+              adapter_ids=d.get("adapter_ids"), slot_mapping=d.get("slot_mapping"), block_table=d.get("block_table"),
+              full_context_lens=d.get("full_context_lens"), computed_context_lens=d.get("computed_context_lens"))
+    res = out.tokens if getattr(out, "tokens", None) is not None else out.logits
+    ev = None
+    if torch.is_tensor(res) and res.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+    return AsyncTensorWrapper(res, ev), bool(torch.is_tensor(res) and res.is_cuda)

@@ -163,6 +163,23 @@ class GroupQueryAttention_QKV(BaseParallelLinear):
         return torch.cat([_gather_heads(q, p.q_idx[rank], D, 0), _gather_heads(k, p.kv_idx[rank], D, 0),
                           _gather_heads(v, p.kv_idx[rank], D, 0)], 0)
 
+    def preshard_hook(self, model_state_dict: dict, prefix: str) -> bool:
+        """Rewrite the fused ``<prefix>.weight / .bias / .scale`` entries of an UNSHARDED state dict to the replicated / padded head
+        layout of this TP degree: rank ``r``'s shard becomes the ``r``-th equal row block, so a generic dim-0 splitter (offline sharded
+        checkpoints, ``save_sharded_checkpoint``) produces exactly what ``shard_fn`` would (reference gqa.py preshard_hook: KV-head
+        replication, Q-head padding, applied to weights AND per-channel quantisation scales)."""
+        tp = self.tensor_parallel_group.size
+        base = prefix[: -len(".weight")] if prefix.endswith(".weight") else prefix.rstrip(".")
+        done = False
+        for suffix in ("weight", "bias", "scale"):
+            k = f"{base}.{suffix}"
+            t = model_state_dict.get(k)
+            if t is None or t.shape[0] == 1:
+                continue
+            model_state_dict[k] = torch.cat([self._shard(t, r) for r in range(tp)], 0)
+            done = True
+        return done
+
     def forward(self, x, norm_weight=None, norm_eps=1e-6, norm_offset=0.0):
         if self.sequence_parallel_enabled:
             x = mappings.all_gather(x, self.sequence_dimension, self.tensor_parallel_group)

@@ -120,6 +120,57 @@ class SubModelRunner:
             i = autobucketing.select_bucket(self.seq_buckets, length, 0, strategy, nc.allow_input_truncation)
         return self.seq_buckets[i]
 
+    def get_target_2d_bucket_for_prefix_caching(self, active_len: int, prefix_len: int, buckets=None, strategy: str = "first_fit"):
+        """(active-token bucket, prefix-length bucket) of a prefix-caching request (reference model_wrapper.py:923-1045).
+        Prefill: smallest active bucket holding the new tokens (+ one KV block with EAGLE, whose target recomputes a block); the empty
+        tail of that bucket absorbs the end of the cached prefix (recomputed instead of read back), the rest of the prefix picks the
+        prefix bucket; 256 < total <= 512 goes to the (512, 0) bucket when it exists.  Decode / speculation: smallest prefix bucket
+        strictly longer than the context (+ speculation length) among the rows with enough active slots."""
+        from ..modules import autobucketing
+        nc = self.neuron_config
+        if strategy not in ("first_fit", "second_fit"):
+            raise ValueError('Strategy must be either "first_fit" or "second_fit"')
+        if buckets is None:
+            buckets = autobucketing.generate_2d_buckets_for_prefix_caching(
+                min(128, nc.max_context_length), nc.max_context_length, min(128, nc.max_length), nc.max_length, self.is_prefill)
+        acts = sorted({b[0] for b in buckets})
+        pres = sorted({b[1] for b in buckets})
+        if not self.is_prefill:
+            spec = 0 if nc.async_mode else (nc.speculation_length if self.n_active_tokens > 1 else 0)
+            ok = sorted((p, a) for a, p in buckets if a >= active_len and p > prefix_len + spec)
+            if not ok:
+                if not nc.allow_input_truncation:
+                    raise ValueError(f"context {prefix_len} exceeds the largest bucket ({pres[-1]}) for {self.tag}")
+                return [acts[-1], pres[-1]]
+            p = ok[0][0]
+            if strategy == "second_fit":
+                p = next((q for q in pres if q > p), p)
+            return [min(a for a, q in buckets if q == ok[0][0] and a >= active_len), p]
+        total = active_len + prefix_len
+        if 256 < total <= 512 and [512, 0] in [list(b) for b in buckets]:
+            return [512, 0]
+        blk = nc.pa_block_size if nc.enable_eagle_speculation else 0
+        need = active_len + blk
+        a = next((x for x in acts if x >= need), None)
+        if a is None:
+            if not nc.allow_input_truncation:
+                raise ValueError(f"prefill length {need} exceeds the largest bucket ({acts[-1]}) for {self.tag}")
+            a = acts[-1]
+        spare = max(0, a - need)
+        if blk:
+            spare = (spare // blk) * blk                       # whole blocks only move from the prefix to the prefill side
+        rest = max(0, prefix_len - spare)
+        p = next((x for x in pres if x >= rest), None)
+        if p is None:
+            raise ValueError(f"prefix length {rest} exceeds the largest prefix bucket ({pres[-1]}) for {self.tag}")
+        return [a, p]
+
+    def vllm_cte_repadding(self, input_ids, attention_mask, position_ids):
+        """vLLM pads a batch of prompts to ITS longest prompt; strip that (true length = max position + 1) and pad to this runner's
+        nearest bucket instead (reference model_wrapper.py:1297-1313).  -> (ids, mask, positions, true length) like ``pad_prefill``."""
+        n = int(position_ids.max()) + 1
+        return self.pad_prefill(input_ids[:, :n], attention_mask[:, :n] if attention_mask is not None else None, position_ids[:, :n])
+
     def pad_prefill(self, input_ids, attention_mask, position_ids):
         """Right/left pad the token axis up to the bucket (reference model_wrapper.py:730-829:
         ids <- pad_token_id, mask <- 0, positions <- 1)."""

@@ -76,3 +76,36 @@ def test_adapter_cache_lru_and_pinning():
     except RuntimeError:
         pass
     assert c.remove("a") == 0 and c.lookup("a") is None
+
+
+def test_lora_serving_package_checkpoint_and_weight_manager(tmp_path):
+    """reference layout modules/lora_serving/{lora_checkpoint,lora_model}.py: PEFT directory round trip, validation against the
+    serving config, host pool limit, and the weight manager's tensor inventory / name -> slot resolution."""
+    import json
+    import pytest
+    from safetensors.torch import save_file
+    from neuronx_distributed_inference_b200.modules.lora_serving import LoraCheckpoint, LoraWeightManager
+    from neuronx_distributed_inference_b200.modules.lora_serving.lora_module import HF_TO_FUSED, TARGETS
+    assert HF_TO_FUSED["k_proj"] == ("qkv_proj", 1) and "gate_up_proj" in TARGETS
+    d = tmp_path / "a1"
+    d.mkdir()
+    sd = _adapter(1)
+    save_file(sd, str(d / "adapter_model.safetensors"))
+    json.dump({"lora_alpha": 8, "r": 4}, open(d / "adapter_config.json", "w"))
+    lc = LoraServingConfig(max_loras=2, max_lora_rank=8, max_cpu_loras=1, lora_alpha=8,
+                           target_modules=["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"])
+    ck = LoraCheckpoint(lc)
+    cfg, got = ck.load_to_cpu("a1", str(d))
+    assert cfg["lora_alpha"] == 8 and set(got) == set(sd) and ck.validate("a1", cfg, got) == (8, 4)
+    with pytest.raises(RuntimeError):
+        ck.load_to_cpu("a2", state_dict=_adapter(2))                 # host pool holds one adapter
+    with pytest.raises(ValueError):
+        LoraCheckpoint(LoraServingConfig(max_loras=2, max_lora_rank=2)).validate("a1", cfg, got)        # rank 4 > 2
+    with pytest.raises(ValueError):
+        LoraCheckpoint(LoraServingConfig(max_loras=2, max_lora_rank=8, target_modules=["q_proj"])).validate("a1", cfg, got)
+    app = build_random_llama(TINY, lora_config=lc, batch_size=2, seq_len=32, max_context_length=16, device="cpu", dtype="float32", seed=11)
+    wm = LoraWeightManager(lc, app.lora_manager.lm, app.lora_manager)
+    n_targets = 2 * 4                                              # layers x fused projections
+    assert len(wm.get_lora_tensors()) == 2 * n_targets and wm.print_lora_memory_footprint() > 0
+    app.lora_manager.add_adapter("a1", state_dict=sd, alpha=8)
+    assert wm.update_lora_adapter_ids(["a1", "a1"]).tolist() == app.lora_manager.adapter_ids(["a1", "a1"]).tolist()

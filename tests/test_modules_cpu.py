@@ -349,3 +349,61 @@ def test_kvcache_utils_reference_names():
     cur = torch.full((5, 1, 4), -1.0)
     out = U.contexted_kv(cache, cur, slots, dc, dn)
     assert out[:, 0, 0].tolist() == [8.0, 9.0, 2.0, -1.0, -1.0, -1.0, -1.0, -1.0]
+
+
+def test_prefix_caching_2d_bucket_rules_and_vllm_repadding():
+    """reference model_wrapper.py:923-1045 (2-D bucket choice) and :1297-1313 (vLLM re-padding)."""
+    from types import SimpleNamespace
+    from neuronx_distributed_inference_b200.runtime.runner import SubModelRunner
+    nc = SimpleNamespace(max_context_length=1024, max_length=4096, pa_block_size=32, enable_eagle_speculation=False, allow_input_truncation=False,
+                         async_mode=False, speculation_length=0, padding_side="right", pad_token_id=0)
+    r = SubModelRunner.__new__(SubModelRunner)
+    r.neuron_config, r.is_prefill, r.tag, r.n_active_tokens = nc, True, "context_encoding_model", 1024
+    grid = [[a, p] for a in (128, 256, 512, 1024) for p in (0, 512, 1024, 2048)]
+    pick = lambda a, p, **kw: r.get_target_2d_bucket_for_prefix_caching(a, p, grid, **kw)        # noqa: E731
+    assert pick(100, 0) == [128, 0]
+    assert pick(300, 100) == [512, 0]                         # 256 < total <= 512 corner case
+    assert pick(600, 700) == [1024, 512]                      # 424 spare prefill slots absorb the prefix tail: 276 left -> 512
+    assert pick(130, 2000) == [256, 2048]
+    nc.enable_eagle_speculation = True
+    assert pick(600, 700) == [1024, 512] and pick(900, 40) == [1024, 0] and pick(900, 100) == [1024, 512]   # +1 block; whole spare blocks only
+    import pytest
+    with pytest.raises(ValueError):
+        pick(1020, 0)                                         # 1020 + one block does not fit
+    nc.enable_eagle_speculation = False
+    r.is_prefill, r.tag, r.n_active_tokens = False, "token_generation_model", 1
+    tk = [[1, p] for p in (512, 1024, 2048)]
+    assert r.get_target_2d_bucket_for_prefix_caching(1, 511, tk) == [1, 512]
+    assert r.get_target_2d_bucket_for_prefix_caching(1, 512, tk) == [1, 1024]                    # strictly longer than the context
+    assert r.get_target_2d_bucket_for_prefix_caching(1, 511, tk, strategy="second_fit") == [1, 1024]
+    # vLLM padded the prompts to 300; the true longest is 140 -> re-padded to the 256 bucket
+    r.is_prefill, r.seq_buckets, r.pad_token_id = True, [128, 256, 512], 0
+    ids = torch.zeros(2, 300, dtype=torch.long)
+    pos = torch.zeros(2, 300, dtype=torch.long)
+    pos[0, :140] = torch.arange(140)
+    pos[1, :90] = torch.arange(90)
+    mask = (pos > 0).int()
+    mask[:, 0] = 1
+    i2, m2, p2, n_true = r.vllm_cte_repadding(ids, mask, pos)
+    assert n_true == 140 and i2.shape == (2, 256) and m2.shape == (2, 256) and int(m2.sum()) == 230
+
+
+def test_gqa_preshard_hook_matches_per_rank_sharding():
+    """KV heads replicated to the TP degree: after the hook, equal dim-0 row blocks ARE the per-rank shards (weights and scales)."""
+    from neuronx_distributed_inference_b200.modules.gqa import GroupQueryAttention_QKV
+    from neuronx_distributed_inference_b200.parallel.state import Group
+    g = Group.__new__(Group)
+    g.size, g.rank = 4, 0
+    for k, v in dict(ranks=[0, 1, 2, 3], pg=None).items():
+        try:
+            setattr(g, k, v)
+        except Exception:
+            pass
+    qkv = GroupQueryAttention_QKV(32, 8, 4, 2, tp_group=g, dtype=torch.float32)
+    full_w, full_s = torch.randn((4 + 2 * 2) * 8, 32), torch.rand((4 + 2 * 2) * 8)
+    sd = {"layers.0.self_attn.qkv_proj.weight": full_w.clone(), "layers.0.self_attn.qkv_proj.scale": full_s.clone()}
+    assert qkv.preshard_hook(sd, "layers.0.self_attn.qkv_proj.weight")
+    W, S = sd["layers.0.self_attn.qkv_proj.weight"], sd["layers.0.self_attn.qkv_proj.scale"]
+    assert W.shape[0] == 4 * (1 + 2 * 1) * 8                                          # 1 q head + 1 (replicated) k + 1 v per rank
+    for r in range(4):
+        assert torch.equal(W.chunk(4, 0)[r], qkv._shard(full_w, r)) and torch.equal(S.chunk(4, 0)[r], qkv._shard(full_s, r))
