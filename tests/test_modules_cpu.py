@@ -392,13 +392,7 @@ def test_gqa_preshard_hook_matches_per_rank_sharding():
     """KV heads replicated to the TP degree: after the hook, equal dim-0 row blocks ARE the per-rank shards (weights and scales)."""
     from neuronx_distributed_inference_b200.modules.gqa import GroupQueryAttention_QKV
     from neuronx_distributed_inference_b200.parallel.state import Group
-    g = Group.__new__(Group)
-    g.size, g.rank = 4, 0
-    for k, v in dict(ranks=[0, 1, 2, 3], pg=None).items():
-        try:
-            setattr(g, k, v)
-        except Exception:
-            pass
+    g = Group(ranks=[0, 1, 2, 3], pg=None, rank=0)
     qkv = GroupQueryAttention_QKV(32, 8, 4, 2, tp_group=g, dtype=torch.float32)
     full_w, full_s = torch.randn((4 + 2 * 2) * 8, 32), torch.rand((4 + 2 * 2) * 8)
     sd = {"layers.0.self_attn.qkv_proj.weight": full_w.clone(), "layers.0.self_attn.qkv_proj.scale": full_s.clone()}
