@@ -17,9 +17,9 @@ from ....parallel import state as pstate
 from ...encoder_base import EncoderRunner
 from .clip.modeling_clip import NeuronClipTextModel, convert_clip_state_dict
 from .modeling_flux import FluxBackboneInferenceConfig, NeuronFluxTransformer2DModel, convert_diffusers_flux_state_dict
-from .pipeline import FlowMatchEulerScheduler, NeuronFluxPipeline
+from .pipeline import FlowMatchEulerScheduler, NeuronFluxControlPipeline, NeuronFluxFillPipeline, NeuronFluxPipeline
 from .t5.modeling_t5 import NeuronT5EncoderModel, convert_t5_state_dict
-from .vae.modeling_vae import NeuronVAEDecoder, convert_vae_decoder_state_dict
+from .vae.modeling_vae import NeuronVAEDecoder, NeuronVAEEncoder, convert_vae_decoder_state_dict, convert_vae_encoder_state_dict
 
 
 def _ns(neuron_config, d: dict) -> InferenceConfig:
@@ -36,7 +36,12 @@ class NeuronFluxApplication:
 
     def __init__(self, model_path: Optional[str], neuron_config: Optional[NeuronConfig] = None, backbone_config: Optional[dict] = None,
                  clip_config: Optional[dict] = None, t5_config: Optional[dict] = None, vae_config: Optional[dict] = None,
-                 height: int = 1024, width: int = 1024):
+                 height: int = 1024, width: int = 1024, task: str = "text-to-image"):
+        """``task``: ``text-to-image`` (FLUX.1 dev / schnell), ``control`` (Canny / Depth dev: backbone in_channels 128) or ``fill``
+        (Fill dev: in_channels 384); the image-conditioned tasks also load the VAE encoder."""
+        if task not in ("text-to-image", "control", "fill"):
+            raise ValueError(f"unknown FLUX task {task}")
+        self.task = task
         self.model_path = model_path
         self.neuron_config = neuron_config or NeuronConfig(batch_size=1, torch_dtype="bfloat16")
         self.height, self.width = height, width
@@ -77,9 +82,10 @@ class NeuronFluxApplication:
             self.clip = NeuronClipTextModel(self.clip_config, dev).eval()
             self.t5 = NeuronT5EncoderModel(self.t5_config, dev).eval()
             self.vae = NeuronVAEDecoder(self.vae_config, dev).eval()
+            self.vae_encoder = NeuronVAEEncoder(self.vae_config, dev).eval() if self.task != "text-to-image" else None
         if random_weights:
             g = torch.Generator(device=dev).manual_seed(seed)
-            for m in (self.transformer, self.clip, self.t5, self.vae):
+            for m in filter(None, (self.transformer, self.clip, self.t5, self.vae, self.vae_encoder)):
                 for n, p in m.named_parameters():
                     if p.dim() == 1 and "norm" in n and "bias" not in n:
                         p.fill_(1.0)
@@ -94,11 +100,18 @@ class NeuronFluxApplication:
             load_sharded(self.clip, convert_clip_state_dict(load_state_dict(os.path.join(mp, "text_encoder")), self.clip_config), dt, strict=False)
             load_sharded(self.t5, convert_t5_state_dict(load_state_dict(os.path.join(mp, "text_encoder_2")), self.t5_config), dt, strict=False)
             load_sharded(self.vae, convert_vae_decoder_state_dict(load_state_dict(os.path.join(mp, "vae"))), dt, strict=False)
+            if self.vae_encoder is not None:
+                load_sharded(self.vae_encoder, convert_vae_encoder_state_dict(load_state_dict(os.path.join(mp, "vae"))), dt, strict=False)
         self.models = [EncoderRunner("clip_text_encoder", self.clip, None, 0, dev), EncoderRunner("t5_text_encoder", self.t5, None, 0, dev),
                        EncoderRunner("flux_backbone", self.transformer, None, 0, dev), EncoderRunner("vae_decoder", self.vae, None, 0, dev)]
-        self.pipe = NeuronFluxPipeline(self.models[2], self.models[0], self.models[1], self.models[3], FlowMatchEulerScheduler(),
-                                       2 ** (len(self.vae_config.block_out_channels) - 1), self.vae_config.latent_channels, dev, dt,
-                                       self.backbone_config.guidance_embeds)
+        pipe_cls = {"text-to-image": NeuronFluxPipeline, "control": NeuronFluxControlPipeline, "fill": NeuronFluxFillPipeline}[self.task]
+        extra = {}
+        if self.vae_encoder is not None:
+            self.models.append(EncoderRunner("vae_encoder", self.vae_encoder, None, 0, dev))
+            extra["vae_encoder"] = self.models[-1]
+        self.pipe = pipe_cls(self.models[2], self.models[0], self.models[1], self.models[3], FlowMatchEulerScheduler(),
+                             2 ** (len(self.vae_config.block_out_channels) - 1), self.vae_config.latent_channels, dev, dt,
+                             self.backbone_config.guidance_embeds, **extra)
         return self
 
     def __call__(self, clip_input_ids, t5_input_ids, **kw):

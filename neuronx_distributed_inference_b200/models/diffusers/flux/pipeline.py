@@ -60,7 +60,7 @@ class NeuronFluxPipeline:
 
     @torch.no_grad()
     def __call__(self, clip_input_ids, t5_input_ids, height=1024, width=1024, num_inference_steps=28, guidance_scale=3.5,
-                 generator=None, latents=None, output_type="pt"):
+                 generator=None, latents=None, output_type="pt", **cond_kw):
         dev = self.device
         B = clip_input_ids.shape[0]
         _, pooled = self.clip(clip_input_ids.to(dev))
@@ -73,11 +73,75 @@ class NeuronFluxPipeline:
         txt_ids = torch.zeros(prompt.shape[1], 3, device=dev)
         ts = self.scheduler.set_timesteps(num_inference_steps, calculate_shift(x.shape[1]))
         g = torch.full((B,), guidance_scale, device=dev, dtype=torch.float32) if self.guidance_embeds else None
+        cond = self.conditioning(B, H, W, **cond_kw)            # None for text-to-image; extra channels for Control / Fill
         for i, t in enumerate(ts):
             tt = (t / 1000).expand(B).to(dev)
-            v = self.transformer(x, prompt, pooled, tt, img_ids, txt_ids, g)
+            xin = x if cond is None else torch.cat([x, cond.to(x.dtype)], 2)
+            v = self.transformer(xin, prompt, pooled, tt, img_ids, txt_ids, g)
             x = self.scheduler.step(v.to(x.dtype), i, x)
         img = self.vae(unpack_latents(x, H, W))
         if output_type == "latent":
             return unpack_latents(x, H, W)
         return (img.float() / 2 + 0.5).clamp(0, 1)
+
+    def conditioning(self, B, H, W, **kw):
+        """Packed per-token conditioning concatenated to the latent tokens along the channel axis at every step."""
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)} for the text-to-image pipeline")
+        return None
+
+
+def _prep_image(img: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """[B,3,h,w] in [0,1] (or already [-1,1] when it has negative values) -> resized to the target size, in [-1,1]."""
+    img = img.float()
+    if img.shape[-2:] != (height, width):
+        img = torch.nn.functional.interpolate(img, size=(height, width), mode="bilinear", align_corners=False)
+    return img if img.min() < 0 else img * 2 - 1
+
+
+class NeuronFluxControlPipeline(NeuronFluxPipeline):
+    """FLUX.1 Canny / Depth (reference pipeline.py NeuronFluxControlPipeline): the control image is VAE-encoded, packed like the
+    latents and concatenated to them channel-wise, so the backbone runs with ``in_channels = 2 * 64``."""
+
+    def __init__(self, *a, vae_encoder: Callable = None, **kw):
+        super().__init__(*a, **kw)
+        self.vae_encoder = vae_encoder
+
+    def conditioning(self, B, H, W, control_image=None, **kw):
+        if control_image is None:
+            raise ValueError("control_image is required")
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)}")
+        img = _prep_image(control_image, H * self.vsf, W * self.vsf).to(self.device, self.dtype)
+        lat = self.vae_encoder(img)
+        if lat.shape[0] != B:
+            lat = lat.expand(B, -1, -1, -1) if lat.shape[0] == 1 else lat.repeat_interleave(B // lat.shape[0], 0)
+        return pack_latents(lat)
+
+
+class NeuronFluxFillPipeline(NeuronFluxPipeline):
+    """FLUX.1 Fill (in/out-painting; reference pipeline.py NeuronFluxFillPipeline): per token the backbone also sees the VAE latents
+    of the image with the hole blanked out (64 channels) and the binary mask of its 8x8-pixel x 2x2-latent footprint (256 channels):
+    ``in_channels = 64 + 64 + 256 = 384``."""
+
+    def __init__(self, *a, vae_encoder: Callable = None, **kw):
+        super().__init__(*a, **kw)
+        self.vae_encoder = vae_encoder
+
+    def conditioning(self, B, H, W, image=None, mask_image=None, **kw):
+        if image is None or mask_image is None:
+            raise ValueError("image and mask_image are required")
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)}")
+        f = self.vsf
+        img = _prep_image(image, H * f, W * f).to(self.device, self.dtype)
+        m = mask_image.float()
+        if m.dim() == 3:
+            m = m.unsqueeze(1)
+        if m.shape[-2:] != (H * f, W * f):
+            m = torch.nn.functional.interpolate(m, size=(H * f, W * f), mode="nearest")
+        m = (m > 0.5).to(self.device, self.dtype)                              # 1 = repaint
+        lat = self.vae_encoder(img * (1 - m))
+        mk = m[:, 0].view(-1, H, f, W, f).permute(0, 2, 4, 1, 3).reshape(-1, f * f, H, W)     # pixel footprint of every latent position
+        out = torch.cat([pack_latents(lat), pack_latents(mk)], 2)
+        return out.expand(B, -1, -1) if out.shape[0] == 1 and B > 1 else out

@@ -131,3 +131,56 @@ def test_scheduler_packing_and_pipeline():
     img = app(torch.randint(3, 99, (1, 8)), torch.randint(3, 99, (1, 6)), num_inference_steps=2,
               generator=torch.Generator().manual_seed(0))
     assert img.shape == (1, 3, 32, 32) and torch.isfinite(img).all() and 0.0 <= float(img.min()) and float(img.max()) <= 1.0
+
+
+def test_flux_control_and_fill_pipelines():
+    """Image-conditioned FLUX (reference NeuronFluxControlPipeline / NeuronFluxFillPipeline): the backbone sees
+    [latents | control latents] (2 x 64 -> here 2 x 16 channels) resp. [latents | masked-image latents | mask footprint]."""
+    nc = NeuronConfig(batch_size=1, torch_dtype="float32", on_cpu=True)
+    lat_c, f = VAE["latent_channels"], 2                                         # two VAE resolutions -> scale factor 2
+    for task, extra_ch in (("control", lat_c * 4), ("fill", lat_c * 4 + f * f * 4)):
+        app = NeuronFluxApplication(None, nc, {**BACKBONE, "in_channels": lat_c * 4 + extra_ch, "out_channels": lat_c * 4}, CLIP, T5, VAE,
+                                    height=16, width=16, task=task).load(random_weights=True)
+        seen = []
+        inner = app.pipe.transformer
+        app.pipe.transformer = lambda x, *a: (seen.append(x.clone()), inner(x, *a))[1]
+        ids1, ids2 = torch.randint(3, 99, (1, 8)), torch.randint(3, 99, (1, 8))
+        img = torch.rand(1, 3, 16, 16)
+        g = torch.Generator().manual_seed(0)
+        if task == "control":
+            out = app(ids1, ids2, num_inference_steps=2, generator=g, control_image=img)
+            cond = app.pipe.conditioning(1, 8, 8, control_image=img)
+            from neuronx_distributed_inference_b200.models.diffusers.flux.pipeline import pack_latents
+            assert torch.allclose(cond, pack_latents(app.vae_encoder(img * 2 - 1)), atol=1e-6)
+        else:
+            mask = torch.zeros(1, 1, 16, 16)
+            mask[..., 4:12, 4:12] = 1
+            out = app(ids1, ids2, num_inference_steps=2, generator=g, image=img, mask_image=mask)
+            cond = app.pipe.conditioning(1, 8, 8, image=img, mask_image=mask)
+            mk = cond[0, :, lat_c * 4:]                                            # [tokens, f*f*4] mask footprint per 2x2 latent patch
+            assert set(mk.unique().tolist()) <= {0.0, 1.0} and mk.shape == (16, f * f * 4)
+            tok = mk.view(4, 4, -1)                                                # token grid 4x4, each covers 4x4 pixels
+            assert tok[1:3, 1:3].min() == 1 and tok[0].max() == 0 and tok[:, 0].max() == 0
+        assert out.shape == (1, 3, 16, 16) and torch.isfinite(out).all()
+        assert len(seen) == 2 and seen[0].shape == (1, 16, lat_c * 4 + extra_ch)
+        assert torch.equal(seen[0][..., lat_c * 4:], seen[1][..., lat_c * 4:]) and torch.allclose(seen[0][..., lat_c * 4:], cond)
+        assert not torch.equal(seen[0][..., : lat_c * 4], seen[1][..., : lat_c * 4])       # the latents moved, the conditioning did not
+    import pytest
+    with pytest.raises(ValueError):
+        app.pipe.conditioning(1, 8, 8, image=img)
+
+
+def test_vae_encoder_shapes_and_state_dict_names():
+    from neuronx_distributed_inference_b200.models.diffusers.flux.vae.modeling_vae import NeuronVAEEncoder, convert_vae_encoder_state_dict
+    app = _app()
+    enc = NeuronVAEEncoder(app.vae_config)
+    z = enc(torch.rand(2, 3, 32, 32) * 2 - 1)
+    assert z.shape == (2, VAE["latent_channels"], 16, 16)
+    # diffusers AutoencoderKL names -> ours (every parameter of the module must be reachable)
+    names = {}
+    for k in enc.state_dict():
+        d = (k.replace("mid_res1.", "mid_block.resnets.0.").replace("mid_res2.", "mid_block.resnets.1.").replace("mid_attn.", "mid_block.attentions.0.")
+             .replace(".downsample.", ".downsamplers.0.conv.").replace(".to_out.", ".to_out.0."))
+        names["encoder." + d] = k
+    sd = convert_vae_encoder_state_dict({d: torch.zeros(1) for d in names} | {"decoder.conv_in.weight": torch.zeros(1)})
+    assert set(sd) == set(enc.state_dict())
