@@ -328,3 +328,36 @@ def test_gemma3_vision_matches_hf(tmp_path):
         exp2 = hf(input_ids=ids2, attention_mask=torch.ones_like(ids2), pixel_values=pix, token_type_ids=(ids2 == 150).int()).logits[:, -1]
     out2 = app(nxt.view(2, 1), position_ids=torch.full((2, 1), 16, dtype=torch.int32))
     assert _rel(out2.logits[:, -1], exp2) < 2e-4
+
+
+def test_mllama_image_tiling_and_vision_mask_helpers_match_transformers():
+    """reference models/mllama/{image_transform,utils}.py — canvas choice, fit-to-canvas size, tiling, aspect-ratio ids / masks and
+    the image -> text-range visibility are checked against the Hugging Face Mllama processor functions."""
+    import random
+    from transformers.models.mllama import image_processing_mllama as I
+    from transformers.models.mllama.processing_mllama import get_cross_attention_token_mask
+    from neuronx_distributed_inference_b200.models.mllama import utils as U
+    from neuronx_distributed_inference_b200.models.mllama.image_transform import VariableSizeImageTransform, custom_image_preprocessing
+    tf = VariableSizeImageTransform(size=56, max_num_tiles=4)
+    assert U.get_all_supported_aspect_ratios(4) == I.get_all_supported_aspect_ratios(4)
+    rng = random.Random(0)
+    for _ in range(200):
+        h, w = rng.randint(8, 400), rng.randint(8, 400)
+        canvas = I.get_optimal_tiled_canvas(h, w, 4, 56)
+        assert tf.get_optimal_tiled_canvas(h, w) == tuple(canvas)
+        assert tf.get_image_size_fit_to_canvas(h, w, *canvas) == tuple(I.get_image_size_fit_to_canvas(h, w, canvas[0], canvas[1], 56))
+    img = torch.rand(3, 50, 100)
+    tiles, ar = tf(img)
+    assert ar == (1, 2) and tiles.shape == (2, 3, 56, 56)
+    exp = I.split_to_tiles(torch.arange(3 * 112 * 112.).view(1, 3, 112, 112), 2, 2)[0]
+    assert torch.equal(tf.split_to_tiles(torch.arange(3 * 112 * 112.).view(3, 112, 112), 2, 2), exp)
+    ars = [[(1, 2), (2, 2)], [(1, 1)]]
+    assert torch.equal(U.convert_aspect_ratios_to_ids(ars, 4), torch.as_tensor(I.convert_aspect_ratios_to_ids(ars, 4)))
+    assert torch.equal(U.get_aspect_ratio_mask(ars, 4), torch.as_tensor(I.build_aspect_ratio_mask(ars, 4)))
+    for ids in ([5, 9, 1, 2, 9, 9, 3, 4], [1, 2, 3], [9, 1, 1], [1, 9, 9], [9, 9, 9, 1]):
+        assert U.create_vision_mask(ids, 9) == get_cross_attention_token_mask(ids, 9)
+    dense = U.vision_mask_to_dense([U.create_vision_mask([5, 9, 1, 2, 9, 3], 9)], [[2, 4]], 6, 2, 4)
+    assert dense[0, :, 0].sum(-1).tolist() == [0, 2, 2, 2, 0, 0] and dense[0, :, 1].sum(-1).tolist() == [0, 0, 0, 0, 4, 4]
+    pix, ids, mask, counts = custom_image_preprocessing([[torch.rand(3, 60, 200)], [torch.rand(3, 50, 50), torch.rand(3, 120, 60)]], 56, 4)
+    assert pix.shape == (2, 2, 4, 3, 56, 56) and counts.tolist() == [[4, 0], [1, 2]] and ids.shape == (2, 2) and mask.shape == (2, 2, 4)
+    assert "<|image|>" in U.add_instruct("hi", True) and "<|image|>" not in U.add_instruct("hi", False)
