@@ -70,3 +70,37 @@ def test_launcher_command():
     from neuronx_distributed_inference_b200.scripts.nxdi_distributed_launcher import build_command
     cmd = build_command(8, script=["-m", "x"])
     assert "--nproc-per-node=8" in cmd and cmd[-2:] == ["-m", "x"]
+
+
+def test_tensor_capture_sessions_on_disk_and_analysis(tmp_path):
+    """Capture hook around a generation loop -> .pt files + capture_metadata.json; analysis against a reference capture pinpoints the
+    first diverging module (reference tensor_capture_utils.py:22-113, 212-426)."""
+    import json
+    from neuronx_distributed_inference_b200.utils.tensor_capture_utils import (TensorCaptureMetadata, analyze_captured_tensors,
+                                                                             get_tensor_capture_hook, list_capturable_modules_in_application)
+    mods = ["layers.0.self_attn", "layers.1.mlp"]
+
+    def run(app, d):
+        hook = get_tensor_capture_hook(mods, capture_indices=[0, 2], tensor_capture_save_dir=d)
+        ids = torch.randint(0, 128, (2, 6), generator=torch.Generator().manual_seed(1))
+        out = hook(app, 0, ids, attention_mask=torch.ones_like(ids))
+        tok = out.logits[:, -1].argmax(-1, keepdim=True)
+        for step in (1, 2):
+            out = hook(app, step, tok, position_ids=torch.full((2, 1), 5 + step, dtype=torch.int32))
+            tok = out.logits[:, -1].argmax(-1, keepdim=True)
+
+    good, bad = str(tmp_path / "good"), str(tmp_path / "bad")
+    run(_app(), good)
+    broken = _app()
+    broken.model.layers[1].mlp.down_proj.weight.data.mul_(1.5)                  # the bug to find
+    run(broken, bad)
+    meta = json.load(open(os.path.join(good, TensorCaptureMetadata.FILE)))["tensors"]
+    assert sorted(meta) == sorted(f for f in os.listdir(good) if f.endswith(".pt")) and len(meta) == 4      # steps 0 and 2 only
+    assert {m["phase"] for m in meta.values()} == {"cte", "tkg"} and {m["module_name"] for m in meta.values()} == set(mods)
+    rep = analyze_captured_tensors(bad, good)
+    assert list(rep)[0].startswith("step0") and all(r["nan"] == 0 for r in rep.values())
+    verdict = {f: r["allclose"] for f, r in rep.items()}
+    assert verdict["step0_cte_layers_0_self_attn_outputs.pt"] and not verdict["step0_cte_layers_1_mlp_outputs.pt"]
+    groups = list_capturable_modules_in_application(_app())
+    assert "layers.0.self_attn" in groups["attention"] and "layers.1.mlp" in groups["mlp"] and "layers.0" in groups["layer"]
+    assert any("norm" in n for n in groups["norm"])
