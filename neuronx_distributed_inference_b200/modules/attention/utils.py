@@ -104,3 +104,15 @@ def order_strided_tensor(t: torch.Tensor, dim: int, stride: int) -> torch.Tensor
     n = t.shape[dim]
     order = torch.arange(n, device=t.device).view(stride, n // stride).t().reshape(-1)
     return t.index_select(dim, order)
+
+
+def validate_tp_prefill_to_dp_decode(num_kv_heads: int, world_size: int, dp_degree: int) -> None:
+    """Prefill in full TP, decode attention in TP x DP (reference :603-622): legal when a rank holds the SAME number of KV heads in
+    both modes, i.e. the DP groups are exactly the ranks that replicate a KV head — otherwise prefill would have to all-gather KV
+    heads into the decode layout.  Same constraint as ``attention_dp_degree == tp / num_kv_heads``."""
+    tp_decode = world_size // dp_degree
+    dp_heads = max(num_kv_heads // tp_decode, 1)
+    tp_heads = max(num_kv_heads // world_size, 1)
+    if dp_heads != tp_heads:
+        raise ValueError(f"attention DP degree {dp_degree} is not supported for {num_kv_heads} KV heads on {world_size} ranks: a rank "
+                         f"would own {dp_heads} KV heads in decode but {tp_heads} in prefill")

@@ -46,6 +46,22 @@ def validate_sampling_params(params: torch.Tensor, on_device_sampling_config) ->
         raise ValueError("temperature must be >= 0")
 
 
+def infer_sampling_params(params: torch.Tensor) -> torch.Tensor:
+    """Special values imply the other columns (reference sampling.py:160-181): ``temperature == 0`` means greedy, so that row's top_k
+    and top_p are reset to 1 (and the temperature to 1 so that no division by zero can occur downstream)."""
+    params = params.clone()
+    greedy = params[:, 2] == 0
+    params[greedy, 0] = 1
+    params[greedy, 1] = 1
+    params[greedy, 2] = 1
+    return params
+
+
+def rand_like(t: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Uniform [0,1) noise shaped like ``t`` on its device (the reference needs an XLA ``Rng`` custom call for this, :88-94)."""
+    return torch.rand(t.shape, dtype=torch.float32, device=t.device, generator=generator)
+
+
 def mask_padded_logits(logits: torch.Tensor, rank: int, world: int, pad_size: int) -> torch.Tensor:
     """Vocab padded to a multiple of tp: the pad columns (all at the end of the last rank's
     shard) must never win (reference sampling.py:24-47)."""

@@ -305,3 +305,46 @@ def check_draft_logits(draft_logits: torch.Tensor, expected_logits: torch.Tensor
                                                  divergence_difference_tol)
             ok &= p
     return ok
+
+
+def generate_with_chunked_prefill(neuron_model, input_ids: torch.Tensor, num_tokens: int, chunk_size: Optional[int] = None,
+                                  block_table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Chunked prefill through the paged KV cache, then greedy decode (reference utils/accuracy.py:948-1100): every sequence's prompt
+    is encoded ``chunk_size`` tokens at a time — each chunk attends to the blocks written by the previous ones
+    (``computed_context_lens``) — and all sequences then decode together.  Block table and slot mapping are generated here
+    (sequence ``b`` owns blocks ``[b * n, (b + 1) * n)``) unless a ``block_table`` is given.
+    -> logits ``[num_tokens, B, V]`` (first entry: the logits after the last prompt token)."""
+    nc = neuron_model.config.neuron_config
+    assert nc.is_block_kv_layout, "chunked prefill uses the block KV cache"
+    B, T = input_ids.shape
+    bs = nc.pa_block_size
+    n_blk = -(-(T + num_tokens) // bs)
+    if block_table is None:
+        assert B * n_blk <= nc.pa_num_blocks, f"need {B * n_blk} KV blocks, have {nc.pa_num_blocks}"
+        block_table = (torch.arange(B).view(B, 1) * n_blk + torch.arange(n_blk).view(1, n_blk)).to(torch.int32)
+    cpc = getattr(nc, "chunked_prefill_config", None)
+    chunk = chunk_size or (getattr(cpc, "kernel_q_tile_size", None) if cpc is not None else None) or nc.max_context_length
+
+    def slots(pos):
+        blk = torch.gather(block_table.long(), 1, pos.long() // bs)
+        return (blk * bs + pos.long() % bs).to(torch.int32)
+
+    neuron_model.reset()
+    out, done = None, 0
+    while done < T:
+        n = min(chunk, T - done)
+        pos = (torch.arange(n) + done).unsqueeze(0).expand(B, n)
+        kw = {}
+        if done:
+            kw = dict(computed_context_lens=torch.full((B,), done), full_context_lens=torch.full((B,), done + n))
+        out = neuron_model(input_ids[:, done:done + n], attention_mask=torch.ones(B, n, dtype=torch.int32), position_ids=pos,
+                           slot_mapping=slots(pos), block_table=block_table, output_logits=True, **kw)
+        done += n
+    logits = [out.logits[:, -1].float().cpu()]
+    pos = torch.full((B, 1), T, dtype=torch.int32)
+    for _ in range(num_tokens - 1):
+        tok = logits[-1].argmax(-1).view(B, 1)
+        out = neuron_model(tok, position_ids=pos, slot_mapping=slots(pos), block_table=block_table, output_logits=True)
+        logits.append(out.logits[:, -1].float().cpu())
+        pos = pos + 1
+    return torch.stack(logits, 0)

@@ -145,3 +145,36 @@ def test_windowed_context_encoding_equals_single_shot():
     a = app(out.tokens.view(2, 1), position_ids=pos)
     b = ref_app(ref.tokens.view(2, 1), position_ids=pos)
     assert torch.allclose(a.logits, b.logits, atol=1e-4)
+
+
+def test_generate_with_chunked_prefill_matches_one_shot_prefill():
+    """reference utils/accuracy.py:948-1100: prompts encoded 5 tokens at a time through the paged cache (each chunk reads the blocks
+    the earlier chunks wrote) give the same logits as one-shot prefill + decode."""
+    from neuronx_distributed_inference_b200.utils.accuracy import generate_with_chunked_prefill
+    kw = dict(batch_size=2, seq_len=64, max_context_length=32, device="cpu", dtype="float32", seed=5, output_logits=True)
+    cont = build_random_llama(TINY, **kw)
+    paged = build_random_llama(TINY, is_block_kv_layout=True, pa_block_size=8, pa_num_blocks=24, **kw)
+    ids = torch.randint(0, 128, (2, 13))
+    got = generate_with_chunked_prefill(paged, ids, num_tokens=5, chunk_size=5)
+    out = cont(ids, attention_mask=torch.ones_like(ids))
+    exp = [out.logits[:, -1].float()]
+    pos = torch.full((2, 1), 13, dtype=torch.int32)
+    for _ in range(4):
+        out = cont(exp[-1].argmax(-1).view(2, 1), position_ids=pos)
+        exp.append(out.logits[:, -1].float())
+        pos = pos + 1
+    exp = torch.stack(exp, 0)
+    assert got.shape == exp.shape and ((got - exp).norm() / exp.norm()) < 1e-5
+
+
+def test_sampling_param_inference_and_dp_validation():
+    import pytest
+    from neuronx_distributed_inference_b200.modules.attention.utils import validate_tp_prefill_to_dp_decode
+    from neuronx_distributed_inference_b200.modules.generation.sampling import infer_sampling_params, prepare_sampling_params, rand_like
+    p = infer_sampling_params(prepare_sampling_params(3, [5, 40, 1], [0.9, 0.5, 1.0], [0.7, 0.0, 1.0]))
+    assert p.tolist()[1] == [1.0, 1.0, 1.0] and p[0].tolist() == pytest.approx([5.0, 0.9, 0.7])
+    r = rand_like(torch.zeros(4, 7))
+    assert r.shape == (4, 7) and (r >= 0).all() and (r < 1).all()
+    validate_tp_prefill_to_dp_decode(num_kv_heads=8, world_size=32, dp_degree=4)      # 4 ranks replicate each KV head
+    with pytest.raises(ValueError):
+        validate_tp_prefill_to_dp_decode(num_kv_heads=8, world_size=8, dp_degree=2)
