@@ -120,6 +120,39 @@ def get_sample_inputs(neuron_config, vocab_cap: int = 100):
     return ids, torch.ones_like(ids)
 
 
+def create_submodule_latency_collectors(model, use_cuda_events: bool = False) -> Dict[str, "LatencyCollector"]:
+    """One collector per sub-model runner (context encoding, token generation, speculation / fused speculation, vision encoder) —
+    reference utils/benchmark.py:397-407."""
+    return {r.tag: LatencyCollector(use_cuda_events) for r in model.models}
+
+
+def register_latency_collectors(latency_collectors: Dict[str, "LatencyCollector"], model) -> None:
+    """Attach the collectors: every runner call is bracketed by ``pre_hook`` / ``hook`` (reference :409-430 uses module forward hooks;
+    the runners call their collector directly so that CUDA-graph replays are timed as well)."""
+    for r in model.models:
+        r.collector = latency_collectors.get(r.tag)
+
+
+def unregister_latency_collectors(model) -> None:
+    for r in model.models:
+        r.collector = None
+
+
+def generate_submodule_reports(latency_collectors: Dict[str, "LatencyCollector"], model, prompt_len: int) -> Dict[str, dict]:
+    """Percentile report per sub-model (reference :432-446).  Tokens per call: the prompt length for context encoding, one step's
+    worth for the decode-side runners (their latency list has one entry per step)."""
+    nc = model.neuron_config
+    reports = {}
+    for r in model.models:
+        col = latency_collectors.get(r.tag)
+        if col is None or not col.latency_list:
+            continue
+        col.finalize()
+        n_tok = prompt_len if r.is_prefill else 1
+        reports[r.tag] = generate_report(col.latency_list, n_tok, nc.max_batch_size, len(col.latency_list), col.device_ms)
+    return reports
+
+
 def benchmark_sampling(model, draft_model=None, generation_config=None, target: str = "all", num_runs: int = 20,
                        benchmark_report_path: Optional[str] = BENCHMARK_REPORT_FILENAME, image=None) -> Dict[str, dict]:
     """End-to-end ``generate`` benchmark + per-sub-model latencies.  EOS is disabled (generation always runs to
@@ -133,34 +166,15 @@ def benchmark_sampling(model, draft_model=None, generation_config=None, target: 
     def run_generate():
         return adapter.generate(ids, attention_mask=mask, max_length=nc.max_length, eos_token_id=None)
 
-    collectors = {}
-    if target in ("all", "context_encode", "token_gen", "speculation"):
-        for r in model.models:
-            collectors[r.tag] = LatencyCollector(use_ev)
-
+    collectors = create_submodule_latency_collectors(model, use_ev) if target in ("all", "context_encode", "token_gen", "speculation") else {}
     bench = Benchmark(run_generate, num_runs=num_runs)
-
-    def install_hooks():  # hooks are registered after warm-up (reference :120-123)
-        for r in model.models:
-            r.collector = collectors.get(r.tag)
-    bench.post_warmup_func = install_hooks
+    bench.post_warmup_func = lambda: register_latency_collectors(collectors, model)     # hooks go in after warm-up (reference :120-123)
     try:
         lat = bench.run()
     finally:
-        for r in model.models:
-            r.collector = None
+        unregister_latency_collectors(model)
     report["e2e_model"] = generate_report(lat, nc.max_length, nc.max_batch_size, num_runs)
-    for r in model.models:
-        col = collectors.get(r.tag)
-        if col is None or not col.latency_list:
-            continue
-        col.finalize()
-        if r.is_prefill:
-            n_tok = ids.shape[1]
-        else:
-            n_tok = max(nc.max_length - ids.shape[1], 1) if r.n_active_tokens == 1 else r.n_active_tokens
-            n_tok = 1
-        report[r.tag] = generate_report(col.latency_list, n_tok, nc.max_batch_size, len(col.latency_list), col.device_ms)
+    report.update(generate_submodule_reports(collectors, model, ids.shape[1]))
     if benchmark_report_path:
         with open(benchmark_report_path, "w") as f:
             json.dump(report, f, indent=2)
