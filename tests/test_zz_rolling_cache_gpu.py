@@ -16,7 +16,7 @@ def _mk(dtype, **kw):
                               app_cls=NeuronMistralForCausalLM, output_logits=True, **kw)
 
 
-@pytest.mark.parametrize("dtype,tol", [("float32", 1e-4), ("bfloat16", 3e-2)])
+@pytest.mark.parametrize("dtype,tol", [("float32", 1e-4), ("bfloat16", 6e-2)])
 def test_rolling_cache_matches_full_cache_gpu(dtype, tol):
     from neuronx_distributed_inference_b200.modules.kvcache.gpt_oss_kv_cache_manager import HybridKVCacheManager
     full, roll = _mk(dtype), _mk(dtype, rolling_sliding_window_cache=True)
