@@ -67,6 +67,7 @@ _H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"
 MODEL_TYPES.update({"lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"}, "falcon_h1": {"causal-lm": f"{_H}:NeuronFalconH1ForCausalLM"},
                     "recurrent_gemma": {"causal-lm": f"{_H}:NeuronRecurrentGemmaForCausalLM"}})
 MODEL_TYPES.update({
+    "idefics": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.idefics:NeuronIdeficsForCausalLM"},
     "mistral3": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.mistral3:NeuronMistral3ForCausalLM"},
     "afmoe": {"causal-lm": f"{_M}:NeuronTrinityForCausalLM"}, "trinity": {"causal-lm": f"{_M}:NeuronTrinityForCausalLM"},
     # Chandra OCR is a Qwen3-VL fine-tune (reference contrib/models/chandra uses the stock Qwen3-VL application)

@@ -361,3 +361,48 @@ def test_mllama_image_tiling_and_vision_mask_helpers_match_transformers():
     pix, ids, mask, counts = custom_image_preprocessing([[torch.rand(3, 60, 200)], [torch.rand(3, 50, 50), torch.rand(3, 120, 60)]], 56, 4)
     assert pix.shape == (2, 2, 4, 3, 56, 56) and counts.tolist() == [[4, 0], [1, 2]] and ids.shape == (2, 2) and mask.shape == (2, 2, 4)
     assert "<|image|>" in U.add_instruct("hi", True) and "<|image|>" not in U.add_instruct("hi", False)
+
+
+@pytest.mark.parametrize("resampler", [False, True])
+def test_idefics_matches_hf(resampler, tmp_path):
+    """Gated cross-attention decoder + CLIP tower: prefill with two images per row (the second hidden from part of the text, one row
+    with text that sees no image at all) and two decode steps, against Hugging Face."""
+    from transformers import IdeficsConfig, IdeficsForVisionText2Text
+    torch.manual_seed(0)
+    cfg = IdeficsConfig(vocab_size=160, additional_vocab_size=4, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4,
+                        cross_layer_interval=2, qk_layer_norms=True, alpha_type="vector", alpha_initializer="normal", alphas_initializer_range=0.5,
+                        vision_config=dict(embed_dim=32, image_size=16, patch_size=4, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64),
+                        perceiver_config=dict(use_resampler=resampler, resampler_n_latents=5, resampler_depth=2, resampler_n_heads=2,
+                                              resampler_head_dim=8, qk_layer_norms_perceiver=True),
+                        use_resampler=resampler, tie_word_embeddings=False, freeze_text_layers=False, freeze_vision_layers=False,
+                        max_position_embeddings=128)
+    hf = IdeficsForVisionText2Text(cfg).eval()
+    for n, p in hf.named_parameters():
+        if "layer_norm" in n or "layernorm" in n:
+            p.data.add_(torch.randn_like(p) * 0.1)
+    ckpt = str(tmp_path / "idefics")
+    hf.save_pretrained(ckpt)
+    app = _build("idefics", hf, ckpt)
+    ids = torch.randint(1, 164, (2, 12))                     # includes ids from the additional vocabulary
+    mask = torch.ones_like(ids)
+    pix = torch.randn(2, 2, 3, 16, 16)
+    iam = torch.zeros(2, 12, 2, dtype=torch.long)
+    iam[0, 2:, 0] = 1
+    iam[0, 7:, 1] = 1
+    iam[1, 5:, 0] = 1                                        # row 1: the first five tokens see no image, image 1 is never used
+    with torch.no_grad():
+        exp = hf(input_ids=ids, attention_mask=mask, pixel_values=pix, image_attention_mask=iam)
+        feat = hf.model.vision_model(pixel_values=pix.flatten(0, 1)).last_hidden_state
+        if resampler:
+            feat = hf.model.perceiver_resampler(feat)
+    assert _rel(app.encode_images(pix), feat.reshape(2, -1, 32)) < 1e-4 and feat.shape[1] == (5 if resampler else 17)
+    out = app(ids, attention_mask=mask, pixel_values=pix, image_attention_mask=iam)
+    assert _rel(out.logits[:, -1], exp.logits[:, -1]) < 2e-4
+    past, tok, last_iam = exp.past_key_values, exp.logits[:, -1].argmax(-1), iam[:, -1:]
+    for step in range(2):
+        with torch.no_grad():
+            e = hf(input_ids=tok.view(2, 1), past_key_values=past, pixel_values=pix, image_attention_mask=last_iam,
+                   attention_mask=torch.ones(2, 13 + step, dtype=torch.long))
+        o = app(tok.view(2, 1), position_ids=torch.full((2, 1), 12 + step, dtype=torch.int32))
+        assert _rel(o.logits[:, -1], e.logits[:, -1]) < 2e-4, step
+        past, tok = e.past_key_values, e.logits[:, -1].argmax(-1)
