@@ -78,7 +78,9 @@ MODEL_TYPES.update({"minicpm": {"causal-lm": f"{_B}:NeuronMiniCPMForCausalLM"}, 
                     "orion": {"causal-lm": f"{_B}:NeuronOrionForCausalLM"}, "janus": {"causal-lm": f"{_B}:NeuronJanusForCausalLM"},
                     "ovis2_5": {"causal-lm": f"{_B}:NeuronOvis2_5ForCausalLM"},
                     "qwen2_5_omni": {"causal-lm": f"{_B}:NeuronQwen2_5OmniForCausalLM"}})
-TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image")
+MODEL_TYPES.update({"wav2vec2": {"audio-frame-classification":
+                                 "neuronx_distributed_inference_b200.contrib.models.wav2vec2:NeuronWav2Vec2ForAudioFrameClassification"}})
+TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image", "audio-frame-classification")
 
 
 def get_model_cls(model_type: str, task_type: str = "causal-lm"):
