@@ -1,8 +1,9 @@
 """FLUX application: four sub-applications (CLIP, T5, MMDiT backbone, VAE decoder) behind one pipeline object.
 
 reference: models/diffusers/flux/application.py (``NeuronFluxApplication``; context-parallel or CFG-parallel with dp=2 :33-65).
-On B200 every sub-model is an eager encoder-style module on the same device; the backbone is tensor parallel over heads, and
-``cfg_parallel`` splits a (conditional, unconditional) batch of 2 across the two halves of the world when true CFG is used."""
+On B200 every sub-model is an eager encoder-style module on the same device; the backbone is tensor parallel over heads.  With
+``world = 2 x tp`` the two replicas of the TP group either split the IMAGE TOKENS (``context_parallel_enabled``: queries local, keys /
+values all-gathered per attention) or the two branches of true classifier-free guidance (``cfg_parallel_enabled``)."""
 from __future__ import annotations
 
 import json
@@ -22,6 +23,13 @@ from .t5.modeling_t5 import NeuronT5EncoderModel, convert_t5_state_dict
 from .vae.modeling_vae import NeuronVAEDecoder, NeuronVAEEncoder, convert_vae_decoder_state_dict, convert_vae_encoder_state_dict
 
 
+def get_flux_parallelism_config(backbone_tp_degree: int, context_parallel_enabled: bool = False, cfg_parallel_enabled: bool = False) -> int:
+    """World size for a backbone TP degree: doubled when one of the two (mutually exclusive) dp=2 modes is on (reference :33-65)."""
+    if context_parallel_enabled and cfg_parallel_enabled:
+        raise ValueError("context_parallel_enabled and cfg_parallel_enabled are mutually exclusive")
+    return backbone_tp_degree * (2 if (context_parallel_enabled or cfg_parallel_enabled) else 1)
+
+
 def _ns(neuron_config, d: dict) -> InferenceConfig:
     ns = InferenceConfig.__new__(InferenceConfig)
     object.__setattr__(ns, "neuron_config", neuron_config)
@@ -36,12 +44,15 @@ class NeuronFluxApplication:
 
     def __init__(self, model_path: Optional[str], neuron_config: Optional[NeuronConfig] = None, backbone_config: Optional[dict] = None,
                  clip_config: Optional[dict] = None, t5_config: Optional[dict] = None, vae_config: Optional[dict] = None,
-                 height: int = 1024, width: int = 1024, task: str = "text-to-image"):
+                 height: int = 1024, width: int = 1024, task: str = "text-to-image", context_parallel_enabled: bool = False,
+                 cfg_parallel_enabled: bool = False):
         """``task``: ``text-to-image`` (FLUX.1 dev / schnell), ``control`` (Canny / Depth dev: backbone in_channels 128) or ``fill``
         (Fill dev: in_channels 384); the image-conditioned tasks also load the VAE encoder."""
         if task not in ("text-to-image", "control", "fill"):
             raise ValueError(f"unknown FLUX task {task}")
         self.task = task
+        self.context_parallel_enabled, self.cfg_parallel_enabled = context_parallel_enabled, cfg_parallel_enabled
+        get_flux_parallelism_config(1, context_parallel_enabled, cfg_parallel_enabled)          # validates exclusivity
         self.model_path = model_path
         self.neuron_config = neuron_config or NeuronConfig(batch_size=1, torch_dtype="bfloat16")
         self.height, self.width = height, width
@@ -66,9 +77,10 @@ class NeuronFluxApplication:
 
     def load(self, path: Optional[str] = None, random_weights: bool = False, seed: int = 0):
         nc = self.neuron_config
+        dp2 = self.context_parallel_enabled or self.cfg_parallel_enabled
         if nc.on_cpu or not torch.cuda.is_available():
             dev = torch.device("cpu")
-            if nc.tp_degree > 1:
+            if nc.tp_degree > 1 or dp2:
                 pstate.init_distributed("gloo")
         else:
             pstate.init_distributed("nccl")
@@ -109,6 +121,14 @@ class NeuronFluxApplication:
         if self.vae_encoder is not None:
             self.models.append(EncoderRunner("vae_encoder", self.vae_encoder, None, 0, dev))
             extra["vae_encoder"] = self.models[-1]
+        if dp2:
+            rep = pstate.get_data_parallel_group()
+            if rep.size != 2:
+                raise RuntimeError(f"context / CFG parallel need world = 2 x tp_degree ({2 * nc.tp_degree}); got {rep.size} replica(s)")
+            if self.context_parallel_enabled:
+                self.transformer.cp_group = rep
+            else:
+                extra["cfg_group"] = rep
         self.pipe = pipe_cls(self.models[2], self.models[0], self.models[1], self.models[3], FlowMatchEulerScheduler(),
                              2 ** (len(self.vae_config.block_out_channels) - 1), self.vae_config.latent_channels, dev, dt,
                              self.backbone_config.guidance_embeds, **extra)

@@ -15,6 +15,7 @@ from .... import ops
 from ....config import InferenceConfig, NeuronConfig
 from ....modules.gqa import GroupQueryAttention_O, GroupQueryAttention_QKV
 from ....modules.norm import RMSNorm
+from ....parallel import mappings
 from ....parallel.layers import ColumnParallelLinear, RowParallelLinear
 from ....parallel.state import get_tensor_model_parallel_group
 from ..embeddings import CombinedTimestepGuidanceTextProjEmbeddings, rope_nd
@@ -42,8 +43,14 @@ def _rope(x, cos, sin):
     return ops.apply_rope(x, cos, sin, True)
 
 
-def _attend(q, k, v, scale):
-    """Joint bidirectional attention over [text | image] tokens: the flash kernel's non-causal mode on CUDA."""
+def _attend(q, k, v, scale, cp=None):
+    """Joint bidirectional attention over [text | image] tokens: the flash kernel's non-causal mode on CUDA.
+    ``cp = (group, n_txt)``: context parallel — this rank holds all text tokens and ITS slice of the image tokens; keys / values of
+    the other slices are all-gathered (already rotated with their own positions), queries stay local."""
+    if cp is not None:
+        g, n = cp
+        k = torch.cat([k[:, :n], mappings.all_gather(k[:, n:].contiguous(), 1, g)], 1)
+        v = torch.cat([v[:, :n], mappings.all_gather(v[:, n:].contiguous(), 1, g)], 1)
     return ops.attention_prefill(q.contiguous(), k.contiguous(), v.contiguous(), scale, causal=False)
 
 
@@ -86,14 +93,14 @@ class FluxDoubleBlock(nn.Module):
         self.ff_context = _FF(dim, dtype, device)
         self.dim, self.scale = dim, hd ** -0.5
 
-    def forward(self, x, c, temb, cos, sin):
+    def forward(self, x, c, temb, cos, sin, cp=None):
         xn, (g_msa, sh_mlp, sc_mlp, g_mlp) = self.norm1(x, temb)
         cn, (cg_msa, csh_mlp, csc_mlp, cg_mlp) = self.norm1_context(c, temb)
         q, k, v = self.attn(xn)
         cq, ck, cv = self.attn_context(cn)
         Nc = c.shape[1]
         q, k, v = torch.cat([cq, q], 1), torch.cat([ck, k], 1), torch.cat([cv, v], 1)
-        o = _attend(_rope(q, cos, sin), _rope(k, cos, sin), v, self.scale)
+        o = _attend(_rope(q, cos, sin), _rope(k, cos, sin), v, self.scale, cp)
         B, N, H, D = o.shape
         o = o.reshape(B, N, H * D)
         x = x + g_msa * self.to_out(o[:, Nc:])
@@ -115,10 +122,10 @@ class FluxSingleBlock(nn.Module):
         self.proj_out_mlp = RowParallelLinear(4 * dim, dim, bias=False, input_is_parallel=True, dtype=dtype, device=device)
         self.scale = hd ** -0.5
 
-    def forward(self, x, temb, cos, sin):
+    def forward(self, x, temb, cos, sin, cp=None):
         xn, (gate,) = self.norm(x, temb)
         q, k, v = self.attn(xn)
-        o = _attend(_rope(q, cos, sin), _rope(k, cos, sin), v, self.scale)
+        o = _attend(_rope(q, cos, sin), _rope(k, cos, sin), v, self.scale, cp)
         B, N, H, D = o.shape
         m = nn.functional.gelu(self.proj_mlp(xn), approximate="tanh")
         return x + gate * (self.proj_out_attn(o.reshape(B, N, H * D)) + self.proj_out_mlp(m))
@@ -139,6 +146,7 @@ class NeuronFluxTransformer2DModel(nn.Module):
         self.single_transformer_blocks = nn.ModuleList([FluxSingleBlock(dim, heads, hd, dt, device) for _ in range(c.num_single_layers)])
         self.norm_out = AdaLayerNormContinuous(dim, dim, dt, device)
         self.proj_out = nn.Linear(dim, c.patch_size ** 2 * c.out_channels, dtype=dt, device=device)
+        self.cp_group = None            # set by the application when ``context_parallel_enabled`` (2 replicas of the TP group)
         for p in self.parameters():
             p.requires_grad_(False)
 
@@ -150,16 +158,22 @@ class NeuronFluxTransformer2DModel(nn.Module):
         temb = self.time_text_embed(timestep.to(dt) * 1000, None if guidance is None else guidance.to(dt) * 1000,
                                     pooled_projections.to(dt))
         c = self.context_embedder(encoder_hidden_states.to(dt))
+        cp, g = None, self.cp_group
+        if g is not None and g.size > 1:
+            n = x.shape[1] // g.size
+            assert n * g.size == x.shape[1], "image tokens must divide evenly over the context-parallel ranks"
+            x, img_ids = x[:, g.rank * n:(g.rank + 1) * n], img_ids[g.rank * n:(g.rank + 1) * n]
+            cp = (g, c.shape[1])
         ids = torch.cat([txt_ids, img_ids], 0)
         cos, sin = rope_nd(ids, self.config.axes_dims_rope)
         cos, sin = cos.unsqueeze(0).expand(x.shape[0], -1, -1), sin.unsqueeze(0).expand(x.shape[0], -1, -1)
         for blk in self.transformer_blocks:
-            x, c = blk(x, c, temb, cos, sin)
+            x, c = blk(x, c, temb, cos, sin, cp)
         h = torch.cat([c, x], 1)
         for blk in self.single_transformer_blocks:
-            h = blk(h, temb, cos, sin)
-        x = h[:, c.shape[1]:]
-        return self.proj_out(self.norm_out(x, temb))
+            h = blk(h, temb, cos, sin, cp)
+        x = self.proj_out(self.norm_out(h[:, c.shape[1]:], temb))
+        return x if cp is None else mappings.all_gather(x.contiguous(), 1, g)
 
 
 def convert_diffusers_flux_state_dict(sd: dict, config) -> dict:

@@ -9,6 +9,8 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
+from ....parallel import mappings
+
 
 def calculate_shift(seq_len, base_len=256, max_len=4096, base_shift=0.5, max_shift=1.15):
     m = (max_shift - base_shift) / (max_len - base_len)
@@ -53,18 +55,27 @@ def latent_image_ids(H2, W2, device):
 
 class NeuronFluxPipeline:
     def __init__(self, transformer: Callable, clip: Callable, t5: Callable, vae_decoder: Callable, scheduler=None,
-                 vae_scale_factor: int = 8, latent_channels: int = 16, device=None, dtype=torch.bfloat16, guidance_embeds=True):
+                 vae_scale_factor: int = 8, latent_channels: int = 16, device=None, dtype=torch.bfloat16, guidance_embeds=True,
+                 cfg_group=None):
+        self.cfg_group = cfg_group
         self.transformer, self.clip, self.t5, self.vae = transformer, clip, t5, vae_decoder
         self.scheduler = scheduler or FlowMatchEulerScheduler()
         self.vsf, self.lc, self.device, self.dtype, self.guidance_embeds = vae_scale_factor, latent_channels, device, dtype, guidance_embeds
 
     @torch.no_grad()
     def __call__(self, clip_input_ids, t5_input_ids, height=1024, width=1024, num_inference_steps=28, guidance_scale=3.5,
-                 generator=None, latents=None, output_type="pt", **cond_kw):
+                 generator=None, latents=None, output_type="pt", negative_clip_input_ids=None, negative_t5_input_ids=None,
+                 true_cfg_scale: float = 1.0, **cond_kw):
+        """``negative_*`` + ``true_cfg_scale > 1``: real classifier-free guidance, ``v = v_neg + s * (v_pos - v_neg)`` (two backbone
+        evaluations per step; with ``cfg_group`` of two replicas each computes one of them — the reference's CFG-parallel dp=2)."""
         dev = self.device
         B = clip_input_ids.shape[0]
         _, pooled = self.clip(clip_input_ids.to(dev))
         prompt = self.t5(t5_input_ids.to(dev))
+        true_cfg = true_cfg_scale > 1.0 and negative_t5_input_ids is not None
+        if true_cfg:
+            _, neg_pooled = self.clip((negative_clip_input_ids if negative_clip_input_ids is not None else clip_input_ids).to(dev))
+            neg_prompt = self.t5(negative_t5_input_ids.to(dev))
         H, W = 2 * (height // (self.vsf * 2)), 2 * (width // (self.vsf * 2))
         if latents is None:
             latents = torch.randn(B, self.lc, H, W, generator=generator, dtype=torch.float32).to(dev, self.dtype)
@@ -77,7 +88,17 @@ class NeuronFluxPipeline:
         for i, t in enumerate(ts):
             tt = (t / 1000).expand(B).to(dev)
             xin = x if cond is None else torch.cat([x, cond.to(x.dtype)], 2)
-            v = self.transformer(xin, prompt, pooled, tt, img_ids, txt_ids, g)
+            if not true_cfg:
+                v = self.transformer(xin, prompt, pooled, tt, img_ids, txt_ids, g)
+            elif self.cfg_group is not None and self.cfg_group.size == 2:
+                mine = (prompt, pooled) if self.cfg_group.rank == 0 else (neg_prompt, neg_pooled)
+                ntxt = torch.zeros(mine[0].shape[1], 3, device=dev)
+                both = mappings.all_gather(self.transformer(xin, mine[0], mine[1], tt, img_ids, ntxt, g).unsqueeze(0).contiguous(), 0, self.cfg_group)
+                v = both[1] + true_cfg_scale * (both[0] - both[1])
+            else:
+                vp = self.transformer(xin, prompt, pooled, tt, img_ids, txt_ids, g)
+                vn = self.transformer(xin, neg_prompt, neg_pooled, tt, img_ids, torch.zeros(neg_prompt.shape[1], 3, device=dev), g)
+                v = vn + true_cfg_scale * (vp - vn)
             x = self.scheduler.step(v.to(x.dtype), i, x)
         img = self.vae(unpack_latents(x, H, W))
         if output_type == "latent":

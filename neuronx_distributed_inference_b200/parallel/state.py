@@ -50,6 +50,7 @@ class _State:
     dp: Group = field(default_factory=lambda: Group([0]))
     dp_tp: Group = field(default_factory=lambda: Group([0]))
     kv_shared: Group = field(default_factory=lambda: Group([0]))  # flash-decoding KV group
+    replica: Group = field(default_factory=lambda: Group([0]))    # same shard in the other replicas of the TP group
     draft: Optional[Group] = None
     world: Group = field(default_factory=lambda: Group([0]))
     extra: Dict[str, Group] = field(default_factory=dict)
@@ -115,6 +116,8 @@ def initialize_model_parallel(tensor_model_parallel_size: int = 1, pipeline_mode
     st.world = Group(list(range(ws)), dist.group.WORLD, me)
     n_tp_groups = ws // tp
     st.tp = _make([list(range(g * tp, (g + 1) * tp)) for g in range(n_tp_groups)], me)
+    # replicas of the TP group (world = dp x tp): ranks holding the SAME shard (FLUX CFG- / context-parallel, reference dp=2)
+    st.replica = _make([[i + g * tp for g in range(n_tp_groups)] for i in range(tp)], me) if n_tp_groups > 1 else Group([me])
 
     def split(deg):
         """Within each TP group: ``deg`` blocks of tp/deg contiguous ranks -> (outer, inner)."""
@@ -207,6 +210,11 @@ def get_expert_model_parallel_rank() -> int:
 
 def get_moe_tp_group() -> Group:
     return _S.moe_tp
+
+
+def get_data_parallel_group() -> Group:
+    """Ranks that hold the same tensor-parallel shard in different replicas of the TP group (size = world / tp)."""
+    return _S.replica
 
 
 def get_world_group() -> Group:

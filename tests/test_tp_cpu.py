@@ -94,3 +94,14 @@ def test_weight_gathered_matmul_gloo():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
+
+
+@pytest.mark.parametrize("i,mode", [(0, "cp"), (1, "cfg")])
+def test_flux_dp2_context_and_cfg_parallel(i, mode):
+    """FLUX with world = 2 x tp (reference application.py:33-65): image tokens split over the two replicas (context parallel), or the
+    conditional / unconditional branches of true CFG split (CFG parallel) — both equal the single-replica result."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29580 + i), os.path.join(ROOT, "tests", "mp", "flux_dp2_worker.py"), mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
