@@ -15,10 +15,9 @@ import torch.nn as nn
 
 from ... import ops
 from ...models.image_to_text_model_base import ImageToTextInferenceConfig, NeuronBaseForImageToText
-from ...models.llama.modeling_llama import NeuronLlamaAttention, NeuronLlamaMLP, NeuronLlamaModel
+from ...models.llama.modeling_llama import NeuronLlamaMLP, NeuronLlamaModel
 from ...models.model_base import DecoderLayer
 from ...models.state_dict_utils import fuse_qkv_and_gate_up
-from ...modules.attention import AttentionBase
 from ...modules.kvcache.multimodal_kv_cache_manager import MultimodalKVCacheManager
 from ...modules.norm import RMSNorm
 from ...modules.vision import PatchEmbed

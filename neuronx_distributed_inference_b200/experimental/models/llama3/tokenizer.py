@@ -4,7 +4,7 @@ framing of the instruct models."""
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Literal, Optional, Sequence, TypedDict
+from typing import Dict, List, Literal, Sequence, TypedDict
 
 Role = Literal["system", "user", "assistant"]
 

@@ -14,7 +14,6 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.nn as nn
 
 from ...parallel import mappings
 from ...parallel.layers import ColumnParallelLinear
