@@ -18,7 +18,16 @@ def tiny_ckpt(tmp_path_factory):
     return save_random_hf_checkpoint(cfg, str(tmp_path_factory.mktemp("ckpt")))
 
 
+def _free_port(hint: int = 0) -> int:
+    """A currently unused TCP port on 127.0.0.1 (the fixed numbers in the tests are only hints: another job on the machine may own them)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _run(n, ckpt, port, **env_extra):
+    port = _free_port(port)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp", "llama_tp_worker.py"), ckpt, "cpu"]
     env = dict(os.environ, OMP_NUM_THREADS="2", **env_extra)
@@ -48,7 +57,7 @@ def test_llama_tp2_sequence_parallel_matches_hf(tiny_ckpt):
 
 def test_data_parallel_sampler_matches_distributed_sampler():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29545", os.path.join(ROOT, "tests", "mp", "dp_sampler_worker.py")]
+           "--master-port", str(_free_port(29545)), os.path.join(ROOT, "tests", "mp", "dp_sampler_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0 and '"ok": true' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
@@ -90,7 +99,7 @@ def test_gemma3_tp2_rolling_sliding_window_cache(tmp_path):
 def test_weight_gathered_matmul_gloo():
     """EAGLE weight-gather projections (reference eagle/utils.py:65-205): y = x @ all_gather(W)^T tiled over K / looped over N."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29575", os.path.join(ROOT, "tests", "mp", "weight_gather_worker.py")]
+           "--master-port", str(_free_port(29575)), os.path.join(ROOT, "tests", "mp", "weight_gather_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
@@ -101,7 +110,7 @@ def test_flux_dp2_context_and_cfg_parallel(i, mode):
     """FLUX with world = 2 x tp (reference application.py:33-65): image tokens split over the two replicas (context parallel), or the
     conditional / unconditional branches of true CFG split (CFG parallel) — both equal the single-replica result."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29580 + i), os.path.join(ROOT, "tests", "mp", "flux_dp2_worker.py"), mode]
+           "--master-port", str(_free_port(29580 + i)), os.path.join(ROOT, "tests", "mp", "flux_dp2_worker.py"), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
