@@ -22,12 +22,24 @@ def _hard_exit(code=0):
 
 
 def main():
+    """``<ckpt>`` and ``MODEL_TYPE`` may be comma-separated lists of equal length: the families run one after the other in the same
+    process group (saves the interpreter + import time of one torchrun per family)."""
     faulthandler.dump_traceback_later(int(os.environ.get('DUMP_AFTER', '240')), exit=True)
-    ckpt, dev = sys.argv[1], sys.argv[2]
+    ckpts, dev = sys.argv[1].split(","), sys.argv[2]
     dtype = sys.argv[3] if len(sys.argv) > 3 else ("float32" if dev == "cpu" else "bfloat16")
+    types = os.environ.get("MODEL_TYPE", "llama").split(",")
+    assert len(types) == len(ckpts)
+    for ckpt, mt in zip(ckpts, types):
+        run_one(ckpt, dev, dtype, mt)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.distributed.barrier()
+        _hard_exit()
+
+
+def run_one(ckpt, dev, dtype, model_type):
     from neuronx_distributed_inference_b200.config import NeuronConfig, OnDeviceSamplingConfig, load_pretrained_config
     from neuronx_distributed_inference_b200.utils.constants import get_model_cls
-    app_cls = get_model_cls(os.environ.get("MODEL_TYPE", "llama"))          # any registered causal-lm family
+    app_cls = get_model_cls(model_type)          # any registered causal-lm family
     from neuronx_distributed_inference_b200.parallel import state as pstate
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -86,12 +98,9 @@ def main():
                     seq = torch.cat([seq, toks[step][b].view(1, 1)], 1)
         tol = 2e-4 if dtype == "float32" else 4e-2
         ok = worst < tol
-        print(json.dumps({"world": world, "device": dev, "dtype": dtype, "worst_rel_err": worst, "ok": ok}))
+        print(json.dumps({"model_type": model_type, "world": world, "device": dev, "dtype": dtype, "worst_rel_err": worst, "ok": ok}), flush=True)
         if not ok:
-            sys.exit(1)
-    if world > 1:
-        torch.distributed.barrier()
-        _hard_exit()
+            os._exit(1)
 
 
 if __name__ == "__main__":

@@ -34,6 +34,7 @@ def _run(n, ckpt, port, **env_extra):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
+    return r.stdout
 
 
 def test_llama_tp2_gloo_matches_hf(tiny_ckpt):
@@ -75,13 +76,14 @@ def _contrib_cfg(name):
     return mod._cfg(name)
 
 
-@pytest.mark.parametrize("i,name", list(enumerate(["lfm2", "recurrent_gemma", "falcon_h1", "afmoe", "phimoe", "persimmon"])))
-def test_contrib_family_tp2_gloo_matches_hf(i, name, tmp_path):
+def test_contrib_families_tp2_gloo_match_hf(tmp_path):
     """The sharding metadata of the contrib blocks (3-way fused conv projection, head-sharded RG-LRU gates, replicated Mamba-2 mixer,
-    q-head-aligned attention gate, expert sharding, per-head LayerNorm) under a real 2-rank gloo group."""
+    q-head-aligned attention gate, expert sharding, per-head LayerNorm) under a real 2-rank gloo group — six families in one launch."""
     from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
-    ckpt = save_random_hf_checkpoint(_contrib_cfg(name), str(tmp_path / name), seed=4)
-    _run(2, ckpt, 29560 + i, MODEL_TYPE={"afmoe": "afmoe"}.get(name, name))
+    names = ["lfm2", "recurrent_gemma", "falcon_h1", "afmoe", "phimoe", "persimmon"]
+    ckpts = [save_random_hf_checkpoint(_contrib_cfg(n), str(tmp_path / n), seed=4) for n in names]
+    out = _run(2, ",".join(ckpts), 29560, MODEL_TYPE=",".join(names), DUMP_AFTER="500")
+    assert out.count('"ok": true') == len(names)
 
 
 def test_gemma3_tp2_rolling_sliding_window_cache(tmp_path):
