@@ -77,10 +77,11 @@ _B = "neuronx_distributed_inference_b200.contrib.models.backbone_ports"
 MODEL_TYPES.update({"minicpm": {"causal-lm": f"{_B}:NeuronMiniCPMForCausalLM"}, "internlm3": {"causal-lm": f"{_B}:NeuronInternLM3ForCausalLM"},
                     "orion": {"causal-lm": f"{_B}:NeuronOrionForCausalLM"}, "janus": {"causal-lm": f"{_B}:NeuronJanusForCausalLM"},
                     "ovis2_5": {"causal-lm": f"{_B}:NeuronOvis2_5ForCausalLM"},
-                    "qwen2_5_omni": {"causal-lm": f"{_B}:NeuronQwen2_5OmniForCausalLM"}})
+                    "qwen2_5_omni": {"causal-lm": f"{_B}:NeuronQwen2_5OmniForCausalLM",
+                                     "audio-text-to-text": "neuronx_distributed_inference_b200.contrib.models.qwen2_5_omni:NeuronQwen2_5OmniThinkerForCausalLM"}})
 MODEL_TYPES.update({"wav2vec2": {"audio-frame-classification":
                                  "neuronx_distributed_inference_b200.contrib.models.wav2vec2:NeuronWav2Vec2ForAudioFrameClassification"}})
-TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image", "audio-frame-classification")
+TASK_TYPES = ("causal-lm", "image-text-to-text", "speech-to-text", "text-to-image", "audio-frame-classification", "audio-text-to-text")
 
 
 def get_model_cls(model_type: str, task_type: str = "causal-lm"):
