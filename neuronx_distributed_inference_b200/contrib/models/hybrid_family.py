@@ -361,42 +361,83 @@ class NeuronRecurrentGemmaForCausalLM(NeuronLlamaForCausalLM):
 
 # ---------------------------------------------------------------------------------------------------------------------- Falcon-H1
 class Mamba2Mixer(nn.Module):
-    """Mamba-2 (SSD) block in recurrent form.  The mixer is small next to attention + MLP in these hybrids and its head / group
-    layout does not divide evenly in general, so it is REPLICATED across tensor-parallel ranks (no collective inside)."""
+    """Mamba-2 (SSD) block in recurrent form, tensor parallel over HEADS: rank ``r`` owns ``nh / tp`` heads — their gate / x rows of
+    ``in_proj``, their ``dt`` / ``A`` / ``D`` entries, the matching convolution channels and ``out_proj`` columns (one all-reduce at the
+    end) — plus the B / C rows of the group(s) those heads belong to (replicated among the ranks of a group when there are fewer groups
+    than ranks).  The gated RMSNorm is per group; when a group spans several ranks its sum of squares is combined across them."""
 
     def __init__(self, config, i, device=None):
         super().__init__()
+        from ...parallel.state import get_tensor_model_parallel_group
         dt = config.neuron_config.torch_dtype
         H = config.hidden_size
-        self.nh, self.hd, self.G, self.N = config.mamba_n_heads, config.mamba_d_head, config.mamba_n_groups, config.mamba_d_state
-        self.I = config.mamba_d_ssm if getattr(config, "mamba_d_ssm", None) is not None else int(config.mamba_expand * H)
-        assert self.I == self.nh * self.hd
-        self.K = config.mamba_d_conv
-        self.conv_dim = self.I + 2 * self.G * self.N
-        mk = lambda *shape: nn.Parameter(torch.zeros(*shape, dtype=dt, device=device), requires_grad=False)   # noqa: E731
-        self.in_proj = nn.Linear(H, self.I + self.conv_dim + self.nh, bias=bool(getattr(config, "mamba_proj_bias", False)), dtype=dt, device=device)
-        self.out_proj = nn.Linear(self.I, H, bias=bool(getattr(config, "projectors_bias", False)), dtype=dt, device=device)
-        self.conv_weight = mk(self.conv_dim, self.K)
-        self.conv_bias = mk(self.conv_dim) if getattr(config, "mamba_conv_bias", True) else None
-        self.dt_bias, self.A_log, self.D = mk(self.nh), mk(self.nh), mk(self.nh)
+        self.tp_group = g = get_tensor_model_parallel_group()
+        tp, r = g.size, g.rank
+        nh, hd, G, N = config.mamba_n_heads, config.mamba_d_head, config.mamba_n_groups, config.mamba_d_state
+        I = config.mamba_d_ssm if getattr(config, "mamba_d_ssm", None) is not None else int(config.mamba_expand * H)
+        assert I == nh * hd and nh % tp == 0 and nh % G == 0 and (G % tp == 0 or tp % G == 0), "Mamba-2 heads / groups vs tp degree"
+        self.nh, self.hd, self.N, self.K = nh // tp, hd, N, config.mamba_d_conv
+        self.G = max(G // tp, 1)                                   # groups whose B / C this rank needs
+        self.I = self.nh * hd
+        self.conv_dim = self.I + 2 * self.G * N
+        self.group_ranks = max(tp // G, 1)                          # ranks sharing one group (norm statistics are combined over them)
+        self.full_group_width = I // G
+        h0, g0 = r * self.nh, (r * G) // tp
+
+        def rows(t, width, start, count, base):                     # rows [base + start*width, base + (start+count)*width)
+            return t[base + start * width: base + (start + count) * width]
+
+        def shard_in(full, rank):                                   # [gate | x | B | C | dt] -> local slices, same order
+            hh, gg = rank * self.nh, (rank * G) // tp
+            return torch.cat([rows(full, hd, hh, self.nh, 0), rows(full, hd, hh, self.nh, I), rows(full, N, gg, self.G, 2 * I),
+                              rows(full, N, gg, self.G, 2 * I + G * N), rows(full, 1, hh, self.nh, 2 * I + 2 * G * N)], 0).contiguous()
+
+        def shard_conv(full, rank):                                 # [x | B | C]
+            hh, gg = rank * self.nh, (rank * G) // tp
+            return torch.cat([rows(full, hd, hh, self.nh, 0), rows(full, N, gg, self.G, I), rows(full, N, gg, self.G, I + G * N)], 0).contiguous()
+
+        def mk(*shape, shard=None):
+            p = nn.Parameter(torch.zeros(*shape, dtype=dt, device=device), requires_grad=False)
+            p.partition_dim, p.tp_group = 0, g
+            if shard is not None:
+                p.shard_fn = shard
+            return p
+        heads = lambda full, rank: full[rank * self.nh: (rank + 1) * self.nh].contiguous()                       # noqa: E731
+        chans = lambda full, rank: full[rank * self.I: (rank + 1) * self.I].contiguous()                         # noqa: E731
+        self.in_proj_weight = mk(self.I + self.conv_dim + self.nh, H, shard=shard_in)
+        self.in_proj_bias = mk(self.I + self.conv_dim + self.nh, shard=shard_in) if getattr(config, "mamba_proj_bias", False) else None
+        self.out_proj = RowParallelLinear(I, H, bias=bool(getattr(config, "projectors_bias", False)), input_is_parallel=True, dtype=dt, device=device)
+        self.conv_weight = mk(self.conv_dim, self.K, shard=shard_conv)
+        self.conv_bias = mk(self.conv_dim, shard=shard_conv) if getattr(config, "mamba_conv_bias", True) else None
+        self.dt_bias, self.A_log, self.D = mk(self.nh, shard=heads), mk(self.nh, shard=heads), mk(self.nh, shard=heads)
         self.gated_norm = bool(getattr(config, "mamba_rms_norm", False))
         self.norm_before_gate = bool(getattr(config, "mamba_norm_before_gate", True))
         if self.gated_norm:
-            self.norm_weight = mk(self.I)
+            self.norm_weight = mk(self.I, shard=chans)
         self.eps = config.rms_norm_eps
         lim = getattr(config, "time_step_limit", (0.0, float("inf")))
         self.dt_min, self.dt_max = float(lim[0]), float(lim[1])
-        for p in self.parameters():
-            p.requires_grad_(False)
         self.conv_state, self.ssm_state = f"m2_conv{i}", f"m2_ssm{i}"
+        del h0, g0
 
     def state_specs(self):
         return {self.conv_state: (self.K - 1, self.conv_dim), self.ssm_state: ((self.nh, self.hd, self.N), torch.float32)}
 
+    def _group_rms(self, y, B, T):
+        """RMS-normalise every group of ``full_group_width`` channels (local share: ``I / G_local``)."""
+        yg = y.view(B, T, self.G, self.I // self.G)
+        ss = yg.pow(2).sum(-1, keepdim=True)
+        if self.group_ranks > 1:                                    # my group is spread over ``group_ranks`` consecutive ranks
+            from ...parallel import mappings
+            allss = mappings.all_gather(ss.unsqueeze(0).contiguous(), 0, self.tp_group)                          # [tp, B, T, 1, 1]
+            first = (self.tp_group.rank // self.group_ranks) * self.group_ranks
+            ss = allss[first: first + self.group_ranks].sum(0)
+        return (yg * torch.rsqrt(ss / self.full_group_width + self.eps)).reshape(B, T, self.I)
+
     def forward(self, xn, meta, kv_mgr):
         B, T, _ = xn.shape
         K, nh, hd, G, N = self.K, self.nh, self.hd, self.G, self.N
-        gate, xBC, dt = self.in_proj(xn).split([self.I, self.conv_dim, nh], -1)
+        gate, xBC, dt = ops.linear(xn, self.in_proj_weight, self.in_proj_bias).split([self.I, self.conv_dim, nh], -1)
         lines = kv_mgr.lines_for(meta.seq_ids)
         states = kv_mgr.states
         w = self.conv_weight.t().unsqueeze(0)
@@ -438,9 +479,7 @@ class Mamba2Mixer(nn.Module):
         if self.gated_norm:
             if not self.norm_before_gate:
                 y = y * F.silu(gate.float())
-            yg = y.view(B, T, G, self.I // G)
-            yg = yg * torch.rsqrt(yg.pow(2).mean(-1, keepdim=True) + self.eps)
-            y = yg.reshape(B, T, self.I) * self.norm_weight.float()
+            y = self._group_rms(y, B, T) * self.norm_weight.float()
             if self.norm_before_gate:
                 y = y * F.silu(gate.float())
         else:
@@ -501,9 +540,9 @@ class NeuronFalconH1ForCausalLM(NeuronLlamaForCausalLM):
         for k, v in sd.items():
             k = k.replace(".feed_forward.", ".mlp.").replace("final_layernorm.", "norm.")
             if k.endswith(".mamba.in_proj.weight"):
-                v = sc(v, mup.view(-1, 1) * g("ssm_in_multiplier"))
+                k, v = k.replace(".in_proj.weight", ".in_proj_weight"), sc(v, mup.view(-1, 1) * g("ssm_in_multiplier"))
             elif k.endswith(".mamba.in_proj.bias"):
-                v = sc(v, mup)
+                k, v = k.replace(".in_proj.bias", ".in_proj_bias"), sc(v, mup)
             elif k.endswith(".mamba.out_proj.weight") or k.endswith(".mamba.out_proj.bias"):
                 v = sc(v, g("ssm_out_multiplier"))
             elif k.endswith(".mamba.conv1d.weight"):

@@ -122,9 +122,9 @@ def _cfg(name):
     if name == "recurrent_gemma":
         return T.RecurrentGemmaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=1,
                                       vocab_size=160, lru_width=64, attention_window_size=8, head_dim=16, tie_word_embeddings=False)
-    if name in ("falcon_h1", "falcon_h1_gated_norm"):
-        return T.FalconH1Config(**BASE, mamba_d_ssm=64, mamba_n_heads=4, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=8, mamba_d_conv=4,
-                                mamba_chunk_size=8, mamba_rms_norm=name.endswith("gated_norm"), attention_in_multiplier=0.7,
+    if name in ("falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group"):
+        return T.FalconH1Config(**BASE, mamba_d_ssm=64, mamba_n_heads=4, mamba_d_head=16, mamba_n_groups=1 if name.endswith("one_group") else 2,
+                                mamba_d_state=8, mamba_d_conv=4, mamba_chunk_size=8, mamba_rms_norm=not name.endswith("falcon_h1"), attention_in_multiplier=0.7,
                                 attention_out_multiplier=1.3, key_multiplier=0.6, embedding_multiplier=2.0, lm_head_multiplier=0.5,
                                 mlp_multipliers=[0.8, 1.2], ssm_in_multiplier=1.1, ssm_out_multiplier=0.9,
                                 ssm_multipliers=[0.9, 1.1, 0.8, 1.2, 0.7], tie_word_embeddings=False)
@@ -140,7 +140,8 @@ def _cfg(name):
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "afmoe", "openai-gpt"])
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "afmoe",
+                                  "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
     from neuronx_distributed_inference_b200.contrib.models.llama_family import CONTRIB_MODEL_TYPES
@@ -151,7 +152,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     from neuronx_distributed_inference_b200.contrib.models.moe_family import MOE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.more_families import MORE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.hybrid_family import HYBRID_MODEL_TYPES
-    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_gated_norm", "")]
+    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_gated_norm", "").replace("_one_group", "")]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
