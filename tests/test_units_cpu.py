@@ -319,3 +319,40 @@ def test_reference_import_paths_resolve():
         m = importlib.import_module(P + mod)
         for n in names:
             assert hasattr(m, n), f"{mod}.{n}"
+
+
+def test_diffusers_padder_activations_and_small_utils():
+    """reference models/diffusers/{padder,activations}.py, utils/decorator_peeling.py, models/image_to_text_model_wrapper.py"""
+    import functools
+    import pytest
+    from neuronx_distributed_inference_b200.models.diffusers.activations import FP32SiLU, NeuronGELU, get_activation
+    from neuronx_distributed_inference_b200.models.diffusers.padder import MaybePadder, pad, pad_interleaved, pad_sizes, round_up_to_divisor
+    from neuronx_distributed_inference_b200.models.image_to_text_model_wrapper import ImageToTextModelWrapper, VisionModelWrapper
+    from neuronx_distributed_inference_b200.utils.decorator_peeling import peel_decorations
+    assert round_up_to_divisor(24, 16) == 32 and round_up_to_divisor(32, 16) == 32
+    assert pad_sizes((2, 3, 4), [0, 2], [5, 6]) == (0, 2, 0, 0, 0, 3) and pad_sizes((2, 3), 1, 5, left=True) == (2, 0, 0, 0)
+    assert pad(torch.ones(2, 3), 1, 5).tolist() == [[1, 1, 1, 0, 0]] * 2 and pad(None, 0, 3) is None
+    assert pad_interleaved(torch.tensor([1, 2, 3]), 0, 9, 1, 2).tolist() == [1, 0, 0, 2, 0, 0, 3, 0, 0]
+    # 6 heads of width 2 padded to 8 heads for TP=2: every half gets 3 real heads + 1 zero head
+    w = torch.arange(1, 13.0).view(12, 1).expand(12, 4).contiguous()
+    p = MaybePadder(16, "interleaved", split_size=6, interleaved_factor=2)(w, 0)
+    assert p.shape == (16, 4) and p[:, 0].tolist() == [1, 2, 3, 4, 5, 6, 0, 0, 7, 8, 9, 10, 11, 12, 0, 0]
+    assert MaybePadder(5)(torch.ones(3, 2), 0).shape == (5, 2) and MaybePadder(5)(None, 0) is None
+    g = NeuronGELU(8, 16, approximate="tanh")
+    x = torch.randn(3, 8)
+    assert torch.allclose(g(x), torch.nn.functional.gelu(torch.nn.functional.linear(x, g.proj.weight, g.proj.bias), approximate="tanh"))
+    h = torch.randn(4, dtype=torch.bfloat16)
+    assert FP32SiLU()(h).dtype == torch.bfloat16 and isinstance(get_activation("swish"), torch.nn.SiLU)
+    with pytest.raises(ValueError):
+        get_activation("nope")
+
+    def deco(f):
+        @functools.wraps(f)
+        def inner(*a):
+            return f(*a) + 1
+        return inner
+
+    def base(v):
+        return v
+    assert peel_decorations(deco(deco(base))) is base and deco(deco(base))(1) == 3
+    assert ImageToTextModelWrapper.__name__ == "SubModelRunner" and VisionModelWrapper.__name__ == "EncoderRunner"
