@@ -356,3 +356,30 @@ def test_diffusers_padder_activations_and_small_utils():
         return v
     assert peel_decorations(deco(deco(base))) is base and deco(deco(base))(1) == 3
     assert ImageToTextModelWrapper.__name__ == "SubModelRunner" and VisionModelWrapper.__name__ == "EncoderRunner"
+
+
+def test_learned_sink_input_processor_and_version(tmp_path):
+    from neuronx_distributed_inference_b200 import _version
+    from neuronx_distributed_inference_b200.modules.attention.sink import LearnedSink
+    from neuronx_distributed_inference_b200.ops import reference as ref
+    from neuronx_distributed_inference_b200.utils.input_processor import build_messages, prepare_generation_inputs_hf
+    assert _version.__version__.count(".") == 2
+    # the stand-alone sink module == the sink handling of the reference attention op
+    sk = LearnedSink(1, 4)
+    sk.sink.copy_(torch.tensor([0.5, -1.0, 2.0, 0.0]))
+    q, k, v = torch.randn(2, 4, 3, 8), torch.randn(2, 4, 5, 8), torch.randn(2, 4, 5, 8)
+    mask = torch.ones(2, 1, 3, 5, dtype=torch.bool)
+    p = sk(q @ k.transpose(-1, -2) * 0.3)
+    assert torch.allclose(p @ v, ref.attention_with_mask(q, k, v, mask, 0.3, sk.get_sink()), atol=1e-5) and (p.sum(-1) < 1).all()
+    img = tmp_path / "x.jpg"
+    img.write_bytes(b"\\xff\\xd8fake")
+    msgs = build_messages("describe", [str(img), "https://host/y.png"])
+    kinds = [c["type"] for c in msgs[0]["content"]]
+    assert kinds == ["image", "image", "text"] and msgs[0]["content"][0]["url"].startswith("data:image/jpeg;base64,")
+
+    class FakeProcessor:
+        def apply_chat_template(self, messages, **kw):
+            assert kw["add_generation_prompt"] and kw["return_dict"]
+            return {"input_ids": torch.ones(1, 4, dtype=torch.long), "attention_mask": torch.ones(1, 4), "pixel_values": torch.zeros(1, 3, 2, 2), "unused": None}
+    ids, m, extra = prepare_generation_inputs_hf("describe", str(img), FakeProcessor())
+    assert ids.shape == (1, 4) and set(extra) == {"pixel_values"}
