@@ -71,3 +71,44 @@ def test_mxfp4_roundtrip_and_gpt_oss_conversion():
     sd = dequantize_mxfp4_state_dict({"layers.0.mlp.experts.down_proj_blocks": blocks, "layers.0.mlp.experts.down_proj_scales": scales})
     assert sd["layers.0.mlp.experts.down_proj"].shape == (3, 64, 8)
     assert pack_fp4_x4_uint16(torch.tensor([[1, 2, 3, 15]])).item() == 1 | (2 << 4) | (3 << 8) | (15 << 12)
+
+
+def test_llama4_fp8_checkpoint_expert_fusion():
+    """reference models/llama4/conversion_script/preprocess_llama4_FP8.py: per-expert fp8 weights + per-channel scales -> fused bf16
+    ``experts.gate_up_proj [E, H, 2I]`` / ``down_proj [E, I, H]`` (and the --keep-fp8 variant with fused scales)."""
+    import torch
+    from neuronx_distributed_inference_b200.models.llama4.conversion_script.preprocess_llama4_fp8 import dequantize_dense, fuse_layer_experts
+    torch.manual_seed(0)
+    E, H, I = 3, 16, 8
+    f8 = torch.float8_e4m3fn
+
+    def q(shape):
+        w = torch.randn(*shape)
+        s = w.abs().amax(1, keepdim=True) / 448.0
+        return (w / s).to(f8), s.to(torch.bfloat16)
+    sd, ref = {}, {}
+    p = "language_model.model.layers.1."
+    for e in range(E):
+        for name, shape in (("gate_proj", (I, H)), ("up_proj", (I, H)), ("down_proj", (H, I))):
+            w, s = q(shape)
+            sd[f"{p}feed_forward.experts.{e}.{name}.weight"], sd[f"{p}feed_forward.experts.{e}.{name}.weight_scale"] = w, s
+            ref[(e, name)] = w.float() * s.float()
+    w, s = q((I, H))
+    sd[p + "feed_forward.shared_expert.gate_proj.weight"], sd[p + "feed_forward.shared_expert.gate_proj.weight_scale"] = w, s
+    keep = {k: v.clone() for k, v in sd.items()}
+    assert fuse_layer_experts(sd, p, E) and not fuse_layer_experts(sd, "language_model.model.layers.0.", E)
+    gu, dn = sd[p + "feed_forward.experts.gate_up_proj"], sd[p + "feed_forward.experts.down_proj"]
+    assert gu.shape == (E, H, 2 * I) and dn.shape == (E, I, H) and gu.dtype == torch.bfloat16
+    x = torch.randn(5, H)
+    for e in range(E):
+        g, u = (x @ gu[e].float()).chunk(2, -1)
+        exp_g, exp_u = x @ ref[(e, "gate_proj")].t(), x @ ref[(e, "up_proj")].t()
+        assert torch.allclose(g, exp_g, atol=0.1, rtol=2e-2) and torch.allclose(u, exp_u, atol=0.1, rtol=2e-2)
+        assert torch.allclose(dn[e].float(), ref[(e, "down_proj")].t(), atol=2e-2, rtol=2e-2)
+    assert not any(".experts.0." in k for k in sd) and dequantize_dense(sd) == 1
+    assert sd[p + "feed_forward.shared_expert.gate_proj.weight"].dtype == torch.bfloat16
+    # fp8 kept: fused weights stay e4m3fn, scales are fused alongside and reproduce the same values
+    assert fuse_layer_experts(keep, p, E, keep_fp8=True)
+    gu8, gs = keep[p + "feed_forward.experts.gate_up_proj"], keep[p + "feed_forward.experts.gate_up_proj.scale"]
+    assert gu8.dtype == f8 and gu8.shape == (E, H, 2 * I) and gs.shape == (E, 1, 2 * I)
+    assert torch.allclose(gu8.float() * gs, gu.float(), atol=2e-2, rtol=2e-2)
