@@ -383,3 +383,25 @@ def test_learned_sink_input_processor_and_version(tmp_path):
             return {"input_ids": torch.ones(1, 4, dtype=torch.long), "attention_mask": torch.ones(1, 4), "pixel_values": torch.zeros(1, 3, 2, 2), "unused": None}
     ids, m, extra = prepare_generation_inputs_hf("describe", str(img), FakeProcessor())
     assert ids.shape == (1, 4) and set(extra) == {"pixel_values"}
+
+
+@pytest.mark.parametrize("past_len,seq_len", [(6, 1), (0, 5)])
+def test_module_from_model_decoder_layer_orchestrator(past_len, seq_len, tmp_path):
+    """reference module_test/{base_template,module_from_model_template}: ONE decoder layer of the HF model vs the same layer of the
+    engine on shared random inputs and a shared pre-filled KV cache (decode step), or without a cache (prefill)."""
+    import transformers as T
+    from neuronx_distributed_inference_b200.config import load_pretrained_config
+    from neuronx_distributed_inference_b200.models.llama.modeling_llama import NeuronLlamaForCausalLM as A
+    from neuronx_distributed_inference_b200.module_test import DecoderLayerFromModelOrchestrator, OrchestratorConfig
+    from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+    ckpt = save_random_hf_checkpoint(T.LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                                   num_key_value_heads=2, vocab_size=128, max_position_embeddings=128), str(tmp_path / "m"), seed=1)
+    hf = T.AutoModelForCausalLM.from_pretrained(ckpt, dtype=torch.float32)
+
+    def factory(device):
+        nc = A.get_neuron_config_cls()(batch_size=2, seq_len=32, max_context_length=16, torch_dtype="float32", on_cpu=device == "cpu")
+        app = A(ckpt, A.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
+        return app.load(None, skip_warmup=True)
+    orch = DecoderLayerFromModelOrchestrator(hf, factory, OrchestratorConfig(past_len=past_len, seq_len=seq_len, layer_idx=1, rtol=1e-4, atol=1e-4))
+    rep = orch.run_validation(devices=("cpu",))
+    assert rep["cpu"] < 1e-3
