@@ -91,10 +91,11 @@ class ExpertMLPs(nn.Module):
                 p.partition_dim = 0
         else:
             self.gate_up_bias = self.down_bias = None
+        self.gate_up_scale = self.down_scale = None        # set by quantization.convert (weight-only int8 / fp8 experts)
 
     def forward(self, x2: torch.Tensor, topk_w: torch.Tensor, topk_i: torch.Tensor, scale_input: bool = False) -> torch.Tensor:
         return ops.moe_experts(x2, self.gate_up_proj, self.down_proj, topk_w, topk_i, self.act, self.expert_offset,
-                               self.gate_up_bias, self.down_bias, self.act_fn, scale_input)
+                               self.gate_up_bias, self.down_bias, self.act_fn, scale_input, self.gate_up_scale, self.down_scale)
 
 
 class MoE(nn.Module):

@@ -300,8 +300,11 @@ def moe_route(router_logits, top_k, act="softmax", normalize=True, act_over_topk
 
 
 def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_offset=0,
-                gate_up_bias=None, down_bias=None, act_fn=None, scale_input=False):
+                gate_up_bias=None, down_bias=None, act_fn=None, scale_input=False, gate_up_scale=None, down_scale=None):
     N = x.shape[0]
+    if gate_up_scale is not None or down_scale is not None:      # 8-bit experts: dequantise the selected experts on the fly
+        return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias, act_fn, scale_input,
+                               gate_up_scale, down_scale)
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and w_gate_up.dtype == x.dtype and act == "silu_mul"
             and act_fn is None and gate_up_bias is None and down_bias is None and N <= GEMV_MAX_TOKENS and not scale_input
             and w_gate_up.is_contiguous() and w_down.is_contiguous() and topk_i.dim() == 2

@@ -282,7 +282,7 @@ def moe_route(router_logits, top_k: int, act: str = "softmax", normalize: bool =
 
 
 def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act: str = "silu_mul", expert_offset: int = 0,
-                gate_up_bias=None, down_bias=None, act_fn=None, scale_input: bool = False):
+                gate_up_bias=None, down_bias=None, act_fn=None, scale_input: bool = False, gate_up_scale=None, down_scale=None):
     """Dropless expert MLPs.  x [N,H]; w_gate_up [E_local, 2I, H] ([gate; up] rows, K-major like nn.Linear — the
     reference stores [E,H,2I]; K-major is what TMA/UMMA and the GEMV kernels stream); w_down
     [E_local, H, I]; experts owned here are [expert_offset, expert_offset+E_local).
@@ -301,10 +301,14 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act: str = "silu_mul", exp
             xin = (xin.float() * wt.unsqueeze(-1)).to(x.dtype)
             wt = torch.ones_like(wt)
         h = F.linear(xin, w_gate_up[e].to(x.dtype))
+        if gate_up_scale is not None:      # weight-only 8-bit experts: per-(expert, output channel) scale applied to the GEMM output
+            h = (h.float() * gate_up_scale[e].float()).to(x.dtype)
         if gate_up_bias is not None:
             h = h + gate_up_bias[e].to(h.dtype)
         h = act_fn(h) if act_fn is not None else activation(h, act)
         y = F.linear(h, w_down[e].to(x.dtype))
+        if down_scale is not None:
+            y = (y.float() * down_scale[e].float()).to(x.dtype)
         if down_bias is not None:
             y = y + down_bias[e].to(y.dtype)
         out[tok] += y.float() * wt.unsqueeze(-1)

@@ -112,3 +112,41 @@ def test_llama4_fp8_checkpoint_expert_fusion():
     gu8, gs = keep[p + "feed_forward.experts.gate_up_proj"], keep[p + "feed_forward.experts.gate_up_proj.scale"]
     assert gu8.dtype == f8 and gu8.shape == (E, H, 2 * I) and gs.shape == (E, 1, 2 * I)
     assert torch.allclose(gu8.float() * gs, gu.float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("qdtype", ["int8", "f8e4m3"])
+def test_mixtral_expert_wise_quantized_checkpoint_flow(qdtype, tmp_path):
+    """``expert_wise_per_channel_symmetric``: the MoE expert banks are stored 8-bit with one scale per expert and output
+    channel, attention projections per channel; the quantised model tracks the fp32 one."""
+    from transformers import MixtralConfig
+    from neuronx_distributed_inference_b200.models.mixtral.modeling_mixtral import NeuronMixtralForCausalLM as A
+    from neuronx_distributed_inference_b200.quantization.convert import quantize_experts
+    w = torch.randn(3, 8, 16)
+    q, s = quantize_experts(w, torch.int8)
+    assert q.dtype == torch.int8 and s.shape == (3, 8) and ((q.float() * s.unsqueeze(-1) - w).abs().max() / w.abs().max()) < 0.02
+    cfg = MixtralConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=160,
+                        max_position_embeddings=128, num_local_experts=4, num_experts_per_tok=2)
+    ckpt = save_random_hf_checkpoint(cfg, str(tmp_path / "ck"), seed=0)
+    qpath = str(tmp_path / "q")
+
+    def build(quantized):
+        nc = A.get_neuron_config_cls()(batch_size=1, seq_len=32, max_context_length=16, torch_dtype="float32", on_cpu=True, output_logits=True,
+                                       quantized=quantized, quantized_checkpoints_path=qpath if quantized else None,
+                                       quantization_type="expert_wise_per_channel_symmetric", quantization_dtype=qdtype,
+                                       modules_to_not_convert=["lm_head"])
+        c = A.get_config_cls()(nc, load_config=load_pretrained_config(ckpt))
+        return A(ckpt, c), c
+    qapp, qcfg = build(True)
+    A.save_quantized_state_dict(ckpt, qcfg)
+    qapp.load(None, skip_warmup=True)
+    ex = qapp.model.layers[0].mlp.expert_mlps
+    want = torch.int8 if qdtype == "int8" else torch.float8_e4m3fn
+    assert ex.gate_up_proj.dtype == want and ex.down_proj.dtype == want
+    assert ex.gate_up_scale.shape == (4, 256) and ex.down_scale.shape == (4, 64) and ex.gate_up_scale.dtype == torch.float32
+    assert not torch.all(ex.gate_up_scale == 1) and qapp.model.layers[0].self_attn.qkv_proj.weight.dtype == want
+    fapp, _ = build(False)
+    fapp.load(None, skip_warmup=True)
+    ids = torch.randint(1, 160, (1, 9))
+    lq, lf = qapp(ids).logits[:, -1].float(), fapp(ids).logits[:, -1].float()
+    rel = ((lq - lf).norm() / lf.norm()).item()
+    assert rel < (0.03 if qdtype == "int8" else 0.12), rel
