@@ -7,6 +7,8 @@
   (sliding-window, MQA, half-rotary) attention block; Gemma norms / embedding scale / GeGLU with biases / logit soft-cap.
   RG-LRU: ``a = exp(-8 * sigmoid(W_a x) * softplus(L))``, ``h_t = a_t h_{t-1} + sqrt(1 - a_t^2) * (sigmoid(W_i x) * x_t)`` with
   block-diagonal (per head) gate matrices; the state is fp32 and reset at position 0.
+* **Bamba** — Mamba-2 layers with a few GQA attention layers (half-rotary) in between, SwiGLU after every mixer; the mixer gates first
+  and then applies one RMSNorm over the whole inner width.
 * **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
   multipliers everywhere (all linear, folded into the weights at load).  Mamba-2: ``h_t = exp(dt_t A) h_{t-1} + dt_t B_t x_t``,
   ``y_t = C_t h_t + D x_t`` per head with grouped B/C, causal conv4 + SiLU in front, gated (grouped) RMSNorm or SiLU gate behind.
@@ -39,10 +41,10 @@ class _HybridModel(NeuronLlamaModel):
     graph_safe = False
 
     def kv_heads_per_rank(self):
-        return next(l.self_attn.n_kv for l in self.layers if hasattr(l, "self_attn"))
+        return next((l.self_attn.n_kv for l in self.layers if hasattr(l, "self_attn")), 1)      # attention-free stacks keep a token KV cache
 
     def kv_head_dim(self):
-        return next(l.self_attn.head_dim for l in self.layers if hasattr(l, "self_attn"))
+        return next((l.self_attn.head_dim for l in self.layers if hasattr(l, "self_attn")), 8)
 
     def init_inference_optimization(self, config):
         super().init_inference_optimization(config)
@@ -366,7 +368,9 @@ class Mamba2Mixer(nn.Module):
     end) — plus the B / C rows of the group(s) those heads belong to (replicated among the ranks of a group when there are fewer groups
     than ranks).  The gated RMSNorm is per group; when a group spans several ranks its sum of squares is combined across them."""
 
-    def __init__(self, config, i, device=None):
+    def __init__(self, config, i, device=None, gated_norm=None, norm_before_gate=None, norm_groups=None, out_bias=None):
+        """The keyword overrides cover the checkpoint families that share this block: Falcon-H1 (grouped norm after / before the gate,
+        optional), Bamba / Granite-4 (gate first, ONE RMSNorm over the whole inner width)."""
         super().__init__()
         from ...parallel.state import get_tensor_model_parallel_group
         dt = config.neuron_config.torch_dtype
@@ -380,8 +384,11 @@ class Mamba2Mixer(nn.Module):
         self.G = max(G // tp, 1)                                   # groups whose B / C this rank needs
         self.I = self.nh * hd
         self.conv_dim = self.I + 2 * self.G * N
-        self.group_ranks = max(tp // G, 1)                          # ranks sharing one group (norm statistics are combined over them)
-        self.full_group_width = I // G
+        NG = G if norm_groups is None else norm_groups             # groups of the gated RMSNorm (may differ from the B / C groups)
+        assert NG % tp == 0 or tp % NG == 0
+        self.norm_G = max(NG // tp, 1)
+        self.group_ranks = max(tp // NG, 1)                         # ranks sharing one norm group (statistics are combined over them)
+        self.full_group_width = I // NG
         h0, g0 = r * self.nh, (r * G) // tp
 
         def rows(t, width, start, count, base):                     # rows [base + start*width, base + (start+count)*width)
@@ -406,12 +413,13 @@ class Mamba2Mixer(nn.Module):
         chans = lambda full, rank: full[rank * self.I: (rank + 1) * self.I].contiguous()                         # noqa: E731
         self.in_proj_weight = mk(self.I + self.conv_dim + self.nh, H, shard=shard_in)
         self.in_proj_bias = mk(self.I + self.conv_dim + self.nh, shard=shard_in) if getattr(config, "mamba_proj_bias", False) else None
-        self.out_proj = RowParallelLinear(I, H, bias=bool(getattr(config, "projectors_bias", False)), input_is_parallel=True, dtype=dt, device=device)
+        ob = bool(getattr(config, "projectors_bias", False)) if out_bias is None else bool(out_bias)
+        self.out_proj = RowParallelLinear(I, H, bias=ob, input_is_parallel=True, dtype=dt, device=device)
         self.conv_weight = mk(self.conv_dim, self.K, shard=shard_conv)
         self.conv_bias = mk(self.conv_dim, shard=shard_conv) if getattr(config, "mamba_conv_bias", True) else None
         self.dt_bias, self.A_log, self.D = mk(self.nh, shard=heads), mk(self.nh, shard=heads), mk(self.nh, shard=heads)
-        self.gated_norm = bool(getattr(config, "mamba_rms_norm", False))
-        self.norm_before_gate = bool(getattr(config, "mamba_norm_before_gate", True))
+        self.gated_norm = bool(getattr(config, "mamba_rms_norm", False)) if gated_norm is None else bool(gated_norm)
+        self.norm_before_gate = bool(getattr(config, "mamba_norm_before_gate", True)) if norm_before_gate is None else bool(norm_before_gate)
         if self.gated_norm:
             self.norm_weight = mk(self.I, shard=chans)
         self.eps = config.rms_norm_eps
@@ -425,7 +433,7 @@ class Mamba2Mixer(nn.Module):
 
     def _group_rms(self, y, B, T):
         """RMS-normalise every group of ``full_group_width`` channels (local share: ``I / G_local``)."""
-        yg = y.view(B, T, self.G, self.I // self.G)
+        yg = y.view(B, T, self.norm_G, self.I // self.norm_G)
         ss = yg.pow(2).sum(-1, keepdim=True)
         if self.group_ranks > 1:                                    # my group is spread over ``group_ranks`` consecutive ranks
             from ...parallel import mappings
@@ -575,4 +583,84 @@ class NeuronFalconH1ForCausalLM(NeuronLlamaForCausalLM):
         pass
 
 
-HYBRID_MODEL_TYPES = {"falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Bamba
+class BambaLayer(nn.Module):
+    mlp_is_moe = False
+
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        dt = config.neuron_config.torch_dtype
+        kinds = getattr(config, "layers_block_type", None)
+        self.is_attn = (kinds[i] == "attention") if kinds else (i in (getattr(config, "attn_layer_indices", None) or []))
+        if self.is_attn:
+            b = bool(getattr(config, "attention_bias", False))
+            self.self_attn = NeuronLlamaAttention(config, i, rotary, device=device, qkv_bias=b, o_bias=b)
+        else:
+            pb = bool(getattr(config, "mamba_proj_bias", False))
+            self.mamba = Mamba2Mixer(config, i, device, gated_norm=True, norm_before_gate=False, norm_groups=1, out_bias=pb)
+        self.mlp = GatedMLP(config.hidden_size, config.intermediate_size, config.hidden_act, dt, bias=bool(getattr(config, "mlp_bias", False)),
+                            device=device)
+        self.input_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)
+        self.pre_ff_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return {} if self.is_attn else self.mamba.state_specs()
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.input_layernorm
+        if self.is_attn:
+            h = self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+        else:
+            h = h + self.mamba(n(h), meta, kv_mgr)
+        n = self.pre_ff_layernorm
+        return self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+
+
+class BambaInferenceConfig(LlamaInferenceConfig):
+    def add_derived_config(self):
+        if getattr(self, "mamba_d_ssm", None) is None:
+            self.mamba_d_ssm = int(getattr(self, "mamba_expand", 2) * self.hidden_size)
+        super().add_derived_config()
+
+
+class NeuronBambaModel(_HybridModel):
+    def make_rotary(self, config, device):
+        from ...models.llama.modeling_llama import rope_scaling_of, rope_theta_of
+        from ...modules.rope import RotaryEmbedding
+        rp = getattr(config, "rope_parameters", None) or {}
+        frac = (rp.get("partial_rotary_factor") if isinstance(rp, dict) else None) or getattr(config, "partial_rotary_factor", None) or 1.0
+        return RotaryEmbedding(int(config.head_dim * float(frac)), max(config.max_position_embeddings, config.neuron_config.seq_len),
+                               rope_theta_of(config), rope_scaling_of(config), device=device)
+
+    def make_layer(self, config, i, rotary, device):
+        return BambaLayer(config, i, rotary, device)
+
+
+class NeuronBambaForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronBambaModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return BambaInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            k = k.replace(".feed_forward.", ".mlp.").replace("final_layernorm.", "norm.")
+            if k.endswith(".mamba.in_proj.weight"):
+                k = k.replace(".in_proj.weight", ".in_proj_weight")
+            elif k.endswith(".mamba.in_proj.bias"):
+                k = k.replace(".in_proj.bias", ".in_proj_bias")
+            elif k.endswith(".mamba.conv1d.weight"):
+                k, v = k.replace(".conv1d.weight", ".conv_weight"), v.squeeze(1)
+            elif k.endswith(".mamba.conv1d.bias"):
+                k = k.replace(".conv1d.bias", ".conv_bias")
+            elif k.endswith(".mamba.norm.weight"):
+                k = k.replace(".mamba.norm.weight", ".mamba.norm_weight")
+            out[k] = v
+        return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
+
+
+HYBRID_MODEL_TYPES = {"bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

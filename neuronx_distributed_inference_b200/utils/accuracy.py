@@ -40,14 +40,15 @@ class TokenMatchingError(AssertionError):
 # ---- goldens ------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def generate_expected_logits(hf_model, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor],
-                             num_tokens: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                             num_tokens: int, use_cache: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Greedy HF generation on CPU.  -> (logits [num_tokens, B, V] fp32, tokens [B, num_tokens]).
     Rows may be right padded (``attention_mask``); each row is run unpadded so HF sees clean inputs."""
     B = input_ids.shape[0]
     if attention_mask is None:
         attention_mask = torch.ones_like(input_ids)
     import inspect
-    has_cache = "past_key_values" in inspect.signature(hf_model.forward).parameters
+    # ``use_cache=False``: recompute the whole prefix every step (an oracle that does not depend on the HF cache implementation)
+    has_cache = use_cache and "past_key_values" in inspect.signature(hf_model.forward).parameters
     all_logits, all_tokens = [], []
     for b in range(B):
         n = int(attention_mask[b].sum())

@@ -134,13 +134,18 @@ def _cfg(name):
                              route_scale=1.5, layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"])
     if name == "openai-gpt":
         return T.OpenAIGPTConfig(n_embd=64, n_layer=3, n_head=4, vocab_size=160, n_positions=256)
+    if name == "bamba":
+        return T.BambaConfig(**BASE, mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=8, mamba_d_conv=4, mamba_expand=2,
+                             attn_layer_indices=[1], mamba_chunk_size=8, tie_word_embeddings=False, pad_token_id=0,
+                             rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=1.0))
+        # (transformers 5.5 rotates the full head whatever the factor says: compare at the common setting)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "afmoe",
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "afmoe",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -160,7 +165,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     ids = torch.randint(1, hf_cfg.vocab_size, (2, 14), generator=g)
     mask = torch.ones_like(ids)
     mask[1, 10:] = 0
-    exp, toks = generate_expected_logits(hf, ids, mask, 10)
+    # transformers 5.5's CACHED Bamba decode drifts 5e-3 from its own full recompute; use the cache-free oracle there
+    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=name != "bamba")
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"
