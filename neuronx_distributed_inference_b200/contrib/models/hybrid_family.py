@@ -9,6 +9,8 @@
   block-diagonal (per head) gate matrices; the state is fp32 and reset at position 0.
 * **Bamba** — Mamba-2 layers with a few GQA attention layers (half-rotary) in between, SwiGLU after every mixer; the mixer gates first
   and then applies one RMSNorm over the whole inner width.
+* **Granite-4.0 hybrid (``granitemoehybrid``)** — Bamba-style Mamba-2 / attention stack (RoPE or no positions at all) with the Granite
+  multipliers and, per layer, an always-on shared SwiGLU plus an optional top-k MoE.
 * **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
   multipliers everywhere (all linear, folded into the weights at load).  Mamba-2: ``h_t = exp(dt_t A) h_{t-1} + dt_t B_t x_t``,
   ``y_t = C_t h_t + D x_t`` per head with grouped B/C, causal conv4 + SiLU in front, gated (grouped) RMSNorm or SiLU gate behind.
@@ -663,4 +665,110 @@ class NeuronBambaForCausalLM(NeuronLlamaForCausalLM):
         return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
 
 
-HYBRID_MODEL_TYPES = {"bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Granite-4.0 hybrid
+class GraniteHybridLayer(nn.Module):
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        from ...modules.moe import ExpertMLPs, MoE, RouterTopK, SharedExperts
+        dt, H = config.neuron_config.torch_dtype, config.hidden_size
+        self.is_attn = config.layers_block_type[i] != "mamba"
+        if self.is_attn:
+            b = bool(getattr(config, "attention_bias", False))
+            self.self_attn = NeuronLlamaAttention(config, i, rotary, device=device, qkv_bias=b, o_bias=b,
+                                                  use_rope=getattr(config, "position_embedding_type", "rope") == "rope",
+                                                  softmax_scale=float(getattr(config, "attention_multiplier", None) or config.head_dim ** -0.5))
+        else:
+            pb = bool(getattr(config, "mamba_proj_bias", False))
+            self.mamba = Mamba2Mixer(config, i, device, gated_norm=True, norm_before_gate=False, norm_groups=1, out_bias=pb)
+        n_exp = int(getattr(config, "num_local_experts", 0) or 0)
+        self.mlp_is_moe = n_exp > 0
+        if self.mlp_is_moe:
+            self.mlp = MoE(RouterTopK(n_exp, config.num_experts_per_tok, H, dt, "softmax", False, True, False, device),
+                           ExpertMLPs(n_exp, H, config.intermediate_size, config.hidden_act, dt, device=device),
+                           SharedExperts(H, config.shared_intermediate_size, config.hidden_act, dt, device))
+        else:
+            self.mlp = GatedMLP(H, config.shared_intermediate_size, config.hidden_act, dt, device=device)
+        self.input_layernorm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.post_attention_layernorm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return {} if self.is_attn else self.mamba.state_specs()
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.input_layernorm
+        if self.is_attn:
+            h = self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+        else:
+            h = h + self.mamba(n(h), meta, kv_mgr)
+        n = self.post_attention_layernorm
+        return self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+
+
+class GraniteHybridInferenceConfig(BambaInferenceConfig):
+    @classmethod
+    def get_neuron_config_cls(cls):
+        from ...config import MoENeuronConfig
+        return MoENeuronConfig
+
+
+class NeuronGraniteHybridModel(_HybridModel):
+    def make_layer(self, config, i, rotary, device):
+        return GraniteHybridLayer(config, i, rotary, device)
+
+    def init_model(self, config):
+        super().init_model(config)
+        self.embed_scale = float(getattr(config, "embedding_multiplier", 1.0))
+
+
+class NeuronGraniteHybridForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronGraniteHybridModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return GraniteHybridInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        """The residual multiplier scales the OUTPUT of every residual branch (mixer out-projection, shared MLP and expert down
+        projections) and the logits scaling divides the head: folded into those weights, as for dense Granite."""
+        rm, ls = float(getattr(config, "residual_multiplier", 1.0)), float(getattr(config, "logits_scaling", 1.0))
+        moe = int(getattr(config, "num_local_experts", 0) or 0) > 0
+        sc = lambda t, f: (t.float() * f).to(t.dtype)                                             # noqa: E731
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".mamba.in_proj.weight"):
+                k = k.replace(".in_proj.weight", ".in_proj_weight")
+            elif k.endswith(".mamba.in_proj.bias"):
+                k = k.replace(".in_proj.bias", ".in_proj_bias")
+            elif k.endswith(".mamba.conv1d.weight"):
+                k, v = k.replace(".conv1d.weight", ".conv_weight"), v.squeeze(1)
+            elif k.endswith(".mamba.conv1d.bias"):
+                k = k.replace(".conv1d.bias", ".conv_bias")
+            elif k.endswith(".mamba.norm.weight"):
+                k = k.replace(".mamba.norm.weight", ".mamba.norm_weight")
+            elif ".mamba.out_proj." in k or ".self_attn.o_proj." in k:
+                v = sc(v, rm)
+            elif k.endswith(".shared_mlp.input_linear.weight"):
+                k = k.replace(".shared_mlp.input_linear.weight", ".mlp.shared_experts.gate_up_proj.weight" if moe else ".mlp.gate_up_proj.weight")
+            elif k.endswith(".shared_mlp.output_linear.weight"):
+                k, v = k.replace(".shared_mlp.output_linear.weight", ".mlp.shared_experts.down_proj.weight" if moe else ".mlp.down_proj.weight"), sc(v, rm)
+            elif k.endswith(".block_sparse_moe.input_linear.weight"):
+                k = k.replace(".block_sparse_moe.input_linear.weight", ".mlp.expert_mlps.gate_up_proj")
+            elif k.endswith(".block_sparse_moe.output_linear.weight"):
+                k, v = k.replace(".block_sparse_moe.output_linear.weight", ".mlp.expert_mlps.down_proj"), sc(v, rm)
+            elif k.endswith(".block_sparse_moe.router.layer.weight"):
+                k, v = k.replace(".block_sparse_moe.router.layer.weight", ".mlp.router.linear_router.weight"), v.float()
+            out[k] = v
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        out["lm_head.weight"] = sc(out["lm_head.weight"], 1.0 / ls)
+        return out
+
+    @staticmethod
+    def update_state_dict_for_tied_weights(sd):
+        pass
+
+
+HYBRID_MODEL_TYPES = {"granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

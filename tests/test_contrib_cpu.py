@@ -139,13 +139,22 @@ def _cfg(name):
                              attn_layer_indices=[1], mamba_chunk_size=8, tie_word_embeddings=False, pad_token_id=0,
                              rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=1.0))
         # (transformers 5.5 rotates the full head whatever the factor says: compare at the common setting)
+    if name in ("granitemoehybrid", "granitemoehybrid_dense_nope"):
+        dense = name.endswith("nope")
+        return T.GraniteMoeHybridConfig(hidden_size=64, intermediate_size=32, shared_intermediate_size=96, num_hidden_layers=3, num_attention_heads=4,
+                                        num_key_value_heads=2, vocab_size=160, max_position_embeddings=256,
+                                        layers_block_type=["mamba", "attention", "mamba"], num_local_experts=0 if dense else 4, num_experts_per_tok=2,
+                                        mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=8, mamba_d_conv=4, mamba_expand=2,
+                                        mamba_chunk_size=8, position_embedding_type="nope" if dense else "rope", embedding_multiplier=3.0,
+                                        attention_multiplier=0.2, residual_multiplier=0.5, logits_scaling=4.0, tie_word_embeddings=False)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("name", ["phi3", "granite", "smollm3", "seed_oss", "olmo2", "gemma2", "glm4", "starcoder2", "stablelm", "cohere",
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
-                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "afmoe",
+                                  "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
+                                  "granitemoehybrid_dense_nope", "afmoe",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -157,7 +166,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     from neuronx_distributed_inference_b200.contrib.models.moe_family import MOE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.more_families import MORE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.hybrid_family import HYBRID_MODEL_TYPES
-    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_gated_norm", "").replace("_one_group", "")]
+    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_gated_norm", "").replace("_one_group", "").replace("_dense_nope", "")]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
@@ -166,7 +175,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     mask = torch.ones_like(ids)
     mask[1, 10:] = 0
     # transformers 5.5's CACHED Bamba decode drifts 5e-3 from its own full recompute; use the cache-free oracle there
-    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=name != "bamba")
+    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid")))
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"
