@@ -339,6 +339,8 @@ def test_diffusers_padder_activations_and_small_utils():
     assert p.shape == (16, 4) and p[:, 0].tolist() == [1, 2, 3, 4, 5, 6, 0, 0, 7, 8, 9, 10, 11, 12, 0, 0]
     assert MaybePadder(5)(torch.ones(3, 2), 0).shape == (5, 2) and MaybePadder(5)(None, 0) is None
     g = NeuronGELU(8, 16, approximate="tanh")
+    g.proj.weight.normal_()                       # parallel layers allocate with torch.empty: give the test defined values
+    g.proj.bias.normal_()
     x = torch.randn(3, 8)
     assert torch.allclose(g(x), torch.nn.functional.gelu(torch.nn.functional.linear(x, g.proj.weight, g.proj.bias), approximate="tanh"))
     h = torch.randn(4, dtype=torch.bfloat16)
