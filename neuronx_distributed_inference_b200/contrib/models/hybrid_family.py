@@ -53,6 +53,8 @@ class _HybridModel(NeuronLlamaModel):
         nc = self.neuron_config
         if nc.is_block_kv_layout or nc.speculation_length or nc.is_medusa or nc.is_chunked_prefill or nc.attention_dp_degree > 1:
             raise NotImplementedError("hybrid recurrent layers: contiguous KV cache, one token per decode step")
+        if nc.padding_side != "right":
+            raise NotImplementedError("hybrid recurrent layers take right-padded prompts (the state after the LAST VALID token is kept)")
         specs = {}
         for layer in self.layers:
             specs.update(getattr(layer, "state_specs", dict)())
