@@ -120,8 +120,11 @@ class IdeficsBlock(nn.Module):
         super().__init__()
         self.cross_attn_block = cross
         self.decoder = decoder
-        self.self_attn = decoder.self_attn              # the engine sizes the KV cache from ``layers[0].self_attn``
         self.layer_idx = decoder.layer_idx
+
+    @property
+    def self_attn(self):                                # the engine sizes the KV cache from ``layers[0].self_attn``
+        return self.decoder.self_attn
 
     def forward(self, h, meta, kv_mgr, lora=None):
         if self.cross_attn_block is not None:
