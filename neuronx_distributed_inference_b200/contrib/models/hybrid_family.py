@@ -11,6 +11,7 @@
   and then applies one RMSNorm over the whole inner width.
 * **Granite-4.0 hybrid (``granitemoehybrid``)** — Bamba-style Mamba-2 / attention stack (RoPE or no positions at all) with the Granite
   multipliers and, per layer, an always-on shared SwiGLU plus an optional top-k MoE.
+* **Mamba-2 (Codestral-Mamba)** — attention-free: ``h += mixer(norm(h))`` per layer; the engine keeps a token-sized dummy KV cache.
 * **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
   multipliers everywhere (all linear, folded into the weights at load).  Mamba-2: ``h_t = exp(dt_t A) h_{t-1} + dt_t B_t x_t``,
   ``y_t = C_t h_t + D x_t`` per head with grouped B/C, causal conv4 + SiLU in front, gated (grouped) RMSNorm or SiLU gate behind.
@@ -773,4 +774,76 @@ class NeuronGraniteHybridForCausalLM(NeuronLlamaForCausalLM):
         pass
 
 
-HYBRID_MODEL_TYPES = {"granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Mamba-2
+class Mamba2InferenceConfig(LlamaInferenceConfig):
+    attribute_map = {"num_heads": "mamba_n_heads", "state_size": "mamba_d_state", "n_groups": "mamba_n_groups",
+                     "conv_kernel": "mamba_d_conv", "expand": "mamba_expand", "layer_norm_epsilon": "rms_norm_eps",
+                     "use_conv_bias": "mamba_conv_bias", "use_bias": "mamba_proj_bias"}
+
+    def get_required_attributes(self):
+        return ["hidden_size", "num_hidden_layers", "vocab_size", "mamba_n_heads", "mamba_d_state"]
+
+    def add_derived_config(self):
+        self.mamba_d_head = self.head_dim                                   # the checkpoint's head_dim is the SSM head width
+        self.mamba_d_ssm = self.mamba_n_heads * self.mamba_d_head
+        self.num_attention_heads = self.num_key_value_heads = 1            # no attention: placeholders for the KV-cache plumbing
+        self.head_dim, self.intermediate_size = 8, self.hidden_size
+        self.max_position_embeddings = getattr(self, "max_position_embeddings", None) or self.neuron_config.seq_len
+        if not hasattr(self, "hidden_act") or self.hidden_act is None:
+            self.hidden_act = "silu"
+        super().add_derived_config()
+
+
+class Mamba2Layer(nn.Module):
+    mlp_is_moe = False
+
+    def __init__(self, config, i, device=None):
+        super().__init__()
+        pb = bool(getattr(config, "mamba_proj_bias", False))
+        self.mixer = Mamba2Mixer(config, i, device, gated_norm=bool(getattr(config, "rms_norm", True)), norm_before_gate=False, norm_groups=1,
+                                 out_bias=pb)
+        self.norm = RMSNorm(config.hidden_size, config.rms_norm_eps, config.neuron_config.torch_dtype, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return self.mixer.state_specs()
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        return h + self.mixer(self.norm(h), meta, kv_mgr)
+
+
+class NeuronMamba2Model(_HybridModel):
+    def make_layer(self, config, i, rotary, device):
+        return Mamba2Layer(config, i, device)
+
+
+class NeuronMamba2ForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronMamba2Model
+    _STATE_DICT_MODEL_PREFIX = "backbone."
+
+    @classmethod
+    def get_config_cls(cls):
+        return Mamba2InferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            k = k.replace("embeddings.", "embed_tokens.").replace("norm_f.", "norm.")
+            if k.endswith(".mixer.in_proj.weight"):
+                k = k.replace(".in_proj.weight", ".in_proj_weight")
+            elif k.endswith(".mixer.in_proj.bias"):
+                k = k.replace(".in_proj.bias", ".in_proj_bias")
+            elif k.endswith(".mixer.conv1d.weight"):
+                k, v = k.replace(".conv1d.weight", ".conv_weight"), v.squeeze(1)
+            elif k.endswith(".mixer.conv1d.bias"):
+                k = k.replace(".conv1d.bias", ".conv_bias")
+            elif k.endswith(".mixer.norm.weight"):
+                k = k.replace(".mixer.norm.weight", ".mixer.norm_weight")
+            out[k] = v
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+HYBRID_MODEL_TYPES = {"mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
