@@ -1,8 +1,7 @@
-"""reference utils/decorator_peeling.py: reach the original function under a stack of ``functools.wraps`` decorators."""
+"""Undo ``functools.wraps`` decoration chains (role of the reference's utils/decorator_peeling.py)."""
+import inspect
 
 
 def peel_decorations(decorated_function):
-    fn = decorated_function
-    while hasattr(fn, "__wrapped__"):
-        fn = fn.__wrapped__
-    return fn
+    """The innermost callable under any number of ``functools.wraps``-style wrappers (follows ``__wrapped__`` links)."""
+    return inspect.unwrap(decorated_function)
