@@ -178,3 +178,30 @@ def test_sampling_param_inference_and_dp_validation():
     validate_tp_prefill_to_dp_decode(num_kv_heads=8, world_size=32, dp_degree=4)      # 4 ranks replicate each KV head
     with pytest.raises(ValueError):
         validate_tp_prefill_to_dp_decode(num_kv_heads=8, world_size=8, dp_degree=2)
+
+
+def test_continuous_batching_scheduler_example_matches_isolated_generation():
+    """examples/continuous_batching_demo.py: staggered arrivals, more requests than cache lines, line reuse, masked idle rows — every
+    request must produce exactly what it produces when it runs alone."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("cb_demo", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                            "examples", "continuous_batching_demo.py"))
+    demo = importlib.util.module_from_spec(spec)
+    sys_modules_guard = spec.name
+    import sys
+    sys.modules[sys_modules_guard] = demo
+    spec.loader.exec_module(demo)
+    kw = dict(seq_len=64, max_context_length=16, device="cpu", dtype="float32", seed=9)
+    app = build_random_llama(TINY, batch_size=3, is_continuous_batching=True, ctx_batch_size=1, kv_cache_batch_size=3, apply_seq_ids_mask=True, **kw)
+    g = torch.Generator().manual_seed(1)
+    reqs = [demo.Request(i, torch.randint(1, 128, (int(torch.randint(3, 12, (1,), generator=g)),), generator=g).tolist(),
+                         int(torch.randint(2, 9, (1,), generator=g)), arrival_step=i) for i in range(7)]
+    done = demo.ContinuousBatcher(app).run(reqs)
+    assert [r.rid for r in done] == list(range(7)) and len({r.line for r in done}) <= 3
+    solo = build_random_llama(TINY, batch_size=1, **kw)
+    for r in done:
+        solo.reset()
+        ids = torch.tensor([r.prompt])
+        exp = _greedy(solo, ids, r.max_new_tokens - 1)[0].tolist() if r.max_new_tokens > 1 else [int(solo(ids, attention_mask=torch.ones_like(ids)).tokens)]
+        assert r.output == exp[: r.max_new_tokens], r.rid
