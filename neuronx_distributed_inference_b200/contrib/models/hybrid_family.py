@@ -13,7 +13,9 @@
   multipliers and, per layer, an always-on shared SwiGLU plus an optional top-k MoE.
 * **Mamba-2 (Codestral-Mamba)** — attention-free: ``h += mixer(norm(h))`` per layer; the engine keeps a token-sized dummy KV cache.
 * **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
-  multipliers everywhere (all linear, folded into the weights at load).  Mamba-2: ``h_t = exp(dt_t A) h_{t-1} + dt_t B_t x_t``,
+  multipliers everywhere (all linear, folded into the weights at load).
+* **Nemotron-H / Nemotron-3-Nano (``nemotron_h``)** — ONE mixer per block (Mamba-2 with a grouped gated norm, GQA attention without
+  positions, squared-ReLU MLP, or a sigmoid-routed MoE of non-gated squared-ReLU experts + a shared expert).  Mamba-2: ``h_t = exp(dt_t A) h_{t-1} + dt_t B_t x_t``,
   ``y_t = C_t h_t + D x_t`` per head with grouped B/C, causal conv4 + SiLU in front, gated (grouped) RMSNorm or SiLU gate behind.
 reference ports: contrib/models/{lfm2-2.6b, recurrentgemma-2b-it, Falcon-H1-0.5B-Instruct}/src."""
 from __future__ import annotations
@@ -846,4 +848,141 @@ class NeuronMamba2ForCausalLM(NeuronLlamaForCausalLM):
         return out
 
 
-HYBRID_MODEL_TYPES = {"mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Nemotron-H
+class _SharedPlainMLP(nn.Module):
+    """Non-gated always-on expert (``down(act(up(x)))``); output left un-reduced like :class:`SharedExperts`."""
+
+    def __init__(self, hidden_size, intermediate_size, act, dtype, device=None):
+        super().__init__()
+        from ...modules.mlp import _PLAIN_ACT
+        self.act = _PLAIN_ACT[act]
+        self.up_proj = ColumnParallelLinear(hidden_size, intermediate_size, bias=False, gather_output=False, dtype=dtype, device=device)
+        self.down_proj = RowParallelLinear(intermediate_size, hidden_size, bias=False, dtype=dtype, device=device, reduce_output=False)
+
+    def forward(self, x2, reduce: bool = False):
+        return self.down_proj(ops.activation(self.up_proj(x2), self.act))
+
+
+class NemotronHInferenceConfig(LlamaInferenceConfig):
+    """NVIDIA Nemotron-H / Nemotron-3-Nano: one mixer per block — Mamba-2, attention WITHOUT positions, squared-ReLU MLP or a
+    DeepSeek-style sigmoid-routed MoE of NON-gated squared-ReLU experts plus one always-on shared expert."""
+    attribute_map = {"mamba_num_heads": "mamba_n_heads", "mamba_head_dim": "mamba_d_head", "n_groups": "mamba_n_groups",
+                     "ssm_state_size": "mamba_d_state", "conv_kernel": "mamba_d_conv", "layer_norm_epsilon": "rms_norm_eps",
+                     "use_conv_bias": "mamba_conv_bias", "use_bias": "mamba_proj_bias"}
+    _PATTERN = {"M": "mamba", "*": "attention", "-": "mlp", "E": "moe"}
+
+    def get_required_attributes(self):
+        return ["hidden_size", "vocab_size", "num_attention_heads", "mamba_n_heads", "mamba_d_head", "mamba_d_state"]
+
+    def add_derived_config(self):
+        if not getattr(self, "layers_block_type", None):                    # original checkpoints: "M-M-M*-..." pattern string
+            self.layers_block_type = [self._PATTERN[c] for c in self.hybrid_override_pattern]
+        self.num_hidden_layers = len(self.layers_block_type)
+        self.mamba_d_ssm = self.mamba_n_heads * self.mamba_d_head
+        self.hidden_act = getattr(self, "mlp_hidden_act", "relu2")
+        if getattr(self, "moe_latent_size", None) is not None:
+            raise NotImplementedError("Nemotron-H latent-projected experts (moe_latent_size)")
+        if getattr(self, "mlp_bias", False):
+            raise NotImplementedError("Nemotron-H with MLP biases")
+        super().add_derived_config()
+
+    @classmethod
+    def get_neuron_config_cls(cls):
+        from ...config import MoENeuronConfig
+        return MoENeuronConfig
+
+
+class NemotronHLayer(nn.Module):
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        from ...models.deepseek.modeling_deepseek import DeepseekRouter
+        from ...modules.mlp import PlainMLP
+        from ...modules.moe import ExpertMLPs, MoE
+        dt, H, act = config.neuron_config.torch_dtype, config.hidden_size, config.hidden_act
+        self.kind = config.layers_block_type[i]
+        self.mlp_is_moe = self.kind == "moe"
+        if self.kind == "attention":
+            b = bool(getattr(config, "attention_bias", False))
+            self.self_attn = NeuronLlamaAttention(config, i, rotary, device=device, qkv_bias=b, o_bias=b, use_rope=False)
+        elif self.kind == "mamba":
+            self.mamba = Mamba2Mixer(config, i, device, gated_norm=True, norm_before_gate=False, norm_groups=config.mamba_n_groups,
+                                     out_bias=bool(getattr(config, "mamba_proj_bias", False)))
+        elif self.kind == "moe":
+            experts = ExpertMLPs(config.n_routed_experts, H, config.moe_intermediate_size, act, dt, device=device, gated=False)
+            self.mlp = MoE(DeepseekRouter(config, device), experts,
+                           _SharedPlainMLP(H, config.moe_shared_expert_intermediate_size, act, dt, device))
+        elif self.kind == "mlp":
+            self.mlp = PlainMLP(H, config.intermediate_size, act, dt, bias=False, device=device)
+        else:
+            raise ValueError(f"unknown Nemotron-H block type {self.kind!r}")
+        self.norm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return self.mamba.state_specs() if self.kind == "mamba" else {}
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.norm
+        if self.kind == "attention":
+            return self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+        if self.kind == "mamba":
+            return h + self.mamba(n(h), meta, kv_mgr)
+        if self.kind == "moe":
+            return self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+        return self.mlp(n(h), residual=h)
+
+
+class NeuronNemotronHModel(_HybridModel):
+    def make_layer(self, config, i, rotary, device):
+        return NemotronHLayer(config, i, rotary, device)
+
+
+class NeuronNemotronHForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronNemotronHModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return NemotronHInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        kinds, out = config.layers_block_type, {}
+        ren = {"mamba": [(".mixer.in_proj.weight", ".mamba.in_proj_weight"), (".mixer.in_proj.bias", ".mamba.in_proj_bias"),
+                         (".mixer.conv1d.weight", ".mamba.conv_weight"), (".mixer.conv1d.bias", ".mamba.conv_bias"),
+                         (".mixer.norm.weight", ".mamba.norm_weight"), (".mixer.", ".mamba.")],
+               "attention": [(".mixer.", ".self_attn.")],
+               "mlp": [(".mixer.up_proj.", ".mlp.fc1."), (".mixer.down_proj.", ".mlp.fc2.")],
+               "moe": [(".mixer.gate.weight", ".mlp.router.linear_router.weight"),
+                       (".mixer.gate.e_score_correction_bias", ".mlp.router.e_score_correction_bias"),
+                       (".mixer.experts.up_proj", ".mlp.expert_mlps.gate_up_proj"), (".mixer.experts.down_proj", ".mlp.expert_mlps.down_proj"),
+                       (".mixer.shared_experts.", ".mlp.shared_experts.")]}
+        sd = {(k[len("backbone."):] if k.startswith("backbone.") else k): v for k, v in sd.items()}   # NVIDIA's on-disk prefix
+        for i, kind in enumerate(kinds):                                    # on disk the experts are separate Linear modules
+            for proj in ("up_proj", "down_proj") if kind == "moe" else ():
+                ws = [sd.pop(f"layers.{i}.mixer.experts.{e}.{proj}.weight", None) for e in range(config.n_routed_experts)]
+                if ws[0] is not None:
+                    sd[f"layers.{i}.mixer.experts.{proj}"] = torch.stack(ws)
+        for k, v in sd.items():
+            k = k.replace("embeddings.", "embed_tokens.").replace("embedding.", "embed_tokens.").replace("norm_f.", "norm.")
+            if k.startswith("layers.") and ".mixer." in k:
+                kind = kinds[int(k.split(".")[1])]
+                for a, b in ren[kind]:
+                    if a in k:
+                        k = k.replace(a, b)
+                        break
+                if k.endswith(".mamba.conv_weight"):
+                    v = v.squeeze(1)
+                if ".mlp.router." in k:
+                    v = v.float()
+            out[k] = v
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers, fuse_mlp=False)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+    @staticmethod
+    def update_state_dict_for_tied_weights(sd):
+        pass
+
+
+HYBRID_MODEL_TYPES = {"nemotron_h": NeuronNemotronHForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

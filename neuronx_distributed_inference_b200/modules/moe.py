@@ -49,8 +49,11 @@ class RouterTopK(nn.Module):
 class ExpertMLPs(nn.Module):
     def __init__(self, num_experts: int, hidden_size: int, intermediate_size: int, hidden_act: str = "silu",
                  dtype=torch.float32, bias: bool = False, device=None, ep_group: Optional[Group] = None,
-                 moe_tp_group: Optional[Group] = None, act_fn: Optional[Callable] = None):
+                 moe_tp_group: Optional[Group] = None, act_fn: Optional[Callable] = None, gated: bool = True):
+        """``gated=False``: plain two-matrix experts ``down(act(up(x)))`` (Nemotron-H / Nemotron-3: squared ReLU); ``gate_up_proj`` is then
+        just the up projection ``[E, I, H]``."""
         super().__init__()
+        self.gated = gated
         self.ep_group = ep_group or get_expert_model_parallel_group()
         self.tp_group = moe_tp_group or get_moe_tp_group()
         ep, tp = self.ep_group.size, self.tp_group.size
@@ -58,9 +61,13 @@ class ExpertMLPs(nn.Module):
         self.num_experts, self.E_local = num_experts, num_experts // ep
         self.I_local = intermediate_size // tp
         self.expert_offset = self.ep_group.rank * self.E_local
-        self.act = {"silu": "silu_mul", "swish": "silu_mul", "gelu": "gelu_mul", "gelu_pytorch_tanh": "gelu_tanh_mul"}[hidden_act]
+        if gated:
+            self.act = {"silu": "silu_mul", "swish": "silu_mul", "gelu": "gelu_mul", "gelu_pytorch_tanh": "gelu_tanh_mul"}[hidden_act]
+        else:
+            self.act = {"swish": "silu", "gelu_pytorch_tanh": "gelu_tanh"}.get(hidden_act, hidden_act)
         self.act_fn = act_fn
-        self.gate_up_proj = nn.Parameter(torch.empty(self.E_local, 2 * self.I_local, hidden_size, dtype=dtype, device=device),
+        nproj = 2 if gated else 1
+        self.gate_up_proj = nn.Parameter(torch.empty(self.E_local, nproj * self.I_local, hidden_size, dtype=dtype, device=device),
                                          requires_grad=False)
         self.down_proj = nn.Parameter(torch.empty(self.E_local, hidden_size, self.I_local, dtype=dtype, device=device),
                                       requires_grad=False)
@@ -68,8 +75,7 @@ class ExpertMLPs(nn.Module):
 
         def shard_gu(full, rank):
             e = full[E0:E0 + El]
-            g, u = e.chunk(2, 1)
-            return torch.cat([g.chunk(tps, 1)[tpr], u.chunk(tps, 1)[tpr]], 1).contiguous()
+            return torch.cat([h.chunk(tps, 1)[tpr] for h in e.chunk(nproj, 1)], 1).contiguous()
 
         def shard_dn(full, rank):
             return full[E0:E0 + El].chunk(tps, 2)[tpr].contiguous()
@@ -79,11 +85,11 @@ class ExpertMLPs(nn.Module):
             p.tp_group = get_tensor_model_parallel_group()
             p.partition_dim = 0
         if bias:
-            self.gate_up_bias = nn.Parameter(torch.zeros(self.E_local, 2 * self.I_local, dtype=dtype, device=device),
+            self.gate_up_bias = nn.Parameter(torch.zeros(self.E_local, nproj * self.I_local, dtype=dtype, device=device),
                                              requires_grad=False)
             self.down_bias = nn.Parameter(torch.zeros(self.E_local, hidden_size, dtype=dtype, device=device), requires_grad=False)
             self.gate_up_bias.shard_fn = lambda full, rank: torch.cat(
-                [h.chunk(tps, 1)[tpr] for h in full[E0:E0 + El].chunk(2, 1)], 1).contiguous()
+                [h.chunk(tps, 1)[tpr] for h in full[E0:E0 + El].chunk(nproj, 1)], 1).contiguous()
             # the down bias must be added once: only the first I-shard carries it
             self.down_bias.shard_fn = lambda full, rank: (full[E0:E0 + El] if tpr == 0 else torch.zeros_like(full[E0:E0 + El]))
             for p in (self.gate_up_bias, self.down_bias):

@@ -64,7 +64,7 @@ MODEL_TYPES.update({
     "codegen": {"causal-lm": f"{_X}:NeuronCodeGenForCausalLM"}, "openai-gpt": {"causal-lm": f"{_X}:NeuronOpenAIGPTForCausalLM"},
 })
 _H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"
-MODEL_TYPES.update({"bamba": {"causal-lm": f"{_H}:NeuronBambaForCausalLM"}, "mamba2": {"causal-lm": f"{_H}:NeuronMamba2ForCausalLM"}, "granitemoehybrid": {"causal-lm": f"{_H}:NeuronGraniteHybridForCausalLM"}, "lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"}, "falcon_h1": {"causal-lm": f"{_H}:NeuronFalconH1ForCausalLM"},
+MODEL_TYPES.update({"nemotron_h": {"causal-lm": f"{_H}:NeuronNemotronHForCausalLM"}, "bamba": {"causal-lm": f"{_H}:NeuronBambaForCausalLM"}, "mamba2": {"causal-lm": f"{_H}:NeuronMamba2ForCausalLM"}, "granitemoehybrid": {"causal-lm": f"{_H}:NeuronGraniteHybridForCausalLM"}, "lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"}, "falcon_h1": {"causal-lm": f"{_H}:NeuronFalconH1ForCausalLM"},
                     "recurrent_gemma": {"causal-lm": f"{_H}:NeuronRecurrentGemmaForCausalLM"}})
 MODEL_TYPES.update({
     "idefics": {"image-text-to-text": "neuronx_distributed_inference_b200.contrib.models.idefics:NeuronIdeficsForCausalLM"},

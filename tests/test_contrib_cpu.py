@@ -147,6 +147,12 @@ def _cfg(name):
                                         mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=8, mamba_d_conv=4, mamba_expand=2,
                                         mamba_chunk_size=8, position_embedding_type="nope" if dense else "rope", embedding_multiplier=3.0,
                                         attention_multiplier=0.2, residual_multiplier=0.5, logits_scaling=4.0, tie_word_embeddings=False)
+    if name == "nemotron_h":
+        return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
+                                 num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
+                                 n_groups=2, ssm_state_size=8, conv_kernel=4, chunk_size=8, n_routed_experts=8, num_experts_per_tok=2,
+                                 moe_intermediate_size=32, moe_shared_expert_intermediate_size=48, n_group=2, topk_group=1,
+                                 routed_scaling_factor=1.5, max_position_embeddings=256)
     if name == "mamba2":
         return T.Mamba2Config(hidden_size=64, num_heads=8, head_dim=16, state_size=8, n_groups=2, conv_kernel=4, expand=2, num_hidden_layers=3,
                               vocab_size=160, chunk_size=8, tie_word_embeddings=False)
@@ -157,7 +163,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "afmoe",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -178,7 +184,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     mask = torch.ones_like(ids)
     mask[1, 10:] = 0
     # transformers 5.5's CACHED Bamba decode drifts 5e-3 from its own full recompute; use the cache-free oracle there
-    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba2")))
+    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba2", "nemotron_h")))
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"

@@ -113,3 +113,38 @@ def test_qwen2_5_omni_thinker_text_backbone(tmp_path):
     save_file({"thinker." + k: v.clone().contiguous() for k, v in hf.state_dict().items()}, os.path.join(dst, "model.safetensors"))
     json.dump({"model_type": "qwen2_5_omni_test", "thinker_config": tc.to_dict()}, open(os.path.join(dst, "config.json"), "w"))
     _check("qwen2_5_omni", hf, dst)
+
+
+def test_nemotron_h_pattern_string_and_dense_mlp_block(tmp_path):
+    """Original Nemotron-H checkpoints describe the stack with ``hybrid_override_pattern`` ("M" Mamba-2, "*" attention, "-" squared-ReLU
+    MLP, "E" MoE) and transformers 5.5 cannot instantiate the "-" blocks, so the pattern parsing and the dense block are checked here
+    directly (the Mamba-2 / attention / MoE blocks are checked against HF in test_contrib_cpu)."""
+    import transformers as T
+    from neuronx_distributed_inference_b200.contrib.models.hybrid_family import NemotronHInferenceConfig, NemotronHLayer
+    hf = T.NemotronHConfig(hidden_size=64, intermediate_size=96, layers_block_type=["mamba", "attention"], num_attention_heads=4,
+                           num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16, n_groups=2,
+                           ssm_state_size=8, conv_kernel=4, n_routed_experts=4, moe_intermediate_size=32,
+                           moe_shared_expert_intermediate_size=48, max_position_embeddings=256)
+    hf.save_pretrained(str(tmp_path))
+    path = os.path.join(str(tmp_path), "config.json")
+    raw = json.load(open(path))
+    raw.pop("layers_block_type", None)
+    raw["hybrid_override_pattern"] = "M-*E"
+    json.dump(raw, open(path, "w"))
+    nc = NemotronHInferenceConfig.get_neuron_config_cls()(batch_size=1, seq_len=32, torch_dtype="float32", on_cpu=True)
+
+    def load(cfg):                                    # AutoConfig would re-derive layers_block_type: feed the raw dictionary
+        for k, v in raw.items():
+            setattr(cfg, k, v)
+    cfg = NemotronHInferenceConfig(nc, load_config=load)
+    assert cfg.layers_block_type == ["mamba", "mlp", "attention", "moe"] and cfg.num_hidden_layers == 4
+    assert cfg.mamba_d_ssm == 128 and cfg.mamba_n_groups == 2 and cfg.hidden_act == "relu2"
+    layer = NemotronHLayer(cfg, 1, None)
+    torch.manual_seed(0)
+    for p in layer.parameters():
+        p.data.normal_(0, 0.2)
+    h = torch.randn(1, 5, 64)
+    n = layer.norm
+    x = h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + n.variance_epsilon) * n.weight
+    ref = h + torch.relu(x @ layer.mlp.fc1.weight.T).square() @ layer.mlp.fc2.weight.T
+    assert torch.allclose(layer(h, None, None), ref, atol=1e-5)
