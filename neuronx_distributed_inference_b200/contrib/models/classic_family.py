@@ -51,7 +51,7 @@ class ClassicDecoderLayer(nn.Module):
                                        qkv_bias=spec["qkv_bias"], o_bias=spec["o_bias"], use_rope=rotary is not None and spec.get("use_rope", True),
                                        rope_interleaved=spec.get("rope_interleaved", False),
                                        sliding_window=spec.get("sliding_window"), softmax_scale=spec.get("softmax_scale"),
-                                       layer_idx=i, device=device)
+                                       clip_qkv=spec.get("clip_qkv"), layer_idx=i, device=device)
         if callable(spec["mlp"]):                     # MoE (or any custom) feed-forward: factory(config, device)
             self.mlp = spec["mlp"](config, device)
             self.mlp_is_moe = True

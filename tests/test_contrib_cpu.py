@@ -147,6 +147,12 @@ def _cfg(name):
                                         mamba_n_heads=8, mamba_d_head=16, mamba_n_groups=2, mamba_d_state=8, mamba_d_conv=4, mamba_expand=2,
                                         mamba_chunk_size=8, position_embedding_type="nope" if dense else "rope", embedding_multiplier=3.0,
                                         attention_multiplier=0.2, residual_multiplier=0.5, logits_scaling=4.0, tie_word_embeddings=False)
+    if name == "ministral":
+        return T.MinistralConfig(**BASE, head_dim=16, sliding_window=8, layer_types=["sliding_attention", "full_attention", "sliding_attention"])
+    if name == "cwm":
+        return T.CwmConfig(**BASE, head_dim=16, sliding_window=8, layer_types=["full_attention", "sliding_attention", "sliding_attention"])
+    if name == "olmo":
+        return T.OlmoConfig(**BASE, clip_qkv=0.4)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -163,7 +169,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -175,7 +181,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     from neuronx_distributed_inference_b200.contrib.models.moe_family import MOE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.more_families import MORE_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.hybrid_family import HYBRID_MODEL_TYPES
-    cls = {**CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_gated_norm", "").replace("_one_group", "").replace("_dense_nope", "")]
+    from neuronx_distributed_inference_b200.contrib.models.recent_families import RECENT_MODEL_TYPES
+    cls = {**RECENT_MODEL_TYPES, **CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_gated_norm", "").replace("_one_group", "").replace("_dense_nope", "")]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
