@@ -879,6 +879,7 @@ class NemotronHInferenceConfig(LlamaInferenceConfig):
             self.layers_block_type = [self._PATTERN[c] for c in self.hybrid_override_pattern]
         self.num_hidden_layers = len(self.layers_block_type)
         self.mamba_d_ssm = self.mamba_n_heads * self.mamba_d_head
+        self.time_step_limit = (float(getattr(self, "time_step_min", 0.0) or 0.0), float("inf"))    # HF floors dt at time_step_min, no ceiling
         self.hidden_act = getattr(self, "mlp_hidden_act", "relu2")
         if getattr(self, "moe_latent_size", None) is not None:
             raise NotImplementedError("Nemotron-H latent-projected experts (moe_latent_size)")

@@ -316,11 +316,9 @@ class NeuronArceeForCausalLM(NeuronLlamaForCausalLM):
         return {k.replace(".mlp.up_proj.", ".mlp.inner.fc1.").replace(".mlp.down_proj.", ".mlp.inner.fc2."): v for k, v in sd.items()}
 
 
-from ...models.qwen3.modeling_qwen3 import NeuronQwen3ForCausalLM as NeuronHunYuanDenseForCausalLM  # noqa: E402  (same block: per-head q/k RMSNorm)
 
 CONTRIB_MODEL_TYPES = {
     "helium": NeuronHeliumForCausalLM, "ernie4_5": NeuronErnie4_5ForCausalLM, "arcee": NeuronArceeForCausalLM,
-    "hunyuan_v1_dense": NeuronHunYuanDenseForCausalLM,
     "phi3": NeuronPhi3ForCausalLM, "granite": NeuronGraniteForCausalLM, "smollm3": NeuronSmolLM3ForCausalLM,
     "seed_oss": NeuronSeedOssForCausalLM, "olmo2": NeuronOlmo2ForCausalLM, "olmo3": NeuronOlmo3ForCausalLM,
     "gemma2": NeuronGemma2ForCausalLM, "glm4": NeuronGlm4ForCausalLM,

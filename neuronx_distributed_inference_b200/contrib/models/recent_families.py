@@ -58,3 +58,32 @@ class NeuronOlmoForCausalLM(_ClassicCausalLM):
 
 
 RECENT_MODEL_TYPES = {"ministral": NeuronMinistralForCausalLM, "cwm": NeuronCwmForCausalLM, "olmo": NeuronOlmoForCausalLM}
+
+
+# ---- HunYuan (dense and MoE): per-head q/k RMSNorm applied AFTER the rotation ---------------------------------------------------------
+class _HunYuanAttention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        b = bool(getattr(config, "attention_bias", False))
+        qk = "rms_post_rope" if getattr(config, "use_qk_norm", True) else None
+        super().__init__(config, layer_idx, rotary_emb, device=device, qkv_bias=b, o_bias=b, qk_norm=qk, qk_norm_eps=config.rms_norm_eps, **over)
+
+
+def _hunyuan_names(sd):
+    return {k.replace(".self_attn.query_layernorm.", ".self_attn.q_layernorm.").replace(".self_attn.key_layernorm.", ".self_attn.k_layernorm."): v
+            for k, v in sd.items()}
+
+
+class NeuronHunYuanDenseModel(NeuronLlamaModel):
+    attention_cls = _HunYuanAttention
+    graph_safe = False
+
+
+class NeuronHunYuanDenseForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronHunYuanDenseModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        return _hunyuan_names(NeuronLlamaForCausalLM.convert_hf_to_neuron_state_dict(sd, config))
+
+
+RECENT_MODEL_TYPES["hunyuan_v1_dense"] = NeuronHunYuanDenseForCausalLM

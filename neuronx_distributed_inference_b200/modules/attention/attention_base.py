@@ -94,9 +94,9 @@ class AttentionBase(nn.Module):
         self.clip_qkv = clip_qkv
         self.softcap = logit_softcap
         self.scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(head_dim)
-        self.qk_norm = qk_norm  # None | "rms_pre_rope" | "l2_post_rope"
+        self.qk_norm = qk_norm  # None | "rms_pre_rope" | "rms_post_rope" (HunYuan; generic path) | "l2_post_rope"
         self.qk_norm_eps = qk_norm_eps
-        if qk_norm == "rms_pre_rope":
+        if qk_norm in ("rms_pre_rope", "rms_post_rope"):
             self.q_layernorm = RMSNorm(head_dim, qk_norm_eps, dtype, device=device)
             self.k_layernorm = RMSNorm(head_dim, qk_norm_eps, dtype, device=device)
         elif qk_norm == "l2_post_rope":
@@ -344,4 +344,7 @@ class AttentionBase(nn.Module):
         if self.qk_norm == "l2_post_rope":
             q = self.qk_l2(q)
             k = self.qk_l2(k)
+        elif self.qk_norm == "rms_post_rope":
+            q = self.q_layernorm(q)
+            k = self.k_layernorm(k)
         return q, k, v

@@ -34,7 +34,7 @@ MODEL_TYPES.update({
     "olmo2": {"causal-lm": f"{_C}:NeuronOlmo2ForCausalLM"}, "olmo3": {"causal-lm": f"{_C}:NeuronOlmo3ForCausalLM"},
     "gemma2": {"causal-lm": f"{_C}:NeuronGemma2ForCausalLM"}, "glm4": {"causal-lm": f"{_C}:NeuronGlm4ForCausalLM"},
     "helium": {"causal-lm": f"{_C}:NeuronHeliumForCausalLM"}, "ernie4_5": {"causal-lm": f"{_C}:NeuronErnie4_5ForCausalLM"},
-    "arcee": {"causal-lm": f"{_C}:NeuronArceeForCausalLM"}, "hunyuan_v1_dense": {"causal-lm": f"{_C}:NeuronHunYuanDenseForCausalLM"},
+    "arcee": {"causal-lm": f"{_C}:NeuronArceeForCausalLM"}, "hunyuan_v1_dense": {"causal-lm": "neuronx_distributed_inference_b200.contrib.models.recent_families:NeuronHunYuanDenseForCausalLM"},
 })
 _K = "neuronx_distributed_inference_b200.contrib.models.classic_family"
 MODEL_TYPES.update({

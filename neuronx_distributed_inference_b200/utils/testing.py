@@ -55,12 +55,27 @@ def build_random_llama(hf_overrides: dict, batch_size: int = 1, seq_len: int = 1
     return app
 
 
-def save_random_hf_checkpoint(hf_config, out_dir: Optional[str] = None, seed: int = 0, dtype=torch.float32) -> str:
+def perturb_constant_vectors(model, std: float = 0.1, seed: int = 1234):
+    """Hugging Face initialises every norm weight to exactly 1 (or 0 for the ``1 + w`` kind) and every bias to 0; a port that forgets to
+    load one of them, or applies it on the wrong side of a rotation, would still match.  Give every CONSTANT 1-D floating parameter /
+    buffer a random perturbation so the comparison can see it."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for _, t in list(model.named_parameters()) + list(model.named_buffers()):
+            if t.dim() == 1 and t.is_floating_point() and t.numel() > 1 and bool((t == t[0]).all()) and float(t[0]) in (0.0, 1.0):
+                t.add_(torch.randn(t.shape, generator=g).to(t.dtype) * std)
+    return model
+
+
+def save_random_hf_checkpoint(hf_config, out_dir: Optional[str] = None, seed: int = 0, dtype=torch.float32, perturb: bool = True) -> str:
     """``AutoModelForCausalLM.from_config(...).save_pretrained`` — how the reference's integration tests
-    make checkpoints without network access (test/integration/utils/test_utils.py:15-48)."""
+    make checkpoints without network access (test/integration/utils/test_utils.py:15-48).  ``perturb``: see
+    :func:`perturb_constant_vectors`."""
     from transformers import AutoModelForCausalLM
     torch.manual_seed(seed)
     model = AutoModelForCausalLM.from_config(hf_config).to(dtype).eval()
+    if perturb:
+        perturb_constant_vectors(model)
     out_dir = out_dir or tempfile.mkdtemp(prefix="nxdi_b200_ckpt_")
     model.save_pretrained(out_dir)
     return out_dir
