@@ -187,6 +187,71 @@ class NeuronLfm2ForCausalLM(NeuronLlamaForCausalLM):
         return fuse_qkv_and_gate_up(out, config.num_hidden_layers)
 
 
+# ---------------------------------------------------------------------------------------------------------------------- LFM2-MoE
+class Lfm2MoeRouter(nn.Module):
+    """sigmoid affinities; the per-expert bias steers the SELECTION only; weights renormalised (+1e-6) and scaled."""
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        self.E, self.top_k = config.num_experts, config.num_experts_per_tok
+        self.norm, self.scaling = bool(getattr(config, "norm_topk_prob", True)), float(getattr(config, "routed_scaling_factor", 1.0))
+        self.linear_router = nn.Linear(config.hidden_size, self.E, bias=False, dtype=torch.float32, device=device)
+        self.linear_router.weight.requires_grad_(False)
+        self.use_bias = bool(getattr(config, "use_expert_bias", True))
+        self.register_buffer("expert_bias", torch.zeros(self.E, dtype=torch.float32, device=device))
+
+    def forward(self, x):
+        logits = F.linear(x.float(), self.linear_router.weight)
+        s = logits.sigmoid()
+        idx = (s + self.expert_bias if self.use_bias else s).topk(self.top_k, -1)[1]
+        w = s.gather(1, idx)
+        if self.norm:
+            w = w / (w.sum(-1, keepdim=True) + 1e-6)
+        return logits, w * self.scaling, idx
+
+
+class Lfm2MoeInferenceConfig(Lfm2InferenceConfig):
+    def add_derived_config(self):
+        self.block_auto_adjust_ff_dim = False                       # LFM2-MoE states its widths directly
+        super().add_derived_config()
+
+    @classmethod
+    def get_neuron_config_cls(cls):
+        from ...config import MoENeuronConfig
+        return MoENeuronConfig
+
+
+class NeuronLfm2MoeModel(NeuronLfm2Model):
+    """LFM2 whose feed-forward becomes a sigmoid-routed MoE from layer ``num_dense_layers`` on."""
+
+    def make_layer(self, config, i, rotary, device):
+        from ...modules.moe import ExpertMLPs, MoE
+        layer = super().make_layer(config, i, rotary, device)
+        if i >= int(getattr(config, "num_dense_layers", 0)):
+            layer.mlp = MoE(Lfm2MoeRouter(config, device),
+                            ExpertMLPs(config.num_experts, config.hidden_size, config.moe_intermediate_size, "silu",
+                                       config.neuron_config.torch_dtype, device=device))
+            layer.mlp_is_moe = True
+        return layer
+
+
+class NeuronLfm2MoeForCausalLM(NeuronLfm2ForCausalLM):
+    _model_cls = NeuronLfm2MoeModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return Lfm2MoeInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        from ...models.state_dict_utils import convert_moe_experts
+        sd = {k.replace(".feed_forward.expert_bias", ".mlp.router.expert_bias"): v for k, v in sd.items()}
+        moe_layers = range(int(getattr(config, "num_dense_layers", 0)), config.num_hidden_layers)
+        sd = convert_moe_experts(sd, config.num_hidden_layers, config.num_experts, moe_prefixes=("feed_forward",), gate_names=("gate",),
+                                 w_names=("w1", "w3", "w2"), layers=moe_layers)
+        return NeuronLfm2ForCausalLM.convert_hf_to_neuron_state_dict(sd, config)
+
+
 # ---------------------------------------------------------------------------------------------------------------------- RecurrentGemma
 class RecurrentGemmaInferenceConfig(LlamaInferenceConfig):
     def get_required_attributes(self):
@@ -986,4 +1051,4 @@ class NeuronNemotronHForCausalLM(NeuronLlamaForCausalLM):
         pass
 
 
-HYBRID_MODEL_TYPES = {"nemotron_h": NeuronNemotronHForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+HYBRID_MODEL_TYPES = {"nemotron_h": NeuronNemotronHForCausalLM, "lfm2_moe": NeuronLfm2MoeForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

@@ -87,3 +87,120 @@ class NeuronHunYuanDenseForCausalLM(NeuronLlamaForCausalLM):
 
 
 RECENT_MODEL_TYPES["hunyuan_v1_dense"] = NeuronHunYuanDenseForCausalLM
+
+
+class _HunYuanMoeModel(NeuronLlamaModel):
+    """Softmax top-k (renormalised) routed SwiGLU experts plus an always-on shared SwiGLU of the dense width."""
+    attention_cls = _HunYuanAttention
+    graph_safe = False
+
+    def make_layer(self, config, i, rotary, device):
+        from ...models.model_base import DecoderLayer
+        from ...modules.moe import ExpertMLPs, MoE, RouterTopK, SharedExperts
+        from ...modules.norm import RMSNorm
+        dt, H = config.neuron_config.torch_dtype, config.hidden_size
+        pick = lambda v: v if isinstance(v, int) else v[i]                                          # noqa: E731  (per-layer lists allowed)
+        E, k = pick(config.num_experts), pick(config.moe_topk)
+        moe = MoE(RouterTopK(E, k, H, dt, "softmax", False, True, False, device),
+                  ExpertMLPs(E, H, config.intermediate_size, config.hidden_act, dt, device=device),
+                  SharedExperts(H, config.intermediate_size, config.hidden_act, dt, device))
+        return DecoderLayer(self.attention_cls(config, i, rotary, device=device), moe, RMSNorm(H, config.rms_norm_eps, dt, device=device),
+                            RMSNorm(H, config.rms_norm_eps, dt, device=device), i, mlp_is_moe=True)
+
+
+class _MoeCfg:
+    @classmethod
+    def get_config_cls(cls):
+        from .moe_family import _MoeConfig
+        return _MoeConfig
+
+
+class NeuronHunYuanMoEForCausalLM(_MoeCfg, NeuronLlamaForCausalLM):
+    _model_cls = _HunYuanMoeModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        from ...models.state_dict_utils import convert_moe_experts
+        sd = {k.replace(".mlp.gate.wg.", ".mlp.gate.").replace(".mlp.shared_mlp.", ".mlp.shared_experts."): v for k, v in sd.items()}
+        for i in range(config.num_hidden_layers):                                                  # shared expert: [gate; up] fused rows
+            b = f"layers.{i}.mlp.shared_experts."
+            if b + "gate_proj.weight" in sd:
+                sd[b + "gate_up_proj.weight"] = torch.cat([sd.pop(b + "gate_proj.weight"), sd.pop(b + "up_proj.weight")], 0)
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+        n_exp = config.num_experts if isinstance(config.num_experts, int) else max(config.num_experts)
+        sd = convert_moe_experts(sd, config.num_hidden_layers, n_exp, moe_prefixes=("mlp",), gate_names=("gate",),
+                                 w_names=("gate_proj", "up_proj", "down_proj"))
+        return _hunyuan_names(sd)
+
+
+# ---- FlexOlmo: the OLMo-2 block (norms AFTER attention / feed-forward, full-width q/k RMSNorm) with an OLMoE feed-forward ---------------
+class FlexOlmoLayer(torch.nn.Module):
+    mlp_is_moe = True
+
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        from ...modules.moe import initialize_moe_module
+        from ...modules.norm import RMSNorm
+        from .llama_family import Olmo2Attention
+        dt = config.neuron_config.torch_dtype
+        self.self_attn = Olmo2Attention(config, i, rotary, device)
+        self.mlp = initialize_moe_module(config, device=device, intermediate_size=config.intermediate_size,
+                                         normalize=bool(getattr(config, "norm_topk_prob", False)))
+        self.post_attention_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)
+        self.post_feedforward_layernorm = RMSNorm(config.hidden_size, config.rms_norm_eps, dt, device=device)
+        self.layer_idx = i
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        h = h + self.post_attention_layernorm(self.self_attn(h, meta, kv_mgr))
+        return h + self.post_feedforward_layernorm(self.mlp(h))
+
+
+class NeuronFlexOlmoModel(NeuronLlamaModel):
+    graph_safe = False
+
+    def make_layer(self, config, i, rotary, device):
+        return FlexOlmoLayer(config, i, rotary, device)
+
+
+class NeuronFlexOlmoForCausalLM(_MoeCfg, NeuronLlamaForCausalLM):
+    _model_cls = NeuronFlexOlmoModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        from .moe_family import NeuronOlmoeForCausalLM
+        return NeuronOlmoeForCausalLM.convert_hf_to_neuron_state_dict(sd, config)
+
+
+# ---- GraniteMoE with the always-on shared SwiGLU (Granite-3.x MoE "shared" variants) -------------------------------------------------
+def _granite_shared_model():
+    from ...modules.moe import SharedExperts
+    from .moe_family import NeuronGraniteMoeForCausalLM, NeuronGraniteMoeModel
+
+    class NeuronGraniteMoeSharedModel(NeuronGraniteMoeModel):
+        def make_layer(self, config, i, rotary, device):
+            layer = super().make_layer(config, i, rotary, device)
+            if getattr(config, "shared_intermediate_size", 0):
+                layer.mlp.shared_experts = SharedExperts(config.hidden_size, config.shared_intermediate_size, config.hidden_act,
+                                                         config.neuron_config.torch_dtype, device)
+            return layer
+
+    class NeuronGraniteMoeSharedForCausalLM(NeuronGraniteMoeForCausalLM):
+        _model_cls = NeuronGraniteMoeSharedModel
+
+        @staticmethod
+        def convert_hf_to_neuron_state_dict(sd, config):
+            rm = float(getattr(config, "residual_multiplier", 1.0))
+            sd = dict(sd)
+            for i in range(config.num_hidden_layers):
+                a, b = f"layers.{i}.shared_mlp.", f"layers.{i}.mlp.shared_experts."
+                if a + "input_linear.weight" in sd:
+                    sd[b + "gate_up_proj.weight"] = sd.pop(a + "input_linear.weight")
+                    w = sd.pop(a + "output_linear.weight")
+                    sd[b + "down_proj.weight"] = (w.float() * rm).to(w.dtype)                      # residual multiplier folded, as for the experts
+            return NeuronGraniteMoeForCausalLM.convert_hf_to_neuron_state_dict(sd, config)
+    return NeuronGraniteMoeSharedForCausalLM
+
+
+NeuronGraniteMoeSharedForCausalLM = _granite_shared_model()
+RECENT_MODEL_TYPES.update({"hunyuan_v1_moe": NeuronHunYuanMoEForCausalLM, "flex_olmo": NeuronFlexOlmoForCausalLM,
+                           "granitemoeshared": NeuronGraniteMoeSharedForCausalLM})

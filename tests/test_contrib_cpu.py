@@ -153,6 +153,18 @@ def _cfg(name):
         return T.CwmConfig(**BASE, head_dim=16, sliding_window=8, layer_types=["full_attention", "sliding_attention", "sliding_attention"])
     if name == "olmo":
         return T.OlmoConfig(**BASE, clip_qkv=0.4)
+    if name == "hunyuan_v1_moe":
+        return T.HunYuanMoEV1Config(**BASE, num_experts=4, moe_topk=2, head_dim=16, pad_token_id=0)
+    if name == "flex_olmo":
+        return T.FlexOlmoConfig(**BASE, num_experts=4, num_experts_per_tok=2, pad_token_id=0)
+    if name == "granitemoeshared":
+        return T.GraniteMoeSharedConfig(**BASE, num_local_experts=4, num_experts_per_tok=2, shared_intermediate_size=96, embedding_multiplier=3.0,
+                                        attention_multiplier=0.2, residual_multiplier=0.5, logits_scaling=4.0)
+    if name == "lfm2_moe":
+        return T.Lfm2MoeConfig(hidden_size=64, intermediate_size=128, moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4,
+                               num_key_value_heads=2, vocab_size=160, num_experts=4, num_experts_per_tok=2, num_dense_layers=1,
+                               layer_types=["conv", "full_attention", "conv"], pad_token_id=0, routed_scaling_factor=1.5,
+                               max_position_embeddings=256)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -171,7 +183,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
