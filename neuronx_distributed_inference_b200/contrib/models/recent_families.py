@@ -204,3 +204,95 @@ def _granite_shared_model():
 NeuronGraniteMoeSharedForCausalLM = _granite_shared_model()
 RECENT_MODEL_TYPES.update({"hunyuan_v1_moe": NeuronHunYuanMoEForCausalLM, "flex_olmo": NeuronFlexOlmoForCausalLM,
                            "granitemoeshared": NeuronGraniteMoeSharedForCausalLM})
+
+
+# ---- MiniMax-M2: full-width q/k RMSNorm, partial rotary, sigmoid router whose bias only steers the selection ---------------------------
+class _SigmoidBiasRouter(torch.nn.Module):
+    def __init__(self, num_experts, top_k, hidden_size, device=None):
+        super().__init__()
+        self.E, self.top_k = num_experts, top_k
+        self.linear_router = torch.nn.Linear(hidden_size, num_experts, bias=False, dtype=torch.float32, device=device)
+        self.linear_router.weight.requires_grad_(False)
+        self.register_buffer("e_score_correction_bias", torch.zeros(num_experts, dtype=torch.float32, device=device))
+
+    def forward(self, x):
+        logits = torch.nn.functional.linear(x.float(), self.linear_router.weight)
+        s = logits.sigmoid()
+        idx = (s + self.e_score_correction_bias).topk(self.top_k, -1)[1]
+        w = s.gather(1, idx)
+        return logits, w / w.sum(-1, keepdim=True), idx
+
+
+def _minimax_m2():
+    from ...models.model_base import DecoderLayer
+    from ...modules.moe import ExpertMLPs, MoE
+    from ...modules.norm import RMSNorm
+    from .llama_family import Olmo2Attention
+    from .moe_family import _MoeConfig
+
+    class MiniMaxM2Config(_MoeConfig):
+        def add_derived_config(self):
+            rp, rd = getattr(self, "rope_parameters", None) or {}, getattr(self, "rotary_dim", None)
+            if rp.get("partial_rotary_factor") is not None:
+                self.partial_rotary_factor = float(rp["partial_rotary_factor"])
+            elif rd:                                        # original config.json: rotary_dim of head_dim channels rotate
+                self.partial_rotary_factor = rd / (getattr(self, "head_dim", None) or self.hidden_size // self.num_attention_heads)
+            super().add_derived_config()
+
+    class NeuronMiniMaxM2Model(NeuronLlamaModel):
+        graph_safe = False
+
+        def make_layer(self, config, i, rotary, device):
+            dt, H = config.neuron_config.torch_dtype, config.hidden_size
+            attn = Olmo2Attention(config, i, rotary, device)
+            moe = MoE(_SigmoidBiasRouter(config.num_local_experts, config.num_experts_per_tok, H, device),
+                      ExpertMLPs(config.num_local_experts, H, config.intermediate_size, config.hidden_act, dt, device=device))
+            return DecoderLayer(attn, moe, RMSNorm(H, config.rms_norm_eps, dt, device=device), RMSNorm(H, config.rms_norm_eps, dt, device=device),
+                                i, mlp_is_moe=True)
+
+    class NeuronMiniMaxM2ForCausalLM(NeuronLlamaForCausalLM):
+        _model_cls = NeuronMiniMaxM2Model
+
+        @classmethod
+        def get_config_cls(cls):
+            return MiniMaxM2Config
+
+        @staticmethod
+        def convert_hf_to_neuron_state_dict(sd, config):
+            from ...models.state_dict_utils import convert_moe_experts
+            sd = {k.replace(".block_sparse_moe.e_score_correction_bias", ".mlp.router.e_score_correction_bias"): v for k, v in sd.items()}
+            sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+            sd = convert_moe_experts(sd, config.num_hidden_layers, config.num_local_experts, moe_prefixes=("block_sparse_moe",),
+                                     gate_names=("gate",), w_names=("w1", "w3", "w2"))
+            return {k.replace(".self_attn.q_norm.weight", ".self_attn.q_norm").replace(".self_attn.k_norm.weight", ".self_attn.k_norm"): v
+                    for k, v in sd.items()}
+    return NeuronMiniMaxM2ForCausalLM
+
+
+NeuronMiniMaxM2ForCausalLM = _minimax_m2()
+RECENT_MODEL_TYPES["minimax_m2"] = NeuronMiniMaxM2ForCausalLM
+
+
+# ---- Solar-Open: the GLM-4.5-MoE block with every layer sparse and no q/k norm (DeepSeek-V3 sigmoid / group-limited router) -----------
+def _solar_open():
+    from .moe_family import NeuronGlm4MoeForCausalLM, _MoeConfig
+
+    class SolarOpenConfig(_MoeConfig):
+        def __init__(self, *a, **kw):
+            self.intermediate_size = None                           # no dense layers: placeholder, set to the expert width below
+            super().__init__(*a, **kw)
+
+        def add_derived_config(self):
+            if not getattr(self, "intermediate_size", None):
+                self.intermediate_size = self.moe_intermediate_size
+            super().add_derived_config()
+
+    class NeuronSolarOpenForCausalLM(NeuronGlm4MoeForCausalLM):
+        @classmethod
+        def get_config_cls(cls):
+            return SolarOpenConfig
+    return NeuronSolarOpenForCausalLM
+
+
+NeuronSolarOpenForCausalLM = _solar_open()
+RECENT_MODEL_TYPES["solar_open"] = NeuronSolarOpenForCausalLM

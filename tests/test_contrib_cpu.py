@@ -165,6 +165,13 @@ def _cfg(name):
                                num_key_value_heads=2, vocab_size=160, num_experts=4, num_experts_per_tok=2, num_dense_layers=1,
                                layer_types=["conv", "full_attention", "conv"], pad_token_id=0, routed_scaling_factor=1.5,
                                max_position_embeddings=256)
+    if name == "minimax_m2":
+        return T.MiniMaxM2Config(**{**BASE, "intermediate_size": 32}, num_local_experts=4, num_experts_per_tok=2, head_dim=16, rotary_dim=8,
+                                 pad_token_id=0, rope_parameters=dict(rope_type="default", rope_theta=10000.0, partial_rotary_factor=0.5))
+    if name == "solar_open":
+        return T.SolarOpenConfig(hidden_size=64, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, vocab_size=160, head_dim=16,
+                                 max_position_embeddings=256, moe_intermediate_size=32, n_routed_experts=8, num_experts_per_tok=2,
+                                 n_shared_experts=1, n_group=2, topk_group=1, routed_scaling_factor=1.5, pad_token_id=0)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -183,7 +190,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
