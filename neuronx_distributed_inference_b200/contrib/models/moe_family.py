@@ -531,6 +531,7 @@ class NeuronErnie4_5MoeForCausalLM(NeuronLlamaForCausalLM):
         for i in range(config.num_hidden_layers):
             m = f"layers.{i}.mlp."
             b = sd.pop(m + "gate.moe_statics.e_score_correction_bias", None)
+            b = sd.pop(m + "moe_statics.e_score_correction_bias", b)        # on-disk spelling (the in-memory module nests it under gate)
             if b is not None:
                 sd[m + "router.e_score_correction_bias"] = b.float().reshape(-1)
             g, u = m + "shared_experts.gate_proj.weight", m + "shared_experts.up_proj.weight"

@@ -296,3 +296,55 @@ def _solar_open():
 
 NeuronSolarOpenForCausalLM = _solar_open()
 RECENT_MODEL_TYPES["solar_open"] = NeuronSolarOpenForCausalLM
+
+
+# ---- EXAONE-MoE: EXAONE-4 attention (per-head q/k RMSNorm; hybrid models rotate only the sliding layers) in a pre-norm block whose
+#      feed-forward is dense or a DeepSeek-V3-style MoE per ``mlp_layer_types`` --------------------------------------------------------
+def _exaone_moe():
+    from ...models.llama.modeling_llama import NeuronLlamaMLP
+    from ...models.model_base import DecoderLayer
+    from ...modules.attention import AttentionBase
+    from ...modules.norm import RMSNorm
+    from .moe_family import NeuronGlm4MoeForCausalLM, _deepseek_moe, _MoeConfig
+
+    class ExaoneMoeConfig(_MoeConfig):
+        def add_derived_config(self):
+            self.n_routed_experts = self.num_experts
+            self.n_shared_experts = getattr(self, "num_shared_experts", 0)
+            if not getattr(self, "mlp_layer_types", None):
+                self.mlp_layer_types = ["sparse"] * self.num_hidden_layers
+            super().add_derived_config()
+
+    class NeuronExaoneMoeModel(NeuronLlamaModel):
+        graph_safe = False
+
+        def make_layer(self, config, i, rotary, device):
+            dt, H = config.neuron_config.torch_dtype, config.hidden_size
+            lt = getattr(config, "layer_types", None)
+            hybrid, sliding = getattr(config, "sliding_window", None) is not None, bool(lt and lt[i] == "sliding_attention")
+            attn = AttentionBase(config, hidden_size=H, num_attention_heads=config.num_attention_heads,
+                                 num_key_value_heads=config.num_key_value_heads, head_dim=config.head_dim, rotary_emb=rotary,
+                                 qk_norm="rms_pre_rope", qk_norm_eps=config.rms_norm_eps, use_rope=(not hybrid) or sliding,
+                                 sliding_window=config.sliding_window if (hybrid and sliding) else None, layer_idx=i,
+                                 rms_norm_eps=config.rms_norm_eps, device=device)
+            moe = config.mlp_layer_types[i] == "sparse"
+            mlp = _deepseek_moe(config, device) if moe else NeuronLlamaMLP(config, device=device)
+            return DecoderLayer(attn, mlp, RMSNorm(H, config.rms_norm_eps, dt, device=device), RMSNorm(H, config.rms_norm_eps, dt, device=device),
+                                i, mlp_is_moe=moe)
+
+    class NeuronExaoneMoeForCausalLM(NeuronGlm4MoeForCausalLM):
+        _model_cls = NeuronExaoneMoeModel
+
+        @classmethod
+        def get_config_cls(cls):
+            return ExaoneMoeConfig
+
+        @staticmethod
+        def convert_hf_to_neuron_state_dict(sd, config):
+            sd = {k.replace(".mlp.e_score_correction_bias", ".mlp.gate.e_score_correction_bias"): v for k, v in sd.items()}   # on-disk spelling
+            return NeuronGlm4MoeForCausalLM.convert_hf_to_neuron_state_dict(sd, config)
+    return NeuronExaoneMoeForCausalLM
+
+
+NeuronExaoneMoeForCausalLM = _exaone_moe()
+RECENT_MODEL_TYPES["exaone_moe"] = NeuronExaoneMoeForCausalLM

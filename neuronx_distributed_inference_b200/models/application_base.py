@@ -191,6 +191,12 @@ class NeuronApplicationBase(nn.Module):
         else:
             sd = state_dict if state_dict is not None else self.checkpoint_loader_fn()
             load_sharded(self.model, sd, nc.torch_dtype, strict=False)
+            rep = self.load_report = getattr(self.model, "_load_report", {"missing": [], "unexpected": []})
+            if rep["missing"] or rep["unexpected"]:     # a port that forgot a tensor must not go unnoticed (the values stay at their init)
+                logger.warning("checkpoint load: %d model tensors not in the checkpoint %s; %d checkpoint tensors unused %s",
+                               len(rep["missing"]), rep["missing"][:6], len(rep["unexpected"]), rep["unexpected"][:6])
+                if rep["missing"] and os.environ.get("B200_STRICT_LOAD") == "1":      # the test-suite setting
+                    raise KeyError(f"model tensors missing from the converted checkpoint: {rep['missing'][:12]}")
         self._post_load(self.model)
         self._attach_symmetric_workspace()
         self._build_speculation(random_weights, seed)

@@ -156,6 +156,7 @@ def shard_state_dict(model: nn.Module, full_sd: Dict[str, torch.Tensor], strict:
         out[name] = t
     if strict and missing:
         raise KeyError(f"missing keys in checkpoint: {missing[:8]}{' ...' if len(missing) > 8 else ''}")
+    model._load_report = {"missing": missing, "unexpected": sorted(set(full_sd) - set(out))}
     return out
 
 

@@ -57,12 +57,12 @@ def build_random_llama(hf_overrides: dict, batch_size: int = 1, seq_len: int = 1
 
 def perturb_constant_vectors(model, std: float = 0.1, seed: int = 1234):
     """Hugging Face initialises every norm weight to exactly 1 (or 0 for the ``1 + w`` kind) and every bias to 0; a port that forgets to
-    load one of them, or applies it on the wrong side of a rotation, would still match.  Give every CONSTANT 1-D floating parameter /
-    buffer a random perturbation so the comparison can see it."""
+    load one of them, or applies it on the wrong side of a rotation, would still match.  Give every CONSTANT vector-shaped (1-D, or [1, n]) floating
+    parameter / buffer a random perturbation so the comparison can see it."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for _, t in list(model.named_parameters()) + list(model.named_buffers()):
-            if t.dim() == 1 and t.is_floating_point() and t.numel() > 1 and bool((t == t[0]).all()) and float(t[0]) in (0.0, 1.0):
+            if t.numel() == max(t.shape, default=0) and t.is_floating_point() and t.numel() > 1 and bool((t == t.flatten()[0]).all()) and float(t.flatten()[0]) in (0.0, 1.0):
                 t.add_(torch.randn(t.shape, generator=g).to(t.dtype) * std)
     return model
 

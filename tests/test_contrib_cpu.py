@@ -172,6 +172,11 @@ def _cfg(name):
         return T.SolarOpenConfig(hidden_size=64, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, vocab_size=160, head_dim=16,
                                  max_position_embeddings=256, moe_intermediate_size=32, n_routed_experts=8, num_experts_per_tok=2,
                                  n_shared_experts=1, n_group=2, topk_group=1, routed_scaling_factor=1.5, pad_token_id=0)
+    if name == "exaone_moe":
+        return T.ExaoneMoeConfig(**{**BASE, "num_hidden_layers": 4}, head_dim=16, moe_intermediate_size=32, num_experts=8, num_experts_per_tok=2,
+                                 num_shared_experts=1, n_group=2, topk_group=1, routed_scaling_factor=1.5, sliding_window=8, sliding_window_pattern=2,
+                                 layer_types=["sliding_attention", "full_attention", "sliding_attention", "full_attention"],
+                                 mlp_layer_types=["dense", "sparse", "sparse", "sparse"], pad_token_id=0)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -190,7 +195,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -207,6 +212,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
+    rep = app.load_report
+    assert not rep["missing"] and not [k for k in rep["unexpected"] if "rotary" not in k and "inv_freq" not in k], rep
     g = torch.Generator().manual_seed(0)
     ids = torch.randint(1, hf_cfg.vocab_size, (2, 14), generator=g)
     mask = torch.ones_like(ids)
