@@ -2,6 +2,8 @@
 import pytest
 import torch
 
+from neuronx_distributed_inference_b200.utils.testing import perturb_constant_vectors  # noqa: E402
+
 from neuronx_distributed_inference_b200.config import NeuronConfig, load_pretrained_config
 
 
@@ -16,6 +18,7 @@ def test_wav2vec2_frame_classifier_matches_hf(stable, tmp_path):
                            vocab_size=32, use_weighted_layer_sum=not stable)
     hf = T.Wav2Vec2ForAudioFrameClassification(cfg).eval()
     ckpt = str(tmp_path / "w2v")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     nc = NeuronConfig(batch_size=4, torch_dtype="float32", on_cpu=True, buckets=[4])
     app = A(ckpt, A.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))

@@ -3,6 +3,8 @@ scattered into the prompt, and decode with M-RoPE position offsets."""
 import pytest
 import torch
 
+from neuronx_distributed_inference_b200.utils.testing import perturb_constant_vectors  # noqa: E402
+
 from neuronx_distributed_inference_b200.config import load_pretrained_config
 from neuronx_distributed_inference_b200.utils.constants import get_model_cls
 
@@ -33,6 +35,7 @@ def test_qwen2_vl_matches_hf(tmp_path):
         image_token_id=150, video_token_id=151, vision_start_token_id=152, vision_end_token_id=153)
     hf = Qwen2VLForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "qwen2vl")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("qwen2_vl", hf, ckpt)
     # two images: 4x4 and 4x8 patches -> 4 and 8 merged tokens
@@ -78,6 +81,7 @@ def test_pixtral_matches_hf(tmp_path):
         image_token_index=150, projector_hidden_act="gelu", vision_feature_layer=-1, vision_feature_select_strategy="full")
     hf = LlavaForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "pixtral")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("pixtral", hf, ckpt)
     pix = torch.randn(2, 3, 16, 16)
@@ -105,6 +109,7 @@ def test_qwen3_vl_matches_hf(tmp_path):
         image_token_id=150, video_token_id=151, vision_start_token_id=152, vision_end_token_id=153)
     hf = Qwen3VLForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "qwen3vl")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("qwen3_vl", hf, ckpt)
     grid = torch.tensor([[1, 4, 4], [1, 4, 8]])
@@ -139,6 +144,7 @@ def test_mllama_matches_hf(tmp_path):
                 p.fill_(0.7)
     hf = hf.eval()
     ckpt = str(tmp_path / "mllama")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("mllama", hf, ckpt)
     app.vision_model.intermediate_is_layer_output = True      # transformers 5.x oracle convention (see modeling_mllama.py)
@@ -188,6 +194,7 @@ def test_llama4_multimodal_matches_hf(tmp_path):
         image_token_index=150)
     hf = Llama4ForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "llama4mm")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("llama4", hf, ckpt)
     pix = torch.randn(2, 3, 16, 16)           # two tiles -> 4 tokens each after the 0.5 pixel shuffle
@@ -213,6 +220,7 @@ def test_llava_1_5_matches_hf(tmp_path):
         image_token_index=150, vision_feature_layer=-2, vision_feature_select_strategy="default")
     hf = LlavaForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "llava")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     cls = NeuronLlavaForCausalLM
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=64, max_context_length=32, torch_dtype="float32", on_cpu=True, output_logits=True)
@@ -244,6 +252,7 @@ def test_qwen2_5_vl_matches_hf(tmp_path):
         image_token_id=150, video_token_id=151, vision_start_token_id=152, vision_end_token_id=153)
     hf = Qwen2_5_VLForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "qwen25vl")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     cls = NeuronQwen25VLForCausalLM
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=64, max_context_length=32, torch_dtype="float32", on_cpu=True, output_logits=True)
@@ -276,6 +285,7 @@ def test_mistral3_matches_hf(tmp_path):
         image_token_index=150, projector_hidden_act="gelu", vision_feature_layer=-1, spatial_merge_size=2)
     hf = Mistral3ForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "mistral3")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("mistral3", hf, ckpt)
     pix = torch.randn(2, 3, 16, 16)
@@ -306,6 +316,7 @@ def test_gemma3_vision_matches_hf(tmp_path):
     hf.model.multi_modal_projector.mm_input_projection_weight.data.normal_(0, 0.1)      # HF initialises the projector to zeros
     hf.model.multi_modal_projector.mm_soft_emb_norm.weight.data.normal_(0, 0.1)
     ckpt = str(tmp_path / "gemma3v")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("gemma3", hf, ckpt)
     pix = torch.randn(3, 3, 16, 16)
@@ -381,6 +392,7 @@ def test_idefics_matches_hf(resampler, tmp_path):
         if "layer_norm" in n or "layernorm" in n:
             p.data.add_(torch.randn_like(p) * 0.1)
     ckpt = str(tmp_path / "idefics")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     app = _build("idefics", hf, ckpt)
     ids = torch.randint(1, 164, (2, 12))                     # includes ids from the additional vocabulary

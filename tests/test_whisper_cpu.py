@@ -1,6 +1,8 @@
 """Whisper: encoder output, teacher-forced decoder logits (prefill + decode with cached cross K/V) and greedy generation vs HF."""
 import torch
 
+from neuronx_distributed_inference_b200.utils.testing import perturb_constant_vectors  # noqa: E402
+
 from neuronx_distributed_inference_b200.config import load_pretrained_config
 from neuronx_distributed_inference_b200.utils.constants import get_model_cls
 
@@ -14,6 +16,7 @@ def test_whisper_matches_hf(tmp_path):
                         suppress_tokens=None, begin_suppress_tokens=None)
     hf = WhisperForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "whisper")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     cls = get_model_cls("whisper", "speech-to-text")
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=32, max_context_length=16, torch_dtype="float32", on_cpu=True, output_logits=True)
@@ -77,6 +80,7 @@ def test_whisper_decoding_rules_and_fallback(tmp_path):
     torch.manual_seed(0)
     hf = T.WhisperForConditionalGeneration(cfg).eval()
     ckpt = str(tmp_path / "w")
+    perturb_constant_vectors(hf)
     hf.save_pretrained(ckpt)
     nc = NeuronConfig(batch_size=2, seq_len=32, max_context_length=8, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = A(ckpt, A.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
