@@ -348,3 +348,22 @@ def _exaone_moe():
 
 NeuronExaoneMoeForCausalLM = _exaone_moe()
 RECENT_MODEL_TYPES["exaone_moe"] = NeuronExaoneMoeForCausalLM
+
+
+# ---- Jais-2: LayerNorm (with bias) pre-norm block, rotary GQA, two-matrix MLP (squared ReLU by default), optional biases ---------------
+class NeuronJais2Model(NeuronClassicModel):
+    def layer_spec(self, config, i):
+        ab, mb = bool(getattr(config, "attention_bias", True)), bool(getattr(config, "mlp_bias", True))
+        return dict(parallel=False, norm_bias=True, mlp="plain", act=getattr(config, "hidden_act", "relu2"), qkv_bias=ab, o_bias=ab, mlp_bias=mb)
+
+
+class NeuronJais2ForCausalLM(_ClassicCausalLM):
+    _model_cls = NeuronJais2Model
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = {k.replace(".mlp.up_proj.", ".mlp.fc1.").replace(".mlp.down_proj.", ".mlp.fc2."): v for k, v in sd.items()}
+        return fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+
+
+RECENT_MODEL_TYPES["jais2"] = NeuronJais2ForCausalLM
