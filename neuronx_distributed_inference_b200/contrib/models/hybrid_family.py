@@ -11,6 +11,7 @@
   and then applies one RMSNorm over the whole inner width.
 * **Granite-4.0 hybrid (``granitemoehybrid``)** — Bamba-style Mamba-2 / attention stack (RoPE or no positions at all) with the Granite
   multipliers and, per layer, an always-on shared SwiGLU plus an optional top-k MoE.
+* **Mamba / Falcon-Mamba** — attention-free Mamba-1 (per-channel selective SSM; Falcon-Mamba adds weight-free RMS on B, C, dt).
 * **Mamba-2 (Codestral-Mamba)** — attention-free: ``h += mixer(norm(h))`` per layer; the engine keeps a token-sized dummy KV cache.
 * **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
   multipliers everywhere (all linear, folded into the weights at load).
@@ -1051,4 +1052,154 @@ class NeuronNemotronHForCausalLM(NeuronLlamaForCausalLM):
         pass
 
 
-HYBRID_MODEL_TYPES = {"nemotron_h": NeuronNemotronHForCausalLM, "lfm2_moe": NeuronLfm2MoeForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Mamba-1
+class Mamba1Mixer(nn.Module):
+    """Selective SSM of Mamba-1 (per-CHANNEL ``dt`` and state ``[I, N]``): ``in_proj -> (x, gate)``, causal depthwise conv + SiLU on
+    x, ``x_proj -> (dt_low_rank, B, C)``, ``dt = softplus(dt_proj(.))``, ``h_t = exp(dt A) h_{t-1} + dt B_t x_t``,
+    ``y = C_t h_t + D x``, gated by ``silu(gate)``.  Tensor parallel over the inner channels: ``x_proj`` is row-parallel (its small
+    ``R + 2N`` output is all-reduced), everything else is channel-local.  ``bcdt_rms``: Falcon-Mamba normalises B, C and the low-rank
+    dt (weight-free RMS)."""
+
+    def __init__(self, config, i, device=None, bcdt_rms=False):
+        super().__init__()
+        dt, H = config.neuron_config.torch_dtype, config.hidden_size
+        I, self.N, self.K, self.R = config.mamba_d_inner, config.mamba_d_state, config.mamba_d_conv, config.mamba_dt_rank
+        pb = bool(getattr(config, "mamba_proj_bias", False))
+        self.in_proj = ColumnParallelLinear(H, 2 * I, bias=pb, gather_output=False, dtype=dt, device=device, stride=2)
+        self.x_proj = RowParallelLinear(I, self.R + 2 * self.N, bias=False, input_is_parallel=True, dtype=dt, device=device)
+        self.dt_proj = ColumnParallelLinear(self.R, I, bias=True, gather_output=False, dtype=dt, device=device)
+        self.out_proj = RowParallelLinear(I, H, bias=pb, input_is_parallel=True, dtype=dt, device=device)
+        g = self.in_proj.tensor_parallel_group
+        self.I = I // g.size
+
+        def mk(*shape):
+            p = nn.Parameter(torch.zeros(*shape, dtype=dt, device=device), requires_grad=False)
+            p.partition_dim, p.tp_group = 0, g
+            return p
+        self.conv_weight = mk(self.I, self.K)
+        self.conv_bias = mk(self.I) if getattr(config, "mamba_conv_bias", True) else None
+        self.A_log, self.D = mk(self.I, self.N), mk(self.I)
+        self.bcdt_eps = float(getattr(config, "mixer_rms_eps", 1e-6)) if bcdt_rms else None
+        self.conv_state, self.ssm_state = f"m1_conv{i}", f"m1_ssm{i}"
+
+    def state_specs(self):
+        return {self.conv_state: (self.K - 1, self.I), self.ssm_state: ((self.I, self.N), torch.float32)}
+
+    def forward(self, xn, meta, kv_mgr):
+        B, T, _ = xn.shape
+        K, N, R = self.K, self.N, self.R
+        x, gate = self.in_proj(xn).chunk(2, -1)
+        lines, states = kv_mgr.lines_for(meta.seq_ids), kv_mgr.states
+        w = self.conv_weight.t().unsqueeze(0)
+        if meta.is_prefill:
+            if meta.has_prefix:
+                raise NotImplementedError("Mamba with a cached prefix")
+            n = _last_valid(meta, B, T, xn.device)
+            pad = F.pad(x, (0, 0, K - 1, 0))
+            conv = sum(pad[:, j:j + T] * w[:, j:j + 1] for j in range(K))
+            idx = (n.view(B, 1) + torch.arange(K - 1, device=xn.device).view(1, -1)).unsqueeze(-1).expand(B, K - 1, self.I)
+            states.write(self.conv_state, lines, pad.gather(1, idx))
+            valid = torch.arange(T, device=xn.device).view(1, T) < n.view(B, 1)
+            h = torch.zeros(B, self.I, N, dtype=torch.float32, device=xn.device)
+        else:
+            if T != 1:
+                raise NotImplementedError("Mamba takes one new token per decode step")
+            win = torch.cat([states.read(self.conv_state, lines).to(x.dtype), x], 1)
+            conv = (win * w).sum(1, keepdim=True)
+            states.write(self.conv_state, lines, win[:, 1:])
+            valid = torch.ones(B, 1, dtype=torch.bool, device=xn.device)
+            h = states.read(self.ssm_state, lines).float()
+        if self.conv_bias is not None:
+            conv = conv + self.conv_bias
+        u = F.silu(conv)
+        dtr, Bm, Cm = self.x_proj(u).split([R, N, N], -1)
+        if self.bcdt_eps is not None:
+            rms = lambda t: (t.float() * torch.rsqrt(t.float().pow(2).mean(-1, keepdim=True) + self.bcdt_eps)).to(t.dtype)     # noqa: E731
+            dtr, Bm, Cm = rms(dtr), rms(Bm), rms(Cm)
+        dt = F.softplus(self.dt_proj(dtr).float())                                                   # [B, T, I]
+        dt = torch.where(valid.unsqueeze(-1), dt, torch.zeros_like(dt))                              # padding: state carried through
+        A = -torch.exp(self.A_log.float())                                                            # [I, N]
+        uf, Bf, Cf = u.float(), Bm.float(), Cm.float()
+        ys = []
+        for t in range(T):
+            h = h * torch.exp(dt[:, t, :, None] * A) + (dt[:, t] * uf[:, t])[..., None] * Bf[:, t, None, :]
+            ys.append((h * Cf[:, t, None, :]).sum(-1))
+        states.write(self.ssm_state, lines, h)
+        y = (torch.stack(ys, 1) + uf * self.D.float()) * F.silu(gate.float())
+        return self.out_proj(y.to(xn.dtype))
+
+
+class Mamba1InferenceConfig(LlamaInferenceConfig):
+    attribute_map = {"state_size": "mamba_d_state", "conv_kernel": "mamba_d_conv", "time_step_rank": "mamba_dt_rank",
+                     "layer_norm_epsilon": "rms_norm_eps", "use_conv_bias": "mamba_conv_bias", "use_bias": "mamba_proj_bias"}
+
+    def get_required_attributes(self):
+        return ["hidden_size", "num_hidden_layers", "vocab_size", "mamba_d_state", "mamba_d_conv"]
+
+    def add_derived_config(self):
+        import math
+        self.mamba_d_inner = int(getattr(self, "intermediate_size", None) or getattr(self, "expand", 2) * self.hidden_size)
+        if isinstance(self.mamba_dt_rank, str) or self.mamba_dt_rank is None:                        # "auto"
+            self.mamba_dt_rank = math.ceil(self.hidden_size / 16)
+        self.num_attention_heads = self.num_key_value_heads = 1                                     # no attention: KV-cache plumbing placeholders
+        self.head_dim, self.intermediate_size = 8, self.mamba_d_inner
+        self.max_position_embeddings = getattr(self, "max_position_embeddings", None) or self.neuron_config.seq_len
+        self.hidden_act = getattr(self, "hidden_act", None) or "silu"
+        super().add_derived_config()
+
+
+class Mamba1Layer(nn.Module):
+    mlp_is_moe = False
+
+    def __init__(self, config, i, device=None, bcdt_rms=False):
+        super().__init__()
+        self.mixer = Mamba1Mixer(config, i, device, bcdt_rms=bcdt_rms)
+        self.norm = RMSNorm(config.hidden_size, config.rms_norm_eps, config.neuron_config.torch_dtype, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return self.mixer.state_specs()
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        return h + self.mixer(self.norm(h), meta, kv_mgr)
+
+
+class NeuronMambaModel(_HybridModel):
+    bcdt_rms = False
+
+    def make_layer(self, config, i, rotary, device):
+        return Mamba1Layer(config, i, device, bcdt_rms=self.bcdt_rms)
+
+
+class NeuronFalconMambaModel(NeuronMambaModel):
+    bcdt_rms = True
+
+
+class NeuronMambaForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronMambaModel
+    _STATE_DICT_MODEL_PREFIX = "backbone."
+
+    @classmethod
+    def get_config_cls(cls):
+        return Mamba1InferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        out = {}
+        for k, v in sd.items():
+            k = k.replace("embeddings.", "embed_tokens.").replace("norm_f.", "norm.")
+            if k.endswith(".mixer.conv1d.weight"):
+                k, v = k.replace(".conv1d.weight", ".conv_weight"), v.squeeze(1)
+            elif k.endswith(".mixer.conv1d.bias"):
+                k = k.replace(".conv1d.bias", ".conv_bias")
+            out[k] = v
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+class NeuronFalconMambaForCausalLM(NeuronMambaForCausalLM):
+    _model_cls = NeuronFalconMambaModel
+
+
+HYBRID_MODEL_TYPES = {"mamba": NeuronMambaForCausalLM, "falcon_mamba": NeuronFalconMambaForCausalLM, "nemotron_h": NeuronNemotronHForCausalLM, "lfm2_moe": NeuronLfm2MoeForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
