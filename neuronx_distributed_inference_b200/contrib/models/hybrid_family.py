@@ -12,6 +12,8 @@
 * **Granite-4.0 hybrid (``granitemoehybrid``)** — Bamba-style Mamba-2 / attention stack (RoPE or no positions at all) with the Granite
   multipliers and, per layer, an always-on shared SwiGLU plus an optional top-k MoE.
 * **Mamba / Falcon-Mamba** — attention-free Mamba-1 (per-channel selective SSM; Falcon-Mamba adds weight-free RMS on B, C, dt).
+* **Jamba** — Mamba-1 layers (learned norms on dt / B / C) with a position-free attention layer every few blocks and a top-k MoE
+  SwiGLU on alternating layers.
 * **Mamba-2 (Codestral-Mamba)** — attention-free: ``h += mixer(norm(h))`` per layer; the engine keeps a token-sized dummy KV cache.
 * **Falcon-H1** — every layer runs a Mamba-2 mixer and GQA attention IN PARALLEL on the same normed input and sums them; muP
   multipliers everywhere (all linear, folded into the weights at load).
@@ -1080,6 +1082,12 @@ class Mamba1Mixer(nn.Module):
         self.conv_bias = mk(self.I) if getattr(config, "mamba_conv_bias", True) else None
         self.A_log, self.D = mk(self.I, self.N), mk(self.I)
         self.bcdt_eps = float(getattr(config, "mixer_rms_eps", 1e-6)) if bcdt_rms else None
+        if bcdt_rms == "weighted":                                 # Jamba: learned RMSNorms on the low-rank dt, B and C (replicated)
+            self.bcdt_eps = None
+            self.dt_layernorm = RMSNorm(self.R, config.rms_norm_eps, dt, device=device)
+            self.b_layernorm = RMSNorm(self.N, config.rms_norm_eps, dt, device=device)
+            self.c_layernorm = RMSNorm(self.N, config.rms_norm_eps, dt, device=device)
+        self.weighted_norms = bcdt_rms == "weighted"
         self.conv_state, self.ssm_state = f"m1_conv{i}", f"m1_ssm{i}"
 
     def state_specs(self):
@@ -1116,6 +1124,8 @@ class Mamba1Mixer(nn.Module):
         if self.bcdt_eps is not None:
             rms = lambda t: (t.float() * torch.rsqrt(t.float().pow(2).mean(-1, keepdim=True) + self.bcdt_eps)).to(t.dtype)     # noqa: E731
             dtr, Bm, Cm = rms(dtr), rms(Bm), rms(Cm)
+        elif self.weighted_norms:
+            dtr, Bm, Cm = self.dt_layernorm(dtr), self.b_layernorm(Bm), self.c_layernorm(Cm)
         dt = F.softplus(self.dt_proj(dtr).float())                                                   # [B, T, I]
         dt = torch.where(valid.unsqueeze(-1), dt, torch.zeros_like(dt))                              # padding: state carried through
         A = -torch.exp(self.A_log.float())                                                            # [I, N]
@@ -1202,4 +1212,96 @@ class NeuronFalconMambaForCausalLM(NeuronMambaForCausalLM):
     _model_cls = NeuronFalconMambaModel
 
 
-HYBRID_MODEL_TYPES = {"mamba": NeuronMambaForCausalLM, "falcon_mamba": NeuronFalconMambaForCausalLM, "nemotron_h": NeuronNemotronHForCausalLM, "lfm2_moe": NeuronLfm2MoeForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}
+# ---------------------------------------------------------------------------------------------------------------------- Jamba
+class JambaInferenceConfig(LlamaInferenceConfig):
+    def add_derived_config(self):
+        import math
+        L = self.num_hidden_layers
+        self.mamba_d_inner = int(getattr(self, "mamba_expand", 2) * self.hidden_size)
+        if isinstance(getattr(self, "mamba_dt_rank", "auto"), str):
+            self.mamba_dt_rank = math.ceil(self.hidden_size / 16)
+        if not getattr(self, "layers_block_type", None):
+            p, o = getattr(self, "attn_layer_period", 8), getattr(self, "attn_layer_offset", 4)
+            self.layers_block_type = ["attention" if i % p == o else "mamba" for i in range(L)]
+        if not getattr(self, "layers_num_experts", None):
+            p, o = getattr(self, "expert_layer_period", 2), getattr(self, "expert_layer_offset", 1)
+            self.layers_num_experts = [self.num_experts if i % p == o else 1 for i in range(L)]
+        super().add_derived_config()
+
+    @classmethod
+    def get_neuron_config_cls(cls):
+        from ...config import MoENeuronConfig
+        return MoENeuronConfig
+
+
+class JambaLayer(nn.Module):
+    """AI21 Jamba: Mamba-1 (with learned dt / B / C norms) or position-free GQA attention, then a SwiGLU that is a softmax top-k MoE
+    (weights NOT renormalised) on every ``expert_layer_period``-th layer."""
+
+    def __init__(self, config, i, rotary, device=None):
+        super().__init__()
+        from ...modules.moe import ExpertMLPs, MoE, RouterTopK
+        dt, H = config.neuron_config.torch_dtype, config.hidden_size
+        self.is_attn = config.layers_block_type[i] == "attention"
+        if self.is_attn:
+            self.self_attn = NeuronLlamaAttention(config, i, rotary, device=device, use_rope=False)
+        else:
+            self.mamba = Mamba1Mixer(config, i, device, bcdt_rms="weighted")
+        E = int(config.layers_num_experts[i])
+        self.mlp_is_moe = E > 1
+        if self.mlp_is_moe:
+            self.mlp = MoE(RouterTopK(E, config.num_experts_per_tok, H, dt, "softmax", False, False, False, device),
+                           ExpertMLPs(E, H, config.intermediate_size, config.hidden_act, dt, device=device))
+        else:
+            self.mlp = GatedMLP(H, config.intermediate_size, config.hidden_act, dt, device=device)
+        self.input_layernorm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.pre_ff_layernorm = RMSNorm(H, config.rms_norm_eps, dt, device=device)
+        self.layer_idx = i
+
+    def state_specs(self):
+        return {} if self.is_attn else self.mamba.state_specs()
+
+    def forward(self, h, meta, kv_mgr, lora=None):
+        n = self.input_layernorm
+        if self.is_attn:
+            h = self.self_attn(h, meta, kv_mgr, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+        else:
+            h = h + self.mamba(n(h), meta, kv_mgr)
+        n = self.pre_ff_layernorm
+        return self.mlp(h, norm_weight=n.weight, norm_eps=n.variance_epsilon, residual=h)
+
+
+class NeuronJambaModel(_HybridModel):
+    def make_layer(self, config, i, rotary, device):
+        return JambaLayer(config, i, rotary, device)
+
+
+class NeuronJambaForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronJambaModel
+
+    @classmethod
+    def get_config_cls(cls):
+        return JambaInferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        from ...models.state_dict_utils import convert_moe_experts
+        out = {}
+        for k, v in sd.items():
+            k = k.replace("final_layernorm.", "norm.")
+            if k.endswith(".mamba.conv1d.weight"):
+                k, v = k.replace(".conv1d.weight", ".conv_weight"), v.squeeze(1)
+            elif k.endswith(".mamba.conv1d.bias"):
+                k = k.replace(".conv1d.bias", ".conv_bias")
+            out[k] = v
+        moe_layers = [i for i, e in enumerate(config.layers_num_experts) if int(e) > 1]
+        out = convert_moe_experts(out, config.num_hidden_layers, config.num_experts, moe_prefixes=("feed_forward",), gate_names=("router",),
+                                  w_names=("gate_proj", "up_proj", "down_proj"), layers=moe_layers)
+        out = {k.replace(".feed_forward.", ".mlp."): v for k, v in out.items()}
+        out = fuse_qkv_and_gate_up(out, config.num_hidden_layers)
+        if "lm_head.weight" not in out:
+            out["lm_head.weight"] = out["embed_tokens.weight"].clone()
+        return out
+
+
+HYBRID_MODEL_TYPES = {"jamba": NeuronJambaForCausalLM, "mamba": NeuronMambaForCausalLM, "falcon_mamba": NeuronFalconMambaForCausalLM, "nemotron_h": NeuronNemotronHForCausalLM, "lfm2_moe": NeuronLfm2MoeForCausalLM, "mamba2": NeuronMamba2ForCausalLM, "granitemoehybrid": NeuronGraniteHybridForCausalLM, "bamba": NeuronBambaForCausalLM, "falcon_h1": NeuronFalconH1ForCausalLM, "lfm2": NeuronLfm2ForCausalLM, "recurrent_gemma": NeuronRecurrentGemmaForCausalLM}

@@ -184,6 +184,10 @@ def _cfg(name):
                              tie_word_embeddings=False)
     if name == "falcon_mamba":
         return T.FalconMambaConfig(hidden_size=64, num_hidden_layers=3, vocab_size=160, state_size=8, conv_kernel=4, expand=2, time_step_rank=4)
+    if name == "jamba":
+        return T.JambaConfig(**{**BASE, "num_hidden_layers": 4}, num_experts=4, num_experts_per_tok=2, attn_layer_period=2, attn_layer_offset=1,
+                             expert_layer_period=2, expert_layer_offset=1, mamba_d_state=8, mamba_d_conv=4, mamba_expand=2, mamba_dt_rank=4,
+                             use_mamba_kernels=False, pad_token_id=0)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -202,7 +206,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe", "jais2", "mamba", "falcon_mamba",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe", "jais2", "mamba", "falcon_mamba", "jamba",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -226,7 +230,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     mask = torch.ones_like(ids)
     mask[1, 10:] = 0
     # transformers 5.5's CACHED Bamba decode drifts 5e-3 from its own full recompute; use the cache-free oracle there
-    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba", "falcon_mamba", "nemotron_h")))
+    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba", "falcon_mamba", "jamba", "nemotron_h")))
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"
