@@ -72,6 +72,8 @@ MODEL_TYPES.update({"ministral": {"causal-lm": f"{_R}:NeuronMinistralForCausalLM
 # Hugging Face model_type spellings of families registered above under the reference's names
 for _alias, _name in {"deepseek_v3": "deepseek", "gemma3_text": "gemma3", "llama4_text": "llama4", "code_llama": "llama"}.items():
     MODEL_TYPES[_alias] = {"causal-lm": MODEL_TYPES[_name]["causal-lm"]}
+_A = "neuronx_distributed_inference_b200.contrib.models.alibi_family"
+MODEL_TYPES.update({"bloom": {"causal-lm": f"{_A}:NeuronBloomForCausalLM"}, "mpt": {"causal-lm": f"{_A}:NeuronMptForCausalLM"}})
 _H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"
 MODEL_TYPES.update({"jamba": {"causal-lm": f"{_H}:NeuronJambaForCausalLM"}, "mamba": {"causal-lm": f"{_H}:NeuronMambaForCausalLM"}, "falcon_mamba": {"causal-lm": f"{_H}:NeuronFalconMambaForCausalLM"},
                     "nemotron_h": {"causal-lm": f"{_H}:NeuronNemotronHForCausalLM"}, "lfm2_moe": {"causal-lm": f"{_H}:NeuronLfm2MoeForCausalLM"}, "bamba": {"causal-lm": f"{_H}:NeuronBambaForCausalLM"}, "mamba2": {"causal-lm": f"{_H}:NeuronMamba2ForCausalLM"}, "granitemoehybrid": {"causal-lm": f"{_H}:NeuronGraniteHybridForCausalLM"}, "lfm2": {"causal-lm": f"{_H}:NeuronLfm2ForCausalLM"}, "falcon_h1": {"causal-lm": f"{_H}:NeuronFalconH1ForCausalLM"},
