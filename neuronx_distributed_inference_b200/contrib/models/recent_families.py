@@ -367,3 +367,42 @@ class NeuronJais2ForCausalLM(_ClassicCausalLM):
 
 
 RECENT_MODEL_TYPES["jais2"] = NeuronJais2ForCausalLM
+
+
+# ---- MLA decoders that reuse the DeepSeek-V3 implementation: GLM-4.7-Flash (``glm4_moe_lite``) and Youtu-LLM (dense MLA) ---------------
+def _mla_ports():
+    from ...models.deepseek.modeling_deepseek import DeepseekInferenceConfig, NeuronDeepseekForCausalLM
+
+    class Glm4MoeLiteConfig(DeepseekInferenceConfig):
+        def add_derived_config(self):
+            kinds = list(getattr(self, "mlp_layer_types", None) or [])
+            if kinds:                                             # dense layers first, sparse after (the only layout DeepSeek-style stacks use)
+                n_dense = kinds.index("sparse") if "sparse" in kinds else len(kinds)
+                if any(k != "sparse" for k in kinds[n_dense:]):
+                    raise NotImplementedError("dense layers after the first sparse layer")
+                self.first_k_dense_replace = n_dense
+            super().add_derived_config()
+
+    class YoutuConfig(DeepseekInferenceConfig):
+        def __init__(self, *a, **kw):
+            self.n_routed_experts, self.num_experts_per_tok = 0, 0          # dense model: no expert layers at all
+            super().__init__(*a, **kw)
+
+        def add_derived_config(self):
+            self.first_k_dense_replace = self.num_hidden_layers
+            super().add_derived_config()
+
+    class NeuronGlm4MoeLiteForCausalLM(NeuronDeepseekForCausalLM):
+        @classmethod
+        def get_config_cls(cls):
+            return Glm4MoeLiteConfig
+
+    class NeuronYoutuForCausalLM(NeuronDeepseekForCausalLM):
+        @classmethod
+        def get_config_cls(cls):
+            return YoutuConfig
+    return NeuronGlm4MoeLiteForCausalLM, NeuronYoutuForCausalLM
+
+
+NeuronGlm4MoeLiteForCausalLM, NeuronYoutuForCausalLM = _mla_ports()
+RECENT_MODEL_TYPES.update({"glm4_moe_lite": NeuronGlm4MoeLiteForCausalLM, "youtu": NeuronYoutuForCausalLM})
