@@ -406,3 +406,35 @@ def _mla_ports():
 
 NeuronGlm4MoeLiteForCausalLM, NeuronYoutuForCausalLM = _mla_ports()
 RECENT_MODEL_TYPES.update({"glm4_moe_lite": NeuronGlm4MoeLiteForCausalLM, "youtu": NeuronYoutuForCausalLM})
+
+
+# ---- Ministral-3: YaRN rotary + the Llama-4 position-dependent query temperature  q *= 1 + beta * log(1 + floor(pos / L0)) -------------
+class _Ministral3Attention(_LayerTypeAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        super().__init__(config, layer_idx, rotary_emb, device=device, **over)
+        rp = getattr(config, "rope_parameters", None) or {}
+        self.q_beta = float(rp.get("llama_4_scaling_beta") or 0.0)
+        self.q_l0 = float(rp.get("original_max_position_embeddings") or config.max_position_embeddings)
+
+    def _simple(self):                      # the fused rope + append kernels do not scale q: take the generic path
+        return self.q_beta == 0.0 and super()._simple()
+
+    def _split_norm_rope(self, qkv, B, T, cos, sin, meta=None):
+        q, k, v = super()._split_norm_rope(qkv, B, T, cos, sin, meta)
+        if self.q_beta:
+            pos = meta.position_ids if (meta is not None and meta.position_ids is not None) else torch.arange(T, device=q.device).view(1, T)
+            temp = 1.0 + self.q_beta * torch.log1p(torch.floor(pos.float() / self.q_l0))
+            q = q * temp.view(pos.shape[0], T, 1, 1).to(q.dtype)
+        return q, k, v
+
+
+class NeuronMinistral3Model(NeuronLlamaModel):
+    attention_cls = _Ministral3Attention
+    graph_safe = False
+
+
+class NeuronMinistral3ForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronMinistral3Model
+
+
+RECENT_MODEL_TYPES["ministral3"] = NeuronMinistral3ForCausalLM
