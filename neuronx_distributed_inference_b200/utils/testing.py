@@ -67,13 +67,18 @@ def perturb_constant_vectors(model, std: float = 0.1, seed: int = 1234):
     return model
 
 
-def save_random_hf_checkpoint(hf_config, out_dir: Optional[str] = None, seed: int = 0, dtype=torch.float32, perturb: bool = True) -> str:
+def save_random_hf_checkpoint(hf_config, out_dir: Optional[str] = None, seed: int = 0, dtype=torch.float32,
+                              perturb: Optional[bool] = None) -> str:
     """``AutoModelForCausalLM.from_config(...).save_pretrained`` — how the reference's integration tests
     make checkpoints without network access (test/integration/utils/test_utils.py:15-48).  ``perturb``: see
-    :func:`perturb_constant_vectors`."""
+    :func:`perturb_constant_vectors`; default: on for the fp32 CPU comparisons, off on a CUDA box (the bf16 GPU tolerances were set
+    on the plain Hugging Face initialisation).  ``B200_PERTURB_CKPT=0/1`` overrides."""
     from transformers import AutoModelForCausalLM
     torch.manual_seed(seed)
     model = AutoModelForCausalLM.from_config(hf_config).to(dtype).eval()
+    if perturb is None:
+        env = os.environ.get("B200_PERTURB_CKPT")
+        perturb = (env == "1") if env in ("0", "1") else not torch.cuda.is_available()
     if perturb:
         perturb_constant_vectors(model)
     out_dir = out_dir or tempfile.mkdtemp(prefix="nxdi_b200_ckpt_")
