@@ -438,3 +438,60 @@ class NeuronMinistral3ForCausalLM(NeuronLlamaForCausalLM):
 
 
 RECENT_MODEL_TYPES["ministral3"] = NeuronMinistral3ForCausalLM
+
+
+# ---- nanochat: weight-free RMSNorms everywhere (embeddings, blocks, q / k after the rotation, output), squared-ReLU MLP, logit soft-cap --
+class _NanoChatAttention(NeuronLlamaAttention):
+    def __init__(self, config, layer_idx, rotary_emb, device=None, **over):
+        super().__init__(config, layer_idx, rotary_emb, device=device, qk_norm="rms_post_rope", qk_norm_eps=config.rms_norm_eps, **over)
+
+    def _rope(self, meta):                  # nanochat rotates the pairs the other way round: (x1, x2) -> (x1 c + x2 s, x2 c - x1 s)
+        cos, sin = super()._rope(meta)
+        return cos, -sin
+
+
+class _NanoChatMLP(torch.nn.Module):
+    def __init__(self, config, device=None):
+        super().__init__()
+        from ...modules.mlp import PlainMLP
+        self.inner = PlainMLP(config.hidden_size, config.intermediate_size, config.hidden_act, config.neuron_config.torch_dtype, bias=False,
+                              device=device)
+
+    def forward(self, x, norm_weight=None, norm_eps=1e-6, norm_offset=0.0, residual=None, lora=None, adapter_ids=None):
+        from ... import ops
+        return self.inner(ops.rmsnorm(x, norm_weight, norm_eps, norm_offset) if norm_weight is not None else x, residual)
+
+
+class NeuronNanoChatModel(NeuronLlamaModel):
+    attention_cls = _NanoChatAttention
+    mlp_cls = _NanoChatMLP
+    graph_safe = False
+
+    def init_model(self, config):
+        super().init_model(config)
+        self.final_logit_softcap = getattr(config, "final_logit_softcapping", None)
+        self._embed_eps = config.rms_norm_eps
+
+    def embed(self, input_ids, inputs_embeds=None, vision_embeddings=None, vision_mask=None):
+        h = super().embed(input_ids, inputs_embeds, vision_embeddings, vision_mask)
+        return (h.float() * torch.rsqrt(h.float().pow(2).mean(-1, keepdim=True) + self._embed_eps)).to(h.dtype)
+
+
+class NeuronNanoChatForCausalLM(NeuronLlamaForCausalLM):
+    _model_cls = NeuronNanoChatModel
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        sd = fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
+        sd = {k.replace(".mlp.fc", ".mlp.inner.fc"): v for k, v in sd.items()}
+        dt = next(iter(sd.values())).dtype
+        for i in range(config.num_hidden_layers):                               # the checkpoint has no norm weights at all: unit weights
+            for n in ("input_layernorm", "post_attention_layernorm"):
+                sd[f"layers.{i}.{n}.weight"] = torch.ones(config.hidden_size, dtype=dt)
+            for n in ("q_layernorm", "k_layernorm"):
+                sd[f"layers.{i}.self_attn.{n}.weight"] = torch.ones(config.head_dim, dtype=dt)
+        sd["norm.weight"] = torch.ones(config.hidden_size, dtype=dt)
+        return sd
+
+
+RECENT_MODEL_TYPES["nanochat"] = NeuronNanoChatForCausalLM

@@ -68,7 +68,7 @@ MODEL_TYPES.update({"ministral": {"causal-lm": f"{_R}:NeuronMinistralForCausalLM
                     "olmo": {"causal-lm": f"{_R}:NeuronOlmoForCausalLM"}, "hunyuan_v1_moe": {"causal-lm": f"{_R}:NeuronHunYuanMoEForCausalLM"},
                     "flex_olmo": {"causal-lm": f"{_R}:NeuronFlexOlmoForCausalLM"}, "minimax_m2": {"causal-lm": f"{_R}:NeuronMiniMaxM2ForCausalLM"},
                     "solar_open": {"causal-lm": f"{_R}:NeuronSolarOpenForCausalLM"}, "exaone_moe": {"causal-lm": f"{_R}:NeuronExaoneMoeForCausalLM"}, "jais2": {"causal-lm": f"{_R}:NeuronJais2ForCausalLM"}, "glm4_moe_lite": {"causal-lm": f"{_R}:NeuronGlm4MoeLiteForCausalLM"},
-                    "youtu": {"causal-lm": f"{_R}:NeuronYoutuForCausalLM"}, "ministral3": {"causal-lm": f"{_R}:NeuronMinistral3ForCausalLM"},
+                    "youtu": {"causal-lm": f"{_R}:NeuronYoutuForCausalLM"}, "ministral3": {"causal-lm": f"{_R}:NeuronMinistral3ForCausalLM"}, "nanochat": {"causal-lm": f"{_R}:NeuronNanoChatForCausalLM"},
                     "granitemoeshared": {"causal-lm": f"{_R}:NeuronGraniteMoeSharedForCausalLM"}})
 # Hugging Face model_type spellings of families registered above under the reference's names
 for _alias, _name in {"deepseek_v3": "deepseek", "gemma3_text": "gemma3", "llama4_text": "llama4", "code_llama": "llama"}.items():

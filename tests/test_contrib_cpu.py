@@ -204,6 +204,8 @@ def _cfg(name):
         return T.Ministral3Config(**BASE, head_dim=16, pad_token_id=0, sliding_window=None,
                                   rope_parameters=dict(rope_type="yarn", rope_theta=10000.0, factor=4.0, original_max_position_embeddings=8,
                                                        beta_fast=32.0, beta_slow=1.0, mscale=1.0, mscale_all_dim=1.0, llama_4_scaling_beta=0.3))
+    if name == "nanochat":
+        return T.NanoChatConfig(**BASE, final_logit_softcapping=5.0)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -222,7 +224,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe", "jais2", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe", "jais2", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nanochat",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -247,7 +249,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     mask = torch.ones_like(ids)
     mask[1, 10:] = 0
     # transformers 5.5's CACHED Bamba decode drifts 5e-3 from its own full recompute; use the cache-free oracle there
-    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nemotron_h")))
+    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nanochat", "nemotron_h")))
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"
