@@ -381,7 +381,7 @@ class NeuronPhiForCausalLM(_ClassicCausalLM):
         return fuse_qkv_and_gate_up(sd, config.num_hidden_layers, fuse_mlp=False)
 
 
-# ---- Falcon (7B-style: multi-query, parallel attention + MLP behind one LayerNorm) ---------------------------------------------------
+# ---- Falcon (7B: multi-query, one LayerNorm; 40B / 180B / Falcon2: grouped-query, per-branch LayerNorms), parallel attention + MLP ---------------------------------------------------
 class FalconInferenceConfig(ClassicInferenceConfig):
     def add_derived_config(self):
         if getattr(self, "new_decoder_architecture", False):
@@ -393,14 +393,16 @@ class FalconInferenceConfig(ClassicInferenceConfig):
 
     def validate_config(self):
         super().validate_config()
-        if getattr(self, "alibi", False) or getattr(self, "new_decoder_architecture", False) or not getattr(self, "parallel_attn", True):
-            raise NotImplementedError("Falcon: only the rotary, parallel-attention, classic (7B-style) layout is implemented")
+        if getattr(self, "alibi", False) or not (getattr(self, "parallel_attn", True) or getattr(self, "new_decoder_architecture", False)):
+            raise NotImplementedError("Falcon: the rotary, parallel-attention layouts (7B-style and the 40B / 180B / Falcon2 decoder) are implemented")
 
 
 class NeuronFalconModel(NeuronClassicModel):
     def layer_spec(self, config, i):
         b = bool(getattr(config, "bias", False))
-        return dict(parallel=True, shared_norm=True, norm_bias=True, mlp="plain", act="gelu", qkv_bias=b, o_bias=b, mlp_bias=b)
+        # 40B / 180B decoder: grouped-query attention and separate LayerNorms in front of the attention and the MLP branches
+        two_ln = bool(getattr(config, "new_decoder_architecture", False)) and (getattr(config, "num_ln_in_parallel_attn", None) or 2) == 2
+        return dict(parallel=True, shared_norm=not two_ln, norm_bias=True, mlp="plain", act="gelu", qkv_bias=b, o_bias=b, mlp_bias=b)
 
 
 class NeuronFalconForCausalLM(_ClassicCausalLM):
@@ -419,7 +421,13 @@ class NeuronFalconForCausalLM(_ClassicCausalLM):
             k = (k.replace(".self_attention.query_key_value.", ".self_attn.qkv_proj.").replace(".self_attention.dense.", ".self_attn.o_proj.")
                  .replace(".mlp.dense_h_to_4h.", ".mlp.fc1.").replace(".mlp.dense_4h_to_h.", ".mlp.fc2."))
             k = k.replace("word_embeddings.", "embed_tokens.").replace("ln_f.", "norm.")
-            out[k] = v        # multi-query fused QKV is already [q heads; k; v]
+            k = k.replace(".ln_attn.", ".input_layernorm.").replace(".ln_mlp.", ".post_attention_layernorm.")
+            if ".self_attn.qkv_proj." in k and getattr(config, "new_decoder_architecture", False):
+                # rows are [kv group, (its q heads..., k, v), D]  ->  [all q heads; all k; all v]
+                nkv, D = config.num_key_value_heads, config.hidden_size // config.num_attention_heads
+                w = v.view(nkv, config.num_attention_heads // nkv + 2, D, *v.shape[1:])
+                v = torch.cat([w[:, :-2].reshape(-1, *v.shape[1:]), w[:, -2].reshape(-1, *v.shape[1:]), w[:, -1].reshape(-1, *v.shape[1:])], 0)
+            out[k] = v        # (7B-style multi-query fused QKV is already [q heads; k; v])
         if "lm_head.weight" not in out:
             out["lm_head.weight"] = out["embed_tokens.weight"].clone()
         return out
