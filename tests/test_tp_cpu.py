@@ -78,11 +78,11 @@ def _contrib_cfg(name):
 
 def test_contrib_families_tp2_gloo_match_hf(tmp_path):
     """The sharding metadata of the contrib blocks (3-way fused conv projection, head-sharded RG-LRU gates, replicated Mamba-2 mixer,
-    q-head-aligned attention gate, expert sharding, per-head LayerNorm) non-gated experts) under a real 2-rank gloo group — ten configurations in one launch."""
+    q-head-aligned attention gate, expert sharding, per-head LayerNorm) non-gated experts) under a real 2-rank gloo group — eleven configurations in one launch."""
     from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
     # falcon_h1: Mamba-2 heads / groups sharded (2 groups on 2 ranks); falcon_h1_one_group: ONE group spanning both ranks with the gated
     # group norm (its sum of squares is combined across the ranks)
-    names = ["lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_one_group", "afmoe", "phimoe", "persimmon", "nemotron_h", "falcon_mamba", "bloom"]
+    names = ["lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_one_group", "afmoe", "phimoe", "persimmon", "nemotron_h", "falcon_mamba", "bloom", "qwen3_next"]
     ckpts = [save_random_hf_checkpoint(_contrib_cfg(n), str(tmp_path / n), seed=4) for n in names]
     out = _run(2, ",".join(ckpts), 29560, MODEL_TYPE=",".join(n.replace("_one_group", "") for n in names), DUMP_AFTER="500")
     assert out.count('"ok": true') == len(names)
