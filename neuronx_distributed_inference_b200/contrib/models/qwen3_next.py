@@ -222,3 +222,43 @@ class NeuronQwen3NextForCausalLM(NeuronLlamaForCausalLM):
         if "lm_head.weight" not in out:
             out["lm_head.weight"] = out["embed_tokens.weight"].clone()
         return out
+
+
+# ---- Qwen3.5 (text decoders): the same block; the DeltaNet projections are stored as four flat matrices ------------------------------------
+class NeuronQwen3_5ForCausalLM(NeuronQwen3NextForCausalLM):
+    """``qwen3_5_text`` / ``qwen3_5_moe_text`` (and the language model inside the ``qwen3_5`` / ``qwen3_5_moe`` checkpoints): in_proj_qkv
+    ``[q | k | v]``, in_proj_z, in_proj_b, in_proj_a are regrouped per key head into the fused layout of :class:`GatedDeltaNet`."""
+    _STATE_DICT_MODEL_PREFIX = "model.language_model."
+
+    @classmethod
+    def get_config_cls(cls):
+        class Qwen3_5InferenceConfig(Qwen3NextInferenceConfig):
+            def __init__(self, *a, **kw):
+                self.intermediate_size = None                                             # all-MoE checkpoints do not state a dense width
+                super().__init__(*a, **kw)
+
+            def add_derived_config(self):
+                if not hasattr(self, "num_experts") or self.num_experts is None:
+                    self.num_experts, self.num_experts_per_tok = 0, 0                     # dense variant
+                if not getattr(self, "intermediate_size", None):
+                    self.intermediate_size = self.moe_intermediate_size
+                super().add_derived_config()
+        return Qwen3_5InferenceConfig
+
+    @staticmethod
+    def convert_hf_to_neuron_state_dict(sd, config):
+        nk, nv, dk, dv = config.linear_num_key_heads, config.linear_num_value_heads, config.linear_key_head_dim, config.linear_value_head_dim
+        r, KD = nv // nk, config.linear_num_key_heads * config.linear_key_head_dim
+        sd = {(k[len("model."):] if k.startswith("model.") and not k.startswith("model.language_model.") else k): v for k, v in sd.items()
+              if not k.startswith(("model.visual.", "visual.", "mtp."))}
+        for i, kind in enumerate(config.layer_types):
+            b = f"layers.{i}.linear_attn."
+            if kind == "full_attention" or b + "in_proj_qkv.weight" not in sd:
+                continue
+            qkv, z = sd.pop(b + "in_proj_qkv.weight"), sd.pop(b + "in_proj_z.weight")
+            H = qkv.shape[-1]
+            q, k, v = qkv[:KD].view(nk, dk, H), qkv[KD:2 * KD].view(nk, dk, H), qkv[2 * KD:].view(nk, r * dv, H)
+            sd[b + "in_proj_qkvz.weight"] = torch.cat([q, k, v, z.view(nk, r * dv, H)], 1).reshape(-1, H).contiguous()
+            bb, aa = sd.pop(b + "in_proj_b.weight").view(nk, r, H), sd.pop(b + "in_proj_a.weight").view(nk, r, H)
+            sd[b + "in_proj_ba.weight"] = torch.cat([bb, aa], 1).reshape(-1, H).contiguous()
+        return NeuronQwen3NextForCausalLM.convert_hf_to_neuron_state_dict(sd, config)

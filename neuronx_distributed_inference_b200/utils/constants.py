@@ -74,6 +74,8 @@ MODEL_TYPES.update({"ministral": {"causal-lm": f"{_R}:NeuronMinistralForCausalLM
 for _alias, _name in {"deepseek_v3": "deepseek", "gemma3_text": "gemma3", "llama4_text": "llama4", "code_llama": "llama"}.items():
     MODEL_TYPES[_alias] = {"causal-lm": MODEL_TYPES[_name]["causal-lm"]}
 MODEL_TYPES["qwen3_next"] = {"causal-lm": "neuronx_distributed_inference_b200.contrib.models.qwen3_next:NeuronQwen3NextForCausalLM"}
+for _t in ("qwen3_5_text", "qwen3_5_moe_text"):
+    MODEL_TYPES[_t] = {"causal-lm": "neuronx_distributed_inference_b200.contrib.models.qwen3_next:NeuronQwen3_5ForCausalLM"}
 _A = "neuronx_distributed_inference_b200.contrib.models.alibi_family"
 MODEL_TYPES.update({"bloom": {"causal-lm": f"{_A}:NeuronBloomForCausalLM"}, "mpt": {"causal-lm": f"{_A}:NeuronMptForCausalLM"}})
 _H = "neuronx_distributed_inference_b200.contrib.models.hybrid_family"

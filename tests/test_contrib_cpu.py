@@ -213,6 +213,13 @@ def _cfg(name):
         return T.Qwen3NextConfig(**{**BASE, "num_hidden_layers": 4}, head_dim=16, linear_num_value_heads=4, linear_num_key_heads=2,
                                  linear_key_head_dim=8, linear_value_head_dim=8, linear_conv_kernel_dim=4, num_experts=4, num_experts_per_tok=2,
                                  moe_intermediate_size=32, shared_expert_intermediate_size=48, pad_token_id=0)
+    if name in ("qwen3_5_moe_text", "qwen3_5_text"):
+        lin = dict(hidden_size=64, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160,
+                   max_position_embeddings=256, linear_num_value_heads=4, linear_num_key_heads=2, linear_key_head_dim=8, linear_value_head_dim=8,
+                   linear_conv_kernel_dim=4, pad_token_id=0)
+        if name == "qwen3_5_text":
+            return T.Qwen3_5TextConfig(**lin, intermediate_size=128)
+        return T.Qwen3_5MoeTextConfig(**lin, num_experts=4, num_experts_per_tok=2, moe_intermediate_size=32, shared_expert_intermediate_size=48)
     if name == "nemotron_h":
         return T.NemotronHConfig(hidden_size=64, intermediate_size=128, layers_block_type=["mamba", "moe", "attention", "moe", "mamba"],
                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, vocab_size=160, mamba_num_heads=8, mamba_head_dim=16,
@@ -231,7 +238,7 @@ def _cfg(name):
                                   "gpt_neox", "gpt2", "helium", "ernie4_5", "arcee", "hunyuan_v1_dense", "opt", "gptj", "phi",
                                   "falcon", "gpt_bigcode", "gpt_neo", "biogpt", "qwen2_moe", "olmoe", "exaone4", "gemma", "vaultgemma",
                                   "glm", "cohere2", "apertus", "nemotron", "persimmon", "xglm", "codegen", "granitemoe", "phimoe", "glm4_moe", "dots1", "ernie4_5_moe", "deepseek_v2", "lfm2", "recurrent_gemma", "falcon_h1", "falcon_h1_gated_norm", "falcon_h1_one_group", "bamba", "granitemoehybrid",
-                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe", "jais2", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nanochat", "falcon_40b_style", "falcon2_style", "qwen3_next",
+                                  "granitemoehybrid_dense_nope", "mamba2", "nemotron_h", "afmoe", "ministral", "cwm", "olmo", "hunyuan_v1_moe", "flex_olmo", "granitemoeshared", "lfm2_moe", "minimax_m2", "solar_open", "exaone_moe", "jais2", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nanochat", "falcon_40b_style", "falcon2_style", "qwen3_next", "qwen3_5_moe_text", "qwen3_5_text",
                                   "openai-gpt"])
 def test_contrib_family_matches_hf(name, tmp_path):
     from transformers import AutoModelForCausalLM
@@ -245,8 +252,8 @@ def test_contrib_family_matches_hf(name, tmp_path):
     from neuronx_distributed_inference_b200.contrib.models.hybrid_family import HYBRID_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.recent_families import RECENT_MODEL_TYPES
     from neuronx_distributed_inference_b200.contrib.models.alibi_family import ALIBI_MODEL_TYPES
-    from neuronx_distributed_inference_b200.contrib.models.qwen3_next import NeuronQwen3NextForCausalLM
-    cls = {"qwen3_next": NeuronQwen3NextForCausalLM, **ALIBI_MODEL_TYPES, **RECENT_MODEL_TYPES, **CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_40b_style", "").replace("falcon2_style", "falcon").replace("_gated_norm", "").replace("_one_group", "").replace("_dense_nope", "")]
+    from neuronx_distributed_inference_b200.contrib.models.qwen3_next import NeuronQwen3_5ForCausalLM, NeuronQwen3NextForCausalLM
+    cls = {"qwen3_next": NeuronQwen3NextForCausalLM, "qwen3_5_moe_text": NeuronQwen3_5ForCausalLM, "qwen3_5_text": NeuronQwen3_5ForCausalLM, **ALIBI_MODEL_TYPES, **RECENT_MODEL_TYPES, **CONTRIB_MODEL_TYPES, **CLASSIC_MODEL_TYPES, **MOE_MODEL_TYPES, **MORE_MODEL_TYPES, **HYBRID_MODEL_TYPES}[name.replace("_40b_style", "").replace("falcon2_style", "falcon").replace("_gated_norm", "").replace("_one_group", "").replace("_dense_nope", "")]
     nc = cls.get_neuron_config_cls()(batch_size=2, seq_len=48, max_context_length=24, torch_dtype="float32", on_cpu=True, output_logits=True)
     app = cls(ckpt, cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt)))
     app.load(None, skip_warmup=True)
@@ -257,7 +264,7 @@ def test_contrib_family_matches_hf(name, tmp_path):
     mask = torch.ones_like(ids)
     mask[1, 10:] = 0
     # transformers 5.5's CACHED Bamba decode drifts 5e-3 from its own full recompute; use the cache-free oracle there
-    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nanochat", "falcon_40b_style", "falcon2_style", "qwen3_next", "nemotron_h")))
+    exp, toks = generate_expected_logits(hf, ids, mask, 10, use_cache=not name.startswith(("bamba", "granitemoehybrid", "mamba", "falcon_mamba", "jamba", "bloom", "mpt", "glm4_moe_lite", "youtu", "ministral3", "nanochat", "falcon_40b_style", "falcon2_style", "qwen3_next", "qwen3_5_moe_text", "qwen3_5_text", "nemotron_h")))
     got = teacher_forced_logits(app, ids, mask, toks)
     err = ((got - exp).norm() / exp.norm()).item()
     assert err < 3e-4, f"{name}: relative logit error {err}"
