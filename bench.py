@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--ctx", type=int, default=128)
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--skip-ci", action="store_true")
+    ap.add_argument("--shard-shapes", type=int, default=1,
+                    help="DIAGNOSTIC (1 GPU): run the per-rank shapes of TP=N without the collectives (compute-only share of a TP step)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -265,6 +267,11 @@ def main():
 
     seq_len = args.ctx + args.steps + args.warmup + 8
     cfg = dict(LLAMA31_8B, num_hidden_layers=args.layers)
+    if args.shard_shapes > 1:
+        n = args.shard_shapes
+        cfg.update(num_attention_heads=32 // n, num_key_value_heads=max(1, 8 // n), intermediate_size=14336 // n,
+                   vocab_size=128256 // n)
+        args.skip_ci = True
     app = build_app(cfg, args.gpus, args.batch, seq_len, args.ctx, async_mode=False)
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
@@ -293,7 +300,8 @@ def main():
     except Exception:
         pass
     out = {
-        "metric": "llama3.1-8b_decode_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
+        "metric": "llama3.1-8b_decode_tokens_per_sec" if args.shard_shapes == 1 else
+                  f"DIAGNOSTIC_tp{args.shard_shapes}_rank_shapes_no_collectives_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": tok_s / BASELINE_TOK_S, "dtype": "bf16", "data": "synthetic",
         "impl": "ours", "ttft_p50_ms": m["ttft_p50_ms"],

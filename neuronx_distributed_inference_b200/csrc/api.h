@@ -11,9 +11,9 @@ constexpr int SYMM_MAX_TILES = 1024;
 constexpr int GEMV_MAX_T = 8;
 
 struct SymmArgs {
-  float* recv[SYMM_MAX_RANKS];      // peer-mapped receive buffers  [2][tp][8][n_max] x {fp32 value, u32 flag} (v1: fp32 only)
-  uint32_t* flags[SYMM_MAX_RANKS];  // peer-mapped flags            [2][tp][SYMM_MAX_TILES]
-  int rank, world, parity, n_max;
+  float* recv[SYMM_MAX_RANKS];  // peer-mapped LL receive buffers  [2 parity][world src][8 tok][n_max] x {fp32 value, u32 tag}
+  const uint32_t* step;         // device-side step counter (bumped once per forward); tag = (step << 8 | call) + 1
+  int rank, world, parity, n_max, call;
 };
 
 struct GemvParams {
@@ -29,8 +29,6 @@ struct GemvParams {
   int act;        // 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up
   int x_in_smem;  // 0: read (already normalised) x through L1 from global
   int wdtype;     // 0 bf16, 1 int8, 2 fp8 e4m3
-  const void* pf_w;  // weights of the NEXT skinny GEMM in the stream (L2 prefetch of its first ring fill) or null
-  int pf_N, pf_K, pf_glu;
   SymmArgs symm;
 };
 
@@ -40,13 +38,13 @@ void gemv_launch(const GemvParams& p, int mode, cudaStream_t stream);  // mode 0
 bool gemv2_supported(int T, int K);
 int gemv2_grid(int N, int K, bool glu);
 int gemv2_pmax(int N, int K, bool glu);
+int gemv2_ntiles(int N, bool glu);
+// debug timeline (tools/prof_decode.py): every decode kernel launched while a buffer is set claims the next slot of 148 x 8 u64
+void gemv2_set_prof(unsigned long long* base, long long n_launches);
+long long prof_next_slot();
+long long prof_count();
+unsigned long long* prof_slot_ptr(long long slot);
 void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* tickets, cudaStream_t stream);
-// chain of up to 4 dependent skinny GEMMs in one persistent launch (gemv2.cu)
-bool gemv_chain_supported(int T, int K_max);
-size_t gemv_chain_ws_floats(const GemvParams* ph, int n);
-size_t gemv_chain_tickets(const GemvParams* ph, int n);
-void gemv_chain_launch(const GemvParams* ph, const int* modes, int n, float* ws_part, unsigned* tickets, unsigned* bar,
-                       cudaStream_t stream);
 // tcgen05 / TMEM / TMA GEMM (gemm_tcgen05.cu): C[M,N_out] = epi(A[M,K] · B[N,K]^T)
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
                          int N, int K, int act, cudaStream_t stream);
@@ -61,8 +59,14 @@ void kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void*
 void paged_kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* slots, int ntok,
                             int tok_bytes, int n_slots, cudaStream_t stream);
 
+// vocabulary-sharded arg-max: per-row {value, global index} exchanged over NVLink LL slots inside the kernel
+struct ArgmaxSymm {
+  float* slots[SYMM_MAX_RANKS];  // peer-mapped  [2 parity][rows_max][world src][2] x {payload, u32 tag}
+  const uint32_t* step;
+  int rank, world, parity, call, rows_max;
+};
 void argmax_launch(const void* logits, int dtype /*0 f32, 1 bf16*/, int64_t* out, float* ws_val, int* ws_idx,
-                   unsigned* tickets, int B, int V, int ld, int nsplit, cudaStream_t stream);
+                   unsigned* tickets, int B, int V, int ld, int nsplit, const ArgmaxSymm* symm, cudaStream_t stream);
 void topk_sample_launch(const void* logits, int dtype, const int* top_k, const float* top_p, const float* temperature,
                         const float* rand, int64_t* out, int B, int V, int ld, int K, cudaStream_t stream);
 

@@ -51,6 +51,7 @@ struct AttnArgs {
   __nv_bfloat16* k_w;
   __nv_bfloat16* v_w;
   float norm_eps;
+  unsigned long long* prof;  // debug timeline or null
   int causal;  // prefill: 1 = causal (default), 0 = bidirectional (encoders: vision towers, Whisper, diffusion)
 };
 
@@ -59,8 +60,9 @@ __device__ __forceinline__ int swz(int row, int chunk) {  // element offset of a
   return row * D + ((chunk ^ (row & 7)) << 3);
 }
 
-// ATT_STAGES: cp.async ring depth.  4 for short decode contexts (a <=256-key context is fetched in one go, the step is
-// latency bound); 2 elsewhere (80 KB of shared memory -> two CTAs per SM, which the bandwidth/FLOP-bound cases need).
+// ATT_STAGES: cp.async ring depth.  3 for short decode contexts (latency bound: 3 x 64 keys in flight; 112 KB at D=128 so that
+// the CTA still co-resides with a ~108 KB decode GEMV CTA whose producer is prefetching the next projection's weights);
+// 2 elsewhere (80 KB of shared memory -> two CTAs per SM, which the bandwidth/FLOP-bound cases need).
 template <int D, int MODE, int ATT_STAGES>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p) {
   constexpr int CH = D / 8;  // 16-byte chunks per row
@@ -68,16 +70,30 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [64][D]
   __nv_bfloat16* sK = sQ + 64 * D;                                 // [STAGES][64][D]
   __nv_bfloat16* sV = sK + ATT_STAGES * 64 * D;                    // [STAGES][64][D]
+  __nv_bfloat16* sNew = sV + ATT_STAGES * 64 * D;                  // fused decode: [2 (k,v)][T][D] rows of this step
   __shared__ float sM[4][16], sL[4][16];
   __shared__ int s_pos[64];
+  __shared__ int s_wp[64];
   __shared__ bool s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int G = p.Hq / p.Hkv;
 
+  // Fused decode (q/k/v straight from the QKV projection) splits the kernel at the dependency: everything that only needs
+  // the step's inputs (positions, cache lines) and the cache rows of EARLIER steps — the tile ranges, the first ring fill of
+  // K/V tiles, cos/sin — runs BEFORE griddepcontrol.wait and overlaps the QKV projection; after the wait only the new rows are
+  // fetched, rotated, written to the cache (for later steps) and patched into the resident tiles from shared memory.
+  const bool fused = (MODE == ATTN_DECODE) && p.qkv != nullptr;
+  unsigned long long* prof = p.prof ? p.prof + (size_t)(blockIdx.x + blockIdx.y * gridDim.x) * 8 : nullptr;
+  if (prof && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prof[0] = t;
+    prof[1] = clock64();
+  }
   pdl_launch_dependents();
-  pdl_wait();
+  if (!fused) pdl_wait();
 
   // ---- work decomposition ----------------------------------------------------------------------------
   int b, kvh, split = 0, R, qh0 = 0, tok0 = 0;
@@ -130,88 +146,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
   const int t_beg = t_lo + split * tps;
   const int t_end = min(nt, t_beg + tps);
 
-  // ---- fused prologue: RMSNorm + RoPE on q (-> sQ) and on the new k rows; k/v appended to the cache ----------
-  // Every split-CTA of this (batch, kv head) writes the same rows (identical values), so whichever CTA owns the
-  // tile that contains the new positions reads its own writes: no inter-CTA ordering is needed.
-  const bool fused = (MODE == ATTN_DECODE) && p.qkv != nullptr;
-  if (fused) {
-    constexpr int HALF = D / 2, PPL = HALF / 32;
-    const int nrows = R + 2 * p.T;
-    for (int i = tid; i < (64 - R) * CH; i += ATT_THREADS)   // rows past R stay zero
-      *reinterpret_cast<uint4*>(sQ + swz<D>(R + i / CH, i % CH)) = make_uint4(0u, 0u, 0u, 0u);
-    for (int row = warp; row < nrows; row += ATT_THREADS / 32) {
-      int t, head, kind;
-      if (row < R) { t = row / G; head = kvh * G + row % G; kind = 0; }
-      else if (row < R + p.T) { t = row - R; head = p.Hq + kvh; kind = 1; }
-      else { t = row - R - p.T; head = p.Hq + p.Hkv + kvh; kind = 2; }
-      const size_t bt = (size_t)b * p.T + t;
-      const __nv_bfloat16* src = p.qkv + (bt * (p.Hq + 2 * p.Hkv) + head) * D;
-      float x1[PPL], x2[PPL];
-#pragma unroll
-      for (int j = 0; j < PPL; ++j) {
-        x1[j] = __bfloat162float(src[lane + 32 * j]);
-        x2[j] = __bfloat162float(src[lane + 32 * j + HALF]);
-      }
-      if (kind != 2) {
-        const __nv_bfloat16* nw = kind == 0 ? p.q_norm : p.k_norm;
-        if (nw != nullptr) {
-          float ss = 0.f;
-#pragma unroll
-          for (int j = 0; j < PPL; ++j) ss += x1[j] * x1[j] + x2[j] * x2[j];
-          ss = warp_sum(ss);
-          const float rstd = rsqrtf(ss / (float)D + p.norm_eps);
-#pragma unroll
-          for (int j = 0; j < PPL; ++j) {   // rounded to bf16 before the rotation, like the unfused path
-            x1[j] = __bfloat162float(__float2bfloat16(x1[j] * rstd * __bfloat162float(nw[lane + 32 * j])));
-            x2[j] = __bfloat162float(__float2bfloat16(x2[j] * rstd * __bfloat162float(nw[lane + 32 * j + HALF])));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < PPL; ++j) {
-          const float cs = p.cos[bt * HALF + lane + 32 * j], sn = p.sin[bt * HALF + lane + 32 * j];
-          const float o1 = x1[j] * cs - x2[j] * sn, o2 = x2[j] * cs + x1[j] * sn;
-          x1[j] = o1;
-          x2[j] = o2;
-        }
-      }
-      if (kind == 0) {
-#pragma unroll
-        for (int j = 0; j < PPL; ++j) {
-          const int c1 = lane + 32 * j, c2 = c1 + HALF;
-          sQ[swz<D>(row, c1 >> 3) + (c1 & 7)] = __float2bfloat16(x1[j]);
-          sQ[swz<D>(row, c2 >> 3) + (c2 & 7)] = __float2bfloat16(x2[j]);
-        }
-      } else {
-        const int wp = p.write_pos[bt];
-        if (seq_ok && wp >= 0 && wp < p.S) {
-          __nv_bfloat16* dst = (kind == 1 ? p.k_w : p.v_w) + (((size_t)line * p.Hkv + kvh) * p.S + wp) * D;
-#pragma unroll
-          for (int j = 0; j < PPL; ++j) {
-            dst[lane + 32 * j] = __float2bfloat16(x1[j]);
-            dst[lane + 32 * j + HALF] = __float2bfloat16(x2[j]);
-          }
-        }
-      }
-    }
-    __threadfence();
-    __syncthreads();
-  }
-
-  // ---- Q tile -> shared (swizzled), then A fragments ----------------------------------------------------
-  for (int i = tid; i < (fused ? 0 : 64 * CH); i += ATT_THREADS) {
-    const int r = i / CH, c = i % CH;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (r < R) {
-      const __nv_bfloat16* src;
-      if (MODE == ATTN_PREFILL)
-        src = p.q + (((size_t)b * p.T + tok0 + r) * p.Hq + qh0) * D;
-      else
-        src = p.q + (((size_t)b * p.T + r / G) * p.Hq + kvh * G + r % G) * D;
-      val = *reinterpret_cast<const uint4*>(src + c * 8);
-    }
-    *reinterpret_cast<uint4*>(sQ + swz<D>(r, c)) = val;
-  }
-
   auto load_tile = [&](int tile, int buf) {
     __nv_bfloat16* dK = sK + buf * 64 * D;
     __nv_bfloat16* dV = sV + buf * 64 * D;
@@ -233,12 +167,141 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
       cp_async16(dV + swz<D>(r, c), p.v + off + c * 8, ok);
     }
   };
-
+  auto prefetch_ring = [&]() {
 #pragma unroll
-  for (int s = 0; s < ATT_STAGES - 1; ++s) {
-    if (t_beg + s < t_end) load_tile(t_beg + s, s);
-    cp_async_commit();  // one group per tile slot (possibly empty) keeps the wait arithmetic uniform
+    for (int s = 0; s < ATT_STAGES - 1; ++s) {
+      if (t_beg + s < t_end) load_tile(t_beg + s, s);
+      cp_async_commit();  // one group per tile slot (possibly empty) keeps the wait arithmetic uniform
+    }
+  };
+
+  // ---- fused prologue: RMSNorm + RoPE on q (-> sQ) and on the new k rows; k/v appended to the cache ----------
+  // Every split-CTA of this (batch, kv head) computes the same new rows (identical values) and patches its own tiles, so no
+  // inter-CTA ordering is needed; the global write only serves later steps.
+  int new_tile_lo = 0x7fffffff, new_tile_hi = -1;
+  if (fused) {
+    constexpr int HALF = D / 2, PPL = HALF / 32;
+    prefetch_ring();                                         // old rows: safe before the dependency
+    for (int t = tid; t < p.T; t += ATT_THREADS) {
+      const int wp = p.write_pos[(size_t)b * p.T + t];
+      s_wp[t] = (seq_ok && wp >= 0 && wp < p.S) ? wp : -1;
+    }
+    const int nrows = R + 2 * p.T;
+    for (int i = tid; i < (64 - R) * CH; i += ATT_THREADS)   // rows past R stay zero
+      *reinterpret_cast<uint4*>(sQ + swz<D>(R + i / CH, i % CH)) = make_uint4(0u, 0u, 0u, 0u);
+    bool waited = false;
+    for (int base = 0; base < nrows; base += 16) {           // 4 warps x 4 rows per pass, loads of a pass issued together
+      float x1[4][PPL], x2[4][PPL], cs[4][PPL], sn[4][PPL];
+      int t_[4], head_[4], kind_[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = base + warp + 4 * u;
+        int t = 0, head = 0, kind = 3;
+        if (row < R) { t = row / G; head = kvh * G + row % G; kind = 0; }
+        else if (row < R + p.T) { t = row - R; head = p.Hq + kvh; kind = 1; }
+        else if (row < nrows) { t = row - R - p.T; head = p.Hq + p.Hkv + kvh; kind = 2; }
+        t_[u] = t; head_[u] = head; kind_[u] = kind;
+        if (kind < 2) {
+          const size_t bt = (size_t)b * p.T + t;
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {
+            cs[u][j] = p.cos[bt * HALF + lane + 32 * j];
+            sn[u][j] = p.sin[bt * HALF + lane + 32 * j];
+          }
+        }
+      }
+      if (!waited) { pdl_wait(); waited = true; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kind_[u] < 3) {
+          const __nv_bfloat16* src = p.qkv + (((size_t)b * p.T + t_[u]) * (p.Hq + 2 * p.Hkv) + head_[u]) * D;
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {
+            x1[u][j] = ldg_act_bf16(src + lane + 32 * j);
+            x2[u][j] = ldg_act_bf16(src + lane + 32 * j + HALF);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kind = kind_[u], t = t_[u];
+        if (kind == 3) continue;
+        const int row = base + warp + 4 * u;
+        if (kind != 2) {
+          const __nv_bfloat16* nw = kind == 0 ? p.q_norm : p.k_norm;
+          if (nw != nullptr) {
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) ss += x1[u][j] * x1[u][j] + x2[u][j] * x2[u][j];
+            ss = warp_sum(ss);
+            const float rstd = rsqrtf(ss / (float)D + p.norm_eps);
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {   // rounded to bf16 before the rotation, like the unfused path
+              x1[u][j] = __bfloat162float(__float2bfloat16(x1[u][j] * rstd * __bfloat162float(nw[lane + 32 * j])));
+              x2[u][j] = __bfloat162float(__float2bfloat16(x2[u][j] * rstd * __bfloat162float(nw[lane + 32 * j + HALF])));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {
+            const float o1 = x1[u][j] * cs[u][j] - x2[u][j] * sn[u][j], o2 = x2[u][j] * cs[u][j] + x1[u][j] * sn[u][j];
+            x1[u][j] = o1;
+            x2[u][j] = o2;
+          }
+        }
+        if (kind == 0) {
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {
+            const int c1 = lane + 32 * j, c2 = c1 + HALF;
+            sQ[swz<D>(row, c1 >> 3) + (c1 & 7)] = __float2bfloat16(x1[u][j]);
+            sQ[swz<D>(row, c2 >> 3) + (c2 & 7)] = __float2bfloat16(x2[u][j]);
+          }
+        } else {
+          __nv_bfloat16* sn_row = sNew + ((size_t)(kind - 1) * p.T + t) * D;
+          const int wp = p.write_pos[(size_t)b * p.T + t];
+          const bool wr = seq_ok && wp >= 0 && wp < p.S;
+          __nv_bfloat16* dst = (kind == 1 ? p.k_w : p.v_w) + (((size_t)line * p.Hkv + kvh) * p.S + (wr ? wp : 0)) * D;
+#pragma unroll
+          for (int j = 0; j < PPL; ++j) {
+            const __nv_bfloat16 y1 = __float2bfloat16(x1[u][j]), y2 = __float2bfloat16(x2[u][j]);
+            sn_row[lane + 32 * j] = y1;
+            sn_row[lane + 32 * j + HALF] = y2;
+            if (wr) {
+              dst[lane + 32 * j] = y1;
+              dst[lane + 32 * j + HALF] = y2;
+            }
+          }
+        }
+      }
+    }
+    if (!waited) pdl_wait();
+    if (prof && tid == 0) prof[2] = clock64();   // (last row pass of this thread done, not the wait itself)
+    __syncthreads();   // sQ, sNew, s_wp visible
+    if (prof && tid == 0) prof[3] = clock64();
+    for (int t = 0; t < p.T; ++t) {
+      const int wp = s_wp[t];
+      if (wp >= 0) {
+        new_tile_lo = min(new_tile_lo, wp / ATT_TILE);
+        new_tile_hi = max(new_tile_hi, wp / ATT_TILE);
+      }
+    }
   }
+
+  // ---- Q tile -> shared (swizzled), then A fragments ----------------------------------------------------
+  for (int i = tid; i < (fused ? 0 : 64 * CH); i += ATT_THREADS) {
+    const int r = i / CH, c = i % CH;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (r < R) {
+      const __nv_bfloat16* src;
+      if (MODE == ATTN_PREFILL)
+        src = p.q + (((size_t)b * p.T + tok0 + r) * p.Hq + qh0) * D;
+      else
+        src = p.q + (((size_t)b * p.T + r / G) * p.Hq + kvh * G + r % G) * D;
+      val = ldg_act(src + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sQ + swz<D>(r, c)) = val;
+  }
+
+  if (!fused) prefetch_ring();
   __syncthreads();  // sQ visible
 
   uint32_t qf[D / 16][4];
@@ -265,6 +328,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
     cp_async_commit();
     cp_async_wait<ATT_STAGES - 1>();
     __syncthreads();
+    if (fused && tile >= new_tile_lo && tile <= new_tile_hi) {
+      // this step's K/V rows: the cp.async above may have fetched them stale (or not at all) — take them from shared memory
+      __nv_bfloat16* pK = sK + buf * 64 * D;
+      __nv_bfloat16* pV = sV + buf * 64 * D;
+      for (int i = tid; i < p.T * 2 * CH; i += ATT_THREADS) {
+        const int t = i / (2 * CH), rem = i % (2 * CH), which = rem / CH, c = rem % CH;
+        const int r = s_wp[t] - tile * ATT_TILE;
+        if (s_wp[t] >= 0 && r >= 0 && r < ATT_TILE)
+          *reinterpret_cast<uint4*>((which ? pV : pK) + swz<D>(r, c)) =
+              *reinterpret_cast<const uint4*>(sNew + ((size_t)which * p.T + t) * D + c * 8);
+      }
+      __syncthreads();
+    }
     if (warp_active) {
       const __nv_bfloat16* tK = sK + buf * 64 * D;
       const __nv_bfloat16* tV = sV + buf * 64 * D;
@@ -341,6 +417,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
     __syncthreads();
   }
 
+  if (prof && tid == 0) prof[4] = clock64();
   // ---- merge the KS key-split warps of each row block (through shared memory, reusing the K buffers) ----
   l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
   l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
@@ -363,21 +440,41 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
 
   const int bh = (MODE == ATTN_PREFILL) ? 0 : blockIdx.x;
   const bool direct = (MODE == ATTN_PREFILL) || p.nsplit == 1;
-  for (int e = tid; e < RB * 16 * D; e += ATT_THREADS) {
-    const int r = e / D, d = e % D;
-    if (r >= R) continue;
+  // per-row merge factors once (row max over the KS key-split warps, rescale factor of each, denominator incl. the sink):
+  // sF[k2][r] = exp2(m_k2 - M) (/ L when written directly), so the element loop below is KS multiply-adds per output
+  float* sF = reinterpret_cast<float*>(sQ);   // [4][64] — the Q tile is dead after the fragments were loaded
+  float* sMl = sF + 4 * 64;                   // [64][2]: row max, row denominator (split-KV partials)
+  for (int r = tid; r < RB * 16; r += ATT_THREADS) {
     const int rbi = r >> 4, i = r & 15;
     float M = -INFINITY;
     for (int k2 = 0; k2 < KS; ++k2) M = fmaxf(M, sM[rbi + RBp * k2][i]);
-    float Lsum = 0.f, acc = 0.f;
+    float Lsum = 0.f, f[4] = {0.f, 0.f, 0.f, 0.f};
     if (M != -INFINITY) {
       for (int k2 = 0; k2 < KS; ++k2) {
-        const int w = rbi + RBp * k2;
-        const float f = exp2f(sM[w][i] - M);
-        Lsum += sL[w][i] * f;
-        acc += sO[((size_t)w * 16 + i) * D + d] * f;
+        f[k2] = exp2f(sM[rbi + RBp * k2][i] - M);
+        Lsum += sL[rbi + RBp * k2][i] * f[k2];
       }
     }
+    float inv = 1.f;
+    if (direct) {
+      float Lf = Lsum;
+      if (p.sinks != nullptr && r < R) {
+        const int qh = (MODE == ATTN_PREFILL) ? qh0 : kvh * G + r % G;
+        const float sk = p.sinks[qh] * kLog2e;
+        if (M == -INFINITY) Lf = 1.f; else Lf += exp2f(sk - M);
+      }
+      inv = (M == -INFINITY || Lf == 0.f) ? 0.f : 1.f / Lf;
+    }
+    for (int k2 = 0; k2 < 4; ++k2) sF[k2 * 64 + r] = f[k2] * inv;
+    sMl[r * 2] = M;
+    sMl[r * 2 + 1] = Lsum;
+  }
+  __syncthreads();
+  for (int e = tid; e < R * D; e += ATT_THREADS) {
+    const int r = e / D, d = e % D;
+    const int rbi = r >> 4, i = r & 15;
+    float acc = 0.f;
+    for (int k2 = 0; k2 < KS; ++k2) acc += sO[((size_t)(rbi + RBp * k2) * 16 + i) * D + d] * sF[k2 * 64 + r];
     if (direct) {
       int qh, tok;
       if (MODE == ATTN_PREFILL) {
@@ -387,25 +484,24 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
         qh = kvh * G + r % G;
         tok = r / G;
       }
-      float Lf = Lsum;
-      if (p.sinks != nullptr) {
-        const float sk = p.sinks[qh] * kLog2e;
-        if (M == -INFINITY) {
-          Lf = 1.f;
-        } else {
-          Lf += exp2f(sk - M);
-        }
-      }
-      const float val = (M == -INFINITY || Lf == 0.f) ? 0.f : acc / Lf;
-      p.out[(((size_t)b * p.T + tok) * p.Hq + qh) * D + d] = __float2bfloat16(val);
+      p.out[(((size_t)b * p.T + tok) * p.Hq + qh) * D + d] = __float2bfloat16(acc);
     } else {
       const size_t wrow = ((size_t)bh * p.nsplit + split) * 64 + r;
       p.ws_o[wrow * D + d] = acc;
       if (d == 0) {
-        p.ws_ml[wrow * 2] = M;
-        p.ws_ml[wrow * 2 + 1] = Lsum;
+        p.ws_ml[wrow * 2] = sMl[r * 2];
+        p.ws_ml[wrow * 2 + 1] = sMl[r * 2 + 1];
       }
     }
+  }
+  if (prof && tid == 0) {
+    unsigned long long t;
+    unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    prof[5] = clock64();
+    prof[6] = t;
+    prof[7] = sm;
   }
   if (direct) return;
 
@@ -445,14 +541,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnArgs p
 template <int D, int MODE, int ATT_STAGES>
 static void launch_attn(const AttnArgs& a, dim3 grid, cudaStream_t stream) {
   auto kern = attention_kernel<D, MODE, ATT_STAGES>;
-  const size_t smem = (size_t)(64 * D + 2 * ATT_STAGES * 64 * D) * sizeof(__nv_bfloat16);
-  static bool configured = false;
-  if (!configured) {
+  // + this step's K/V rows (fused decode: [2][T][D], patched into the resident tiles)
+  const size_t extra = (MODE == ATTN_DECODE && a.qkv != nullptr) ? (size_t)2 * a.T * D * sizeof(__nv_bfloat16) : 0;
+  const size_t smem = (size_t)(64 * D + 2 * ATT_STAGES * 64 * D) * sizeof(__nv_bfloat16) + extra;
+  static size_t configured = 0;
+  if (smem > configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    configured = smem;
   }
   launch_pdl(kern, grid, dim3(ATT_THREADS), smem, stream, a);
 }
+
+static bool grid_fits_prof(int ctas) { return ctas <= 148; }
 
 void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream) {
   AttnArgs a{};
@@ -478,16 +578,17 @@ void attention_decode_launch(const AttnDecodeParams& p, cudaStream_t stream) {
   a.k_w = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.k_cache));
   a.v_w = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(p.v_cache));
   a.norm_eps = p.norm_eps;
+  a.prof = (grid_fits_prof(p.B * p.Hkv * p.nsplit)) ? prof_slot_ptr(prof_next_slot()) : nullptr;
   if (p.T * (p.Hq / p.Hkv) > 64) throw std::runtime_error("attention_decode: T * group size must be <= 64");
   dim3 grid(p.B * p.Hkv, p.nsplit);
   const bool paged = p.block_table != nullptr;
   const bool deep = p.nsplit == 1;  // short context, single split: latency bound -> deep prefetch
   if (p.D == 128) {
-    if (paged) { if (deep) launch_attn<128, ATTN_PAGED, 4>(a, grid, stream); else launch_attn<128, ATTN_PAGED, 2>(a, grid, stream); }
-    else { if (deep) launch_attn<128, ATTN_DECODE, 4>(a, grid, stream); else launch_attn<128, ATTN_DECODE, 2>(a, grid, stream); }
+    if (paged) { if (deep) launch_attn<128, ATTN_PAGED, 3>(a, grid, stream); else launch_attn<128, ATTN_PAGED, 2>(a, grid, stream); }
+    else { if (deep) launch_attn<128, ATTN_DECODE, 3>(a, grid, stream); else launch_attn<128, ATTN_DECODE, 2>(a, grid, stream); }
   } else if (p.D == 64) {
-    if (paged) { if (deep) launch_attn<64, ATTN_PAGED, 4>(a, grid, stream); else launch_attn<64, ATTN_PAGED, 2>(a, grid, stream); }
-    else { if (deep) launch_attn<64, ATTN_DECODE, 4>(a, grid, stream); else launch_attn<64, ATTN_DECODE, 2>(a, grid, stream); }
+    if (paged) { if (deep) launch_attn<64, ATTN_PAGED, 3>(a, grid, stream); else launch_attn<64, ATTN_PAGED, 2>(a, grid, stream); }
+    else { if (deep) launch_attn<64, ATTN_DECODE, 3>(a, grid, stream); else launch_attn<64, ATTN_DECODE, 2>(a, grid, stream); }
   } else {
     throw std::runtime_error("attention_decode: head_dim must be 64 or 128");
   }

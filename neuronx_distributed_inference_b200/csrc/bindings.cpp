@@ -44,20 +44,13 @@ struct Scratch {
 };
 static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t nt);
 
-static bool use_gemv2(int T, int K) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("NXDI_B200_GEMV");
-    v = (e == nullptr) ? 2 : atoi(e);
-  }
-  return v == 2 && gemv2_supported(T, K);
-}
+static bool use_gemv2(int T, int K) { return gemv2_supported(T, K); }
 
 static void run_gemv(GemvParams& p, int mode, const at::Device& dev) {
   if (use_gemv2(p.T, p.K) && p.x_in_smem) {
     auto& s = scratch(dev, 0, 0, 0);
     const bool glu = p.act != 0;
-    const int n_tiles = glu ? ((p.N / 2) + 7) / 8 : (p.N + 15) / 16;
+    const int n_tiles = gemv2_ntiles(p.N, glu);
     const int64_t need = (int64_t)n_tiles * gemv2_pmax(p.N, p.K, glu) * 128;
     auto o = at::TensorOptions().device(dev);
     if (!s.gemv_ws.defined() || s.gemv_ws.numel() < need) s.gemv_ws = at::empty({std::max<int64_t>(need, 4 << 20)}, o.dtype(at::kFloat));
@@ -65,7 +58,7 @@ static void run_gemv(GemvParams& p, int mode, const at::Device& dev) {
       s.gemv_tickets = at::zeros({std::max<int64_t>(n_tiles, 1 << 15)}, o.dtype(at::kInt));
     gemv2_launch(p, mode, s.gemv_ws.data_ptr<float>(), reinterpret_cast<unsigned*>(s.gemv_tickets.data_ptr<int>()), cur_stream());
   } else {
-    TORCH_CHECK(mode == 0 || !use_gemv2(1, 256), "fused all-reduce: v1/v2 kernels use different slot layouts; T*K too large for v2");
+    TORCH_CHECK(p.K % 256 == 0, "gemv: K must be a multiple of 256 on the wide-activation fallback");
     gemv_launch(p, mode, cur_stream());
   }
 }
@@ -105,21 +98,12 @@ static void check_gemv_inputs(const at::Tensor& x, const at::Tensor& w) {
   TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1));
   TORCH_CHECK(is_bf16(x) && is_bf16(w), "gemv: bf16 activations and weights");
   TORCH_CHECK(x.size(0) >= 1 && x.size(0) <= GEMV_MAX_T, "gemv: 1..8 tokens");
-  TORCH_CHECK(x.size(1) % 256 == 0 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && w.is_contiguous());
-}
-
-static void set_prefetch(GemvParams& p, const c10::optional<at::Tensor>& next_w, bool next_glu) {
-  if (!next_w.has_value() || !is_bf16(*next_w) || next_w->dim() != 2 || !next_w->is_contiguous() || next_w->size(1) % 256 != 0) return;
-  p.pf_w = next_w->data_ptr();
-  p.pf_N = next_w->size(0);
-  p.pf_K = next_w->size(1);
-  p.pf_glu = next_glu ? 1 : 0;
+  TORCH_CHECK(x.size(1) % 64 == 0 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && w.is_contiguous());
 }
 
 at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                 const c10::optional<at::Tensor>& norm_w, double eps, double offset, int64_t act,
-                const c10::optional<at::Tensor>& scale, const c10::optional<at::Tensor>& residual,
-                const c10::optional<at::Tensor>& next_w, bool next_glu) {
+                const c10::optional<at::Tensor>& scale, const c10::optional<at::Tensor>& residual) {
   if (scale.has_value()) {
     // weight-only quantised path (int8 / fp8-e4m3, per-channel or per-tensor scale)
     TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && is_bf16(x));
@@ -151,7 +135,6 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
     TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
   GemvParams p{};
   fill_params(p, xn, w, bias, norm_w, eps, offset, (int)act, residual, scale, y, x_in_smem);
-  set_prefetch(p, next_w, next_glu);
   run_gemv(p, 0, x.device());
   return y;
 }
@@ -178,11 +161,12 @@ at::Tensor gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
 // Row-parallel GEMV -> one-shot all-reduce over NVLink peer buffers -> +bias +residual.  ONE kernel.
 at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                           const c10::optional<at::Tensor>& residual, const std::vector<int64_t>& recv_ptrs,
-                          const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t parity, int64_t n_max,
-                          const c10::optional<at::Tensor>& next_w, bool next_glu) {
+                          const at::Tensor& step, int64_t rank, int64_t parity, int64_t call, int64_t n_max) {
   check_gemv_inputs(x, w);
   const int world = recv_ptrs.size();
-  TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS && (int)flag_ptrs.size() == world);
+  TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS);
+  TORCH_CHECK(step.is_cuda() && step.scalar_type() == at::kInt && step.numel() >= 1, "gemv_allreduce: step counter must be a CUDA int32 tensor");
+  TORCH_CHECK(gemv2_supported(x.size(0), x.size(1)), "gemv_allreduce: activations too wide for shared memory");
   const int N = w.size(0);
   TORCH_CHECK(N <= n_max && (N + 15) / 16 <= SYMM_MAX_TILES, "gemv_allreduce: output too wide for the workspace");
   c10::cuda::CUDAGuard guard(x.device());
@@ -193,68 +177,16 @@ at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::o
     TORCH_CHECK(residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
   GemvParams p{};
   fill_params(p, xn, w, bias, c10::nullopt, 0, 0, 0, residual, c10::nullopt, y, x_in_smem);
-  for (int i = 0; i < world; ++i) {
-    p.symm.recv[i] = reinterpret_cast<float*>(recv_ptrs[i]);
-    p.symm.flags[i] = reinterpret_cast<uint32_t*>(flag_ptrs[i]);
-  }
+  for (int i = 0; i < world; ++i) p.symm.recv[i] = reinterpret_cast<float*>(recv_ptrs[i]);
+  p.symm.step = reinterpret_cast<const uint32_t*>(step.data_ptr<int>());
   p.symm.rank = rank;
   p.symm.world = world;
   p.symm.parity = parity;
+  p.symm.call = call;
   p.symm.n_max = n_max;
-  set_prefetch(p, next_w, next_glu);
   run_gemv(p, 1, x.device());
   return y;
 }
-
-// Chain of dependent skinny GEMMs in ONE persistent launch (decode layer tail: o_proj -> gate_up -> down -> next qkv).
-// Per phase i: y[i] = epi( norm?(x[i]) · w[i]^T ); modes[i] == 1 -> fused all-reduce with parity parities[i].
-void gemv_chain(const std::vector<at::Tensor>& xs, const std::vector<at::Tensor>& ws,
-                const std::vector<c10::optional<at::Tensor>>& biases, const std::vector<c10::optional<at::Tensor>>& norms,
-                const std::vector<c10::optional<at::Tensor>>& residuals, std::vector<at::Tensor>& ys,
-                const std::vector<int64_t>& acts, const std::vector<int64_t>& modes, const std::vector<double>& eps,
-                const std::vector<double>& offset,
-                const std::vector<int64_t>& recv_ptrs, const std::vector<int64_t>& flag_ptrs, int64_t rank,
-                const std::vector<int64_t>& parities, int64_t n_max) {
-  const int n = xs.size();
-  TORCH_CHECK(n >= 1 && n <= 4 && (int)ws.size() == n && (int)ys.size() == n && (int)acts.size() == n && (int)modes.size() == n);
-  c10::cuda::CUDAGuard guard(xs[0].device());
-  GemvParams ph[4];
-  int md[4];
-  int kmax = 0;
-  for (int i = 0; i < n; ++i) {
-    check_gemv_inputs(xs[i], ws[i]);
-    TORCH_CHECK(xs[i].size(0) == xs[0].size(0), "gemv_chain: all phases share the token count");
-    ph[i] = GemvParams{};
-    at::Tensor y = ys[i];
-    fill_params(ph[i], xs[i], ws[i], biases[i], norms[i], eps[i], offset[i], (int)acts[i], residuals[i], c10::nullopt, y, true);
-    md[i] = (int)modes[i];
-    if (md[i] == 1) {
-      const int world = recv_ptrs.size();
-      TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS && ph[i].N <= n_max);
-      for (int r = 0; r < world; ++r) {
-        ph[i].symm.recv[r] = reinterpret_cast<float*>(recv_ptrs[r]);
-        ph[i].symm.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
-      }
-      ph[i].symm.rank = rank;
-      ph[i].symm.world = world;
-      ph[i].symm.parity = parities[i];
-      ph[i].symm.n_max = n_max;
-    }
-    kmax = std::max(kmax, ph[i].K);
-  }
-  TORCH_CHECK(gemv_chain_supported(ph[0].T, kmax), "gemv_chain: activations too wide for shared memory");
-  static std::unordered_map<int, std::array<at::Tensor, 3>> pool;   // per device: ws, tickets, barrier
-  auto& sl = pool[xs[0].device().index()];
-  auto o = at::TensorOptions().device(xs[0].device());
-  const int64_t need_ws = gemv_chain_ws_floats(ph, n), need_t = gemv_chain_tickets(ph, n);
-  if (!sl[0].defined() || sl[0].numel() < need_ws) sl[0] = at::empty({std::max<int64_t>(need_ws, 8 << 20)}, o.dtype(at::kFloat));
-  if (!sl[1].defined() || sl[1].numel() < need_t) sl[1] = at::zeros({std::max<int64_t>(need_t, 1 << 16)}, o.dtype(at::kInt));
-  if (!sl[2].defined()) sl[2] = at::zeros({64}, o.dtype(at::kInt));
-  gemv_chain_launch(ph, md, n, sl[0].data_ptr<float>(), reinterpret_cast<unsigned*>(sl[1].data_ptr<int>()),
-                    reinterpret_cast<unsigned*>(sl[2].data_ptr<int>()), cur_stream());
-}
-
-bool gemv_chain_ok(int64_t T, int64_t K_max) { return gemv_chain_supported((int)T, (int)K_max); }
 
 // Routed experts of a decode step: x [T,H], w_gate_up [E,2I,H], w_down [E,H,I], topk_w/topk_i [T,k] -> [T,H] (local experts only;
 // the caller all-reduces across EP/TP ranks).
@@ -359,7 +291,8 @@ static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t n
   return s;
 }
 
-at::Tensor argmax(const at::Tensor& logits) {
+at::Tensor argmax(const at::Tensor& logits, const std::vector<int64_t>& slot_ptrs, const c10::optional<at::Tensor>& step,
+                  int64_t rank, int64_t parity, int64_t call, int64_t rows_max) {
   TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
   TORCH_CHECK(logits.scalar_type() == at::kFloat || is_bf16(logits), "argmax: fp32 or bf16 logits");
   const int B = logits.size(0), V = logits.size(1);
@@ -367,8 +300,18 @@ at::Tensor argmax(const at::Tensor& logits) {
   auto out = at::empty({B}, logits.options().dtype(at::kLong));
   const int nsplit = std::max(1, std::min(64, V / 2048));
   auto& ws = scratch(logits.device(), (int64_t)B * nsplit, (int64_t)B * nsplit, B);
+  ArgmaxSymm sy{};
+  const int world = slot_ptrs.size();
+  if (world > 1) {
+    TORCH_CHECK(world <= SYMM_MAX_RANKS && step.has_value() && step->is_cuda() && step->scalar_type() == at::kInt && B <= rows_max,
+                "argmax exchange: bad symmetric arguments");
+    for (int i = 0; i < world; ++i) sy.slots[i] = reinterpret_cast<float*>(slot_ptrs[i]);
+    sy.step = reinterpret_cast<const uint32_t*>(step->data_ptr<int>());
+    sy.rank = rank; sy.world = world; sy.parity = parity; sy.call = call; sy.rows_max = rows_max;
+  }
   argmax_launch(logits.data_ptr(), is_bf16(logits) ? 1 : 0, out.data_ptr<int64_t>(), ws.f.data_ptr<float>(), ws.i.data_ptr<int>(),
-                reinterpret_cast<unsigned*>(ws.tickets.data_ptr<int>()), B, V, (int)logits.stride(0), nsplit, cur_stream());
+                reinterpret_cast<unsigned*>(ws.tickets.data_ptr<int>()), B, V, (int)logits.stride(0), nsplit,
+                world > 1 ? &sy : nullptr, cur_stream());
   return out;
 }
 
@@ -510,9 +453,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm", &nxdi::rmsnorm);
   m.def("gemv", &nxdi::gemv);
   m.def("gemv_allreduce", &nxdi::gemv_allreduce);
-  m.def("gemv_chain", &nxdi::gemv_chain);
+  m.def("set_prof", [](const c10::optional<at::Tensor>& buf) {
+    if (!buf.has_value()) { nxdi::gemv2_set_prof(nullptr, 0); return; }
+    TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous());
+    nxdi::gemv2_set_prof(reinterpret_cast<unsigned long long*>(buf->data_ptr<int64_t>()), buf->numel() / (148 * 8));
+  });
+  m.def("prof_count", []() { return (int64_t)nxdi::prof_count(); });
+  m.def("gemv2_supported", [](int64_t T, int64_t K) { return nxdi::gemv2_supported((int)T, (int)K); });
   m.def("moe_decode", &nxdi::moe_decode);
-  m.def("gemv_chain_ok", &nxdi::gemv_chain_ok);
   m.def("gemm", &nxdi::gemm);
   m.def("symm_alloc", &nxdi::symm_alloc);
   m.def("symm_open", &nxdi::symm_open);

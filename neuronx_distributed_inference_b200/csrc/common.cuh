@@ -40,6 +40,20 @@ __device__ __forceinline__ uint4 ldg_cached(const void* p) {
   return r;
 }
 
+// ACTIVATION loads (anything a previous kernel of the stream wrote): L2 only.  Decode kernels overlap under programmatic
+// dependent launch — several grids are co-resident on an SM, and L1 is invalidated per LAUNCH, not per dependency: a line of a
+// recycled activation buffer cached by an older, still-running grid could otherwise be hit stale by a newer one.
+__device__ __forceinline__ uint4 ldg_act(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_act_bf16(const __nv_bfloat16* p) {
+  unsigned short r;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return __uint_as_float(((uint32_t)r) << 16);
+}
+
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -104,6 +118,23 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_relaxed_sys_f32x4(float* p, float a, float b, float c, float d) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
+}
+
+// "LL" cross-GPU transport: payload and tag travel in ONE 8-byte store (single-copy atomic), so the receiver needs no fence
+// and no separate flag: it polls the same 8 bytes until the tag is the one it expects.
+__device__ __forceinline__ void st_ll(float* p, float v, uint32_t flag) {  // 8-byte {value, tag}: single-copy atomic
+  asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ void ld_ll(const float* p, float& v, uint32_t& flag) {
+  uint32_t a, b;
+  asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+  v = __uint_as_float(a);
+  flag = b;
+}
+
+// tag of a collective: (device-side step counter << 8 | index of the collective inside the forward) + 1 (parallel/symm.py)
+__device__ __forceinline__ uint32_t ll_tag(const uint32_t* step, int call) {
+  return ((__ldcg(step) << 8) | (uint32_t)(call & 255)) + 1u;
 }
 
 }  // namespace nxdi

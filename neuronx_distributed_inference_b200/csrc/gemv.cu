@@ -19,9 +19,9 @@ size_t gemv_smem_bytes(int T, int K, bool x_in_smem) {
   return (x_in_smem ? (size_t)T * (K * 2 + 64) : 0) + (2 * GEMV_WARPS * 128 + 64) * sizeof(float);
 }
 
-template <bool GLU, int MODE>
+template <bool GLU>
 static void launch_gemv(const GemvParams& p, cudaStream_t stream) {
-  auto kern = gemv_kernel<GLU, MODE>;
+  auto kern = gemv_kernel<GLU>;
   const size_t smem = gemv_smem_bytes(p.T, p.K, p.x_in_smem);
   static bool configured = false;
   if (!configured) {
@@ -36,13 +36,9 @@ static void launch_gemv(const GemvParams& p, cudaStream_t stream) {
 
 void gemv_launch(const GemvParams& p, int mode, cudaStream_t stream) {
   const bool glu = p.act != ACT_NONE;
-  if (mode == 1) {
-    launch_gemv<false, 1>(p, stream);
-  } else if (glu) {
-    launch_gemv<true, 0>(p, stream);
-  } else {
-    launch_gemv<false, 0>(p, stream);
-  }
+  if (mode != 0) throw std::runtime_error("gemv v1: the fused all-reduce lives in gemv2 (activations must fit shared memory)");
+  if (glu) launch_gemv<true>(p, stream);
+  else launch_gemv<false>(p, stream);
 }
 
 // rmsnorm kernel (also used to pre-normalise x when T*K does not fit the GEMV's shared memory)

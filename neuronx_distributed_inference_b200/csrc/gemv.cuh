@@ -12,8 +12,9 @@
 //     in flight while the current tile is reduced across the 8 warps and written out;
 //   * the first weight batch is issued BEFORE griddepcontrol.wait (PDL): weights never depend on the
 //     previous kernel, so HBM streaming continues across kernel boundaries inside the decode CUDA graph;
-//   * epilogues: bias, SwiGLU/GeGLU (tile = 8 gate rows + 8 up rows), or the fused one-shot all-reduce over
-//     NVLink peer memory + residual add (MODE_ALLREDUCE, see gemv_allreduce.cu).
+//   * epilogues: bias, residual, SwiGLU/GeGLU (tile = 8 gate rows + 8 up rows).
+// Role since round 2: the fallback for activations too wide for shared memory (T*K*2 > ~200 KB, e.g. 8 tokens x K=14336);
+// everything else — and every fused all-reduce — runs on the TMA-pipelined gemv2.cu.
 #pragma once
 #include "api.h"
 #include "common.cuh"
@@ -50,8 +51,7 @@ __device__ __forceinline__ void gemv_rows(int tile, int g, int N, int& r0, int& 
   }
 }
 
-// MODE: 0 plain epilogue, 1 fused all-reduce epilogue
-template <bool GLU, int MODE>
+template <bool GLU>
 __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -199,32 +199,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams 
           for (int w = 0; w < GEMV_WARPS; ++w) v += rb[w * 128 + row * 8 + col];
           const int n = ctile * 16 + row;
           if (n < N) {
-            if (MODE == 0) {
-              if (p.bias != nullptr) v += __bfloat162float(BIAS[n]);
-              if (p.residual != nullptr) v += __bfloat162float(RES[(size_t)col * p.ldy + n]);
-              Y[(size_t)col * p.ldy + n] = __float2bfloat16(v);
-            } else {
-              // one-shot all-reduce, phase 1: push my partial into every rank's receive buffer
-              const SymmArgs& s = p.symm;
-              const size_t off = ((size_t)(s.parity * s.world + s.rank) * 8 + col) * s.n_max + n;
-#pragma unroll
-              for (int d = 0; d < SYMM_MAX_RANKS; ++d)
-                if (d < s.world) s.recv[d][off] = v;
-            }
+            if (p.bias != nullptr) v += __bfloat162float(BIAS[n]);
+            if (p.residual != nullptr) v += __bfloat162float(RES[(size_t)col * p.ldy + n]);
+            Y[(size_t)col * p.ldy + n] = __float2bfloat16(v);
           }
         }
-      }
-    }
-    if (MODE == 1) {
-      __syncthreads();  // all partial stores of this tile issued
-      if (tid < p.symm.world) {
-        __threadfence_system();
-        const SymmArgs& s = p.symm;
-        uint32_t* fl = s.flags[0];
-#pragma unroll
-        for (int d = 1; d < SYMM_MAX_RANKS; ++d)
-          if (d == tid) fl = s.flags[d];
-        st_release_sys(fl + (size_t)(s.parity * s.world + s.rank) * SYMM_MAX_TILES + ctile, 1u);
       }
     }
     parity ^= 1;
@@ -264,44 +243,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams 
     consume(0);
     issue(0);
     consume(1);
-  }
-
-  if (MODE == 1) {
-    // ---- all-reduce phase 2: wait for every rank's partials of my tiles, reduce in rank order ------
-    const SymmArgs& s = p.symm;
-    uint32_t* my_flags = s.flags[0];
-    float* my_recv = s.recv[0];
-#pragma unroll
-    for (int d = 1; d < SYMM_MAX_RANKS; ++d)
-      if (d == s.rank) { my_flags = s.flags[d]; my_recv = s.recv[d]; }
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      if (tid < s.world) {
-        uint32_t* f = my_flags + (size_t)(s.parity * s.world + tid) * SYMM_MAX_TILES + tile;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) == 0u) {
-          if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail loudly instead of hanging the GPU
-            printf("gemv_allreduce: rank %d timed out waiting for rank %d tile %d\n", s.rank, tid, tile);
-            __trap();
-          }
-        }
-        *f = 0u;  // self-resetting flag (next use of this slot is two collectives away)
-      }
-      __syncthreads();
-      if (tid < 128) {
-        const int col = tid >> 4, row = tid & 15, n = tile * 16 + row;
-        if (col < T && n < N) {
-          float v = 0.f;
-          for (int r = 0; r < s.world; ++r) {
-            const volatile float* src = my_recv + ((size_t)(s.parity * s.world + r) * 8 + col) * s.n_max + n;
-            v += *src;
-          }
-          if (p.bias != nullptr) v += __bfloat162float(BIAS[n]);
-          if (p.residual != nullptr) v += __bfloat162float(RES[(size_t)col * p.ldy + n]);
-          Y[(size_t)col * p.ldy + n] = __float2bfloat16(v);
-        }
-      }
-      __syncthreads();
-    }
   }
 }
 

@@ -16,10 +16,14 @@ __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return _
 
 // ---- arg-max -------------------------------------------------------------------------------------------
 // grid (nsplit, B).  Partial (value,index) per CTA -> workspace; the last CTA of a row (atomic ticket) reduces.
+// Vocabulary-sharded lm_head (sy.world > 1): the row's winner is exchanged with every peer INSIDE this kernel — the
+// {value, tag} / {global index, tag} pairs go straight into each rank's slot over NVLink (LL stores), every rank polls its
+// `world` slots and picks the same global winner (ties -> lowest index, like a flat arg-max).  Replaces local arg-max +
+// NCCL all-gather + five torch glue kernels in the decode graph (reference: modules/generation/sampling.py:306-326).
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ logits, int64_t* __restrict__ out,
                                                      float* __restrict__ ws_val, int* __restrict__ ws_idx,
-                                                     unsigned* __restrict__ tickets, int V, int ld) {
+                                                     unsigned* __restrict__ tickets, int V, int ld, const ArgmaxSymm sy) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x, tid = threadIdx.x;
@@ -67,6 +71,48 @@ __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ logit
       const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
       if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
     }
+    if (sy.world > 1) {
+      const uint32_t tag = ll_tag(sy.step, sy.call);
+      const int gix = ix + sy.rank * V;
+      if (tid < sy.world) {
+        float* dst = sy.slots[0];
+#pragma unroll
+        for (int d = 1; d < SYMM_MAX_RANKS; ++d)
+          if (d == tid) dst = sy.slots[d];
+        dst += (((size_t)sy.parity * sy.rows_max + b) * sy.world + sy.rank) * 4;
+        st_ll(dst, v, tag);
+        st_ll(dst + 2, __int_as_float(gix), tag);
+      }
+      v = -FLT_MAX;
+      ix = 0x7fffffff;
+      if (tid < sy.world) {
+        const float* src = sy.slots[0];
+#pragma unroll
+        for (int d = 1; d < SYMM_MAX_RANKS; ++d)
+          if (d == sy.rank) src = sy.slots[d];
+        src += (((size_t)sy.parity * sy.rows_max + b) * sy.world + tid) * 4;
+        float a, c;
+        uint32_t fa, fc;
+        const long long t0 = clock64();
+        while (true) {
+          ld_ll(src, a, fa);
+          ld_ll(src + 2, c, fc);
+          if (fa == tag && fc == tag) break;
+          if (clock64() - t0 > 8000000000LL) {
+            printf("argmax exchange: rank %d timed out waiting for rank %d (row %d, tag %u, seen %u %u)\n", sy.rank, tid, b, tag, fa, fc);
+            __trap();
+          }
+        }
+        v = a;
+        ix = __float_as_int(c);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+      }
+    }
     if (tid == 0) {
       out[b] = ix;
       tickets[b] = 0;  // ready for the next launch / graph replay
@@ -75,14 +121,16 @@ __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ logit
 }
 
 void argmax_launch(const void* logits, int dtype, int64_t* out, float* ws_val, int* ws_idx, unsigned* tickets, int B, int V,
-                   int ld, int nsplit, cudaStream_t stream) {
+                   int ld, int nsplit, const ArgmaxSymm* symm, cudaStream_t stream) {
   dim3 grid(nsplit, B);
+  ArgmaxSymm sy{};
+  if (symm != nullptr) sy = *symm;
   if (dtype == 0)
     launch_pdl(argmax_kernel<float>, grid, dim3(256), 0, stream, reinterpret_cast<const float*>(logits), out, ws_val, ws_idx,
-               tickets, V, ld);
+               tickets, V, ld, sy);
   else
     launch_pdl(argmax_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(logits), out,
-               ws_val, ws_idx, tickets, V, ld);
+               ws_val, ws_idx, tickets, V, ld, sy);
 }
 
 // ---- top-k / top-p / temperature sampling ------------------------------------------------------------------

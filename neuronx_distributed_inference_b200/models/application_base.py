@@ -505,7 +505,12 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
             self._spec_prev = ids.gather(1, (n - 1).clamp_min(0))
             self.kv_cache_populated = True
             return self._construct_output(out)
-        accepted, n_acc, nxt, npos, prev, out_t = fused(ids, pos, sid, self._spec_prev)
+        from ..generation.speculative import FusedSpeculativeModel
+        if isinstance(fused, FusedSpeculativeModel) and sampling_params is not None:
+            # do_sample: the draft samples and the target verifies by rejection sampling (speculative.py::forward_sampling)
+            accepted, n_acc, nxt, npos, prev, out_t = fused(ids, pos, sid, self._spec_prev, sampling_params.to(dev))
+        else:
+            accepted, n_acc, nxt, npos, prev, out_t = fused(ids, pos, sid, self._spec_prev)
         self._spec_prev = prev
         res = CausalLMOutput(tokens=accepted, logits=out_t.logits, hidden_states=None)
         res.fused_outputs = [accepted, nxt, None, npos, n_acc]
@@ -547,7 +552,8 @@ class NeuronBaseForCausalLM(NeuronApplicationBase):
     def _is_prefill(position_ids, computed_context_lens=None) -> bool:
         if computed_context_lens is not None:
             return True
-        return min(position_ids[:, 0].tolist()) == 0
+        # whole tensor, like the reference (model_base.py:3546): with left padding column 0 holds the pad position (1)
+        return int(position_ids.min()) == 0
 
     def _construct_output(self, out: ModelOutput) -> CausalLMOutput:
         res = CausalLMOutput(logits=out.logits, tokens=out.tokens, hidden_states=out.hidden_states,

@@ -240,7 +240,7 @@ class NeuronBaseModel(nn.Module):
                         active_mask=kw.get("active_mask"), active_base=kw.get("active_base"), slot_mapping=kw.get("slot_mapping"),
                         block_table=kw.get("block_table"), has_prefix=has_prefix,
                         adapter_ids=kw.get("adapter_ids"), rotary_position_ids=kw.get("rotary_position_ids"),
-                        capture={} if kw.get("capture") else None)
+                        capture={} if kw.get("capture") else None, seq_hint=int(kw.get("seq_hint") or 0))
         for k in getattr(self, "meta_extra_keys", ()):
             if kw.get(k) is not None:
                 meta.extras[k] = kw[k]
@@ -259,6 +259,8 @@ class NeuronBaseModel(nn.Module):
         if is_prefill is None:
             is_prefill = T > 1 and T != nc.speculation_length and T != nc.medusa_speculation_length
         meta = self.build_meta(input_ids, attention_mask, position_ids, seq_ids, is_prefill, **kw)
+        if self.tp_group.symm is not None:
+            self.tp_group.symm.begin_step()     # fresh tags for this forward's in-kernel collectives (parallel/symm.py)
         h = self.embed(input_ids, inputs_embeds, vision_embeddings, vision_mask)
         sp = self._set_sequence_parallel(is_prefill and T % self.tp_group.size == 0 and T >= self.tp_group.size)
         if sp:
@@ -271,12 +273,7 @@ class NeuronBaseModel(nn.Module):
         lora = getattr(self, "lora", None) if meta.adapter_ids is not None else None
         aux_layers = getattr(self, "aux_hidden_layers", None) if output_hidden else None
         aux = []
-        if not is_prefill and h.is_cuda and not getattr(self, "_prefetch_linked", False):
-            self._link_weight_prefetch()
-        chain = (not is_prefill and lora is None and aux_layers is None and prev_hidden is None and self._chain_ok(h, meta, kw))
-        if chain:
-            h = self._decode_layers_chained(h, meta)
-        for i, layer in enumerate(() if chain else self.layers):
+        for i, layer in enumerate(self.layers):
             h = layer(h, meta, self.kv_mgr, lora=lora.for_layer(i)) if lora is not None else layer(h, meta, self.kv_mgr)
             if aux_layers is not None and i in aux_layers:
                 aux.append(h)
@@ -316,7 +313,7 @@ class NeuronBaseModel(nn.Module):
             Bo, To, V = logits.shape
             toks = self.sampler(logits.reshape(Bo * To, V),
                                 None if sampling_params is None else sampling_params.repeat_interleave(To, 0),
-                                rand)
+                                rand if (rand is None or To == 1 or rand.shape[0] == Bo * To) else rand.repeat_interleave(To, 0))
             out.tokens = toks.view(Bo, To) if To > 1 else toks.view(Bo)
         if want_logits or not self.on_device_sampling:
             out.logits = self.gather_logits(logits)
@@ -330,89 +327,6 @@ class NeuronBaseModel(nn.Module):
         (reference model_base.py:478-508, modeling_llama.py:1172-1187)."""
         hn = self.final_hidden(h_out)
         return torch.stack([self.gather_logits(head(hn)) for head in self.medusa_heads], 0)
-
-    def _link_weight_prefetch(self):
-        """Tell every decode GEMV which weight matrix the stream touches next (``w._nxdi_next = (next_w, next_is_glu)``):
-        the kernel warms L2 with the first ring fill of its successor while its own tail drains (csrc/gemv2.cu)."""
-        self._prefetch_linked = True
-        from ..modules.mlp import GatedMLP
-        seq = []
-        for layer in self.layers:
-            attn, mlp = getattr(layer, "self_attn", None), getattr(layer, "mlp", None)
-            if attn is None or not hasattr(attn, "qkv_proj") or not isinstance(mlp, GatedMLP):
-                return
-            seq += [(attn.qkv_proj.weight, False), (attn.o_proj.weight, False), (mlp.gate_up_proj.weight, True),
-                    (mlp.down_proj.weight, False)]
-        seq.append((self.lm_head.weight, False))
-        for (w, _), nxt in zip(seq[:-1], seq[1:]):
-            if nxt[0].dtype == torch.bfloat16 and nxt[0].dim() == 2:
-                w._nxdi_next = nxt
-
-    # ---- persistent GEMV chain (decode fast path) ---------------------------------------------------------------------
-    def _chain_ok(self, h, meta, kw) -> bool:
-        """Dense Llama-style blocks, bf16 CUDA, <= 8 tokens: the four projections between two attention calls run as ONE
-        persistent kernel (ops.gemv_chain).  Decided once per (token count) and cached."""
-        import os
-        M = h.shape[0] * h.shape[1]
-        key = ("chain", M, h.dtype)
-        cache = self.__dict__.setdefault("_chain_cache", {})
-        if key not in cache:
-            ok = (h.is_cuda and h.dtype == torch.bfloat16 and M <= ops.GEMV_MAX_TOKENS and os.environ.get("NXDI_B200_CHAIN", "0") == "1"
-                  and not self.neuron_config.is_block_kv_layout and meta.capture is None)
-            kmax = 0
-            if ok:
-                from ..modules.mlp import GatedMLP
-                g = self.tp_group
-                for layer in self.layers:
-                    attn, mlp = getattr(layer, "self_attn", None), getattr(layer, "mlp", None)
-                    if type(layer) is not DecoderLayer or not isinstance(mlp, GatedMLP) or attn is None \
-                            or not hasattr(attn, "chain_eligible") or not attn.chain_eligible(self.kv_mgr, h.dtype):
-                        ok = False
-                        break
-                    ws = [attn.qkv_proj.weight, attn.o_proj.weight, mlp.gate_up_proj.weight, mlp.down_proj.weight]
-                    if any(w.dtype != torch.bfloat16 or w.shape[1] % 256 != 0 or not w.is_contiguous() for w in ws) \
-                            or any(getattr(m, "scale", None) is not None for m in (mlp.gate_up_proj, mlp.down_proj)) \
-                            or getattr(layer.input_layernorm, "weight", None) is None \
-                            or getattr(layer.post_attention_layernorm, "weight", None) is None \
-                            or getattr(mlp.down_proj, "reduce_dtype", None) not in (None, torch.float32):
-                        ok = False
-                        break
-                    kmax = max(kmax, *[w.shape[1] for w in ws])
-                if ok and g.size > 1:
-                    ok = g.symm is not None and self.hidden_size <= g.symm.n_max
-                ok = ok and ops.gemv_chain_supported(M, kmax)
-            cache[key] = ok
-        return cache[key] and meta.active_mask is None and meta.slot_mapping is None
-
-    def _decode_layers_chained(self, h, meta):
-        B, T, H = h.shape
-        M = B * T
-        g = self.tp_group
-        ar = g.size > 1
-        layers = self.layers
-        x = h.reshape(M, H)
-        l0 = layers[0]
-        n0 = l0.input_layernorm
-        qkv = ops.linear(h, l0.self_attn.qkv_proj.weight, l0.self_attn.qkv_proj.bias, norm_weight=n0.weight,
-                         norm_eps=n0.variance_epsilon, norm_offset=n0.offset)
-        for i, layer in enumerate(layers):
-            attn, mlp, n2 = layer.self_attn, layer.mlp, layer.post_attention_layernorm
-            o = attn.decode_core(qkv, meta, self.kv_mgr, B, T).reshape(M, -1)
-            phases = [
-                dict(x=o, w=attn.o_proj.weight, bias=attn.o_proj.bias, residual=x, allreduce=ar),
-                dict(x=0, w=mlp.gate_up_proj.weight, bias=mlp.gate_up_proj.bias, norm=n2.weight, eps=n2.variance_epsilon,
-                     offset=n2.offset, act=mlp.act),
-                dict(x=1, w=mlp.down_proj.weight, bias=mlp.down_proj.bias, residual=0, allreduce=ar),
-            ]
-            if i + 1 < len(layers):
-                nx = layers[i + 1]
-                n1 = nx.input_layernorm
-                phases.append(dict(x=2, w=nx.self_attn.qkv_proj.weight, bias=nx.self_attn.qkv_proj.bias, norm=n1.weight,
-                                   eps=n1.variance_epsilon, offset=n1.offset))
-            ys = ops.gemv_chain(phases, g)
-            x = ys[2]
-            qkv = ys[3].view(B, T, -1) if len(ys) > 3 else None
-        return x.view(B, T, H)
 
     def _set_sequence_parallel(self, on: bool) -> bool:
         """SP is a prefill-only layout; the parallel layers carry a static flag in the reference, here it is switched per

@@ -87,6 +87,15 @@ class Sampler(nn.Module):
     def _rand(self, B, device):
         if self.deterministic:
             return torch.full((B,), 0.5, device=device)
+        if device.type == "cuda":
+            # The device's DEFAULT generator: it is the only one torch registers with a CUDA graph under capture (a private
+            # torch.Generator raises "CUDA generator not in capture mode" inside the decode / prefill graphs), and its philox
+            # offset advances per replay, so graph replays draw fresh numbers.  Seeded once per sampler from the config.
+            if self._gen is None:
+                self._gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+                if not torch.cuda.is_current_stream_capturing():
+                    self._gen.manual_seed(int(self.cfg.seed) if self.cfg else 0)
+            return torch.rand(B, device=device)
         if self._gen is None or self._gen.device != device:
             self._gen = torch.Generator(device=device)
             self._gen.manual_seed(int(self.cfg.seed) if self.cfg else 0)
@@ -97,6 +106,9 @@ class Sampler(nn.Module):
         g = self.tp_group
         if not self.vocab_shard:
             return ops.argmax(logits)
+        tok = ops.argmax_sharded(logits, g)                       # one kernel: local arg-max + NVLink LL exchange
+        if tok is not None:
+            return tok
         idx = ops.argmax(logits)                                  # local arg-max kernel
         val = logits.gather(1, idx.view(-1, 1)).view(-1).float()
         idx = idx + g.rank * logits.shape[-1]

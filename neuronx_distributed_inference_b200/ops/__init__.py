@@ -63,7 +63,6 @@ def rmsnorm(x, weight, eps: float, offset: float = 0.0, residual=None):
     return ref.rmsnorm(x, weight, eps, offset, residual)
 
 
-_PREFETCH_NEXT = os.environ.get("NXDI_B200_PREFETCH_NEXT", "0") == "1"   # measured: L2 warm-up of the successor costs more than it hides
 _ACT_CODES = {None: 0, "silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
 
 
@@ -81,20 +80,17 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
             if wq and T <= GEMV_MAX_TOKENS and K % 16 == 0 and w.dim() == 2:
                 stats["qgemv"] += 1
                 r2 = residual.reshape(T, -1).contiguous() if (residual is not None and act is None) else None
-                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale.float().contiguous(), r2,
-                              None, False)
+                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale.float().contiguous(), r2)
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
-            if not wq and T <= GEMV_MAX_TOKENS and K % 256 == 0:
+            if not wq and T <= GEMV_MAX_TOKENS and K % 64 == 0 and (K % 256 == 0 or _C().gemv2_supported(T, K)):
                 stats["gemv"] += 1
                 r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
-                nxt = getattr(w, "_nxdi_next", None) if _PREFETCH_NEXT else None
-                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2,
-                              nxt[0] if nxt else None, bool(nxt[1]) if nxt else False)
+                y = _C().gemv(x2, w, bias, norm_weight, norm_eps, norm_offset, _ACT_CODES[act], scale, r2)
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
             n_out = N // 2 if act is not None else N
-            if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM and (T > GEMV_MAX_TOKENS or K % 256 != 0):
+            if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM and (T > GEMV_MAX_TOKENS or K % 64 != 0):
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
                 stats["gemm_tcgen05"] += 1
@@ -114,11 +110,11 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
     K = x.shape[-1]
     T = x.numel() // K
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and group.symm is not None and T <= GEMV_MAX_TOKENS
-            and K % 256 == 0 and w.is_contiguous() and w.dtype == x.dtype and scale is None
+            and K % 64 == 0 and w.is_contiguous() and w.dtype == x.dtype and scale is None
+            and _C().gemv2_supported(T, K)
             and reduce_dtype in (None, torch.float32)):
         stats["gemv_allreduce"] += 1
-        y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None,
-                                      scale, getattr(w, "_nxdi_next", None) if _PREFETCH_NEXT else None)
+        y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None)
         return y.view(*x.shape[:-1], y.shape[-1])
     y = linear(x, w, None, scale=scale)
     y = mappings.all_reduce(y, group, reduce_dtype=reduce_dtype)
@@ -127,53 +123,6 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
     if residual is not None:
         y = y + residual
     return y
-
-
-def gemv_chain_supported(T: int, k_max: int) -> bool:
-    return bool(_C().gemv_chain_ok(int(T), int(k_max)))
-
-
-def gemv_chain(phases, group=None):
-    """Up to four DEPENDENT skinny GEMMs (T <= 8 tokens) in one persistent kernel launch with grid barriers in between
-    (csrc/gemv2.cu ``gemv_chain_kernel``).  ``phases``: list of dicts
-        x         tensor [T,K]  or  int j  (= output of phase j)
-        w         [N,K] bf16;  bias / norm (fused RMSNorm of x) / eps / offset optional
-        residual  tensor [T,N]  or  int j
-        act       None | "silu_mul" | "gelu_tanh_mul" | "gelu_mul"   (GLU epilogue: output N/2 wide)
-        allreduce bool: fused one-shot all-reduce over the group's symmetric workspace
-    Returns the list of outputs.  CUDA only (the decode fast path); callers fall back to ``linear`` otherwise."""
-    T = phases[0]["x"].shape[0]
-    ys, xs, ws, bs, ns, rs, acts, modes, eps, offs, pars = [], [], [], [], [], [], [], [], [], [], []
-    symm = group.symm if group is not None else None
-    for ph in phases:
-        w = ph["w"]
-        glu = ph.get("act") is not None
-        n_out = w.shape[0] // 2 if glu else w.shape[0]
-        ys.append(torch.empty(T, n_out, dtype=w.dtype, device=w.device))
-    for i, ph in enumerate(phases):
-        x = ph["x"]
-        xs.append(ys[x] if isinstance(x, int) else x)
-        ws.append(ph["w"])
-        bs.append(ph.get("bias"))
-        ns.append(ph.get("norm"))
-        r = ph.get("residual")
-        rs.append(ys[r] if isinstance(r, int) else r)
-        acts.append(_ACT_CODES[ph.get("act")])
-        ar = bool(ph.get("allreduce")) and symm is not None
-        modes.append(1 if ar else 0)
-        eps.append(float(ph.get("eps", 1e-6)))
-        offs.append(float(ph.get("offset", 0.0)))
-        if ar:
-            pars.append(symm.parity)
-            symm.parity ^= 1
-            symm.calls += 1
-        else:
-            pars.append(0)
-    stats["gemv_chain"] += 1
-    _C().gemv_chain(xs, ws, bs, ns, rs, ys, acts, modes, eps, offs, symm.recv_ptrs if symm is not None else [],
-                    symm.flag_ptrs if symm is not None else [], symm.rank if symm is not None else 0, pars,
-                    symm.n_max if symm is not None else 0)
-    return ys
 
 
 def apply_rope(x, cos, sin, interleaved: bool = False):
@@ -279,8 +228,20 @@ def paged_attention_decode(q, k_cache, v_cache, block_table, positions, scale, w
 def argmax(logits):
     if _use_cuda(logits) and logits.dim() == 2 and logits.dtype in (torch.float32, torch.bfloat16):
         stats["argmax"] += 1
-        return _C().argmax(logits.contiguous())
+        return _C().argmax(logits.contiguous(), [], None, 0, 0, 0, 0)
     return ref.argmax(logits)
+
+
+def argmax_sharded(logits, group):
+    """Arg-max over a vocabulary-sharded logits row block [B, V_local] -> GLOBAL token ids [B], ONE kernel: the per-rank
+    winners are exchanged through the group's symmetric workspace inside the arg-max kernel (csrc/sampling.cu).  Returns None
+    when the fused path does not apply (CPU, no workspace): the caller falls back to all-gather + glue."""
+    symm = getattr(group, "symm", None)
+    if (symm is None or not _use_cuda(logits) or logits.dim() != 2 or logits.dtype not in (torch.float32, torch.bfloat16)
+            or logits.shape[0] > symm.ARGMAX_ROWS):
+        return None
+    stats["argmax_exchange"] += 1
+    return symm.argmax(logits.contiguous())
 
 
 def sample(logits, top_k, top_p, temperature, rand=None, global_topk: int = 256):

@@ -16,6 +16,7 @@ sharder (modules/checkpoint.py::shard_state_dict) instead of the reference's tra
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -156,7 +157,15 @@ class ParallelEmbedding(nn.Module):
         self.sequence_parallel_enabled = sequence_parallel_enabled
         self.sequence_dimension = 1 if sequence_dimension is None else sequence_dimension
         self.pad_size = 0
-        if shard_across_embedding:
+        # B200: a GPU has 180 GB — sharding a ~1 GB table buys nothing and costs a collective (all-gather / all-reduce) inside
+        # every decode step.  On CUDA the table is REPLICATED (partition_dim None: the checkpoint sharder copies it whole) and
+        # the lookup is local; NXDI_B200_SHARD_EMBEDDING=1 restores the reference layouts (also what the CPU / gloo path tests).
+        self.replicated = (tp > 1 and device is not None and torch.device(device).type == "cuda"
+                           and os.environ.get("NXDI_B200_SHARD_EMBEDDING", "0") != "1")
+        if self.replicated:
+            shape = (num_embeddings, embedding_dim)
+            pdim = None
+        elif shard_across_embedding:
             shape = (num_embeddings, divide(embedding_dim, tp))
             pdim = 1
         else:
@@ -172,7 +181,7 @@ class ParallelEmbedding(nn.Module):
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
         g = self.tensor_parallel_group
-        if g.size == 1:
+        if g.size == 1 or self.replicated:
             return nn.functional.embedding(ids, self.weight)
         if self.shard_across_embedding:
             y = nn.functional.embedding(ids, self.weight)

@@ -221,9 +221,11 @@ class SubModelRunner:
             for s in range(0, B, self.batch_size):
                 sl = slice(s, s + self.batch_size)
                 sub = {k: (v[sl] if torch.is_tensor(v) and v.shape[:1] == (B,) else v) for k, v in kw.items()}
-                outs.append(self._call(input_ids[sl], None if attention_mask is None else attention_mask[sl],
-                                 position_ids[sl], seq_ids[sl],
-                                 None if sampling_params is None else sampling_params[sl], **sub))
+                o = self._call(input_ids[sl], None if attention_mask is None else attention_mask[sl],
+                               position_ids[sl], seq_ids[sl],
+                               None if sampling_params is None else sampling_params[sl], **sub)
+                # graph-backed outputs are views of the graph's static buffers: the next chunk's replay overwrites them
+                outs.append(_clone_output(o))
             return _cat_outputs(outs)
         if self.is_prefill:
             return self._run_prefill(input_ids, attention_mask, position_ids, seq_ids, sampling_params, **kw)
@@ -383,8 +385,9 @@ class SubModelRunner:
         si = g.inputs
 
         def step():
+            # seq_hint: the graph of sequence bucket `sb` bakes a split-KV grid sized for sb keys, not for the whole cache
             out = self.model(si["input_ids"], None, si["position_ids"], si["seq_ids"], si["sampling_params"],
-                             is_prefill=False, **kwargs)
+                             is_prefill=False, seq_hint=int(key[1]), **kwargs)
             if self.async_feedback and out.tokens is not None:
                 si["input_ids"].copy_(out.tokens.view(Bb, 1))
                 si["position_ids"].add_(1)
@@ -427,6 +430,11 @@ class SubModelRunner:
         if g is None:
             g = self._capture(key, Bb, T, kwargs)
         return g
+
+
+def _clone_output(o: ModelOutput) -> ModelOutput:
+    c = lambda t: None if t is None else t.clone()
+    return ModelOutput(tokens=c(o.tokens), logits=c(o.logits), hidden_states=c(o.hidden_states))
 
 
 def _cat_outputs(outs: List[ModelOutput]) -> ModelOutput:

@@ -48,6 +48,7 @@ def main():
         res = torch.randn(T, N, device=dev, dtype=torch.bfloat16)
         dist.broadcast(res, 0)
         for it in range(3):
+            g.symm.begin_step()
             y = ops.linear_allreduce(x, w, None, g, residual=res)
             torch.cuda.synchronize()
         ref = (x.float() @ w.float().t())
@@ -71,6 +72,7 @@ def main():
     s.wait_stream(torch.cuda.current_stream())
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=s):
+        g.symm.begin_step()      # captured: every replay bumps the device-side step counter -> fresh tags
         y = res
         for _ in range(64):
             y = ops.linear_allreduce(x, w, None, g, residual=y)

@@ -37,7 +37,7 @@ def test_rmsnorm(rows, H):
 
 @pytest.mark.parametrize("T", [1, 2, 3, 8])
 @pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (1000 * 16, 2048), (4096, 14336), (512, 512), (40, 256),
-                                 (3072, 4096), (64128, 4096), (4096, 7168), (4096, 2048)])
+                                 (3072, 4096), (64128, 4096), (4096, 7168), (4096, 2048), (4096, 1792), (768, 4096), (4096, 320)])
 def test_gemv(T, N, K):
     x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16)
     w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
@@ -215,41 +215,6 @@ def test_gemm_tcgen05_norm_swiglu(M, N, K):
     xn = ref.rmsnorm(x.float(), g.float(), 1e-5).to(torch.bfloat16).float()
     yr = ref.linear(xn, w.float(), None, act="silu_mul")
     assert y.shape == (M, N // 2) and _rel(y, yr) < 8e-3
-
-
-@pytest.mark.parametrize("T,H,I,NQKV", [(2, 4096, 14336, 6144), (1, 2048, 8192, 2560), (8, 4096, 3584, 1536), (4, 1024, 2816, 1536)])
-def test_gemv_chain_matches_sequential_reference(T, H, I, NQKV):
-    """o_proj(+res) -> rmsnorm+gate_up+SwiGLU -> down(+res) -> rmsnorm+qkv(+bias) in ONE persistent launch."""
-    torch.manual_seed(0)
-    dev, dt = "cuda", torch.bfloat16
-    o = torch.randn(T, H, device=dev, dtype=dt)
-    h = torch.randn(T, H, device=dev, dtype=dt)
-    wo = (torch.randn(H, H, device=dev) * 0.02).to(dt)
-    wgu = (torch.randn(2 * I, H, device=dev) * 0.02).to(dt)
-    wd = (torch.randn(H, I, device=dev) * 0.02).to(dt)
-    wq = (torch.randn(NQKV, H, device=dev) * 0.02).to(dt)
-    bq = (torch.randn(NQKV, device=dev) * 0.1).to(dt)
-    n2 = (1 + 0.1 * torch.randn(H, device=dev)).to(dt)
-    n1 = (1 + 0.1 * torch.randn(H, device=dev)).to(dt)
-    if not ops.gemv_chain_supported(T, max(H, I)):
-        pytest.skip("activations do not fit next to the stage ring")
-    phases = [dict(x=o, w=wo, residual=h), dict(x=0, w=wgu, norm=n2, eps=1e-5, act="silu_mul"),
-              dict(x=1, w=wd, residual=0), dict(x=2, w=wq, bias=bq, norm=n1, eps=1e-5)]
-    for rep in range(3):      # repeated launches reuse tickets / barrier words
-        ys = ops.gemv_chain(phases)
-    torch.cuda.synchronize()
-
-    def rms(x, w):
-        xf = x.float()
-        return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()).to(dt)
-    h1 = (o.float() @ wo.float().T + h.float()).to(dt)
-    gu = rms(h1, n2).float() @ wgu.float().T
-    u = (torch.nn.functional.silu(gu[:, :I]) * gu[:, I:]).to(dt)
-    h2 = (u.float() @ wd.float().T + h1.float()).to(dt)
-    q = (rms(h2, n1).float() @ wq.float().T + bq.float()).to(dt)
-    for got, exp, name in zip(ys, (h1, u, h2, q), ("h1", "u", "h2", "qkv")):
-        err = (got.float() - exp.float()).abs().max().item()
-        assert err <= 0.02 * exp.float().abs().max().item() + 0.02, f"{name}: {err}"
 
 
 @pytest.mark.parametrize("D,nq,nkv,T,ctx,qk_norm", [(128, 32, 8, 1, 200, False), (128, 8, 2, 4, 1500, False), (64, 14, 2, 1, 77, True),

@@ -16,12 +16,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--out", default="gpurun_out/trace.json")
+    ap.add_argument("--shard-shapes", type=int, default=1, help="1 GPU: per-rank shapes of TP=N, no collectives")
     a = ap.parse_args()
     from neuronx_distributed_inference_b200.parallel import state as pstate
     pstate.init_distributed("nccl")
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     rank = int(os.environ.get("RANK", "0"))
-    app = build_app(dict(LLAMA31_8B, num_hidden_layers=a.layers), a.gpus, 2, 256, 128, False)
+    cfg = dict(LLAMA31_8B, num_hidden_layers=a.layers)
+    if a.shard_shapes > 1:
+        n = a.shard_shapes
+        cfg.update(num_attention_heads=32 // n, num_key_value_heads=max(1, 8 // n), intermediate_size=14336 // n, vocab_size=128256 // n)
+    app = build_app(cfg, a.gpus, 2, 256, 128, False)
     ids = torch.randint(0, 100, (2, 128))
     tok = app(ids, attention_mask=torch.ones_like(ids)).tokens
     tkg = app.token_generation_model
