@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace nxdi {
 
 constexpr int SYMM_MAX_RANKS = 8;
@@ -39,6 +41,8 @@ bool gemv2_supported(int T, int K);
 int gemv2_grid(int N, int K, bool glu);
 int gemv2_pmax(int N, int K, bool glu);
 int gemv2_ntiles(int N, bool glu);
+void gemv2_plan(int N, int K, bool glu, int* rows8, int* whole, int* grid, int* pmax);
+int pick_nsplit(int B, int Hkv, int S_hint);
 // debug timeline (tools/prof_decode.py): every decode kernel launched while a buffer is set claims the next slot of 148 x 8 u64
 void gemv2_set_prof(unsigned long long* base, long long n_launches);
 long long prof_next_slot();
@@ -115,5 +119,19 @@ struct AttnPrefillParams {
   int causal;
 };
 void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream);
+
+// persistent decode-step kernel (decode_step.cu): all decoder layers of one decode step in one launch
+long long dstep_new(int T);
+void dstep_set_symm(long long h, const std::vector<long long>& recv_ptrs, const void* step, int rank, int n_max);
+void dstep_add_gemv(long long h, const void* w, int N, int K, const void* x, int ldx, const void* bias, const void* norm_w, float eps,
+                    float norm_offset, int act, const void* residual, void* y, int ldy, bool allreduce);
+void dstep_add_attn(long long h, const void* qkv, void* out, void* k_cache, void* v_cache, const void* q_norm, const void* k_norm,
+                    float norm_eps, int B, int T, int Hq, int Hkv, int D, int S, int L, float scale, int window, const float* sinks,
+                    int nsplit);
+void dstep_finalize(long long h);
+int dstep_num_allreduce(long long h);
+void dstep_free(long long h);
+void dstep_launch(long long h, const int* positions, const int* write_pos, const int* lines, const float* cos, const float* sin,
+                  int call_base, int parity_base, cudaStream_t stream);
 
 }  // namespace nxdi

@@ -332,7 +332,7 @@ at::Tensor topk_sample(const at::Tensor& logits, const at::Tensor& top_k, const 
 }
 
 // ---- attention -----------------------------------------------------------------------------------------------------
-static int pick_nsplit(int B, int Hkv, int S_hint) {
+int pick_nsplit(int B, int Hkv, int S_hint) {
   const int ctas = B * Hkv;
   // short contexts: one 64-key tile per CTA (latency bound: tiles in parallel, not in sequence);
   // long contexts: ~4 tiles per CTA once the chip is full
@@ -449,7 +449,56 @@ at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at:
 
 }  // namespace nxdi
 
+namespace nxdi {
+// ---- persistent decode-step kernel -------------------------------------------------------------------------------------
+int64_t dstep_new_b(int64_t T) { return dstep_new((int)T); }
+void dstep_set_symm_b(int64_t h, const std::vector<int64_t>& recv_ptrs, const at::Tensor& step, int64_t rank, int64_t n_max) {
+  std::vector<long long> v(recv_ptrs.begin(), recv_ptrs.end());
+  dstep_set_symm(h, v, step.data_ptr(), (int)rank, (int)n_max);
+}
+void dstep_add_gemv_b(int64_t h, const at::Tensor& w, const at::Tensor& x, const c10::optional<at::Tensor>& bias,
+                      const c10::optional<at::Tensor>& norm_w, double eps, double offset, int64_t act,
+                      const c10::optional<at::Tensor>& residual, at::Tensor& y, bool allreduce) {
+  TORCH_CHECK(w.is_cuda() && w.dim() == 2 && w.is_contiguous() && is_bf16(w) && is_bf16(x) && is_bf16(y));
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(1) == w.size(1) && y.dim() == 2 && y.stride(1) == 1 && x.stride(0) % 8 == 0);
+  const int N = w.size(0), K = w.size(1);
+  TORCH_CHECK(K % 64 == 0 && y.size(1) == (act != 0 ? N / 2 : N) && y.size(0) == x.size(0));
+  if (residual.has_value()) TORCH_CHECK(residual->stride(0) == y.stride(0) && residual->stride(1) == 1 && is_bf16(*residual));
+  dstep_add_gemv(h, w.data_ptr(), N, K, x.data_ptr(), (int)x.stride(0), optr(bias), optr(norm_w), (float)eps, (float)offset, (int)act,
+                 optr(residual), y.data_ptr(), (int)y.stride(0), allreduce);
+}
+void dstep_add_attn_b(int64_t h, const at::Tensor& qkv, at::Tensor& out, at::Tensor& k_cache, at::Tensor& v_cache,
+                      const c10::optional<at::Tensor>& q_norm, const c10::optional<at::Tensor>& k_norm, double eps, int64_t B,
+                      int64_t T, int64_t nq, int64_t nkv, int64_t D, double scale, int64_t window, const c10::optional<at::Tensor>& sinks,
+                      int64_t s_hint) {
+  TORCH_CHECK(is_bf16(qkv) && is_bf16(out) && is_bf16(k_cache) && k_cache.dim() == 4 && k_cache.is_contiguous() && v_cache.is_contiguous());
+  TORCH_CHECK(k_cache.size(1) == nkv && k_cache.size(3) == D && qkv.is_contiguous() && out.is_contiguous());
+  const int S = k_cache.size(2), L = k_cache.size(0);
+  const int nsplit = pick_nsplit((int)B, (int)nkv, s_hint > 0 ? (int)std::min<int64_t>(s_hint, S) : S);
+  dstep_add_attn(h, qkv.data_ptr(), out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), optr(q_norm), optr(k_norm), (float)eps,
+                 (int)B, (int)T, (int)nq, (int)nkv, (int)D, S, L, (float)scale, (int)window,
+                 sinks.has_value() ? sinks->data_ptr<float>() : nullptr, nsplit);
+}
+void dstep_launch_b(int64_t h, const at::Tensor& positions, const at::Tensor& write_pos, const at::Tensor& lines,
+                    const at::Tensor& cos, const at::Tensor& sin, int64_t call_base, int64_t parity_base) {
+  TORCH_CHECK(positions.is_cuda() && positions.scalar_type() == at::kInt && write_pos.scalar_type() == at::kInt &&
+              lines.scalar_type() == at::kInt && positions.is_contiguous() && write_pos.is_contiguous() && lines.is_contiguous());
+  TORCH_CHECK(cos.scalar_type() == at::kFloat && sin.scalar_type() == at::kFloat && cos.is_contiguous() && sin.is_contiguous());
+  c10::cuda::CUDAGuard guard(positions.device());
+  dstep_launch(h, positions.data_ptr<int>(), write_pos.data_ptr<int>(), lines.data_ptr<int>(), cos.data_ptr<float>(),
+               sin.data_ptr<float>(), (int)call_base, (int)parity_base, cur_stream());
+}
+}  // namespace nxdi
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("dstep_new", &nxdi::dstep_new_b);
+  m.def("dstep_set_symm", &nxdi::dstep_set_symm_b);
+  m.def("dstep_add_gemv", &nxdi::dstep_add_gemv_b);
+  m.def("dstep_add_attn", &nxdi::dstep_add_attn_b);
+  m.def("dstep_finalize", [](int64_t h) { nxdi::dstep_finalize(h); });
+  m.def("dstep_num_allreduce", [](int64_t h) { return (int64_t)nxdi::dstep_num_allreduce(h); });
+  m.def("dstep_free", [](int64_t h) { nxdi::dstep_free(h); });
+  m.def("dstep_launch", &nxdi::dstep_launch_b);
   m.def("rmsnorm", &nxdi::rmsnorm);
   m.def("gemv", &nxdi::gemv);
   m.def("gemv_allreduce", &nxdi::gemv_allreduce);

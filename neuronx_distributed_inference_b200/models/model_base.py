@@ -273,7 +273,14 @@ class NeuronBaseModel(nn.Module):
         lora = getattr(self, "lora", None) if meta.adapter_ids is not None else None
         aux_layers = getattr(self, "aux_hidden_layers", None) if output_hidden else None
         aux = []
-        for i, layer in enumerate(self.layers):
+        mega = False
+        if not is_prefill and lora is None and aux_layers is None and prev_hidden is None:
+            from ..runtime import decode_step
+            if decode_step.eligible(self, h, meta, kw):
+                # every layer of the decode step in ONE persistent kernel (csrc/decode_step.cu)
+                h = decode_step.run_layers(self, h, meta)
+                mega = True
+        for i, layer in enumerate(() if mega else self.layers):
             h = layer(h, meta, self.kv_mgr, lora=lora.for_layer(i)) if lora is not None else layer(h, meta, self.kv_mgr)
             if aux_layers is not None and i in aux_layers:
                 aux.append(h)

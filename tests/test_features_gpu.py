@@ -145,3 +145,44 @@ def test_mixtral_decode_runs_under_cuda_graphs_with_moe_kernels():
     got = run(app)
     assert ops.stats["moe_decode"] > before and len(app.token_generation_model._graphs) > 0
     assert torch.equal(got, run(mk(False)))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(hidden_size=1024, intermediate_size=2816, num_hidden_layers=3, num_attention_heads=8, num_key_value_heads=2, head_dim=128),
+    dict(hidden_size=2048, intermediate_size=1792, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=1, head_dim=128),
+    dict(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=16, num_key_value_heads=16, head_dim=64),
+])
+def test_persistent_decode_step_matches_layer_by_layer(cfg):
+    """csrc/decode_step.cu (all layers of a decode step in one persistent launch) vs the per-kernel path: same logits."""
+    from neuronx_distributed_inference_b200 import ops
+    from neuronx_distributed_inference_b200.runtime import decode_step
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    torch.manual_seed(0)
+    app = build_random_llama(dict(cfg, vocab_size=4096), batch_size=2, seq_len=256, max_context_length=128, device="cuda",
+                             output_logits=True)
+    ids = torch.randint(0, 4096, (2, 100))
+
+    def run(enabled):
+        decode_step._ENABLED = enabled
+        app.reset()
+        out = app(ids, attention_mask=torch.ones_like(ids))
+        tok = out.tokens
+        pos = torch.full((2, 1), 100, dtype=torch.int32)
+        logits = []
+        for _ in range(6):
+            out = app(tok.view(2, 1).cpu(), position_ids=pos)
+            logits.append(out.logits.float().clone())
+            tok = out.tokens
+            pos = pos + 1
+        torch.cuda.synchronize()
+        return torch.stack(logits)
+    try:
+        n0 = ops.stats["decode_step"]
+        a = run(True)
+        assert ops.stats["decode_step"] > n0, "persistent decode-step kernel was not used"
+        b = run(False)
+    finally:
+        decode_step._ENABLED = True
+    rel = ((a - b).norm() / b.norm()).item()
+    assert rel < 2e-2, rel
+    assert (a.argmax(-1) == b.argmax(-1)).float().mean().item() > 0.9
