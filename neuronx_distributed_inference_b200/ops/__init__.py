@@ -110,6 +110,7 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
     K = x.shape[-1]
     T = x.numel() // K
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and group.symm is not None and T <= GEMV_MAX_TOKENS
+            and w.shape[0] <= group.symm.n_max
             and K % 64 == 0 and w.is_contiguous() and w.dtype == x.dtype and scale is None
             and _C().gemv2_supported(T, K)
             and reduce_dtype in (None, torch.float32)):

@@ -19,7 +19,9 @@ import torch
 
 from .. import ops
 
-_ENABLED = os.environ.get("NXDI_B200_DECODE_STEP", "1") != "0"
+# Opt-in: correct (tests/test_features_gpu.py) but measured SLOWER than the per-kernel path on B200 so far (Llama-3.1-8B bs 2:
+# 4.27 vs 2.82 ms/step at TP1, 1.57 vs 1.15 ms on TP8 shard shapes — profiles/decode_r2.md has the phase timeline and the analysis).
+_ENABLED = os.environ.get("NXDI_B200_DECODE_STEP", "0") == "1"
 
 
 def eligible(model, h: torch.Tensor, meta, kw) -> bool:

@@ -37,7 +37,7 @@ def main():
     g = pstate.get_tensor_model_parallel_group()
     dev = torch.device("cuda", torch.cuda.current_device())
     log("groups ok")
-    g.symm = SymmetricWorkspace.create(g, dev, max_width=4096)
+    g.symm = SymmetricWorkspace.create(g, dev, max_width=8192)
     log("workspace ok", [hex(p) for p in g.symm.recv_ptrs])
     torch.manual_seed(rank)
     worst = 0.0

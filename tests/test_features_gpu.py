@@ -182,7 +182,7 @@ def test_persistent_decode_step_matches_layer_by_layer(cfg):
         assert ops.stats["decode_step"] > n0, "persistent decode-step kernel was not used"
         b = run(False)
     finally:
-        decode_step._ENABLED = True
+        decode_step._ENABLED = False
     rel = ((a - b).norm() / b.norm()).item()
     assert rel < 2e-2, rel
     assert (a.argmax(-1) == b.argmax(-1)).float().mean().item() > 0.9
