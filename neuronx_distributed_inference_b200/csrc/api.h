@@ -120,6 +120,23 @@ struct AttnPrefillParams {
 };
 void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream);
 
+// symmetric heap (symm_heap.cpp) and NVLS collectives (nvls.cu)
+long long symm_heap_create(long long bytes, int device, int world, int rank);
+long long symm_heap_size(long long h);
+long long symm_heap_local_va(long long h);
+int symm_heap_export_fd(long long h);
+long long symm_heap_import_peer(long long h, int peer, int fd);
+bool symm_heap_multicast_supported(int device);
+int symm_heap_mc_create(long long h, int world);
+void symm_heap_mc_import(long long h, int fd);
+void symm_heap_mc_add_device(long long h);
+long long symm_heap_mc_bind_map(long long h);
+long long symm_heap_mc_va(long long h);
+void symm_heap_destroy(long long h);
+constexpr int NVLS_SIG_WORDS = 2 * 64 * SYMM_MAX_RANKS;   // [2 phase][64 CTAs][world] u32 signal words per heap
+void nvls_collective_launch(int mode, const long long* sig_ptrs, const void* step, int rank, int world, int call, void* mc, void* local,
+                            const void* residual, void* out, int segs, int rows_per_seg, int row_elems, cudaStream_t stream);
+
 // persistent decode-step kernel (decode_step.cu): all decoder layers of one decode step in one launch
 long long dstep_new(int T);
 void dstep_set_symm(long long h, const std::vector<long long>& recv_ptrs, const void* step, int rank, int n_max);

@@ -141,7 +141,7 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
 
 // tcgen05 GEMM for T > 8 tokens (prefill, long speculation windows)
 at::Tensor gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias, int64_t act,
-                const c10::optional<at::Tensor>& residual) {
+                const c10::optional<at::Tensor>& residual, const c10::optional<at::Tensor>& out) {
   TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1));
   TORCH_CHECK(is_bf16(x) && is_bf16(w) && x.stride(1) == 1 && w.is_contiguous());
   const int M = x.size(0), K = x.size(1), N = w.size(0);
@@ -150,7 +150,9 @@ at::Tensor gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
   const int n_out = glu ? N / 2 : N;
   TORCH_CHECK(n_out % 8 == 0 && (!glu || N % 2 == 0));
   c10::cuda::CUDAGuard guard(x.device());
-  auto y = at::empty({M, n_out}, x.options());
+  if (out.has_value())
+    TORCH_CHECK(out->is_cuda() && is_bf16(*out) && out->dim() == 2 && out->size(0) == M && out->size(1) == n_out && out->is_contiguous());
+  auto y = out.has_value() ? *out : at::empty({M, n_out}, x.options());
   if (residual.has_value())
     TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(0) == M && residual->size(1) == n_out && is_bf16(*residual));
   gemm_tcgen05_launch(x.data_ptr(), (int)x.stride(0), w.data_ptr(), optr(bias), optr(residual), y.data_ptr(), n_out, M, N, K,
@@ -450,6 +452,21 @@ at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at:
 }  // namespace nxdi
 
 namespace nxdi {
+// ---- symmetric heap + NVLS collectives -------------------------------------------------------------------------------------
+// mode 0 all-reduce (in place in the symmetric buffer; `out` = private copy (+ residual) when given), 1 reduce-scatter, 2 all-gather
+void nvls_collective(int64_t mode, const std::vector<int64_t>& sig_ptrs, const at::Tensor& step, int64_t rank, int64_t call,
+                     int64_t mc_ptr, int64_t local_ptr, const c10::optional<at::Tensor>& residual, const c10::optional<at::Tensor>& out,
+                     int64_t segs, int64_t rows_per_seg, int64_t row_elems) {
+  TORCH_CHECK(step.is_cuda() && step.scalar_type() == at::kInt);
+  if (residual.has_value()) TORCH_CHECK(is_bf16(*residual) && residual->is_contiguous());
+  if (out.has_value()) TORCH_CHECK(is_bf16(*out) && out->is_contiguous());
+  c10::cuda::CUDAGuard guard(step.device());
+  std::vector<long long> sp(sig_ptrs.begin(), sig_ptrs.end());
+  nvls_collective_launch((int)mode, sp.data(), step.data_ptr(), (int)rank, (int)sp.size(), (int)call, reinterpret_cast<void*>(mc_ptr),
+                         reinterpret_cast<void*>(local_ptr), residual.has_value() ? residual->data_ptr() : nullptr,
+                         out.has_value() ? out->data_ptr() : nullptr, (int)segs, (int)rows_per_seg, (int)row_elems, cur_stream());
+}
+
 // ---- persistent decode-step kernel -------------------------------------------------------------------------------------
 int64_t dstep_new_b(int64_t T) { return dstep_new((int)T); }
 void dstep_set_symm_b(int64_t h, const std::vector<int64_t>& recv_ptrs, const at::Tensor& step, int64_t rank, int64_t n_max) {
@@ -491,6 +508,18 @@ void dstep_launch_b(int64_t h, const at::Tensor& positions, const at::Tensor& wr
 }  // namespace nxdi
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("symm_heap_create", [](int64_t bytes, int64_t dev, int64_t world, int64_t rank) { return (int64_t)nxdi::symm_heap_create(bytes, (int)dev, (int)world, (int)rank); });
+  m.def("symm_heap_size", [](int64_t h) { return (int64_t)nxdi::symm_heap_size(h); });
+  m.def("symm_heap_local_va", [](int64_t h) { return (int64_t)nxdi::symm_heap_local_va(h); });
+  m.def("symm_heap_export_fd", [](int64_t h) { return (int64_t)nxdi::symm_heap_export_fd(h); });
+  m.def("symm_heap_import_peer", [](int64_t h, int64_t peer, int64_t fd) { return (int64_t)nxdi::symm_heap_import_peer(h, (int)peer, (int)fd); });
+  m.def("symm_heap_multicast_supported", [](int64_t dev) { return nxdi::symm_heap_multicast_supported((int)dev); });
+  m.def("symm_heap_mc_create", [](int64_t h, int64_t world) { return (int64_t)nxdi::symm_heap_mc_create(h, (int)world); });
+  m.def("symm_heap_mc_import", [](int64_t h, int64_t fd) { nxdi::symm_heap_mc_import(h, (int)fd); });
+  m.def("symm_heap_mc_add_device", [](int64_t h) { nxdi::symm_heap_mc_add_device(h); });
+  m.def("symm_heap_mc_bind_map", [](int64_t h) { return (int64_t)nxdi::symm_heap_mc_bind_map(h); });
+  m.def("symm_heap_destroy", [](int64_t h) { nxdi::symm_heap_destroy(h); });
+  m.def("nvls_collective", &nxdi::nvls_collective);
   m.def("dstep_new", &nxdi::dstep_new_b);
   m.def("dstep_set_symm", &nxdi::dstep_set_symm_b);
   m.def("dstep_add_gemv", &nxdi::dstep_add_gemv_b);

@@ -1,13 +1,20 @@
 // Prefill / large-T GEMM on the 5th-generation tensor cores:  C[M,N] = epilogue( A[M,K] · B[N,K]^T )   (bf16 in, fp32 acc)
 //
 //   A = activations [tokens, K] (K-major), B = nn.Linear weight [out, K] (K-major)  ->  no transposes anywhere.
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128x64 A and 128x64 B tiles through a 4-deep mbarrier ring;
-//   * ONE elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128x128x16) with shared-memory descriptors;
-//     the 128x128 fp32 accumulator lives in TMEM (128 columns); tcgen05.commit releases smem stages / signals the
-//     epilogue through mbarriers — no thread ever holds accumulator fragments during the main loop;
-//   * 4 epilogue warps read the accumulator with tcgen05.ld (32x32b: one TMEM lane = one output row per thread),
-//     apply bias / residual / SwiGLU (tile = 64 gate + 64 up columns of the fused gate_up weight) and store bf16.
-//   Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (lane quarter = warp % 4).
+//   PERSISTENT: one CTA per SM walks the tile list (M fastest, so the CTAs resident at any moment share a few weight tiles and
+//   the weights leave HBM once).  CTA tile = (TM x 128) rows x BN columns:
+//     <TM 2, BN 128>  prefill of <= 256 tokens: ONE row of tiles, every weight byte is fetched exactly once (memory bound);
+//     <TM 1, BN 256>  larger M: UMMA 128x256x16 reads 12 KB of shared memory per 128 tensor cycles (96 B/clk) — two 128x128
+//                     instructions would read 16 KB (128 B/clk = the whole smem bandwidth; measured 72 % of cuBLAS, stuck);
+//     <TM 1, BN 128>  M <= 128.
+//   * warp 0: TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B) through a 4-deep mbarrier ring of 32/48 KB stages; the WEIGHT
+//     tiles of the first ring fill are issued BEFORE griddepcontrol.wait (weights never depend on the previous kernel);
+//   * warp 1: ONE elected thread issues tcgen05.mma.cta_group::1.kind::f16 with shared-memory descriptors; accumulators live in
+//     TMEM, double buffered (2 x TM x 128 columns): tcgen05.commit releases smem stages and hands a finished accumulator to the
+//     epilogue through mbarriers, and the mainloop of tile i+1 runs while tile i is being written out;
+//   * warps 4..7: epilogue — tcgen05.ld (32x32b: one TMEM lane = one output row per thread), bias / residual / SwiGLU (tile = 64
+//     gate + 64 up columns of the fused gate_up weight), bf16 stores; or, for the row-parallel sequence-parallel prefill, the
+//     fused REDUCE-SCATTER epilogue (see GemmParams::rs_*).
 // reference kernels replaced: K3 qkv, K4 output_projection_cte, K5 mlp (prefill variants), K15 collective matmul.
 #include <algorithm>
 #include <string>
@@ -17,19 +24,21 @@
 
 namespace nxdi {
 
-// GM_BN is a template parameter: 128 for large grids; 64 when a 128-wide tiling would leave SMs idle (prefill with a few
-// hundred tokens: M/128 x N/128 tiles < 2 x #SMs) — twice the CTAs, 96 KB of shared memory so two CTAs share an SM.
 constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
 constexpr int GM_THREADS = 256;
-constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;
+constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;   // one 128-row A sub-tile
 
 struct GemmParams {
-  CUtensorMap tma_a;  // A [M,K]: dims {K, M}, box {64, 128}, SWIZZLE_128B
+  CUtensorMap tma_a;  // A [M,K]: dims {K, M}, box {64, TM*128}, SWIZZLE_128B (one instruction per k-block for both sub-tiles)
   CUtensorMap tma_b;  // B [N,K]: dims {K, N}, box {64, 128 (64 for GLU)}
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, N_out] or null
   __nv_bfloat16* c;               // [M, N_out]
   int M, N, K, ldc, act;          // act: 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up  (N_out = N/2 when act != 0)
+  int m_tiles, n_tiles;           // tile grid (CTA tiles of TM*128 x 128 output columns; 64 output features for GLU)
+  int splits;                     // split-K factor: work item = (tile, k slice); partial accumulators meet in `ws`
+  float* ws;                      // [tiles][splits][TM*128][128] fp32 partials (L2 resident)
+  unsigned* tickets;              // [tiles], self-resetting
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -92,27 +101,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
-template <int GM_BN>
-__global__ void __launch_bounds__(GM_THREADS, GM_BN == 64 ? 2 : 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int GM_B_BYTES = GM_BN * GM_BK * 2;
-  constexpr int GM_TMEM_COLS = GM_BN;
+__device__ __forceinline__ void mb_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
+}
+
+template <int TM, int BN>
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int B_BYTES = BN * GM_BK * 2;
+  constexpr int STAGE_BYTES = TM * GM_A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = TM * BN;            // TMEM columns of one accumulator buffer
+  constexpr int TMEM_COLS = 2 * ACC_COLS;         // double buffered: 256 (TM=1) or 512 (TM=2)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                  // [STAGES][128][64] bf16, swizzled
-  uint8_t* sB = smem + GM_STAGES * GM_A_BYTES;         // [STAGES][128][64]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + GM_STAGES * GM_B_BYTES);
+  uint8_t* smem = smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u);
+  // stage s: [TM][128][64] A sub-tiles, then [128][64] B tile (all 128B-swizzled, 1024-aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GM_STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + GM_STAGES;
-  uint64_t* tmem_full = empty_bar + GM_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + GM_STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // raster: M tiles vary fastest, so the CTAs resident at any moment share a handful of weight (B) tiles and stream the
-  // weights from HBM exactly once; A (activations, a few MB) is what gets re-read, from L2.  (ncu on the first version,
-  // N-fastest: 3.77 GB of DRAM reads for a 0.25 GB problem.)
-  const int m0 = blockIdx.x * GM_BM;
   const bool glu = p.act != 0;
-  const int n_out0 = blockIdx.y * (glu ? GM_BN / 2 : GM_BN);  // first output column of this tile
   const int nkb = p.K / GM_BK;
+  const int S = p.splits;
+  const int total_tiles = p.m_tiles * p.n_tiles * S;   // work items: (tile, k slice), k slice fastest
+  const int tile_out = glu ? BN / 2 : BN;   // output columns per tile
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tma_a) : "memory");
@@ -120,14 +133,17 @@ __global__ void __launch_bounds__(GM_THREADS, GM_BN == 64 ? 2 : 1) gemm_tcgen05_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GM_STAGES; ++s) {
-      mb_init(&full_bar[s], 1);
+      mb_init(&full_bar[s], 2);    // two producers (weights: warp 0, activations: warp 3), each posts its own byte count
       mb_init(&empty_bar[s], 1);
     }
-    mb_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mb_init(&tmem_full[b], 1);
+      mb_init(&tmem_empty[b], 4);   // the four epilogue warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(GM_TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -136,126 +152,206 @@ __global__ void __launch_bounds__(GM_THREADS, GM_BN == 64 ? 2 : 1) gemm_tcgen05_
   const uint32_t tmem_base = *tmem_slot;
 
   pdl_launch_dependents();
-  pdl_wait();  // A (activations) is produced by the previous kernel
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  if (warp == 0 || warp == 3) {
+    // ================= TMA producers =================
+    // One issuing thread sustains ~one TMA instruction per 0.2 us (tools/bench_stream.cu); a k-block of 48 KB issued as three
+    // instructions by ONE thread took 0.5 us while the tensor pipe needs 0.26 us for it.  So the two operands have their own
+    // producer warp — warp 0 streams the WEIGHT tile (and starts before griddepcontrol.wait: weights do not depend on the previous
+    // kernel), warp 3 the ACTIVATION tile (one 256-row box when TM = 2) — both post to the same full barrier.
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % GM_STAGES;
-        const uint32_t ph = (uint32_t)((kb / GM_STAGES) & 1);
-        mb_wait(&empty_bar[s], ph ^ 1u);
-        mb_expect(&full_bar[s], GM_A_BYTES + GM_B_BYTES);
-        tma_2d(sA + s * GM_A_BYTES, &p.tma_a, kb * GM_BK, m0, &full_bar[s]);
-        if (glu) {  // 64 gate rows + 64 up rows of the fused [gate; up] weight
-          tma_2d(sB + s * GM_B_BYTES, &p.tma_b, kb * GM_BK, n_out0, &full_bar[s]);
-          tma_2d(sB + s * GM_B_BYTES + GM_B_BYTES / 2, &p.tma_b, kb * GM_BK, (p.N >> 1) + n_out0, &full_bar[s]);
-        } else {
-          tma_2d(sB + s * GM_B_BYTES, &p.tma_b, kb * GM_BK, n_out0, &full_bar[s]);
+      const bool is_b = warp == 0;
+      if (!is_b) pdl_wait();
+      long long it = 0;   // k-block counter across work items (ring position)
+      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        const int t = w / S, ks = w % S;
+        const int m0 = (t % p.m_tiles) * (TM * GM_BM), n_out0 = (t / p.m_tiles) * tile_out;
+        const int kb0 = (int)((long long)nkb * ks / S), kb1 = (int)((long long)nkb * (ks + 1) / S);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = (int)(it % GM_STAGES);
+          const uint32_t ph = (uint32_t)((it / GM_STAGES) & 1);
+          mb_wait(&empty_bar[s], ph ^ 1u);
+          if (is_b) {
+            mb_expect(&full_bar[s], B_BYTES);
+            uint8_t* sB = smem + s * STAGE_BYTES + TM * GM_A_BYTES;
+            if (glu) {  // 64 gate rows + 64 up rows of the fused [gate; up] weight
+              tma_2d(sB, &p.tma_b, kb * GM_BK, n_out0, &full_bar[s]);
+              tma_2d(sB + B_BYTES / 2, &p.tma_b, kb * GM_BK, (p.N >> 1) + n_out0, &full_bar[s]);
+            } else {
+              tma_2d(sB, &p.tma_b, kb * GM_BK, n_out0, &full_bar[s]);
+            }
+          } else {
+            mb_expect(&full_bar[s], TM * GM_A_BYTES);
+            tma_2d(smem + s * STAGE_BYTES, &p.tma_a, kb * GM_BK, m0, &full_bar[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(GM_BM, GM_BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % GM_STAGES;
-        const uint32_t ph = (uint32_t)((kb / GM_STAGES) & 1);
-        mb_wait(&full_bar[s], ph);
+      constexpr uint32_t idesc = umma_idesc(GM_BM, BN);
+      long long it = 0;
+      int tc = 0;
+      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tc) {
+        const int ks = w % S;
+        const int kb0 = (int)((long long)nkb * ks / S), kb1 = (int)((long long)nkb * (ks + 1) / S);
+        const int buf = tc & 1;
+        mb_wait(&tmem_empty[buf], (uint32_t)(((tc >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_desc(sA + s * GM_A_BYTES), db = umma_desc(sB + s * GM_B_BYTES);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = (int)(it % GM_STAGES);
+          const uint32_t ph = (uint32_t)((it / GM_STAGES) & 1);
+          mb_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t db = umma_desc(smem + s * STAGE_BYTES + TM * GM_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < GM_BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int sub = 0; sub < TM; ++sub) {
+            const uint64_t da = umma_desc(smem + s * STAGE_BYTES + sub * GM_A_BYTES);
+            const uint32_t acc = tmem_base + (uint32_t)(buf * ACC_COLS + sub * BN);
+#pragma unroll
+            for (int k = 0; k < GM_BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              umma_f16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+        umma_commit(&tmem_full[buf]);       // accumulator(s) of this tile complete
       }
-      umma_commit(tmem_full);        // accumulator complete
     }
   } else if (warp >= 4) {
-    // ================= epilogue: TMEM -> registers -> global =================
+    // ================= epilogue: TMEM -> registers -> (split-K fix-up) -> global =================
+    pdl_wait();   // residual rows come from the previous kernels
+    __shared__ int s_last;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;     // one output row per thread
-    mb_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int etid = threadIdx.x - 128;     // 0..127 inside the epilogue group
     const int n_out = glu ? (p.N >> 1) : p.N;
-    if (!glu) {
+    // final math + store of 32 accumulator columns [c0, c0+32) of one row (GLU: gate chunk + matching up chunk)
+    auto store_chunk = [&](int row, int n_out0, int c0, const uint32_t (&vg)[32], const uint32_t (&vu)[32]) {
+      const int col0 = n_out0 + c0;
+      if (row >= p.M || col0 >= n_out) return;
+      __nv_bfloat16* dst = p.c + (size_t)row * p.ldc + col0;
+      const __nv_bfloat16* res = (!glu && p.residual) ? p.residual + (size_t)row * p.ldc + col0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a = __uint_as_float(vg[j + e]);
+          const bool in = col0 + j + e < n_out;
+          if (p.bias && in) a += __bfloat162float(p.bias[col0 + j + e]);
+          if (glu) {
+            float up = __uint_as_float(vu[j + e]);
+            if (p.bias && in) up += __bfloat162float(p.bias[n_out + col0 + j + e]);
+            a = (p.act == 1 ? silu(a) : (p.act == 2 ? gelu_tanh(a) : gelu_erf(a))) * up;
+          }
+          f[e] = a;
+        }
+        if (col0 + j + 8 <= n_out) {
+          if (res) {
+            const uint4 r = ldg_act(res + j);
+            f[0] += bf16lo(r.x); f[1] += bf16hi(r.x); f[2] += bf16lo(r.y); f[3] += bf16hi(r.y);
+            f[4] += bf16lo(r.z); f[5] += bf16hi(r.z); f[6] += bf16lo(r.w); f[7] += bf16hi(r.w);
+          }
+          *reinterpret_cast<uint4*>(dst + j) =
+              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        } else {
+          for (int e = 0; e < 8; ++e)
+            if (col0 + j + e < n_out) dst[j + e] = __float2bfloat16(f[e] + (res ? ldg_act_bf16(res + j + e) : 0.f));
+        }
+      }
+    };
+    const int half = glu ? BN / 2 : BN;   // accumulator columns holding "gate or value"
+    int tc = 0;
+    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tc) {
+      const int t = w / S, ks = w % S;
+      const int buf = tc & 1;
+      const int m0 = (t % p.m_tiles) * (TM * GM_BM), n_out0 = (t / p.m_tiles) * tile_out;
+      mb_wait(&tmem_full[buf], (uint32_t)((tc >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float* my_ws = S > 1 ? p.ws + ((size_t)t * S + ks) * (TM * GM_BM) * BN : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < GM_BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int col0 = n_out0 + c0;
-        if (row < p.M && col0 < n_out) {
-          __nv_bfloat16* dst = p.c + (size_t)row * p.ldc + col0;
-          const __nv_bfloat16* res = p.residual ? p.residual + (size_t)row * p.ldc + col0 : nullptr;
+      for (int sub = 0; sub < TM; ++sub) {
+        const int r_in = sub * GM_BM + q * 32 + lane;         // row inside the CTA tile (one per thread)
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_COLS + sub * BN);
+        if (S > 1) {
+          // split-K: park the fp32 partial tile (row-contiguous 128 B chunks per thread)
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint4* d4 = reinterpret_cast<uint4*>(my_ws + (size_t)r_in * BN + c0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              f[e] = __uint_as_float(v[j + e]);
-              if (p.bias) f[e] += __bfloat162float(p.bias[col0 + j + e]);
-            }
-            if (res) {
-              const uint4 r = *reinterpret_cast<const uint4*>(res + j);
-              f[0] += bf16lo(r.x); f[1] += bf16hi(r.x); f[2] += bf16lo(r.y); f[3] += bf16hi(r.y);
-              f[4] += bf16lo(r.z); f[5] += bf16hi(r.z); f[6] += bf16lo(r.w); f[7] += bf16hi(r.w);
-            }
-            if (col0 + j + 8 <= n_out) {
-              *reinterpret_cast<uint4*>(dst + j) =
-                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-            } else {
-              for (int e = 0; e < 8; ++e)
-                if (col0 + j + e < n_out) dst[j + e] = __float2bfloat16(f[e]);
-            }
+            for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < half; c0 += 32) {
+            uint32_t vg[32], vu[32];
+            tmem_ld32(lane_addr + c0, vg);
+            if (glu) tmem_ld32(lane_addr + BN / 2 + c0, vu);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            store_chunk(m0 + r_in, n_out0, c0, vg, vu);
           }
         }
       }
-    } else {
-      // columns [0,64) = gate, [64,128) = up of the same 64 output features
+      // this warp has read its lanes of the buffer: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mb_arrive(&tmem_empty[buf]);
+      if (S > 1) {
+        // the LAST k slice of a tile to arrive sums the partials (slice order: deterministic) and runs the real epilogue
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) s_last = (atomicAdd(&p.tickets[t], 1u) == (unsigned)(S - 1)) ? 1 : 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (s_last) {
+          __threadfence();
+          const float* tile_ws = p.ws + (size_t)t * S * (TM * GM_BM) * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < GM_BN / 2; c0 += 32) {
-        uint32_t vg[32], vu[32];
-        tmem_ld32(lane_addr + c0, vg);
-        tmem_ld32(lane_addr + GM_BN / 2 + c0, vu);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int col0 = n_out0 + c0;
-        if (row < p.M && col0 < n_out) {
-          __nv_bfloat16* dst = p.c + (size_t)row * p.ldc + col0;
+          for (int sub = 0; sub < TM; ++sub) {
+            const int r_in = sub * GM_BM + q * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < half; c0 += 32) {
+              uint32_t vg[32], vu[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
+              for (int j = 0; j < 32; ++j) vg[j] = vu[j] = 0u;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float gte = __uint_as_float(vg[j + e]), up = __uint_as_float(vu[j + e]);
-              if (p.bias) {
-                gte += __bfloat162float(p.bias[col0 + j + e]);
-                up += __bfloat162float(p.bias[n_out + col0 + j + e]);
+              for (int sl = 0; sl < 4; ++sl) {      // S <= 4: fully unrolled so that all partial loads of a chunk are in flight
+                if (sl >= S) break;
+                const float* src = tile_ws + ((size_t)sl * (TM * GM_BM) + r_in) * BN + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a = __ldcg(reinterpret_cast<const float4*>(src + j));
+                  vg[j] = __float_as_uint(__uint_as_float(vg[j]) + a.x);
+                  vg[j + 1] = __float_as_uint(__uint_as_float(vg[j + 1]) + a.y);
+                  vg[j + 2] = __float_as_uint(__uint_as_float(vg[j + 2]) + a.z);
+                  vg[j + 3] = __float_as_uint(__uint_as_float(vg[j + 3]) + a.w);
+                  if (glu) {
+                    const float4 b = __ldcg(reinterpret_cast<const float4*>(src + BN / 2 + j));
+                    vu[j] = __float_as_uint(__uint_as_float(vu[j]) + b.x);
+                    vu[j + 1] = __float_as_uint(__uint_as_float(vu[j + 1]) + b.y);
+                    vu[j + 2] = __float_as_uint(__uint_as_float(vu[j + 2]) + b.z);
+                    vu[j + 3] = __float_as_uint(__uint_as_float(vu[j + 3]) + b.w);
+                  }
+                }
               }
-              const float a = p.act == 1 ? silu(gte) : (p.act == 2 ? gelu_tanh(gte) : gelu_erf(gte));
-              f[e] = a * up;
-            }
-            if (col0 + j + 8 <= n_out) {
-              *reinterpret_cast<uint4*>(dst + j) =
-                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-            } else {
-              for (int e = 0; e < 8; ++e)
-                if (col0 + j + e < n_out) dst[j + e] = __float2bfloat16(f[e]);
+              store_chunk(m0 + r_in, n_out0, c0, vg, vu);
             }
           }
+          if (etid == 0) p.tickets[t] = 0;   // re-armed for the next launch / graph replay
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last reusable
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(GM_TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -284,44 +380,94 @@ static void make_2d(CUtensorMap* tm, const void* ptr, int rows, int K, int ld_el
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (gemm) failed: " + std::to_string((int)r));
 }
 
+// split-K scratch (per device): fp32 partial tiles + tickets
+static size_t gemm_ws_bytes() { return (size_t)96 << 20; }
+static int gemm_max_tickets() { return 1 << 16; }
+static float* g_gemm_ws[16] = {nullptr};
+static unsigned* g_gemm_tk[16] = {nullptr};
+static float* gemm_ws() {
+  int dev;
+  cudaGetDevice(&dev);
+  if (g_gemm_ws[dev] == nullptr) {
+    if (cudaMalloc(&g_gemm_ws[dev], gemm_ws_bytes()) != cudaSuccess) throw std::runtime_error("gemm: split-K workspace allocation failed");
+  }
+  return g_gemm_ws[dev];
+}
+static unsigned* gemm_tickets() {
+  int dev;
+  cudaGetDevice(&dev);
+  if (g_gemm_tk[dev] == nullptr) {
+    if (cudaMalloc(&g_gemm_tk[dev], gemm_max_tickets() * sizeof(unsigned)) != cudaSuccess) throw std::runtime_error("gemm: ticket allocation failed");
+    cudaMemset(g_gemm_tk[dev], 0, gemm_max_tickets() * sizeof(unsigned));
+  }
+  return g_gemm_tk[dev];
+}
+
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
                          int N, int K, int act, cudaStream_t stream) {
   GemmParams p;
   const bool glu = act != 0;
-  make_2d(&p.tma_a, a, M, K, lda, GM_BM);
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int n_out_ = glu ? N / 2 : N;
-  const long long tiles128 = (long long)((M + GM_BM - 1) / GM_BM) * ((n_out_ + (glu ? 63 : 127)) / (glu ? 64 : 128));
-  static int force_bn = -1;
-  if (force_bn < 0) {
-    const char* e = getenv("NXDI_B200_GEMM_BN");
-    force_bn = e ? atoi(e) : 0;
-  }
-  const int BN = force_bn ? force_bn : (tiles128 < 2LL * n_sms ? 64 : 128);
-  make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.c = reinterpret_cast<__nv_bfloat16*>(c);
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.act = act;
-  const size_t smem = GM_STAGES * (GM_A_BYTES + BN * GM_BK * 2) + 256 + 1024;
+  // TM = 2 (256-row CTA tiles) whenever there is more than one 128-row block: each weight tile then feeds two UMMAs
+  static int force_tm = -1;
+  if (force_tm < 0) {
+    const char* e = getenv("NXDI_B200_GEMM_TM");
+    force_tm = e ? atoi(e) : 0;
+  }
+  const int TM = force_tm ? force_tm : ((M > GM_BM && M <= 2 * GM_BM) ? 2 : 1);
+  const int BN = (TM == 1 && M > 2 * GM_BM) ? 256 : 128;
+  make_2d(&p.tma_a, a, M, K, lda, TM * GM_BM);
+  make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN);
+  const int n_out = glu ? N / 2 : N;
+  const int tile_out = glu ? BN / 2 : BN;
+  p.m_tiles = (M + TM * GM_BM - 1) / (TM * GM_BM);
+  p.n_tiles = (n_out + tile_out - 1) / tile_out;
+  // split-K when the tile grid leaves SMs idle or quantises badly (skinny prefill: M <= 256, N of a few thousand):
+  // minimise  ceil(tiles * S / SMs) / S  (+ a small fix-up charge), bounded by the workspace and >= 8 k-blocks per slice
+  const int tiles = p.m_tiles * p.n_tiles, nkb = K / GM_BK;
+  static int force_s = -1;
+  if (force_s < 0) {
+    const char* e = getenv("NXDI_B200_GEMM_SPLITK");
+    force_s = e ? atoi(e) : 0;
+  }
+  int best_s = 1;
+  double best = 1e30;
+  const size_t tile_ws_bytes = (size_t)TM * GM_BM * BN * 4;
+  // only when at most a quarter of the SMs would get a tile (measured: the partial round trip costs ~10 us, so a 1.5-wave grid
+  // such as gate_up at M = 256 — 224 tiles — is better left alone: 86 us unsplit vs 280 us with 3 slices)
+  if (tiles * 4 <= n_sms) {
+    for (int sgl = 1; sgl <= 4; ++sgl) {
+      if (sgl > 1 && (nkb / sgl < 8 || (size_t)tiles * sgl * tile_ws_bytes > gemm_ws_bytes())) break;
+      const double cost = (double)((tiles * sgl + n_sms - 1) / n_sms) / sgl + (sgl > 1 ? 0.06 : 0.0);
+      if (cost < best - 1e-9) { best = cost; best_s = sgl; }
+    }
+  }
+  p.splits = force_s > 0 ? std::min({force_s, 4, std::max(1, nkb / 2)}) : best_s;
+  if ((size_t)tiles * p.splits * tile_ws_bytes > gemm_ws_bytes() || tiles > gemm_max_tickets()) p.splits = 1;
+  p.ws = p.splits > 1 ? gemm_ws() : nullptr;
+  p.tickets = gemm_tickets();
+  const size_t smem = (size_t)GM_STAGES * (TM * GM_A_BYTES + BN * GM_BK * 2) + 256 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GM_STAGES * (GM_A_BYTES + 128 * GM_BK * 2) + 256 + 1024);
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GM_STAGES * (GM_A_BYTES + 64 * GM_BK * 2) + 256 + 1024);
+    const int max_smem = GM_STAGES * (2 * GM_A_BYTES + 128 * GM_BK * 2) + 256 + 1024;   // == 1 x A + 256-row B
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     configured = true;
   }
-  const int n_out = glu ? N / 2 : N;
-  const int tile_n = glu ? BN / 2 : BN;
-  dim3 grid((M + GM_BM - 1) / GM_BM, (n_out + tile_n - 1) / tile_n);
-  if (BN == 64) launch_pdl(gemm_tcgen05_kernel<64>, grid, dim3(GM_THREADS), smem, stream, p);
-  else launch_pdl(gemm_tcgen05_kernel<128>, grid, dim3(GM_THREADS), smem, stream, p);
+  const int grid = std::min(n_sms, p.m_tiles * p.n_tiles * p.splits);
+  if (TM == 2) launch_pdl(gemm_tcgen05_kernel<2, 128>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
+  else if (BN == 256) launch_pdl(gemm_tcgen05_kernel<1, 256>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
+  else launch_pdl(gemm_tcgen05_kernel<1, 128>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
 }
 
 }  // namespace nxdi

@@ -250,6 +250,17 @@ class NeuronApplicationBase(nn.Module):
             from ..parallel.symm import SymmetricWorkspace
             hidden = getattr(self.config, "hidden_size", 8192)
             g.symm = SymmetricWorkspace.create(g, self.device, max_tokens=ops.GEMV_MAX_TOKENS, max_width=hidden)
+        if (g.size > 1 and self.device.type == "cuda" and nc.fused_collectives and g.symm is not None and getattr(g, "heap", None) is None
+                and os.environ.get("NXDI_B200_SYMM_HEAP", "1") != "0"):
+            # prefill-sized collectives: VMM symmetric heap + NVLS multicast (in-switch all-reduce / reduce-scatter / all-gather)
+            from ..parallel.symm_heap import SymmetricHeap
+            try:
+                g.heap = SymmetricHeap(g, self.device, int(os.environ.get("NXDI_B200_SYMM_HEAP_MB", "512")) << 20)
+                if not g.heap.has_multicast:
+                    logger.warning("symmetric heap: NVLS multicast not available on this system; prefill collectives stay on NCCL")
+            except Exception as e:      # no fd passing / no VMM support: keep NCCL
+                logger.warning("symmetric heap unavailable (%s); prefill collectives stay on NCCL", str(e).split("\n")[0])
+                g.heap = None
 
     def _build_runners(self):
         raise NotImplementedError

@@ -66,9 +66,23 @@ def rmsnorm(x, weight, eps: float, offset: float = 0.0, residual=None):
 _ACT_CODES = {None: 0, "silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
 
 
+def staging_for(group, x, w):
+    """Output tensor for a row-parallel GEMM inside the group's symmetric staging area (partial sums that an in-switch collective
+    consumes next), or None when the group has no heap / the shape does not qualify."""
+    heap = getattr(group, "heap", None)
+    if heap is None or not x.is_cuda or x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        return None
+    shape = tuple(x.shape[:-1]) + (w.shape[0],)
+    T = x.numel() // x.shape[-1]
+    if T <= GEMV_MAX_TOKENS or not heap.usable(torch.empty(0, dtype=torch.bfloat16, device=x.device), None, shape):
+        return None
+    return heap.staging(shape)
+
+
 def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offset: float = 0.0,
-           act: Optional[str] = None, scale=None, residual=None):
-    """y = act(rmsnorm(x) @ w^T + bias) (+ residual).  w: [N,K] bf16, or int8/fp8 with per-channel ``scale``."""
+           act: Optional[str] = None, scale=None, residual=None, out=None):
+    """y = act(rmsnorm(x) @ w^T + bias) (+ residual).  w: [N,K] bf16, or int8/fp8 with per-channel ``scale``.
+    ``out``: preallocated result (tcgen05 GEMM path only; used to land partial sums in the symmetric heap)."""
     if _use_cuda(x) and x.dtype in _FAST_DTYPES:
         K = x.shape[-1]
         T = x.numel() // K
@@ -95,11 +109,16 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
                 stats["gemm_tcgen05"] += 1
                 r2 = residual.reshape(T, -1) if (residual is not None and act is None) else None
-                y = _C().gemm(x2.contiguous(), w, bias, _ACT_CODES[act], r2)
-                y = y.view(*x.shape[:-1], y.shape[-1])
+                o2 = out.view(T, -1) if out is not None else None
+                y = _C().gemm(x2.contiguous(), w, bias, _ACT_CODES[act], r2, o2)
+                y = out if out is not None else y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
     y = ref.linear(x, w, bias, norm_weight, norm_eps, norm_offset, act, scale)
-    return y if residual is None else y + residual
+    y = y if residual is None else y + residual
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=None):
@@ -117,6 +136,11 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
         stats["gemv_allreduce"] += 1
         y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None)
         return y.view(*x.shape[:-1], y.shape[-1])
+    heap = getattr(group, "heap", None)
+    if heap is not None and scale is None:
+        # prefill: partial sums land in the symmetric staging area (bias on rank 0 only), one in-switch all-reduce adds the residual
+        y = linear(x, w, bias if group.rank == 0 else None, out=staging_for(group, x, w))
+        return mappings.all_reduce(y, group, reduce_dtype=reduce_dtype, residual=residual)
     y = linear(x, w, None, scale=scale)
     y = mappings.all_reduce(y, group, reduce_dtype=reduce_dtype)
     if bias is not None:

@@ -77,7 +77,8 @@ class ColumnParallelLinear(BaseParallelLinear):
         """``norm_weight``: fuse an RMSNorm of x into the GEMM prologue.  ``act='silu_mul'``:
         weight rows are [gate; up] and the output is silu(gate)*up (SwiGLU epilogue)."""
         if self.sequence_parallel_enabled:
-            x = mappings.all_gather(x, self.sequence_dimension, self.tensor_parallel_group)
+            # consumed by the GEMM right below: the NVLS path hands back a view of the symmetric staging area (no copy)
+            x = mappings.all_gather(x, self.sequence_dimension, self.tensor_parallel_group, transient=True)
         bias = None if self.skip_bias_add else self.bias
         y = ops.linear(x, self.weight, bias, norm_weight=norm_weight, norm_eps=norm_eps,
                        norm_offset=norm_offset, act=act, scale=getattr(self, "scale", None))
@@ -130,11 +131,11 @@ class RowParallelLinear(BaseParallelLinear):
             return ops.linear(x, self.weight, self.bias if g.size == 1 or g.rank == 0 else None, residual=residual,
                               scale=getattr(self, "scale", None))
         if self.sequence_parallel_enabled:
-            y = ops.linear(x, self.weight, None, scale=getattr(self, "scale", None))
-            y = mappings.reduce_scatter(y, self.sequence_dimension, g)
-            if self.bias is not None:
-                y = y + self.bias
-            return y if residual is None else y + residual
+            # the replicated bias joins the partial sums on rank 0 only; the GEMM writes its partials straight into the symmetric
+            # staging area when the group has one, and the reduce-scatter (+ residual) is one in-switch kernel
+            b0 = self.bias if g.rank == 0 else None
+            y = ops.linear(x, self.weight, b0, scale=getattr(self, "scale", None), out=ops.staging_for(g, x, self.weight))
+            return mappings.reduce_scatter(y, self.sequence_dimension, g, residual=residual)
         return ops.linear_allreduce(x, self.weight, self.bias, g, residual=residual,
                                     reduce_dtype=self.reduce_dtype, scale=getattr(self, "scale", None))
 

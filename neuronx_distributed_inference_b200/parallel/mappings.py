@@ -19,10 +19,22 @@ def _g(group: Optional[Group]) -> Group:
     return group if group is not None else get_tensor_model_parallel_group()
 
 
-def all_reduce(x: torch.Tensor, group: Optional[Group] = None, op=None, reduce_dtype=None) -> torch.Tensor:
+def _heap(g: Group):
+    """The group's symmetric heap (parallel/symm_heap.py) when the in-switch (NVLS) collectives are available."""
+    return getattr(g, "heap", None)
+
+
+def all_reduce(x: torch.Tensor, group: Optional[Group] = None, op=None, reduce_dtype=None, residual=None) -> torch.Tensor:
+    """sum over the group (+ ``residual``, fused on the NVLS path)."""
     g = _g(group)
     if g.size == 1:
-        return x
+        return x if residual is None else x + residual
+    heap = _heap(g)
+    if (heap is not None and op in (None, dist.ReduceOp.SUM) and reduce_dtype in (None, x.dtype, torch.float32)
+            and heap.usable(x)):
+        return heap.all_reduce(x, residual)      # two-shot in-switch reduction, fp32 accumulation
+    if residual is not None:
+        return all_reduce(x, g, op, reduce_dtype) + residual
     op = op or dist.ReduceOp.SUM
     if reduce_dtype is not None and reduce_dtype != x.dtype:
         y = x.to(reduce_dtype)
@@ -33,11 +45,20 @@ def all_reduce(x: torch.Tensor, group: Optional[Group] = None, op=None, reduce_d
     return x
 
 
-def all_gather(x: torch.Tensor, dim: int, group: Optional[Group] = None) -> torch.Tensor:
+def all_gather(x: torch.Tensor, dim: int, group: Optional[Group] = None, transient: bool = False) -> torch.Tensor:
+    """``transient``: the caller consumes the result before the next collective of the group (the NVLS path then returns a view
+    of the symmetric staging area instead of a private copy)."""
     g = _g(group)
     if g.size == 1:
         return x
     dim = dim % x.dim()
+    heap = _heap(g)
+    if heap is not None and x.dim() > 0:
+        full = list(x.shape)
+        full[dim] *= g.size
+        if heap.usable(x, dim, full):
+            y = heap.all_gather(x, dim)          # every rank multicasts its slice (multimem.st)
+            return y if transient else y.clone()
     x = x.contiguous()
     if x.dim() == 0:
         x = x.reshape(1)
@@ -49,12 +70,17 @@ def all_gather(x: torch.Tensor, dim: int, group: Optional[Group] = None) -> torc
     return out.movedim(0, dim).reshape(x.shape[:dim] + (g.size * x.shape[dim],) + x.shape[dim + 1:])
 
 
-def reduce_scatter(x: torch.Tensor, dim: int, group: Optional[Group] = None, op=None) -> torch.Tensor:
+def reduce_scatter(x: torch.Tensor, dim: int, group: Optional[Group] = None, op=None, residual=None) -> torch.Tensor:
     g = _g(group)
     if g.size == 1:
-        return x
+        return x if residual is None else x + residual
     dim = dim % x.dim()
     assert x.shape[dim] % g.size == 0
+    heap = _heap(g)
+    if heap is not None and op in (None, dist.ReduceOp.SUM) and heap.usable(x, dim):
+        return heap.reduce_scatter(x, dim, residual)     # rank r pulls the switch-reduced slice r (+ residual)
+    if residual is not None:
+        return reduce_scatter(x, dim, g, op) + residual
     op = op or dist.ReduceOp.SUM
     xs = x.movedim(dim, 0).contiguous()
     out = torch.empty((xs.shape[0] // g.size,) + tuple(xs.shape[1:]), dtype=x.dtype, device=x.device)

@@ -31,6 +31,7 @@ class Group:
     pg: Optional[object] = None
     rank: int = 0  # my index inside ``ranks``
     symm: Optional[object] = None  # lazily attached SymmetricWorkspace (parallel/symm.py)
+    heap: Optional[object] = None  # lazily attached SymmetricHeap + NVLS collectives (parallel/symm_heap.py)
 
     @property
     def size(self) -> int:
