@@ -119,6 +119,9 @@ struct AttnPrefillParams {
   int causal;
 };
 void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream);
+// tcgen05 / TMEM / TMA flash attention (attention_tc.cu), head_dim 128
+void attention_prefill_tc_launch(const void* q, const void* k, const void* v, void* out, const float* sinks, int B, int T, int Hq, int Hkv,
+                                 float scale, int causal, int window, float softcap, cudaStream_t stream);
 
 // symmetric heap (symm_heap.cpp) and NVLS collectives (nvls.cu)
 long long symm_heap_create(long long bytes, int device, int world, int rank);

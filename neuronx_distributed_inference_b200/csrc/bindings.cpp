@@ -452,6 +452,18 @@ at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at:
 }  // namespace nxdi
 
 namespace nxdi {
+at::Tensor attention_prefill_tc(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, double scale, int64_t window,
+                                const c10::optional<at::Tensor>& sinks, bool causal, double softcap) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous() && is_bf16(q) && is_bf16(k) && is_bf16(v));
+  const int B = q.size(0), T = q.size(1), Hq = q.size(2), D = q.size(3), Hkv = k.size(2);
+  TORCH_CHECK(D == 128 && k.size(1) == T && k.size(3) == D && v.sizes() == k.sizes() && Hq % Hkv == 0, "attention_prefill_tc: head_dim 128, equal q/k lengths");
+  c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty_like(q);
+  attention_prefill_tc_launch(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), sinks.has_value() ? sinks->data_ptr<float>() : nullptr,
+                              B, T, Hq, Hkv, (float)scale, causal ? 1 : 0, (int)window, (float)softcap, cur_stream());
+  return out;
+}
+
 // ---- symmetric heap + NVLS collectives -------------------------------------------------------------------------------------
 // mode 0 all-reduce (in place in the symmetric buffer; `out` = private copy (+ residual) when given), 1 reduce-scatter, 2 all-gather
 void nvls_collective(int64_t mode, const std::vector<int64_t>& sig_ptrs, const at::Tensor& step, int64_t rank, int64_t call,
@@ -520,6 +532,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_heap_mc_bind_map", [](int64_t h) { return (int64_t)nxdi::symm_heap_mc_bind_map(h); });
   m.def("symm_heap_destroy", [](int64_t h) { nxdi::symm_heap_destroy(h); });
   m.def("nvls_collective", &nxdi::nvls_collective);
+  m.def("attention_prefill_tc", &nxdi::attention_prefill_tc);
   m.def("dstep_new", &nxdi::dstep_new_b);
   m.def("dstep_set_symm", &nxdi::dstep_set_symm_b);
   m.def("dstep_add_gemv", &nxdi::dstep_add_gemv_b);

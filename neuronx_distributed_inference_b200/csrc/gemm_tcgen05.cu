@@ -423,8 +423,18 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
     const char* e = getenv("NXDI_B200_GEMM_TM");
     force_tm = e ? atoi(e) : 0;
   }
-  const int TM = force_tm ? force_tm : ((M > GM_BM && M <= 2 * GM_BM) ? 2 : 1);
-  const int BN = (TM == 1 && M > 2 * GM_BM) ? 256 : 128;
+  // tile shape: see the header.  Skinny problems (M <= 256) that would leave SMs without a tile trade weight reuse for occupancy:
+  // first 128-row tiles (TM 1), then 64-column tiles — aggregate TMA throughput scales with the number of busy SMs
+  // (M = 256, N = 6144: 48 tiles of 256x128 took 48 us, 192 tiles of 128x64 ~30 us; cuBLAS 23.5 us)
+  int TM = (M > GM_BM && M <= 2 * GM_BM) ? 2 : 1;
+  int BN = (TM == 1 && M > 2 * GM_BM) ? 256 : 128;
+  if (M <= 2 * GM_BM) {
+    const int n_out_ = glu ? N / 2 : N;
+    auto n_tiles_of = [&](int tm, int bn) { return ((M + tm * GM_BM - 1) / (tm * GM_BM)) * ((n_out_ + (glu ? bn / 2 : bn) - 1) / (glu ? bn / 2 : bn)); };
+    if (TM == 2 && n_tiles_of(2, 128) < n_sms) TM = 1;
+    if (n_tiles_of(TM, 128) < n_sms) BN = 64;
+  }
+  if (force_tm) TM = force_tm;
   make_2d(&p.tma_a, a, M, K, lda, TM * GM_BM);
   make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN);
   const int n_out = glu ? N / 2 : N;
@@ -462,11 +472,13 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
     cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     configured = true;
   }
   const int grid = std::min(n_sms, p.m_tiles * p.n_tiles * p.splits);
   if (TM == 2) launch_pdl(gemm_tcgen05_kernel<2, 128>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
   else if (BN == 256) launch_pdl(gemm_tcgen05_kernel<1, 256>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
+  else if (BN == 64) launch_pdl(gemm_tcgen05_kernel<1, 64>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
   else launch_pdl(gemm_tcgen05_kernel<1, 128>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
 }
 

@@ -220,9 +220,18 @@ def rope_attention_decode(qkv, cos, sin, k_cache, v_cache, seq_ids, write_positi
     return attention_decode(q, k_cache, v_cache, seq_ids, positions, scale, window, None, sinks, seq_hint=seq_hint)
 
 
+_ATTN_TC = os.environ.get("NXDI_B200_ATTN_TC", "1") != "0"   # 0: the mma.sync flash kernel for head_dim 128 too (A/B baseline)
+
+
 def attention_prefill(q, k, v, scale, causal: bool = True, window=None, chunk=None, key_valid=None,
                       q_pos=None, sinks=None, softcap=None):
     D = q.shape[-1]
+    if (_use_cuda(q) and q.dtype in _FAST_DTYPES and D == 128 and _ATTN_TC and chunk is None and (causal or not window)
+            and key_valid is None and q_pos is None and q.shape[1] == k.shape[1] and k.dtype == q.dtype):
+        # Blackwell path: tcgen05 QK^T / PV with TMEM accumulators, TMA tiles (csrc/attention_tc.cu); soft-cap is an argument
+        stats["attn_prefill_tc"] += 1
+        return _C().attention_prefill_tc(q.contiguous(), k.contiguous(), v.contiguous(), float(scale), int(window or 0), sinks,
+                                         bool(causal), float(softcap or 0.0))
     if (_use_cuda(q) and q.dtype in _FAST_DTYPES and D in (64, 128) and chunk is None and (causal or not window)
             and key_valid is None and q_pos is None and softcap is None and q.shape[1] == k.shape[1]):
         stats["attn_prefill"] += 1

@@ -302,3 +302,23 @@ def test_bidirectional_flash_attention_matches_reference(B, T, Hq, Hkv, D):
     assert ops.stats["attn_prefill"] == before + 1
     exp = ref.attention_prefill(q.float(), k.float(), v.float(), D ** -0.5, causal=False)
     assert (got.float() - exp).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,T,Hq,Hkv,causal,window,softcap,sinks", [
+    (1, 128, 2, 1, True, 0, 0.0, False), (2, 300, 4, 2, True, 0, 0.0, False), (1, 1024, 8, 2, True, 0, 0.0, False),
+    (1, 640, 4, 4, True, 200, 0.0, True), (2, 257, 2, 1, False, 0, 0.0, False), (1, 512, 4, 1, True, 0, 30.0, False),
+    (1, 2048, 4, 1, True, 0, 0.0, False)])
+def test_attention_prefill_tcgen05(B, T, Hq, Hkv, causal, window, softcap, sinks):
+    """csrc/attention_tc.cu (tcgen05 QK^T / PV, TMEM accumulators, TMA tiles, MN-major V) vs the fp32 PyTorch definition."""
+    D = 128
+    torch.manual_seed(1)
+    q = torch.randn(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    k = torch.randn(B, T, Hkv, D, device=DEV, dtype=torch.bfloat16)
+    v = torch.randn(B, T, Hkv, D, device=DEV, dtype=torch.bfloat16)
+    sk = torch.randn(Hq, device=DEV) if sinks else None
+    scale = D ** -0.5
+    n0 = ops.stats["attn_prefill_tc"]
+    o = ops.attention_prefill(q, k, v, scale, causal, window or None, sinks=sk, softcap=softcap or None)
+    assert ops.stats["attn_prefill_tc"] == n0 + 1
+    orf = ref.attention_prefill(q.float(), k.float(), v.float(), scale, causal, window or None, sinks=sk, softcap=softcap or None)
+    assert o.shape == orf.shape and _rel(o, orf) < 1.2e-2, _rel(o, orf)
