@@ -50,8 +50,17 @@ long long prof_count();
 unsigned long long* prof_slot_ptr(long long slot);
 void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* tickets, cudaStream_t stream);
 // tcgen05 / TMEM / TMA GEMM (gemm_tcgen05.cu): C[M,N_out] = epi(A[M,K] · B[N,K]^T)
+// fused GEMM -> in-switch reduce-scatter (see GemmParams in gemm_tcgen05.cu)
+struct GemmRsArgs {
+  long long flag_ptrs[SYMM_MAX_RANKS];   // peer-mapped [max_tiles][world] u32
+  const void* mc;                        // multicast address of the staging buffer `c`
+  void* out;                             // private output [M / world, N]
+  const void* residual;                  // [M / world, N] or null
+  const void* step;
+  int call, rank, world, rows_per_seg, max_tiles;
+};
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
-                         int N, int K, int act, cudaStream_t stream);
+                         int N, int K, int act, cudaStream_t stream, const GemmRsArgs* rs = nullptr);
 void rmsnorm_launch(const void* x, const void* res_in, const void* w, void* y, void* res_out, int rows, int H, float eps,
                     float offset, cudaStream_t stream);
 

@@ -452,6 +452,30 @@ at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at:
 }  // namespace nxdi
 
 namespace nxdi {
+// Row-parallel GEMM with the reduce-scatter fused into the kernel: x [M, K] (M = segs * rows_per_seg, rows of a segment split
+// evenly over the ranks) -> private output [M / world, N] = sum over ranks of x_r w_r^T (+ bias on rank 0) (+ residual).
+// `staging` is this rank's symmetric buffer for the partial sums, `mc_ptr` its multicast address.
+at::Tensor gemm_reduce_scatter(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias, at::Tensor& staging,
+                               int64_t mc_ptr, const std::vector<int64_t>& flag_ptrs, int64_t max_tiles, const at::Tensor& step,
+                               int64_t call, int64_t rank, int64_t rows_per_seg, const c10::optional<at::Tensor>& residual) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && is_bf16(x) && is_bf16(w) && w.is_contiguous());
+  const int M = x.size(0), K = x.size(1), N = w.size(0), world = flag_ptrs.size();
+  TORCH_CHECK(K % 64 == 0 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && world >= 2 && world <= SYMM_MAX_RANKS);
+  TORCH_CHECK(is_bf16(staging) && staging.is_contiguous() && staging.numel() == (int64_t)M * N);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = at::empty({M / world, N}, x.options());
+  if (residual.has_value()) TORCH_CHECK(is_bf16(*residual) && residual->is_contiguous() && residual->numel() == out.numel());
+  GemmRsArgs rs{};
+  for (int i = 0; i < world; ++i) rs.flag_ptrs[i] = flag_ptrs[i];
+  rs.mc = reinterpret_cast<const void*>(mc_ptr);
+  rs.out = out.data_ptr();
+  rs.residual = residual.has_value() ? residual->data_ptr() : nullptr;
+  rs.step = step.data_ptr();
+  rs.call = (int)call; rs.rank = (int)rank; rs.world = world; rs.rows_per_seg = (int)rows_per_seg; rs.max_tiles = (int)max_tiles;
+  gemm_tcgen05_launch(x.data_ptr(), (int)x.stride(0), w.data_ptr(), optr(bias), nullptr, staging.data_ptr(), N, M, N, K, 0, cur_stream(), &rs);
+  return out;
+}
+
 at::Tensor attention_prefill_tc(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, double scale, int64_t window,
                                 const c10::optional<at::Tensor>& sinks, bool causal, double softcap) {
   TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous() && is_bf16(q) && is_bf16(k) && is_bf16(v));
@@ -533,6 +557,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_heap_destroy", [](int64_t h) { nxdi::symm_heap_destroy(h); });
   m.def("nvls_collective", &nxdi::nvls_collective);
   m.def("attention_prefill_tc", &nxdi::attention_prefill_tc);
+  m.def("gemm_reduce_scatter", &nxdi::gemm_reduce_scatter);
   m.def("dstep_new", &nxdi::dstep_new_b);
   m.def("dstep_set_symm", &nxdi::dstep_set_symm_b);
   m.def("dstep_add_gemv", &nxdi::dstep_add_gemv_b);

@@ -39,6 +39,19 @@ struct GemmParams {
   int splits;                     // split-K factor: work item = (tile, k slice); partial accumulators meet in `ws`
   float* ws;                      // [tiles][splits][TM*128][128] fp32 partials (L2 resident)
   unsigned* tickets;              // [tiles], self-resetting
+  // ---- fused reduce-scatter epilogue (row-parallel layers of the sequence-parallel prefill; rs_world == 0: plain GEMM) ----
+  // `c` is then this rank's symmetric staging buffer of PARTIAL sums.  After a tile's stores the CTA publishes the collective's
+  // tag into slot [tile][my rank] of the rank that OWNS the tile's rows (st.release.sys over the peer mapping).  When a CTA has
+  // finished its own tiles its epilogue warps turn to the tiles this rank owns: they wait until all `rs_world` slots of a tile
+  // carry the tag, pull the tile REDUCED IN THE SWITCH (multimem.ld_reduce over the multicast mapping of the staging buffer),
+  // add the residual and write the private output rows.  The transfer of a tile thus overlaps the GEMM of the following ones.
+  uint32_t* rs_flags[SYMM_MAX_RANKS];   // [tiles][world] u32 on every rank (peer mapped)
+  const uint8_t* rs_mc;                 // multicast address of the staging buffer
+  __nv_bfloat16* rs_out;                // [owned rows][N] private output
+  const __nv_bfloat16* rs_residual;     // [owned rows][N] or null
+  const uint32_t* rs_step;              // device step counter (tag = (step << 8 | call) + 1)
+  int rs_call, rs_rank, rs_world;
+  int rs_tiles_per_seg;                 // m-tiles per segment (batch row); rank r owns tiles [r, r+1) * tiles_per_seg / world of each
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -301,6 +314,21 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mb_arrive(&tmem_empty[buf]);
+      if (p.rs_world > 0) {
+        // publish: this rank's partial tile is in its staging buffer (barrier + system-scope release by one thread)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          const int mt = t % p.m_tiles;
+          const int per = p.rs_tiles_per_seg / p.rs_world;
+          const int owner = (mt % p.rs_tiles_per_seg) / per;
+          uint32_t* fl = p.rs_flags[0];
+#pragma unroll
+          for (int d = 1; d < SYMM_MAX_RANKS; ++d)
+            if (d == owner) fl = p.rs_flags[d];
+          __threadfence_system();
+          st_release_sys(fl + (size_t)t * p.rs_world + p.rs_rank, ll_tag(p.rs_step, p.rs_call));
+        }
+      }
       if (S > 1) {
         // the LAST k slice of a tile to arrive sums the partials (slice order: deterministic) and runs the real epilogue
         __threadfence();
@@ -344,6 +372,67 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
           if (etid == 0) p.tickets[t] = 0;   // re-armed for the next launch / graph replay
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last reusable
+      }
+    }
+    if (p.rs_world > 0) {
+      // ---- reduce phase: the tiles whose rows this rank owns, dealt round-robin to the CTAs ----
+      const uint32_t tag = ll_tag(p.rs_step, p.rs_call);
+      const int per = p.rs_tiles_per_seg / p.rs_world;           // owned m-tiles per segment
+      const int segs = p.m_tiles / p.rs_tiles_per_seg;
+      const int owned_m = per * segs;
+      const uint32_t* my_flags = p.rs_flags[0];
+#pragma unroll
+      for (int d = 1; d < SYMM_MAX_RANKS; ++d)
+        if (d == p.rs_rank) my_flags = p.rs_flags[d];
+      for (int u = blockIdx.x; u < owned_m * p.n_tiles; u += gridDim.x) {
+        const int lm = u % owned_m, nt = u / owned_m;              // local m-tile (row block of the private output), n-tile
+        const int mt = (lm / per) * p.rs_tiles_per_seg + p.rs_rank * per + lm % per;   // global m-tile
+        const int t = nt * p.m_tiles + mt;
+        if (etid < p.rs_world) {
+          const long long t0 = clock64();
+          // tags grow monotonically, and a peer that is already one collective ahead has certainly finished this one
+          while ((int)(ld_acquire_sys(my_flags + (size_t)t * p.rs_world + etid) - tag) < 0) {
+            if (clock64() - t0 > 8000000000LL) {
+              printf("gemm reduce-scatter: rank %d timed out waiting for rank %d tile %d (tag %u)\n", p.rs_rank, etid, t, tag);
+              __trap();
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // 128 rows x BN columns of bf16, 16 bytes per access: thread -> (row, 16-byte column chunk)
+        constexpr int CPR = BN / 8;                               // 16-byte chunks per row
+        const int n0 = nt * BN;
+        // 8 in-switch reductions in flight per thread (one is a ~3 us round trip through the NVSwitch)
+        for (int i0 = etid; i0 < GM_BM * CPR; i0 += 128 * 8) {
+          uint32_t q[8][4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * 128;
+            const int r = i / CPR, col = n0 + (i % CPR) * 8;
+            if (i < GM_BM * CPR && col < p.N) {
+              const size_t src = ((size_t)(mt * GM_BM + r) * p.ldc + col) * 2;      // byte offset inside the staging buffer
+              asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(q[j][0]), "=r"(q[j][1]), "=r"(q[j][2]), "=r"(q[j][3]) : "l"(p.rs_mc + src) : "memory");
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = i0 + j * 128;
+            const int r = i / CPR, col = n0 + (i % CPR) * 8;
+            if (i < GM_BM * CPR && col < p.N) {
+              const size_t dsto = (size_t)(lm * GM_BM + r) * p.N + col;
+              if (p.rs_residual != nullptr) {
+                const uint4 rr = ldg_act(p.rs_residual + dsto);
+                q[j][0] = pack_bf16(bf16lo(q[j][0]) + bf16lo(rr.x), bf16hi(q[j][0]) + bf16hi(rr.x));
+                q[j][1] = pack_bf16(bf16lo(q[j][1]) + bf16lo(rr.y), bf16hi(q[j][1]) + bf16hi(rr.y));
+                q[j][2] = pack_bf16(bf16lo(q[j][2]) + bf16lo(rr.z), bf16hi(q[j][2]) + bf16hi(rr.z));
+                q[j][3] = pack_bf16(bf16lo(q[j][3]) + bf16lo(rr.w), bf16hi(q[j][3]) + bf16hi(rr.w));
+              }
+              *reinterpret_cast<uint4*>(p.rs_out + dsto) = make_uint4(q[j][0], q[j][1], q[j][2], q[j][3]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }
@@ -404,8 +493,8 @@ static unsigned* gemm_tickets() {
 }
 
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
-                         int N, int K, int act, cudaStream_t stream) {
-  GemmParams p;
+                         int N, int K, int act, cudaStream_t stream, const GemmRsArgs* rs) {
+  GemmParams p{};
   const bool glu = act != 0;
   static int n_sms = 0;
   if (n_sms == 0) {
@@ -435,6 +524,11 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
     if (n_tiles_of(TM, 128) < n_sms) BN = 64;
   }
   if (force_tm) TM = force_tm;
+  if (rs != nullptr) {   // fused reduce-scatter: 128-row tiles so that a tile has exactly one owner; no split-K
+    if (glu) throw std::runtime_error("gemm: the fused reduce-scatter needs a plain epilogue");
+    TM = 1;
+    BN = M > 2 * GM_BM ? 256 : 128;
+  }
   make_2d(&p.tma_a, a, M, K, lda, TM * GM_BM);
   make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN);
   const int n_out = glu ? N / 2 : N;
@@ -462,9 +556,23 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
     }
   }
   p.splits = force_s > 0 ? std::min({force_s, 4, std::max(1, nkb / 2)}) : best_s;
+  if (rs != nullptr) p.splits = 1;
   if ((size_t)tiles * p.splits * tile_ws_bytes > gemm_ws_bytes() || tiles > gemm_max_tickets()) p.splits = 1;
   p.ws = p.splits > 1 ? gemm_ws() : nullptr;
   p.tickets = gemm_tickets();
+  if (rs != nullptr) {
+    const int rows_per_seg = rs->rows_per_seg;
+    if (rows_per_seg % (GM_BM * rs->world) != 0 || M % rows_per_seg != 0 || N % 8 != 0 || ldc != N)
+      throw std::runtime_error("gemm: fused reduce-scatter needs rows_per_rank % 128 == 0 and a dense [M, N] staging buffer");
+    for (int i = 0; i < rs->world; ++i) p.rs_flags[i] = reinterpret_cast<uint32_t*>(rs->flag_ptrs[i]);
+    p.rs_mc = reinterpret_cast<const uint8_t*>(rs->mc);
+    p.rs_out = reinterpret_cast<__nv_bfloat16*>(rs->out);
+    p.rs_residual = reinterpret_cast<const __nv_bfloat16*>(rs->residual);
+    p.rs_step = reinterpret_cast<const uint32_t*>(rs->step);
+    p.rs_call = rs->call; p.rs_rank = rs->rank; p.rs_world = rs->world;
+    p.rs_tiles_per_seg = rows_per_seg / GM_BM;
+    if ((long long)p.m_tiles * p.n_tiles > rs->max_tiles) throw std::runtime_error("gemm: too many tiles for the reduce-scatter flag array");
+  }
   const size_t smem = (size_t)GM_STAGES * (TM * GM_A_BYTES + BN * GM_BK * 2) + 256 + 1024;
   static bool configured = false;
   if (!configured) {

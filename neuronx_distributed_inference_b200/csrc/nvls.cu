@@ -103,23 +103,33 @@ __global__ void __launch_bounds__(NVLS_THREADS) nvls_kernel(const NvlsArgs a) {
     nvls_barrier(a, tag, 1);   // everyone's slice has landed everywhere
     return;
   }
-  for (long long lv = t0; lv < my_vec; lv += tstride) {
-    const long long v = gvec(lv);
-    uint32_t r[4];
-    mm_ld_reduce_bf16x8(a.mc + v * 16, r);
-    if (MODE == 0) {
-      mm_st_16B(a.mc + v * 16, r);             // broadcast the reduced slice into every copy
-    } else {
-      // reduce-scatter: my slice -> private output rows [segs * my_rows][row_elems] (+ residual of the same shape)
-      const long long o = lv * 8;
-      if (a.residual != nullptr) {
-        const uint4 q = ldg_act(a.residual + o);
-        r[0] = pack_bf16(bf16lo(r[0]) + bf16lo(q.x), bf16hi(r[0]) + bf16hi(q.x));
-        r[1] = pack_bf16(bf16lo(r[1]) + bf16lo(q.y), bf16hi(r[1]) + bf16hi(q.y));
-        r[2] = pack_bf16(bf16lo(r[2]) + bf16lo(q.z), bf16hi(r[2]) + bf16hi(q.z));
-        r[3] = pack_bf16(bf16lo(r[3]) + bf16lo(q.w), bf16hi(r[3]) + bf16hi(q.w));
+  // 4 in-switch reductions in flight per thread (each is a round trip through the NVSwitch)
+  for (long long lv0 = t0; lv0 < my_vec; lv0 += tstride * 4) {
+    uint32_t r[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long lv = lv0 + j * tstride;
+      if (lv < my_vec) mm_ld_reduce_bf16x8(a.mc + gvec(lv) * 16, r[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long lv = lv0 + j * tstride;
+      if (lv >= my_vec) continue;
+      const long long v = gvec(lv);
+      if (MODE == 0) {
+        mm_st_16B(a.mc + v * 16, r[j]);             // broadcast the reduced slice into every copy
+      } else {
+        // reduce-scatter: my slice -> private output rows [segs * my_rows][row_elems] (+ residual of the same shape)
+        const long long o = lv * 8;
+        if (a.residual != nullptr) {
+          const uint4 q = ldg_act(a.residual + o);
+          r[j][0] = pack_bf16(bf16lo(r[j][0]) + bf16lo(q.x), bf16hi(r[j][0]) + bf16hi(q.x));
+          r[j][1] = pack_bf16(bf16lo(r[j][1]) + bf16lo(q.y), bf16hi(r[j][1]) + bf16hi(q.y));
+          r[j][2] = pack_bf16(bf16lo(r[j][2]) + bf16lo(q.z), bf16hi(r[j][2]) + bf16hi(q.z));
+          r[j][3] = pack_bf16(bf16lo(r[j][3]) + bf16lo(q.w), bf16hi(r[j][3]) + bf16hi(q.w));
+        }
+        *reinterpret_cast<uint4*>(a.out + o) = make_uint4(r[j][0], r[j][1], r[j][2], r[j][3]);
       }
-      *reinterpret_cast<uint4*>(a.out + o) = make_uint4(r[0], r[1], r[2], r[3]);
     }
   }
   nvls_barrier(a, tag, 1);     // all slices reduced (and broadcast): the buffer may be read / overwritten

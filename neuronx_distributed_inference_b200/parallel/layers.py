@@ -134,6 +134,15 @@ class RowParallelLinear(BaseParallelLinear):
             # the replicated bias joins the partial sums on rank 0 only; the GEMM writes its partials straight into the symmetric
             # staging area when the group has one, and the reduce-scatter (+ residual) is one in-switch kernel
             b0 = self.bias if g.rank == 0 else None
+            heap = getattr(g, "heap", None)
+            sd = self.sequence_dimension % x.dim()
+            if (heap is not None and getattr(self, "scale", None) is None and sd == x.dim() - 2
+                    and heap.gemm_rs_usable(x, self.weight, x.shape[sd])):
+                # ONE kernel: tcgen05 GEMM -> per-tile hand-off over NVLink -> in-switch reduce (multimem.ld_reduce) of the rows this
+                # rank owns -> + residual (csrc/gemm_tcgen05.cu, fused reduce-scatter epilogue)
+                ops.stats["gemm_reduce_scatter"] += 1
+                y = heap.gemm_reduce_scatter(x.reshape(-1, x.shape[-1]), self.weight, b0, x.shape[sd], residual)
+                return y.view(*x.shape[:sd], x.shape[sd] // g.size, self.weight.shape[0])
             y = ops.linear(x, self.weight, b0, scale=getattr(self, "scale", None), out=ops.staging_for(g, x, self.weight))
             return mappings.reduce_scatter(y, self.sequence_dimension, g, residual=residual)
         return ops.linear_allreduce(x, self.weight, self.bias, g, residual=residual,

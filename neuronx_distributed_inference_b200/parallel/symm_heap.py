@@ -216,6 +216,45 @@ class SymmetricHeap:
         self._launch(2, off, segs, rows, row, None, None)
         return full
 
+    # ---- fused GEMM -> reduce-scatter (csrc/gemm_tcgen05.cu, rs_* parameters) -----------------------------------------------
+    _RS_MAX_TILES = 16384
+
+    def _rs_resources(self, nbytes: int):
+        """Flag array [max_tiles][world] + TWO staging buffers (a rank may be one collective ahead of its slowest peer, whose
+        in-switch reads of the previous staging buffer may still be in flight)."""
+        if getattr(self, "_rs_flags_off", None) is None:
+            self._rs_flags_off = self.alloc(self._RS_MAX_TILES * self.world * 4)
+            self._rs_stage_off, self._rs_stage_bytes, self._rs_n = [None, None], 0, 0
+        if nbytes > self._rs_stage_bytes:
+            size = max(nbytes, 48 << 20)
+            if self._top + 2 * size + 4096 > self.size:
+                return False
+            self._rs_stage_off = [self.alloc(size), self.alloc(size)]
+            self._rs_stage_bytes = size
+        return True
+
+    def gemm_rs_usable(self, x: torch.Tensor, w: torch.Tensor, rows_per_seg: int) -> bool:
+        M = x.numel() // x.shape[-1]
+        return (self.has_multicast and self.group.symm is not None and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+                and w.dim() == 2 and w.is_contiguous() and w.shape[1] % 64 == 0 and w.shape[0] % 8 == 0
+                and rows_per_seg % (128 * self.world) == 0 and M % rows_per_seg == 0 and M > 8
+                and ((M + 127) // 128) * ((w.shape[0] + 127) // 128) <= self._RS_MAX_TILES
+                and os.environ.get("NXDI_B200_FUSED_RS", "1") != "0" and self._rs_resources(M * w.shape[0] * 2))
+
+    def gemm_reduce_scatter(self, x2d: torch.Tensor, w: torch.Tensor, bias, rows_per_seg: int, residual=None) -> torch.Tensor:
+        """x2d [M, K_local] -> [M / world, N]: partial GEMM, reduce-scatter over the sequence rows and residual add in ONE kernel."""
+        M, N = x2d.shape[0], w.shape[0]
+        off = self._rs_stage_off[self._rs_n & 1]
+        self._rs_n += 1
+        staging = self.tensor(off, (M, N))
+        symm = self.group.symm
+        flags = [va + self._rs_flags_off for va in self.peer_va]
+        out = self.C.gemm_reduce_scatter(x2d, w, bias, staging, self.mc_va + off, flags, self._RS_MAX_TILES, symm.step_t, symm.call,
+                                         self.rank, rows_per_seg, residual.reshape(-1, N).contiguous() if residual is not None else None)
+        symm.call += 1
+        symm.calls += 1
+        return out
+
     def close(self):
         if getattr(self, "h", None) is not None:
             self.C.symm_heap_destroy(self.h)
