@@ -58,6 +58,10 @@ struct GemmRsArgs {
   const void* residual;                  // [M / world, N] or null
   const void* step;
   int call, rank, world, rows_per_seg, max_tiles;
+  // all-reduce flavour: multicast address of the symmetric output [M, N] (null: reduce-scatter), completion flags, CTA counter
+  const void* bcast_mc;
+  long long done_ptrs[SYMM_MAX_RANKS];
+  void* cta_counter;
 };
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
                          int N, int K, int act, cudaStream_t stream, const GemmRsArgs* rs = nullptr);

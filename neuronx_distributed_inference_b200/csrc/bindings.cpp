@@ -457,18 +457,25 @@ namespace nxdi {
 // `staging` is this rank's symmetric buffer for the partial sums, `mc_ptr` its multicast address.
 at::Tensor gemm_reduce_scatter(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias, at::Tensor& staging,
                                int64_t mc_ptr, const std::vector<int64_t>& flag_ptrs, int64_t max_tiles, const at::Tensor& step,
-                               int64_t call, int64_t rank, int64_t rows_per_seg, const c10::optional<at::Tensor>& residual) {
+                               int64_t call, int64_t rank, int64_t rows_per_seg, const c10::optional<at::Tensor>& residual,
+                               int64_t bcast_mc_ptr, const std::vector<int64_t>& done_ptrs, const c10::optional<at::Tensor>& cta_counter) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && is_bf16(x) && is_bf16(w) && w.is_contiguous());
   const int M = x.size(0), K = x.size(1), N = w.size(0), world = flag_ptrs.size();
   TORCH_CHECK(K % 64 == 0 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && world >= 2 && world <= SYMM_MAX_RANKS);
   TORCH_CHECK(is_bf16(staging) && staging.is_contiguous() && staging.numel() == (int64_t)M * N);
   c10::cuda::CUDAGuard guard(x.device());
-  auto out = at::empty({M / world, N}, x.options());
-  if (residual.has_value()) TORCH_CHECK(is_bf16(*residual) && residual->is_contiguous() && residual->numel() == out.numel());
+  const bool bcast = bcast_mc_ptr != 0;   // all-reduce flavour: result lands in the symmetric output buffer of every rank
+  auto out = bcast ? at::empty({0}, x.options()) : at::empty({M / world, N}, x.options());
+  if (residual.has_value())
+    TORCH_CHECK(is_bf16(*residual) && residual->is_contiguous() && residual->numel() == (bcast ? (int64_t)M * N : out.numel()));
+  if (bcast) TORCH_CHECK((int)done_ptrs.size() == world && cta_counter.has_value() && cta_counter->is_cuda() && cta_counter->scalar_type() == at::kInt);
   GemmRsArgs rs{};
   for (int i = 0; i < world; ++i) rs.flag_ptrs[i] = flag_ptrs[i];
   rs.mc = reinterpret_cast<const void*>(mc_ptr);
-  rs.out = out.data_ptr();
+  rs.out = bcast ? nullptr : out.data_ptr();
+  rs.bcast_mc = reinterpret_cast<const void*>(bcast_mc_ptr);
+  for (int i = 0; i < world && bcast; ++i) rs.done_ptrs[i] = done_ptrs[i];
+  rs.cta_counter = bcast ? cta_counter->data_ptr() : nullptr;
   rs.residual = residual.has_value() ? residual->data_ptr() : nullptr;
   rs.step = step.data_ptr();
   rs.call = (int)call; rs.rank = (int)rank; rs.world = world; rs.rows_per_seg = (int)rows_per_seg; rs.max_tiles = (int)max_tiles;

@@ -52,6 +52,12 @@ struct GemmParams {
   const uint32_t* rs_step;              // device step counter (tag = (step << 8 | call) + 1)
   int rs_call, rs_rank, rs_world;
   int rs_tiles_per_seg;                 // m-tiles per segment (batch row); rank r owns tiles [r, r+1) * tiles_per_seg / world of each
+  // ---- all-reduce flavour of the same epilogue: the reduced tile (+ residual, indexed by GLOBAL row) is multicast into every
+  // rank's copy of a symmetric output buffer (multimem.st); the kernel ends with a cross-GPU completion flag exchange, so when it
+  // has finished on a rank the whole [M, N] result is present there.  rs_bcast_mc == null: reduce-scatter into rs_out.
+  uint8_t* rs_bcast_mc;                 // multicast address of the symmetric OUTPUT buffer [M, N]
+  uint32_t* rs_done[SYMM_MAX_RANKS];    // [world] u32 on every rank (peer mapped): "rank s has broadcast all its tiles"
+  unsigned* rs_cta_counter;             // local: CTAs of this launch that finished their reduce tiles (self-resetting)
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -420,7 +426,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
             const int i = i0 + j * 128;
             const int r = i / CPR, col = n0 + (i % CPR) * 8;
             if (i < GM_BM * CPR && col < p.N) {
-              const size_t dsto = (size_t)(lm * GM_BM + r) * p.N + col;
+              const bool bcast = p.rs_bcast_mc != nullptr;
+              // reduce-scatter: rows of the private output; all-reduce: rows of the full tensor
+              const size_t dsto = (size_t)((bcast ? mt : lm) * GM_BM + r) * p.N + col;
               if (p.rs_residual != nullptr) {
                 const uint4 rr = ldg_act(p.rs_residual + dsto);
                 q[j][0] = pack_bf16(bf16lo(q[j][0]) + bf16lo(rr.x), bf16hi(q[j][0]) + bf16hi(rr.x));
@@ -428,7 +436,39 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
                 q[j][2] = pack_bf16(bf16lo(q[j][2]) + bf16lo(rr.z), bf16hi(q[j][2]) + bf16hi(rr.z));
                 q[j][3] = pack_bf16(bf16lo(q[j][3]) + bf16lo(rr.w), bf16hi(q[j][3]) + bf16hi(rr.w));
               }
-              *reinterpret_cast<uint4*>(p.rs_out + dsto) = make_uint4(q[j][0], q[j][1], q[j][2], q[j][3]);
+              if (bcast)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.rs_bcast_mc + dsto * 2), "r"(q[j][0]),
+                             "r"(q[j][1]), "r"(q[j][2]), "r"(q[j][3]) : "memory");
+              else
+                *reinterpret_cast<uint4*>(p.rs_out + dsto) = make_uint4(q[j][0], q[j][1], q[j][2], q[j][3]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (p.rs_bcast_mc != nullptr) {
+        // completion: the last CTA of this rank to finish its tiles tells every rank; nobody leaves before all ranks have told
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          __threadfence_system();
+          if (atomicAdd(p.rs_cta_counter, 1u) == gridDim.x - 1) {
+            *p.rs_cta_counter = 0;
+            __threadfence_system();
+#pragma unroll
+            for (int d = 0; d < SYMM_MAX_RANKS; ++d)
+              if (d < p.rs_world) st_release_sys(p.rs_done[d] + p.rs_rank, tag);
+          }
+        }
+        if (etid < p.rs_world) {
+          const uint32_t* mine = p.rs_done[0];
+#pragma unroll
+          for (int d = 1; d < SYMM_MAX_RANKS; ++d)
+            if (d == p.rs_rank) mine = p.rs_done[d];
+          const long long t0 = clock64();
+          while ((int)(ld_acquire_sys(mine + etid) - tag) < 0) {
+            if (clock64() - t0 > 8000000000LL) {
+              printf("gemm all-reduce: rank %d timed out waiting for the completion flag of rank %d (tag %u)\n", p.rs_rank, etid, tag);
+              __trap();
             }
           }
         }
@@ -571,6 +611,9 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
     p.rs_step = reinterpret_cast<const uint32_t*>(rs->step);
     p.rs_call = rs->call; p.rs_rank = rs->rank; p.rs_world = rs->world;
     p.rs_tiles_per_seg = rows_per_seg / GM_BM;
+    p.rs_bcast_mc = reinterpret_cast<uint8_t*>(const_cast<void*>(rs->bcast_mc));
+    for (int i = 0; i < rs->world; ++i) p.rs_done[i] = reinterpret_cast<uint32_t*>(rs->done_ptrs[i]);
+    p.rs_cta_counter = reinterpret_cast<unsigned*>(rs->cta_counter);
     if ((long long)p.m_tiles * p.n_tiles > rs->max_tiles) throw std::runtime_error("gemm: too many tiles for the reduce-scatter flag array");
   }
   const size_t smem = (size_t)GM_STAGES * (TM * GM_A_BYTES + BN * GM_BK * 2) + 256 + 1024;

@@ -137,6 +137,12 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
         y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None)
         return y.view(*x.shape[:-1], y.shape[-1])
     heap = getattr(group, "heap", None)
+    if heap is not None and scale is None and reduce_dtype in (None, torch.float32, x.dtype) and T > GEMV_MAX_TOKENS \
+            and heap.gemm_ar_usable(x, w):
+        # prefill: tcgen05 GEMM -> per-tile hand-off -> in-switch reduce of the owned tiles -> multicast of the result, ONE kernel
+        stats["gemm_all_reduce"] += 1
+        y = heap.gemm_all_reduce(x.reshape(T, K), w, bias if group.rank == 0 else None, residual)
+        return y.view(*x.shape[:-1], w.shape[0])
     if heap is not None and scale is None:
         # prefill: partial sums land in the symmetric staging area (bias on rank 0 only), one in-switch all-reduce adds the residual
         y = linear(x, w, bias if group.rank == 0 else None, out=staging_for(group, x, w))

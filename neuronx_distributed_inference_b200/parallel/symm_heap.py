@@ -250,10 +250,40 @@ class SymmetricHeap:
         symm = self.group.symm
         flags = [va + self._rs_flags_off for va in self.peer_va]
         out = self.C.gemm_reduce_scatter(x2d, w, bias, staging, self.mc_va + off, flags, self._RS_MAX_TILES, symm.step_t, symm.call,
-                                         self.rank, rows_per_seg, residual.reshape(-1, N).contiguous() if residual is not None else None)
+                                         self.rank, rows_per_seg, residual.reshape(-1, N).contiguous() if residual is not None else None,
+                                         0, [], None)
         symm.call += 1
         symm.calls += 1
         return out
+
+    def gemm_ar_usable(self, x: torch.Tensor, w: torch.Tensor) -> bool:
+        M = x.numel() // x.shape[-1]
+        return self.gemm_rs_usable(x, w, M) and os.environ.get("NXDI_B200_FUSED_AR", "1") != "0"
+
+    def gemm_all_reduce(self, x2d: torch.Tensor, w: torch.Tensor, bias, residual=None) -> torch.Tensor:
+        """x2d [M, K_local] -> [M, N] = sum over ranks (+ bias on rank 0, + residual): partial GEMM, in-switch reduction of the
+        tiles this rank owns, multicast of the result to every rank and the completion handshake — ONE kernel.  The result is
+        copied out of the symmetric output buffer (two of them alternate; callers may keep the tensor)."""
+        M, N = x2d.shape[0], w.shape[0]
+        if getattr(self, "_ar_out_off", None) is None or M * N * 2 > self._ar_out_bytes:
+            size = max(M * N * 2, 32 << 20)
+            self._ar_out_off = [self.alloc(size), self.alloc(size)]
+            self._ar_out_bytes = size
+            self._ar_done_off = self.alloc(256)
+            self._ar_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        off = self._rs_stage_off[self._rs_n & 1]
+        out_off = self._ar_out_off[self._rs_n & 1]
+        self._rs_n += 1
+        staging = self.tensor(off, (M, N))
+        symm = self.group.symm
+        flags = [va + self._rs_flags_off for va in self.peer_va]
+        done = [va + self._ar_done_off for va in self.peer_va]
+        self.C.gemm_reduce_scatter(x2d, w, bias, staging, self.mc_va + off, flags, self._RS_MAX_TILES, symm.step_t, symm.call, self.rank, M,
+                                   residual.reshape(-1, N).contiguous() if residual is not None else None, self.mc_va + out_off, done,
+                                   self._ar_counter)
+        symm.call += 1
+        symm.calls += 1
+        return self.tensor(out_off, (M, N)).clone()
 
     def close(self):
         if getattr(self, "h", None) is not None:

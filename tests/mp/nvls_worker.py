@@ -84,6 +84,24 @@ def main():
         e = rel(y, ref); worst = max(worst, e)
         log(f"fused gemm+reduce_scatter B={Bb} T={T} K={K} N={N}: rel {e:.2e}")
         assert e < 1e-2
+    # fused GEMM -> all-reduce (reduce owned tiles in the switch, multicast the result): one kernel
+    for (M, K, N) in [(128 * world, 512, 1024), (2048, 1792, 4096)]:
+        g.symm.begin_step()
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16) * 0.5
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+        res = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+        dist.broadcast(res, 0)
+        assert heap.gemm_ar_usable(x, w)
+        for it in range(3):
+            y = heap.gemm_all_reduce(x, w, None, res)
+        ref = x.float() @ w.float().t()
+        dist.all_reduce(ref)
+        e = rel(y, ref + res.float()); worst = max(worst, e)
+        ys = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(ys, y)
+        same = all(torch.equal(ys[0], t) for t in ys)
+        log(f"fused gemm+all_reduce M={M} K={K} N={N}: rel {e:.2e} identical {same}")
+        assert e < 1e-2 and same
     # timing: fused vs GEMM + NVLS reduce-scatter kernel vs GEMM + NCCL
     out = {}
     Bb, T, K, N = 1, 2048, 1792, 4096
@@ -100,7 +118,16 @@ def main():
         o = torch.empty(Bb * T // world, N, device=dev, dtype=torch.bfloat16)
         dist.reduce_scatter_tensor(o, y.view(-1, N))
         return o + res.view(-1, N)
-    for name, fn in (("fused", t_fused), ("gemm_plus_nvls", t_nvls), ("gemm_plus_nccl", t_nccl)):
+    xf = x.reshape(-1, K)
+    resf = torch.randn(Bb * T, N, device=dev, dtype=torch.bfloat16)
+    def t_fused_ar():
+        return heap.gemm_all_reduce(xf, w, None, resf)
+    def t_nccl_ar():
+        y = ops.linear(xf, w, None)
+        dist.all_reduce(y)
+        return y + resf
+    for name, fn in (("fused", t_fused), ("gemm_plus_nvls", t_nvls), ("gemm_plus_nccl", t_nccl), ("fused_allreduce", t_fused_ar),
+                     ("gemm_plus_nccl_allreduce", t_nccl_ar)):
         g.symm.begin_step()
         for _ in range(3): fn()
         torch.cuda.synchronize(); dist.barrier()

@@ -29,3 +29,16 @@ def test_llama_tp_fused_allreduce_matches_hf(n, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"ok": true' in r.stdout
+
+
+@pytest.mark.parametrize("n", [2, 8])
+def test_symmetric_heap_nvls_collectives_and_fused_gemm(n):
+    """VMM symmetric heap + NVLS multicast: in-switch all-reduce / reduce-scatter / all-gather and the fused tcgen05 GEMM ->
+    reduce-scatter / all-reduce kernels vs NCCL (tests/mp/nvls_worker.py asserts the numerics on every rank)."""
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29650 + n), os.path.join(ROOT, "tests", "mp", "nvls_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"ok": true' in r.stdout
