@@ -136,6 +136,12 @@ void attention_prefill_launch(const AttnPrefillParams& p, cudaStream_t stream);
 void attention_prefill_tc_launch(const void* q, const void* k, const void* v, void* out, const float* sinks, int B, int T, int Hq, int Hkv,
                                  float scale, int causal, int window, float softcap, cudaStream_t stream);
 
+// W8A8 fp8 path: dynamic per-token activation quantisation (quant.cu) + tcgen05 kind::f8f6f4 GEMM (gemm_tcgen05.cu)
+void rmsnorm_quant_launch(const void* x, const void* gamma, void* q, float* scale, int rows, int H, float eps, float offset, float clamp,
+                          cudaStream_t stream);
+void gemm_fp8_launch(const void* a, int lda, const void* b, const float* a_scale, const float* w_scale, int w_scale_n, const void* bias,
+                     const void* residual, void* c, int ldc, int M, int N, int K, int act, cudaStream_t stream);
+
 // symmetric heap (symm_heap.cpp) and NVLS collectives (nvls.cu)
 long long symm_heap_create(long long bytes, int device, int world, int rank);
 long long symm_heap_size(long long h);

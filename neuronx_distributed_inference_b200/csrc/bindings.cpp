@@ -452,6 +452,36 @@ at::Tensor attention_prefill(const at::Tensor& q, const at::Tensor& k, const at:
 }  // namespace nxdi
 
 namespace nxdi {
+// ---- W8A8 fp8 ------------------------------------------------------------------------------------------------------------------
+std::tuple<at::Tensor, at::Tensor> rmsnorm_quant(const at::Tensor& x, const c10::optional<at::Tensor>& gamma, double eps, double offset,
+                                                 double clamp) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && is_bf16(x));
+  if (gamma.has_value()) TORCH_CHECK(is_bf16(*gamma) && gamma->numel() == x.size(1));
+  c10::cuda::CUDAGuard guard(x.device());
+  auto q = at::empty(x.sizes(), x.options().dtype(at::kFloat8_e4m3fn));
+  auto scale = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  rmsnorm_quant_launch(x.data_ptr(), optr(gamma), q.data_ptr(), scale.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (float)eps,
+                       (float)offset, (float)clamp, cur_stream());
+  return {q, scale};
+}
+at::Tensor gemm_fp8(const at::Tensor& xq, const at::Tensor& a_scale, const at::Tensor& w, const at::Tensor& w_scale,
+                    const c10::optional<at::Tensor>& bias, int64_t act, const c10::optional<at::Tensor>& residual) {
+  TORCH_CHECK(xq.is_cuda() && xq.dim() == 2 && xq.is_contiguous() && xq.scalar_type() == at::kFloat8_e4m3fn);
+  TORCH_CHECK(w.dim() == 2 && w.is_contiguous() && w.scalar_type() == at::kFloat8_e4m3fn && w.size(1) == xq.size(1));
+  const int M = xq.size(0), K = xq.size(1), N = w.size(0);
+  TORCH_CHECK(K % 128 == 0 && a_scale.scalar_type() == at::kFloat && a_scale.numel() == M && w_scale.scalar_type() == at::kFloat &&
+              (w_scale.numel() == 1 || w_scale.numel() == N) && a_scale.is_contiguous() && w_scale.is_contiguous());
+  const bool glu = act != 0;
+  const int n_out = glu ? N / 2 : N;
+  TORCH_CHECK(n_out % 8 == 0);
+  c10::cuda::CUDAGuard guard(xq.device());
+  auto y = at::empty({M, n_out}, xq.options().dtype(at::kBFloat16));
+  if (residual.has_value()) TORCH_CHECK(!glu && is_bf16(*residual) && residual->is_contiguous() && residual->numel() == y.numel());
+  gemm_fp8_launch(xq.data_ptr(), K, w.data_ptr(), a_scale.data_ptr<float>(), w_scale.data_ptr<float>(), (int)w_scale.numel(), optr(bias),
+                  optr(residual), y.data_ptr(), n_out, M, N, K, (int)act, cur_stream());
+  return y;
+}
+
 // Row-parallel GEMM with the reduce-scatter fused into the kernel: x [M, K] (M = segs * rows_per_seg, rows of a segment split
 // evenly over the ranks) -> private output [M / world, N] = sum over ranks of x_r w_r^T (+ bias on rank 0) (+ residual).
 // `staging` is this rank's symmetric buffer for the partial sums, `mc_ptr` its multicast address.
@@ -565,6 +595,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nvls_collective", &nxdi::nvls_collective);
   m.def("attention_prefill_tc", &nxdi::attention_prefill_tc);
   m.def("gemm_reduce_scatter", &nxdi::gemm_reduce_scatter);
+  m.def("rmsnorm_quant", &nxdi::rmsnorm_quant);
+  m.def("gemm_fp8", &nxdi::gemm_fp8);
   m.def("dstep_new", &nxdi::dstep_new_b);
   m.def("dstep_set_symm", &nxdi::dstep_set_symm_b);
   m.def("dstep_add_gemv", &nxdi::dstep_add_gemv_b);

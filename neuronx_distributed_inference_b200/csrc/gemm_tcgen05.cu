@@ -36,6 +36,11 @@ struct GemmParams {
   __nv_bfloat16* c;               // [M, N_out]
   int M, N, K, ldc, act;          // act: 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up  (N_out = N/2 when act != 0)
   int m_tiles, n_tiles;           // tile grid (CTA tiles of TM*128 x 128 output columns; 64 output features for GLU)
+  // fp8 (e4m3 x e4m3 -> fp32, tcgen05 kind::f8f6f4): acc * a_scale[row] * w_scale[col] (dynamic per-token activation scale,
+  // per-output-channel or per-tensor weight scale); null for bf16
+  const float* a_scale;
+  const float* w_scale;
+  int w_scale_n;
   int splits;                     // split-K factor: work item = (tile, k slice); partial accumulators meet in `ws`
   float* ws;                      // [tiles][splits][TM*128][128] fp32 partials (L2 resident)
   unsigned* tickets;              // [tiles], self-resetting
@@ -106,6 +111,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor for kind::f8f6f4: D = f32, A = B = e4m3 (format 0), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f8(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
@@ -124,7 +140,7 @@ __device__ __forceinline__ void mb_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
 }
 
-template <int TM, int BN>
+template <int TM, int BN, bool FP8>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   constexpr int B_BYTES = BN * GM_BK * 2;
   constexpr int STAGE_BYTES = TM * GM_A_BYTES + B_BYTES;
@@ -141,7 +157,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool glu = p.act != 0;
-  const int nkb = p.K / GM_BK;
+  constexpr int BKE = FP8 ? 128 : 64;   // elements per 128-byte k-block row
+  const int nkb = p.K / BKE;
   const int S = p.splits;
   const int total_tiles = p.m_tiles * p.n_tiles * S;   // work items: (tile, k slice), k slice fastest
   const int tile_out = glu ? BN / 2 : BN;   // output columns per tile
@@ -194,14 +211,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
             mb_expect(&full_bar[s], B_BYTES);
             uint8_t* sB = smem + s * STAGE_BYTES + TM * GM_A_BYTES;
             if (glu) {  // 64 gate rows + 64 up rows of the fused [gate; up] weight
-              tma_2d(sB, &p.tma_b, kb * GM_BK, n_out0, &full_bar[s]);
-              tma_2d(sB + B_BYTES / 2, &p.tma_b, kb * GM_BK, (p.N >> 1) + n_out0, &full_bar[s]);
+              tma_2d(sB, &p.tma_b, kb * BKE, n_out0, &full_bar[s]);
+              tma_2d(sB + B_BYTES / 2, &p.tma_b, kb * BKE, (p.N >> 1) + n_out0, &full_bar[s]);
             } else {
-              tma_2d(sB, &p.tma_b, kb * GM_BK, n_out0, &full_bar[s]);
+              tma_2d(sB, &p.tma_b, kb * BKE, n_out0, &full_bar[s]);
             }
           } else {
             mb_expect(&full_bar[s], TM * GM_A_BYTES);
-            tma_2d(smem + s * STAGE_BYTES, &p.tma_a, kb * GM_BK, m0, &full_bar[s]);
+            tma_2d(smem + s * STAGE_BYTES, &p.tma_a, kb * BKE, m0, &full_bar[s]);
           }
         }
       }
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(GM_BM, BN);
+      constexpr uint32_t idesc = FP8 ? umma_idesc_f8(GM_BM, BN) : umma_idesc(GM_BM, BN);
       long long it = 0;
       int tc = 0;
       for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tc) {
@@ -231,7 +248,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < GM_BK / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-              umma_f16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              // (fp8: 32 elements = 32 bytes per instruction; bf16: 16 elements = 32 bytes — the same descriptor step)
+              if (FP8) umma_f8(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              else umma_f16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
@@ -252,6 +271,33 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
       if (row >= p.M || col0 >= n_out) return;
       __nv_bfloat16* dst = p.c + (size_t)row * p.ldc + col0;
       const __nv_bfloat16* res = (!glu && p.residual) ? p.residual + (size_t)row * p.ldc + col0 : nullptr;
+      // fp8: combined dequantisation factors of this row x these 32 columns (row scale x channel scale), vector loads
+      float sc_g[32], sc_u[32];
+      if (FP8) {
+        const float as = p.a_scale[row];
+        const bool full = col0 + 32 <= n_out && p.w_scale_n != 1;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 g4, u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (full) {
+            g4 = __ldg(reinterpret_cast<const float4*>(p.w_scale + col0 + j));
+            if (glu) u4 = __ldg(reinterpret_cast<const float4*>(p.w_scale + n_out + col0 + j));
+          } else if (p.w_scale_n == 1) {
+            g4 = u4 = make_float4(p.w_scale[0], p.w_scale[0], p.w_scale[0], p.w_scale[0]);
+          } else {
+            float t[4], tu[4];
+            for (int e = 0; e < 4; ++e) {
+              const bool in = col0 + j + e < n_out;
+              t[e] = in ? p.w_scale[col0 + j + e] : 0.f;
+              tu[e] = (in && glu) ? p.w_scale[n_out + col0 + j + e] : 0.f;
+            }
+            g4 = make_float4(t[0], t[1], t[2], t[3]);
+            u4 = make_float4(tu[0], tu[1], tu[2], tu[3]);
+          }
+          sc_g[j] = g4.x * as; sc_g[j + 1] = g4.y * as; sc_g[j + 2] = g4.z * as; sc_g[j + 3] = g4.w * as;
+          sc_u[j] = u4.x * as; sc_u[j + 1] = u4.y * as; sc_u[j + 2] = u4.z * as; sc_u[j + 3] = u4.w * as;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         float f[8];
@@ -259,9 +305,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
         for (int e = 0; e < 8; ++e) {
           float a = __uint_as_float(vg[j + e]);
           const bool in = col0 + j + e < n_out;
+          float up_s = 1.f;
+          if (FP8) {
+            a *= sc_g[j + e];
+            up_s = sc_u[j + e];
+          }
           if (p.bias && in) a += __bfloat162float(p.bias[col0 + j + e]);
           if (glu) {
-            float up = __uint_as_float(vu[j + e]);
+            float up = __uint_as_float(vu[j + e]) * up_s;
             if (p.bias && in) up += __bfloat162float(p.bias[n_out + col0 + j + e]);
             a = (p.act == 1 ? silu(a) : (p.act == 2 ? gelu_tanh(a) : gelu_erf(a))) * up;
           }
@@ -498,12 +549,12 @@ static EncodeTiledFn2 encode_fn() {
   }
   return fn;
 }
-static void make_2d(CUtensorMap* tm, const void* ptr, int rows, int K, int ld_elems, int box_rows) {
+static void make_2d(CUtensorMap* tm, const void* ptr, int rows, int K, int ld_elems, int box_rows, bool fp8 = false) {
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
-  cuuint32_t box[2] = {GM_BK, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * (fp8 ? 1 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(fp8 ? 128 : GM_BK), (cuuint32_t)box_rows};   // 128-byte rows either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = encode_fn()(tm, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (gemm) failed: " + std::to_string((int)r));
@@ -532,10 +583,13 @@ static unsigned* gemm_tickets() {
   return g_gemm_tk[dev];
 }
 
-void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
-                         int N, int K, int act, cudaStream_t stream, const GemmRsArgs* rs) {
+static void gemm_launch_impl(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M, int N,
+                             int K, int act, cudaStream_t stream, const GemmRsArgs* rs, const float* a_scale, const float* w_scale,
+                             int w_scale_n) {
   GemmParams p{};
   const bool glu = act != 0;
+  const bool fp8 = a_scale != nullptr;
+  p.a_scale = a_scale; p.w_scale = w_scale; p.w_scale_n = w_scale_n;
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev;
@@ -569,15 +623,15 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
     TM = 1;
     BN = M > 2 * GM_BM ? 256 : 128;
   }
-  make_2d(&p.tma_a, a, M, K, lda, TM * GM_BM);
-  make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN);
+  make_2d(&p.tma_a, a, M, K, lda, TM * GM_BM, fp8);
+  make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN, fp8);
   const int n_out = glu ? N / 2 : N;
   const int tile_out = glu ? BN / 2 : BN;
   p.m_tiles = (M + TM * GM_BM - 1) / (TM * GM_BM);
   p.n_tiles = (n_out + tile_out - 1) / tile_out;
   // split-K when the tile grid leaves SMs idle or quantises badly (skinny prefill: M <= 256, N of a few thousand):
   // minimise  ceil(tiles * S / SMs) / S  (+ a small fix-up charge), bounded by the workspace and >= 8 k-blocks per slice
-  const int tiles = p.m_tiles * p.n_tiles, nkb = K / GM_BK;
+  const int tiles = p.m_tiles * p.n_tiles, nkb = K / (fp8 ? 128 : GM_BK);
   static int force_s = -1;
   if (force_s < 0) {
     const char* e = getenv("NXDI_B200_GEMM_SPLITK");
@@ -620,17 +674,41 @@ void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias
   static bool configured = false;
   if (!configured) {
     const int max_smem = GM_STAGES * (2 * GM_A_BYTES + 128 * GM_BK * 2) + 256 + 1024;   // == 1 x A + 256-row B
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     configured = true;
   }
   const int grid = std::min(n_sms, p.m_tiles * p.n_tiles * p.splits);
-  if (TM == 2) launch_pdl(gemm_tcgen05_kernel<2, 128>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
-  else if (BN == 256) launch_pdl(gemm_tcgen05_kernel<1, 256>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
-  else if (BN == 64) launch_pdl(gemm_tcgen05_kernel<1, 64>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
-  else launch_pdl(gemm_tcgen05_kernel<1, 128>, dim3(grid), dim3(GM_THREADS), smem, stream, p);
+  const dim3 g(grid), b3(GM_THREADS);
+  if (fp8) {
+    if (TM == 2) launch_pdl(gemm_tcgen05_kernel<2, 128, true>, g, b3, smem, stream, p);
+    else if (BN == 256) launch_pdl(gemm_tcgen05_kernel<1, 256, true>, g, b3, smem, stream, p);
+    else if (BN == 64) launch_pdl(gemm_tcgen05_kernel<1, 64, true>, g, b3, smem, stream, p);
+    else launch_pdl(gemm_tcgen05_kernel<1, 128, true>, g, b3, smem, stream, p);
+  } else {
+    if (TM == 2) launch_pdl(gemm_tcgen05_kernel<2, 128, false>, g, b3, smem, stream, p);
+    else if (BN == 256) launch_pdl(gemm_tcgen05_kernel<1, 256, false>, g, b3, smem, stream, p);
+    else if (BN == 64) launch_pdl(gemm_tcgen05_kernel<1, 64, false>, g, b3, smem, stream, p);
+    else launch_pdl(gemm_tcgen05_kernel<1, 128, false>, g, b3, smem, stream, p);
+  }
+}
+
+void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
+                         int N, int K, int act, cudaStream_t stream, const GemmRsArgs* rs) {
+  gemm_launch_impl(a, lda, b, bias, residual, c, ldc, M, N, K, act, stream, rs, nullptr, nullptr, 0);
+}
+
+// W8A8 fp8-e4m3 GEMM: a [M, K] fp8 with per-row scale, b [N, K] fp8 with per-channel (w_scale_n == N) or per-tensor (1) scale
+void gemm_fp8_launch(const void* a, int lda, const void* b, const float* a_scale, const float* w_scale, int w_scale_n, const void* bias,
+                     const void* residual, void* c, int ldc, int M, int N, int K, int act, cudaStream_t stream) {
+  if (K % 128 != 0) throw std::runtime_error("gemm_fp8: K must be a multiple of 128");
+  gemm_launch_impl(a, lda, b, bias, residual, c, ldc, M, N, K, act, stream, nullptr, a_scale, w_scale, w_scale_n);
 }
 
 }  // namespace nxdi

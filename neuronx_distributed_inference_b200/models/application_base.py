@@ -245,6 +245,12 @@ class NeuronApplicationBase(nn.Module):
 
     def _attach_symmetric_workspace(self):
         nc = self.neuron_config
+        # W8A8: dynamic per-token fp8 activations into the tcgen05 kind::f8f6f4 GEMM (prefill-sized token counts); the reference's
+        # quantized_mlp_kernel_enabled / activation_quantization_type="dynamic" / rmsnorm_quantize_kernel_enabled switches
+        # (models/config.py:219-242 of the reference)
+        if self.device.type == "cuda" and (nc.quantized_mlp_kernel_enabled or nc.rmsnorm_quantize_kernel_enabled
+                                           or nc.activation_quantization_type == "dynamic"):
+            ops.set_activation_quant(True)
         g = pstate.get_tensor_model_parallel_group()
         if g.size > 1 and self.device.type == "cuda" and nc.fused_collectives and g.symm is None:
             from ..parallel.symm import SymmetricWorkspace

@@ -104,6 +104,16 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
             n_out = N // 2 if act is not None else N
+            if (wq and _ACT_QUANT and w.dtype == torch.float8_e4m3fn and T > GEMV_MAX_TOKENS and K % 128 == 0 and n_out % 8 == 0
+                    and w.dim() == 2 and K <= 16384):
+                # W8A8: RMSNorm + per-token fp8 quantisation in one kernel, then the fp8 tensor-core GEMM (2x the bf16 rate);
+                # acc * a_scale[row] * w_scale[col] in the epilogue
+                stats["gemm_fp8"] += 1
+                xq, a_s = _C().rmsnorm_quant(x2.contiguous(), norm_weight, float(norm_eps), float(norm_offset), float("inf"))
+                r2 = residual.reshape(T, -1).contiguous() if (residual is not None and act is None) else None
+                y = _C().gemm_fp8(xq, a_s, w, scale.float().contiguous(), bias, _ACT_CODES[act], r2)
+                y = y.view(*x.shape[:-1], y.shape[-1])
+                return y if (residual is None or r2 is not None) else y + residual
             if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM and (T > GEMV_MAX_TOKENS or K % 64 != 0):
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
@@ -317,8 +327,24 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
                            act_fn, scale_input)
 
 
-def rmsnorm_quant(x, weight, eps, clamp=float("inf")):
+def rmsnorm_quant(x, weight, eps, clamp=float("inf"), offset: float = 0.0):
+    """(fp8-e4m3 activations, per-row fp32 scale): RMSNorm (``weight`` may be None) fused with dynamic per-token quantisation.
+    ONE kernel on CUDA (csrc/quant.cu); reference kernel K6 (modeling_llama.py:553-575)."""
+    if _use_cuda(x) and x.dtype in _FAST_DTYPES and x.shape[-1] % 8 == 0 and x.shape[-1] <= 16384:
+        stats["rmsnorm_quant"] += 1
+        q, s = _C().rmsnorm_quant(x.reshape(-1, x.shape[-1]).contiguous(), weight, float(eps), float(offset), float(clamp))
+        return q.view(x.shape), s.view(*x.shape[:-1], 1)
     return ref.rmsnorm_quant(x, weight, eps, clamp)
+
+
+_ACT_QUANT = os.environ.get("NXDI_B200_FP8_ACT", "0") == "1"
+
+
+def set_activation_quant(flag: bool):
+    """W8A8: fp8 weights meet dynamically quantised fp8 activations on the tensor cores (tcgen05 kind::f8f6f4) for T > 8 tokens.
+    Set from ``NeuronConfig.activation_quantization_type == "dynamic"`` / ``quantized_mlp_kernel_enabled``; off = weight-only."""
+    global _ACT_QUANT
+    _ACT_QUANT = bool(flag)
 
 
 activation = ref.activation

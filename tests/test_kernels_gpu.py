@@ -322,3 +322,31 @@ def test_attention_prefill_tcgen05(B, T, Hq, Hkv, causal, window, softcap, sinks
     assert ops.stats["attn_prefill_tc"] == n0 + 1
     orf = ref.attention_prefill(q.float(), k.float(), v.float(), scale, causal, window or None, sinks=sk, softcap=softcap or None)
     assert o.shape == orf.shape and _rel(o, orf) < 1.2e-2, _rel(o, orf)
+
+
+@pytest.mark.parametrize("M,N,K,act,per_tensor", [(256, 4096, 4096, None, False), (300, 2 * 1024, 2048, "silu_mul", False),
+                                                  (2048, 4096, 1024, None, True), (64, 512, 512, None, False)])
+def test_fp8_w8a8_gemm_and_rmsnorm_quant(M, N, K, act, per_tensor):
+    """RMSNorm + dynamic per-token fp8 quantisation (csrc/quant.cu) and the fp8 tensor-core GEMM (tcgen05 kind::f8f6f4) against
+    the SAME quantised operands evaluated in fp32 (isolates the kernels from the quantisation error itself)."""
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16) * 2
+    g = (torch.randn(K, device=DEV) * 0.2 + 1).to(torch.bfloat16)
+    wf = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    ws = (wf.abs().amax() / 448).reshape(1) if per_tensor else wf.abs().amax(1) / 448
+    wq = (wf / (ws if per_tensor else ws[:, None])).to(torch.float8_e4m3fn)
+    b = torch.randn(N, device=DEV, dtype=torch.bfloat16)
+    xq, a_s = ops.rmsnorm_quant(x, g, 1e-5)
+    assert xq.dtype == torch.float8_e4m3fn and a_s.shape == (M, 1)
+    xn = ref.rmsnorm(x.float(), g.float(), 1e-5).to(torch.bfloat16).float()
+    assert _rel(xq.float() * a_s, xn) < 4e-2                      # fp8 e4m3 rounding of the normalised row
+    assert torch.allclose(a_s.view(-1), xn.abs().amax(1) / 448, rtol=2e-2)
+    ops.set_activation_quant(True)
+    try:
+        n0 = ops.stats["gemm_fp8"]
+        y = ops.linear(x, wq, b, norm_weight=g, norm_eps=1e-5, act=act, scale=ws.float())
+        assert ops.stats["gemm_fp8"] == n0 + 1
+    finally:
+        ops.set_activation_quant(False)
+    yr = ref.linear((xq.float() * a_s), wq.float() * (ws if per_tensor else ws[:, None]), b.float(), act=act)
+    assert y.shape == yr.shape and _rel(y, yr) < 8e-3, _rel(y, yr)
