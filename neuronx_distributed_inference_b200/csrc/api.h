@@ -142,6 +142,16 @@ void rmsnorm_quant_launch(const void* x, const void* gamma, void* q, float* scal
 void gemm_fp8_launch(const void* a, int lda, const void* b, const float* a_scale, const float* w_scale, int w_scale_n, const void* bias,
                      const void* residual, void* c, int ldc, int M, int N, int K, int act, cudaStream_t stream);
 
+// mixture-of-experts prefill: device-side permutation (moe_grouped.cu) around the grouped tcgen05 GEMM (gemm_tcgen05.cu)
+void moe_plan_launch(const int* topk_i, int entries, int expert_offset, int e_local, int R, int* pos, int* row_entry, int* tile_expert,
+                     cudaStream_t stream);
+void moe_gather_launch(const void* x, const float* topk_w, const int* row_entry, const int* tile_expert, void* xp, int R, int H, int k,
+                       int scale_input, cudaStream_t stream);
+void moe_combine_launch(const void* y, const float* topk_w, const int* pos, void* out, int N, int H, int k, int scale_input,
+                        cudaStream_t stream);
+void gemm_grouped_launch(const void* a, const void* b, const void* bias, void* c, int R, int N, int K, int n_experts, int act,
+                         const int* tile_expert, const float* a_scale, const float* w_scale, cudaStream_t stream);
+
 // symmetric heap (symm_heap.cpp) and NVLS collectives (nvls.cu)
 long long symm_heap_create(long long bytes, int device, int world, int rank);
 long long symm_heap_size(long long h);

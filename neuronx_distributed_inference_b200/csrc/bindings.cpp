@@ -210,6 +210,43 @@ at::Tensor moe_decode(const at::Tensor& x, const at::Tensor& w_gate_up, const at
   return y.to(x.scalar_type());
 }
 
+// Routed experts of a prefill-sized batch (any N): permutation on the device + two grouped tcgen05 GEMMs + weighted combine.
+// act: 1 silu*up, 2 gelu_tanh*up, 3 gelu*up.  gate_up_bias [E, 2I] / down_bias [E, H] optional (bf16).
+at::Tensor moe_grouped(const at::Tensor& x, const at::Tensor& w_gate_up, const at::Tensor& w_down, const at::Tensor& topk_w,
+                       const at::Tensor& topk_i, int64_t expert_offset, int64_t act, bool scale_input,
+                       const c10::optional<at::Tensor>& gate_up_bias, const c10::optional<at::Tensor>& down_bias) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && is_bf16(x) && is_bf16(w_gate_up) && is_bf16(w_down));
+  TORCH_CHECK(w_gate_up.dim() == 3 && w_down.dim() == 3 && w_gate_up.is_contiguous() && w_down.is_contiguous());
+  const int N = x.size(0), H = x.size(1), E = w_gate_up.size(0), I = w_gate_up.size(1) / 2, k = topk_i.size(1);
+  TORCH_CHECK(w_gate_up.size(2) == H && w_down.size(0) == E && w_down.size(1) == H && w_down.size(2) == I);
+  TORCH_CHECK(H % 64 == 0 && I % 64 == 0, "moe_grouped: hidden and intermediate sizes must be multiples of 64");
+  TORCH_CHECK(topk_w.scalar_type() == at::kFloat && topk_i.scalar_type() == at::kInt && topk_w.is_contiguous() &&
+              topk_i.is_contiguous() && topk_w.numel() == (int64_t)N * k && topk_i.size(0) == N);
+  if (gate_up_bias) TORCH_CHECK(is_bf16(*gate_up_bias) && gate_up_bias->is_contiguous() && gate_up_bias->numel() == (int64_t)E * 2 * I);
+  if (down_bias) TORCH_CHECK(is_bf16(*down_bias) && down_bias->is_contiguous() && down_bias->numel() == (int64_t)E * H);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t R = (((int64_t)N * k + (int64_t)E * 127) + 127) / 128 * 128;   // static bound: graph-stable shapes
+  auto iopt = x.options().dtype(at::kInt);
+  auto pos = at::empty({(int64_t)N * k}, iopt);
+  auto row_entry = at::empty({R}, iopt);
+  auto tile_expert = at::empty({R / 128}, iopt);
+  auto xp = at::empty({R, H}, x.options());
+  auto h = at::empty({R, I}, x.options());
+  auto y = at::empty({R, H}, x.options());
+  auto out = at::empty({N, H}, x.options());
+  auto st = cur_stream();
+  moe_plan_launch(topk_i.data_ptr<int>(), N * k, (int)expert_offset, E, (int)R, pos.data_ptr<int>(), row_entry.data_ptr<int>(),
+                  tile_expert.data_ptr<int>(), st);
+  moe_gather_launch(x.data_ptr(), topk_w.data_ptr<float>(), row_entry.data_ptr<int>(), tile_expert.data_ptr<int>(), xp.data_ptr(), (int)R,
+                    H, k, scale_input ? 1 : 0, st);
+  gemm_grouped_launch(xp.data_ptr(), w_gate_up.data_ptr(), gate_up_bias ? gate_up_bias->data_ptr() : nullptr, h.data_ptr(), (int)R, 2 * I,
+                      H, E, (int)act, tile_expert.data_ptr<int>(), nullptr, nullptr, st);
+  gemm_grouped_launch(h.data_ptr(), w_down.data_ptr(), down_bias ? down_bias->data_ptr() : nullptr, y.data_ptr(), (int)R, H, I, E, 0,
+                      tile_expert.data_ptr<int>(), nullptr, nullptr, st);
+  moe_combine_launch(y.data_ptr(), topk_w.data_ptr<float>(), pos.data_ptr<int>(), out.data_ptr(), N, H, k, scale_input ? 1 : 0, st);
+  return out;
+}
+
 // ---- symmetric (peer-mapped) workspace ---------------------------------------------------------------------
 std::tuple<int64_t, pybind11::bytes> symm_alloc(int64_t nbytes) {
   void* p = nullptr;
@@ -616,6 +653,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("prof_count", []() { return (int64_t)nxdi::prof_count(); });
   m.def("gemv2_supported", [](int64_t T, int64_t K) { return nxdi::gemv2_supported((int)T, (int)K); });
   m.def("moe_decode", &nxdi::moe_decode);
+  m.def("moe_grouped", &nxdi::moe_grouped);
   m.def("gemm", &nxdi::gemm);
   m.def("symm_alloc", &nxdi::symm_alloc);
   m.def("symm_open", &nxdi::symm_open);

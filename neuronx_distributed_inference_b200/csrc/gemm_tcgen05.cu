@@ -63,6 +63,11 @@ struct GemmParams {
   uint8_t* rs_bcast_mc;                 // multicast address of the symmetric OUTPUT buffer [M, N]
   uint32_t* rs_done[SYMM_MAX_RANKS];    // [world] u32 on every rank (peer mapped): "rank s has broadcast all its tiles"
   unsigned* rs_cta_counter;             // local: CTAs of this launch that finished their reduce tiles (self-resetting)
+  // ---- grouped (mixture-of-experts) flavour: A holds the tokens PERMUTED by expert, every expert's rows padded to whole 128-row
+  // tiles (csrc/moe_grouped.cu builds the permutation on the device); B is the stacked weight [E * N, K] and m-tile `mt` multiplies
+  // with the rows of expert grp_tile_expert[mt] (< 0: tile not in use this step, skipped by every role).  M is the STATIC upper
+  // bound of permuted rows, so the launch is shape-stable under CUDA graphs whatever the routing.
+  const int* grp_tile_expert;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -197,12 +202,19 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
     // kernel), warp 3 the ACTIVATION tile (one 256-row box when TM = 2) — both post to the same full barrier.
     if (lane == 0) {
       const bool is_b = warp == 0;
-      if (!is_b) pdl_wait();
+      // (grouped: the routing plan comes from the preceding kernels, so the weight producer waits too)
+      if (!is_b || p.grp_tile_expert != nullptr) pdl_wait();
       long long it = 0;   // k-block counter across work items (ring position)
       for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
         const int t = w / S, ks = w % S;
         const int m0 = (t % p.m_tiles) * (TM * GM_BM), n_out0 = (t / p.m_tiles) * tile_out;
         const int kb0 = (int)((long long)nkb * ks / S), kb1 = (int)((long long)nkb * (ks + 1) / S);
+        int eo = 0;       // grouped: first row of this tile's expert inside the stacked weight
+        if (p.grp_tile_expert != nullptr) {
+          const int e = __ldg(p.grp_tile_expert + t % p.m_tiles);
+          if (e < 0) continue;
+          eo = e * p.N;
+        }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = (int)(it % GM_STAGES);
           const uint32_t ph = (uint32_t)((it / GM_STAGES) & 1);
@@ -211,10 +223,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
             mb_expect(&full_bar[s], B_BYTES);
             uint8_t* sB = smem + s * STAGE_BYTES + TM * GM_A_BYTES;
             if (glu) {  // 64 gate rows + 64 up rows of the fused [gate; up] weight
-              tma_2d(sB, &p.tma_b, kb * BKE, n_out0, &full_bar[s]);
-              tma_2d(sB + B_BYTES / 2, &p.tma_b, kb * BKE, (p.N >> 1) + n_out0, &full_bar[s]);
+              tma_2d(sB, &p.tma_b, kb * BKE, eo + n_out0, &full_bar[s]);
+              tma_2d(sB + B_BYTES / 2, &p.tma_b, kb * BKE, eo + (p.N >> 1) + n_out0, &full_bar[s]);
             } else {
-              tma_2d(sB, &p.tma_b, kb * BKE, n_out0, &full_bar[s]);
+              tma_2d(sB, &p.tma_b, kb * BKE, eo + n_out0, &full_bar[s]);
             }
           } else {
             mb_expect(&full_bar[s], TM * GM_A_BYTES);
@@ -229,8 +241,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
       constexpr uint32_t idesc = FP8 ? umma_idesc_f8(GM_BM, BN) : umma_idesc(GM_BM, BN);
       long long it = 0;
       int tc = 0;
-      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tc) {
+      if (p.grp_tile_expert != nullptr) pdl_wait();
+      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
         const int ks = w % S;
+        if (p.grp_tile_expert != nullptr && __ldg(p.grp_tile_expert + (w / S) % p.m_tiles) < 0) continue;
         const int kb0 = (int)((long long)nkb * ks / S), kb1 = (int)((long long)nkb * (ks + 1) / S);
         const int buf = tc & 1;
         mb_wait(&tmem_empty[buf], (uint32_t)(((tc >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator buffer
@@ -256,6 +270,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
           umma_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
         }
         umma_commit(&tmem_full[buf]);       // accumulator(s) of this tile complete
+        ++tc;
       }
     }
   } else if (warp >= 4) {
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
     const int etid = threadIdx.x - 128;     // 0..127 inside the epilogue group
     const int n_out = glu ? (p.N >> 1) : p.N;
     // final math + store of 32 accumulator columns [c0, c0+32) of one row (GLU: gate chunk + matching up chunk)
+    int cur_eo = 0;   // grouped: offset of the current tile's expert inside bias / w_scale ([E][N])
     auto store_chunk = [&](int row, int n_out0, int c0, const uint32_t (&vg)[32], const uint32_t (&vu)[32]) {
       const int col0 = n_out0 + c0;
       if (row >= p.M || col0 >= n_out) return;
@@ -280,16 +296,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
         for (int j = 0; j < 32; j += 4) {
           float4 g4, u4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (full) {
-            g4 = __ldg(reinterpret_cast<const float4*>(p.w_scale + col0 + j));
-            if (glu) u4 = __ldg(reinterpret_cast<const float4*>(p.w_scale + n_out + col0 + j));
+            g4 = __ldg(reinterpret_cast<const float4*>(p.w_scale + cur_eo + col0 + j));
+            if (glu) u4 = __ldg(reinterpret_cast<const float4*>(p.w_scale + cur_eo + n_out + col0 + j));
           } else if (p.w_scale_n == 1) {
             g4 = u4 = make_float4(p.w_scale[0], p.w_scale[0], p.w_scale[0], p.w_scale[0]);
           } else {
             float t[4], tu[4];
             for (int e = 0; e < 4; ++e) {
               const bool in = col0 + j + e < n_out;
-              t[e] = in ? p.w_scale[col0 + j + e] : 0.f;
-              tu[e] = (in && glu) ? p.w_scale[n_out + col0 + j + e] : 0.f;
+              t[e] = in ? p.w_scale[cur_eo + col0 + j + e] : 0.f;
+              tu[e] = (in && glu) ? p.w_scale[cur_eo + n_out + col0 + j + e] : 0.f;
             }
             g4 = make_float4(t[0], t[1], t[2], t[3]);
             u4 = make_float4(tu[0], tu[1], tu[2], tu[3]);
@@ -310,10 +326,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
             a *= sc_g[j + e];
             up_s = sc_u[j + e];
           }
-          if (p.bias && in) a += __bfloat162float(p.bias[col0 + j + e]);
+          if (p.bias && in) a += __bfloat162float(p.bias[cur_eo + col0 + j + e]);
           if (glu) {
             float up = __uint_as_float(vu[j + e]) * up_s;
-            if (p.bias && in) up += __bfloat162float(p.bias[n_out + col0 + j + e]);
+            if (p.bias && in) up += __bfloat162float(p.bias[cur_eo + n_out + col0 + j + e]);
             a = (p.act == 1 ? silu(a) : (p.act == 2 ? gelu_tanh(a) : gelu_erf(a))) * up;
           }
           f[e] = a;
@@ -334,8 +350,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
     };
     const int half = glu ? BN / 2 : BN;   // accumulator columns holding "gate or value"
     int tc = 0;
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tc) {
+    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
       const int t = w / S, ks = w % S;
+      if (p.grp_tile_expert != nullptr) {
+        const int e = __ldg(p.grp_tile_expert + t % p.m_tiles);
+        if (e < 0) continue;
+        cur_eo = e * p.N;
+      }
       const int buf = tc & 1;
       const int m0 = (t % p.m_tiles) * (TM * GM_BM), n_out0 = (t / p.m_tiles) * tile_out;
       mb_wait(&tmem_full[buf], (uint32_t)((tc >> 1) & 1));
@@ -430,6 +451,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last reusable
       }
+      ++tc;
     }
     if (p.rs_world > 0) {
       // ---- reduce phase: the tiles whose rows this rank owns, dealt round-robin to the CTAs ----
@@ -585,8 +607,9 @@ static unsigned* gemm_tickets() {
 
 static void gemm_launch_impl(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M, int N,
                              int K, int act, cudaStream_t stream, const GemmRsArgs* rs, const float* a_scale, const float* w_scale,
-                             int w_scale_n) {
+                             int w_scale_n, const int* tile_expert = nullptr, int n_experts = 1) {
   GemmParams p{};
+  p.grp_tile_expert = tile_expert;
   const bool glu = act != 0;
   const bool fp8 = a_scale != nullptr;
   p.a_scale = a_scale; p.w_scale = w_scale; p.w_scale_n = w_scale_n;
@@ -618,13 +641,18 @@ static void gemm_launch_impl(const void* a, int lda, const void* b, const void* 
     if (n_tiles_of(TM, 128) < n_sms) BN = 64;
   }
   if (force_tm) TM = force_tm;
+  if (tile_expert != nullptr) {   // grouped: one expert per 128-row tile
+    if (M % GM_BM != 0) throw std::runtime_error("grouped gemm: the permuted row bound must be a multiple of 128");
+    TM = 1;
+    BN = 256;
+  }
   if (rs != nullptr) {   // fused reduce-scatter: 128-row tiles so that a tile has exactly one owner; no split-K
     if (glu) throw std::runtime_error("gemm: the fused reduce-scatter needs a plain epilogue");
     TM = 1;
     BN = M > 2 * GM_BM ? 256 : 128;
   }
   make_2d(&p.tma_a, a, M, K, lda, TM * GM_BM, fp8);
-  make_2d(&p.tma_b, b, N, K, K, glu ? BN / 2 : BN, fp8);
+  make_2d(&p.tma_b, b, N * n_experts, K, K, glu ? BN / 2 : BN, fp8);
   const int n_out = glu ? N / 2 : N;
   const int tile_out = glu ? BN / 2 : BN;
   p.m_tiles = (M + TM * GM_BM - 1) / (TM * GM_BM);
@@ -650,7 +678,7 @@ static void gemm_launch_impl(const void* a, int lda, const void* b, const void* 
     }
   }
   p.splits = force_s > 0 ? std::min({force_s, 4, std::max(1, nkb / 2)}) : best_s;
-  if (rs != nullptr) p.splits = 1;
+  if (rs != nullptr || tile_expert != nullptr) p.splits = 1;
   if ((size_t)tiles * p.splits * tile_ws_bytes > gemm_ws_bytes() || tiles > gemm_max_tickets()) p.splits = 1;
   p.ws = p.splits > 1 ? gemm_ws() : nullptr;
   p.tickets = gemm_tickets();
@@ -702,6 +730,16 @@ static void gemm_launch_impl(const void* a, int lda, const void* b, const void* 
 void gemm_tcgen05_launch(const void* a, int lda, const void* b, const void* bias, const void* residual, void* c, int ldc, int M,
                          int N, int K, int act, cudaStream_t stream, const GemmRsArgs* rs) {
   gemm_launch_impl(a, lda, b, bias, residual, c, ldc, M, N, K, act, stream, rs, nullptr, nullptr, 0);
+}
+
+// grouped GEMM of the mixture-of-experts layers: a [R, K] tokens permuted by expert (R % 128 == 0), b [E, N, K] stacked expert
+// weights, tile_expert [R / 128] (device; -1 = unused tile), bias [E, N] or null; fp8 when a_scale != null (w_scale [E, N])
+void gemm_grouped_launch(const void* a, const void* b, const void* bias, void* c, int R, int N, int K, int n_experts, int act,
+                         const int* tile_expert, const float* a_scale, const float* w_scale, cudaStream_t stream) {
+  if (K % (a_scale ? 128 : 64) != 0) throw std::runtime_error("grouped gemm: K must be a multiple of 64 (128 for fp8)");
+  const int n_out = act ? N / 2 : N;
+  gemm_launch_impl(a, K, b, bias, nullptr, c, n_out, R, N, K, act, stream, nullptr, a_scale, w_scale, a_scale ? N : 0, tile_expert,
+                   n_experts);
 }
 
 // W8A8 fp8-e4m3 GEMM: a [M, K] fp8 with per-row scale, b [N, K] fp8 with per-channel (w_scale_n == N) or per-tensor (1) scale

@@ -323,8 +323,23 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
         stats["moe_decode"] += 1
         return _C().moe_decode(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(),
                                topk_i.to(torch.int32).contiguous(), int(expert_offset))
+    # prefill-sized batches: device-side permutation + grouped tcgen05 GEMMs (static shapes: replays under CUDA graphs)
+    if (_use_cuda(x) and _MOE_GROUPED and x.dtype == torch.bfloat16 and w_gate_up.dtype == x.dtype and w_down.dtype == x.dtype
+            and act in _MOE_ACTS and act_fn is None and topk_i.dim() == 2 and topk_i.shape[1] <= 64
+            and w_gate_up.is_contiguous() and w_down.is_contiguous() and x.shape[1] % 64 == 0 and w_down.shape[2] % 64 == 0
+            and w_gate_up.shape[0] <= 512
+            and (gate_up_bias is None or gate_up_bias.dtype == x.dtype) and (down_bias is None or down_bias.dtype == x.dtype)):
+        stats["moe_grouped"] += 1
+        return _C().moe_grouped(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(), topk_i.to(torch.int32).contiguous(),
+                                int(expert_offset), _MOE_ACTS[act], bool(scale_input),
+                                None if gate_up_bias is None else gate_up_bias.contiguous(),
+                                None if down_bias is None else down_bias.contiguous())
     return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias,
                            act_fn, scale_input)
+
+
+_MOE_GROUPED = os.environ.get("NXDI_B200_MOE_GROUPED", "1") == "1"
+_MOE_ACTS = {"silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
 
 
 def rmsnorm_quant(x, weight, eps, clamp=float("inf"), offset: float = 0.0):
