@@ -171,11 +171,14 @@ def measure(app, batch, ctx, steps, warmup, n_ttft=9):
         tok = app(pin_ids, position_ids=pin_pos).tokens.cpu()
         pos += 1
 
+    hist = []
+
     def e2e_loop():
         nonlocal tok, pos
         for _ in range(steps):
             pin_ids.copy_(tok.view(batch, 1)); pin_pos.copy_(pos)
             tok = app(pin_ids, position_ids=pin_pos).tokens.cpu()   # D2H read of the step result
+            hist.append(tok.view(-1).clone())
             pos += 1
     if os.environ.get("NXDI_BENCH_PROFILE_E2E"):
         import cProfile, pstats
@@ -185,7 +188,85 @@ def measure(app, batch, ctx, steps, warmup, n_ttft=9):
     h2d = pin_ids.numel() * 8 + pin_pos.numel() * 4 + batch * 4 + batch * 12  # ids, positions, seq_ids, sampling params
     d2h = batch * 8
     return dict(ms_per_step=ms / steps, ttft_p50_ms=ttft[len(ttft) // 2], e2e_ms_per_step=e2e_ms / steps,
-                launches_per_step=per_step, h2d=h2d, d2h=d2h)
+                launches_per_step=per_step, h2d=h2d, d2h=d2h, checksum=token_checksum(torch.stack(hist[-steps:], 1)))
+
+
+def token_checksum(tokens):
+    """sha1 of the greedy token ids of the timed e2e decode + whether every rank produced the same ids (tensor-parallel
+    ranks sample from identical gathered logits: any divergence means a broken collective)."""
+    import hashlib
+    import torch.distributed as dist
+    h = hashlib.sha1(tokens.to("cpu").long().contiguous().numpy().tobytes()).hexdigest()[:16]
+    agree = True
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        allh = [None] * dist.get_world_size()
+        dist.all_gather_object(allh, h)
+        agree = all(x == allh[0] for x in allh)
+    return {"sha1_16": h, "n_tokens": int(tokens.numel()), "ranks_agree": agree,
+            "distinct_tokens": int(tokens.unique().numel())}
+
+
+# ---- the other BASELINE.json configs (bench.py --config ...): same JSON line, measured through the public generate() API ----
+DBRX_1L = dict(d_model=6144, n_heads=48, n_layers=1, max_seq_len=32768, vocab_size=100352,
+               attn_config=dict(kv_n_heads=8, clip_qkv=8.0, rope_theta=500000.0),
+               ffn_config=dict(ffn_hidden_size=10752, moe_num_experts=16, moe_top_k=4, hidden_size=6144))
+LLAMA2_7B = dict(hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=32,
+                 head_dim=128, vocab_size=32000, max_position_embeddings=4096, rms_norm_eps=1e-5, rope_theta=10000.0)
+OPEN_LLAMA_7B = dict(LLAMA2_7B, max_position_embeddings=2048, rms_norm_eps=1e-6)
+OPEN_LLAMA_3B = dict(hidden_size=3200, intermediate_size=8640, num_hidden_layers=26, num_attention_heads=32, num_key_value_heads=32,
+                     head_dim=100)
+
+
+def build_config_app(name, tp, batch, seq_len, ctx):
+    from neuronx_distributed_inference_b200.config import OnDeviceSamplingConfig
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    common = dict(batch_size=batch, seq_len=seq_len, max_context_length=ctx, device="cuda", tp_degree=tp, dtype="bfloat16",
+                  skip_warmup=True, enable_bucketing=True, on_device_sampling_config=OnDeviceSamplingConfig(top_k=1))
+    if name == "dbrx":
+        from neuronx_distributed_inference_b200.models.dbrx.modeling_dbrx import NeuronDbrxForCausalLM
+        return build_random_llama(DBRX_1L, app_cls=NeuronDbrxForCausalLM, **common), \
+            "DBRX (1 of 40 layers as in the reference's integration config, 16 experts top-4, random-init)"
+    if name == "quant":
+        return build_random_llama(LLAMA2_7B, quantized=True, quantization_dtype="f8e4m3", quantization_type="per_channel_symmetric",
+                                  **common), "Llama-2-7b (32 layers, per-channel-symmetric fp8-e4m3 weights, random-init)"
+    if name == "spec":
+        return build_random_llama(OPEN_LLAMA_7B, speculation_length=5, enable_fused_speculation=True,
+                                  fused_draft=dict(hf=OPEN_LLAMA_3B, neuron={}), **common), \
+            "open_llama_7b target + open_llama_3b draft (fused speculation, k=5, random-init: acceptance is chance level)"
+    raise KeyError(name)
+
+
+def measure_generate(app, batch, ctx, steps, warmup, n_ttft=5):
+    """TTFT + tokens/s of ``HuggingFaceGenerationAdapter.generate`` (prompt on the host, sequences read back to the host)."""
+    import torch
+    from neuronx_distributed_inference_b200 import ops
+    from neuronx_distributed_inference_b200.utils.hf_adapter import HuggingFaceGenerationAdapter
+    prompt = torch.randint(1, 100, (batch, ctx))
+    mask = torch.ones_like(prompt)
+    ttft = []
+    for i in range(n_ttft + 2):
+        app.reset()
+        ms = device_time_ms(lambda: app(prompt, attention_mask=mask.int()))
+        if i >= 2:
+            ttft.append(ms)
+    ttft.sort()
+    ad = HuggingFaceGenerationAdapter(app)
+    for _ in range(max(1, warmup // 4)):
+        app.reset()
+        ad.generate(prompt, attention_mask=mask, max_new_tokens=steps)
+    s0 = sum(ops.stats.values())
+    out = {}
+
+    def run():
+        app.reset()
+        out["o"] = ad.generate(prompt, attention_mask=mask, max_new_tokens=steps, return_dict_in_generate=True)
+    ms = device_time_ms(run)
+    launches = sum(ops.stats.values()) - s0
+    seq = out["o"].sequences
+    new = seq[:, ctx:]
+    stats = getattr(out["o"], "speculation_stats", None)
+    return dict(ms_total=ms, new_tokens=int(new.shape[1]), ttft_p50_ms=ttft[len(ttft) // 2], launches=launches,
+                checksum=token_checksum(new), speculation_stats=stats, h2d=prompt.numel() * 8 + mask.numel() * 8, d2h=seq.numel() * 8)
 
 
 def ci_harness(app, batch, ctx, seq_len, n_runs=5, output_logits=False):
@@ -242,6 +323,9 @@ def main():
     ap.add_argument("--ctx", type=int, default=128)
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--skip-ci", action="store_true")
+    ap.add_argument("--config", default="llama8b", choices=["llama8b", "dbrx", "quant", "spec"],
+                    help="BASELINE.json config: llama8b (headline, default), dbrx (1-layer MoE), quant (Llama-2-7b fp8), "
+                         "spec (open_llama 7b + 3b draft)")
     ap.add_argument("--shard-shapes", type=int, default=1,
                     help="DIAGNOSTIC (1 GPU): run the per-rank shapes of TP=N without the collectives (compute-only share of a TP step)")
     args = ap.parse_args()
@@ -266,6 +350,8 @@ def main():
     load_extension()
 
     seq_len = args.ctx + args.steps + args.warmup + 8
+    if args.config != "llama8b":
+        return run_other_config(args, rank, real_stdout, seq_len)
     cfg = dict(LLAMA31_8B, num_hidden_layers=args.layers)
     if args.shard_shapes > 1:
         n = args.shard_shapes
@@ -318,6 +404,7 @@ def main():
                 "CUDA-graph replay, D2H tokens) per step"},
         "gpu_launches": int(m["launches_per_step"] * args.steps),
         "gpu_launches_per_step": int(m["launches_per_step"]),
+        "greedy_checksum": m["checksum"],
         "clocks": clocks,
     }
     if ci is not None:
@@ -325,6 +412,41 @@ def main():
     if rank == 0:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    if dist.is_initialized():
+        dist.barrier()
+        _hard_exit()
+    return 0
+
+
+def run_other_config(args, rank, real_stdout, seq_len):
+    import torch
+    import torch.distributed as dist
+    seq_len = max(seq_len, args.ctx + 6 * (args.steps + 8))      # room for the speculation windows
+    app, desc = build_config_app(args.config, args.gpus, args.batch, seq_len, args.ctx)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    m = measure_generate(app, args.batch, args.ctx, args.steps, args.warmup)
+    clocks = sampler.stop()
+    decode_ms = max(m["ms_total"] - m["ttft_p50_ms"], 1e-3)
+    tok_s = args.batch * m["new_tokens"] * 1e3 / decode_ms
+    e2e_tok_s = args.batch * m["new_tokens"] * 1e3 / m["ms_total"]
+    out = {"metric": f"{args.config}_generate_decode_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
+           "steps": m["new_tokens"], "warmup": args.warmup, "ms_per_step": decode_ms / max(1, m["new_tokens"]), "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.config != "quant" else "bf16 activations, fp8-e4m3 weights",
+           "data": "synthetic", "impl": "ours", "ttft_p50_ms": m["ttft_p50_ms"],
+           "config": {"model": desc, "global_batch": args.batch, "seq_len": seq_len, "prompt_len": args.ctx,
+                      "parallelism": f"tp{args.gpus}", "sampling": "on-device greedy (top_k=1)",
+                      "timing": "device events around HuggingFaceGenerationAdapter.generate (prefill + decode loop, host-resident "
+                                "prompt and result); value = new tokens / (total - p50 TTFT)",
+                      "l2_policy": "inputs larger than L2: every step streams all weight shards; no explicit flush"},
+           "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": m["h2d"] / max(1, m["new_tokens"]),
+                   "d2h_bytes_per_step": m["d2h"] / max(1, m["new_tokens"]), "ms_total": m["ms_total"],
+                   "path": "HuggingFaceGenerationAdapter.generate"},
+           "gpu_launches": int(m["launches"]), "greedy_checksum": m["checksum"], "speculation_stats": m["speculation_stats"],
+           "clocks": clocks}
+    if rank == 0:
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out, default=str) + "\n").encode())
     if dist.is_initialized():
         dist.barrier()
         _hard_exit()

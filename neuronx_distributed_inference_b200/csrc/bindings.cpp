@@ -1,5 +1,6 @@
 // pybind11 surface of the sm_100a extension (neuronx_distributed_inference_b200._C).  Compiled by the host
 // compiler; the CUDA translation units expose raw-pointer launchers (api.h).
+#include <limits>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -214,12 +215,27 @@ at::Tensor moe_decode(const at::Tensor& x, const at::Tensor& w_gate_up, const at
 // act: 1 silu*up, 2 gelu_tanh*up, 3 gelu*up.  gate_up_bias [E, 2I] / down_bias [E, H] optional (bf16).
 at::Tensor moe_grouped(const at::Tensor& x, const at::Tensor& w_gate_up, const at::Tensor& w_down, const at::Tensor& topk_w,
                        const at::Tensor& topk_i, int64_t expert_offset, int64_t act, bool scale_input,
-                       const c10::optional<at::Tensor>& gate_up_bias, const c10::optional<at::Tensor>& down_bias) {
-  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && is_bf16(x) && is_bf16(w_gate_up) && is_bf16(w_down));
+                       const c10::optional<at::Tensor>& gate_up_bias, const c10::optional<at::Tensor>& down_bias,
+                       const c10::optional<at::Tensor>& gate_up_scale, const c10::optional<at::Tensor>& down_scale) {
+  // W8A8 experts: fp8-e4m3 weights with per-(expert, channel) scales; the permuted activations and the intermediate are quantised
+  // per row (quant.cu) and both grouped GEMMs run on the kind::f8f6f4 tensor-core path
+  const bool fp8 = gate_up_scale.has_value();
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && is_bf16(x));
+  if (fp8) {
+    TORCH_CHECK(w_gate_up.scalar_type() == at::kFloat8_e4m3fn && w_down.scalar_type() == at::kFloat8_e4m3fn && down_scale.has_value());
+    TORCH_CHECK(gate_up_scale->scalar_type() == at::kFloat && gate_up_scale->is_contiguous() && down_scale->scalar_type() == at::kFloat &&
+                down_scale->is_contiguous());
+  } else {
+    TORCH_CHECK(is_bf16(w_gate_up) && is_bf16(w_down));
+  }
   TORCH_CHECK(w_gate_up.dim() == 3 && w_down.dim() == 3 && w_gate_up.is_contiguous() && w_down.is_contiguous());
   const int N = x.size(0), H = x.size(1), E = w_gate_up.size(0), I = w_gate_up.size(1) / 2, k = topk_i.size(1);
   TORCH_CHECK(w_gate_up.size(2) == H && w_down.size(0) == E && w_down.size(1) == H && w_down.size(2) == I);
   TORCH_CHECK(H % 64 == 0 && I % 64 == 0, "moe_grouped: hidden and intermediate sizes must be multiples of 64");
+  if (fp8) {
+    TORCH_CHECK(H % 128 == 0 && I % 128 == 0 && H <= 16384 && I <= 16384, "moe_grouped (fp8): sizes must be multiples of 128, <= 16384");
+    TORCH_CHECK(gate_up_scale->numel() == (int64_t)E * 2 * I && down_scale->numel() == (int64_t)E * H);
+  }
   TORCH_CHECK(topk_w.scalar_type() == at::kFloat && topk_i.scalar_type() == at::kInt && topk_w.is_contiguous() &&
               topk_i.is_contiguous() && topk_w.numel() == (int64_t)N * k && topk_i.size(0) == N);
   if (gate_up_bias) TORCH_CHECK(is_bf16(*gate_up_bias) && gate_up_bias->is_contiguous() && gate_up_bias->numel() == (int64_t)E * 2 * I);
@@ -239,10 +255,23 @@ at::Tensor moe_grouped(const at::Tensor& x, const at::Tensor& w_gate_up, const a
                   tile_expert.data_ptr<int>(), st);
   moe_gather_launch(x.data_ptr(), topk_w.data_ptr<float>(), row_entry.data_ptr<int>(), tile_expert.data_ptr<int>(), xp.data_ptr(), (int)R,
                     H, k, scale_input ? 1 : 0, st);
-  gemm_grouped_launch(xp.data_ptr(), w_gate_up.data_ptr(), gate_up_bias ? gate_up_bias->data_ptr() : nullptr, h.data_ptr(), (int)R, 2 * I,
-                      H, E, (int)act, tile_expert.data_ptr<int>(), nullptr, nullptr, st);
-  gemm_grouped_launch(h.data_ptr(), w_down.data_ptr(), down_bias ? down_bias->data_ptr() : nullptr, y.data_ptr(), (int)R, H, I, E, 0,
-                      tile_expert.data_ptr<int>(), nullptr, nullptr, st);
+  const float inf = std::numeric_limits<float>::infinity();
+  if (fp8) {
+    auto bopt = x.options().dtype(at::kByte);
+    auto xq = at::empty({R, H}, bopt), hq = at::empty({R, I}, bopt);
+    auto xs = at::empty({R}, x.options().dtype(at::kFloat)), hs = at::empty({R}, x.options().dtype(at::kFloat));
+    rmsnorm_quant_launch(xp.data_ptr(), nullptr, xq.data_ptr(), xs.data_ptr<float>(), (int)R, H, 0.f, 0.f, inf, st);
+    gemm_grouped_launch(xq.data_ptr(), w_gate_up.data_ptr(), gate_up_bias ? gate_up_bias->data_ptr() : nullptr, h.data_ptr(), (int)R, 2 * I,
+                        H, E, (int)act, tile_expert.data_ptr<int>(), xs.data_ptr<float>(), gate_up_scale->data_ptr<float>(), st);
+    rmsnorm_quant_launch(h.data_ptr(), nullptr, hq.data_ptr(), hs.data_ptr<float>(), (int)R, I, 0.f, 0.f, inf, st);
+    gemm_grouped_launch(hq.data_ptr(), w_down.data_ptr(), down_bias ? down_bias->data_ptr() : nullptr, y.data_ptr(), (int)R, H, I, E, 0,
+                        tile_expert.data_ptr<int>(), hs.data_ptr<float>(), down_scale->data_ptr<float>(), st);
+  } else {
+    gemm_grouped_launch(xp.data_ptr(), w_gate_up.data_ptr(), gate_up_bias ? gate_up_bias->data_ptr() : nullptr, h.data_ptr(), (int)R,
+                        2 * I, H, E, (int)act, tile_expert.data_ptr<int>(), nullptr, nullptr, st);
+    gemm_grouped_launch(h.data_ptr(), w_down.data_ptr(), down_bias ? down_bias->data_ptr() : nullptr, y.data_ptr(), (int)R, H, I, E, 0,
+                        tile_expert.data_ptr<int>(), nullptr, nullptr, st);
+  }
   moe_combine_launch(y.data_ptr(), topk_w.data_ptr<float>(), pos.data_ptr<int>(), out.data_ptr(), N, H, k, scale_input ? 1 : 0, st);
   return out;
 }

@@ -242,8 +242,9 @@ def maybe_graph_step(owner, fn, example_inputs, n_outputs: int, key):
     import os
     dev = example_inputs[0].device
     tm = getattr(owner, "target_model", None)
+    dm = getattr(owner, "draft_model", None)      # a draft on the PyTorch composite path (odd head_dim, ...) is not capturable either
     if (dev.type != "cuda" or os.environ.get("NXDI_B200_SPEC_GRAPH", "1") == "0" or tm is None or not getattr(tm, "graph_safe", False)
-            or not tm.neuron_config.cuda_graphs):
+            or not tm.neuron_config.cuda_graphs or (dm is not None and not getattr(dm, "graph_safe", True))):
         return fn
     cache = owner.__dict__.setdefault("_graphed_steps", {})
     if key not in cache:

@@ -44,6 +44,12 @@ def _as_dict(x):
 
 
 class DbrxBlock(nn.Module):
+    mlp_is_moe = True
+
+    @property
+    def mlp(self):
+        return self.ffn
+
     def __init__(self, config, i, rotary, device=None):
         super().__init__()
         dt = config.neuron_config.torch_dtype

@@ -108,6 +108,17 @@ class NeuronBaseModel(nn.Module):
                 return False
         return True
 
+    def _moe_kernels_cover_prefill(self) -> bool:
+        """Routed experts of a prefill-sized batch run through the device-side permutation + grouped tcgen05 GEMMs
+        (ops.moe_experts -> csrc/moe_grouped.cu): static shapes, no host sync -> context encoding may be graph-captured."""
+        if not self._moe_kernels_cover_decode():
+            return False
+        for layer in self.layers:
+            ex = getattr(getattr(layer, "mlp", None), "expert_mlps", None) if getattr(layer, "mlp_is_moe", False) else None
+            if ex is not None and (ex.gate_up_proj.shape[2] % 64 != 0 or ex.down_proj.shape[2] % 64 != 0 or ex.gate_up_proj.shape[0] > 512):
+                return False
+        return True
+
     def _kernels_cover_decode(self) -> bool:
         nc = self.neuron_config
         if nc.torch_dtype != torch.bfloat16 or nc.kv_cache_quant:

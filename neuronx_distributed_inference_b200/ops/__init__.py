@@ -313,7 +313,21 @@ def moe_route(router_logits, top_k, act="softmax", normalize=True, act_over_topk
 def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_offset=0,
                 gate_up_bias=None, down_bias=None, act_fn=None, scale_input=False, gate_up_scale=None, down_scale=None):
     N = x.shape[0]
-    if gate_up_scale is not None or down_scale is not None:      # 8-bit experts: dequantise the selected experts on the fly
+    if gate_up_scale is not None or down_scale is not None:
+        # fp8 experts with dynamic activation quantisation asked for: W8A8 grouped GEMMs on the kind::f8f6f4 tensor-core path
+        if (_use_cuda(x) and _MOE_GROUPED and _ACT_QUANT and N > GEMV_MAX_TOKENS and x.dtype == torch.bfloat16 and act in _MOE_ACTS
+                and w_gate_up.dtype == torch.float8_e4m3fn and w_down.dtype == torch.float8_e4m3fn and act_fn is None
+                and gate_up_scale is not None and down_scale is not None and gate_up_scale.dim() == 2 and down_scale.dim() == 2
+                and x.shape[1] % 128 == 0 and w_down.shape[2] % 128 == 0 and max(x.shape[1], w_down.shape[2]) <= 16384
+                and topk_i.dim() == 2 and topk_i.shape[1] <= 64 and w_gate_up.shape[0] <= 512
+                and (gate_up_bias is None or gate_up_bias.dtype == x.dtype) and (down_bias is None or down_bias.dtype == x.dtype)):
+            stats["moe_grouped_fp8"] += 1
+            return _C().moe_grouped(x.contiguous(), w_gate_up.contiguous(), w_down.contiguous(), topk_w.float().contiguous(),
+                                    topk_i.to(torch.int32).contiguous(), int(expert_offset), _MOE_ACTS[act], bool(scale_input),
+                                    None if gate_up_bias is None else gate_up_bias.contiguous(),
+                                    None if down_bias is None else down_bias.contiguous(),
+                                    gate_up_scale.float().contiguous(), down_scale.float().contiguous())
+        # weight-only 8-bit experts: dequantise the selected experts on the fly
         return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias, act_fn, scale_input,
                                gate_up_scale, down_scale)
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and w_gate_up.dtype == x.dtype and act == "silu_mul"
@@ -333,7 +347,7 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
         return _C().moe_grouped(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(), topk_i.to(torch.int32).contiguous(),
                                 int(expert_offset), _MOE_ACTS[act], bool(scale_input),
                                 None if gate_up_bias is None else gate_up_bias.contiguous(),
-                                None if down_bias is None else down_bias.contiguous())
+                                None if down_bias is None else down_bias.contiguous(), None, None)
     return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias,
                            act_fn, scale_input)
 

@@ -69,8 +69,10 @@ class SubModelRunner:
                                    and nc.torch_dtype == torch.bfloat16 and not nc.is_block_kv_layout and not nc.is_prefix_caching
                                    and os.environ.get("NXDI_B200_PREFILL_GRAPHS", "1") != "0"
                                    and hasattr(model, "_kernels_cover_decode") and model._kernels_cover_decode()
-                                   # MoE prefill dispatches tokens to experts with data-dependent shapes
-                                   and not any(getattr(l, "mlp_is_moe", False) for l in getattr(model, "layers", [])))
+                                   # MoE prefill: only when the routed experts take the grouped-GEMM path (static shapes);
+                                   # the PyTorch dispatch has data-dependent shapes
+                                   and (not any(getattr(l, "mlp_is_moe", False) for l in getattr(model, "layers", []))
+                                        or (hasattr(model, "_moe_kernels_cover_prefill") and model._moe_kernels_cover_prefill())))
         self._prefill_pool = None
         self._graphs: Dict[Tuple, _Graph] = {}
         self.pad_token_id = getattr(config, "pad_token_id", None) or nc.pad_token_id or 0

@@ -308,6 +308,47 @@ def test_moe_grouped_gemm_matches_reference(N, k, E, H, I, off, act, bias, scale
     assert err2 <= 0.02 * exp2.float().abs().max().item() + 0.02, err2
 
 
+def test_moe_grouped_fp8_experts_w8a8():
+    """fp8 expert banks + dynamic per-row activation quantisation through the grouped kind::f8f6f4 GEMMs == the same math in fp32."""
+    torch.manual_seed(0)
+    dev, dt = "cuda", torch.bfloat16
+    N, k, E, H, I = 600, 2, 8, 1024, 512
+    x = torch.randn(N, H, device=dev, dtype=dt)
+    wgu = torch.randn(E, 2 * I, H, device=dev) * 0.03
+    wd = torch.randn(E, H, I, device=dev) * 0.03
+    gs = wgu.abs().amax(-1) / 448.0
+    ds = wd.abs().amax(-1) / 448.0
+    wgu_q = (wgu / gs.unsqueeze(-1)).to(torch.float8_e4m3fn)
+    wd_q = (wd / ds.unsqueeze(-1)).to(torch.float8_e4m3fn)
+    idx = torch.rand(N, E, device=dev).topk(k, dim=-1).indices
+    w = torch.rand(N, k, device=dev)
+    ops.set_activation_quant(True)
+    try:
+        before = ops.stats["moe_grouped_fp8"]
+        got = ops.moe_experts(x, wgu_q, wd_q, w, idx, "silu_mul", 0, None, None, None, False, gs, ds)
+        assert ops.stats["moe_grouped_fp8"] == before + 1
+    finally:
+        ops.set_activation_quant(False)
+    # reference: quantise the activations the same way (per row, e4m3), accumulate in fp32
+    def q8(t):
+        s_ = t.float().abs().amax(-1, keepdim=True).clamp_min(1e-12) / 448.0
+        return (t.float() / s_).to(torch.float8_e4m3fn).float() * s_
+    out = torch.zeros(N, H, device=dev)
+    for e in range(E):
+        sel = idx == e
+        tok = sel.any(-1).nonzero().flatten()
+        if tok.numel() == 0:
+            continue
+        wt = (w * sel).sum(-1)[tok]
+        hh = q8(x[tok]) @ (wgu_q[e].float() * gs[e].unsqueeze(-1)).t()
+        g_, u_ = hh.chunk(2, -1)
+        hh = (torch.nn.functional.silu(g_) * u_).to(dt)
+        yy = (q8(hh) @ (wd_q[e].float() * ds[e].unsqueeze(-1)).t()).to(dt).float()
+        out[tok] += yy * wt.unsqueeze(-1)
+    err = (got.float() - out).abs().max().item()
+    assert err <= 0.03 * out.abs().max().item() + 0.03, err
+
+
 @pytest.mark.parametrize("wdtype", [torch.int8, torch.float8_e4m3fn])
 @pytest.mark.parametrize("T,N,K,act,norm,res,per_tensor", [(2, 4096, 4096, None, True, False, False), (1, 6144, 4096, None, False, True, False),
                                                            (8, 2048, 14336, None, False, True, True), (4, 7168, 4096, "silu_mul", True, False, False),
