@@ -263,6 +263,15 @@ def measure_generate(app, batch, ctx, steps, warmup, n_ttft=5):
     ms = device_time_ms(run)
     launches = sum(ops.stats.values()) - s0
     seq = out["o"].sequences
+    # decode replays CUDA graphs (no Python-level dispatch to count): count the kernels of ONE eager decode step instead
+    try:
+        s1 = sum(ops.stats.values())
+        with torch.no_grad():
+            app.model(seq[:, -1:].to(app.device), None, torch.full((batch, 1), seq.shape[1] - 1, dtype=torch.int32, device=app.device),
+                      torch.arange(batch, dtype=torch.int32, device=app.device), None, is_prefill=False)
+        launches = max(launches, (sum(ops.stats.values()) - s1) * int(seq.shape[1] - ctx))
+    except Exception:
+        pass
     new = seq[:, ctx:]
     stats = getattr(out["o"], "speculation_stats", None)
     return dict(ms_total=ms, new_tokens=int(new.shape[1]), ttft_p50_ms=ttft[len(ttft) // 2], launches=launches,

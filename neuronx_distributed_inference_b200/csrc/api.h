@@ -24,7 +24,8 @@ struct GemvParams {
   const void* bias;      // [N] bf16 or null
   const void* norm_w;    // [K] bf16 or null (fused RMSNorm of x)
   const void* residual;  // [T, N] bf16 or null
-  const float* scale;    // [N] fp32 per-output-channel dequant scale or null
+  const float* scale;    // [N] (or [1]) fp32 dequant scale of 8-bit weights, or null
+  int scale_n;           // numel of `scale`
   void* y;               // [T, N_out] bf16
   int T, N, K, ldx, ldy;
   float eps, norm_offset;
@@ -37,9 +38,9 @@ struct GemvParams {
 size_t gemv_smem_bytes(int T, int K, bool x_in_smem);
 void gemv_launch(const GemvParams& p, int mode, cudaStream_t stream);  // mode 0 plain, 1 fused all-reduce
 // v2: bulk-async pipelined, stream-K balanced (gemv2.cu)
-bool gemv2_supported(int T, int K);
-int gemv2_grid(int N, int K, bool glu);
-int gemv2_pmax(int N, int K, bool glu);
+bool gemv2_supported(int T, int K, int wt = 0);   // wt: 0 bf16 weights, 1 int8, 2 fp8-e4m3 (weight-only)
+int gemv2_grid(int N, int K, bool glu, int wt = 0);
+int gemv2_pmax(int N, int K, bool glu, int wt = 0);
 int gemv2_ntiles(int N, bool glu);
 void gemv2_plan(int N, int K, bool glu, int* rows8, int* whole, int* grid, int* pmax);
 int pick_nsplit(int B, int Hkv, int S_hint);
@@ -139,6 +140,7 @@ void attention_prefill_tc_launch(const void* q, const void* k, const void* v, vo
 // W8A8 fp8 path: dynamic per-token activation quantisation (quant.cu) + tcgen05 kind::f8f6f4 GEMM (gemm_tcgen05.cu)
 void rmsnorm_quant_launch(const void* x, const void* gamma, void* q, float* scale, int rows, int H, float eps, float offset, float clamp,
                           cudaStream_t stream);
+void dequant_bf16_launch(const void* w, int wdtype, const float* scale, int scale_n, void* out, int N, int K, cudaStream_t stream);
 void gemm_fp8_launch(const void* a, int lda, const void* b, const float* a_scale, const float* w_scale, int w_scale_n, const void* bias,
                      const void* residual, void* c, int ldc, int M, int N, int K, int act, cudaStream_t stream);
 

@@ -45,20 +45,20 @@ struct Scratch {
 };
 static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t nt);
 
-static bool use_gemv2(int T, int K) { return gemv2_supported(T, K); }
-
 static void run_gemv(GemvParams& p, int mode, const at::Device& dev) {
-  if (use_gemv2(p.T, p.K) && p.x_in_smem) {
+  const int wt = p.scale != nullptr ? p.wdtype : 0;
+  if (gemv2_supported(p.T, p.K, wt) && p.x_in_smem) {
     auto& s = scratch(dev, 0, 0, 0);
     const bool glu = p.act != 0;
     const int n_tiles = gemv2_ntiles(p.N, glu);
-    const int64_t need = (int64_t)n_tiles * gemv2_pmax(p.N, p.K, glu) * 128;
+    const int64_t need = (int64_t)n_tiles * gemv2_pmax(p.N, p.K, glu, wt) * 128;
     auto o = at::TensorOptions().device(dev);
     if (!s.gemv_ws.defined() || s.gemv_ws.numel() < need) s.gemv_ws = at::empty({std::max<int64_t>(need, 4 << 20)}, o.dtype(at::kFloat));
     if (!s.gemv_tickets.defined() || s.gemv_tickets.numel() < n_tiles)
       s.gemv_tickets = at::zeros({std::max<int64_t>(n_tiles, 1 << 15)}, o.dtype(at::kInt));
     gemv2_launch(p, mode, s.gemv_ws.data_ptr<float>(), reinterpret_cast<unsigned*>(s.gemv_tickets.data_ptr<int>()), cur_stream());
   } else {
+    TORCH_CHECK(wt == 0, "gemv: 8-bit weights need the TMA streaming kernel");
     TORCH_CHECK(p.K % 256 == 0, "gemv: K must be a multiple of 256 on the wide-activation fallback");
     gemv_launch(p, mode, cur_stream());
   }
@@ -75,6 +75,7 @@ static void fill_params(GemvParams& p, const at::Tensor& x, const at::Tensor& w,
   p.norm_w = x_in_smem ? optr(norm_w) : nullptr;
   p.residual = optr(residual);
   p.scale = scale.has_value() ? scale->data_ptr<float>() : nullptr;
+  p.scale_n = scale.has_value() ? (int)scale->numel() : 0;
   p.y = y.data_ptr();
   p.T = x.size(0);
   p.K = x.size(1);
@@ -117,6 +118,14 @@ at::Tensor gemv(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
     const bool glu = act != 0;
     auto y = at::empty({x.size(0), glu ? N / 2 : N}, x.options());
     if (residual.has_value()) TORCH_CHECK(!glu && residual->is_contiguous() && residual->size(1) == N && is_bf16(*residual));
+    // the TMA-streamed kernel (same ring as bf16, bytes expanded in registers) whenever the shapes allow it
+    static const bool q2 = []() { const char* e = getenv("NXDI_B200_QGEMV2"); return e == nullptr || atoi(e) != 0; }();
+    if (q2 && gemv2_supported((int)x.size(0), (int)x.size(1), i8 ? 1 : 2) && x.stride(0) % 8 == 0 && (!glu || N % 2 == 0)) {
+      GemvParams p{};
+      fill_params(p, x, w, bias, norm_w, eps, offset, (int)act, residual, scale, y, true);
+      run_gemv(p, 0, x.device());
+      return y;
+    }
     static int n_sms = 0;
     if (n_sms == 0) n_sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
     qgemv_launch(x.data_ptr(), w.data_ptr(), scale->data_ptr<float>(), (int)scale->numel(), optr(bias), optr(norm_w), optr(residual),
@@ -164,12 +173,22 @@ at::Tensor gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at
 // Row-parallel GEMV -> one-shot all-reduce over NVLink peer buffers -> +bias +residual.  ONE kernel.
 at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                           const c10::optional<at::Tensor>& residual, const std::vector<int64_t>& recv_ptrs,
-                          const at::Tensor& step, int64_t rank, int64_t parity, int64_t call, int64_t n_max) {
-  check_gemv_inputs(x, w);
+                          const at::Tensor& step, int64_t rank, int64_t parity, int64_t call, int64_t n_max,
+                          const c10::optional<at::Tensor>& scale) {
+  int wt = 0;
+  if (scale.has_value()) {   // weight-only int8 / fp8 row-parallel layer
+    TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && is_bf16(x) && w.is_contiguous());
+    TORCH_CHECK(x.size(0) >= 1 && x.size(0) <= GEMV_MAX_T && x.stride(1) == 1 && x.stride(0) % 8 == 0);
+    wt = w.scalar_type() == at::kChar ? 1 : 2;
+    TORCH_CHECK(wt == 1 || w.scalar_type() == at::kFloat8_e4m3fn, "gemv_allreduce: int8 or float8_e4m3fn weights");
+    TORCH_CHECK(scale->scalar_type() == at::kFloat && scale->is_contiguous() && (scale->numel() == 1 || scale->numel() == w.size(0)));
+  } else {
+    check_gemv_inputs(x, w);
+  }
   const int world = recv_ptrs.size();
   TORCH_CHECK(world >= 2 && world <= SYMM_MAX_RANKS);
   TORCH_CHECK(step.is_cuda() && step.scalar_type() == at::kInt && step.numel() >= 1, "gemv_allreduce: step counter must be a CUDA int32 tensor");
-  TORCH_CHECK(gemv2_supported(x.size(0), x.size(1)), "gemv_allreduce: activations too wide for shared memory");
+  TORCH_CHECK(gemv2_supported(x.size(0), x.size(1), wt), "gemv_allreduce: activations too wide for shared memory");
   const int N = w.size(0);
   TORCH_CHECK(N <= n_max && (N + 15) / 16 <= SYMM_MAX_TILES, "gemv_allreduce: output too wide for the workspace");
   c10::cuda::CUDAGuard guard(x.device());
@@ -179,7 +198,7 @@ at::Tensor gemv_allreduce(const at::Tensor& x, const at::Tensor& w, const c10::o
   if (residual.has_value())
     TORCH_CHECK(residual->is_contiguous() && residual->size(0) == x.size(0) && residual->size(1) == N && is_bf16(*residual));
   GemvParams p{};
-  fill_params(p, xn, w, bias, c10::nullopt, 0, 0, 0, residual, c10::nullopt, y, x_in_smem);
+  fill_params(p, xn, w, bias, c10::nullopt, 0, 0, 0, residual, scale, y, x_in_smem);
   for (int i = 0; i < world; ++i) p.symm.recv[i] = reinterpret_cast<float*>(recv_ptrs[i]);
   p.symm.step = reinterpret_cast<const uint32_t*>(step.data_ptr<int>());
   p.symm.rank = rank;
@@ -209,6 +228,19 @@ at::Tensor moe_decode(const at::Tensor& x, const at::Tensor& w_gate_up, const at
   moe_decode_launch(x.data_ptr(), w_gate_up.data_ptr(), w_down.data_ptr(), topk_w.data_ptr<float>(), topk_i.data_ptr<int>(),
                     u.data_ptr(), y.data_ptr<float>(), T, k, H, I, E, (int)expert_offset, n_sms, cur_stream());
   return y.to(x.scalar_type());
+}
+
+// int8 / fp8 weight [N, K] x scale -> bf16 into `out` (a caller-owned scratch: one buffer serves every layer of a model)
+at::Tensor dequant_bf16(const at::Tensor& w, const at::Tensor& scale, at::Tensor out) {
+  TORCH_CHECK(w.is_cuda() && w.dim() == 2 && w.is_contiguous() && scale.scalar_type() == at::kFloat && scale.is_contiguous());
+  const bool i8 = w.scalar_type() == at::kChar;
+  TORCH_CHECK(i8 || w.scalar_type() == at::kFloat8_e4m3fn, "dequant_bf16: int8 or float8_e4m3fn weights");
+  TORCH_CHECK(scale.numel() == 1 || scale.numel() == w.size(0));
+  TORCH_CHECK(out.is_cuda() && is_bf16(out) && out.is_contiguous() && out.numel() >= w.numel());
+  c10::cuda::CUDAGuard guard(w.device());
+  dequant_bf16_launch(w.data_ptr(), i8 ? 1 : 2, scale.data_ptr<float>(), (int)scale.numel(), out.data_ptr(), (int)w.size(0), (int)w.size(1),
+                      cur_stream());
+  return out.flatten().narrow(0, 0, w.numel()).view({w.size(0), w.size(1)});
 }
 
 // Routed experts of a prefill-sized batch (any N): permutation on the device + two grouped tcgen05 GEMMs + weighted combine.
@@ -680,9 +712,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     nxdi::gemv2_set_prof(reinterpret_cast<unsigned long long*>(buf->data_ptr<int64_t>()), buf->numel() / (148 * 8));
   });
   m.def("prof_count", []() { return (int64_t)nxdi::prof_count(); });
-  m.def("gemv2_supported", [](int64_t T, int64_t K) { return nxdi::gemv2_supported((int)T, (int)K); });
+  m.def("gemv2_supported", [](int64_t T, int64_t K, int64_t wt) { return nxdi::gemv2_supported((int)T, (int)K, (int)wt); },
+        pybind11::arg("T"), pybind11::arg("K"), pybind11::arg("wt") = 0);
   m.def("moe_decode", &nxdi::moe_decode);
   m.def("moe_grouped", &nxdi::moe_grouped);
+  m.def("dequant_bf16", &nxdi::dequant_bf16);
   m.def("gemm", &nxdi::gemm);
   m.def("symm_alloc", &nxdi::symm_alloc);
   m.def("symm_open", &nxdi::symm_open);

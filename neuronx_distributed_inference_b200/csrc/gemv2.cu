@@ -37,7 +37,7 @@ struct Gemv2Params {
   int max_inflight;
 };
 
-template <bool GLU, int MODE>
+template <bool GLU, int MODE, int WT>
 __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const __grid_constant__ Gemv2Params pp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const __grid_const
   __shared__ int s_flag;
   G2Smem sm;
   sm.NS = pp.n_stages;
-  const int Kp = (ph.K + G2_KC - 1) / G2_KC * G2_KC;
+  const int Kp = (ph.K + g2_kc(WT) - 1) / g2_kc(WT) * g2_kc(WT);
   sm.stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: keeps the address space
   sm.xs = sm.stage_base + (size_t)sm.NS * G2_STAGE_BYTES;
   sm.red = reinterpret_cast<float*>(sm.xs + (size_t)ph.T * (Kp * 2 + 64));
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemv2_kernel(const __grid_const
   }
   int stage = 0;
   uint32_t lap = 0, xph = 0;
-  g2_consume<GLU, MODE>(ph, pp.symm, sm, blockIdx.x, tid, stage, lap, xph, [] { pdl_wait(); });
+  g2_consume<GLU, MODE, WT>(ph, pp.symm, sm, blockIdx.x, tid, stage, lap, xph, [] { pdl_wait(); });
 }
 
 static int g2_num_sms() {
@@ -93,22 +93,22 @@ static int g2_num_sms() {
   return n;
 }
 
-static size_t g2_fixed_smem(int T, int K) {
-  const int Kp = (K + G2_KC - 1) / G2_KC * G2_KC;
+static size_t g2_fixed_smem(int T, int K, int wt = 0) {
+  const int Kp = (K + g2_kc(wt) - 1) / g2_kc(wt) * g2_kc(wt);
   return (size_t)T * (Kp * 2 + 64) + (G2_CONSUMER_WARPS * 128 + 64) * sizeof(float) + (2 * G2_MAX_STAGES + 1) * sizeof(uint64_t) +
          128 + 1024;  // + worst-case 1 KB alignment slack
 }
 
-bool gemv2_supported(int T, int K) {
-  return K % 64 == 0 && g2_fixed_smem(T, K) + 3 * G2_STAGE_BYTES <= G2_SMEM_BUDGET;
+bool gemv2_supported(int T, int K, int wt) {
+  return K % (wt ? 128 : 64) == 0 && g2_fixed_smem(T, K, wt) + 3 * G2_STAGE_BYTES <= G2_SMEM_BUDGET;
 }
 
 // Small weights: whole tiles per CTA (no cross-CTA fix-up).  Large weights: stream-K (perfect byte balance matters more).
 static bool g2_rows8(int N, bool glu) { return !glu && N % 8 == 0 && (N + 15) / 16 < 100; }
 static int g2_ntiles(int N, bool glu) { return glu ? ((N / 2) + 7) / 8 : (g2_rows8(N, glu) ? (N + 7) / 8 : (N + 15) / 16); }
-static double g2_tile_bytes(int N, int K, bool glu) { return (g2_rows8(N, glu) ? 8.0 : 16.0) * K * 2; }
+static double g2_tile_bytes(int N, int K, bool glu, int wt) { return (g2_rows8(N, glu) ? 8.0 : 16.0) * K * (wt ? 1 : 2); }
 
-static bool g2_whole_tiles(int N, int K, bool glu) {
+static bool g2_whole_tiles(int N, int K, bool glu, int wt = 0) {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("NXDI_B200_GEMV_WHOLE_TILES");
@@ -119,20 +119,20 @@ static bool g2_whole_tiles(int N, int K, bool glu) {
   const int sms = g2_num_sms();
   const int active = std::min(sms, n_tiles);
   const int per = (n_tiles + active - 1) / active;            // tiles of the busiest CTA
-  const double tile_bytes = g2_tile_bytes(N, K, glu);
+  const double tile_bytes = g2_tile_bytes(N, K, glu, wt);
   // one SM pulls at most ~100 GB/s; all of them together ~6 TB/s (bytes per microsecond below)
   const double bw_sm = std::min(100e3, 6.0e6 / active);
   const double t_whole = per * tile_bytes / bw_sm;
   // stream-K: perfectly balanced bytes + the fix-up (partials, ticket, re-read: ~3.5-4 us; tools/bench_gemv_fixed.py:
   // 4096x4096 11.1 -> 6.8 us, 1536x4096 10.4 -> 4.6 us once it is gone; Llama-8B decode 3.67 -> 3.19 ms/step)
-  const double t_streamk = (double)N * K * 2 / 6.0e6 + 4.0;
+  const double t_streamk = (double)N * K * (wt ? 1 : 2) / 6.0e6 + 4.0;
   return t_whole <= t_streamk + 0.5;
 }
 
-int gemv2_grid(int N, int K, bool glu) {
+int gemv2_grid(int N, int K, bool glu, int wt) {
   const int n_tiles = g2_ntiles(N, glu);
-  if (g2_whole_tiles(N, K, glu)) return std::min(g2_num_sms(), n_tiles);
-  const long long U = (long long)n_tiles * ((K + G2_KC - 1) / G2_KC);
+  if (g2_whole_tiles(N, K, glu, wt)) return std::min(g2_num_sms(), n_tiles);
+  const long long U = (long long)n_tiles * ((K + g2_kc(wt) - 1) / g2_kc(wt));
   return (int)std::min<long long>(g2_num_sms(), std::max<long long>(U / 2, 1));   // >= 32 KB of weights per CTA
 }
 
@@ -153,21 +153,21 @@ void gemv2_plan(int N, int K, bool glu, int* rows8, int* whole, int* grid, int* 
   *pmax = gemv2_grid(N, K, glu) / g2_ntiles(N, glu) + 3;
 }
 
-int gemv2_pmax(int N, int K, bool glu) {
+int gemv2_pmax(int N, int K, bool glu, int wt) {
   const int n_tiles = g2_ntiles(N, glu);
-  return gemv2_grid(N, K, glu) / n_tiles + 3;
+  return gemv2_grid(N, K, glu, wt) / n_tiles + 3;
 }
 
-template <bool GLU, int MODE>
+template <bool GLU, int MODE, int WT>
 static void launch_gemv2(const Gemv2Params& pp, cudaStream_t stream) {
-  auto kern = gemv2_kernel<GLU, MODE>;
+  auto kern = gemv2_kernel<GLU, MODE, WT>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BUDGET);
     configured = true;
   }
-  const size_t smem = g2_fixed_smem(pp.ph.T, pp.ph.K) + (size_t)pp.n_stages * G2_STAGE_BYTES;
-  const int grid = gemv2_grid(pp.ph.N, pp.ph.K, GLU);
+  const size_t smem = g2_fixed_smem(pp.ph.T, pp.ph.K, WT) + (size_t)pp.n_stages * G2_STAGE_BYTES;
+  const int grid = gemv2_grid(pp.ph.N, pp.ph.K, GLU, WT);
   launch_pdl(kern, dim3(grid), dim3(G2_THREADS), smem, stream, pp);
 }
 
@@ -189,12 +189,14 @@ static EncodeTiledFn encode_tiled() {
 // W [N, K] bf16 row-major as a 3-D tensor {64 k, N rows, K/64 groups} (strides 2 B, K*2 B, 128 B); box {64, rows, 8}:
 // one instruction fetches rows x 512 k, and the box lands in shared memory as [k group][row][64 k] — 128-byte lines whose
 // index & 7 is the row & 7, so the eight rows an LDS.128 phase touches sit in eight different swizzle positions.
-void make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K, int box_rows) {
-  cuuint64_t gdim[3] = {64, (cuuint64_t)N, (cuuint64_t)(K / 64)};
-  cuuint64_t gstride[2] = {(cuuint64_t)K * 2, 128};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)G2_KG};
+// (8-bit weights: {128 k, N rows, K/128 groups} of bytes — the same 128-byte lines, twice the k per stage)
+void make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K, int box_rows, int wt) {
+  const int line = wt ? 128 : 64, es = wt ? 1 : 2;
+  cuuint64_t gdim[3] = {(cuuint64_t)line, (cuuint64_t)N, (cuuint64_t)(K / line)};
+  cuuint64_t gstride[2] = {(cuuint64_t)K * es, 128};
+  cuuint32_t box[3] = {(cuuint32_t)line, (cuuint32_t)box_rows, (cuuint32_t)G2_KG};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), gdim, gstride, box, estr,
+  CUresult r = encode_tiled()(tm, wt ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
@@ -209,12 +211,13 @@ static int g2_pick_stages(const GemvParams& p, bool glu, bool whole) {
     const char* e = getenv("NXDI_B200_GEMV_SMEM_KB");
     budget_kb = e ? atoi(e) : G2_SMEM_CORES / 1024;
   }
-  const size_t fixed = g2_fixed_smem(p.T, p.K);
+  const int wt = p.scale != nullptr ? p.wdtype : 0;
+  const size_t fixed = g2_fixed_smem(p.T, p.K, wt);
   const size_t budget = std::min<size_t>((size_t)budget_kb * 1024, G2_SMEM_BUDGET);
   int ns = budget > fixed ? (int)((budget - fixed) / G2_STAGE_BYTES) : 0;
   const int n_tiles = g2_ntiles(p.N, glu);
-  const int n_chunks = (p.K + G2_KC - 1) / G2_KC;
-  const int G = gemv2_grid(p.N, p.K, glu);
+  const int n_chunks = (p.K + g2_kc(wt) - 1) / g2_kc(wt);
+  const int G = gemv2_grid(p.N, p.K, glu, wt);
   const long long per_cta = whole ? (long long)((n_tiles + G - 1) / G) * n_chunks : ((long long)n_tiles * n_chunks + G - 1) / G;
   ns = (int)std::min<long long>(ns, per_cta);
   ns = std::min(ns, G2_MAX_STAGES);
@@ -242,17 +245,24 @@ void gemv2_launch(const GemvParams& p, int mode, float* ws_part, unsigned* ticke
   pp.symm.step = p.symm.step; pp.symm.rank = p.symm.rank; pp.symm.world = p.symm.world; pp.symm.n_max = p.symm.n_max;
   ph.prof = prof_slot_ptr(prof_next_slot());
   const bool glu = p.act != 0;
+  const int wt = p.scale != nullptr ? p.wdtype : 0;
+  ph.wt = wt; ph.wscale = p.scale; ph.wscale_n = p.scale_n;
   ph.rows8 = g2_rows8(p.N, glu) ? 1 : 0;
-  make_weight_tmap(&pp.tmap, p.w, p.N, p.K, (glu || ph.rows8) ? 8 : 16);
+  make_weight_tmap(&pp.tmap, p.w, p.N, p.K, (glu || ph.rows8) ? 8 : 16, wt);
   ph.ws_part = ws_part;
   ph.tickets = tickets;
-  ph.p_max = gemv2_pmax(p.N, p.K, glu);
-  ph.whole_tiles = g2_whole_tiles(p.N, p.K, glu) ? 1 : 0;
+  ph.p_max = gemv2_pmax(p.N, p.K, glu, wt);
+  ph.whole_tiles = g2_whole_tiles(p.N, p.K, glu, wt) ? 1 : 0;
   pp.n_stages = g2_pick_stages(p, glu, ph.whole_tiles != 0);
   pp.max_inflight = g2_max_inflight() < pp.n_stages ? g2_max_inflight() : 0;
-  if (mode == 1) launch_gemv2<false, 1>(pp, stream);
-  else if (glu) launch_gemv2<true, 0>(pp, stream);
-  else launch_gemv2<false, 0>(pp, stream);
+#define G2_LAUNCH(WT)                                      \
+  if (mode == 1) launch_gemv2<false, 1, WT>(pp, stream);   \
+  else if (glu) launch_gemv2<true, 0, WT>(pp, stream);     \
+  else launch_gemv2<false, 0, WT>(pp, stream);
+  if (wt == 0) { G2_LAUNCH(0) }
+  else if (wt == 1) { G2_LAUNCH(1) }
+  else { G2_LAUNCH(2) }
+#undef G2_LAUNCH
 }
 
 }  // namespace nxdi

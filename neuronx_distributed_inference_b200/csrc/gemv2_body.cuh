@@ -75,7 +75,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 // host helpers implemented in gemv2.cu
-void make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K, int box_rows);
+void make_weight_tmap(CUtensorMap* tm, const void* w, int N, int K, int box_rows, int wt = 0);
 int g2_num_sms_public();
 int g2_max_inflight();   // NXDI_B200_GEMV_INFLIGHT
 
@@ -98,7 +98,14 @@ struct G2Phase {
   int whole_tiles;           // CTAs own whole tiles (no stream-K fix-up)
   int grid;                  // CTAs that share this phase's units
   int parity, call;          // fused all-reduce: receive-buffer parity and call index (tag) of this collective
+  // weight-only 8-bit weights (wt: 0 bf16, 1 int8, 2 fp8-e4m3): the SAME ring streams bytes — a stage is then 16 rows x 1024 k — and
+  // the consumers expand them to f16 pairs in registers (exact) for an f16 MMA against x converted to f16 once in the prologue;
+  // acc * wscale[n] (per output channel, or [0] per tensor) in the epilogue
+  const float* wscale;
+  int wscale_n;
+  int wt;
 };
+__host__ __device__ __forceinline__ int g2_kc(int wt) { return wt ? 2 * G2_KC : G2_KC; }   // k elements per 16 KB stage
 
 // Symmetric-workspace constants of a launch (same for every all-reduce phase)
 struct G2Symm {
@@ -129,7 +136,7 @@ struct G2Units {   // unit range of CTA `c` in a phase
 };
 __device__ __forceinline__ G2Units g2_units(const G2Phase& p, bool GLU, int c) {
   G2Units u;
-  u.n_chunks = (p.K + G2_KC - 1) / G2_KC;
+  u.n_chunks = (p.K + g2_kc(p.wt) - 1) / g2_kc(p.wt);
   u.rows8 = !GLU && p.rows8 != 0;
   u.TR = u.rows8 ? 8 : 16;
   u.n_tiles = GLU ? ((p.N >> 1) + 7) >> 3 : (p.N + u.TR - 1) / u.TR;
@@ -179,7 +186,29 @@ __device__ __forceinline__ void g2_produce(const G2Phase& p, const G2Smem& sm, c
 
 // ---- consumers: the 256 threads of warps 0..7.  `wait_dep()` blocks until the phase's inputs are complete (griddepcontrol.wait
 //      in the stand-alone kernel, a device-side counter in the persistent one); everything before it overlaps the producer of x.
-template <bool GLU, int MODE, class WaitDep>
+// 4 one-byte weights (one 32-bit word, k ascending) -> two f16x2 registers (k, k+1), (k+2, k+3); exact for both formats
+template <int WT>
+__device__ __forceinline__ void g2_expand4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  if (WT == 2) {
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(lo) : "h"((unsigned short)(w & 0xffffu)));
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hi) : "h"((unsigned short)(w >> 16)));
+  } else {
+    // int8: bias to unsigned, splice under the exponent of 1024.0 (f16 ulp 1 in [1024, 2048)), subtract 1024 + 128
+    const uint32_t u = w ^ 0x80808080u;
+    const uint32_t a = __byte_perm(u, 0x64646464u, 0x5140), b = __byte_perm(u, 0x64646464u, 0x5342);
+    const uint32_t k1152 = 0x64806480u;
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(k1152));
+    asm("sub.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(b), "r"(k1152));
+  }
+}
+// two fp32 -> f16x2 with saturation to the finite range (activations of the 8-bit weight paths)
+__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <bool GLU, int MODE, int WT = 0, class WaitDep>
 __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, const G2Smem& sm, const int c, const int tid,
                                            int& stage, uint32_t& lap, uint32_t& xph, WaitDep&& wait_dep) {
   const int lane = tid & 31, warp = tid >> 5;
@@ -192,8 +221,11 @@ __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, c
   const int n_chunks = un.n_chunks, n_tiles = un.n_tiles, TR = un.TR;
   const bool rows8 = un.rows8;
   const long long U = un.U, u_beg = un.u_beg, u_end = un.u_end;
-  const int Kp = n_chunks * G2_KC;
-  const int xs_stride = Kp * 2 + 64;
+  constexpr int KC = WT ? 2 * G2_KC : G2_KC;   // k elements per stage
+  const int Kp = n_chunks * KC;
+  // row stride of x in shared memory: the 16-byte offset (8-bit paths: lanes of a quad are 32 bytes apart) or the 64-byte
+  // offset (bf16: 16 bytes apart) keeps the 8-lane LDS.128 phases of two token rows in disjoint banks
+  const int xs_stride = Kp * 2 + (WT != 0 ? 16 : 64);
   const uint32_t stage_u = smem_u32(sm.stage_base), xs_u = smem_u32(sm.xs), red_u = smem_u32(sm.red), rstd_u = smem_u32(sm.rstd_s);
   uint64_t* full_bar = sm.full_bar;
   uint64_t* empty_bar = sm.empty_bar;
@@ -240,7 +272,8 @@ __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, c
   }
   mbar_wait(sm.x_bar, xph);
   xph ^= 1u;
-  if (has_norm) {
+  if (has_norm || WT != 0) {
+    // one in-place pass over x: sum of squares (fused RMSNorm), x gamma, and for the 8-bit weight paths bf16 -> f16
     const float o = p.norm_offset;
 #pragma unroll
     for (int t = 0; t < GEMV_MAX_T; ++t) {
@@ -251,18 +284,28 @@ __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, c
           if (j < per_thread) {
             const uint32_t a = xs_u + t * xs_stride + (ctid + 256 * j) * 16;
             uint4 w = lds128(a);
-            const uint4 gm = gq[j];
-            acc += bf16lo(w.x) * bf16lo(w.x) + bf16hi(w.x) * bf16hi(w.x) + bf16lo(w.y) * bf16lo(w.y) + bf16hi(w.y) * bf16hi(w.y) +
-                   bf16lo(w.z) * bf16lo(w.z) + bf16hi(w.z) * bf16hi(w.z) + bf16lo(w.w) * bf16lo(w.w) + bf16hi(w.w) * bf16hi(w.w);
-            w.x = pack_bf16(bf16lo(w.x) * (bf16lo(gm.x) + o), bf16hi(w.x) * (bf16hi(gm.x) + o));
-            w.y = pack_bf16(bf16lo(w.y) * (bf16lo(gm.y) + o), bf16hi(w.y) * (bf16hi(gm.y) + o));
-            w.z = pack_bf16(bf16lo(w.z) * (bf16lo(gm.z) + o), bf16hi(w.z) * (bf16hi(gm.z) + o));
-            w.w = pack_bf16(bf16lo(w.w) * (bf16lo(gm.w) + o), bf16hi(w.w) * (bf16hi(gm.w) + o));
+            float f[8] = {bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y), bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w)};
+            if (has_norm) {
+              const uint4 gm = gq[j];
+              const float gf[8] = {bf16lo(gm.x), bf16hi(gm.x), bf16lo(gm.y), bf16hi(gm.y), bf16lo(gm.z), bf16hi(gm.z), bf16lo(gm.w), bf16hi(gm.w)};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                acc += f[e] * f[e];
+                f[e] *= gf[e] + o;
+              }
+            }
+            if (WT != 0) {
+              w = make_uint4(pack_f16_sat(f[0], f[1]), pack_f16_sat(f[2], f[3]), pack_f16_sat(f[4], f[5]), pack_f16_sat(f[6], f[7]));
+            } else {
+              w = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
             sts128(a, w);
           }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) sts_f32(rstd_u + (warp * 8 + t) * 4, acc);
+        if (has_norm) {
+          acc = warp_sum(acc);
+          if (lane == 0) sts_f32(rstd_u + (warp * 8 + t) * 4, acc);
+        }
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -283,23 +326,33 @@ __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, c
 
   // epilogue operands of the tile being streamed (bias / residual of this thread's (col, row)): fetched when the tile STARTS,
   // so their L2 latency hides behind the weight stream instead of sitting on the critical path after the last stage
-  float pre_b0 = 0.f, pre_b1 = 0.f, pre_r = 0.f;
+  float pre_b0 = 0.f, pre_b1 = 0.f, pre_r = 0.f, pre_s0 = 1.f, pre_s1 = 1.f;
   auto prefetch_epilogue = [&](int tile) {
     pre_b0 = pre_b1 = pre_r = 0.f;
+    pre_s0 = pre_s1 = 1.f;
     if (ctid >= 128) return;
     const int col = ctid >> 4, row = ctid & 15;
     if (col >= T) return;
     if (GLU) {
       const int n = tile * 8 + row, half = N >> 1;
-      if (row < 8 && n < half && BIAS != nullptr) {
-        pre_b0 = __bfloat162float(BIAS[n]);
-        pre_b1 = __bfloat162float(BIAS[half + n]);
+      if (row < 8 && n < half) {
+        if (BIAS != nullptr) {
+          pre_b0 = __bfloat162float(BIAS[n]);
+          pre_b1 = __bfloat162float(BIAS[half + n]);
+        }
+        if (WT != 0) {
+          pre_s0 = __ldg(p.wscale + (p.wscale_n == 1 ? 0 : n));
+          pre_s1 = __ldg(p.wscale + (p.wscale_n == 1 ? 0 : half + n));
+        }
       }
-    } else if (MODE == 0) {
+    } else {
       const int n = tile * TR + row;
       if (row < TR && n < N) {
-        if (BIAS != nullptr) pre_b0 = __bfloat162float(BIAS[n]);
-        if (RES != nullptr) pre_r = ldg_act_bf16(RES + (size_t)col * p.ldy + n);
+        if (WT != 0) pre_s0 = __ldg(p.wscale + (p.wscale_n == 1 ? 0 : n));
+        if (MODE == 0) {
+          if (BIAS != nullptr) pre_b0 = __bfloat162float(BIAS[n]);
+          if (RES != nullptr) pre_r = ldg_act_bf16(RES + (size_t)col * p.ldy + n);
+        }
       }
     }
   };
@@ -313,14 +366,14 @@ __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, c
       const int n = tile * 8 + row, half = N >> 1;
       if (n >= half) return;
       const float rs = rstd_of(col);
-      const float gate = v_gate_or_val * rs + pre_b0, up = v_up * rs + pre_b1;
+      const float gate = v_gate_or_val * (rs * pre_s0) + pre_b0, up = v_up * (rs * pre_s1) + pre_b1;
       const float a = p.act == 1 ? silu(gate) : (p.act == 2 ? gelu_tanh(gate) : gelu_erf(gate));
       Y[(size_t)col * p.ldy + n] = __float2bfloat16(a * up);
     } else {
       if (row >= TR) return;
       const int n = tile * TR + row;
       if (n >= N) return;
-      float v = v_gate_or_val * rstd_of(col);
+      float v = v_gate_or_val * (rstd_of(col) * pre_s0);
       if (MODE == 0) {
         Y[(size_t)col * p.ldy + n] = __float2bfloat16(v + pre_b0 + pre_r);
       } else {
@@ -367,10 +420,48 @@ __device__ __forceinline__ void g2_consume(const G2Phase& p, const G2Symm& sy, c
       const int chunk = chunk_first + i;
       mbar_wait(&full_bar[stage], lap);
       const uint32_t sA = stage_u + stage * G2_STAGE_BYTES;
-      const uint32_t xk = xrow + (chunk * G2_KC + warp * 64 + t4 * 8) * 2;
       // stage layout: line = kg * rows + row (rows = 16; GLU / rows8: two halves of [8 kg][8 rows])
+      if (WT != 0) {
+        // 8-bit weights: a 128-byte line holds 128 k of one row; this thread takes 16-byte chunks t4 and t4 + 4 (16 k each) of
+        // rows g and g + 8, expands them to f16 pairs and multiplies them with the matching 32 bytes of x (f16): 4 MMAs per chunk.
+        // Any k -> MMA-slot assignment is fine as long as A and B agree: pair m of a chunk (k = 2m, 2m + 1) is slot pair m.
+        const uint32_t xk8 = xrow + (chunk * KC + warp * 128 + t4 * 16) * 2;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 2; ++j) {
+          const int ch = (j << 2) + t4;
+          uint4 q0, q1 = make_uint4(0u, 0u, 0u, 0u);
+          if (GLU) {
+            q0 = lds128(sA + swz128(warp * 8 + g, ch) * 2);
+            q1 = lds128(sA + G2_STAGE_BYTES / 2 + swz128(warp * 8 + g, ch) * 2);
+          } else if (rows8) {
+            q0 = lds128(sA + swz128(warp * 8 + g, ch) * 2);
+          } else {
+            q0 = lds128(sA + swz128(warp * 16 + g, ch) * 2);
+            q1 = lds128(sA + swz128(warp * 16 + g + 8, ch) * 2);
+          }
+          uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+          if (tok_ok) {
+            x0 = lds128(xk8 + j * 128);
+            x1 = lds128(xk8 + j * 128 + 16);
+          }
+          uint32_t pa[8], pb[8];
+          g2_expand4<WT>(q0.x, pa[0], pa[1]); g2_expand4<WT>(q0.y, pa[2], pa[3]);
+          g2_expand4<WT>(q0.z, pa[4], pa[5]); g2_expand4<WT>(q0.w, pa[6], pa[7]);
+          g2_expand4<WT>(q1.x, pb[0], pb[1]); g2_expand4<WT>(q1.y, pb[2], pb[3]);
+          g2_expand4<WT>(q1.z, pb[4], pb[5]); g2_expand4<WT>(q1.w, pb[6], pb[7]);
+          const uint32_t xb[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const uint32_t a[4] = {pa[2 * m], pb[2 * m], pa[2 * m + 1], pb[2 * m + 1]};
+            const uint32_t b[2] = {xb[2 * m], xb[2 * m + 1]};
+            if (m & 1) mma_f16_16816(c1, a, b);
+            else mma_f16_16816(c0, a, b);
+          }
+        }
+      }
+      const uint32_t xk = xrow + (chunk * G2_KC + warp * 64 + t4 * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < (WT != 0 ? 0 : 2); ++j) {
         const int ch = (j << 2) + t4;
         uint4 a0, a1 = make_uint4(0u, 0u, 0u, 0u);
         if (GLU) {

@@ -224,6 +224,9 @@ class NeuronApplicationBase(nn.Module):
                     tmp.normal_(0.0, 0.02, generator=gen)
                     p.copy_(tmp)
                     del tmp
+            for m in self.model.modules():      # heads stored zero-padded to a kernel width (modules/gqa.py)
+                if hasattr(m, "zero_head_padding"):
+                    m.zero_head_padding()
 
     def to_cpu(self):
         """CPU execution path (reference application_base.py:556-628)."""

@@ -93,7 +93,9 @@ class NeuronBaseModel(nn.Module):
         """Dense decoder on the contiguous cache with a garbage line: the PyTorch composite path has no host sync either."""
         nc = self.neuron_config
         return (not nc.is_block_kv_layout and not nc.kv_cache_quant and getattr(self.kv_mgr, "garbage", 0) == 1
-                and not any(getattr(l, "mlp_is_moe", False) for l in self.layers))
+                and not any(getattr(l, "mlp_is_moe", False) for l in self.layers)
+                # head rows that are not 16-byte multiples take the PyTorch cache append (boolean indexing: a host sync)
+                and all((getattr(getattr(l, "self_attn", None), "head_dim", 8) * 2) % 16 == 0 for l in self.layers))
 
     def _moe_kernels_cover_decode(self) -> bool:
         if self.device_ is None or torch.device(self.device_).type != "cuda":

@@ -20,6 +20,7 @@ flash decoding (KV sequence-sharded inside a KV-replication group).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -76,15 +77,28 @@ class AttentionBase(nn.Module):
         self.layer_idx = layer_idx
         self.tp_group = tensor_model_parallel_group or get_tensor_model_parallel_group()
         dtype = nc.torch_dtype
+        # Odd head sizes (80, 96, 100, 112 ...): the attention kernels are specialised for 64 / 128 channels.  On the CUDA bf16 path
+        # the heads are STORED zero-padded to the next kernel width (Wqkv rows / Wo columns padded at load time, KV cache that wide):
+        # q.k over the padded channels adds zeros, the padded V channels stay zero, so the function is unchanged; the softmax scale and
+        # the rotary tables keep the checkpoint's head size.
+        self.logical_head_dim = head_dim
+        rot = getattr(rotary_emb, "dim", None) if (use_rope and rotary_emb is not None) else None
+        dev_is_cuda = device is not None and torch.device(device).type == "cuda"
+        if (dev_is_cuda and dtype == torch.bfloat16 and head_dim not in (64, 128) and head_dim < 128 and head_dim % 2 == 0
+                and qk_norm is None and attention_chunk_size is None and not logit_softcap and nc.lora_config is None
+                and (rot is None or rot == head_dim) and os.environ.get("NXDI_B200_PAD_HEAD_DIM", "1") != "0"):
+            head_dim = 64 if head_dim < 64 else 128
         self.hidden_size, self.head_dim = hidden_size, head_dim
         self.num_attention_heads, self.num_key_value_heads = num_attention_heads, num_key_value_heads
         sp = nc.sequence_parallel_enabled
+        pad_split = not rope_interleaved
         self.qkv_proj = GroupQueryAttention_QKV(qkv_input_size or hidden_size, head_dim, num_attention_heads, num_key_value_heads,
                                                 self.tp_group, dtype, qkv_bias, sharding_strategy, device,
-                                                sequence_parallel_enabled=sp)
+                                                sequence_parallel_enabled=sp, src_head_dim=self.logical_head_dim, pad_split=pad_split)
         self.o_proj = GroupQueryAttention_O(hidden_size, head_dim, num_attention_heads, num_key_value_heads,
                                             self.tp_group, dtype, o_bias, sharding_strategy, device,
-                                            sequence_parallel_enabled=sp, reduce_dtype=nc.rpl_reduce_dtype)
+                                            sequence_parallel_enabled=sp, reduce_dtype=nc.rpl_reduce_dtype,
+                                            src_head_dim=self.logical_head_dim, pad_split=pad_split)
         self.n_q, self.n_kv = self.qkv_proj.n_q, self.qkv_proj.n_kv
         self.rotary_emb = rotary_emb
         self.use_rope = use_rope and rotary_emb is not None
@@ -93,7 +107,7 @@ class AttentionBase(nn.Module):
         self.attention_chunk_size = attention_chunk_size
         self.clip_qkv = clip_qkv
         self.softcap = logit_softcap
-        self.scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(head_dim)
+        self.scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(self.logical_head_dim)
         self.qk_norm = qk_norm  # None | "rms_pre_rope" | "rms_post_rope" (HunYuan; generic path) | "l2_post_rope"
         self.qk_norm_eps = qk_norm_eps
         if qk_norm in ("rms_pre_rope", "rms_post_rope"):
@@ -135,6 +149,18 @@ class AttentionBase(nn.Module):
         if key not in meta.rope_cache:
             pos = meta.rotary_position_ids if meta.rotary_position_ids is not None else meta.position_ids
             meta.rope_cache[key] = self.rotary_emb(pos)
+        if self.head_dim != self.logical_head_dim:
+            # padded heads: identity rotation (cos 1, sin 0) for the padded channel pairs
+            pkey = (key, self.head_dim)
+            if pkey not in meta.rope_cache:
+                cos, sin = meta.rope_cache[key]
+                extra = self.head_dim // 2 - cos.shape[-1]
+                if self.rope_interleaved or extra <= 0:
+                    padded = (torch.nn.functional.pad(cos, (0, max(extra, 0)), value=1.0), torch.nn.functional.pad(sin, (0, max(extra, 0))))
+                else:
+                    padded = (torch.nn.functional.pad(cos, (0, extra), value=1.0), torch.nn.functional.pad(sin, (0, extra)))
+                meta.rope_cache[pkey] = padded
+            return meta.rope_cache[pkey]
         return meta.rope_cache[key]
 
     def _simple(self) -> bool:

@@ -127,6 +127,31 @@ def _gather_heads(t: torch.Tensor, idx: List[int], head_dim: int, dim: int) -> t
     return out.reshape(shape)
 
 
+def head_pad_index(src_dim: int, dst_dim: int, split: bool) -> torch.Tensor:
+    """Where the ``src_dim`` real channels of a head live inside its zero-padded ``dst_dim`` storage.  ``split`` (rotate-half RoPE):
+    the two halves keep their pairing distance — first half at [0, src/2), second half at [dst/2, dst/2 + src/2) — so a kernel that
+    rotates channel i with channel i + dst/2 rotates exactly the original pairs; otherwise (interleaved RoPE / no RoPE): a prefix."""
+    if not split:
+        return torch.arange(src_dim)
+    h = src_dim // 2
+    return torch.cat([torch.arange(h), dst_dim // 2 + torch.arange(h)])
+
+
+def _pad_heads(t: torch.Tensor, src_dim: int, dst_dim: int, dim: int, split: bool) -> torch.Tensor:
+    """[..., heads * src_dim, ...] -> [..., heads * dst_dim, ...] along ``dim``: each head zero-padded (see head_pad_index)."""
+    if src_dim == dst_dim:
+        return t
+    shape = list(t.shape)
+    heads = shape[dim] // src_dim
+    cast = t.dtype in (torch.float8_e4m3fn, torch.float8_e5m2)
+    v = (t.view(torch.uint8) if cast else t).reshape(shape[:dim] + [heads, src_dim] + shape[dim + 1:])
+    out = v.new_zeros(shape[:dim] + [heads, dst_dim] + shape[dim + 1:])
+    out.index_copy_(dim + 1, head_pad_index(src_dim, dst_dim, split).to(v.device), v)
+    shape[dim] = heads * dst_dim
+    out = out.reshape(shape)
+    return out.view(t.dtype) if cast else out
+
+
 class GroupQueryAttention_QKV(BaseParallelLinear):
     """Fused ``Wqkv`` column-parallel projection: local rows = [q heads | k heads | v heads] of this
     rank.  State-dict key: ``Wqkv.weight`` holding the *unsharded* concat [q; k; v]."""
@@ -134,11 +159,15 @@ class GroupQueryAttention_QKV(BaseParallelLinear):
     def __init__(self, hidden_size: int, head_dim: int, num_attention_heads: int, num_key_value_heads: int,
                  tp_group: Optional[Group] = None, dtype=torch.float32, bias: bool = False,
                  desired_sharding_strategy: Optional[GQA] = None, device=None,
-                 sequence_parallel_enabled: bool = False, sequence_dimension: int = 1):
+                 sequence_parallel_enabled: bool = False, sequence_dimension: int = 1,
+                 src_head_dim: Optional[int] = None, pad_split: bool = True):
+        """``src_head_dim``: head size of the CHECKPOINT when the layer stores its heads zero-padded to ``head_dim`` (odd head sizes
+        such as 80 / 96 / 100 run on the 64 / 128-wide attention kernels; AttentionBase decides)."""
         super().__init__()
         self.tensor_parallel_group = tp_group or get_tensor_model_parallel_group()
         tp = self.tensor_parallel_group.size
         self.hidden_size, self.head_dim = hidden_size, head_dim
+        self.src_head_dim, self.pad_split = src_head_dim or head_dim, pad_split
         self.plan = make_gqa_plan(tp, num_attention_heads, num_key_value_heads, desired_sharding_strategy)
         self.n_q, self.n_kv = self.plan.q_per_rank, self.plan.kv_per_rank
         self.sequence_parallel_enabled = sequence_parallel_enabled
@@ -156,12 +185,26 @@ class GroupQueryAttention_QKV(BaseParallelLinear):
 
     def _shard(self, full: torch.Tensor, rank: int) -> torch.Tensor:
         """full: [(n_q + 2 n_kv) * D, ...] unsharded (works for weight, bias, per-channel scale)."""
-        p, D = self.plan, self.head_dim
+        p, D, Dp, sp = self.plan, self.src_head_dim, self.head_dim, self.pad_split
         if full.shape[0] == 1:  # per-tensor scale
             return full.clone()
         q, k, v = full.split([p.n_q * D, p.n_kv * D, p.n_kv * D], 0)
-        return torch.cat([_gather_heads(q, p.q_idx[rank], D, 0), _gather_heads(k, p.kv_idx[rank], D, 0),
-                          _gather_heads(v, p.kv_idx[rank], D, 0)], 0)
+        return torch.cat([_pad_heads(_gather_heads(q, p.q_idx[rank], D, 0), D, Dp, 0, sp),
+                          _pad_heads(_gather_heads(k, p.kv_idx[rank], D, 0), D, Dp, 0, sp),
+                          _pad_heads(_gather_heads(v, p.kv_idx[rank], D, 0), D, Dp, 0, sp)], 0)
+
+    def zero_head_padding(self):
+        """Random-init helper: the padded channels of every head must be zero (they are, after a checkpoint load)."""
+        if self.src_head_dim == self.head_dim:
+            return
+        keep = torch.zeros(self.head_dim, dtype=torch.bool)
+        keep[head_pad_index(self.src_head_dim, self.head_dim, self.pad_split)] = True
+        rows = keep.repeat(self.n_q + 2 * self.n_kv).to(self.weight.device)
+        with torch.no_grad():
+            for t in (self.weight, self.bias):
+                if t is not None:
+                    z = t.view(torch.uint8) if t.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) else t
+                    z[~rows] = 0
 
     def preshard_hook(self, model_state_dict: dict, prefix: str) -> bool:
         """Rewrite the fused ``<prefix>.weight / .bias / .scale`` entries of an UNSHARDED state dict to the replicated / padded head
@@ -194,12 +237,13 @@ class GroupQueryAttention_O(BaseParallelLinear):
                  tp_group: Optional[Group] = None, dtype=torch.float32, bias: bool = False,
                  desired_sharding_strategy: Optional[GQA] = None, device=None,
                  sequence_parallel_enabled: bool = False, sequence_dimension: int = 1,
-                 reduce_dtype=None, out_size: Optional[int] = None):
+                 reduce_dtype=None, out_size: Optional[int] = None, src_head_dim: Optional[int] = None, pad_split: bool = True):
         super().__init__()
         self.tensor_parallel_group = tp_group or get_tensor_model_parallel_group()
         tp = self.tensor_parallel_group.size
         self.plan = make_gqa_plan(tp, num_attention_heads, num_key_value_heads, desired_sharding_strategy)
         self.head_dim = head_dim
+        self.src_head_dim, self.pad_split = src_head_dim or head_dim, pad_split
         self.sequence_parallel_enabled = sequence_parallel_enabled
         self.sequence_dimension = sequence_dimension
         self.reduce_dtype = reduce_dtype
@@ -217,7 +261,18 @@ class GroupQueryAttention_O(BaseParallelLinear):
     def _shard(self, full: torch.Tensor, rank: int) -> torch.Tensor:
         if full.dim() == 1 or full.shape[-1] == 1:  # per-out-channel scale / per-tensor: replicated
             return full.clone()
-        return _gather_heads(full, self.plan.q_idx[rank], self.head_dim, 1)
+        return _pad_heads(_gather_heads(full, self.plan.q_idx[rank], self.src_head_dim, 1), self.src_head_dim, self.head_dim, 1,
+                          self.pad_split)
+
+    def zero_head_padding(self):
+        if self.src_head_dim == self.head_dim:
+            return
+        keep = torch.zeros(self.head_dim, dtype=torch.bool)
+        keep[head_pad_index(self.src_head_dim, self.head_dim, self.pad_split)] = True
+        cols = keep.repeat(self.plan.q_per_rank).to(self.weight.device)
+        with torch.no_grad():
+            z = self.weight.view(torch.uint8) if self.weight.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) else self.weight
+            z[:, ~cols] = 0
 
     def forward(self, x, residual=None):
         g = self.tensor_parallel_group

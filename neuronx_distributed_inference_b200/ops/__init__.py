@@ -114,6 +114,11 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
                 y = _C().gemm_fp8(xq, a_s, w, scale.float().contiguous(), bias, _ACT_CODES[act], r2)
                 y = y.view(*x.shape[:-1], y.shape[-1])
                 return y if (residual is None or r2 is not None) else y + residual
+            if (wq and T > GEMV_MAX_TOKENS and w.dim() == 2 and K % 64 == 0 and n_out % 8 == 0 and _TCGEN05_GEMM
+                    and x.dtype == torch.bfloat16):
+                # weight-only 8-bit prefill: one expansion pass into a shared bf16 scratch (stays in L2), then the bf16 tensor-core GEMM
+                stats["dequant_gemm"] += 1
+                w, scale, wq = _C().dequant_bf16(w, scale.float().contiguous(), _dequant_scratch(w)), None, False
             if not wq and n_out % 8 == 0 and K % 64 == 0 and _TCGEN05_GEMM and (T > GEMV_MAX_TOKENS or K % 64 != 0):
                 if norm_weight is not None:
                     x2 = rmsnorm(x2, norm_weight, norm_eps, norm_offset)
@@ -131,6 +136,19 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
     return y
 
 
+_DEQ_SCRATCH = {}
+
+
+def _dequant_scratch(w):
+    """One bf16 scratch per device, grown to the largest 8-bit weight seen (consumed by the GEMM enqueued right after the expansion;
+    stream order makes the reuse by the next layer safe)."""
+    buf = _DEQ_SCRATCH.get(w.device)
+    if buf is None or buf.numel() < w.numel():
+        buf = torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device)
+        _DEQ_SCRATCH[w.device] = buf
+    return buf
+
+
 def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=None):
     """Row-parallel GEMM -> all-reduce (+bias, +residual).  T <= 8 tokens on CUDA with a
     symmetric workspace attached to the group: ONE kernel (GEMV, P2P stores of partials into every
@@ -138,13 +156,15 @@ def linear_allreduce(x, w, bias, group, residual=None, reduce_dtype=None, scale=
     from ..parallel import mappings
     K = x.shape[-1]
     T = x.numel() // K
+    wq = w.dtype in (torch.int8, torch.float8_e4m3fn) and scale is not None and scale.dim() == 1 and w.dim() == 2
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and group.symm is not None and T <= GEMV_MAX_TOKENS
             and w.shape[0] <= group.symm.n_max
-            and K % 64 == 0 and w.is_contiguous() and w.dtype == x.dtype and scale is None
-            and _C().gemv2_supported(T, K)
+            and K % 64 == 0 and w.is_contiguous() and ((w.dtype == x.dtype and scale is None) or wq)
+            and _C().gemv2_supported(T, K, (1 if w.dtype == torch.int8 else 2) if wq else 0)
             and reduce_dtype in (None, torch.float32)):
         stats["gemv_allreduce"] += 1
-        y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None)
+        y = group.symm.gemv_allreduce(x.reshape(T, K), w, bias, residual.reshape(T, -1) if residual is not None else None,
+                                      scale.float().contiguous() if wq else None)
         return y.view(*x.shape[:-1], y.shape[-1])
     heap = getattr(group, "heap", None)
     if heap is not None and scale is None and reduce_dtype in (None, torch.float32, x.dtype) and T > GEMV_MAX_TOKENS \

@@ -76,9 +76,10 @@ class SymmetricWorkspace:
         self.step_t.add_(1)
         self.call = 0
 
-    def gemv_allreduce(self, x, w, bias=None, residual=None):
+    def gemv_allreduce(self, x, w, bias=None, residual=None, scale=None):
+        """``scale``: fp32 per-output-channel (or per-tensor) dequantisation scale of int8 / fp8 weights."""
         y = self._C.gemv_allreduce(x, w, bias, residual, self.recv_ptrs, self.step_t, self.rank, self.parity, self.call,
-                                   self.n_max)
+                                   self.n_max, scale)
         self.parity ^= 1
         self.call += 1
         self.calls += 1

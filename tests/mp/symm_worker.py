@@ -62,6 +62,28 @@ def main():
         same = all(torch.equal(ys[0], t) for t in ys)
         log(f"T={T} N={N} K={K} rel_err={err:.2e} identical_across_ranks={same}")
         assert err < 1e-2 and same
+    # weight-only 8-bit row-parallel layers through the same fused kernel (bytes streamed by TMA, expanded in registers)
+    from neuronx_distributed_inference_b200.ops import reference as refops
+    for wdt in (torch.float8_e4m3fn, torch.int8):
+        for (T, N, K) in [(2, 4096, 1792), (4, 4096, 1408), (1, 2048, 512)]:
+            x = torch.randn(T, K, device=dev, dtype=torch.bfloat16)
+            q, sc = refops.quantize_per_channel(torch.randn(N, K, device=dev) / K ** 0.5, wdt)
+            res = torch.randn(T, N, device=dev, dtype=torch.bfloat16)
+            dist.broadcast(res, 0)
+            n0 = ops.stats["gemv_allreduce"]
+            g.symm.begin_step()
+            y = ops.linear_allreduce(x, q, None, g, residual=res, scale=sc)
+            torch.cuda.synchronize()
+            assert ops.stats["gemv_allreduce"] == n0 + 1
+            ref = x.float() @ (q.float() * sc.float()[:, None]).t()
+            dist.all_reduce(ref)
+            ref = ref + res.float()
+            err = ((y.float() - ref).norm() / ref.norm()).item()
+            ys = [torch.empty_like(y) for _ in range(world)]
+            dist.all_gather(ys, y)
+            same = all(torch.equal(ys[0], t) for t in ys)
+            log(f"quantised {wdt} T={T} N={N} K={K} rel_err={err:.2e} identical_across_ranks={same}")
+            assert err < 1e-2 and same
     # graph capture + replay, timing vs NCCL
     T, N, K = 2, 4096, 512
     x = torch.randn(T, K, device=dev, dtype=torch.bfloat16)

@@ -186,3 +186,51 @@ def test_persistent_decode_step_matches_layer_by_layer(cfg):
     rel = ((a - b).norm() / b.norm()).item()
     assert rel < 2e-2, rel
     assert (a.argmax(-1) == b.argmax(-1)).float().mean().item() > 0.9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("head_dim,heads,kv", [(100, 4, 4), (80, 4, 2), (48, 8, 2)])
+def test_odd_head_dims_run_on_padded_kernels(head_dim, heads, kv, monkeypatch):
+    """Head sizes the attention kernels are not specialised for (open_llama_3b: 100, ...) are stored zero-padded to 64 / 128 channels on
+    the CUDA bf16 path (modules/gqa.py, attention_base.py).  Same weights, padding off (PyTorch composite attention) vs on (kernels):
+    same logits up to bf16 rounding, and the padded model is graph-safe."""
+    from neuronx_distributed_inference_b200 import ops
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    hf = dict(hidden_size=heads * head_dim, intermediate_size=512, num_hidden_layers=2, num_attention_heads=heads,
+              num_key_value_heads=kv, head_dim=head_dim, vocab_size=512)
+    ids = torch.randint(1, 512, (2, 12))
+    mask = torch.ones_like(ids)
+
+    feed = [torch.randint(1, 512, (2, 1)) for _ in range(4)]      # teacher-forced decode inputs (greedy feedback would amplify near-ties)
+
+    def logits_of(app):
+        app.reset()
+        out = app(ids, attention_mask=mask)
+        lg = [out.logits[:, -1].float()]
+        pos = torch.full((2, 1), 12, dtype=torch.int32)
+        for i, tok in enumerate(feed):
+            lg.append(app(tok, position_ids=pos + i).logits[:, -1].float())
+        return torch.stack(lg)
+
+    def build(pad):
+        monkeypatch.setenv("NXDI_B200_PAD_HEAD_DIM", "1" if pad else "0")
+        app = build_random_llama(hf, batch_size=2, seq_len=64, max_context_length=16, device="cuda", dtype="bfloat16", seed=11,
+                                 output_logits=True)
+        attn = app.model.layers[0].self_attn
+        assert attn.head_dim == ((64 if head_dim < 64 else 128) if pad else head_dim) and attn.logical_head_dim == head_dim
+        return app
+    app0 = build(False)
+    l0 = logits_of(app0)
+    sd = {k: v.clone() for k, v in app0.model.state_dict().items()}
+    app1 = build(True)
+    assert app1.model.graph_safe
+    # copy the unpadded weights into the padded layout through the layers' own shard functions
+    with torch.no_grad():
+        for name, p_ in app1.model.named_parameters():
+            src = sd[name]
+            p_.copy_(p_.shard_fn(src.cpu(), 0).to(p_.device) if (src.shape != p_.shape and hasattr(p_, "shard_fn")) else src)
+    n0 = ops.stats["rope_attn_decode"]
+    l1 = logits_of(app1)
+    assert ops.stats["rope_attn_decode"] > n0
+    rel = ((l1 - l0).norm() / l0.norm()).item()
+    assert rel < 3e-2, rel

@@ -352,9 +352,13 @@ def test_moe_grouped_fp8_experts_w8a8():
 @pytest.mark.parametrize("wdtype", [torch.int8, torch.float8_e4m3fn])
 @pytest.mark.parametrize("T,N,K,act,norm,res,per_tensor", [(2, 4096, 4096, None, True, False, False), (1, 6144, 4096, None, False, True, False),
                                                            (8, 2048, 14336, None, False, True, True), (4, 7168, 4096, "silu_mul", True, False, False),
-                                                           (3, 1000, 1040, None, False, False, False)])
+                                                           (3, 1000, 1040, None, False, False, False),
+                                                           # Llama-2-7b: K = 11008 is not a multiple of the 1024-k stage, GLU tiles
+                                                           (2, 4096, 11008, None, False, True, False), (2, 22016, 4096, "silu_mul", True, False, False),
+                                                           (5, 520, 1280, None, True, True, False)])
 def test_quantized_gemv_matches_dequantized_reference(wdtype, T, N, K, act, norm, res, per_tensor):
-    """Weight-only int8 / fp8 decode GEMV (csrc/qgemv.cu) == dequantise-then-matmul."""
+    """Weight-only int8 / fp8 decode GEMV == dequantise-then-matmul.  K % 128 == 0: the TMA-streamed gemv2 kernel (8-bit weights
+    expanded to f16 in registers, csrc/gemv2_body.cuh); otherwise the CUDA-core fallback (csrc/qgemv.cu)."""
     torch.manual_seed(0)
     dev, dt = "cuda", torch.bfloat16
     w = torch.randn(N, K, device=dev) * 0.05
@@ -376,6 +380,21 @@ def test_quantized_gemv_matches_dequantized_reference(wdtype, T, N, K, act, norm
         exp = exp + r.float()
     err = (got.float() - exp.float()).abs().max().item()
     assert err <= 0.02 * exp.abs().max().item() + 0.03, err
+
+
+@pytest.mark.parametrize("wdtype", [torch.int8, torch.float8_e4m3fn])
+def test_weight_only_prefill_expands_once_then_tensor_core_gemm(wdtype):
+    """T > 8 with 8-bit weights and no activation quantisation: one dequantise-to-bf16 pass into the shared scratch + tcgen05 GEMM."""
+    torch.manual_seed(0)
+    T, N, K = 256, 2 * 1408, 1024
+    q, s = ref.quantize_per_channel(torch.randn(N, K, device="cuda") * 0.05, wdtype)
+    x = torch.randn(T, K, device="cuda", dtype=torch.bfloat16)
+    nw = (1 + 0.1 * torch.randn(K, device="cuda")).to(torch.bfloat16)
+    n0, n1 = ops.stats["dequant_gemm"], ops.stats["gemm_tcgen05"]
+    got = ops.linear(x, q, None, norm_weight=nw, norm_eps=1e-5, act="silu_mul", scale=s)
+    assert ops.stats["dequant_gemm"] == n0 + 1 and ops.stats["gemm_tcgen05"] == n1 + 1
+    exp = ref.linear(x.float(), q, None, nw.float(), 1e-5, 0.0, "silu_mul", s)
+    assert _rel(got, exp) < 1e-2, _rel(got, exp)
 
 
 @pytest.mark.parametrize("B,T,Hq,Hkv,D", [(2, 200, 8, 8, 64), (1, 1500, 4, 4, 128), (3, 77, 16, 4, 128)])

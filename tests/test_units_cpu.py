@@ -407,3 +407,25 @@ def test_module_from_model_decoder_layer_orchestrator(past_len, seq_len, tmp_pat
     orch = DecoderLayerFromModelOrchestrator(hf, factory, OrchestratorConfig(past_len=past_len, seq_len=seq_len, layer_idx=1, rtol=1e-4, atol=1e-4))
     rep = orch.run_validation(devices=("cpu",))
     assert rep["cpu"] < 1e-3
+
+
+@pytest.mark.parametrize("D,Dp,split", [(100, 128, True), (80, 128, True), (48, 64, True), (96, 128, False)])
+def test_zero_padded_heads_compute_the_same_attention(D, Dp, split):
+    """modules/gqa.py head padding: Wqkv rows / Wo columns of every head zero-padded to a kernel width, rotary tables padded with the
+    identity rotation, softmax scale of the ORIGINAL head size -> the attention block computes the same function."""
+    import torch.nn.functional as F
+    from neuronx_distributed_inference_b200.modules.gqa import _pad_heads
+    from neuronx_distributed_inference_b200.ops import reference as ref
+    torch.manual_seed(0)
+    B, T, nq, nkv, H = 2, 5, 4, 2, 64
+    wqkv, wo, x = torch.randn((nq + 2 * nkv) * D, H, dtype=torch.float64), torch.randn(H, nq * D, dtype=torch.float64), torch.randn(B, T, H, dtype=torch.float64)
+    ang = torch.rand(B, T, D // 2, dtype=torch.float64) * 6.28
+
+    def run(wqkv, wo, d, cos, sin):
+        q, k, v = (x @ wqkv.t()).view(B, T, nq + 2 * nkv, d).split([nq, nkv, nkv], 2)
+        q, k = ref.apply_rope(q, cos, sin, not split), ref.apply_rope(k, cos, sin, not split)
+        return ref.attention_prefill(q, k, v, D ** -0.5, True).reshape(B, T, nq * d) @ wo.t()
+    y0 = run(wqkv, wo, D, ang.cos(), ang.sin())
+    y1 = run(_pad_heads(wqkv, D, Dp, 0, split), _pad_heads(wo, D, Dp, 1, split), Dp,
+             F.pad(ang.cos(), (0, (Dp - D) // 2), value=1.0), F.pad(ang.sin(), (0, (Dp - D) // 2)))
+    assert (y0 - y1).abs().max().item() < 1e-5 * y0.abs().max().item()      # (the reference ops evaluate softmax in fp32)
