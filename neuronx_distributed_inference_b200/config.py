@@ -453,7 +453,9 @@ class MoENeuronConfig(NeuronConfig):
         self.moe_ep_degree = g("moe_ep_degree", None)
         self.transpose_shared_experts_weights = g("transpose_shared_experts_weights", False)
         self.blockwise_matmul_config = g("blockwise_matmul_config", {})
-        self.router_config = g("router_config", None) or {"dtype": "float32", "act_fn": "softmax"}
+        rc = g("router_config", None)
+        self.router_config_explicit = rc is not None      # a user-given router config overrides the family's default activation
+        self.router_config = rc or {"dtype": "float32", "act_fn": "softmax"}
         super().__init__(**kw)
         if self.moe_tp_degree is None:
             self.moe_tp_degree = self.tp_degree // max(self.moe_ep_degree or 1, 1)

@@ -86,8 +86,12 @@ CONFIG_FLAGS = [
     ("qkv-kernel-fuse-residual-add", _FLAG), ("fused-rmsnorm-skip-gamma", _FLAG), ("out-proj-kernel-enabled", _FLAG),
     ("k-cache-transposed", _FLAG), ("logical-nc-config", _INT), ("cc-pipeline-tiling-factor", _INT),
     ("enable-spill-reload-dge", _FLAG), ("scratchpad-page-size", _INT), ("target", _STR),
+    ("attn-block-tkg-nki-kernel-cache-update", _FLAG), ("attn-block-tkg-nki-kernel-cascaded-attention", _FLAG),
+    ("qkv-nki-kernel-enabled", _FLAG), ("qkv-cte-nki-kernel-fuse-rope", _FLAG), ("strided-context-parallel-kernel-enabled", _FLAG),
+    ("enable-cte-modular-flow", _FLAG), ("enable-output-completion-notifications", _FLAG), ("logical-neuron-cores", _INT),
     # run control (:360-408)
     ("skip-warmup", _FLAG), ("apply-seq-ids-mask", _FLAG), ("on-cpu", _FLAG),
+    ("cast-type", dict(choices=["config", "as-declared"], default=None)),
     # B200-native
     ("cuda-graphs", dict(action=argparse.BooleanOptionalAction, default=None)),
     ("fused-collectives", dict(action=argparse.BooleanOptionalAction, default=None)),
@@ -118,6 +122,24 @@ def setup_run_parser(p: argparse.ArgumentParser):
     p.add_argument("--sampling-dp-degree", type=int)
     for flag, kw in CONFIG_FLAGS:
         p.add_argument("--" + flag, **kw)
+    # spellings of the reference that map onto the same config fields (reference :243-275)
+    p.add_argument("--start_rank_id", dest="start_rank_id", type=int)
+    p.add_argument("--local_ranks_size", dest="local_ranks_size", type=int)
+    p.add_argument("--enable-block-kv-layout", dest="is_block_kv_layout", action="store_true", default=None)
+    p.add_argument("--enable-prefix-caching", dest="is_prefix_caching", action="store_true", default=None)
+    p.add_argument("--enable-chunked-prefill", dest="is_chunked_prefill", action="store_true", default=None)
+    p.add_argument("--enable-torch-dist", action="store_true",
+                   help="initialise torch.distributed (gloo) even for a single-rank CPU run (multi-node examples of the reference)")
+    # KV-cache quantisation (reference :186-195)
+    p.add_argument("--k-quant-method", type=str, default="per_tensor_symmetric",
+                   help="per_tensor_symmetric | per_channel_symmetric | per_key_symmetric")
+    p.add_argument("--v-quant-method", type=str, default="per_tensor_symmetric")
+    p.add_argument("--kv-quant-dtype", type=str, default="float8_e4m3fn")
+    p.add_argument("--kv-direct-cast", action=argparse.BooleanOptionalAction, default=True,
+                   help="direct cast to the KV dtype (no scales); --no-kv-direct-cast uses the k/v quantisation methods")
+    # MoE router (reference :210-211)
+    p.add_argument("--router-act-fn", type=str)
+    p.add_argument("--router-dtype", type=str)
     # speculation / draft
     p.add_argument("--draft-model-path", type=str)
     p.add_argument("--compiled-draft-model-path", type=str)
@@ -133,6 +155,9 @@ def setup_run_parser(p: argparse.ArgumentParser):
     p.add_argument("--target-modules", nargs="+")
     p.add_argument("--lora-ckpt-path", dest="lora_ckpt_paths", type=str, action="append")
     p.add_argument("--lora-ckpt-path-cpu", dest="lora_ckpt_paths_cpu", type=str, action="append")
+    p.add_argument("--enable-dynamic-multi-lora", action="store_true")
+    p.add_argument("--lora-ckpt-json", dest="lora_ckpt_json", type=str, default=None,
+                   help='JSON file {"lora-ckpt-dir": ..., "lora-ckpt-paths": {id: path}, "lora-ckpt-paths-cpu": {id: path}}')
     p.add_argument("--adapter-id", dest="adapter_ids", type=str, action="append")
     p.add_argument("--modules-to-not-convert-file", type=str)
     # report / debug (:339-358)
@@ -178,10 +203,35 @@ def create_neuron_config(model_cls, args):
         from .config import LoraServingConfig
         def kv(items):
             return dict(i.split(":", 1) if ":" in i else (os.path.basename(i), i) for i in (items or []))
+        paths, paths_cpu = kv(args.lora_ckpt_paths), kv(args.lora_ckpt_paths_cpu)
+        if args.lora_ckpt_json:      # reference lora_serving/config.py: one JSON file naming every adapter (HBM-resident and host-resident)
+            with open(args.lora_ckpt_json) as f:
+                j = json.load(f)
+            base = j.get("lora-ckpt-dir", "")
+            paths.update({k: os.path.join(base, v) for k, v in (j.get("lora-ckpt-paths") or {}).items()})
+            paths_cpu.update({k: os.path.join(base, v) for k, v in (j.get("lora-ckpt-paths-cpu") or {}).items()})
+        max_cpu = args.max_cpu_loras
+        if args.enable_dynamic_multi_lora and max_cpu <= 0:
+            max_cpu = max(len(paths_cpu), args.max_loras)      # dynamic multi-LoRA = adapters swapped in from host memory
         kw["lora_config"] = LoraServingConfig(max_loras=args.max_loras, max_lora_rank=args.max_lora_rank,
-                                              max_cpu_loras=args.max_cpu_loras, target_modules=args.target_modules,
-                                              lora_ckpt_paths=kv(args.lora_ckpt_paths),
-                                              lora_ckpt_paths_cpu=kv(args.lora_ckpt_paths_cpu))
+                                              max_cpu_loras=max_cpu, target_modules=args.target_modules,
+                                              lora_ckpt_paths=paths, lora_ckpt_paths_cpu=paths_cpu)
+    for f_ in ("is_block_kv_layout", "is_prefix_caching"):
+        if getattr(args, f_, None):
+            kw[f_] = True
+    if kw.get("kv_cache_quant"):
+        from .config import KVQuantizationConfig
+        direct = args.kv_direct_cast
+        # per_key_symmetric == one scale per KV head ("per_head"); per_tensor / per_channel as named
+        mode = {"per_tensor_symmetric": "per_tensor", "per_channel_symmetric": "per_channel", "per_key_symmetric": "per_head"}
+        if not direct and args.k_quant_method != args.v_quant_method:
+            raise ValueError("--k-quant-method and --v-quant-method must agree (one scale mode per cache)")
+        if not direct and args.k_quant_method not in mode:
+            raise ValueError(f"unknown KV quantisation method {args.k_quant_method!r}")
+        kw["kv_quant_config"] = KVQuantizationConfig(dtype=str(args.kv_quant_dtype).replace("torch.", ""),
+                                                     scale_mode="direct_cast" if direct else mode[args.k_quant_method])
+    if args.router_act_fn or args.router_dtype:
+        kw["router_config"] = {"act_fn": args.router_act_fn or "softmax", "dtype": args.router_dtype or "float32"}
     if args.modules_to_not_convert_file:
         with open(args.modules_to_not_convert_file) as f:
             d = json.load(f)
@@ -194,9 +244,10 @@ def create_neuron_config(model_cls, args):
     if args.medusa_tree_json:
         with open(args.medusa_tree_json) as f:
             kw["medusa_tree"] = json.load(f)
-    if args.max_num_seqs:
+    if args.max_num_seqs or getattr(args, "is_chunked_prefill", None):
         from .config import ChunkedPrefillConfig
-        kw["chunked_prefill_config"] = ChunkedPrefillConfig(max_num_seqs=args.max_num_seqs)
+        kw["chunked_prefill_config"] = ChunkedPrefillConfig(**({"max_num_seqs": args.max_num_seqs} if args.max_num_seqs else {}))
+        kw.setdefault("is_block_kv_layout", True)      # chunked prefill runs on the paged cache (config.py validation)
     return model_cls.get_neuron_config_cls()(**kw)
 
 
@@ -215,6 +266,15 @@ def _maybe_relaunch(args, argv):
 def run_inference(model_cls, args):
     """compile -> load -> accuracy -> generate -> benchmark (reference :493-668)."""
     from transformers import AutoTokenizer, GenerationConfig
+    if getattr(args, "enable_torch_dist", False):
+        # reference :245-250 — keep the processes of a multi-node example in step through torch.distributed even when the model
+        # itself is single-rank; rendezvous from the usual MASTER_ADDR / RANK / WORLD_SIZE environment (defaults: one local rank)
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29534")
+            dist.init_process_group("gloo" if args.on_cpu or not torch.cuda.is_available() else "nccl",
+                                    rank=int(os.environ.get("RANK", "0")), world_size=int(os.environ.get("WORLD_SIZE", "1")))
     nc = create_neuron_config(model_cls, args)
     cfg_cls = model_cls.get_config_cls()
     config = cfg_cls(nc, load_config=load_pretrained_config(args.model_path))

@@ -39,8 +39,15 @@ class RouterTopK(nn.Module):
         self.linear_router = nn.Linear(hidden_size, num_experts, bias=bias, dtype=torch.float32, device=device)
         for p in self.linear_router.parameters():
             p.requires_grad_(False)
+        self.compute_dtype = torch.float32      # router_config["dtype"] (reference RouterConfig): precision of the router GEMM
 
     def forward(self, x: torch.Tensor):
+        if self.compute_dtype != torch.float32:
+            cd = self.compute_dtype
+            logits = nn.functional.linear(x.to(cd), self.linear_router.weight.to(cd),
+                                          None if self.linear_router.bias is None else self.linear_router.bias.to(cd)).float()
+            w, idx = ops.moe_route(logits, self.top_k, self.act_fn, self.normalize, self.act_over_topk)
+            return logits, w, idx
         logits = nn.functional.linear(x.float(), self.linear_router.weight, self.linear_router.bias)
         w, idx = ops.moe_route(logits, self.top_k, self.act_fn, self.normalize, self.act_over_topk)
         return logits, w, idx
@@ -199,7 +206,12 @@ def initialize_moe_module(config, device=None, hidden_act: Optional[str] = None,
     I = intermediate_size or getattr(config, "moe_intermediate_size", None) or config.intermediate_size
     if normalize is None:
         normalize = getattr(nc, "normalize_top_k_affinities", True)
+    if getattr(nc, "router_config_explicit", False):      # --router-act-fn / --router-dtype
+        router_act = nc.router_config.get("act_fn", router_act)
     router = RouterTopK(E, k, config.hidden_size, dt, router_act, router_bias, normalize, apply_act_fn_over_topk, device)
+    if getattr(nc, "router_config_explicit", False):
+        from ..config import to_torch_dtype
+        router.compute_dtype = to_torch_dtype(nc.router_config.get("dtype", "float32"))
     experts = ExpertMLPs(E, config.hidden_size, I, hidden_act or config.hidden_act, dt, expert_bias, device, act_fn=act_fn)
     sh = None
     if shared:

@@ -48,3 +48,33 @@ def test_inference_demo_runs_end_to_end_on_cpu(tiny_model_dir, tmp_path):
     assert os.path.exists(os.path.join(art, "neuron_config.json")) or any(f.endswith(".json") for f in os.listdir(art))
     assert os.path.exists(os.path.join(cap, "saved_inputs_1.pt"))
     assert os.path.isdir(os.path.join(str(tmp_path / "snap"), "context_encoding_model"))
+
+
+def test_cli_accepts_every_reference_flag_spelling(tmp_path):
+    """The flags of the reference's `inference_demo run` (inference_demo.py:99-408) that are aliases or feed nested configs."""
+    import json
+    from neuronx_distributed_inference_b200 import inference_demo as demo
+    from neuronx_distributed_inference_b200.models.llama.modeling_llama import NeuronLlamaForCausalLM
+    from neuronx_distributed_inference_b200.models.mixtral.modeling_mixtral import NeuronMixtralForCausalLM
+    lj = tmp_path / "lora.json"
+    lj.write_text(json.dumps({"lora-ckpt-dir": "/adapters", "lora-ckpt-paths": {"a": "a.pt"}, "lora-ckpt-paths-cpu": {"b": "b.pt", "c": "c.pt"}}))
+    base = ["--model-type", "llama", "--task-type", "causal-lm", "run", "--model-path", "m", "--compiled-model-path", "c", "--prompt", "hi",
+            "--on-cpu", "--batch-size", "1", "--seq-len", "64", "--max-context-length", "32"]
+    a = demo.parse_args(base + ["--enable-block-kv-layout", "--pa-num-blocks", "8", "--pa-block-size", "16", "--enable-prefix-caching",
+                                "--kv-cache-quant", "--no-kv-direct-cast", "--k-quant-method", "per_key_symmetric",
+                                "--v-quant-method", "per_key_symmetric", "--kv-quant-dtype", "float8_e4m3fn", "--cast-type", "as-declared",
+                                "--start_rank_id", "0", "--local_ranks_size", "1", "--enable-lora", "--enable-dynamic-multi-lora",
+                                "--lora-ckpt-json", str(lj), "--qkv-nki-kernel-enabled", "--qkv-cte-nki-kernel-fuse-rope",
+                                "--attn-block-tkg-nki-kernel-cache-update", "--attn-block-tkg-nki-kernel-cascaded-attention",
+                                "--strided-context-parallel-kernel-enabled", "--enable-output-completion-notifications",
+                                "--logical-neuron-cores", "2", "--enable-torch-dist"])
+    nc = demo.create_neuron_config(NeuronLlamaForCausalLM, a)
+    assert nc.is_block_kv_layout and nc.is_prefix_caching and nc.cast_type == "as-declared"
+    assert nc.kv_cache_quant and nc.kv_quant_config.scale_mode == "per_head" and nc.kv_quant_config.dtype == "float8_e4m3fn"
+    assert nc.lora_config.dynamic_multi_lora and nc.lora_config.lora_ckpt_paths == {"a": "/adapters/a.pt"}
+    assert set(nc.lora_config.lora_ckpt_paths_cpu) == {"b", "c"} and a.enable_torch_dist
+    b = demo.parse_args([x if x != "llama" else "mixtral" for x in base] + ["--router-act-fn", "sigmoid", "--router-dtype", "bfloat16",
+                                                                          "--enable-chunked-prefill", "--pa-num-blocks", "8",
+                                                                          "--pa-block-size", "16"])
+    mc = demo.create_neuron_config(NeuronMixtralForCausalLM, b)
+    assert mc.router_config == {"act_fn": "sigmoid", "dtype": "bfloat16"} and mc.is_chunked_prefill and mc.is_block_kv_layout
