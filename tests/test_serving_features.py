@@ -205,3 +205,60 @@ def test_continuous_batching_scheduler_example_matches_isolated_generation():
         ids = torch.tensor([r.prompt])
         exp = _greedy(solo, ids, r.max_new_tokens - 1)[0].tolist() if r.max_new_tokens > 1 else [int(solo(ids, attention_mask=torch.ones_like(ids)).tokens)]
         assert r.output == exp[: r.max_new_tokens], r.rid
+
+
+def test_hf_adapter_is_a_generation_mixin_and_runs_hf_machinery():
+    """``HuggingFaceGenerationAdapter`` is a ``PreTrainedModel + GenerationMixin`` (reference hf_adapter.py:104): plain greedy through
+    ``GenerationMixin.generate`` -> our ``_sample`` equals the lean host loop; HF logits processors (min_new_tokens, repetition penalty,
+    a user ``LogitsProcessor``), ``StoppingCriteriaList`` objects and streamers are honoured."""
+    from transformers import GenerationConfig, LogitsProcessor, LogitsProcessorList, PreTrainedModel, StoppingCriteria, StoppingCriteriaList
+    from transformers.generation.utils import GenerationMixin
+    from neuronx_distributed_inference_b200.utils.hf_adapter import HuggingFaceGenerationAdapter
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    app = build_random_llama(dict(vocab_size=160), batch_size=2, seq_len=64, max_context_length=16, device="cpu", dtype="float32",
+                             output_logits=True, seed=3)
+    ad = HuggingFaceGenerationAdapter(app)
+    assert isinstance(ad, PreTrainedModel) and isinstance(ad, GenerationMixin) and ad.can_generate()
+    ids = torch.randint(1, 160, (2, 7))
+    mask = torch.ones_like(ids)
+    lean = ad.generate(ids, attention_mask=mask, max_new_tokens=10)
+    hf = ad.generate(ids, attention_mask=mask, max_new_tokens=10, use_hf_generate=True, do_sample=False)
+    assert torch.equal(lean, hf)
+
+    class Ban(LogitsProcessor):                      # forbid the token greedy decoding would pick first
+        def __init__(self, tok):
+            self.tok = tok
+
+        def __call__(self, input_ids, scores):
+            scores[:, self.tok] = float("-inf")
+            return scores
+    banned = int(lean[0, 7])
+    out = ad.generate(ids, attention_mask=mask, max_new_tokens=6, logits_processor=LogitsProcessorList([Ban(banned)]), do_sample=False)
+    assert banned not in out[:, 7:].tolist()[0] and out.shape == (2, 13)
+
+    class StopAt(StoppingCriteria):
+        def __call__(self, input_ids, scores, **kw):
+            return torch.full((input_ids.shape[0],), input_ids.shape[1] >= 10, dtype=torch.bool)
+    out = ad.generate(ids, attention_mask=mask, max_new_tokens=20, stopping_criteria=StoppingCriteriaList([StopAt()]), do_sample=False)
+    assert out.shape[1] == 10 and torch.equal(out, lean[:, :10])
+
+    eos = int(lean[0, 8])                            # min_new_tokens keeps EOS away until 5 tokens are out
+    gc = GenerationConfig(max_new_tokens=8, min_new_tokens=5, eos_token_id=eos, pad_token_id=0, do_sample=False)
+    out = ad.generate(ids, attention_mask=mask, generation_config=gc)
+    assert eos not in out[0, 7:12].tolist()
+
+    class Collect:
+        def __init__(self):
+            self.items, self.ended = [], False
+
+        def put(self, v):
+            self.items.append(v.clone())
+
+        def end(self):
+            self.ended = True
+    st = Collect()
+    out = ad.generate(ids[:1], attention_mask=mask[:1], max_new_tokens=4, streamer=st, do_sample=False, return_dict_in_generate=True,
+                      output_scores=True)
+    # (HF's generate() hands the prompt to the streamer first, then one item per new token)
+    assert st.ended and len(st.items) == 5 and torch.equal(st.items[0], ids[:1])
+    assert torch.equal(torch.cat(st.items[1:]), out.sequences[0, 7:]) and len(out.scores) == 4
