@@ -71,7 +71,7 @@ void rmsnorm_launch(const void* x, const void* res_in, const void* w, void* y, v
 
 void rope_kv_append_launch(const void* qkv, const float* cos, const float* sin, void* q_out, void* k_cache, void* v_cache,
                            const int* lines, const int* positions, const void* q_norm, const void* k_norm, float eps, int B,
-                           int T, int nq, int nkv, int D, int L, int S, cudaStream_t stream);
+                           int T, int nq, int nkv, int D, int L, int S, cudaStream_t stream, void* k_out = nullptr, void* v_out = nullptr);
 void kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* lines,
                       const int* positions, int B, int T, int H, int row_bytes, int L, int S, cudaStream_t stream);
 void paged_kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* slots, int ntok,

@@ -42,6 +42,15 @@ std::tuple<at::Tensor, at::Tensor> rmsnorm(const at::Tensor& x, const at::Tensor
 
 struct Scratch {
   at::Tensor f, i, tickets, gemv_ws, gemv_tickets;
+  // Buffers that were outgrown are RETIRED, never freed: CUDA graphs captured earlier hold their addresses (a decode graph of a
+  // small sequence bucket keeps replaying after a larger bucket made the workspace grow); freeing them would hand the memory to
+  // the caching allocator while those graphs still write their split-KV partials / stream-K tickets there.
+  std::vector<at::Tensor> retired;
+  void grow(at::Tensor& t, int64_t n, const at::TensorOptions& o, bool zero) {
+    if (t.defined() && t.numel() >= n) return;
+    if (t.defined()) retired.push_back(t);
+    t = zero ? at::zeros({n}, o) : at::empty({n}, o);
+  }
 };
 static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t nt);
 
@@ -53,9 +62,8 @@ static void run_gemv(GemvParams& p, int mode, const at::Device& dev) {
     const int n_tiles = gemv2_ntiles(p.N, glu);
     const int64_t need = (int64_t)n_tiles * gemv2_pmax(p.N, p.K, glu, wt) * 128;
     auto o = at::TensorOptions().device(dev);
-    if (!s.gemv_ws.defined() || s.gemv_ws.numel() < need) s.gemv_ws = at::empty({std::max<int64_t>(need, 4 << 20)}, o.dtype(at::kFloat));
-    if (!s.gemv_tickets.defined() || s.gemv_tickets.numel() < n_tiles)
-      s.gemv_tickets = at::zeros({std::max<int64_t>(n_tiles, 1 << 15)}, o.dtype(at::kInt));
+    s.grow(s.gemv_ws, std::max<int64_t>(need, 4 << 20), o.dtype(at::kFloat), false);
+    s.grow(s.gemv_tickets, std::max<int64_t>(n_tiles, 1 << 15), o.dtype(at::kInt), true);
     gemv2_launch(p, mode, s.gemv_ws.data_ptr<float>(), reinterpret_cast<unsigned*>(s.gemv_tickets.data_ptr<int>()), cur_stream());
   } else {
     TORCH_CHECK(wt == 0, "gemv: 8-bit weights need the TMA streaming kernel");
@@ -355,6 +363,32 @@ at::Tensor rope_kv_append(const at::Tensor& qkv, const at::Tensor& cos, const at
   return q;
 }
 
+// prefill flavour: the same single pass also returns the rotated k and the v of the new tokens as contiguous [B, T, nkv, D]
+std::tuple<at::Tensor, at::Tensor, at::Tensor> rope_kv_split_append(const at::Tensor& qkv, const at::Tensor& cos, const at::Tensor& sin,
+                                                                   at::Tensor& k_cache, at::Tensor& v_cache, const at::Tensor& lines,
+                                                                   const at::Tensor& positions, int64_t nq, int64_t nkv, int64_t D,
+                                                                   const c10::optional<at::Tensor>& q_norm,
+                                                                   const c10::optional<at::Tensor>& k_norm, double eps) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.dim() == 3 && qkv.is_contiguous() && is_bf16(qkv) && is_bf16(k_cache));
+  const int B = qkv.size(0), T = qkv.size(1);
+  TORCH_CHECK(qkv.size(2) == (nq + 2 * nkv) * D);
+  TORCH_CHECK(cos.scalar_type() == at::kFloat && cos.is_contiguous() && sin.is_contiguous() &&
+              cos.numel() == (int64_t)B * T * D / 2 && sin.numel() == cos.numel());
+  TORCH_CHECK(k_cache.dim() == 4 && k_cache.size(1) == nkv && k_cache.size(3) == D && k_cache.is_contiguous() &&
+              v_cache.is_contiguous());
+  TORCH_CHECK(lines.scalar_type() == at::kInt && positions.scalar_type() == at::kInt && positions.is_contiguous() &&
+              lines.numel() == B && positions.numel() == B * T);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  auto q = at::empty({B, T, nq, D}, qkv.options());
+  auto k = at::empty({B, T, nkv, D}, qkv.options());
+  auto v = at::empty({B, T, nkv, D}, qkv.options());
+  rope_kv_append_launch(qkv.data_ptr(), cos.data_ptr<float>(), sin.data_ptr<float>(), q.data_ptr(), k_cache.data_ptr(),
+                        v_cache.data_ptr(), lines.data_ptr<int>(), positions.data_ptr<int>(), optr(q_norm), optr(k_norm),
+                        (float)eps, B, T, (int)nq, (int)nkv, (int)D, (int)k_cache.size(0), (int)k_cache.size(2), cur_stream(),
+                        k.data_ptr(), v.data_ptr());
+  return {q, k, v};
+}
+
 void kv_append(at::Tensor& k_cache, at::Tensor& v_cache, const at::Tensor& k_new, const at::Tensor& v_new,
                const at::Tensor& lines, const at::Tensor& positions) {
   TORCH_CHECK(k_new.is_cuda() && k_new.dim() == 4 && k_new.is_contiguous() && v_new.is_contiguous());
@@ -385,9 +419,10 @@ static Scratch& scratch(const at::Device& dev, int64_t nf, int64_t ni, int64_t n
   static std::map<int, Scratch> all;
   auto& s = all[dev.index()];
   auto o = at::TensorOptions().device(dev);
-  if (!s.f.defined() || s.f.numel() < nf) s.f = at::empty({std::max<int64_t>(nf, 1 << 16)}, o.dtype(at::kFloat));
-  if (!s.i.defined() || s.i.numel() < ni) s.i = at::empty({std::max<int64_t>(ni, 1 << 16)}, o.dtype(at::kInt));
-  if (!s.tickets.defined() || s.tickets.numel() < nt) s.tickets = at::zeros({std::max<int64_t>(nt, 1 << 14)}, o.dtype(at::kInt));
+  // generous first sizes (16 MB of partials covers B = 8, 8 kv heads, 32 splits at head_dim 128) so that growth is rare
+  s.grow(s.f, std::max<int64_t>(nf, 4 << 20), o.dtype(at::kFloat), false);
+  s.grow(s.i, std::max<int64_t>(ni, 1 << 16), o.dtype(at::kInt), false);
+  s.grow(s.tickets, std::max<int64_t>(nt, 1 << 14), o.dtype(at::kInt), true);
   return s;
 }
 
@@ -724,6 +759,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_free", &nxdi::symm_free);
   m.def("symm_as_tensor", &nxdi::symm_as_tensor);
   m.def("rope_kv_append", &nxdi::rope_kv_append);
+  m.def("rope_kv_split_append", &nxdi::rope_kv_split_append);
   m.def("kv_append", &nxdi::kv_append);
   m.def("paged_kv_append", &nxdi::paged_kv_append);
   m.def("argmax", &nxdi::argmax);

@@ -34,7 +34,7 @@ struct GemmParams {
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, N_out] or null
   __nv_bfloat16* c;               // [M, N_out]
-  int M, N, K, ldc, act;          // act: 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up  (N_out = N/2 when act != 0)
+  int M, N, K, ldc, act;          // act: 0 none, 1 silu*up, 2 gelu_tanh*up, 3 gelu*up, 4 GPT-OSS clamped SwiGLU  (N_out = N/2 when act != 0)
   int m_tiles, n_tiles;           // tile grid (CTA tiles of TM*128 x 128 output columns; 64 output features for GLU)
   // fp8 (e4m3 x e4m3 -> fp32, tcgen05 kind::f8f6f4): acc * a_scale[row] * w_scale[col] (dynamic per-token activation scale,
   // per-output-channel or per-tensor weight scale); null for bf16
@@ -330,7 +330,12 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tcgen05_kernel(const __gri
           if (glu) {
             float up = __uint_as_float(vu[j + e]) * up_s;
             if (p.bias && in) up += __bfloat162float(p.bias[cur_eo + n_out + col0 + j + e]);
-            a = (p.act == 1 ? silu(a) : (p.act == 2 ? gelu_tanh(a) : gelu_erf(a))) * up;
+            if (p.act == 4) {   // GPT-OSS clamped SwiGLU: (clamp(up, -7, 7) + 1) * g * sigmoid(1.702 g), g = min(gate, 7)
+              const float g = fminf(a, 7.f), u = fminf(fmaxf(up, -7.f), 7.f);
+              a = (u + 1.f) * g * (1.f / (1.f + __expf(-1.702f * g)));
+            } else {
+              a = (p.act == 1 ? silu(a) : (p.act == 2 ? gelu_tanh(a) : gelu_erf(a))) * up;
+            }
           }
           f[e] = a;
         }

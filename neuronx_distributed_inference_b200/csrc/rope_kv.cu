@@ -12,6 +12,7 @@ template <int D>
 __global__ void rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv,  // [B*T, (nq+2nkv)*D]
                                       const float* __restrict__ cos, const float* __restrict__ sin,  // [B*T, D/2]
                                       __nv_bfloat16* __restrict__ q_out,                              // [B*T, nq, D]
+                                      __nv_bfloat16* __restrict__ k_out, __nv_bfloat16* __restrict__ v_out,   // [B*T, nkv, D] or null
                                       __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
                                       const int* __restrict__ lines, const int* __restrict__ positions,  // [B], [B*T]
                                       const __nv_bfloat16* __restrict__ q_norm, const __nv_bfloat16* __restrict__ k_norm,
@@ -50,9 +51,14 @@ __global__ void rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv,  //
     dst[i + HALF] = __float2bfloat16(x2);
     return;
   }
+  const int kvh = is_k ? head - nq : head - nq - nkv;
+  if (k_out != nullptr) {   // prefill: attention consumes the fresh (rotated) k / v directly, no cache read
+    __nv_bfloat16* o = (is_k ? k_out : v_out) + ((size_t)bt * nkv + kvh) * D;
+    o[i] = __float2bfloat16(x1);
+    o[i + HALF] = __float2bfloat16(x2);
+  }
   const int line = lines[b], pos = positions[bt];
   if (line < 0 || line >= L || pos < 0 || pos >= S) return;  // masked sequence / padding: skip the write
-  const int kvh = is_k ? head - nq : head - nq - nkv;
   __nv_bfloat16* cache = is_k ? k_cache : v_cache;
   __nv_bfloat16* dst = cache + (((size_t)line * nkv + kvh) * S + pos) * D;
   dst[i] = __float2bfloat16(x1);
@@ -61,11 +67,12 @@ __global__ void rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv,  //
 
 void rope_kv_append_launch(const void* qkv, const float* cos, const float* sin, void* q_out, void* k_cache, void* v_cache,
                            const int* lines, const int* positions, const void* q_norm, const void* k_norm, float eps, int B,
-                           int T, int nq, int nkv, int D, int L, int S, cudaStream_t stream) {
+                           int T, int nq, int nkv, int D, int L, int S, cudaStream_t stream, void* k_out, void* v_out) {
   dim3 grid(B * T, nq + 2 * nkv);
 #define LAUNCH(DD)                                                                                                   \
   launch_pdl(rope_kv_append_kernel<DD>, grid, dim3(DD / 2), 0, stream, reinterpret_cast<const __nv_bfloat16*>(qkv), cos, \
-             sin, reinterpret_cast<__nv_bfloat16*>(q_out), reinterpret_cast<__nv_bfloat16*>(k_cache),                 \
+             sin, reinterpret_cast<__nv_bfloat16*>(q_out), reinterpret_cast<__nv_bfloat16*>(k_out),                   \
+             reinterpret_cast<__nv_bfloat16*>(v_out), reinterpret_cast<__nv_bfloat16*>(k_cache),                      \
              reinterpret_cast<__nv_bfloat16*>(v_cache), lines, positions, reinterpret_cast<const __nv_bfloat16*>(q_norm), \
              reinterpret_cast<const __nv_bfloat16*>(k_norm), eps, T, nq, nkv, L, S)
   if (D == 128) LAUNCH(128);

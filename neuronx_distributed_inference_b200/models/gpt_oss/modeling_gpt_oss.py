@@ -25,6 +25,9 @@ def gpt_oss_glu(h: torch.Tensor) -> torch.Tensor:
     return ((up + 1) * gate * torch.sigmoid(gate * ALPHA)).to(h.dtype)
 
 
+gpt_oss_glu.kernel_act = "gpt_oss_glu"      # epilogue of the grouped tcgen05 GEMM (csrc/gemm_tcgen05.cu, act 4)
+
+
 class GptOssInferenceConfig(LlamaInferenceConfig):
     def get_required_attributes(self):
         return super().get_required_attributes() + ["num_local_experts", "num_experts_per_tok"]
@@ -40,7 +43,8 @@ def _sliding(config, i):
 
 
 class NeuronGptOssModel(NeuronLlamaModel):
-    graph_safe = False
+    graph_safe = False            # the PyTorch expert dispatch synchronises ...
+    moe_decode_graph_safe = True  # ... the grouped-GEMM path (biases + clamped SwiGLU in the epilogue) does not
 
     def make_layer(self, config, i, rotary, device):
         nc = config.neuron_config

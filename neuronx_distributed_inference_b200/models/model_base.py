@@ -105,8 +105,14 @@ class NeuronBaseModel(nn.Module):
                 continue
             moe = layer.mlp
             ex = getattr(moe, "expert_mlps", None)
-            if ex is None or getattr(moe, "early_affinity_modulation", False) or ex.act != "silu_mul" or ex.act_fn is not None \
-                    or ex.gate_up_bias is not None or ex.down_bias is not None or ex.gate_up_proj.dtype != torch.bfloat16:
+            if ex is None or ex.gate_up_proj.dtype != torch.bfloat16:
+                return False
+            plain = (not getattr(moe, "early_affinity_modulation", False) and ex.act == "silu_mul" and ex.act_fn is None
+                     and ex.gate_up_bias is None and ex.down_bias is None)        # moe_decode kernels (T <= 8)
+            kact = ex.act if ex.act_fn is None else getattr(ex.act_fn, "kernel_act", None)
+            grouped = (kact in ops._MOE_ACTS and ex.gate_up_proj.shape[2] % 64 == 0 and ex.down_proj.shape[2] % 64 == 0
+                       and ex.gate_up_proj.shape[0] <= 512 and getattr(ex, "gated", True))   # grouped tcgen05 GEMMs (any T)
+            if not (plain or grouped):
                 return False
         return True
 

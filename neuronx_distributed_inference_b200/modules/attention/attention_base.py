@@ -165,8 +165,8 @@ class AttentionBase(nn.Module):
 
     def _simple(self) -> bool:
         """Eligible for the fused rope+norm+append kernel."""
-        return (self.use_rope and not self.rope_interleaved and self.clip_qkv is None
-                and self.qk_norm in (None, "rms_pre_rope"))
+        # (clip_qkv is applied to the projection's output before any of the fused kernels consume it)
+        return (self.use_rope and not self.rope_interleaved and self.qk_norm in (None, "rms_pre_rope"))
 
     def forward(self, hidden: torch.Tensor, meta: AttnMeta, kv_mgr, norm_weight=None, norm_eps=None,
                 norm_offset: float = 0.0, residual: Optional[torch.Tensor] = None, lora=None) -> torch.Tensor:
@@ -212,9 +212,17 @@ class AttentionBase(nn.Module):
             kn = self.k_layernorm.weight if self.qk_norm == "rms_pre_rope" else None
             k = v = None
             if meta.is_prefill:
-                # prefill attention consumes the fresh k/v directly (no cache read): split here
-                q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
-                kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, wpos, lines)
+                # prefill attention consumes the fresh k/v directly (no cache read): split here.  Plain bf16 cache: split + q/k norm +
+                # RoPE + cache write in one kernel; managers with their own update logic (quantised, rolling, hybrid) keep theirs
+                qkvs = None
+                if type(kv_mgr).__name__ == "KVCacheManager" and not roll and getattr(kv_mgr, "k_scale", None) is None \
+                        and meta.capture is None:
+                    qkvs = ops.rope_kv_split_append(qkv, cos, sin, k_cache, v_cache, lines, wpos, nq, nkv, D, qn, kn, self.qk_norm_eps)
+                if qkvs is not None:
+                    q, k, v = qkvs
+                else:
+                    q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
+                    kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, wpos, lines)
             elif (meta.active_mask is None and self.attention_chunk_size is None and not self.softcap
                   and getattr(kv_mgr, "k_scale", None) is None and meta.capture is None):
                 o = ops.rope_attention_decode(qkv, cos, sin, k_cache, v_cache, lines, wpos, hpos,
@@ -281,7 +289,7 @@ class AttentionBase(nn.Module):
     def chain_eligible(self, kv_mgr, dtype) -> bool:
         """This layer's decode step can run as [rope+append kernel, attention kernel] around the persistent GEMV chain."""
         k_cache, _ = kv_mgr.get_kv_by_layer_id(self.layer_idx)
-        return (self._simple() and self.kv_group is None and k_cache.dtype == dtype and self.head_dim in (64, 128)
+        return (self._simple() and self.clip_qkv is None and self.kv_group is None and k_cache.dtype == dtype and self.head_dim in (64, 128)
                 and getattr(self.qkv_proj, "scale", None) is None and getattr(self.o_proj, "scale", None) is None
                 and not self.qkv_proj.sequence_parallel_enabled and self.attention_chunk_size is None and not self.softcap)
 

@@ -137,6 +137,7 @@ def linear(x, w, bias=None, norm_weight=None, norm_eps: float = 1e-6, norm_offse
 
 
 _DEQ_SCRATCH = {}
+_DEQ_RETIRED = []
 
 
 def _dequant_scratch(w):
@@ -144,6 +145,8 @@ def _dequant_scratch(w):
     stream order makes the reuse by the next layer safe)."""
     buf = _DEQ_SCRATCH.get(w.device)
     if buf is None or buf.numel() < w.numel():
+        if buf is not None:
+            _DEQ_RETIRED.append(buf)      # never freed: CUDA graphs captured with the smaller scratch still hold its address
         buf = torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device)
         _DEQ_SCRATCH[w.device] = buf
     return buf
@@ -211,6 +214,22 @@ def rope_kv_append(qkv, cos, sin, k_cache, v_cache, seq_ids, positions, n_q, n_k
     k = ref.apply_rope(k, cos, sin, interleaved)
     kv_append(k_cache, v_cache, k, v, seq_ids, positions)
     return q
+
+
+def rope_kv_split_append(qkv, cos, sin, k_cache, v_cache, seq_ids, positions, n_q, n_kv, head_dim, q_norm=None, k_norm=None,
+                         norm_eps: float = 1e-6):
+    """Prefill: split the fused QKV projection, per-head q/k RMSNorm, RoPE, cache write AND the contiguous rotated k / v of the new
+    tokens for the flash kernel — ONE kernel (csrc/rope_kv.cu) instead of the split / rotate / cat / append chain.
+    -> (q [B,T,n_q,D], k [B,T,n_kv,D], v [B,T,n_kv,D]) or None when the kernel does not apply."""
+    B, T = positions.shape
+    D = head_dim
+    if (_use_cuda(qkv) and qkv.dtype == torch.bfloat16 and k_cache.dtype == qkv.dtype and D in (64, 128, 256) and cos is not None
+            and cos.shape[-1] * 2 == D):
+        stats["rope_kv_split_append"] += 1
+        return _C().rope_kv_split_append(qkv.reshape(B, T, -1).contiguous(), cos.contiguous(), sin.contiguous(), k_cache, v_cache,
+                                         seq_ids.to(torch.int32), positions.to(torch.int32).contiguous(), n_q, n_kv, D, q_norm, k_norm,
+                                         norm_eps)
+    return None
 
 
 def kv_append(k_cache, v_cache, k_new, v_new, seq_ids, positions):
@@ -350,6 +369,8 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
         # weight-only 8-bit experts: dequantise the selected experts on the fly
         return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias, act_fn, scale_input,
                                gate_up_scale, down_scale)
+    # activations with a kernel implementation: the named GLU ones, or a callable that names its kernel twin (``kernel_act``)
+    kact = act if act_fn is None else getattr(act_fn, "kernel_act", None)
     if (_use_cuda(x) and x.dtype in _FAST_DTYPES and w_gate_up.dtype == x.dtype and act == "silu_mul"
             and act_fn is None and gate_up_bias is None and down_bias is None and N <= GEMV_MAX_TOKENS and not scale_input
             and w_gate_up.is_contiguous() and w_down.is_contiguous() and topk_i.dim() == 2
@@ -359,13 +380,13 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
                                topk_i.to(torch.int32).contiguous(), int(expert_offset))
     # prefill-sized batches: device-side permutation + grouped tcgen05 GEMMs (static shapes: replays under CUDA graphs)
     if (_use_cuda(x) and _MOE_GROUPED and x.dtype == torch.bfloat16 and w_gate_up.dtype == x.dtype and w_down.dtype == x.dtype
-            and act in _MOE_ACTS and act_fn is None and topk_i.dim() == 2 and topk_i.shape[1] <= 64
+            and kact in _MOE_ACTS and topk_i.dim() == 2 and topk_i.shape[1] <= 64
             and w_gate_up.is_contiguous() and w_down.is_contiguous() and x.shape[1] % 64 == 0 and w_down.shape[2] % 64 == 0
             and w_gate_up.shape[0] <= 512
             and (gate_up_bias is None or gate_up_bias.dtype == x.dtype) and (down_bias is None or down_bias.dtype == x.dtype)):
         stats["moe_grouped"] += 1
         return _C().moe_grouped(x.contiguous(), w_gate_up, w_down, topk_w.float().contiguous(), topk_i.to(torch.int32).contiguous(),
-                                int(expert_offset), _MOE_ACTS[act], bool(scale_input),
+                                int(expert_offset), _MOE_ACTS[kact], bool(scale_input),
                                 None if gate_up_bias is None else gate_up_bias.contiguous(),
                                 None if down_bias is None else down_bias.contiguous(), None, None)
     return ref.moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act, expert_offset, gate_up_bias, down_bias,
@@ -373,7 +394,7 @@ def moe_experts(x, w_gate_up, w_down, topk_w, topk_i, act="silu_mul", expert_off
 
 
 _MOE_GROUPED = os.environ.get("NXDI_B200_MOE_GROUPED", "1") == "1"
-_MOE_ACTS = {"silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3}
+_MOE_ACTS = {"silu_mul": 1, "gelu_tanh_mul": 2, "gelu_mul": 3, "gpt_oss_glu": 4}
 
 
 def rmsnorm_quant(x, weight, eps, clamp=float("inf"), offset: float = 0.0):

@@ -320,7 +320,11 @@ class SubModelRunner:
         self._symm_even()
         g.graph.replay()
         o = g.out
-        return ModelOutput(tokens=o.tokens, logits=o.logits, hidden_states=o.hidden_states)
+        # logits / hidden states are handed out as copies: the graph's static output buffer is overwritten by the next replay, and a
+        # caller that keeps `out.logits` across calls (accuracy checks, logit matching) must not see it change under its feet.  The
+        # sampled tokens stay a view (8 bytes per row, consumed immediately by every loop in this repo; the async path reads them in place).
+        return ModelOutput(tokens=o.tokens, logits=None if o.logits is None else o.logits.clone(),
+                           hidden_states=None if o.hidden_states is None else o.hidden_states.clone())
 
     # ---- decode ------------------------------------------------------------------------------
     def _pick_batch_bucket(self, B):
@@ -372,8 +376,8 @@ class SubModelRunner:
         self.n_launch += 1
         o = g.out
         return ModelOutput(tokens=None if o.tokens is None else o.tokens[:B],
-                           logits=None if o.logits is None else o.logits[:B],
-                           hidden_states=None if o.hidden_states is None else o.hidden_states[:B])
+                           logits=None if o.logits is None else o.logits[:B].clone(),
+                           hidden_states=None if o.hidden_states is None else o.hidden_states[:B].clone())
 
     def _capture(self, key, Bb, T, kwargs) -> _Graph:
         dev = self.device

@@ -147,6 +147,43 @@ def test_mixtral_decode_runs_under_cuda_graphs_with_moe_kernels():
     assert torch.equal(got, run(mk(False)))
 
 
+def test_gpt_oss_and_dbrx_run_under_cuda_graphs_with_grouped_moe():
+    """Families whose experts the moe_decode kernels do not cover (GPT-OSS: biases + clamped SwiGLU) or whose prefill used to be eager
+    (every MoE): routed experts through the grouped tcgen05 GEMMs at every token count -> prefill AND decode replay from CUDA graphs,
+    tokens equal the graph-free run."""
+    from neuronx_distributed_inference_b200 import ops
+    from neuronx_distributed_inference_b200.models.dbrx.modeling_dbrx import NeuronDbrxForCausalLM
+    from neuronx_distributed_inference_b200.models.gpt_oss.modeling_gpt_oss import NeuronGptOssForCausalLM
+    from neuronx_distributed_inference_b200.utils.testing import build_random_llama
+    cases = [
+        (NeuronGptOssForCausalLM, dict(hidden_size=256, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                       vocab_size=512, head_dim=64, num_local_experts=4, num_experts_per_tok=2, sliding_window=16,
+                                       layer_types=["sliding_attention", "full_attention"])),
+        (NeuronDbrxForCausalLM, dict(d_model=256, n_heads=4, n_layers=2, max_seq_len=256, vocab_size=512,
+                                     attn_config=dict(kv_n_heads=2, clip_qkv=8.0, rope_theta=10000.0),
+                                     ffn_config=dict(ffn_hidden_size=256, moe_num_experts=4, moe_top_k=2, hidden_size=256))),
+    ]
+    for cls, hf in cases:
+        def mk(graphs):
+            return build_random_llama(hf, batch_size=2, seq_len=128, max_context_length=32, device="cuda", dtype="bfloat16", seed=9,
+                                      app_cls=cls, cuda_graphs=graphs)
+        app = mk(True)
+        assert app.model.graph_safe and app.token_generation_model.use_graphs, cls.__name__
+        ids = torch.randint(1, 512, (2, 20))
+
+        def run(a):
+            t = a(ids, attention_mask=torch.ones_like(ids)).tokens.view(2, 1).cpu()
+            out = [t]
+            for i in range(6):
+                t = a(t, position_ids=torch.full((2, 1), 20 + i, dtype=torch.int32)).tokens.view(2, 1).cpu()
+                out.append(t)
+            return torch.cat(out, 1)
+        before = ops.stats["moe_grouped"]
+        got = run(app)
+        assert ops.stats["moe_grouped"] > before and len(app.token_generation_model._graphs) > 0, cls.__name__
+        assert torch.equal(got, run(mk(False))), cls.__name__
+
+
 @pytest.mark.parametrize("cfg", [
     dict(hidden_size=1024, intermediate_size=2816, num_hidden_layers=3, num_attention_heads=8, num_key_value_heads=2, head_dim=128),
     dict(hidden_size=2048, intermediate_size=1792, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=1, head_dim=128),
@@ -206,10 +243,10 @@ def test_odd_head_dims_run_on_padded_kernels(head_dim, heads, kv, monkeypatch):
     def logits_of(app):
         app.reset()
         out = app(ids, attention_mask=mask)
-        lg = [out.logits[:, -1].float()]
+        lg = [out.logits[:, -1].float().clone()]
         pos = torch.full((2, 1), 12, dtype=torch.int32)
         for i, tok in enumerate(feed):
-            lg.append(app(tok, position_ids=pos + i).logits[:, -1].float())
+            lg.append(app(tok, position_ids=pos + i).logits[:, -1].float().clone())
         return torch.stack(lg)
 
     def build(pad):

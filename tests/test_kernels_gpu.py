@@ -37,7 +37,7 @@ def test_rmsnorm(rows, H):
 
 @pytest.mark.parametrize("T", [1, 2, 3, 8])
 @pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (1000 * 16, 2048), (4096, 14336), (512, 512), (40, 256),
-                                 (3072, 4096), (64128, 4096), (4096, 7168), (4096, 2048), (4096, 1792), (768, 4096), (4096, 320)])
+                                 (3072, 4096), (64128, 4096), (4096, 7168), (4096, 2048), (4096, 1792), (768, 4096), (4096, 320), (400, 512)])
 def test_gemv(T, N, K):
     x = torch.randn(T, K, device=DEV, dtype=torch.bfloat16)
     w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
@@ -218,7 +218,9 @@ def test_gemm_tcgen05_norm_swiglu(M, N, K):
 
 
 @pytest.mark.parametrize("D,nq,nkv,T,ctx,qk_norm", [(128, 32, 8, 1, 200, False), (128, 8, 2, 4, 1500, False), (64, 14, 2, 1, 77, True),
-                                                     (128, 4, 1, 8, 40, True)])
+                                                     (128, 4, 1, 8, 40, True),
+                                                     # multi-head attention (one q head per kv head: a single row per CTA), short contexts
+                                                     (128, 4, 4, 1, 12, False), (64, 8, 8, 1, 50, False), (128, 32, 32, 1, 130, False)])
 def test_rope_attention_decode_equals_two_kernel_path(D, nq, nkv, T, ctx, qk_norm):
     """RoPE + q/k norm + cache append folded into the attention kernel == rope_kv_append kernel + attention kernel."""
     torch.manual_seed(0)
@@ -241,6 +243,43 @@ def test_rope_attention_decode_equals_two_kernel_path(D, nq, nkv, T, ctx, qk_nor
     assert ops.stats["rope_attn_decode"] > 0
     assert torch.equal(k1, k2) and torch.equal(v1, v2)
     assert (got.float() - exp.float()).abs().max().item() <= 2e-2
+    # and against the fp32 PyTorch definition of the whole step (RoPE, append, attention over the cache lines)
+    qr, kr, vr = qkv.view(B, T, nq + 2 * nkv, D).float().split([nq, nkv, nkv], 2)
+    if qk_norm:
+        qr, kr = ref.rmsnorm(qr, qn.float(), 1e-6), ref.rmsnorm(kr, kn.float(), 1e-6)
+    qr, kr = ref.apply_rope(qr, cos, sin, False), ref.apply_rope(kr, cos, sin, False)
+    k3, v3 = kc.float().clone(), vc.float().clone()
+    ref.kv_append(k3, v3, kr, vr, lines, pos)
+    full = ref.attention_decode(qr, k3, v3, lines, pos, D ** -0.5)
+    assert _rel(got, full) < 2e-2, _rel(got, full)
+
+
+@pytest.mark.parametrize("D,nq,nkv,B,T,qk_norm", [(128, 8, 2, 2, 300, False), (64, 6, 2, 1, 77, True), (128, 4, 4, 3, 16, True)])
+def test_prefill_split_rope_append_single_kernel(D, nq, nkv, B, T, qk_norm):
+    """csrc/rope_kv.cu prefill flavour: q, rotated k, v (contiguous) + cache write from ONE pass over the fused QKV output."""
+    torch.manual_seed(0)
+    dev, dt = "cuda", torch.bfloat16
+    L, S = B + 1, 512
+    qkv = torch.randn(B, T, (nq + 2 * nkv) * D, device=dev, dtype=dt)
+    kc = torch.zeros(L, nkv, S, D, device=dev, dtype=dt)
+    vc = torch.zeros_like(kc)
+    lines = torch.arange(B, device=dev, dtype=torch.int32)
+    pos = torch.arange(T, device=dev, dtype=torch.int32).view(1, T).repeat(B, 1)
+    pos[0, -3:] = -1                                      # padding: not written to the cache
+    ang = torch.rand(B, T, D // 2, device=dev) * 6.28
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    qn = (1 + 0.1 * torch.randn(D, device=dev)).to(dt) if qk_norm else None
+    kn = (1 + 0.1 * torch.randn(D, device=dev)).to(dt) if qk_norm else None
+    q, k, v = ops.rope_kv_split_append(qkv, cos, sin, kc, vc, lines, pos, nq, nkv, D, qn, kn, 1e-6)
+    k2, v2 = torch.zeros_like(kc), torch.zeros_like(vc)
+    q_ref = ops.rope_kv_append(qkv, cos, sin, k2, v2, lines, pos, nq, nkv, D, False, qn, kn, 1e-6)     # the decode-time kernel
+    assert torch.equal(q, q_ref) and torch.equal(kc, k2) and torch.equal(vc, v2)
+    qr, kr, vr = qkv.view(B, T, nq + 2 * nkv, D).split([nq, nkv, nkv], 2)
+    if qk_norm:
+        kr = ref.rmsnorm(kr, kn, 1e-6)
+    kr = ref.apply_rope(kr, cos, sin, False)
+    assert (k.float() - kr.float()).abs().max().item() < 3e-2 and torch.equal(v, vr)
+    assert torch.equal(kc[B - 1, :, :T - 3], k[B - 1, :T - 3].transpose(0, 1)) and float(kc[0, :, T - 3:T].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("T,k,E,H,I,off", [(2, 2, 8, 4096, 1792, 0), (1, 4, 16, 2048, 768, 0), (8, 2, 4, 1024, 512, 2), (3, 8, 64, 2048, 256, 16)])
@@ -267,6 +306,8 @@ def test_moe_decode_kernels_match_reference(T, k, E, H, I, off):
     (1000, 2, 4, 1024, 448, 2, "gelu_tanh_mul", True, False), # expert-parallel shard (foreign experts), biases, odd I (7 x 64)
     (257, 1, 16, 512, 256, 0, "silu_mul", False, True),       # Llama-4 style: top-1, affinity on the expert input
     (2048, 4, 16, 2048, 1344, 0, "silu_mul", False, False),   # DBRX TP8 shard shape (I = 10752 / 8) at reduced hidden size
+    (200, 4, 8, 512, 256, 0, "gpt_oss_glu", True, False),     # GPT-OSS: biased experts, clamped SwiGLU epilogue (callable with a kernel twin)
+    (3, 4, 8, 512, 256, 0, "gpt_oss_glu", True, False),       # ... at decode size (no moe_decode kernel for biased experts: grouped path)
 ])
 def test_moe_grouped_gemm_matches_reference(N, k, E, H, I, off, act, bias, scale_input):
     """Prefill MoE: device-side permutation + grouped tcgen05 GEMMs (csrc/moe_grouped.cu, gemm_tcgen05.cu grouped mode)."""
@@ -282,12 +323,17 @@ def test_moe_grouped_gemm_matches_reference(N, k, E, H, I, off, act, bias, scale
     if N >= 1000:
         idx[:, 0] = off          # a hot expert: many tiles of one expert, others nearly empty
     w = torch.rand(N, k, device=dev)
+    act_fn = None
+    if act == "gpt_oss_glu":
+        from neuronx_distributed_inference_b200.models.gpt_oss.modeling_gpt_oss import gpt_oss_glu
+        act, act_fn = "silu_mul", gpt_oss_glu
+        x = x * 4                                # reach the clamps
     before = ops.stats["moe_grouped"]
-    got = ops.moe_experts(x, wgu, wd, w, idx, act, off, gb, db, None, scale_input)
+    got = ops.moe_experts(x, wgu, wd, w, idx, act, off, gb, db, act_fn, scale_input)
     assert ops.stats["moe_grouped"] == before + 1
-    got2 = ops.moe_experts(x, wgu, wd, w, idx, act, off, gb, db, None, scale_input)
+    got2 = ops.moe_experts(x, wgu, wd, w, idx, act, off, gb, db, act_fn, scale_input)
     assert torch.equal(got, got2)                # row order inside an expert may differ run to run; the result may not
-    exp = ref.moe_experts(x, wgu, wd, w, idx, act, off, gb, db, None, scale_input)
+    exp = ref.moe_experts(x, wgu, wd, w, idx, act, off, gb, db, act_fn, scale_input)
     err = (got.float() - exp.float()).abs().max().item()
     assert err <= 0.02 * exp.float().abs().max().item() + 0.02, err
     # the same launch sequence replays under a CUDA graph with a different routing
@@ -295,15 +341,15 @@ def test_moe_grouped_gemm_matches_reference(N, k, E, H, I, off, act, bias, scale
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        ops.moe_experts(x_s, wgu, wd, w_s, idx_s, act, off, gb, db, None, scale_input)
+        ops.moe_experts(x_s, wgu, wd, w_s, idx_s, act, off, gb, db, act_fn, scale_input)
     torch.cuda.current_stream().wait_stream(s)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        out_s = ops.moe_experts(x_s, wgu, wd, w_s, idx_s, act, off, gb, db, None, scale_input)
+        out_s = ops.moe_experts(x_s, wgu, wd, w_s, idx_s, act, off, gb, db, act_fn, scale_input)
     idx2 = torch.rand(N, n_global, device=dev).topk(k, dim=-1).indices
     idx_s.copy_(idx2)
     g.replay()
-    exp2 = ref.moe_experts(x, wgu, wd, w, idx2, act, off, gb, db, None, scale_input)
+    exp2 = ref.moe_experts(x, wgu, wd, w, idx2, act, off, gb, db, act_fn, scale_input)
     err2 = (out_s.float() - exp2.float()).abs().max().item()
     assert err2 <= 0.02 * exp2.float().abs().max().item() + 0.02, err2
 
