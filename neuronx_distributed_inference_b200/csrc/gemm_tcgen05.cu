@@ -639,13 +639,38 @@ static void gemm_launch_impl(const void* a, int lda, const void* b, const void* 
   // (M = 256, N = 6144: 48 tiles of 256x128 took 48 us, 192 tiles of 128x64 ~30 us; cuBLAS 23.5 us)
   int TM = (M > GM_BM && M <= 2 * GM_BM) ? 2 : 1;
   int BN = (TM == 1 && M > 2 * GM_BM) ? 256 : 128;
-  if (M <= 2 * GM_BM) {
+  int model_split = 0;
+  if (M <= 4 * GM_BM) {
+    // Weight-dominated sizes (M <= 512): a CTA is bound by its shared-memory fill rate (~100 GB/s per SM), so a tile costs
+    // (TM*128 + BN) operand rows per k-block and the launch costs  waves x that  — pick the shape that minimises it (ties: the larger
+    // tile).  Measured (profiles/r2/skinny_gemm_sweep.txt): M = 256 qkv 51 -> 37 us with 128x128 instead of 128x64 tiles (192 tiles were
+    // two waves), o_proj best with 128x64 (one wave of 128 tiles).  Split-K only pays for very deep K with less than half the SMs
+    // busy (down: 84 -> 68 us with two k slices); everywhere else the partial round trip costs more than it gains.
     const int n_out_ = glu ? N / 2 : N;
-    auto n_tiles_of = [&](int tm, int bn) { return ((M + tm * GM_BM - 1) / (tm * GM_BM)) * ((n_out_ + (glu ? bn / 2 : bn) - 1) / (glu ? bn / 2 : bn)); };
-    if (TM == 2 && n_tiles_of(2, 128) < n_sms) TM = 1;
-    if (n_tiles_of(TM, 128) < n_sms) BN = 64;
+    const int cand[4][2] = {{2, 128}, {1, 256}, {1, 128}, {1, 64}};
+    long best_cost = -1;
+    for (int ci = 0; ci < 4; ++ci) {
+      const int tm = cand[ci][0], bn = cand[ci][1];
+      const int t_out = glu ? bn / 2 : bn;
+      const long tiles_ = (long)((M + tm * GM_BM - 1) / (tm * GM_BM)) * ((n_out_ + t_out - 1) / t_out);
+      const long cost = ((tiles_ + n_sms - 1) / n_sms) * (tm * GM_BM + bn);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; TM = tm; BN = bn; }
+    }
+    if (K >= 8192) {   // deep K: 128x128 tiles in two k slices when that still fits one wave
+      const long t128 = (long)((M + GM_BM - 1) / GM_BM) * ((n_out_ + (glu ? 64 : 128) - 1) / (glu ? 64 : 128));
+      if (2 * t128 <= n_sms && (GM_BM + 128) / 2 * 14 / 10 < best_cost) { TM = 1; BN = 128; model_split = 2; }
+    }
   }
   if (force_tm) TM = force_tm;
+  {
+    // tuning override: NXDI_B200_GEMM_BN = 64 | 128 | 256 (256 only with 128-row tiles; 64 only with 128-row tiles)
+    const char* e = getenv("NXDI_B200_GEMM_BN");
+    const int fbn = e ? atoi(e) : 0;
+    if (fbn == 64 || fbn == 128 || fbn == 256) {
+      BN = fbn;
+      if (BN != 128) TM = 1;
+    }
+  }
   if (tile_expert != nullptr) {   // grouped: one expert per 128-row tile
     if (M % GM_BM != 0) throw std::runtime_error("grouped gemm: the permuted row bound must be a multiple of 128");
     TM = 1;
@@ -682,7 +707,9 @@ static void gemm_launch_impl(const void* a, int lda, const void* b, const void* 
       if (cost < best - 1e-9) { best = cost; best_s = sgl; }
     }
   }
+  if (model_split > 0 && force_s <= 0 && !force_tm) best_s = model_split;
   p.splits = force_s > 0 ? std::min({force_s, 4, std::max(1, nkb / 2)}) : best_s;
+  if (force_s > 0 && (size_t)tiles * p.splits * tile_ws_bytes > gemm_ws_bytes()) p.splits = 1;
   if (rs != nullptr || tile_expert != nullptr) p.splits = 1;
   if ((size_t)tiles * p.splits * tile_ws_bytes > gemm_ws_bytes() || tiles > gemm_max_tickets()) p.splits = 1;
   p.ws = p.splits > 1 ? gemm_ws() : nullptr;
