@@ -35,7 +35,7 @@ def _to_dev(t, device, dtype=None, non_blocking=True):
         t = t.to(dtype)
     if t.device != device:
         if t.device.type == "cpu" and device.type == "cuda" and not t.is_pinned():
-            t = t.pin_memory()
+            t = t.contiguous().pin_memory()      # (expanded views — M-RoPE position ids — cannot be pinned in place)
         t = t.to(device, non_blocking=non_blocking)
     return t
 
