@@ -42,3 +42,16 @@ def test_symmetric_heap_nvls_collectives_and_fused_gemm(n):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"ok": true' in r.stdout
+
+
+@pytest.mark.parametrize("n", [2, 8])
+def test_fused_gemv_allreduce_kernel_bf16_and_8bit_weights(n):
+    """The one-kernel GEMV -> all-reduce -> +residual (LL protocol over peer memory) for bf16, fp8 and int8 weights: numerics vs
+    GEMM + NCCL all-reduce, bitwise equality across ranks, CUDA-graph replay with fresh tags (tests/mp/symm_worker.py)."""
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + n), os.path.join(ROOT, "tests", "mp", "symm_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "identical_across_ranks=False" not in r.stdout and "quantised torch.int8" in r.stdout
