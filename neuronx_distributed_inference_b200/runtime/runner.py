@@ -268,7 +268,14 @@ class SubModelRunner:
         kwargs = self._common_kwargs(kw)
         if self.use_prefill_graphs and not any(torch.is_tensor(v) for v in kwargs.values()) and not kwargs.get("has_prefix") \
                 and ids.shape[1] <= 2048:
-            return self._run_prefill_graph(ids, mask, pos, seq_ids, sampling_params, kwargs)
+            try:
+                return self._run_prefill_graph(ids, mask, pos, seq_ids, sampling_params, kwargs)
+            except RuntimeError as e:
+                # an op of this configuration is not capturable (same policy as the decode runner): eager context encoding from now on
+                logger.warning("%s: CUDA-graph capture of context encoding failed (%s); falling back to eager prefill", self.tag,
+                               str(e).split("\n")[0])
+                torch.cuda.synchronize(dev)
+                self.use_prefill_graphs = False
         with torch.no_grad():
             return self.model(_to_dev(ids, dev), _to_dev(mask, dev), _to_dev(pos, dev, torch.int32),
                               _to_dev(seq_ids, dev, torch.int32), _to_dev(sampling_params, dev, torch.float32),
