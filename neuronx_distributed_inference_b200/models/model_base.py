@@ -173,12 +173,12 @@ class NeuronBaseModel(nn.Module):
                       num_lines=lines, dtype=dtype, device=self.device_,
                       quant_config=nc.kv_quant_config if nc.kv_cache_quant else None)
             if nc.attention_dp_degree > 1:
-                # attention DP lives inside the KV-replication group (ranks that would otherwise hold identical KV)
-                from ..parallel.state import get_kv_shared_group
-                g = get_kv_shared_group()
-                if g.size != nc.attention_dp_degree:
-                    raise NotImplementedError(f"attention_dp_degree ({nc.attention_dp_degree}) must equal the KV replication "
-                                              f"factor tp/num_kv_heads ({g.size}) — see DESIGN.md §5")
+                # attention DP lives inside the KV-replication group (ranks that would otherwise hold identical KV); any other
+                # degree: a block of adjacent TP ranks, each keeping ALL the block's kv heads for its share of the batch rows
+                attn0 = self.layers[0].self_attn
+                g = attn0.dp_group
+                if getattr(attn0, "dp_general", False):
+                    kw["num_kv_heads"] = self.kv_heads_per_rank() * g.size
                 self.kv_mgr = DataParallelKVCacheManager(dp_rank=g.rank, dp_size=g.size, **kw)
             elif nc.rolling_sliding_window_cache and any(self._layer_windows()):
                 from ..modules.kvcache.gpt_oss_kv_cache_manager import HybridKVCacheManager

@@ -29,7 +29,8 @@ import torch.nn as nn
 
 from ... import ops
 from ...parallel import mappings
-from ...parallel.state import (Group, get_context_parallel_group, get_context_parallel_tp_group,
+from ...parallel.state import (Group, get_attention_dp_block_group, get_context_parallel_block_group,
+                              get_context_parallel_group, get_context_parallel_tp_group,
                               get_data_parallel_attention_group, get_kv_shared_group,
                               get_tensor_model_parallel_group)
 from ..gqa import GQA, GroupQueryAttention_O, GroupQueryAttention_QKV
@@ -137,9 +138,17 @@ class AttentionBase(nn.Module):
         rep = get_kv_shared_group()
         self.dp_group = rep if (nc.attention_dp_degree > 1 and rep.size == nc.attention_dp_degree) else None
         self.cp_group = rep if (nc.cp_degree > 1 and rep.size == nc.cp_degree) else None
+        # Any other degree that divides tp: a block of adjacent TP ranks whose members hold DIFFERENT kv heads (or a mix).  The
+        # group then also all-gathers its K/V heads (CP: per prefill; DP: the cache of a rank stores all the block's heads for ITS
+        # batch rows), so that any member can serve any head of the block — the reference's `cp_degree | tp_degree` meshes
+        # (attention_process_groups.py:81-110) without a second, differently sharded copy of the attention weights.
+        self.cp_general = self.dp_general = False
         if nc.cp_degree > 1 and self.cp_group is None:
-            raise NotImplementedError(f"cp_degree ({nc.cp_degree}) must equal the KV replication factor tp/num_kv_heads "
-                                      f"({rep.size}) — see DESIGN.md §5")
+            self.cp_group, self.cp_general = get_context_parallel_block_group(), True
+        if nc.attention_dp_degree > 1 and self.dp_group is None:
+            self.dp_group, self.dp_general = get_attention_dp_block_group(), True
+        if (self.cp_general or self.dp_general) and (nc.is_block_kv_layout or nc.flash_decoding_enabled):
+            raise NotImplementedError("general CP / attention-DP meshes with the paged cache or flash decoding")
 
     # ------------------------------------------------------------------------------------
     def _rope(self, meta: AttnMeta):
@@ -187,7 +196,7 @@ class AttentionBase(nn.Module):
         paged = meta.slot_mapping is not None
         if self.kv_group is not None:
             return self._forward_flash_decoding(qkv, meta, kv_mgr, cos, sin, residual, B, T)
-        if (self.dp_group is not None and not meta.is_prefill) or \
+        if (self.dp_group is not None and (not meta.is_prefill or self.dp_general)) or \
                 (self.cp_group is not None and meta.is_prefill and not meta.has_prefix and T % self.cp_group.size == 0):
             return self._forward_group_parallel(qkv, meta, kv_mgr, cos, sin, residual, B, T)
         k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
@@ -320,21 +329,42 @@ class AttentionBase(nn.Module):
         D, nq = self.head_dim, self.n_q
         q, k, v = self._split_norm_rope(qkv, B, T, cos, sin, meta)
         lines = kv_mgr.lines_for(meta.seq_ids)
-        kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)     # non-owned rows -> garbage line
+        ka = va = None
+        if self.dp_general:
+            # general attention DP: this rank's cache keeps ALL kv heads of its block for the batch rows it owns
+            ka = mappings.all_gather(k.contiguous(), 2, self.dp_group)
+            va = mappings.all_gather(v.contiguous(), 2, self.dp_group)
+            kv_mgr.update(self.layer_idx, ka, va, meta.seq_ids, meta.write_positions, lines)
+        else:
+            kv_mgr.update(self.layer_idx, k, v, meta.seq_ids, meta.write_positions, lines)     # non-owned rows -> garbage line
+
+        def gathered(t, g):
+            return None if t is None else mappings.all_gather(t.contiguous(), 0, g)
         if meta.is_prefill:
             g = self.cp_group
+            if g is None or meta.has_prefix or T % g.size != 0:
+                # (general attention DP without CP: the prefill itself is ordinary attention over the local heads)
+                right = self._arange_pos(meta)
+                o = ops.attention_prefill(q, k, v, self.scale, True, self.sliding_window, self.attention_chunk_size,
+                                          None if right else meta.key_valid, None if right else meta.position_ids, self.sinks, self.softcap)
+                return self.o_proj(o.reshape(B, T, nq * D), residual)
             n = T // g.size
             qa = mappings.all_gather(q.contiguous(), 2, g)[:, g.rank * n:(g.rank + 1) * n]       # [B, T/r, r*nq, D]
             qpos = meta.position_ids[:, g.rank * n:(g.rank + 1) * n]
-            o = ops.attention_prefill(qa.contiguous(), k, v, self.scale, True, self.sliding_window, self.attention_chunk_size,
-                                      meta.key_valid, qpos, self.sinks, self.softcap)
+            kk, vv = k, v
+            if self.cp_general:      # members hold different kv heads: gather them too (rank-major, like the q heads)
+                same = self.dp_general and self.dp_group is g
+                kk = ka if same else mappings.all_gather(k.contiguous(), 2, g)
+                vv = va if same else mappings.all_gather(v.contiguous(), 2, g)
+            o = ops.attention_prefill(qa.contiguous(), kk, vv, self.scale, True, self.sliding_window, self.attention_chunk_size,
+                                      meta.key_valid, qpos, gathered(self.sinks, g), self.softcap)
             o = mappings.all_gather(o.contiguous(), 1, g)                                          # [B, T, r*nq, D]
         else:
             g = self.dp_group
             k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)
             qa = mappings.all_gather(q.contiguous(), 2, g)
             o = ops.attention_decode(qa, k_cache, v_cache, lines, meta.position_ids, self.scale, self.sliding_window,
-                                     self.attention_chunk_size, None, None, self.softcap, seq_hint=meta.seq_hint)
+                                     self.attention_chunk_size, gathered(self.sinks, g), None, self.softcap, seq_hint=meta.seq_hint)
             owned = (lines < kv_mgr.num_lines).view(B, 1, 1, 1)
             o = torch.where(owned, o, torch.zeros_like(o))
             o = mappings.all_reduce(o.float(), g).to(q.dtype)

@@ -51,6 +51,8 @@ class _State:
     dp: Group = field(default_factory=lambda: Group([0]))
     dp_tp: Group = field(default_factory=lambda: Group([0]))
     kv_shared: Group = field(default_factory=lambda: Group([0]))  # flash-decoding KV group
+    cp_block: Group = field(default_factory=lambda: Group([0]))   # cp_degree CONTIGUOUS tp ranks (general context parallelism)
+    dp_block: Group = field(default_factory=lambda: Group([0]))   # attention_dp_degree contiguous tp ranks (general attention DP)
     replica: Group = field(default_factory=lambda: Group([0]))    # same shard in the other replicas of the TP group
     draft: Optional[Group] = None
     world: Group = field(default_factory=lambda: Group([0]))
@@ -152,6 +154,9 @@ def initialize_model_parallel(tensor_model_parallel_size: int = 1, pipeline_mode
         _, st.kv_shared = split(tp // kv_shared_size)
     else:
         st.kv_shared = Group([me])
+    # blocks of adjacent TP ranks for CP / attention DP when the degree is not the KV replication factor (attention_base.py)
+    st.cp_block = split(tp // context_parallel_size)[1] if context_parallel_size > 1 else Group([me])
+    st.dp_block = split(tp // attention_dp_size)[1] if attention_dp_size > 1 else Group([me])
     _S = st
     return st
 
@@ -224,6 +229,14 @@ def get_world_group() -> Group:
 
 def get_kv_shared_group() -> Group:
     return _S.kv_shared
+
+
+def get_context_parallel_block_group() -> Group:
+    return _S.cp_block
+
+
+def get_attention_dp_block_group() -> Group:
+    return _S.dp_block
 
 
 def get_speculative_draft_group() -> Group:

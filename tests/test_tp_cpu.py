@@ -118,3 +118,11 @@ def test_flux_dp2_context_and_cfg_parallel(i, mode):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
+
+
+def test_llama_general_cp_and_attention_dp_meshes_match_hf(tiny_ckpt):
+    # degrees that are NOT the KV replication factor: TP2 (one kv head per rank, no replication) with cp = dp = 2, and TP4
+    # (replication factor 2) with cp = 4 — blocks of adjacent ranks that gather their K/V heads
+    _run(2, tiny_ckpt, 29561, ATTENTION_DP="2", CP="2")
+    _run(4, tiny_ckpt, 29562, ATTENTION_DP="2", CP="4")
+    _run(2, tiny_ckpt, 29563, ATTENTION_DP="2")            # general DP alone: the prefill is ordinary attention, the cache write gathers heads
