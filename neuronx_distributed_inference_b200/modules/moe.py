@@ -8,8 +8,9 @@ Parallel layout on B200 (one NVSwitch domain, activations replicated across the 
     ``moe_ep * moe_tp == tp_degree``;
   * every rank evaluates only its (expert, I-slice) shard on the replicated tokens and contributes a partial
     ``[N, H]``; the combine is one all-reduce over the TP group — on the decode path it is the fused
-    GEMV->all-reduce epilogue.  This is the reference's ``ep_dispatch_cc_option="AR_AG"`` family; a token all-to-all
-    is only required when tokens are *sharded* (attention-DP), see ``dispatch_tokens`` below.
+    GEMV->all-reduce epilogue, at prefill sizes the in-switch all-reduce.  This is the reference's
+    ``ep_dispatch_cc_option="AR_AG"`` family; neither the reference nor this engine shards the TOKENS across expert ranks, so
+    there is no token all-to-all.  Routed experts run through ``ops.moe_experts`` (device-side permutation + grouped tcgen05 GEMMs).
 Weights are stored K-major: ``gate_up_proj [E_local, 2*I_local, H]`` ([gate; up] rows) and ``down_proj
 [E_local, H, I_local]`` (the reference keeps ``[E,H,2I]`` / ``[E,I,H]``; conversion happens at checkpoint load).
 """
@@ -169,29 +170,6 @@ class SharedExperts(nn.Module):
 
     def forward(self, x2, reduce: bool = False):
         return self.down_proj(self.gate_up_proj(x2, act=self.act))
-
-
-def dispatch_tokens(x2: torch.Tensor, topk_i: torch.Tensor, num_experts: int, ep_group: Group):
-    """Expert all-to-all for *sharded* tokens (attention data-parallel decode / sequence-parallel prefill): every rank
-    sends each token to the ranks owning its experts and receives the tokens routed to its own experts.
-    NCCL path (baseline); the fused P2P dispatch/combine kernel replaces it on the decode path when available."""
-    ep = ep_group.size
-    if ep == 1:
-        return x2, topk_i, None
-    per = num_experts // ep
-    dest = (topk_i // per)                                   # [N,k] destination ep-rank of every (token, slot)
-    N, k = topk_i.shape
-    # pad-to-max dense exchange: [ep, N*k, H] with a validity mask (static shapes: graph capturable)
-    send = x2.new_zeros(ep, N * k, x2.shape[-1])
-    valid = torch.zeros(ep, N * k, dtype=torch.bool, device=x2.device)
-    flat_dest = dest.reshape(-1)
-    ar = torch.arange(N * k, device=x2.device)
-    send[flat_dest, ar] = x2.repeat_interleave(k, 0)
-    valid[flat_dest, ar] = True
-    recv = mappings.all_to_all(send, 0, 0, ep_group)
-    rvalid = mappings.all_to_all(valid.to(torch.uint8), 0, 0, ep_group).bool()
-    ridx = mappings.all_to_all(topk_i.reshape(1, -1).expand(ep, -1).contiguous(), 0, 0, ep_group)
-    return recv, ridx, rvalid
 
 
 def initialize_moe_module(config, device=None, hidden_act: Optional[str] = None, shared: bool = False,
