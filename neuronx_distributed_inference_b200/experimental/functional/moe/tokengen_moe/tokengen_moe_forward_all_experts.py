@@ -1,0 +1,2 @@
+"""reference experimental/functional/moe/tokengen_moe/tokengen_moe_forward_all_experts.py:10."""
+from ... import tokengen_moe_megakernel_forward_all_experts  # noqa: F401
