@@ -375,25 +375,35 @@ def main():
     tok_s = args.batch * 1e3 / m["ms_per_step"]
     e2e_tok_s = args.batch * 1e3 / m["e2e_ms_per_step"]
     ci = None
-    if not args.skip_ci and args.layers == 32:
-        del app
-        torch.cuda.empty_cache()
-        pstate.get_tensor_model_parallel_group().symm = None
-        # the published 306 ms / 1665 tok/s were measured with output_logits=True: that is the headline
-        # like-for-like block; the logits-off variant is reported next to it
-        app4 = build_app(LLAMA31_8B_CI4, args.gpus, 2, 256, 128, async_mode=False, output_logits=True)
-        ci = ci_harness(app4, 2, 128, 256, output_logits=True)
-        del app4
-        torch.cuda.empty_cache()
-        pstate.get_tensor_model_parallel_group().symm = None
-        app4 = build_app(LLAMA31_8B_CI4, args.gpus, 2, 256, 128, async_mode=False, output_logits=False)
-        ci["logits_off"] = {k: v for k, v in ci_harness(app4, 2, 128, 256, output_logits=False).items()
-                            if k in ("e2e_p50_ms", "throughput_tok_s")}
+    app4 = None
     weights_gb = None
     try:
-        weights_gb = sum(p.numel() * p.element_size() for p in (app4 if ci else app).model.parameters()) / 1e9
+        weights_gb = sum(p.numel() * p.element_size() for p in app.model.parameters()) / 1e9
     except Exception:
         pass
+    if not args.skip_ci and args.layers == 32 and args.gpus > 1:
+        # the like-for-like reproduction of the reference's CI configuration is a ONE-GPU block (the reference's number is a fixed
+        # TP=32 Trn1 figure, not a scaling curve); a failure of a secondary block on one rank must not be able to wedge the job
+        ci = {"skipped": "reported by the 1-GPU run only"}
+    elif not args.skip_ci and args.layers == 32:
+        # The secondary block must never cost the headline line: any failure in it is reported inside the JSON instead.
+        try:
+            del app
+            torch.cuda.empty_cache()
+            tpg = pstate.get_tensor_model_parallel_group()
+            tpg.symm = None
+            # the published 306 ms / 1665 tok/s were measured with output_logits=True: that is the headline
+            # like-for-like block; the logits-off variant is reported next to it
+            app4 = build_app(LLAMA31_8B_CI4, args.gpus, 2, 256, 128, async_mode=False, output_logits=True)
+            ci = ci_harness(app4, 2, 128, 256, output_logits=True)
+            del app4
+            torch.cuda.empty_cache()
+            tpg.symm = None
+            app4 = build_app(LLAMA31_8B_CI4, args.gpus, 2, 256, 128, async_mode=False, output_logits=False)
+            ci["logits_off"] = {k: v for k, v in ci_harness(app4, 2, 128, 256, output_logits=False).items()
+                                if k in ("e2e_p50_ms", "throughput_tok_s")}
+        except Exception as e:      # noqa: BLE001
+            ci = dict(ci or {}, error=f"{type(e).__name__}: {str(e)[:200]}")
     out = {
         "metric": "llama3.1-8b_decode_tokens_per_sec" if args.shard_shapes == 1 else
                   f"DIAGNOSTIC_tp{args.shard_shapes}_rank_shapes_no_collectives_tokens_per_sec", "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus,
