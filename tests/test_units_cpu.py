@@ -429,3 +429,51 @@ def test_zero_padded_heads_compute_the_same_attention(D, Dp, split):
     y1 = run(_pad_heads(wqkv, D, Dp, 0, split), _pad_heads(wo, D, Dp, 1, split), Dp,
              F.pad(ang.cos(), (0, (Dp - D) // 2), value=1.0), F.pad(ang.sin(), (0, (Dp - D) // 2)))
     assert (y0 - y1).abs().max().item() < 1e-5 * y0.abs().max().item()      # (the reference ops evaluate softmax in fp32)
+
+
+def test_module_test_template_tree_mlp_from_model(tmp_path):
+    """reference module_test/{base_template,module_from_model_template}: the four-step adapters and the pairwise orchestrator — the MLP of
+    decoder layer 1 cut out of a Hugging Face Llama and out of the engine application built from the same checkpoint."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from neuronx_distributed_inference_b200.config import NeuronConfig, load_pretrained_config
+    from neuronx_distributed_inference_b200.models.llama.modeling_llama import LlamaInferenceConfig, NeuronLlamaForCausalLM
+    from neuronx_distributed_inference_b200.module_test.base_template import ModuleAdapterBase, OrchestratorBase
+    from neuronx_distributed_inference_b200.module_test.module_from_model_template import (
+        MFMHFAdapter, MFMNxDICPUSingleRankAdapter, MFMOrchestratorBase, MFMOrchestratorConfig, build_prefixes_map,
+        extract_subweights_by_prefixes)
+    from neuronx_distributed_inference_b200.utils.testing import save_random_hf_checkpoint
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=160)
+    ckpt = save_random_hf_checkpoint(cfg, str(tmp_path / "ck"), seed=1)
+    assert build_prefixes_map(None, ["mlp"], 1, "model.layers") == {"mlp": "model.layers.1"}
+    assert build_prefixes_map(["model", "model.layers"], ["rotary_emb", "self_attn"], 0, "x") == {"rotary_emb": "model", "self_attn": "model.layers.0"}
+    sd = {"model.layers.1.mlp.up.weight": 1, "model.layers.1.mlp_other.w": 2, "model.layers.0.mlp.up.weight": 3}
+    assert extract_subweights_by_prefixes({"mlp": "model.layers.1"}, sd) == {"mlp.up.weight": 1}
+
+    def hf_forward(self, hidden_states):
+        return self.mlp(hidden_states)
+
+    def engine_forward(self, hidden_states):
+        return self.mlp(hidden_states)
+
+    def app_factory(path, device):
+        nc = NeuronConfig(batch_size=2, seq_len=32, max_context_length=16, torch_dtype="float32", on_cpu=(device == "cpu"))
+        app = NeuronLlamaForCausalLM(path, LlamaInferenceConfig(nc, load_config=load_pretrained_config(path)))
+        return app.load(None, skip_warmup=True)
+    conf = MFMOrchestratorConfig(batch_size=2, torch_dtype=torch.float32, hf_weight_ckpt_path=ckpt, layer_id=1, atol=1e-4, rtol=1e-4,
+                                 prep_input_config=MFMOrchestratorConfig.PrepInputConfig(seq_len=3, hf_hidden_size=64))
+    errs = MFMOrchestratorBase([MFMHFAdapter(hf_forward, LlamaForCausalLM, ["mlp"], layer_id=1),
+                                MFMNxDICPUSingleRankAdapter(engine_forward, app_factory, ["mlp"], layer_id=1)], conf).run_validation()
+    assert len(errs) == 1 and max(errs.values()) < 1e-4
+
+    class Wrong(ModuleAdapterBase):          # a deliberately different module must be caught by the pairwise comparison
+        def define_module_cls(self):
+            class PassThrough(torch.nn.Module):
+                def forward(self, hidden_states):
+                    return hidden_states
+            self.module_cls = PassThrough
+    with pytest.raises(AssertionError, match="mismatch"):
+        OrchestratorBase([MFMHFAdapter(hf_forward, LlamaForCausalLM, ["mlp"], layer_id=1), Wrong()], conf).run_validation()
+    kv = OrchestratorBase([], MFMOrchestratorConfig(batch_size=2, torch_dtype=torch.float32, prep_input_config=conf.prep_input_config,
+                                                    prep_kv_cache_config=MFMOrchestratorConfig.PrepKVCacheConfig(ctx_len=5, num_head=2, hf_head_hidden_size=16))
+                          ).prepare_kv_cache_hf_format()
+    assert kv[0].shape == (2, 2, 5, 16) and not torch.equal(kv[0], kv[1])
