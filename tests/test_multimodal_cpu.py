@@ -56,6 +56,10 @@ def test_qwen2_vl_matches_hf(tmp_path):
         vis = vis.pooler_output if hasattr(vis, "pooler_output") else vis
     got_vis = app.encode_images(pix, image_grid_thw=grid)
     assert _rel(got_vis, vis) < 1e-4 * DEVICE["tol"]
+    if DEVICE["on_cpu"]:      # the reference's stand-alone image-encoding application name (wraps the same tower)
+        from neuronx_distributed_inference_b200.models.qwen2_vl.modeling_qwen2_vl_vision import NeuronQwen2VLForImageEncoding
+        enc = NeuronQwen2VLForImageEncoding(ckpt, app.config).load(None, skip_warmup=True)
+        assert _rel(enc(pix, image_grid_thw=grid), vis) < 1e-4
     out = app(ids, attention_mask=mask, pixel_values=pix, image_grid_thw=grid)
     last = mask.sum(-1) - 1
     exp_last = exp.logits[torch.arange(2), last]

@@ -477,3 +477,45 @@ def test_module_test_template_tree_mlp_from_model(tmp_path):
                                                     prep_kv_cache_config=MFMOrchestratorConfig.PrepKVCacheConfig(ctx_len=5, num_head=2, hf_head_hidden_size=16))
                           ).prepare_kv_cache_hf_format()
     assert kv[0].shape == (2, 2, 5, 16) and not torch.equal(kv[0], kv[1])
+
+
+def test_reference_model_import_paths_and_helpers():
+    """The reference's per-family module paths that this tree folds into one file each resolve, and their small helpers behave."""
+    import importlib
+    from types import SimpleNamespace
+    base = "neuronx_distributed_inference_b200.models."
+    for mod, names in {
+        "qwen2_vl.modeling_qwen2_vl_text": ["NeuronQwen2VLTextModel", "NeuronQwen2VLTextForCausalLM"],
+        "qwen2_vl.modeling_qwen2_vl_vision": ["NeuronQwen2VisionModel", "NeuronQwen2VLForImageEncoding", "PatchMerger"],
+        "qwen3_vl.modeling_qwen3_vl_text": ["NeuronQwen3VLTextModel", "NeuronQwen3VLTextForCausalLM"],
+        "qwen3_vl.modeling_qwen3_vl_vision": ["NeuronQwen3VLVisionModel", "NeuronQwen3VLForImageEncoding"],
+        "pixtral.modeling_pixtral_vision": ["NeuronPixtralVisionModel", "NeuronPixtralForImageEncoding"],
+        "mllama.modeling_mllama_vision": ["NeuronMllamaVisionModel"], "mllama.aspect_ratio_utils": ["get_all_supported_aspect_ratios"],
+        "llama4.utils.input_processor": ["prepare_generation_inputs_hf"], "whisper.utils.state_dict": ["convert_hf_state_dict_to_neuron"],
+        "gpt_oss.hf_configuration": ["GptOssConfig"], "deepseek.rope_util": ["DeepseekV3YarnRotaryEmbedding", "yarn_get_mscale"],
+    }.items():
+        m = importlib.import_module(base + mod)
+        assert all(hasattr(m, n) for n in names), (mod, names)
+    from neuronx_distributed_inference_b200.models.llama4.utils import encoder_utils as eu
+    from neuronx_distributed_inference_b200.models.llama4.utils.layer_utils import is_after_nope_layer, is_before_nope_layer
+    from neuronx_distributed_inference_b200.models.qwen2_vl.utils.vision_utils import calculate_max_grid_size, calculate_pixels_per_image
+    from neuronx_distributed_inference_b200.models.qwen3_vl.utils.slicing import slice_by_image_hw
+    from neuronx_distributed_inference_b200.models.whisper.utils.config import get_dims_from_config
+    cfg = SimpleNamespace(no_rope_layers=[1, 1, 1, 0, 1])
+    assert [is_before_nope_layer(cfg, i) for i in range(5)] == [False, False, True, False, False]
+    assert [is_after_nope_layer(cfg, i) for i in range(5)] == [True, False, False, False, True]
+    px, n = eu.pad_image_tensor(torch.ones(3, 2, 4, 4), 8)
+    assert px.shape == (8, 2, 4, 4) and n == 3 and float(px[3:].abs().sum()) == 0 and eu.depad_output(px, n).shape[0] == 3
+    mask = torch.tensor([[0, 1, 1, 0], [1, 0, 0, 0]], dtype=torch.bool)
+    pos = eu.generate_positions_from_mask(mask)
+    assert pos.tolist() == [1, 2, 4] and eu.pad_positions(pos, 5, 8).tolist() == [1, 2, 4, 8, 8]
+    h = torch.zeros(2, 4, 3)
+    out = eu.scatter_by_index_put(h, torch.arange(15.).view(5, 3), eu.pad_positions(pos, 5, 8))
+    assert out[0, 1].tolist() == [0., 1., 2.] and out[1, 0].tolist() == [6., 7., 8.] and float(out[0, 0].abs().sum()) == 0
+    assert eu.generate_llama4_vision_encoder_buckets(1, 16) == [1, 2, 4, 8, 16]
+    assert calculate_pixels_per_image(640, 320) == (308 // 14) * (644 // 14) and calculate_max_grid_size(640, 320) == 46
+    parts = slice_by_image_hw(torch.arange(24).view(24, 1), torch.tensor([[1, 2, 4], [1, 4, 4]]))
+    assert [p.shape[0] for p in parts] == [8, 16]
+    d = get_dims_from_config(SimpleNamespace(num_mel_bins=80, max_source_positions=1500, d_model=384, encoder_attention_heads=6, encoder_layers=4,
+                                             vocab_size=51865, max_target_positions=448, decoder_attention_heads=6, decoder_layers=4))
+    assert d.n_audio_state == 384 and d.n_text_layer == 4
