@@ -67,7 +67,7 @@ IGNORED_ON_B200 = {
     "attn_block_tkg_nki_kernel_cascaded_attention": False,
     "attn_block_tkg_nki_kernel_use_online_softmax": True,
     "attn_block_tkg_nki_kernel_disable_gpsimd_sb2sb": False,
-    "attn_block_cte_nki_kernel_enabled": False, "strided_context_parallel_kernel_enabled": False,
+    "attn_block_cte_nki_kernel_enabled": False,
     "moe_fused_nki_kernel_enabled": None, "router_topk_nki_kernel_enabled": None,
     "expert_mlp_nki_kernel_enabled": None, "shared_mlp_nki_kernel_enabled": None,
     "eagle_rolling_buffer_kernel_enabled": False, "disable_kv_cache_tiling": False,
@@ -303,6 +303,8 @@ class NeuronConfig:
         # ---- parallelism (config.py:361-391)
         self.tp_degree = g("tp_degree", 1)
         self.cp_degree = g("cp_degree", 1)
+        # context parallelism splits the query sequence in contiguous slices; strided = positions j, j + cp, ... (causal load balance)
+        self.strided_context_parallel_kernel_enabled = g("strided_context_parallel_kernel_enabled", False)
         self.mlp_cp_degree = g("mlp_cp_degree", 1)
         self.attention_dp_degree = g("attention_dp_degree", 1)
         self.pp_degree = g("pp_degree", 1)

@@ -349,8 +349,12 @@ class AttentionBase(nn.Module):
                                           None if right else meta.key_valid, None if right else meta.position_ids, self.sinks, self.softcap)
                 return self.o_proj(o.reshape(B, T, nq * D), residual)
             n = T // g.size
-            qa = mappings.all_gather(q.contiguous(), 2, g)[:, g.rank * n:(g.rank + 1) * n]       # [B, T/r, r*nq, D]
-            qpos = meta.position_ids[:, g.rank * n:(g.rank + 1) * n]
+            # contiguous slices by default; strided (rank j takes positions j, j + r, ...) balances the causal work between the
+            # ranks — the reference's strided_context_parallel_kernel_enabled (attention_base.py:546-561)
+            strided = bool(getattr(self.neuron_config, "strided_context_parallel_kernel_enabled", False))
+            sl = slice(g.rank, None, g.size) if strided else slice(g.rank * n, (g.rank + 1) * n)
+            qa = mappings.all_gather(q.contiguous(), 2, g)[:, sl]                                 # [B, T/r, r*nq, D]
+            qpos = meta.position_ids[:, sl]
             kk, vv = k, v
             if self.cp_general:      # members hold different kv heads: gather them too (rank-major, like the q heads)
                 same = self.dp_general and self.dp_group is g
@@ -359,6 +363,8 @@ class AttentionBase(nn.Module):
             o = ops.attention_prefill(qa.contiguous(), kk, vv, self.scale, True, self.sliding_window, self.attention_chunk_size,
                                       meta.key_valid, qpos, gathered(self.sinks, g), self.softcap)
             o = mappings.all_gather(o.contiguous(), 1, g)                                          # [B, T, r*nq, D]
+            if strided:      # rank-major [r][T/r] -> interleaved sequence order
+                o = o.view(B, g.size, n, o.shape[2], D).transpose(1, 2).reshape(B, T, o.shape[2], D)
         else:
             g = self.dp_group
             k_cache, v_cache = kv_mgr.get_kv_by_layer_id(self.layer_idx)

@@ -51,6 +51,7 @@ def run_one(ckpt, dev, dtype, model_type):
                       sequence_parallel_enabled=os.environ.get("SEQUENCE_PARALLEL", "0") == "1",
                       rolling_sliding_window_cache=os.environ.get("ROLLING_SWA", "0") == "1",
                       attention_dp_degree=int(os.environ.get("ATTENTION_DP", "1")), cp_degree=int(os.environ.get("CP", "1")),
+                      strided_context_parallel_kernel_enabled=os.environ.get("STRIDED_CP", "0") == "1",
                       is_continuous_batching=int(os.environ.get("ATTENTION_DP", "1")) > 1)
     cfg = app_cls.get_config_cls()(nc, load_config=load_pretrained_config(ckpt))
     app = app_cls(ckpt, cfg)

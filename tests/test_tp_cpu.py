@@ -126,3 +126,4 @@ def test_llama_general_cp_and_attention_dp_meshes_match_hf(tiny_ckpt):
     _run(2, tiny_ckpt, 29561, ATTENTION_DP="2", CP="2")
     _run(4, tiny_ckpt, 29562, ATTENTION_DP="2", CP="4")
     _run(2, tiny_ckpt, 29563, ATTENTION_DP="2")            # general DP alone: the prefill is ordinary attention, the cache write gathers heads
+    _run(2, tiny_ckpt, 29564, CP="2", STRIDED_CP="1")      # strided sequence split (causal load balance)
